@@ -1,0 +1,194 @@
+/*
+ * fiksi_b200 — C ABI of the B200-native Fiksi numeric solve path.
+ *
+ * This header is the drop-in boundary.  In the reference the seam is a crate-private Rust generic,
+ *     pub(crate) fn levenberg_marquardt<P: Problem>(problem: &mut P, variables: &mut [f64])
+ *         (fiksi/src/solve/lm.rs:21, trait Problem at fiksi/src/solve/mod.rs:29-49),
+ * called from fiksi/src/assemble/mod.rs:150 with a `Subsystem` built at assemble/mod.rs:132-146.
+ * A per-row callback cannot cross to a GPU, so the boundary moves up to the data `Subsystem::new`
+ * receives: the flattened problem below.  Everything is plain pointers and sizes; all pointers are
+ * HOST memory owned by the caller unless a function says "device".  No function aborts: each
+ * returns FK_OK (0) or a negative fk_status and leaves a message for fk_last_error().
+ *
+ * There is no CPU fallback: every solve entry point fails with FK_ERR_NO_DEVICE / FK_ERR_CUDA when
+ * no sm_100a device is usable.
+ */
+#ifndef FIKSI_B200_H
+#define FIKSI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FK_API __attribute__((visibility("default")))
+
+typedef enum fk_status {
+    FK_OK = 0,
+    FK_ERR_INVALID = -1,    /* null pointer, index out of range, unknown kind */
+    FK_ERR_NO_DEVICE = -2,  /* no CUDA device / wrong architecture */
+    FK_ERR_CUDA = -3,       /* CUDA runtime failure (message in fk_last_error) */
+    FK_ERR_OOM = -4,        /* host or device allocation failed */
+    FK_ERR_TOO_LARGE = -5,  /* problem does not fit the selected path */
+    FK_ERR_INTERNAL = -6
+} fk_status;
+
+/* Expression kinds in the order of `enum Expression`, fiksi/src/constraints/expressions.rs:28-40. */
+typedef enum fk_kind {
+    FK_VARIABLE_VARIABLE_EQUALITY = 0,      /* idx: v1, v2                     slots 2 */
+    FK_POINT_POINT_DISTANCE = 1,            /* idx: p1, p2          param dist  slots 4 */
+    FK_POINT_POINT_POINT_ANGLE = 2,         /* idx: p1, p2, p3      param angle slots 6 */
+    FK_POINT_LINE_INCIDENCE = 3,            /* idx: p, l1, l2                  slots 6 */
+    FK_POINT_LINE_DISTANCE = 4,             /* idx: p, l1, l2       param dist  slots 6 */
+    FK_POINT_CIRCLE_INCIDENCE = 5,          /* idx: p, center, radius_var      slots 5 */
+    FK_SEGMENT_SEGMENT_LENGTH_EQUALITY = 6, /* idx: s1p1, s1p2, s2p1, s2p2     slots 8 */
+    FK_LINE_LINE_ANGLE = 7,                 /* idx: l1p1, l1p2, l2p1, l2p2 param angle  8 */
+    FK_LINE_LINE_PARALLELISM = 8,           /* same idx                        slots 8 */
+    FK_LINE_LINE_PERPENDICULARITY = 9,      /* same idx                        slots 8 */
+    FK_LINE_CIRCLE_TANGENCY = 10,           /* idx: l1, l2, center, radius_var slots 7 */
+    FK_NUM_KINDS = 11
+} fk_kind;
+
+/*
+ * The flattened problem == the arguments of `Subsystem::new` (fiksi/src/assemble/mod.rs:132-146):
+ *   vars      system.variables_transformed: scaled, free ones already perturbed; fixed variables
+ *             are read from here (fiksi/src/variable_map.rs:57-72)
+ *   kind/idx/param   system.expressions_transformed as SoA; idx holds the base indices exactly as
+ *             stored in the Expression structs (a point index p expands to slots p, p+1,
+ *             expressions.rs:48-182); param is the scaled distance or the angle, 0 if none
+ *   free_vars ascending global variable indices == IndexSet order (fiksi/src/subsystem.rs:22,35)
+ *   rows      expression ids of this problem in row order (assemble/mod.rs:136-145)
+ */
+typedef struct fk_problem {
+    uint32_t n_vars;
+    const double* vars;
+    uint32_t n_expr;
+    const uint8_t* kind;   /* [n_expr] */
+    const uint32_t* idx;   /* [n_expr][4] */
+    const double* param;   /* [n_expr] */
+    uint32_t n_free;
+    const uint32_t* free_vars; /* [n_free] */
+    uint32_t n_rows;
+    const uint32_t* rows;  /* [n_rows] */
+} fk_problem;
+
+/* Exit reasons == the four exits of fiksi/src/solve/lm.rs plus the guard for its unbounded loop. */
+typedef enum fk_exit {
+    FK_EXIT_CONVERGED_RESIDUAL = 0, /* sum r^2 < 1e-8                       lm.rs:110-112 */
+    FK_EXIT_SMALL_STEP = 1,         /* sum delta^2 < 1e-12                  lm.rs:139-142 */
+    FK_EXIT_STALLED = 2,            /* relative decrease <= 1e-6            lm.rs:164-168 */
+    FK_EXIT_MAX_OUTER = 3,          /* 100 outer iterations                 lm.rs:109     */
+    FK_EXIT_LAMBDA_OVERFLOW = 4     /* lambda reached +inf: the reference would spin forever */
+} fk_exit;
+
+/* New output (the reference returns `()`, fiksi/src/lib.rs:464-466). 40 bytes. */
+typedef struct fk_report {
+    uint32_t exit_reason;    /* fk_exit */
+    uint32_t outer_iters;    /* outer iterations that entered the damping loop */
+    uint32_t factorizations; /* damping-loop iterations (one factor + solve each) */
+    uint32_t accepted;       /* accepted steps */
+    double ssr;              /* sum of squared residuals at the returned variables (scaled units) */
+    double lambda;           /* final damping factor */
+    uint64_t trace_hash;     /* h = 3h + code + 1 per decision; code 0 unsolved, 1 accept, 2 reject */
+} fk_report;
+
+/* ---- library / device ------------------------------------------------------------------- */
+FK_API int fk_version(void);
+FK_API const char* fk_last_error(void);          /* thread-local, never NULL */
+FK_API int fk_device_count(void);                /* usable CUDA devices, 0 if none */
+
+/* ---- symbolic analysis, computed once per topology --------------------------------------- */
+/* A topology is a problem without its numbers: kinds, indices, free set and row list.  Creating
+ * it runs the host symbolic pipeline that replaces, per LM call in the reference,
+ *   SparseColMat::from_triplet_mat   solvi/src/sparse_col_mat.rs:690-737   (augmented CSC pattern)
+ *   colamd_rs::colamd                colamd_rs/src/colamd.rs:354-494       (column permutation)
+ *   elimination_tree / post_order / CholeskyCounts / CholeskyStructure
+ *                                    solvi/src/decomposition/sparse/cholesky.rs:31-595
+ * `vars` and `param` of the problem are ignored. */
+typedef struct fk_topology fk_topology;
+
+typedef struct fk_topology_info {
+    uint32_t n_vars, n_expr, n_free, n_rows;
+    uint32_t jac_nnz;      /* structural entries of J (duplicates merged), without damping rows */
+    uint32_t aug_nnz;      /* jac_nnz + n_free */
+    uint32_t r_nnz;        /* entries of R = L^T including the diagonal */
+    uint32_t etree_height; /* longest root-to-leaf path, in columns */
+    uint32_t path;         /* 0 tile-per-sketch (shared memory), 1 CTA-per-sketch, 2 global sparse */
+    uint32_t tile;         /* lanes per sketch on path 0/1 */
+    uint32_t smem_bytes;   /* shared memory per sketch on path 0/1 */
+    uint32_t reserved;
+    uint64_t chol_flops;   /* sum over columns of colcount^2: flops of one sparse factorisation */
+} fk_topology_info;
+
+FK_API int fk_topology_create(const fk_problem* problem, fk_topology** out);
+FK_API void fk_topology_destroy(fk_topology* topo);
+FK_API int fk_topology_info_get(const fk_topology* topo, fk_topology_info* info);
+
+/* Parity probes.  Each output may be NULL.  Sizes: aug_colptr[n_free+1], aug_rowidx[aug_nnz],
+ * colamd_perm[n_free], etree_parent[n_free] (-1 == root; of the permuted matrix), r_colptr[n_free+1],
+ * r_rowidx[r_nnz] (pattern of R, per column ascending rows, diagonal last — identical to
+ * SymbolicQr::r_structure, solvi/src/decomposition/sparse/qr.rs:80-82). */
+FK_API int fk_topology_symbolic(const fk_topology* topo, uint32_t* aug_colptr, uint32_t* aug_rowidx,
+                                int32_t* colamd_perm, int32_t* etree_parent, uint32_t* r_colptr,
+                                uint32_t* r_rowidx);
+/* Convenience: create + probe + destroy. */
+FK_API int fk_symbolic(const fk_problem* problem, uint32_t* aug_colptr, uint32_t* aug_rowidx,
+                       int32_t* colamd_perm, int32_t* etree_parent, uint32_t* r_colptr,
+                       uint32_t* r_rowidx);
+
+/* ---- Levenberg–Marquardt ----------------------------------------------------------------- */
+/* == levenberg_marquardt(problem, variables), fiksi/src/solve/lm.rs:21.  free_values in/out,
+ * length n_free.  Picks the batched kernel (n = 1) or the large sparse path by size. */
+FK_API int fk_lm_solve(const fk_problem* problem, double* free_values, fk_report* report);
+
+/* n independent problems (one per sketch or connected component).  Problems with identical
+ * topology are grouped and solved by one batched launch per group and device; contiguous ranges
+ * of each group go to the n_gpus devices (0 == all visible), no inter-GPU traffic. */
+FK_API int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems,
+                             double* const* free_values, fk_report* reports, int n_gpus);
+
+/* Uniform batch: n sketches sharing one topology.  vars[n][n_vars], param[n][n_expr] (row-major,
+ * one sketch after another), free_out[n][n_free], reports[n].  This is the throughput entry
+ * point for configs 2, 4 and 5. */
+FK_API int fk_batch_solve(const fk_topology* topo, uint32_t n, const double* vars,
+                          const double* param, double* free_out, fk_report* reports, int n_gpus);
+
+/* Device-resident batch plan (one device; used by bench.py and by fk_batch_solve internally). */
+typedef struct fk_batch_plan fk_batch_plan;
+FK_API int fk_batch_plan_create(const fk_topology* topo, uint32_t capacity, int device,
+                                fk_batch_plan** out);
+FK_API void fk_batch_plan_destroy(fk_batch_plan* plan);
+/* Async H2D of n sketches from (ideally pinned) host memory on `stream` (cudaStream_t, may be 0). */
+FK_API int fk_batch_plan_upload(fk_batch_plan* plan, uint32_t n, const double* vars,
+                                const double* param, void* stream);
+/* Launch the LM kernel over the n resident sketches.  Inputs are not modified, so the call can be
+ * repeated on the same resident data. */
+FK_API int fk_batch_plan_run(fk_batch_plan* plan, void* stream);
+/* Async D2H of results of the last run. */
+FK_API int fk_batch_plan_download(fk_batch_plan* plan, double* free_out, fk_report* reports,
+                                  void* stream);
+/* Device pointers of the resident buffers (any may be NULL): vars, param, free_out, reports. */
+FK_API int fk_batch_plan_device_ptrs(fk_batch_plan* plan, void** vars, void** param,
+                                     void** free_out, void** reports);
+/* Number of kernel launches issued by this plan so far / name of the LM kernel. */
+FK_API uint64_t fk_batch_plan_launches(const fk_batch_plan* plan);
+
+/* Pinned host memory helpers (so that callers without a CUDA binding can stage inputs). */
+FK_API void* fk_host_alloc(size_t bytes);
+FK_API void fk_host_free(void* p);
+
+/* ---- residual / Jacobian evaluation kernels on their own (assembly GB/s metric) ----------- */
+/* Evaluates all rows of n sketches of a topology once: residuals out_r[n][n_rows] and Jacobian
+ * values scattered into the precomputed CSC pattern out_j[n][jac_nnz] (device-resident plan
+ * buffers).  == Subsystem::calculate_residuals_and_sparse_jacobian, fiksi/src/subsystem.rs:126-166
+ * followed by SparseColMat::from_triplet_mat.  mode 0: residuals + Jacobian (K1); mode 1:
+ * residuals only (K2, subsystem.rs:93-104). */
+FK_API int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream);
+FK_API int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_j, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIKSI_B200_H */

@@ -1,0 +1,740 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// CPU restatement of Fiksi's numeric solve path: the 11 residual/gradient expressions, the
+// `Subsystem` problem (free/fixed variable map, COO triplets for free columns), the
+// Levenberg–Marquardt driver on the augmented system [J; sqrt(lambda) I] with sparse Householder
+// QR under COLAMD ordering, the connected-component graph (including its stale-index behaviour),
+// and `assemble::solve`'s scale / perturb / write-back.  Every routine cites the reference lines
+// it follows (paths relative to /root/reference).
+//
+// Parity status: the linear algebra underneath is pinned by the reference's known-answer tests
+// (see solvi_ref.hpp / colamd_ref.hpp); the LCG by fiksi/src/rand.rs:49-63; the expression
+// gradients by the reference's finite-difference property (expressions.rs:1196-1510); the
+// end-to-end scenarios by the reference's residual thresholds (fiksi/src/tests/*.rs).  The
+// reference cannot be compiled in this environment (no Rust toolchain), so CONVERGED COORDINATES
+// ARE PARITY-UNPINNED against a reference binary; SURVEY.md App. E hand-derived checkpoints are
+// checked in tests/test_oracle_fiksi.py.
+//
+// One extension: the reference's inner damping loop is unbounded and spins forever once lambda
+// overflows to +inf (every later step is NaN; lm.rs:115-191).  The oracle stops there and reports
+// exit_reason 4 ("reference would hang").
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "solvi_ref.hpp"
+
+namespace orc {
+namespace fiksi {
+
+// fiksi/src/rand.rs:13-40
+struct Rng {
+    uint32_t state;
+    explicit Rng(uint32_t seed) : state(seed) {}
+    uint32_t next_u32() {
+        state = state * 1664525u + 1013904223u;
+        return state;
+    }
+    double next_f64() {
+        uint32_t val = next_u32();
+        return (1. / (double)UINT32_MAX) * (double)val;
+    }
+};
+
+// fiksi/src/utils.rs:12-33 (sequential left-to-right sums)
+inline double sum_squares(const double* v, size_t n) {
+    double s = 0.0;
+    for (size_t i = 0; i < n; i++) s += v[i] * v[i];
+    return s;
+}
+
+// fiksi/src/constraints/expressions.rs:28-40 — kinds in enum order.
+enum Kind : uint8_t {
+    VariableVariableEquality = 0,
+    PointPointDistance = 1,
+    PointPointPointAngle = 2,
+    PointLineIncidence = 3,
+    PointLineDistance = 4,
+    PointCircleIncidence = 5,
+    SegmentSegmentLengthEquality = 6,
+    LineLineAngle = 7,
+    LineLineParallelism = 8,
+    LineLinePerpendicularity = 9,
+    LineCircleTangency = 10,
+    NUM_KINDS = 11,
+};
+
+struct Expression {
+    uint8_t kind = 0;
+    uint32_t idx[4] = {0, 0, 0, 0};  // base indices exactly as stored in the reference structs
+    double param = 0.0;              // distance / angle, 0 if none
+};
+
+// expressions.rs:48-182.  Returns the number of variable slots.
+inline int variable_indices(const Expression& e, uint32_t out[8]) {
+    const uint32_t* i = e.idx;
+    switch (e.kind) {
+        case VariableVariableEquality:
+            out[0] = i[0]; out[1] = i[1];
+            return 2;
+        case PointPointDistance:
+            out[0] = i[0]; out[1] = i[0] + 1; out[2] = i[1]; out[3] = i[1] + 1;
+            return 4;
+        case PointPointPointAngle:
+        case PointLineIncidence:
+        case PointLineDistance:
+            out[0] = i[0]; out[1] = i[0] + 1; out[2] = i[1]; out[3] = i[1] + 1;
+            out[4] = i[2]; out[5] = i[2] + 1;
+            return 6;
+        case PointCircleIncidence:
+            out[0] = i[0]; out[1] = i[0] + 1; out[2] = i[1]; out[3] = i[1] + 1; out[4] = i[2];
+            return 5;
+        case SegmentSegmentLengthEquality:
+        case LineLineAngle:
+        case LineLineParallelism:
+        case LineLinePerpendicularity:
+            out[0] = i[0]; out[1] = i[0] + 1; out[2] = i[1]; out[3] = i[1] + 1;
+            out[4] = i[2]; out[5] = i[2] + 1; out[6] = i[3]; out[7] = i[3] + 1;
+            return 8;
+        case LineCircleTangency:
+            out[0] = i[0]; out[1] = i[0] + 1; out[2] = i[1]; out[3] = i[1] + 1;
+            out[4] = i[2]; out[5] = i[2] + 1; out[6] = i[3];
+            return 7;
+    }
+    return 0;
+}
+
+// expressions.rs:195-211
+inline Expression transform(const Expression& e, double length_scale_recip) {
+    Expression t = e;
+    if (e.kind == PointPointDistance || e.kind == PointLineDistance)
+        t.param = length_scale_recip * e.param;
+    return t;
+}
+
+static const double PI = 3.14159265358979323846264338327950288;  // core::f64::consts::PI
+
+// expressions.rs:319-353
+inline double ppd_eval(const double* v, double param_distance, double g[4]) {
+    double p1x = v[0], p1y = v[1], p2x = v[2], p2y = v[3];
+    double dx = p1x - p2x, dy = p1y - p2y;
+    double distance = std::sqrt(dx * dx + dy * dy);
+    double residual = distance - param_distance;
+    double distance_recip = 1. / distance;
+    g[0] = (p1x - p2x) * distance_recip;
+    g[1] = (p1y - p2y) * distance_recip;
+    g[2] = -(p1x - p2x) * distance_recip;
+    g[3] = -(p1y - p2y) * distance_recip;
+    return residual;
+}
+
+inline double wrap_angle(double angle) {
+    // expressions.rs:393-399,665-671
+    if (angle > PI) return angle - 2.0 * PI;
+    if (angle < -PI) return angle + 2.0 * PI;
+    return angle;
+}
+
+// expressions.rs:214-276 + the per-kind kernels :291-874.  `v` holds the slot values in
+// `variable_indices` order; `g` receives one entry per slot.  Returns the residual.
+inline double compute_residual_and_gradient(const Expression& e, const double v[8], double g[8]) {
+    switch (e.kind) {
+        case VariableVariableEquality: {  // :291-301
+            g[0] = -1.;
+            g[1] = 1.;
+            return v[1] - v[0];
+        }
+        case PointPointDistance:
+            return ppd_eval(v, e.param, g);
+        case PointPointPointAngle: {  // :372-425
+            double ux = v[0] - v[2], uy = v[1] - v[3];
+            double vx = v[4] - v[2], vy = v[5] - v[3];
+            double angle = wrap_angle(std::atan2(vy, vx) - std::atan2(uy, ux));
+            double residual = angle - e.param;
+            double ur = 1. / (ux * ux + uy * uy);
+            double vr = 1. / (vx * vx + vy * vy);
+            double d1x = uy * ur, d1y = -ux * ur;
+            double d3x = -vy * vr, d3y = vx * vr;
+            double d2x = -d1x - d3x, d2y = -d1y - d3y;
+            g[0] = d1x; g[1] = d1y; g[2] = d2x; g[3] = d2y; g[4] = d3x; g[5] = d3y;
+            return residual;
+        }
+        case PointLineIncidence: {  // :445-477
+            double px = v[0], py = v[1], l1x = v[2], l1y = v[3], l2x = v[4], l2y = v[5];
+            double ux = l2x - l1x, uy = l2y - l1y;
+            double wx = px - l1x, wy = py - l1y;
+            double residual = ux * wy - uy * wx;
+            g[0] = -uy; g[1] = ux; g[2] = -py + l2y; g[3] = px - l2x; g[4] = wy; g[5] = -wx;
+            return residual;
+        }
+        case PointLineDistance: {  // :500-544
+            double px = v[0], py = v[1], l1x = v[2], l1y = v[3], l2x = v[4], l2y = v[5];
+            double ux = l2x - l1x, uy = l2y - l1y;
+            double wx = px - l1x, wy = py - l1y;
+            double cross = ux * wy - uy * wx;
+            double len2 = ux * ux + uy * uy;
+            double len = std::sqrt(len2);
+            double lr = 1. / len;
+            double a = cross / len2;
+            double b = -a * ux;
+            double c = px + a * uy;
+            double residual = lr * cross - e.param;
+            g[0] = -lr * uy;
+            g[1] = lr * ux;
+            g[2] = -lr * (b - l2y + py);
+            g[3] = -lr * (l2x - c);
+            g[4] = lr * (b + wy);
+            g[5] = -lr * (c - l1x);
+            return residual;
+        }
+        case PointCircleIncidence: {  // :560-576
+            double r = ppd_eval(v, v[4], g);
+            g[4] = -1.;
+            return r;
+        }
+        case SegmentSegmentLengthEquality: {  // :593-620
+            double g1[4], g2[4];
+            double r1 = ppd_eval(v, 0., g1);
+            double r2 = ppd_eval(v + 4, 0., g2);
+            g[0] = -g1[0]; g[1] = -g1[1]; g[2] = -g1[2]; g[3] = -g1[3];
+            g[4] = g2[0]; g[5] = g2[1]; g[6] = g2[2]; g[7] = g2[3];
+            return r2 - r1;
+        }
+        case LineLineAngle: {  // :640-696
+            double ux = v[2] - v[0], uy = v[3] - v[1];
+            double vx = v[6] - v[4], vy = v[7] - v[5];
+            double angle = wrap_angle(std::atan2(vy, vx) - std::atan2(uy, ux));
+            double residual = angle - e.param;
+            double ur = 1. / (ux * ux + uy * uy);
+            double vr = 1. / (vx * vx + vy * vy);
+            double a = -uy * ur, b = ux * ur, c = vy * vr, d = -vx * vr;
+            g[0] = a; g[1] = b; g[2] = -a; g[3] = -b; g[4] = c; g[5] = d; g[6] = -c; g[7] = -d;
+            return residual;
+        }
+        case LineLineParallelism: {  // :713-752
+            double ux = v[2] - v[0], uy = v[3] - v[1];
+            double vx = v[6] - v[4], vy = v[7] - v[5];
+            double residual = vx * uy - vy * ux;
+            g[0] = vy; g[1] = -vx; g[2] = -vy; g[3] = vx; g[4] = -uy; g[5] = ux; g[6] = uy; g[7] = -ux;
+            return residual;
+        }
+        case LineLinePerpendicularity: {  // :769-799
+            double ux = v[2] - v[0], uy = v[3] - v[1];
+            double vx = v[6] - v[4], vy = v[7] - v[5];
+            double residual = vx * ux + vy * uy;
+            g[0] = -vx; g[1] = -vy; g[2] = vx; g[3] = vy; g[4] = -ux; g[5] = -uy; g[6] = ux; g[7] = uy;
+            return residual;
+        }
+        case LineCircleTangency: {  // :816-874
+            double l1x = v[0], l1y = v[1], l2x = v[2], l2y = v[3], cx = v[4], cy = v[5], rad = v[6];
+            double ddx = l1x - l2x, ddy = l1y - l2y;
+            double length2 = ddx * ddx + ddy * ddy;
+            double length = std::sqrt(length2);
+            if (length == 0.) {
+                for (int k = 0; k < 7; k++) g[k] = 0.;
+                return 0.;
+            }
+            double length_recip = 1. / length;
+            double signed_area = l1x * (l2y - cy) + l2x * (cy - l1y) + cx * (l1y - l2y);
+            double residual = length_recip * std::fabs(signed_area) - rad;
+            // f64::signum: 1.0 for +0.0 and positives, -1.0 for -0.0 and negatives, NaN for NaN
+            double sign = std::isnan(signed_area) ? signed_area : std::copysign(1.0, signed_area);
+            double length3_recip = 1. / (length2 * length);
+            g[0] = sign * length3_recip * (length2 * (l2y - cy) + signed_area * (l2x - l1x));
+            g[1] = sign * length3_recip * (length2 * (-l2x + cx) + signed_area * (l2y - l1y));
+            g[2] = sign * length3_recip * (length2 * (cy - l1y) - signed_area * (l2x - l1x));
+            g[3] = sign * length3_recip * (length2 * (l1x - cx) - signed_area * (l2y - l1y));
+            g[4] = sign * length_recip * (l1y - l2y);
+            g[5] = sign * length_recip * (-l1x + l2x);
+            g[6] = -1.;
+            return residual;
+        }
+    }
+    return 0.;
+}
+
+// fiksi/src/subsystem.rs:9-167 + variable_map.rs:43-73.  The IndexSet lookup becomes a dense
+// var -> free index table (same mapping: index == insertion order of `free_variables`).
+struct Subsystem {
+    const double* system_variables;      // scaled system variables (fixed values are read here)
+    const Expression* all_expressions;   // scaled expressions
+    std::vector<uint32_t> expressions;   // rows: expression ids
+    std::vector<uint32_t> free_variables;  // insertion order == free index
+    std::vector<int32_t> var_to_free;    // -1 if fixed / not in this subsystem
+
+    Subsystem(const double* vars, size_t n_vars, const Expression* exprs,
+              const std::vector<uint32_t>& free_vars, const std::vector<uint32_t>& rows)
+        : system_variables(vars), all_expressions(exprs), expressions(rows), free_variables(free_vars),
+          var_to_free(n_vars, -1) {
+        for (size_t k = 0; k < free_vars.size(); k++)
+            if (var_to_free[free_vars[k]] < 0) var_to_free[free_vars[k]] = (int32_t)k;
+    }
+    uint32_t num_variables() const { return (uint32_t)free_variables.size(); }
+    uint32_t num_residuals() const { return (uint32_t)expressions.size(); }
+
+    double value_of(uint32_t var, const double* free_values) const {
+        int32_t f = var_to_free[var];
+        return f >= 0 ? free_values[f] : system_variables[var];
+    }
+    // subsystem.rs:93-104
+    void calculate_residuals(const double* variables, double* residuals) const {
+        uint32_t vi[8];
+        double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8];
+        for (size_t row = 0; row < expressions.size(); row++) {
+            const Expression& e = all_expressions[expressions[row]];
+            int a = variable_indices(e, vi);
+            for (int k = 0; k < a; k++) vals[k] = value_of(vi[k], variables);
+            residuals[row] = compute_residual_and_gradient(e, vals, grad);
+        }
+    }
+    // subsystem.rs:126-166
+    void calculate_residuals_and_sparse_jacobian(const double* variables, double* residuals,
+                                                 solvi::TripletMat& jac) const {
+        uint32_t vi[8];
+        double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t row = 0; row < expressions.size(); row++) {
+            const Expression& e = all_expressions[expressions[row]];
+            int a = variable_indices(e, vi);
+            for (int k = 0; k < a; k++) vals[k] = value_of(vi[k], variables);
+            residuals[row] = compute_residual_and_gradient(e, vals, grad);
+            for (int k = 0; k < a; k++) {
+                int32_t f = var_to_free[vi[k]];
+                if (f >= 0) jac.push_triplet(row, (size_t)f, grad[k]);
+            }
+        }
+    }
+};
+
+enum ExitReason : uint32_t {
+    EXIT_CONVERGED_RESIDUAL = 0,  // lm.rs:110-112
+    EXIT_SMALL_STEP = 1,          // lm.rs:139-142
+    EXIT_STALLED = 2,             // lm.rs:164-168
+    EXIT_MAX_OUTER = 3,           // lm.rs:109
+    EXIT_LAMBDA_OVERFLOW = 4,     // reference would spin forever
+};
+
+struct LmReport {
+    uint32_t exit_reason = 0;
+    uint32_t outer_iters = 0;     // outer iterations that entered the damping loop
+    uint32_t factorizations = 0;  // inner iterations (one factorize + solve each)
+    uint32_t accepted = 0;        // accepted steps
+    double ssr = 0.0;             // sum of squared residuals at the returned variables
+    double lambda = 0.0;          // final damping
+    uint64_t trace_hash = 0;      // rolling base-3 hash of decisions: 1 accept, 2 reject, 0 unsolved
+    std::string trace;            // 'A' accept, 'R' reject, 'U' unsolved (R diagonal exactly zero)
+    // symbolic artefacts of the (only) SymbolicQr::build call, for the parity probes
+    solvi::Structure jacobian_structure;
+    solvi::SymbolicQr symbolic;
+    std::vector<double> initial_residuals;  // before negation
+};
+
+inline uint64_t trace_push(uint64_t h, uint32_t code) { return h * 3u + code + 1u; }
+
+// fiksi/src/solve/lm.rs:21-197
+inline void levenberg_marquardt(const Subsystem& problem, double* variables, LmReport& rep,
+                                bool keep_artifacts = false) {
+    size_t nrows = problem.num_residuals(), ncols = problem.num_variables();
+    std::vector<double> xs(variables, variables + ncols);
+    std::vector<double> residuals(nrows, 0.), residuals_scratch(nrows, 0.), b_aug(nrows + ncols, 0.);
+    solvi::TripletMat jac(nrows, ncols);
+    problem.calculate_residuals_and_sparse_jacobian(xs.data(), residuals.data(), jac);
+    if (keep_artifacts) rep.initial_residuals = residuals;
+    for (double& r : residuals) r = -r;
+    for (size_t idx = 0; idx < ncols; idx++) jac.push_triplet(nrows + idx, idx, 0.);
+    solvi::SparseColMat csc = solvi::SparseColMat::from_triplet_mat(jac);
+    solvi::SymbolicQr sym = solvi::SymbolicQr::build(csc.structure, solvi::QrOrdering::Colamd);
+    solvi::Qr qr(sym);
+    if (keep_artifacts) rep.jacobian_structure = csc.structure;
+
+    double ssr = sum_squares(residuals.data(), nrows);
+    double lambda = 0.5;
+    rep.exit_reason = EXIT_MAX_OUTER;
+    bool done = false;
+    for (int outer = 0; outer < 100 && !done; outer++) {
+        if (ssr < 1e-8) {
+            rep.exit_reason = EXIT_CONVERGED_RESIDUAL;
+            break;
+        }
+        rep.outer_iters++;
+        for (;;) {
+            if (!std::isfinite(lambda)) {
+                rep.exit_reason = EXIT_LAMBDA_OVERFLOW;
+                done = true;
+                break;
+            }
+            double sl = std::sqrt(lambda);
+            for (size_t idx = 0; idx < ncols; idx++)
+                csc.values[csc.structure.column_pointers[idx + 1] - 1] = sl;
+            qr.factorize(csc);
+            rep.factorizations++;
+            for (size_t i = 0; i < nrows; i++) b_aug[i] = residuals[i];
+            for (size_t i = nrows; i < nrows + ncols; i++) b_aug[i] = 0.;
+            bool solved = qr.solve_mut(b_aug.data());
+            if (!solved) {
+                lambda *= 8.;
+                rep.trace.push_back('U');
+                rep.trace_hash = trace_push(rep.trace_hash, 0);
+                continue;
+            }
+            const double* delta = b_aug.data();
+            if (sum_squares(delta, ncols) < 1e-12) {
+                rep.exit_reason = EXIT_SMALL_STEP;
+                done = true;
+                break;
+            }
+            for (size_t idx = 0; idx < ncols; idx++) xs[idx] = variables[idx] + delta[idx];
+            problem.calculate_residuals(xs.data(), residuals_scratch.data());
+            double ssr_s = sum_squares(residuals_scratch.data(), nrows);
+            if (ssr_s < ssr) {
+                lambda *= 0.125;
+                if (lambda < 1e-50) lambda = 1e-50;
+                for (size_t idx = 0; idx < ncols; idx++) variables[idx] = xs[idx];
+                rep.accepted++;
+                rep.trace.push_back('A');
+                rep.trace_hash = trace_push(rep.trace_hash, 1);
+                if ((ssr - ssr_s) / ssr <= 1e-6) {
+                    ssr = ssr_s;  // report the value at the returned variables
+                    rep.exit_reason = EXIT_STALLED;
+                    done = true;
+                    break;
+                }
+                ssr = ssr_s;
+                jac.clear();
+                problem.calculate_residuals_and_sparse_jacobian(xs.data(), residuals.data(), jac);
+                for (double& r : residuals) r = -r;
+                for (size_t idx = 0; idx < ncols; idx++) jac.push_triplet(nrows + idx, idx, 0.);
+                csc = solvi::SparseColMat::from_triplet_mat(jac);
+                break;
+            } else {
+                lambda *= 2.;
+                rep.trace.push_back('R');
+                rep.trace_hash = trace_push(rep.trace_hash, 2);
+            }
+        }
+    }
+    rep.ssr = ssr;
+    rep.lambda = lambda;
+    if (keep_artifacts) rep.symbolic = std::move(sym);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model layer: graph, system, assemble::solve
+// ---------------------------------------------------------------------------------------------
+
+// fiksi/src/graph.rs:120-259 (incremental connected components, stale indices preserved)
+struct ConnectedComponent {
+    std::set<uint32_t> elements, constraints;
+};
+struct Graph {
+    size_t n_elements = 0, n_constraints = 0;
+    std::vector<uint32_t> element_cc;  // 0 == None, otherwise 1-based component index
+    std::vector<ConnectedComponent> components;
+
+    uint32_t add_element() {
+        element_cc.push_back(0);
+        return (uint32_t)n_elements++;
+    }
+    // graph.rs:178-225
+    void merge_connected_components(uint32_t constraint, const uint32_t* elements, int n) {
+        uint32_t target = 0;
+        size_t size_largest = 0;
+        for (int k = 0; k < n; k++) {
+            uint32_t ci = element_cc[elements[k]];
+            if (ci != 0) {
+                const ConnectedComponent& c = components[ci - 1];
+                if (c.elements.size() > size_largest) {
+                    target = ci;
+                    size_largest = c.elements.size();
+                }
+            }
+        }
+        if (target == 0) {
+            components.emplace_back();
+            target = (uint32_t)components.size();
+        }
+        ConnectedComponent tc = std::move(components[target - 1]);
+        components[target - 1] = ConnectedComponent();
+        for (int k = 0; k < n; k++) {
+            uint32_t ci = element_cc[elements[k]];
+            if (ci != 0) {
+                ConnectedComponent c = std::move(components[ci - 1]);
+                components[ci - 1] = ConnectedComponent();
+                tc.elements.insert(c.elements.begin(), c.elements.end());
+                tc.constraints.insert(c.constraints.begin(), c.constraints.end());
+            } else {
+                tc.elements.insert(elements[k]);
+            }
+            element_cc[elements[k]] = target;
+        }
+        tc.constraints.insert(constraint);
+        components[target - 1] = std::move(tc);
+    }
+    // graph.rs:235-254
+    uint32_t add_constraint(const uint32_t* elements, int n) {
+        uint32_t id = (uint32_t)n_constraints++;
+        merge_connected_components(id, elements, n);
+        return id;
+    }
+};
+
+enum ElementTag : uint8_t { ELength = 0, EPoint = 1, ELine = 2, ECircle = 3 };
+struct EncodedElement {
+    uint8_t tag;
+    uint32_t a, b;  // Length{idx=a}; Point{idx=a}; Line{p1=a,p2=b}; Circle{center=a,radius=b}
+};
+struct EncodedConstraint {
+    uint8_t tag;  // ConstraintTag order, constraints/mod.rs:893-905 (0 = PointPointCoincidence)
+    uint32_t expressions_idx;
+};
+// constraints/mod.rs:907-924,948-990: only PointPointCoincidence has valency 2.
+inline uint8_t valency_of(uint8_t constraint_tag) { return constraint_tag == 0 ? 2 : 1; }
+
+struct SolvingOptions {
+    bool perturb = true;  // lib.rs:232-236
+};
+
+struct System {
+    Graph graph;
+    std::vector<EncodedElement> elements;
+    std::vector<double> variables, variables_transformed;
+    std::vector<uint32_t> variable_to_primitive;
+    std::set<uint32_t> fixed_variables;
+    std::vector<EncodedConstraint> constraints;
+    std::vector<Expression> expressions, expressions_transformed;
+    std::vector<LmReport> last_reports;  // one per solved component, in component order
+
+    // lib.rs:363-407
+    uint32_t add_element(const double* vars, int n, EncodedElement (*mk)(uint32_t, uint32_t, uint32_t),
+                         uint32_t a, uint32_t b) {
+        uint32_t id = (uint32_t)elements.size();
+        uint32_t variables_idx = (uint32_t)variables.size();
+        for (int k = 0; k < n; k++) {
+            variables.push_back(vars[k]);
+            variable_to_primitive.push_back(id);
+        }
+        graph.add_element();
+        elements.push_back(mk(variables_idx, a, b));
+        return id;
+    }
+    // elements/mod.rs:280-454
+    uint32_t add_length(double length) {
+        return add_element(&length, 1, [](uint32_t vi, uint32_t, uint32_t) { return EncodedElement{ELength, vi, 0}; }, 0, 0);
+    }
+    uint32_t add_point(double x, double y) {
+        double v[2] = {x, y};
+        return add_element(v, 2, [](uint32_t vi, uint32_t, uint32_t) { return EncodedElement{EPoint, vi, 0}; }, 0, 0);
+    }
+    uint32_t add_line(uint32_t p1, uint32_t p2) {
+        return add_element(nullptr, 0, [](uint32_t, uint32_t a, uint32_t b) { return EncodedElement{ELine, a, b}; },
+                           elements[p1].a, elements[p2].a);
+    }
+    uint32_t add_circle(uint32_t center, uint32_t radius) {
+        return add_element(nullptr, 0, [](uint32_t, uint32_t a, uint32_t b) { return EncodedElement{ECircle, a, b}; },
+                           elements[center].a, elements[radius].a);
+    }
+    // elements/mod.rs variable_indices per element type
+    int element_variables(uint32_t id, uint32_t out[4]) const {
+        const EncodedElement& e = elements[id];
+        switch (e.tag) {
+            case ELength: out[0] = e.a; return 1;
+            case EPoint: out[0] = e.a; out[1] = e.a + 1; return 2;
+            case ELine: out[0] = e.a; out[1] = e.a + 1; out[2] = e.b; out[3] = e.b + 1; return 4;
+            case ECircle: out[0] = e.a; out[1] = e.a + 1; out[2] = e.b; return 3;
+        }
+        return 0;
+    }
+    // elements/mod.rs:60-86
+    void fix(uint32_t id) {
+        uint32_t v[4];
+        int n = element_variables(id, v);
+        for (int k = 0; k < n; k++) fixed_variables.insert(v[k]);
+    }
+    void unfix(uint32_t id) {
+        uint32_t v[4];
+        int n = element_variables(id, v);
+        for (int k = 0; k < n; k++) fixed_variables.erase(v[k]);
+    }
+
+    // lib.rs:412-445
+    uint32_t push_constraint(uint8_t tag, const Expression* exprs, int n) {
+        uint32_t id = (uint32_t)constraints.size();
+        constraints.push_back({tag, (uint32_t)expressions.size()});
+        for (int k = 0; k < n; k++) expressions.push_back(exprs[k]);
+        return id;
+    }
+    uint32_t prim(uint32_t var) const { return variable_to_primitive[var]; }
+
+    // constraints/mod.rs:317-891.  Arguments are element ids of the kinds the reference takes.
+    uint32_t point_point_coincidence(uint32_t p1, uint32_t p2) {
+        uint32_t i1 = elements[p1].a, i2 = elements[p2].a;
+        uint32_t inc[2] = {p1, p2};
+        graph.add_constraint(inc, 2);
+        Expression e[2];
+        e[0].kind = VariableVariableEquality; e[0].idx[0] = i1; e[0].idx[1] = i2;
+        e[1].kind = VariableVariableEquality; e[1].idx[0] = i1 + 1; e[1].idx[1] = i2 + 1;
+        return push_constraint(0, e, 2);
+    }
+    uint32_t point_point_distance(uint32_t p1, uint32_t p2, double distance) {
+        uint32_t inc[2] = {p1, p2};
+        graph.add_constraint(inc, 2);
+        Expression e;
+        e.kind = PointPointDistance; e.idx[0] = elements[p1].a; e.idx[1] = elements[p2].a; e.param = distance;
+        return push_constraint(1, &e, 1);
+    }
+    uint32_t point_point_point_angle(uint32_t p1, uint32_t p2, uint32_t p3, double angle) {
+        uint32_t inc[3] = {p1, p2, p3};
+        graph.add_constraint(inc, 3);
+        Expression e;
+        e.kind = PointPointPointAngle;
+        e.idx[0] = elements[p1].a; e.idx[1] = elements[p2].a; e.idx[2] = elements[p3].a; e.param = angle;
+        return push_constraint(2, &e, 1);
+    }
+    uint32_t point_line_incidence(uint32_t point, uint32_t line) {
+        uint32_t l1 = elements[line].a, l2 = elements[line].b;
+        uint32_t inc[3] = {point, prim(l1), prim(l2)};
+        graph.add_constraint(inc, 3);
+        Expression e;
+        e.kind = PointLineIncidence; e.idx[0] = elements[point].a; e.idx[1] = l1; e.idx[2] = l2;
+        return push_constraint(3, &e, 1);
+    }
+    uint32_t point_line_distance(uint32_t point, uint32_t line, double distance) {
+        uint32_t l1 = elements[line].a, l2 = elements[line].b;
+        uint32_t inc[3] = {point, prim(l1), prim(l2)};
+        graph.add_constraint(inc, 3);
+        Expression e;
+        e.kind = PointLineDistance; e.idx[0] = elements[point].a; e.idx[1] = l1; e.idx[2] = l2; e.param = distance;
+        return push_constraint(4, &e, 1);
+    }
+    uint32_t point_circle_incidence(uint32_t point, uint32_t circle) {
+        uint32_t c = elements[circle].a, r = elements[circle].b;
+        uint32_t inc[3] = {point, prim(c), prim(r)};
+        graph.add_constraint(inc, 3);
+        Expression e;
+        e.kind = PointCircleIncidence; e.idx[0] = elements[point].a; e.idx[1] = c; e.idx[2] = r;
+        return push_constraint(5, &e, 1);
+    }
+    uint32_t four_point(uint8_t ctag, uint8_t kind, uint32_t a, uint32_t b, uint32_t c, uint32_t d, double param) {
+        uint32_t inc[4] = {prim(a), prim(b), prim(c), prim(d)};
+        graph.add_constraint(inc, 4);
+        Expression e;
+        e.kind = kind; e.idx[0] = a; e.idx[1] = b; e.idx[2] = c; e.idx[3] = d; e.param = param;
+        return push_constraint(ctag, &e, 1);
+    }
+    uint32_t segment_segment_length_equality(uint32_t s1p1, uint32_t s1p2, uint32_t s2p1, uint32_t s2p2) {
+        return four_point(6, SegmentSegmentLengthEquality, elements[s1p1].a, elements[s1p2].a,
+                          elements[s2p1].a, elements[s2p2].a, 0.);
+    }
+    uint32_t line_line_angle(uint32_t l1, uint32_t l2, double angle) {
+        return four_point(7, LineLineAngle, elements[l1].a, elements[l1].b, elements[l2].a, elements[l2].b, angle);
+    }
+    uint32_t line_line_parallelism(uint32_t l1, uint32_t l2) {
+        return four_point(8, LineLineParallelism, elements[l1].a, elements[l1].b, elements[l2].a, elements[l2].b, 0.);
+    }
+    uint32_t line_line_perpendicularity(uint32_t l1, uint32_t l2) {
+        return four_point(9, LineLinePerpendicularity, elements[l1].a, elements[l1].b, elements[l2].a, elements[l2].b, 0.);
+    }
+    uint32_t line_circle_tangency(uint32_t line, uint32_t circle) {
+        return four_point(10, LineCircleTangency, elements[line].a, elements[line].b, elements[circle].a,
+                          elements[circle].b, 0.);
+    }
+
+    // constraints/mod.rs:88-110 (IdentityVariableMap: every variable reads system.variables)
+    double calculate_residual(uint32_t constraint) const {
+        const EncodedConstraint& c = constraints[constraint];
+        int val = valency_of(c.tag);
+        auto one = [&](const Expression& e) {
+            uint32_t vi[8];
+            double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8];
+            int a = variable_indices(e, vi);
+            for (int k = 0; k < a; k++) vals[k] = variables[vi[k]];
+            return compute_residual_and_gradient(e, vals, grad);
+        };
+        if (val > 1) {
+            double s = 0.0;
+            for (int k = 0; k < val; k++) {
+                double r = one(expressions[c.expressions_idx + k]);
+                s += r * r;
+            }
+            return std::sqrt(s);
+        }
+        return one(expressions[c.expressions_idx]);
+    }
+
+    // assemble/mod.rs:32-44
+    double calculate_system_scale() const {
+        double s = 0.0;
+        size_t n = 0;
+        for (double v : variables) { s += v * v; n++; }
+        for (const Expression& e : expressions)
+            if (e.kind == PointPointDistance || e.kind == PointLineDistance) { s += e.param * e.param; n++; }
+        return std::sqrt(s / (double)n);
+    }
+
+    // One component's flattened problem as handed to `Subsystem::new` (assemble/mod.rs:91-146).
+    struct ComponentProblem {
+        std::vector<uint32_t> free_variables, rows;
+    };
+
+    // assemble/mod.rs:46-146: scale, then per component (Vec order, empty ones skipped) the free
+    // set, the perturbation and the row list.  `visit(cp)` is called at the point where the
+    // reference constructs the `Subsystem`, i.e. `variables_transformed` holds the perturbation of
+    // this and all earlier components only (matters for stale elements).
+    template <class Visit>
+    double for_each_component(const SolvingOptions& opts, Visit visit) {
+        Rng rng(42);
+        double system_scale = calculate_system_scale();
+        double recip = 1. / system_scale;
+        variables_transformed.assign(variables.size(), 0.);
+        for (size_t i = 0; i < variables.size(); i++) variables_transformed[i] = variables[i] * recip;
+        expressions_transformed.clear();
+        for (const Expression& e : expressions) expressions_transformed.push_back(transform(e, recip));
+        for (size_t ci = 0; ci < graph.components.size(); ci++) {
+            const ConnectedComponent& cc = graph.components[ci];
+            if (cc.elements.empty()) continue;
+            std::set<uint32_t> free_set;
+            for (uint32_t el : cc.elements) {
+                uint32_t v[4];
+                int n = element_variables(el, v);
+                for (int k = 0; k < n; k++)
+                    if (!fixed_variables.count(v[k])) free_set.insert(v[k]);
+            }
+            if (opts.perturb) {
+                for (uint32_t fv : free_set) {
+                    double& variable = variables_transformed[fv];
+                    double r1 = rng.next_f64();
+                    double r2 = rng.next_f64();
+                    variable += variable * (1. / 8196.) * r1 + (1. / 65568.) * r2;
+                }
+            }
+            ComponentProblem cp;
+            cp.free_variables.assign(free_set.begin(), free_set.end());
+            for (uint32_t c : cc.constraints)
+                for (int off = 0; off < valency_of(constraints[c].tag); off++)
+                    cp.rows.push_back(constraints[c].expressions_idx + (uint32_t)off);
+            visit(cp, system_scale);
+        }
+        return system_scale;
+    }
+
+    // assemble/mod.rs:127-167 with Decomposer::None + Optimizer::LevenbergMarquardt.
+    void solve(const SolvingOptions& opts, bool keep_artifacts = false) {
+        last_reports.clear();
+        for_each_component(opts, [&](const ComponentProblem& cp, double system_scale) {
+            std::vector<double> free_values;
+            for (uint32_t fv : cp.free_variables) free_values.push_back(variables_transformed[fv]);
+            Subsystem sub(variables_transformed.data(), variables_transformed.size(),
+                          expressions_transformed.data(), cp.free_variables, cp.rows);
+            LmReport rep;
+            levenberg_marquardt(sub, free_values.data(), rep, keep_artifacts);
+            for (size_t k = 0; k < cp.free_variables.size(); k++)
+                variables[cp.free_variables[k]] = system_scale * free_values[k];
+            last_reports.push_back(std::move(rep));
+        });
+    }
+};
+
+}  // namespace fiksi
+}  // namespace orc
