@@ -1,0 +1,150 @@
+"""Thin Python face of the C ABI (include/fiksi_b200.h): topology, symbolic probes, LM solves.
+
+All numerics happen inside libfiksi_b200.so (host symbolic pipeline in C++, kernels in CUDA for
+sm_100a).  Nothing here computes residuals, Jacobians, orderings or factorizations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (FkProblem, FkReport, FkTopologyInfo, REPORT_DTYPE, check, lib, make_problem, ptr)
+
+
+class Topology:
+    """fk_topology: symbolic analysis computed once per topology."""
+
+    def __init__(self, problem: FkProblem, keepalive=None):
+        self._h = C.c_void_p()
+        check(lib().fk_topology_create(C.byref(problem), C.byref(self._h)))
+        self._keep = keepalive
+        info = FkTopologyInfo()
+        check(lib().fk_topology_info_get(self._h, C.byref(info)))
+        self.info = {n: getattr(info, n) for n, _ in FkTopologyInfo._fields_}
+
+    @classmethod
+    def from_arrays(cls, n_vars, kind, idx, free_vars, rows):
+        p, keep = make_problem(np.zeros(n_vars), kind, idx, np.zeros(len(kind)), free_vars, rows)
+        return cls(p, keep)
+
+    def symbolic(self):
+        i = self.info
+        n = i["n_free"]
+        out = {
+            "aug_colptr": np.zeros(n + 1, np.uint32), "aug_rowidx": np.zeros(max(i["aug_nnz"], 1), np.uint32),
+            "perm": np.zeros(max(n, 1), np.int32), "etree_parent": np.zeros(max(n, 1), np.int32),
+            "r_colptr": np.zeros(n + 1, np.uint32), "r_rowidx": np.zeros(max(i["r_nnz"], 1), np.uint32),
+        }
+        check(lib().fk_topology_symbolic(self._h, ptr(out["aug_colptr"], C.c_uint32), ptr(out["aug_rowidx"], C.c_uint32),
+                                         ptr(out["perm"], C.c_int32), ptr(out["etree_parent"], C.c_int32),
+                                         ptr(out["r_colptr"], C.c_uint32), ptr(out["r_rowidx"], C.c_uint32)))
+        out["aug_rowidx"] = out["aug_rowidx"][:i["aug_nnz"]]
+        out["perm"] = out["perm"][:n]
+        out["etree_parent"] = out["etree_parent"][:n]
+        out["r_rowidx"] = out["r_rowidx"][:i["r_nnz"]]
+        return out
+
+    def batch_solve(self, vars_, param, n_gpus=1):
+        """fk_batch_solve on host buffers: vars[n][n_vars], param[n][n_expr] -> (free[n][n_free], reports)."""
+        vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+        param = np.ascontiguousarray(param, dtype=np.float64)
+        n = vars_.shape[0]
+        out = np.zeros((n, self.info["n_free"]), dtype=np.float64)
+        reports = np.zeros(n, dtype=REPORT_DTYPE)
+        check(lib().fk_batch_solve(self._h, n, ptr(vars_, C.c_double), ptr(param, C.c_double), ptr(out, C.c_double),
+                                   reports.ctypes.data_as(C.POINTER(FkReport)), n_gpus))
+        return out, reports
+
+    def plan(self, capacity, device=0):
+        return BatchPlan(self, capacity, device)
+
+    def close(self):
+        if self._h:
+            lib().fk_topology_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchPlan:
+    """fk_batch_plan: device-resident buffers for n sketches of one topology on one device."""
+
+    def __init__(self, topo: Topology, capacity: int, device: int = 0):
+        self.topo = topo
+        self._h = C.c_void_p()
+        check(lib().fk_batch_plan_create(topo._h, capacity, device, C.byref(self._h)))
+        self.capacity = capacity
+        self.n = 0
+
+    def upload(self, vars_, param, stream=0):
+        n = vars_.shape[0]
+        check(lib().fk_batch_plan_upload(self._h, n, C.c_void_p(vars_.ctypes.data), C.c_void_p(param.ctypes.data), C.c_void_p(stream)))
+        self.n = n
+
+    def upload_ptr(self, n, vars_ptr, param_ptr, stream=0):
+        check(lib().fk_batch_plan_upload(self._h, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr), C.c_void_p(stream)))
+        self.n = n
+
+    def run(self, stream=0):
+        check(lib().fk_batch_plan_run(self._h, C.c_void_p(stream)))
+
+    def download(self, free_out, reports, stream=0):
+        check(lib().fk_batch_plan_download(self._h, C.c_void_p(free_out.ctypes.data if free_out is not None else 0),
+                                           C.c_void_p(reports.ctypes.data if reports is not None else 0), C.c_void_p(stream)))
+
+    def download_ptr(self, free_ptr, rep_ptr, stream=0):
+        check(lib().fk_batch_plan_download(self._h, C.c_void_p(free_ptr), C.c_void_p(rep_ptr), C.c_void_p(stream)))
+
+    def eval(self, mode=0, stream=0):
+        check(lib().fk_batch_plan_eval(self._h, mode, C.c_void_p(stream)))
+
+    def eval_download(self, out_r, out_j, stream=0):
+        check(lib().fk_batch_plan_eval_download(self._h, C.c_void_p(out_r.ctypes.data if out_r is not None else 0),
+                                                C.c_void_p(out_j.ctypes.data if out_j is not None else 0), C.c_void_p(stream)))
+
+    @property
+    def launches(self):
+        return int(lib().fk_batch_plan_launches(self._h))
+
+    def close(self):
+        if self._h:
+            lib().fk_batch_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count() -> int:
+    return int(lib().fk_device_count())
+
+
+def lm_solve(problem: FkProblem, free_values):
+    """== levenberg_marquardt(problem, variables) (fiksi/src/solve/lm.rs:21) through fk_lm_solve."""
+    x = np.array(free_values, dtype=np.float64)
+    rep = FkReport()
+    check(lib().fk_lm_solve(C.byref(problem), ptr(x, C.c_double), C.byref(rep)))
+    return x, report_dict(rep)
+
+
+def lm_solve_batch(problems, free_values_list, n_gpus=1):
+    n = len(problems)
+    arr = (C.POINTER(FkProblem) * n)(*[C.pointer(p) for p in problems])
+    xs = [np.array(v, dtype=np.float64) for v in free_values_list]
+    fv = (C.POINTER(C.c_double) * n)(*[ptr(x, C.c_double) for x in xs])
+    reports = np.zeros(n, dtype=REPORT_DTYPE)
+    check(lib().fk_lm_solve_batch(n, arr, fv, reports.ctypes.data_as(C.POINTER(FkReport)), n_gpus))
+    return xs, reports
+
+
+def report_dict(rep):
+    return {"exit_reason": rep.exit_reason, "outer_iters": rep.outer_iters, "factorizations": rep.factorizations,
+            "accepted": rep.accepted, "ssr": rep.ssr, "lambda": rep.lambda_, "trace_hash": rep.trace_hash}

@@ -1,0 +1,446 @@
+// extern "C" entry points of libfiksi_b200.so (declared in include/fiksi_b200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fiksi_b200.h"
+#include "lm_kernels.cuh"
+#include "symbolic.hpp"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? FK_ERR_OOM : FK_ERR_CUDA;
+}
+#define CU(call)                                           \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+int usable_devices() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// Packs the topology tables into one device allocation and fills the DevProgram view.
+struct DeviceProgram {
+    int device = -1;
+    void* buf = nullptr;
+    fk::DevProgram view{};
+    ~DeviceProgram() {
+        if (buf) {
+            cudaSetDevice(device);
+            cudaFree(buf);
+        }
+    }
+};
+
+template <class T>
+size_t reserve(size_t& off, size_t count) {
+    off = (off + 15) & ~size_t(15);
+    size_t at = off;
+    off += std::max<size_t>(count, 1) * sizeof(T);
+    return at;
+}
+
+int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
+    CU(cudaSetDevice(device));
+    struct Item { const void* src; size_t bytes; size_t at; };
+    std::vector<Item> items;
+    size_t off = 0;
+    auto add = [&](const auto& vec) {
+        using T = typename std::decay<decltype(vec)>::type::value_type;
+        size_t at = reserve<T>(off, vec.size());
+        items.push_back({vec.data(), vec.size() * sizeof(T), at});
+        return at;
+    };
+    size_t o_kind = add(t.row_kind), o_expr = add(t.row_expr), o_svar = add(t.slot_var), o_scol = add(t.slot_col),
+           o_spos = add(t.slot_pos), o_sdup = add(t.slot_dup), o_free = add(t.free_vars), o_perm = add(t.perm),
+           o_lcp = add(t.l_colptr), o_lri = add(t.l_rowidx), o_hp = add(t.h_ptr), o_hpr = add(t.h_pairs),
+           o_gp = add(t.g_ptr), o_gpr = add(t.g_pairs), o_up = add(t.u_ptr), o_ut = add(t.u_trip),
+           o_rcp = add(t.r_colptr), o_rri = add(t.r_rowidx), o_rlp = add(t.r_lpos);
+    std::vector<unsigned char> host(off + 16, 0);
+    for (const Item& it : items)
+        if (it.bytes) std::memcpy(host.data() + it.at, it.src, it.bytes);
+    CU(cudaMalloc(&out.buf, host.size()));
+    out.device = device;
+    CU(cudaMemcpy(out.buf, host.data(), host.size(), cudaMemcpyHostToDevice));
+    unsigned char* b = (unsigned char*)out.buf;
+    fk::DevProgram& v = out.view;
+    v.n_vars = t.n_vars; v.n_expr = t.n_expr; v.n = t.n_free; v.m = t.n_rows;
+    v.jnnz = t.jac_nnz; v.lnnz = (uint32_t)t.l_rowidx.size(); v.nlevels = t.etree_height; v.pad_ = 0;
+    v.row_kind = (const uint8_t*)(b + o_kind); v.row_expr = (const uint32_t*)(b + o_expr);
+    v.slot_var = (const uint32_t*)(b + o_svar); v.slot_col = (const int32_t*)(b + o_scol);
+    v.slot_pos = (const int32_t*)(b + o_spos); v.slot_dup = (const uint8_t*)(b + o_sdup);
+    v.free_vars = (const uint32_t*)(b + o_free); v.perm = (const int32_t*)(b + o_perm);
+    v.l_colptr = (const uint32_t*)(b + o_lcp); v.l_rowidx = (const uint32_t*)(b + o_lri);
+    v.h_ptr = (const uint32_t*)(b + o_hp); v.h_pairs = (const uint32_t*)(b + o_hpr);
+    v.g_ptr = (const uint32_t*)(b + o_gp); v.g_pairs = (const uint32_t*)(b + o_gpr);
+    v.u_ptr = (const uint32_t*)(b + o_up); v.u_trip = (const uint32_t*)(b + o_ut);
+    v.r_colptr = (const uint32_t*)(b + o_rcp); v.r_rowidx = (const uint32_t*)(b + o_rri);
+    v.r_lpos = (const uint32_t*)(b + o_rlp);
+    return FK_OK;
+}
+
+}  // namespace
+
+struct fk_topology {
+    fk::Topology t;
+    std::mutex mu;
+    std::map<int, std::unique_ptr<DeviceProgram>> programs;
+
+    int program_for(int device, const fk::DevProgram** out) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = programs.find(device);
+        if (it == programs.end()) {
+            std::unique_ptr<DeviceProgram> p(new DeviceProgram());
+            int rc = upload_program(t, device, *p);
+            if (rc != FK_OK) return rc;
+            it = programs.emplace(device, std::move(p)).first;
+        }
+        *out = &it->second->view;
+        return FK_OK;
+    }
+};
+
+struct fk_batch_plan {
+    fk_topology* topo = nullptr;
+    int device = 0;
+    uint32_t capacity = 0, n = 0;
+    const fk::DevProgram* prog = nullptr;
+    double *d_vars = nullptr, *d_params = nullptr, *d_out = nullptr, *d_er = nullptr, *d_ej = nullptr;
+    fk_report* d_rep = nullptr;
+    uint64_t launches = 0;
+    ~fk_batch_plan() {
+        cudaSetDevice(device);
+        cudaFree(d_vars); cudaFree(d_params); cudaFree(d_out); cudaFree(d_er); cudaFree(d_ej); cudaFree(d_rep);
+    }
+};
+
+extern "C" {
+
+int fk_version(void) { return 100; }
+const char* fk_last_error(void) { return g_error.c_str(); }
+int fk_device_count(void) { return usable_devices(); }
+
+int fk_topology_create(const fk_problem* problem, fk_topology** out) {
+    if (!problem || !out) return fail(FK_ERR_INVALID, "null argument");
+    std::unique_ptr<fk_topology> t(new (std::nothrow) fk_topology());
+    if (!t) return fail(FK_ERR_OOM, "host allocation failed");
+    int rc;
+    try {
+        rc = t->t.build(*problem);
+    } catch (const std::bad_alloc&) {
+        return fail(FK_ERR_OOM, "host allocation failed in symbolic analysis");
+    }
+    if (rc != FK_OK) return fail(rc, t->t.error);
+    *out = t.release();
+    return FK_OK;
+}
+
+void fk_topology_destroy(fk_topology* topo) { delete topo; }
+
+int fk_topology_info_get(const fk_topology* topo, fk_topology_info* info) {
+    if (!topo || !info) return fail(FK_ERR_INVALID, "null argument");
+    topo->t.fill_info(info);
+    return FK_OK;
+}
+
+int fk_topology_symbolic(const fk_topology* topo, uint32_t* aug_colptr, uint32_t* aug_rowidx, int32_t* colamd_perm,
+                         int32_t* etree_parent, uint32_t* r_colptr, uint32_t* r_rowidx) {
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    const fk::Topology& t = topo->t;
+    auto copy = [](auto* dst, const auto& v) {
+        if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    copy(aug_colptr, t.aug_colptr); copy(aug_rowidx, t.aug_rowidx); copy(colamd_perm, t.perm);
+    copy(etree_parent, t.parent); copy(r_colptr, t.r_colptr); copy(r_rowidx, t.r_rowidx);
+    return FK_OK;
+}
+
+int fk_symbolic(const fk_problem* problem, uint32_t* aug_colptr, uint32_t* aug_rowidx, int32_t* colamd_perm,
+                int32_t* etree_parent, uint32_t* r_colptr, uint32_t* r_rowidx) {
+    fk_topology* t = nullptr;
+    int rc = fk_topology_create(problem, &t);
+    if (rc != FK_OK) return rc;
+    rc = fk_topology_symbolic(t, aug_colptr, aug_rowidx, colamd_perm, etree_parent, r_colptr, r_rowidx);
+    fk_topology_destroy(t);
+    return rc;
+}
+
+// ---- device-resident batch plan -----------------------------------------------------------------
+int fk_batch_plan_create(const fk_topology* topo_c, uint32_t capacity, int device, fk_batch_plan** out) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo || !out || capacity == 0) return fail(FK_ERR_INVALID, "null topology / zero capacity");
+    int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    if (topo->t.path == 2)
+        return fail(FK_ERR_TOO_LARGE, "topology needs the global sparse path; use fk_lm_solve");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(FK_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
+    std::unique_ptr<fk_batch_plan> p(new fk_batch_plan());
+    p->topo = topo; p->device = device; p->capacity = capacity;
+    int rc = topo->program_for(device, &p->prog);
+    if (rc != FK_OK) return rc;
+    const fk::Topology& t = topo->t;
+    CU(cudaMalloc(&p->d_vars, sizeof(double) * std::max<size_t>(1, (size_t)capacity * t.n_vars)));
+    CU(cudaMalloc(&p->d_params, sizeof(double) * std::max<size_t>(1, (size_t)capacity * t.n_expr)));
+    CU(cudaMalloc(&p->d_out, sizeof(double) * std::max<size_t>(1, (size_t)capacity * t.n_free)));
+    CU(cudaMalloc(&p->d_rep, sizeof(fk_report) * (size_t)capacity));
+    *out = p.release();
+    return FK_OK;
+}
+
+void fk_batch_plan_destroy(fk_batch_plan* plan) { delete plan; }
+
+int fk_batch_plan_upload(fk_batch_plan* plan, uint32_t n, const double* vars, const double* param, void* stream) {
+    if (!plan || n > plan->capacity || (n && (!vars || (!param && plan->topo->t.n_expr))))
+        return fail(FK_ERR_INVALID, "bad upload arguments");
+    const fk::Topology& t = plan->topo->t;
+    CU(cudaSetDevice(plan->device));
+    plan->n = n;
+    if (n && t.n_vars) CU(cudaMemcpyAsync(plan->d_vars, vars, sizeof(double) * (size_t)n * t.n_vars, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (n && t.n_expr) CU(cudaMemcpyAsync(plan->d_params, param, sizeof(double) * (size_t)n * t.n_expr, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return FK_OK;
+}
+
+int fk_batch_plan_run(fk_batch_plan* plan, void* stream) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    CU(cudaSetDevice(plan->device));
+    int e = fk::launch_batch_lm(*plan->prog, plan->topo->t.tile, plan->n, plan->d_vars, plan->d_params, plan->d_out,
+                                plan->d_rep, stream);
+    if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_lm_kernel");
+    if (plan->n) plan->launches++;
+    return FK_OK;
+}
+
+int fk_batch_plan_download(fk_batch_plan* plan, double* free_out, fk_report* reports, void* stream) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    const fk::Topology& t = plan->topo->t;
+    CU(cudaSetDevice(plan->device));
+    if (free_out && plan->n && t.n_free)
+        CU(cudaMemcpyAsync(free_out, plan->d_out, sizeof(double) * (size_t)plan->n * t.n_free, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (reports && plan->n)
+        CU(cudaMemcpyAsync(reports, plan->d_rep, sizeof(fk_report) * (size_t)plan->n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return FK_OK;
+}
+
+int fk_batch_plan_device_ptrs(fk_batch_plan* plan, void** vars, void** param, void** free_out, void** reports) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    if (vars) *vars = plan->d_vars;
+    if (param) *param = plan->d_params;
+    if (free_out) *free_out = plan->d_out;
+    if (reports) *reports = plan->d_rep;
+    return FK_OK;
+}
+
+uint64_t fk_batch_plan_launches(const fk_batch_plan* plan) { return plan ? plan->launches : 0; }
+
+int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    const fk::Topology& t = plan->topo->t;
+    CU(cudaSetDevice(plan->device));
+    if (!plan->d_er) CU(cudaMalloc(&plan->d_er, sizeof(double) * std::max<size_t>(1, (size_t)plan->capacity * t.n_rows)));
+    if (!plan->d_ej && mode == 0) CU(cudaMalloc(&plan->d_ej, sizeof(double) * std::max<size_t>(1, (size_t)plan->capacity * t.jac_nnz)));
+    int e = fk::launch_batch_eval(*plan->prog, plan->n, plan->d_vars, plan->d_params, plan->d_er, plan->d_ej, mode, stream);
+    if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_eval_kernel");
+    if (plan->n) plan->launches++;
+    return FK_OK;
+}
+
+int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_j, void* stream) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    const fk::Topology& t = plan->topo->t;
+    CU(cudaSetDevice(plan->device));
+    if (out_r && plan->d_er && plan->n)
+        CU(cudaMemcpyAsync(out_r, plan->d_er, sizeof(double) * (size_t)plan->n * t.n_rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (out_j && plan->d_ej && plan->n)
+        CU(cudaMemcpyAsync(out_j, plan->d_ej, sizeof(double) * (size_t)plan->n * t.jac_nnz, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return FK_OK;
+}
+
+void* fk_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void fk_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- host-buffer batch: shard by sketch over the devices, pipeline chunks per device ----------------
+static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars,
+                            const double* param, double* free_out, fk_report* reports, std::string* err) {
+    const fk::Topology& t = topo->t;
+    const uint32_t total = hi - lo;
+    if (total == 0) return FK_OK;
+    const uint32_t kStreams = 3;
+    uint32_t chunk = std::max<uint32_t>(1024, (total + 7) / 8);
+    chunk = std::min(chunk, total);
+    int rc = FK_OK;
+    fk_batch_plan* plans[kStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (uint32_t s = 0; s < kStreams; s++) {
+            if (streams[s]) cudaStreamDestroy(streams[s]);
+            delete plans[s];
+        }
+    };
+    for (uint32_t s = 0; s < kStreams && rc == FK_OK; s++) {
+        rc = fk_batch_plan_create(topo, chunk, device, &plans[s]);
+        if (rc == FK_OK && cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking) != cudaSuccess)
+            rc = fail(FK_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    uint32_t s = 0;
+    for (uint32_t at = lo; at < hi && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
+        uint32_t cnt = std::min(chunk, hi - at);
+        // a plan's buffers are reused only after its previous chunk has fully drained
+        if (cudaStreamSynchronize(streams[s]) != cudaSuccess) { rc = fail(FK_ERR_CUDA, "stream sync failed"); break; }
+        rc = fk_batch_plan_upload(plans[s], cnt, vars + (size_t)at * t.n_vars, param ? param + (size_t)at * t.n_expr : nullptr, streams[s]);
+        if (rc == FK_OK) rc = fk_batch_plan_run(plans[s], streams[s]);
+        if (rc == FK_OK) rc = fk_batch_plan_download(plans[s], free_out + (size_t)at * t.n_free, reports ? reports + at : nullptr, streams[s]);
+    }
+    for (uint32_t k = 0; k < kStreams; k++)
+        if (streams[k] && cudaStreamSynchronize(streams[k]) != cudaSuccess && rc == FK_OK)
+            rc = cuda_fail(cudaGetLastError(), "batch kernel / copy failed");
+    if (rc != FK_OK && err) *err = g_error;
+    cleanup();
+    return rc;
+}
+
+int fk_batch_solve(const fk_topology* topo_c, uint32_t n, const double* vars, const double* param, double* free_out,
+                   fk_report* reports, int n_gpus) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    if (n == 0) return FK_OK;
+    if (!vars || !free_out || (!param && topo->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
+    int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
+    int base = 0;
+    if (const char* d = std::getenv("FK_DEVICE")) base = std::atoi(d);  // one-process-per-GPU launches
+    if (n_gpus == 1) {
+        if (base < 0 || base >= ndev) base = 0;
+        return run_device_range(topo, base, 0, n, vars, param, free_out, reports, nullptr);
+    }
+    std::vector<int> rcs(n_gpus, FK_OK);
+    std::vector<std::string> errs(n_gpus);
+    std::vector<std::thread> pool;
+    for (int g = 0; g < n_gpus; g++) {
+        uint32_t lo = (uint32_t)((uint64_t)n * g / n_gpus), hi = (uint32_t)((uint64_t)n * (g + 1) / n_gpus);
+        pool.emplace_back([=, &rcs, &errs]() { rcs[g] = run_device_range(topo, g, lo, hi, vars, param, free_out, reports, &errs[g]); });
+    }
+    for (auto& th : pool) th.join();
+    for (int g = 0; g < n_gpus; g++)
+        if (rcs[g] != FK_OK) return fail(rcs[g], errs[g]);
+    return FK_OK;
+}
+
+// ---- general entry points ------------------------------------------------------------------------------
+int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* const* free_values, fk_report* reports,
+                      int n_gpus) {
+    if (n == 0) return FK_OK;
+    if (!problems || !free_values) return fail(FK_ERR_INVALID, "null argument");
+    // group by topology: build each problem's topology key, reuse the first topology of a group
+    struct Group {
+        std::unique_ptr<fk_topology, void (*)(fk_topology*)> topo{nullptr, fk_topology_destroy};
+        std::vector<uint32_t> members;
+    };
+    std::vector<Group> groups;
+    std::multimap<uint64_t, size_t> by_sig;
+    for (uint32_t i = 0; i < n; i++) {
+        const fk_problem* p = problems[i];
+        if (!p || !free_values[i]) return fail(FK_ERR_INVALID, "null problem in batch");
+        // cheap structural signature (same mixing as Topology::build would be overkill here)
+        uint64_t sig = 1469598103934665603ull;
+        auto mixb = [&](const void* d, size_t bytes) {
+            const unsigned char* c = (const unsigned char*)d;
+            for (size_t k = 0; k < bytes; k++) sig = (sig ^ c[k]) * 1099511628211ull;
+        };
+        uint32_t hdr[4] = {p->n_vars, p->n_expr, p->n_free, p->n_rows};
+        mixb(hdr, sizeof hdr);
+        if (p->n_expr) { mixb(p->kind, p->n_expr); mixb(p->idx, 16 * (size_t)p->n_expr); }
+        if (p->n_free) mixb(p->free_vars, 4 * (size_t)p->n_free);
+        if (p->n_rows) mixb(p->rows, 4 * (size_t)p->n_rows);
+        size_t gi = SIZE_MAX;
+        auto range = by_sig.equal_range(sig);
+        for (auto it = range.first; it != range.second; ++it) {
+            const fk::Topology& t = groups[it->second].topo->t;
+            if (t.n_vars == p->n_vars && t.n_expr == p->n_expr && t.n_free == p->n_free && t.n_rows == p->n_rows &&
+                (!p->n_expr || (!std::memcmp(t.kind.data(), p->kind, p->n_expr) && !std::memcmp(t.idx.data(), p->idx, 16 * (size_t)p->n_expr))) &&
+                (!p->n_free || !std::memcmp(t.free_vars.data(), p->free_vars, 4 * (size_t)p->n_free)) &&
+                (!p->n_rows || !std::memcmp(t.rows.data(), p->rows, 4 * (size_t)p->n_rows))) {
+                gi = it->second;
+                break;
+            }
+        }
+        if (gi == SIZE_MAX) {
+            fk_topology* t = nullptr;
+            int rc = fk_topology_create(p, &t);
+            if (rc != FK_OK) return rc;
+            groups.emplace_back();
+            groups.back().topo.reset(t);
+            gi = groups.size() - 1;
+            by_sig.emplace(sig, gi);
+        }
+        groups[gi].members.push_back(i);
+    }
+    for (Group& gr : groups) {
+        const fk::Topology& t = gr.topo->t;
+        const size_t cnt = gr.members.size();
+        if (t.path == 2) return fail(FK_ERR_TOO_LARGE, "problem needs the global sparse path, which fk_lm_solve_batch does not take");
+        std::vector<double> vars(cnt * t.n_vars), param(cnt * std::max<uint32_t>(t.n_expr, 1)), out(cnt * std::max<uint32_t>(t.n_free, 1));
+        std::vector<fk_report> reps(cnt);
+        for (size_t k = 0; k < cnt; k++) {
+            const fk_problem* p = problems[gr.members[k]];
+            if (t.n_vars) std::memcpy(&vars[k * t.n_vars], p->vars, sizeof(double) * t.n_vars);
+            for (uint32_t f = 0; f < t.n_free; f++) vars[k * t.n_vars + t.free_vars[f]] = free_values[gr.members[k]][f];
+            if (t.n_expr) {
+                if (p->param) std::memcpy(&param[k * t.n_expr], p->param, sizeof(double) * t.n_expr);
+                else std::fill(param.begin() + k * t.n_expr, param.begin() + (k + 1) * t.n_expr, 0.0);
+            }
+        }
+        int rc = fk_batch_solve(gr.topo.get(), (uint32_t)cnt, vars.data(), param.data(), out.data(), reps.data(), n_gpus);
+        if (rc != FK_OK) return rc;
+        for (size_t k = 0; k < cnt; k++) {
+            std::memcpy(free_values[gr.members[k]], &out[k * t.n_free], sizeof(double) * t.n_free);
+            if (reports) reports[gr.members[k]] = reps[k];
+        }
+    }
+    return FK_OK;
+}
+
+int fk_lm_solve(const fk_problem* problem, double* free_values, fk_report* report) {
+    const fk_problem* ps[1] = {problem};
+    double* fv[1] = {free_values};
+    return fk_lm_solve_batch(1, ps, fv, report, 1);
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// Batched Levenberg–Marquardt on sm_100a: K1 (residual + Jacobian into a precomputed pattern),
+// K2 (residual only), K3 (H = JᵀJ + lambda I, g = Jᵀ(-r) through contribution lists, no atomics)
+// and K4 (the whole LM loop with an LDLᵀ factorisation in shared memory) — SURVEY §2 "new
+// kernels".  Control flow follows fiksi/src/solve/lm.rs:21-193 line by line; the
+// linear solve is the normal-equation form north_star asks for instead of the reference's sparse
+// Householder QR of [J; sqrt(lambda) I] (solvi/src/decomposition/sparse/qr.rs:281-356).
+//
+// Compiled with -fmad=false: every a*b+c below is two roundings unless it is an explicit fma().
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+
+#include "expressions.cuh"
+#include "lm_kernels.cuh"
+
+namespace fk {
+
+template <int TILE>
+struct TileOps {
+    static constexpr bool kWholeCta = TILE > 32;
+    __device__ static __forceinline__ unsigned mask() {
+        if constexpr (TILE >= 32) {
+            return 0xFFFFFFFFu;
+        } else {
+            const unsigned lane_in_warp = threadIdx.x & 31u;
+            return ((1u << TILE) - 1u) << (lane_in_warp & ~(unsigned)(TILE - 1));
+        }
+    }
+    __device__ static __forceinline__ void sync(unsigned m) {
+        if (kWholeCta) __syncthreads();
+        else __syncwarp(m);
+    }
+};
+
+// Evaluate all rows of one sketch with the lanes of a tile.  `xfree` holds the current free
+// values (shared memory); fixed variables come from the sketch's `vars` in global memory
+// (fiksi/src/variable_map.rs:57-72).  == Subsystem::calculate_residuals_and_sparse_jacobian,
+// fiksi/src/subsystem.rs:126-166, writing straight into the CSC slots that
+// SparseColMat::from_triplet_mat would produce (duplicates of a column inside one row are summed).
+template <int TILE, bool WITH_JACOBIAN>
+__device__ __forceinline__ void eval_tile(const DevProgram& P, int lane, const double* xfree,
+                                          const double* __restrict__ vars, const double* __restrict__ params,
+                                          double* rdst, double* jdst) {
+    for (uint32_t row = lane; row < P.m; row += TILE) {
+        const int kind = __ldg(P.row_kind + row);
+        const int a = dev::arity_of(kind);
+        double v[8], g[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            v[s] = 0.0;
+            if (s < a) {
+                const int32_t c = __ldg(P.slot_col + row * 8 + s);
+                v[s] = c >= 0 ? xfree[c] : __ldg(vars + __ldg(P.slot_var + row * 8 + s));
+            }
+        }
+        const double param = __ldg(params + __ldg(P.row_expr + row));
+        rdst[row] = dev::eval_expression(kind, v, param, g);
+        if (WITH_JACOBIAN) {
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                if (s < a) {
+                    const int32_t pos = __ldg(P.slot_pos + row * 8 + s);
+                    if (pos >= 0) {
+                        if (__ldg(P.slot_dup + row * 8 + s)) jdst[pos] += g[s];
+                        else jdst[pos] = g[s];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Sequential left-to-right sum of squares, as fiksi/src/solve/lm.rs:195-197 (every lane computes
+// the same value, which keeps the LM control flow uniform across the tile without a broadcast).
+__device__ __forceinline__ double sum_squares_seq(const double* v, uint32_t n) {
+    double s = 0.0;
+    for (uint32_t i = 0; i < n; i++) s += v[i] * v[i];
+    return s;
+}
+
+// K3: H0 = JᵀJ in L storage (permuted, lower) and g = Jᵀ rneg (permuted).  Each output entry is
+// the sum of its precomputed contribution list in row order: a segmented reduction, no atomics.
+template <int TILE>
+__device__ __forceinline__ void assemble_tile(const DevProgram& P, int lane, const double* J,
+                                              const double* rneg, double* H0, double* g) {
+    for (uint32_t p = lane; p < P.lnnz; p += TILE) {
+        const uint32_t b = __ldg(P.h_ptr + p), e = __ldg(P.h_ptr + p + 1);
+        double s = 0.0;
+        for (uint32_t q = b; q < e; q++) s = fma(J[__ldg(P.h_pairs + 2 * q)], J[__ldg(P.h_pairs + 2 * q + 1)], s);
+        H0[p] = s;
+    }
+    for (uint32_t k = lane; k < P.n; k += TILE) {
+        const uint32_t b = __ldg(P.g_ptr + k), e = __ldg(P.g_ptr + k + 1);
+        double s = 0.0;
+        for (uint32_t q = b; q < e; q++) s = fma(J[__ldg(P.g_pairs + 2 * q)], rneg[__ldg(P.g_pairs + 2 * q + 1)], s);
+        g[k] = s;
+    }
+}
+
+// LDLᵀ of work (= H0 + lam2 I) in place: column k keeps the unscaled entries (L D)(i,k); invd[k]
+// = 1/D(k).  Right-looking, one tile-wide step per column.  Returns 0 ok, 1 non-positive pivot,
+// 2 NaN pivot.
+template <int TILE>
+__device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsigned msk, double* work, double* invd) {
+    for (uint32_t k = 0; k < P.n; k++) {
+        const double d = work[__ldg(P.l_colptr + k)];
+        if (d != d) return 2;
+        if (!(d > 0.0) || d == INFINITY) return 1;
+        const double inv = 1.0 / d;
+        if (lane == 0) invd[k] = inv;
+        const uint32_t b = __ldg(P.u_ptr + k), e = __ldg(P.u_ptr + k + 1);
+        for (uint32_t t = b + lane; t < e; t += TILE) {
+            const uint32_t dst = __ldg(P.u_trip + 3 * t), ia = __ldg(P.u_trip + 3 * t + 1), ib = __ldg(P.u_trip + 3 * t + 2);
+            work[dst] = fma(-(work[ia] * inv), work[ib], work[dst]);
+        }
+        TileOps<TILE>::sync(msk);
+    }
+    return 0;
+}
+
+// Solve (L D Lᵀ) z = g; w holds g on entry (permuted order) and z on return.
+template <int TILE>
+__device__ __forceinline__ void solve_tile(const DevProgram& P, int lane, unsigned msk, const double* work,
+                                           const double* invd, double* w) {
+    // forward: unit lower triangular L' = (L D) D^-1, column oriented
+    for (uint32_t k = 0; k < P.n; k++) {
+        const double t = w[k] * invd[k];
+        const uint32_t b = __ldg(P.l_colptr + k) + 1, e = __ldg(P.l_colptr + k + 1);
+        for (uint32_t q = b + lane; q < e; q += TILE) {
+            const uint32_t i = __ldg(P.l_rowidx + q);
+            w[i] = fma(-work[q], t, w[i]);
+        }
+        TileOps<TILE>::sync(msk);
+    }
+    for (uint32_t k = lane; k < P.n; k += TILE) w[k] *= invd[k];
+    TileOps<TILE>::sync(msk);
+    // backward: L'ᵀ, column oriented over the columns of R = Lᵀ (diagonal is the last entry)
+    for (uint32_t kk = P.n; kk-- > 0;) {
+        const double zk = w[kk];
+        const uint32_t b = __ldg(P.r_colptr + kk), e = __ldg(P.r_colptr + kk + 1) - 1;
+        for (uint32_t q = b + lane; q < e; q += TILE) {
+            const uint32_t j = __ldg(P.r_rowidx + q);
+            w[j] = fma(-(work[__ldg(P.r_lpos + q)] * invd[j]), zk, w[j]);
+        }
+        TileOps<TILE>::sync(msk);
+    }
+}
+
+__device__ __forceinline__ uint64_t trace_push(uint64_t h, uint32_t code) { return h * 3ull + code + 1ull; }
+
+template <int TILE>
+__global__ void __launch_bounds__(TILE > 128 ? TILE : 128)
+fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doubles,
+                   const double* __restrict__ vars_all, const double* __restrict__ params_all,
+                   double* __restrict__ free_out, fk_report* __restrict__ reports) {
+    extern __shared__ double smem[];
+    const int tiles_per_cta = blockDim.x / TILE;
+    const int tile_id = threadIdx.x / TILE;
+    const int lane = threadIdx.x % TILE;
+    const uint32_t sketch = blockIdx.x * tiles_per_cta + tile_id;
+    if (sketch >= n_sketches) return;
+    const unsigned msk = TileOps<TILE>::mask();
+    const uint32_t n = P.n, m = P.m;
+
+    double* x = smem + (size_t)tile_id * stride_doubles;
+    double* xs = x + n;
+    double* g = xs + n;
+    double* w = g + n;
+    double* invd = w + n;
+    double* rneg = invd + n;
+    double* rs = rneg + m;
+    double* H0 = rs + m;
+    double* work = H0 + P.lnnz;
+
+    const double* vars = vars_all + (size_t)sketch * P.n_vars;
+    const double* params = params_all + (size_t)sketch * P.n_expr;
+
+    for (uint32_t i = lane; i < n; i += TILE) x[i] = __ldg(vars + __ldg(P.free_vars + i));
+    TileOps<TILE>::sync(msk);
+
+    // lm.rs:80-106: initial residuals + Jacobian, r := -r, ssr
+    eval_tile<TILE, true>(P, lane, x, vars, params, rs, work);
+    TileOps<TILE>::sync(msk);
+    double ssr = sum_squares_seq(rs, m);
+    for (uint32_t i = lane; i < m; i += TILE) rneg[i] = -rs[i];
+    TileOps<TILE>::sync(msk);
+    assemble_tile<TILE>(P, lane, work, rneg, H0, g);
+    TileOps<TILE>::sync(msk);
+
+    double lambda = 0.5;  // lm.rs:108
+    uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
+    uint64_t trace = 0;
+    bool done = false;
+
+    for (int outer = 0; outer < 100 && !done; outer++) {  // lm.rs:109
+        if (ssr < 1e-8) {                                   // lm.rs:110-112
+            exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+            break;
+        }
+        outer_iters++;
+        for (;;) {  // lm.rs:115, unbounded in the reference
+            if (!isfinite(lambda)) {
+                exit_reason = FK_EXIT_LAMBDA_OVERFLOW;
+                done = true;
+                break;
+            }
+            // lm.rs:119-125: the damping entries are sqrt(lambda); their square lands on diag(H)
+            const double sl = sqrt(lambda);
+            const double lam2 = sl * sl;
+            for (uint32_t p = lane; p < P.lnnz; p += TILE) work[p] = H0[p];
+            TileOps<TILE>::sync(msk);
+            for (uint32_t k = lane; k < n; k += TILE) work[__ldg(P.l_colptr + k)] += lam2;
+            TileOps<TILE>::sync(msk);
+
+            const int fstat = factor_tile<TILE>(P, lane, msk, work, invd);  // replaces lm.rs:128
+            factorizations++;
+            if (fstat == 1) {  // lm.rs:134-137 (`!solved`)
+                lambda *= 8.0;
+                trace = trace_push(trace, 0);
+                TileOps<TILE>::sync(msk);
+                continue;
+            }
+            double ssr_s = NAN;
+            if (fstat == 0) {
+                for (uint32_t k = lane; k < n; k += TILE) w[k] = g[k];
+                TileOps<TILE>::sync(msk);
+                solve_tile<TILE>(P, lane, msk, work, invd, w);  // replaces lm.rs:130-132
+                // delta back in variable order (P_c z, qr.rs:354), parked in xs
+                for (uint32_t k = lane; k < n; k += TILE) xs[__ldg(P.perm + k)] = w[k];
+                TileOps<TILE>::sync(msk);
+                if (sum_squares_seq(xs, n) < 1e-12) {  // lm.rs:139-142
+                    exit_reason = FK_EXIT_SMALL_STEP;
+                    done = true;
+                    break;
+                }
+                TileOps<TILE>::sync(msk);
+                for (uint32_t i = lane; i < n; i += TILE) xs[i] = x[i] + xs[i];  // lm.rs:144-146
+                TileOps<TILE>::sync(msk);
+                // lm.rs:148-149 (+ the Jacobian the accept branch would recompute at lm.rs:173-185)
+                eval_tile<TILE, true>(P, lane, xs, vars, params, rs, work);
+                TileOps<TILE>::sync(msk);
+                ssr_s = sum_squares_seq(rs, m);
+            }
+            if (ssr_s < ssr) {  // lm.rs:151 (strict; NaN rejects)
+                lambda *= 0.125;
+                if (lambda < 1e-50) lambda = 1e-50;
+                accepted++;
+                trace = trace_push(trace, 1);
+                for (uint32_t i = lane; i < n; i += TILE) x[i] = xs[i];
+                if ((ssr - ssr_s) / ssr <= 1e-6) {  // lm.rs:164-168
+                    ssr = ssr_s;
+                    exit_reason = FK_EXIT_STALLED;
+                    done = true;
+                    TileOps<TILE>::sync(msk);
+                    break;
+                }
+                ssr = ssr_s;
+                for (uint32_t i = lane; i < m; i += TILE) rneg[i] = -rs[i];
+                TileOps<TILE>::sync(msk);
+                assemble_tile<TILE>(P, lane, work, rneg, H0, g);
+                TileOps<TILE>::sync(msk);
+                break;
+            } else {  // lm.rs:187-190
+                lambda *= 2.0;
+                trace = trace_push(trace, 2);
+                TileOps<TILE>::sync(msk);
+            }
+        }
+    }
+
+    TileOps<TILE>::sync(msk);
+    double* out = free_out + (size_t)sketch * n;
+    for (uint32_t i = lane; i < n; i += TILE) out[i] = x[i];
+    if (lane == 0) {
+        fk_report rep;
+        rep.exit_reason = exit_reason;
+        rep.outer_iters = outer_iters;
+        rep.factorizations = factorizations;
+        rep.accepted = accepted;
+        rep.ssr = ssr;
+        rep.lambda = lambda;
+        rep.trace_hash = trace;
+        reports[sketch] = rep;
+    }
+}
+
+// K1 / K2 on their own: one thread per (sketch, row), used for the assembly-bandwidth metric and
+// for per-entry parity tests.  mode 0: residual + Jacobian, mode 1: residual only.
+template <bool WITH_JACOBIAN>
+__global__ void __launch_bounds__(256)
+fk_batch_eval_kernel(const DevProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
+                     const double* __restrict__ params_all, double* __restrict__ out_r, double* __restrict__ out_j) {
+    const uint64_t total = (uint64_t)n_sketches * P.m;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t sketch = (uint32_t)(t / P.m), row = (uint32_t)(t % P.m);
+        const double* vars = vars_all + (size_t)sketch * P.n_vars;
+        const int kind = __ldg(P.row_kind + row);
+        const int a = dev::arity_of(kind);
+        double v[8], g[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) v[s] = s < a ? __ldg(vars + __ldg(P.slot_var + row * 8 + s)) : 0.0;
+        const double param = __ldg(params_all + (size_t)sketch * P.n_expr + __ldg(P.row_expr + row));
+        out_r[(size_t)sketch * P.m + row] = dev::eval_expression(kind, v, param, g);
+        if (WITH_JACOBIAN) {
+            double* jdst = out_j + (size_t)sketch * P.jnnz;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                if (s < a) {
+                    const int32_t pos = __ldg(P.slot_pos + row * 8 + s);
+                    if (pos >= 0) {
+                        if (__ldg(P.slot_dup + row * 8 + s)) jdst[pos] += g[s];
+                        else jdst[pos] = g[s];
+                    }
+                }
+            }
+        }
+    }
+}
+
+const char* lm_kernel_name() { return "fk_batch_lm_kernel"; }
+
+template <int TILE>
+static int launch_lm_t(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
+                       double* free_out, fk_report* reports, cudaStream_t stream) {
+    const uint32_t stride = lm_smem_doubles(prog.n, prog.m, prog.jnnz, prog.lnnz);
+    const size_t bytes_per_sketch = (size_t)stride * sizeof(double);
+    int tiles_per_cta;
+    if (TILE > 32) {
+        tiles_per_cta = 1;
+    } else {
+        tiles_per_cta = 128 / TILE;
+        const size_t budget = 64 * 1024;  // keep several CTAs resident per SM
+        while (tiles_per_cta > 1 && bytes_per_sketch * tiles_per_cta > budget) tiles_per_cta >>= 1;
+    }
+    const size_t smem = bytes_per_sketch * tiles_per_cta;
+    cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const uint32_t grid = (n_sketches + tiles_per_cta - 1) / tiles_per_cta;
+    fk_batch_lm_kernel<TILE><<<grid, TILE * tiles_per_cta, smem, stream>>>(prog, n_sketches, stride, vars, params, free_out, reports);
+    return (int)cudaGetLastError();
+}
+
+int launch_batch_lm(const DevProgram& prog, uint32_t tile, uint32_t n_sketches, const double* vars,
+                    const double* params, double* free_out, fk_report* reports, void* stream) {
+    if (n_sketches == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (tile) {
+        case 8: return launch_lm_t<8>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 16: return launch_lm_t<16>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 32: return launch_lm_t<32>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 256: return launch_lm_t<256>(prog, n_sketches, vars, params, free_out, reports, s);
+        default: return (int)cudaErrorInvalidValue;
+    }
+}
+
+int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
+                      double* out_r, double* out_j, int mode, void* stream) {
+    if (n_sketches == 0 || prog.m == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t total = (uint64_t)n_sketches * prog.m;
+    uint64_t blocks = (total + 255) / 256;
+    const uint64_t cap = 148ull * 8 * 4;  // a few waves of resident CTAs, grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    if (mode == 0) fk_batch_eval_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(prog, n_sketches, vars, params, out_r, out_j);
+    else fk_batch_eval_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(prog, n_sketches, vars, params, out_r, out_j);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fk

@@ -1,0 +1,317 @@
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "colamd_order.hpp"
+
+namespace fk {
+
+int expand_slots(uint8_t kind, const uint32_t idx[4], uint32_t out[8]) {
+    // Layout per kind: which stored index each slot comes from and whether it is the +1 (y) half.
+    // 'p' = point (two slots), 'v' = single variable.  expressions.rs:48-182.
+    static const char* shape[FK_NUM_KINDS] = {"vv", "pp", "ppp", "ppp", "ppp", "ppv", "pppp", "pppp", "pppp", "pppp", "pppv"};
+    if (kind >= FK_NUM_KINDS) return -1;
+    int n = 0;
+    for (int k = 0; shape[kind][k]; k++) {
+        out[n++] = idx[k];
+        if (shape[kind][k] == 'p') out[n++] = idx[k] + 1;
+    }
+    return n;
+}
+
+static uint64_t mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    return h ^ (h >> 33);
+}
+
+int Topology::build(const fk_problem& p) {
+    if ((p.n_expr && (!p.kind || !p.idx)) || (p.n_free && !p.free_vars) || (p.n_rows && !p.rows)) {
+        error = "null array in fk_problem";
+        return FK_ERR_INVALID;
+    }
+    n_vars = p.n_vars; n_expr = p.n_expr; n_free = p.n_free; n_rows = p.n_rows;
+    kind.assign(p.kind, p.kind + n_expr);
+    idx.assign(p.idx, p.idx + 4 * (size_t)n_expr);
+    free_vars.assign(p.free_vars, p.free_vars + n_free);
+    rows.assign(p.rows, p.rows + n_rows);
+
+    signature = mix(mix(mix(0x1234, n_vars), n_free), n_rows);
+    for (uint32_t r : rows) {
+        if (r >= n_expr) { error = "row references an expression out of range"; return FK_ERR_INVALID; }
+        signature = mix(signature, kind[r]);
+        for (int q = 0; q < 4; q++) signature = mix(signature, idx[4 * (size_t)r + q]);
+    }
+    for (uint32_t v : free_vars) signature = mix(signature, v);
+
+    // free-column lookup: rank in free_vars == IndexSet index (subsystem.rs:35,66-68)
+    std::vector<int32_t> var_to_free(n_vars, -1);
+    for (uint32_t k = 0; k < n_free; k++) {
+        uint32_t v = free_vars[k];
+        if (v >= n_vars) { error = "free variable out of range"; return FK_ERR_INVALID; }
+        if (var_to_free[v] >= 0) { error = "duplicate free variable"; return FK_ERR_INVALID; }
+        var_to_free[v] = (int32_t)k;
+    }
+
+    // ---- slot tables ------------------------------------------------------------------------
+    const uint32_t m = n_rows, n = n_free;
+    row_kind.resize(m); row_expr.resize(m);
+    slot_var.assign((size_t)m * 8, 0); slot_col.assign((size_t)m * 8, -2);
+    slot_pos.assign((size_t)m * 8, -1); slot_dup.assign((size_t)m * 8, 0);
+    std::vector<uint32_t> col_count(n + 1, 0);
+    eval_bytes = 0;
+    static const int stored_idx[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
+    for (uint32_t r = 0; r < m; r++) {
+        uint32_t e = rows[r];
+        uint8_t kd = kind[e];
+        uint32_t sv[8];
+        int a = expand_slots(kd, &idx[4 * (size_t)e], sv);
+        if (a < 0) { error = "unknown expression kind"; return FK_ERR_INVALID; }
+        row_kind[r] = kd; row_expr[r] = e;
+        int f = 0;
+        for (int s = 0; s < a; s++) {
+            if (sv[s] >= n_vars) { error = "expression references a variable out of range"; return FK_ERR_INVALID; }
+            slot_var[(size_t)r * 8 + s] = sv[s];
+            int32_t c = var_to_free[sv[s]];
+            slot_col[(size_t)r * 8 + s] = c;
+            if (c < 0) continue;
+            f++;
+            bool dup = false;
+            for (int t = 0; t < s; t++) dup |= slot_col[(size_t)r * 8 + t] == c;
+            slot_dup[(size_t)r * 8 + s] = dup;
+            if (!dup) col_count[c]++;
+        }
+        // kind + stored indices + param + gathered vars + scatter slots + r + J
+        eval_bytes += 1 + 4 * stored_idx[kd] + 8 + 8 * a + 4 * f + 8 + 8 * f;
+    }
+
+    // ---- augmented CSC pattern ----------------------------------------------------------------
+    aug_colptr.assign(n + 1, 0);
+    for (uint32_t c = 0; c < n; c++) aug_colptr[c + 1] = aug_colptr[c] + col_count[c] + 1;
+    aug_rowidx.assign(aug_colptr[n], 0);
+    jac_nnz = aug_colptr[n] - n;
+    {
+        std::vector<uint32_t> fill(aug_colptr.begin(), aug_colptr.begin() + n);
+        for (uint32_t r = 0; r < m; r++)        // rows ascending -> every column list ends up sorted
+            for (int s = 0; s < 8; s++) {
+                int32_t c = slot_col[(size_t)r * 8 + s];
+                if (c < 0 || slot_dup[(size_t)r * 8 + s]) continue;
+                aug_rowidx[fill[c]++] = r;
+            }
+        for (uint32_t c = 0; c < n; c++) aug_rowidx[fill[c]] = m + c;  // damping row last
+        // Jacobian value position of a slot = CSC position with the damping entries squeezed out
+        std::vector<uint32_t> cursor(n);
+        for (uint32_t c = 0; c < n; c++) cursor[c] = aug_colptr[c] - c;
+        for (uint32_t r = 0; r < m; r++) {
+            for (int s = 0; s < 8; s++) {
+                int32_t c = slot_col[(size_t)r * 8 + s];
+                if (c < 0) continue;
+                if (!slot_dup[(size_t)r * 8 + s]) {
+                    slot_pos[(size_t)r * 8 + s] = (int32_t)cursor[c]++;
+                } else {
+                    for (int t = 0; t < s; t++)
+                        if (slot_col[(size_t)r * 8 + t] == c) { slot_pos[(size_t)r * 8 + s] = slot_pos[(size_t)r * 8 + t]; break; }
+                }
+            }
+        }
+    }
+
+    // ---- fill-reducing ordering -----------------------------------------------------------------
+    perm = ColamdOrder::order((int)(m + n), (int)n, aug_colptr.data(), aug_rowidx.data());
+    iperm.assign(n, 0);
+    for (uint32_t k = 0; k < n; k++) iperm[perm[k]] = (int32_t)k;
+
+    // ---- column elimination tree of A*P (tree of (AP)ᵀ(AP), never formed) -------------------------
+    // Liu's algorithm with path compression; `last_col[i]` links row i to the previous column that
+    // held it, which is all of the product's structure that matters.
+    parent.assign(n, -1);
+    std::vector<int32_t> first_col(m + n, -1);
+    {
+        std::vector<int32_t> anc(n, -1), last_col(m + n, -1);
+        for (uint32_t j = 0; j < n; j++) {
+            uint32_t src = (uint32_t)perm[j];
+            for (uint32_t q = aug_colptr[src]; q < aug_colptr[src + 1]; q++) {
+                uint32_t i = aug_rowidx[q];
+                if (first_col[i] < 0) first_col[i] = (int32_t)j;
+                for (int32_t k = last_col[i]; k != -1 && k < (int32_t)j;) {
+                    int32_t up = anc[k];
+                    anc[k] = (int32_t)j;
+                    if (up == -1) parent[k] = (int32_t)j;
+                    k = up;
+                }
+                last_col[i] = (int32_t)j;
+            }
+        }
+    }
+    {
+        std::vector<uint32_t> depth(n, 0);
+        etree_height = n ? 1 : 0;
+        for (uint32_t jj = n; jj-- > 0;) {  // parents have larger indices
+            if (parent[jj] >= 0) depth[jj] = depth[parent[jj]] + 1;
+            etree_height = std::max(etree_height, depth[jj] + 1);
+        }
+    }
+
+    // ---- pattern of R = Lᵀ: union of row subtrees (columns of A*P walked up the tree) ------------
+    r_colptr.assign(n + 1, 0);
+    r_rowidx.clear();
+    {
+        std::vector<int32_t> mark(n, -1);
+        std::vector<uint32_t> col;
+        for (uint32_t j = 0; j < n; j++) {
+            col.clear();
+            mark[j] = (int32_t)j;
+            uint32_t src = (uint32_t)perm[j];
+            for (uint32_t q = aug_colptr[src]; q < aug_colptr[src + 1]; q++) {
+                for (int32_t k = first_col[aug_rowidx[q]]; k != -1 && k < (int32_t)j && mark[k] != (int32_t)j; k = parent[k]) {
+                    mark[k] = (int32_t)j;
+                    col.push_back((uint32_t)k);
+                }
+            }
+            std::sort(col.begin(), col.end());
+            r_rowidx.insert(r_rowidx.end(), col.begin(), col.end());
+            r_rowidx.push_back(j);
+            r_colptr[j + 1] = (uint32_t)r_rowidx.size();
+        }
+    }
+    const uint32_t lnnz = (uint32_t)r_rowidx.size();
+
+    // ---- L in CSC (transpose of R): diagonal first, then ascending rows ---------------------------
+    l_colptr.assign(n + 1, 0);
+    for (uint32_t q = 0; q < lnnz; q++) l_colptr[r_rowidx[q] + 1]++;
+    for (uint32_t k = 0; k < n; k++) l_colptr[k + 1] += l_colptr[k];
+    l_rowidx.assign(lnnz, 0);
+    r_lpos.assign(lnnz, 0);
+    {
+        std::vector<uint32_t> fill(l_colptr.begin(), l_colptr.begin() + n);
+        for (uint32_t k = 0; k < n; k++) l_rowidx[fill[k]++] = k;  // diagonal
+        for (uint32_t j = 0; j < n; j++)
+            for (uint32_t q = r_colptr[j]; q < r_colptr[j + 1]; q++) {
+                uint32_t i = r_rowidx[q];  // R(i, j) == L(j, i)
+                if (i == j) { r_lpos[q] = l_colptr[j]; continue; }
+                r_lpos[q] = fill[i];
+                l_rowidx[fill[i]++] = j;
+            }
+    }
+    chol_flops = 0;
+    uint64_t n_updates = 0;
+    max_col_updates = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        uint64_t c = l_colptr[k + 1] - l_colptr[k];
+        chol_flops += c * c;
+        uint64_t u = (c - 1) * c / 2;
+        n_updates += u;
+        max_col_updates = std::max<uint32_t>(max_col_updates, (uint32_t)std::min<uint64_t>(u, 0xFFFFFFFFu));
+    }
+
+    // ---- path selection -----------------------------------------------------------------------------
+    {
+        uint64_t work = std::max<uint64_t>(jac_nnz, lnnz);
+        uint64_t dbl = 5ull * n + 2ull * m + lnnz + work;  // == lm_smem_doubles()
+        uint64_t bytes = dbl * 8;
+        smem_bytes = (uint32_t)std::min<uint64_t>(bytes, 0xFFFFFFFFu);
+        uint32_t w = std::max(m, n);
+        if (bytes <= 24 * 1024 && n_updates < (1u << 22)) {
+            path = 0;
+            tile = w <= 10 ? 8 : (w <= 20 ? 16 : 32);
+        } else if (bytes <= 200 * 1024 && n_updates < (1u << 25)) {
+            path = 1;
+            tile = 256;
+        } else {
+            path = 2;
+            tile = 0;
+        }
+        if (const char* t = std::getenv("FK_TILE")) {
+            int v = std::atoi(t);
+            if (path == 0 && (v == 8 || v == 16 || v == 32)) tile = (uint32_t)v;
+        }
+    }
+
+    // ---- contribution lists of H = JᵀJ in L storage, and of g = Jᵀ(-r) ----------------------------------
+    auto l_find = [&](uint32_t row, uint32_t col) -> int64_t {  // position of L(row, col), row >= col
+        const uint32_t* b = l_rowidx.data() + l_colptr[col] + 1;
+        const uint32_t* e = l_rowidx.data() + l_colptr[col + 1];
+        if (row == col) return l_colptr[col];
+        const uint32_t* it = std::lower_bound(b, e, row);
+        return (it != e && *it == row) ? (int64_t)(it - l_rowidx.data()) : -1;
+    };
+    h_ptr.assign((size_t)lnnz + 1, 0);
+    for (int pass = 0; pass < 2; pass++) {
+        std::vector<uint32_t> fill;
+        if (pass == 1) {
+            for (uint32_t q = 0; q < lnnz; q++) h_ptr[q + 1] += h_ptr[q];
+            h_pairs.assign(2 * (size_t)h_ptr[lnnz], 0);
+            fill.assign(h_ptr.begin(), h_ptr.begin() + lnnz);
+        }
+        for (uint32_t r = 0; r < m; r++) {
+            int32_t cs[8], ps[8];
+            int cnt = 0;
+            for (int s = 0; s < 8; s++) {
+                int32_t c = slot_col[(size_t)r * 8 + s];
+                if (c < 0 || slot_dup[(size_t)r * 8 + s]) continue;
+                cs[cnt] = iperm[c];
+                ps[cnt++] = slot_pos[(size_t)r * 8 + s];
+            }
+            for (int a = 0; a < cnt; a++)
+                for (int b = 0; b <= a; b++) {
+                    uint32_t hi = (uint32_t)std::max(cs[a], cs[b]), lo = (uint32_t)std::min(cs[a], cs[b]);
+                    int64_t pos = l_find(hi, lo);
+                    if (pos < 0) { error = "internal: JtJ entry outside the L pattern"; return FK_ERR_INTERNAL; }
+                    if (pass == 0) h_ptr[pos + 1]++;
+                    else {
+                        h_pairs[2 * (size_t)fill[pos]] = (uint32_t)ps[a];
+                        h_pairs[2 * (size_t)fill[pos] + 1] = (uint32_t)ps[b];
+                        fill[pos]++;
+                    }
+                }
+        }
+    }
+    g_ptr.assign(n + 1, 0);
+    g_pairs.clear();
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t c = (uint32_t)perm[k];
+        uint32_t jp = aug_colptr[c] - c;
+        for (uint32_t q = aug_colptr[c]; q + 1 < aug_colptr[c + 1]; q++, jp++) {
+            g_pairs.push_back(jp);
+            g_pairs.push_back(aug_rowidx[q]);
+        }
+        g_ptr[k + 1] = (uint32_t)(g_pairs.size() / 2);
+    }
+
+    // ---- LDLᵀ update schedule (shared-memory paths only) ------------------------------------------
+    u_ptr.assign(n + 1, 0);
+    u_trip.clear();
+    if (path != 2) {
+        u_trip.reserve(3 * (size_t)n_updates);
+        for (uint32_t k = 0; k < n; k++) {
+            uint32_t b0 = l_colptr[k] + 1, e0 = l_colptr[k + 1];
+            for (uint32_t qb = b0; qb < e0; qb++) {       // column j = row of entry qb
+                uint32_t j = l_rowidx[qb];
+                for (uint32_t qa = qb; qa < e0; qa++) {   // rows i >= j
+                    int64_t dst = l_find(l_rowidx[qa], j);
+                    if (dst < 0) { error = "internal: fill outside the L pattern"; return FK_ERR_INTERNAL; }
+                    u_trip.push_back((uint32_t)dst);
+                    u_trip.push_back(qa);
+                    u_trip.push_back(qb);
+                }
+            }
+            u_ptr[k + 1] = (uint32_t)(u_trip.size() / 3);
+        }
+    }
+    return FK_OK;
+}
+
+void Topology::fill_info(fk_topology_info* info) const {
+    std::memset(info, 0, sizeof(*info));
+    info->n_vars = n_vars; info->n_expr = n_expr; info->n_free = n_free; info->n_rows = n_rows;
+    info->jac_nnz = jac_nnz;
+    info->aug_nnz = jac_nnz + n_free;
+    info->r_nnz = (uint32_t)r_rowidx.size();
+    info->etree_height = etree_height;
+    info->path = path; info->tile = tile; info->smem_bytes = smem_bytes;
+    info->chol_flops = chol_flops;
+}
+
+}  // namespace fk

@@ -1,0 +1,81 @@
+// Host-side symbolic pipeline of the product: everything that depends only on the topology of a
+// flattened problem (kinds, indices, free set, row list) and is therefore computed once and
+// reused by every Levenberg–Marquardt iteration of every sketch with that topology.
+//
+// Replaces, per LM call in the reference:
+//   Subsystem slot lookups            fiksi/src/subsystem.rs:126-166, variable_map.rs:57-72
+//   SparseColMat::from_triplet_mat    solvi/src/sparse_col_mat.rs:690-737   (CSC pattern, per step!)
+//   colamd_rs::colamd                 colamd_rs/src/colamd.rs:354-494
+//   permute_columns / elimination_tree / CholeskyStructure
+//                                     solvi/src/sparse_col_mat.rs:456-502,
+//                                     solvi/src/decomposition/sparse/cholesky.rs:31-84,359-595
+// and adds what the normal-equation formulation needs (reference has no counterpart): the
+// contribution lists of H = JᵀJ, the LDLᵀ update schedule and the triangular-solve schedules.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fiksi_b200.h"
+
+namespace fk {
+
+// Number of variable slots per expression kind (fiksi/src/constraints/expressions.rs:48-182).
+inline int kind_arity(uint8_t kind) {
+    static const int a[FK_NUM_KINDS] = {2, 4, 6, 6, 6, 5, 8, 8, 8, 8, 7};
+    return kind < FK_NUM_KINDS ? a[kind] : -1;
+}
+// Expands the stored base indices into variable slots.  Returns arity or -1.
+int expand_slots(uint8_t kind, const uint32_t idx[4], uint32_t out[8]);
+
+struct Topology {
+    // ---- copy of the structural inputs -----------------------------------------------------
+    uint32_t n_vars = 0, n_expr = 0, n_free = 0, n_rows = 0;
+    std::vector<uint8_t> kind;       // [n_expr]
+    std::vector<uint32_t> idx;       // [n_expr][4]
+    std::vector<uint32_t> free_vars; // [n_free]
+    std::vector<uint32_t> rows;      // [n_rows]
+    uint64_t signature = 0;          // hash of the above (grouping key of fk_lm_solve_batch)
+
+    // ---- per-row slot tables (a1, a4, a5 of SURVEY §8a) ------------------------------------
+    std::vector<uint8_t> row_kind;   // [n_rows]
+    std::vector<uint32_t> row_expr;  // [n_rows] expression id (parameter index)
+    std::vector<uint32_t> slot_var;  // [n_rows][8] global variable index
+    std::vector<int32_t> slot_col;   // [n_rows][8] free column, -1 if fixed, -2 if unused slot
+    std::vector<int32_t> slot_pos;   // [n_rows][8] position in the Jacobian value array, -1 if none
+    std::vector<uint8_t> slot_dup;   // [n_rows][8] 1: an earlier slot of this row has the same column
+    uint64_t eval_bytes = 0;         // algorithmic bytes of one residual+Jacobian evaluation (§8d)
+
+    // ---- patterns ---------------------------------------------------------------------------
+    // Augmented (n_rows + n_free) x n_free CSC pattern: per column ascending expression rows, then
+    // the damping row n_rows + c (fiksi/src/solve/lm.rs:92-98).  Bit-exact parity object #1.
+    std::vector<uint32_t> aug_colptr, aug_rowidx;
+    uint32_t jac_nnz = 0;            // aug_nnz - n_free; Jacobian values are stored in CSC order
+    std::vector<int32_t> perm;       // COLAMD: perm[k] = original column at position k.  Parity #2.
+    std::vector<int32_t> iperm;      // iperm[c] = position of original column c
+    std::vector<int32_t> parent;     // column elimination tree of A*P (-1 root)
+    std::vector<uint32_t> r_colptr, r_rowidx;  // R = Lᵀ pattern, per column ascending rows, diagonal last
+    std::vector<uint32_t> l_colptr, l_rowidx;  // L pattern (CSC), per column diagonal first, then ascending
+    uint32_t etree_height = 0;
+    uint64_t chol_flops = 0;
+
+    // ---- schedules for the shared-memory LM kernel (empty when the problem takes the global path)
+    std::vector<uint32_t> h_ptr;     // [l_nnz+1] contributions of every L position
+    std::vector<uint32_t> h_pairs;   // 2 Jacobian positions per contribution
+    std::vector<uint32_t> g_ptr;     // [n_free+1] per permuted column: (Jacobian position, row) pairs
+    std::vector<uint32_t> g_pairs;
+    std::vector<uint32_t> u_ptr;     // [n_free+1] per column: update triples (dst, a, b) of the LDLᵀ step
+    std::vector<uint32_t> u_trip;
+    std::vector<uint32_t> r_lpos;    // [r_nnz] position in L storage of every R entry (back substitution)
+    uint32_t max_col_updates = 0;
+
+    uint32_t path = 0, tile = 32, smem_bytes = 0;
+
+    std::string error;
+
+    // Runs the whole pipeline.  Returns FK_OK or an error status (message in `error`).
+    int build(const fk_problem& p);
+    void fill_info(fk_topology_info* info) const;
+};
+
+}  // namespace fk
