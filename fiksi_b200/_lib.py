@@ -35,7 +35,7 @@ class FkReport(C.Structure):
 class FkTopologyInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "n_vars", "n_expr", "n_free", "n_rows", "jac_nnz", "aug_nnz", "r_nnz", "etree_height",
-        "path", "tile", "smem_bytes", "reserved")] + [("chol_flops", C.c_uint64)]
+        "path", "tile", "smem_bytes", "eval_bytes")] + [("chol_flops", C.c_uint64)]
 
 
 REPORT_DTYPE = np.dtype([
@@ -50,7 +50,7 @@ EXPORTS = [
     "fk_batch_solve", "fk_batch_plan_create", "fk_batch_plan_destroy", "fk_batch_plan_upload",
     "fk_batch_plan_run", "fk_batch_plan_download", "fk_batch_plan_device_ptrs",
     "fk_batch_plan_launches", "fk_host_alloc", "fk_host_free", "fk_batch_plan_eval",
-    "fk_batch_plan_eval_download",
+    "fk_batch_plan_eval_download", "fk_batch_solve_device", "fk_fp64_peak_tflops",
 ]
 
 _lib = None

@@ -56,6 +56,11 @@ class Topology:
                                    reports.ctypes.data_as(C.POINTER(FkReport)), n_gpus))
         return out, reports
 
+    def batch_solve_into(self, device, n, vars_ptr, param_ptr, out_ptr, rep_ptr):
+        """fk_batch_solve_device on caller-owned (ideally pinned) host buffers given as addresses."""
+        check(lib().fk_batch_solve_device(self._h, device, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr),
+                                          C.c_void_p(out_ptr), C.c_void_p(rep_ptr)))
+
     def plan(self, capacity, device=0):
         return BatchPlan(self, capacity, device)
 
@@ -121,6 +126,12 @@ class BatchPlan:
             self.close()
         except Exception:
             pass
+
+
+def fp64_peak_tflops(device=0) -> float:
+    out = C.c_double(0.0)
+    check(lib().fk_fp64_peak_tflops(device, C.byref(out)))
+    return out.value
 
 
 def device_count() -> int:

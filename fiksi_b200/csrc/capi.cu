@@ -105,10 +105,34 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
 
 }  // namespace
 
+struct fk_batch_plan;
+// Per-device staging pipeline of fk_batch_solve: kStreams plans + streams, reused across calls.
+struct DevicePipeline {
+    static constexpr uint32_t kStreams = 3;
+    std::mutex mu;
+    int device = -1;
+    uint32_t chunk = 0;
+    fk_batch_plan* plans[kStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    void release();
+    ~DevicePipeline() { release(); }
+};
+
 struct fk_topology {
     fk::Topology t;
     std::mutex mu;
     std::map<int, std::unique_ptr<DeviceProgram>> programs;
+    std::map<int, std::unique_ptr<DevicePipeline>> pipelines;
+
+    DevicePipeline* pipeline_for(int device) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto& p = pipelines[device];
+        if (!p) {
+            p.reset(new DevicePipeline());
+            p->device = device;
+        }
+        return p.get();
+    }
 
     int program_for(int device, const fk::DevProgram** out) {
         std::lock_guard<std::mutex> lock(mu);
@@ -137,6 +161,17 @@ struct fk_batch_plan {
         cudaFree(d_vars); cudaFree(d_params); cudaFree(d_out); cudaFree(d_er); cudaFree(d_ej); cudaFree(d_rep);
     }
 };
+
+void DevicePipeline::release() {
+    if (device >= 0) cudaSetDevice(device);
+    for (uint32_t s = 0; s < kStreams; s++) {
+        if (streams[s]) cudaStreamDestroy(streams[s]);
+        streams[s] = nullptr;
+        delete plans[s];
+        plans[s] = nullptr;
+    }
+    chunk = 0;
+}
 
 extern "C" {
 
@@ -283,6 +318,17 @@ int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_
     return FK_OK;
 }
 
+int fk_fp64_peak_tflops(int device, double* out) {
+    if (!out) return fail(FK_ERR_INVALID, "null argument");
+    if (usable_devices() == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible");
+    CU(cudaSetDevice(device));
+    double v = 0.0;
+    int e = fk::measure_fp64_peak(&v);
+    if (e != 0) return cuda_fail((cudaError_t)e, "fp64 peak microbenchmark");
+    *out = v;
+    return FK_OK;
+}
+
 void* fk_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
@@ -301,38 +347,50 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
     const fk::Topology& t = topo->t;
     const uint32_t total = hi - lo;
     if (total == 0) return FK_OK;
-    const uint32_t kStreams = 3;
-    uint32_t chunk = std::max<uint32_t>(1024, (total + 7) / 8);
-    chunk = std::min(chunk, total);
+    DevicePipeline* pl = topo->pipeline_for(device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    constexpr uint32_t kStreams = DevicePipeline::kStreams;
+    // chunks small enough to overlap H2D / kernel / D2H, large enough to fill the machine
+    uint32_t chunk = std::min(total, std::max<uint32_t>(4096, (total + 7) / 8));
     int rc = FK_OK;
-    fk_batch_plan* plans[kStreams] = {nullptr, nullptr, nullptr};
-    cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
-    auto cleanup = [&]() {
-        for (uint32_t s = 0; s < kStreams; s++) {
-            if (streams[s]) cudaStreamDestroy(streams[s]);
-            delete plans[s];
+    if (pl->chunk < chunk) {
+        pl->release();
+        for (uint32_t s = 0; s < kStreams && rc == FK_OK; s++) {
+            rc = fk_batch_plan_create(topo, chunk, device, &pl->plans[s]);
+            if (rc == FK_OK && cudaStreamCreateWithFlags(&pl->streams[s], cudaStreamNonBlocking) != cudaSuccess)
+                rc = fail(FK_ERR_CUDA, "cudaStreamCreate failed");
         }
-    };
-    for (uint32_t s = 0; s < kStreams && rc == FK_OK; s++) {
-        rc = fk_batch_plan_create(topo, chunk, device, &plans[s]);
-        if (rc == FK_OK && cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking) != cudaSuccess)
-            rc = fail(FK_ERR_CUDA, "cudaStreamCreate failed");
+        if (rc == FK_OK) pl->chunk = chunk;
+        else pl->release();
+    } else {
+        chunk = pl->chunk >= total ? std::min(total, std::max<uint32_t>(4096, (total + 7) / 8)) : pl->chunk;
     }
     uint32_t s = 0;
     for (uint32_t at = lo; at < hi && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
         uint32_t cnt = std::min(chunk, hi - at);
         // a plan's buffers are reused only after its previous chunk has fully drained
-        if (cudaStreamSynchronize(streams[s]) != cudaSuccess) { rc = fail(FK_ERR_CUDA, "stream sync failed"); break; }
-        rc = fk_batch_plan_upload(plans[s], cnt, vars + (size_t)at * t.n_vars, param ? param + (size_t)at * t.n_expr : nullptr, streams[s]);
-        if (rc == FK_OK) rc = fk_batch_plan_run(plans[s], streams[s]);
-        if (rc == FK_OK) rc = fk_batch_plan_download(plans[s], free_out + (size_t)at * t.n_free, reports ? reports + at : nullptr, streams[s]);
+        if (cudaStreamSynchronize(pl->streams[s]) != cudaSuccess) { rc = fail(FK_ERR_CUDA, "stream sync failed"); break; }
+        rc = fk_batch_plan_upload(pl->plans[s], cnt, vars + (size_t)at * t.n_vars, param ? param + (size_t)at * t.n_expr : nullptr, pl->streams[s]);
+        if (rc == FK_OK) rc = fk_batch_plan_run(pl->plans[s], pl->streams[s]);
+        if (rc == FK_OK) rc = fk_batch_plan_download(pl->plans[s], free_out + (size_t)at * t.n_free, reports ? reports + at : nullptr, pl->streams[s]);
     }
     for (uint32_t k = 0; k < kStreams; k++)
-        if (streams[k] && cudaStreamSynchronize(streams[k]) != cudaSuccess && rc == FK_OK)
+        if (pl->streams[k] && cudaStreamSynchronize(pl->streams[k]) != cudaSuccess && rc == FK_OK)
             rc = cuda_fail(cudaGetLastError(), "batch kernel / copy failed");
     if (rc != FK_OK && err) *err = g_error;
-    cleanup();
     return rc;
+}
+
+int fk_batch_solve_device(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param,
+                          double* free_out, fk_report* reports) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    if (n == 0) return FK_OK;
+    if (!vars || !free_out || (!param && topo->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
+    int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    return run_device_range(topo, device, 0, n, vars, param, free_out, reports, nullptr);
 }
 
 int fk_batch_solve(const fk_topology* topo_c, uint32_t n, const double* vars, const double* param, double* free_out,
@@ -344,11 +402,10 @@ int fk_batch_solve(const fk_topology* topo_c, uint32_t n, const double* vars, co
     int ndev = usable_devices();
     if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
     if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
-    int base = 0;
-    if (const char* d = std::getenv("FK_DEVICE")) base = std::atoi(d);  // one-process-per-GPU launches
     if (n_gpus == 1) {
-        if (base < 0 || base >= ndev) base = 0;
-        return run_device_range(topo, base, 0, n, vars, param, free_out, reports, nullptr);
+        int cur = 0;  // one process per GPU: honour the caller's current device
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+        return run_device_range(topo, cur, 0, n, vars, param, free_out, reports, nullptr);
     }
     std::vector<int> rcs(n_gpus, FK_OK);
     std::vector<std::string> errs(n_gpus);

@@ -320,6 +320,43 @@ fk_batch_eval_kernel(const DevProgram P, uint32_t n_sketches, const double* __re
 
 const char* lm_kernel_name() { return "fk_batch_lm_kernel"; }
 
+// FP64 roofline denominator: 8 independent DFMA chains per thread, enough warps to fill every SMSP.
+__global__ void __launch_bounds__(256) fk_fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int measure_fp64_peak(double* tflops) {
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(double) * blocks * threads);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(t0);
+        fk_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d);
+    if (e != cudaSuccess) return (int)e;
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return 0;
+}
+
 template <int TILE>
 static int launch_lm_t(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                        double* free_out, fk_report* reports, cudaStream_t stream) {

@@ -44,5 +44,7 @@ int launch_batch_lm(const DevProgram& prog, uint32_t tile, uint32_t n_sketches, 
 int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double* vars,
                       const double* params, double* out_r, double* out_j, int mode, void* stream);
 const char* lm_kernel_name();
+// DFMA throughput microbenchmark on the current device (TFLOP/s, 2 flops per DFMA).
+int measure_fp64_peak(double* tflops);
 
 }  // namespace fk

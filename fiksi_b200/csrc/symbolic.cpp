@@ -312,6 +312,7 @@ void Topology::fill_info(fk_topology_info* info) const {
     info->etree_height = etree_height;
     info->path = path; info->tile = tile; info->smem_bytes = smem_bytes;
     info->chol_flops = chol_flops;
+    info->eval_bytes = (uint32_t)std::min<uint64_t>(eval_bytes, 0xFFFFFFFFu);
 }
 
 }  // namespace fk

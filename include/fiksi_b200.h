@@ -118,7 +118,7 @@ typedef struct fk_topology_info {
     uint32_t path;         /* 0 tile-per-sketch (shared memory), 1 CTA-per-sketch, 2 global sparse */
     uint32_t tile;         /* lanes per sketch on path 0/1 */
     uint32_t smem_bytes;   /* shared memory per sketch on path 0/1 */
-    uint32_t reserved;
+    uint32_t eval_bytes;   /* algorithmic bytes of one residual+Jacobian evaluation of one sketch */
     uint64_t chol_flops;   /* sum over columns of colcount^2: flops of one sparse factorisation */
 } fk_topology_info;
 
@@ -155,6 +155,10 @@ FK_API int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems,
 FK_API int fk_batch_solve(const fk_topology* topo, uint32_t n, const double* vars,
                           const double* param, double* free_out, fk_report* reports, int n_gpus);
 
+/* Same on one explicit device (one process per GPU launches, e.g. under torchrun). */
+FK_API int fk_batch_solve_device(const fk_topology* topo, int device, uint32_t n, const double* vars,
+                                 const double* param, double* free_out, fk_report* reports);
+
 /* Device-resident batch plan (one device; used by bench.py and by fk_batch_solve internally). */
 typedef struct fk_batch_plan fk_batch_plan;
 FK_API int fk_batch_plan_create(const fk_topology* topo, uint32_t capacity, int device,
@@ -174,6 +178,10 @@ FK_API int fk_batch_plan_device_ptrs(fk_batch_plan* plan, void** vars, void** pa
                                      void** free_out, void** reports);
 /* Number of kernel launches issued by this plan so far / name of the LM kernel. */
 FK_API uint64_t fk_batch_plan_launches(const fk_batch_plan* plan);
+
+/* Measured FP64 DFMA throughput of `device` in TFLOP/s (roofline denominator for the
+ * factorisation; MEASURED_PEAKS.json carries no FP64 figure). */
+FK_API int fk_fp64_peak_tflops(int device, double* out);
 
 /* Pinned host memory helpers (so that callers without a CUDA binding can stage inputs). */
 FK_API void* fk_host_alloc(size_t bytes);
