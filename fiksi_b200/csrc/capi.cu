@@ -75,11 +75,12 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
         items.push_back({vec.data(), vec.size() * sizeof(T), at});
         return at;
     };
-    size_t o_kind = add(t.row_kind), o_expr = add(t.row_expr), o_svar = add(t.slot_var), o_scol = add(t.slot_col),
-           o_spos = add(t.slot_pos), o_sdup = add(t.slot_dup), o_free = add(t.free_vars), o_perm = add(t.perm),
-           o_lcp = add(t.l_colptr), o_lri = add(t.l_rowidx), o_hp = add(t.h_ptr), o_hpr = add(t.h_pairs),
-           o_gp = add(t.g_ptr), o_gpr = add(t.g_pairs), o_up = add(t.u_ptr), o_ut = add(t.u_trip),
-           o_rcp = add(t.r_colptr), o_rri = add(t.r_rowidx), o_rlp = add(t.r_lpos);
+    const fk::Topology::Tables& tb = t.tab;
+    size_t o_free = add(t.free_vars), o_perm = add(t.perm), o_rh = add(tb.row_hdr), o_rs = add(tb.row_slots),
+           o_al = add(tb.asm_len), o_af = add(tb.asm_first), o_ad = add(tb.asm_dst), o_ao = add(tb.asm_ops),
+           o_gl = add(tb.g_len), o_gf = add(tb.g_first), o_gd = add(tb.g_dst), o_go = add(tb.g_ops),
+           o_fh = add(tb.f_hdr), o_fo = add(tb.f_ops), o_sh = add(tb.s_hdr), o_so = add(tb.s_ops),
+           o_bh = add(tb.b_hdr), o_bo = add(tb.b_ops), o_dp = add(tb.diag_pos);
     std::vector<unsigned char> host(off + 16, 0);
     for (const Item& it : items)
         if (it.bytes) std::memcpy(host.data() + it.at, it.src, it.bytes);
@@ -89,17 +90,18 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
     unsigned char* b = (unsigned char*)out.buf;
     fk::DevProgram& v = out.view;
     v.n_vars = t.n_vars; v.n_expr = t.n_expr; v.n = t.n_free; v.m = t.n_rows;
-    v.jnnz = t.jac_nnz; v.lnnz = (uint32_t)t.l_rowidx.size(); v.nlevels = t.etree_height; v.pad_ = 0;
-    v.row_kind = (const uint8_t*)(b + o_kind); v.row_expr = (const uint32_t*)(b + o_expr);
-    v.slot_var = (const uint32_t*)(b + o_svar); v.slot_col = (const int32_t*)(b + o_scol);
-    v.slot_pos = (const int32_t*)(b + o_spos); v.slot_dup = (const uint8_t*)(b + o_sdup);
+    v.jnnz = t.jac_nnz; v.lnnz = (uint32_t)t.l_rowidx.size(); v.tile = t.tile; v.uniform_kind = tb.uniform_kind;
+    v.eval_rounds = tb.eval_rounds; v.asm_rounds = (uint32_t)tb.asm_len.size(); v.g_rounds = (uint32_t)tb.g_len.size(); v.pad_ = 0;
     v.free_vars = (const uint32_t*)(b + o_free); v.perm = (const int32_t*)(b + o_perm);
-    v.l_colptr = (const uint32_t*)(b + o_lcp); v.l_rowidx = (const uint32_t*)(b + o_lri);
-    v.h_ptr = (const uint32_t*)(b + o_hp); v.h_pairs = (const uint32_t*)(b + o_hpr);
-    v.g_ptr = (const uint32_t*)(b + o_gp); v.g_pairs = (const uint32_t*)(b + o_gpr);
-    v.u_ptr = (const uint32_t*)(b + o_up); v.u_trip = (const uint32_t*)(b + o_ut);
-    v.r_colptr = (const uint32_t*)(b + o_rcp); v.r_rowidx = (const uint32_t*)(b + o_rri);
-    v.r_lpos = (const uint32_t*)(b + o_rlp);
+    v.row_hdr = (const uint32_t*)(b + o_rh); v.row_slots = (const uint2*)(b + o_rs);
+    v.asm_len = (const uint32_t*)(b + o_al); v.asm_first = (const uint32_t*)(b + o_af);
+    v.asm_dst = (const uint32_t*)(b + o_ad); v.asm_ops = (const uint32_t*)(b + o_ao);
+    v.g_len = (const uint32_t*)(b + o_gl); v.g_first = (const uint32_t*)(b + o_gf);
+    v.g_dst = (const uint32_t*)(b + o_gd); v.g_ops = (const uint32_t*)(b + o_go);
+    v.f_hdr = (const uint2*)(b + o_fh); v.f_ops = (const uint2*)(b + o_fo);
+    v.s_hdr = (const uint2*)(b + o_sh); v.s_ops = (const uint32_t*)(b + o_so);
+    v.b_hdr = (const uint2*)(b + o_bh); v.b_ops = (const uint32_t*)(b + o_bo);
+    v.diag_pos = (const uint32_t*)(b + o_dp);
     return FK_OK;
 }
 
@@ -266,7 +268,7 @@ int fk_batch_plan_upload(fk_batch_plan* plan, uint32_t n, const double* vars, co
 int fk_batch_plan_run(fk_batch_plan* plan, void* stream) {
     if (!plan) return fail(FK_ERR_INVALID, "null plan");
     CU(cudaSetDevice(plan->device));
-    int e = fk::launch_batch_lm(*plan->prog, plan->topo->t.tile, plan->n, plan->d_vars, plan->d_params, plan->d_out,
+    int e = fk::launch_batch_lm(*plan->prog, plan->n, plan->d_vars, plan->d_params, plan->d_out,
                                 plan->d_rep, stream);
     if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_lm_kernel");
     if (plan->n) plan->launches++;

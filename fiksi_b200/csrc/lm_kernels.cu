@@ -16,6 +16,8 @@
 
 namespace fk {
 
+constexpr uint32_t kNop = 0xFFFFFFFFu;
+
 template <int TILE>
 struct TileOps {
     static constexpr bool kWholeCta = TILE > 32;
@@ -33,39 +35,39 @@ struct TileOps {
     }
 };
 
-// Evaluate all rows of one sketch with the lanes of a tile.  `xfree` holds the current free
-// values (shared memory); fixed variables come from the sketch's `vars` in global memory
-// (fiksi/src/variable_map.rs:57-72).  == Subsystem::calculate_residuals_and_sparse_jacobian,
-// fiksi/src/subsystem.rs:126-166, writing straight into the CSC slots that
-// SparseColMat::from_triplet_mat would produce (duplicates of a column inside one row are summed).
-template <int TILE, bool WITH_JACOBIAN>
-__device__ __forceinline__ void eval_tile(const DevProgram& P, int lane, const double* xfree,
-                                          const double* __restrict__ vars, const double* __restrict__ params,
-                                          double* rdst, double* jdst) {
-    for (uint32_t row = lane; row < P.m; row += TILE) {
-        const int kind = __ldg(P.row_kind + row);
-        const int a = dev::arity_of(kind);
-        double v[8], g[8];
+// One expression row: gather the slot values (free ones from `xfree`, fixed ones from the
+// sketch's `vars`, fiksi/src/variable_map.rs:57-72), evaluate, store the residual and scatter
+// the gradient into the precomputed CSC slots (duplicates of a column inside a row are summed, as
+// SparseColMat::from_triplet_mat does).  == one iteration of the loop at
+// fiksi/src/subsystem.rs:143-165.  KIND >= 0: every row of the topology has this kind.
+template <int KIND, bool WITH_JACOBIAN>
+__device__ __forceinline__ void eval_row(const DevProgram& P, uint32_t row, const double* xfree,
+                                         const double* __restrict__ vars, const double* __restrict__ params,
+                                         double* rdst, double* jdst) {
+    const uint32_t hdr = __ldg(P.row_hdr + row);
+    if (hdr == kNop) return;
+    const int kind = KIND >= 0 ? KIND : (int)(hdr & 0xFFu);
+    const int a = dev::arity_of(kind);
+    uint2 sl[8];
+    double v[8], g[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        v[s] = 0.0;
+        sl[s] = make_uint2(kNop, kNop);
+        if (s < a) {
+            sl[s] = __ldg(P.row_slots + row * 8 + s);
+            v[s] = (int32_t)sl[s].x >= 0 ? xfree[sl[s].x] : __ldg(vars + (sl[s].x & 0x7FFFFFFFu));
+        }
+    }
+    const double param = __ldg(params + (hdr >> 8));
+    rdst[row] = dev::eval_expression(kind, v, param, g);
+    if (WITH_JACOBIAN) {
 #pragma unroll
         for (int s = 0; s < 8; s++) {
-            v[s] = 0.0;
-            if (s < a) {
-                const int32_t c = __ldg(P.slot_col + row * 8 + s);
-                v[s] = c >= 0 ? xfree[c] : __ldg(vars + __ldg(P.slot_var + row * 8 + s));
-            }
-        }
-        const double param = __ldg(params + __ldg(P.row_expr + row));
-        rdst[row] = dev::eval_expression(kind, v, param, g);
-        if (WITH_JACOBIAN) {
-#pragma unroll
-            for (int s = 0; s < 8; s++) {
-                if (s < a) {
-                    const int32_t pos = __ldg(P.slot_pos + row * 8 + s);
-                    if (pos >= 0) {
-                        if (__ldg(P.slot_dup + row * 8 + s)) jdst[pos] += g[s];
-                        else jdst[pos] = g[s];
-                    }
-                }
+            if (s < a && sl[s].y != kNop) {
+                const uint32_t pos = sl[s].y & 0xFFFFFFu;
+                if (sl[s].y & 0x40000000u) jdst[pos] += g[s];
+                else jdst[pos] = g[s];
             }
         }
     }
@@ -75,73 +77,99 @@ __device__ __forceinline__ void eval_tile(const DevProgram& P, int lane, const d
 // the same value, which keeps the LM control flow uniform across the tile without a broadcast).
 __device__ __forceinline__ double sum_squares_seq(const double* v, uint32_t n) {
     double s = 0.0;
+#pragma unroll 4
     for (uint32_t i = 0; i < n; i++) s += v[i] * v[i];
     return s;
 }
 
 // K3: H0 = JᵀJ in L storage (permuted, lower) and g = Jᵀ rneg (permuted).  Each output entry is
-// the sum of its precomputed contribution list in row order: a segmented reduction, no atomics.
+// the sum of its precomputed contribution list in row order — a segmented reduction without
+// atomics; entries are grouped longest list first so that a round has one trip count.
 template <int TILE>
 __device__ __forceinline__ void assemble_tile(const DevProgram& P, int lane, const double* J,
                                               const double* rneg, double* H0, double* g) {
-    for (uint32_t p = lane; p < P.lnnz; p += TILE) {
-        const uint32_t b = __ldg(P.h_ptr + p), e = __ldg(P.h_ptr + p + 1);
+    for (uint32_t rd = 0; rd < P.asm_rounds; rd++) {
+        const uint32_t dst = __ldg(P.asm_dst + rd * TILE + lane);
+        const uint32_t len = __ldg(P.asm_len + rd);
+        const uint32_t* ops = P.asm_ops + (size_t)__ldg(P.asm_first + rd) * TILE + lane;
         double s = 0.0;
-        for (uint32_t q = b; q < e; q++) s = fma(J[__ldg(P.h_pairs + 2 * q)], J[__ldg(P.h_pairs + 2 * q + 1)], s);
-        H0[p] = s;
+        for (uint32_t t = 0; t < len; t++) {
+            const uint32_t op = __ldg(ops + t * TILE);
+            if (op != kNop) s = fma(J[op & 0xFFFFu], J[op >> 16], s);
+        }
+        if (dst != kNop) H0[dst] = s;
     }
-    for (uint32_t k = lane; k < P.n; k += TILE) {
-        const uint32_t b = __ldg(P.g_ptr + k), e = __ldg(P.g_ptr + k + 1);
+    for (uint32_t rd = 0; rd < P.g_rounds; rd++) {
+        const uint32_t dst = __ldg(P.g_dst + rd * TILE + lane);
+        const uint32_t len = __ldg(P.g_len + rd);
+        const uint32_t* ops = P.g_ops + (size_t)__ldg(P.g_first + rd) * TILE + lane;
         double s = 0.0;
-        for (uint32_t q = b; q < e; q++) s = fma(J[__ldg(P.g_pairs + 2 * q)], rneg[__ldg(P.g_pairs + 2 * q + 1)], s);
-        g[k] = s;
+        for (uint32_t t = 0; t < len; t++) {
+            const uint32_t op = __ldg(ops + t * TILE);
+            if (op != kNop) s = fma(J[op & 0xFFFFu], rneg[op >> 16], s);
+        }
+        if (dst != kNop) g[dst] = s;
     }
 }
 
-// LDLᵀ of work (= H0 + lam2 I) in place: column k keeps the unscaled entries (L D)(i,k); invd[k]
-// = 1/D(k).  Right-looking, one tile-wide step per column.  Returns 0 ok, 1 non-positive pivot,
-// 2 NaN pivot.
+// LDLᵀ of (work + lam2 I) in place: column k keeps the unscaled entries (L D)(i,k); invd[k] =
+// 1/D(k).  Right-looking; per column every lane applies at most one packed update per round.
+// Returns 0 ok, 1 non-positive pivot, 2 NaN pivot.
 template <int TILE>
-__device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsigned msk, double* work, double* invd) {
+__device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsigned msk, double lam2,
+                                           double* work, double* invd) {
     for (uint32_t k = 0; k < P.n; k++) {
-        const double d = work[__ldg(P.l_colptr + k)];
+        const uint2 hdr = __ldg(P.f_hdr + k);
+        const double d = work[hdr.x & 0xFFFFu] + lam2;
         if (d != d) return 2;
         if (!(d > 0.0) || d == INFINITY) return 1;
         const double inv = 1.0 / d;
         if (lane == 0) invd[k] = inv;
-        const uint32_t b = __ldg(P.u_ptr + k), e = __ldg(P.u_ptr + k + 1);
-        for (uint32_t t = b + lane; t < e; t += TILE) {
-            const uint32_t dst = __ldg(P.u_trip + 3 * t), ia = __ldg(P.u_trip + 3 * t + 1), ib = __ldg(P.u_trip + 3 * t + 2);
-            work[dst] = fma(-(work[ia] * inv), work[ib], work[dst]);
+        const uint32_t rounds = hdr.x >> 16;
+        const uint2* ops = P.f_ops + (size_t)hdr.y * TILE + lane;
+        for (uint32_t r = 0; r < rounds; r++) {
+            const uint2 op = __ldg(ops + r * TILE);
+            if (op.x != kNop) {
+                const uint32_t dst = op.x & 0xFFFFu;
+                work[dst] = fma(-(work[op.x >> 16] * inv), work[op.y], work[dst]);
+            }
         }
         TileOps<TILE>::sync(msk);
     }
     return 0;
 }
 
-// Solve (L D Lᵀ) z = g; w holds g on entry (permuted order) and z on return.
+// Solve (L D Lᵀ) z = g.  w holds g on entry (permuted order); the solution is written in
+// variable order (delta[perm[k]] = z[k], the P_c z of qr.rs:354) into `delta`.
 template <int TILE>
 __device__ __forceinline__ void solve_tile(const DevProgram& P, int lane, unsigned msk, const double* work,
-                                           const double* invd, double* w) {
+                                           const double* invd, double* w, double* delta) {
     // forward: unit lower triangular L' = (L D) D^-1, column oriented
     for (uint32_t k = 0; k < P.n; k++) {
+        const uint2 hdr = __ldg(P.s_hdr + k);
         const double t = w[k] * invd[k];
-        const uint32_t b = __ldg(P.l_colptr + k) + 1, e = __ldg(P.l_colptr + k + 1);
-        for (uint32_t q = b + lane; q < e; q += TILE) {
-            const uint32_t i = __ldg(P.l_rowidx + q);
-            w[i] = fma(-work[q], t, w[i]);
+        const uint32_t* ops = P.s_ops + (size_t)hdr.y * TILE + lane;
+        for (uint32_t r = 0; r < hdr.x; r++) {
+            const uint32_t op = __ldg(ops + r * TILE);
+            if (op != kNop) {
+                const uint32_t i = op & 0xFFFFu;
+                w[i] = fma(-work[op >> 16], t, w[i]);
+            }
         }
         TileOps<TILE>::sync(msk);
     }
-    for (uint32_t k = lane; k < P.n; k += TILE) w[k] *= invd[k];
-    TileOps<TILE>::sync(msk);
-    // backward: L'ᵀ, column oriented over the columns of R = Lᵀ (diagonal is the last entry)
+    // backward: D Lᵀ z = y column by column over R = Lᵀ: z_k = y_k / d_k, then y_j -= (L D)(k,j) z_k
     for (uint32_t kk = P.n; kk-- > 0;) {
-        const double zk = w[kk];
-        const uint32_t b = __ldg(P.r_colptr + kk), e = __ldg(P.r_colptr + kk + 1) - 1;
-        for (uint32_t q = b + lane; q < e; q += TILE) {
-            const uint32_t j = __ldg(P.r_rowidx + q);
-            w[j] = fma(-(work[__ldg(P.r_lpos + q)] * invd[j]), zk, w[j]);
+        const uint2 hdr = __ldg(P.b_hdr + kk);
+        const double zk = w[kk] * invd[kk];
+        if (lane == 0) delta[__ldg(P.perm + kk)] = zk;
+        const uint32_t* ops = P.b_ops + (size_t)hdr.y * TILE + lane;
+        for (uint32_t r = 0; r < hdr.x; r++) {
+            const uint32_t op = __ldg(ops + r * TILE);
+            if (op != kNop) {
+                const uint32_t j = op & 0xFFFFu;
+                w[j] = fma(-work[op >> 16], zk, w[j]);
+            }
         }
         TileOps<TILE>::sync(msk);
     }
@@ -149,7 +177,7 @@ __device__ __forceinline__ void solve_tile(const DevProgram& P, int lane, unsign
 
 __device__ __forceinline__ uint64_t trace_push(uint64_t h, uint32_t code) { return h * 3ull + code + 1ull; }
 
-template <int TILE>
+template <int TILE, int KIND>
 __global__ void __launch_bounds__(TILE > 128 ? TILE : 128)
 fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doubles,
                    const double* __restrict__ vars_all, const double* __restrict__ params_all,
@@ -180,7 +208,7 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
     TileOps<TILE>::sync(msk);
 
     // lm.rs:80-106: initial residuals + Jacobian, r := -r, ssr
-    eval_tile<TILE, true>(P, lane, x, vars, params, rs, work);
+    for (uint32_t rd = 0; rd < P.eval_rounds; rd++) eval_row<KIND, true>(P, rd * TILE + lane, x, vars, params, rs, work);
     TileOps<TILE>::sync(msk);
     double ssr = sum_squares_seq(rs, m);
     for (uint32_t i = lane; i < m; i += TILE) rneg[i] = -rs[i];
@@ -209,11 +237,10 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
             const double sl = sqrt(lambda);
             const double lam2 = sl * sl;
             for (uint32_t p = lane; p < P.lnnz; p += TILE) work[p] = H0[p];
-            TileOps<TILE>::sync(msk);
-            for (uint32_t k = lane; k < n; k += TILE) work[__ldg(P.l_colptr + k)] += lam2;
+            for (uint32_t k = lane; k < n; k += TILE) w[k] = g[k];
             TileOps<TILE>::sync(msk);
 
-            const int fstat = factor_tile<TILE>(P, lane, msk, work, invd);  // replaces lm.rs:128
+            const int fstat = factor_tile<TILE>(P, lane, msk, lam2, work, invd);  // replaces lm.rs:128
             factorizations++;
             if (fstat == 1) {  // lm.rs:134-137 (`!solved`)
                 lambda *= 8.0;
@@ -223,13 +250,8 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
             }
             double ssr_s = NAN;
             if (fstat == 0) {
-                for (uint32_t k = lane; k < n; k += TILE) w[k] = g[k];
-                TileOps<TILE>::sync(msk);
-                solve_tile<TILE>(P, lane, msk, work, invd, w);  // replaces lm.rs:130-132
-                // delta back in variable order (P_c z, qr.rs:354), parked in xs
-                for (uint32_t k = lane; k < n; k += TILE) xs[__ldg(P.perm + k)] = w[k];
-                TileOps<TILE>::sync(msk);
-                if (sum_squares_seq(xs, n) < 1e-12) {  // lm.rs:139-142
+                solve_tile<TILE>(P, lane, msk, work, invd, w, xs);  // replaces lm.rs:130-132
+                if (sum_squares_seq(xs, n) < 1e-12) {               // lm.rs:139-142
                     exit_reason = FK_EXIT_SMALL_STEP;
                     done = true;
                     break;
@@ -238,7 +260,8 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
                 for (uint32_t i = lane; i < n; i += TILE) xs[i] = x[i] + xs[i];  // lm.rs:144-146
                 TileOps<TILE>::sync(msk);
                 // lm.rs:148-149 (+ the Jacobian the accept branch would recompute at lm.rs:173-185)
-                eval_tile<TILE, true>(P, lane, xs, vars, params, rs, work);
+                for (uint32_t rd = 0; rd < P.eval_rounds; rd++)
+                    eval_row<KIND, true>(P, rd * TILE + lane, xs, vars, params, rs, work);
                 TileOps<TILE>::sync(msk);
                 ssr_s = sum_squares_seq(rs, m);
             }
@@ -295,23 +318,32 @@ fk_batch_eval_kernel(const DevProgram P, uint32_t n_sketches, const double* __re
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t sketch = (uint32_t)(t / P.m), row = (uint32_t)(t % P.m);
         const double* vars = vars_all + (size_t)sketch * P.n_vars;
-        const int kind = __ldg(P.row_kind + row);
+        // no free-value overlay here: free variables are read from the sketch's vars as well
+        const uint32_t hdr = __ldg(P.row_hdr + row);
+        const int kind = (int)(hdr & 0xFFu);
         const int a = dev::arity_of(kind);
+        uint2 sl[8];
         double v[8], g[8];
 #pragma unroll
-        for (int s = 0; s < 8; s++) v[s] = s < a ? __ldg(vars + __ldg(P.slot_var + row * 8 + s)) : 0.0;
-        const double param = __ldg(params_all + (size_t)sketch * P.n_expr + __ldg(P.row_expr + row));
+        for (int s = 0; s < 8; s++) {
+            v[s] = 0.0;
+            sl[s] = make_uint2(kNop, kNop);
+            if (s < a) {
+                sl[s] = __ldg(P.row_slots + row * 8 + s);
+                const uint32_t var = (int32_t)sl[s].x >= 0 ? __ldg(P.free_vars + sl[s].x) : (sl[s].x & 0x7FFFFFFFu);
+                v[s] = __ldg(vars + var);
+            }
+        }
+        const double param = __ldg(params_all + (size_t)sketch * P.n_expr + (hdr >> 8));
         out_r[(size_t)sketch * P.m + row] = dev::eval_expression(kind, v, param, g);
         if (WITH_JACOBIAN) {
             double* jdst = out_j + (size_t)sketch * P.jnnz;
 #pragma unroll
             for (int s = 0; s < 8; s++) {
-                if (s < a) {
-                    const int32_t pos = __ldg(P.slot_pos + row * 8 + s);
-                    if (pos >= 0) {
-                        if (__ldg(P.slot_dup + row * 8 + s)) jdst[pos] += g[s];
-                        else jdst[pos] = g[s];
-                    }
+                if (s < a && sl[s].y != kNop) {
+                    const uint32_t pos = sl[s].y & 0xFFFFFFu;
+                    if (sl[s].y & 0x40000000u) jdst[pos] += g[s];
+                    else jdst[pos] = g[s];
                 }
             }
         }
@@ -357,7 +389,7 @@ int measure_fp64_peak(double* tflops) {
     return 0;
 }
 
-template <int TILE>
+template <int TILE, int KIND>
 static int launch_lm_t(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                        double* free_out, fk_report* reports, cudaStream_t stream) {
     const uint32_t stride = lm_smem_doubles(prog.n, prog.m, prog.jnnz, prog.lnnz);
@@ -371,22 +403,29 @@ static int launch_lm_t(const DevProgram& prog, uint32_t n_sketches, const double
         while (tiles_per_cta > 1 && bytes_per_sketch * tiles_per_cta > budget) tiles_per_cta >>= 1;
     }
     const size_t smem = bytes_per_sketch * tiles_per_cta;
-    cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_kernel<TILE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const uint32_t grid = (n_sketches + tiles_per_cta - 1) / tiles_per_cta;
-    fk_batch_lm_kernel<TILE><<<grid, TILE * tiles_per_cta, smem, stream>>>(prog, n_sketches, stride, vars, params, free_out, reports);
+    fk_batch_lm_kernel<TILE, KIND><<<grid, TILE * tiles_per_cta, smem, stream>>>(prog, n_sketches, stride, vars, params, free_out, reports);
     return (int)cudaGetLastError();
 }
 
-int launch_batch_lm(const DevProgram& prog, uint32_t tile, uint32_t n_sketches, const double* vars,
-                    const double* params, double* free_out, fk_report* reports, void* stream) {
+template <int TILE>
+static int launch_lm_k(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
+                       double* free_out, fk_report* reports, cudaStream_t s) {
+    if (prog.uniform_kind == 1) return launch_lm_t<TILE, 1>(prog, n_sketches, vars, params, free_out, reports, s);
+    return launch_lm_t<TILE, -1>(prog, n_sketches, vars, params, free_out, reports, s);
+}
+
+int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
+                    double* free_out, fk_report* reports, void* stream) {
     if (n_sketches == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (tile) {
-        case 8: return launch_lm_t<8>(prog, n_sketches, vars, params, free_out, reports, s);
-        case 16: return launch_lm_t<16>(prog, n_sketches, vars, params, free_out, reports, s);
-        case 32: return launch_lm_t<32>(prog, n_sketches, vars, params, free_out, reports, s);
-        case 256: return launch_lm_t<256>(prog, n_sketches, vars, params, free_out, reports, s);
+    switch (prog.tile) {
+        case 8: return launch_lm_k<8>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 16: return launch_lm_k<16>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 32: return launch_lm_k<32>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 256: return launch_lm_k<256>(prog, n_sketches, vars, params, free_out, reports, s);
         default: return (int)cudaErrorInvalidValue;
     }
 }

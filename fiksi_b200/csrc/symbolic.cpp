@@ -300,6 +300,108 @@ int Topology::build(const fk_problem& p) {
             u_ptr[k + 1] = (uint32_t)(u_trip.size() / 3);
         }
     }
+    return path == 2 ? FK_OK : build_tables();
+}
+
+// Lane-padded op tables for the shared-memory kernel (see Topology::Tables).
+int Topology::build_tables() {
+    const uint32_t n = n_free, m = n_rows, T = tile;
+    const uint32_t NOP = 0xFFFFFFFFu;
+    const uint32_t lnnz = (uint32_t)l_rowidx.size();
+    if (lnnz >= 0xFFFF || jac_nnz >= 0xFFFF || n >= 0xFFFF || m >= 0xFFFF || n_expr >= (1u << 24)) {
+        error = "problem too large for the 16-bit shared-memory tables";
+        return FK_ERR_TOO_LARGE;
+    }
+    Tables& t = tab;
+    // ---- evaluation rows -------------------------------------------------------------------------
+    t.eval_rounds = (m + T - 1) / T;
+    t.row_hdr.assign((size_t)t.eval_rounds * T, NOP);
+    t.row_slots.assign((size_t)t.eval_rounds * T * 16, NOP);
+    t.uniform_kind = m ? row_kind[0] : -1;
+    for (uint32_t r = 0; r < m; r++) {
+        if (row_kind[r] != t.uniform_kind) t.uniform_kind = -1;
+        t.row_hdr[r] = row_kind[r] | (row_expr[r] << 8);
+        for (int s = 0; s < 8; s++) {
+            int32_t c = slot_col[(size_t)r * 8 + s];
+            if (c == -2) continue;  // unused slot
+            uint32_t src = c >= 0 ? (uint32_t)c : (0x80000000u | slot_var[(size_t)r * 8 + s]);
+            int32_t jp = slot_pos[(size_t)r * 8 + s];
+            uint32_t pos = jp < 0 ? NOP : ((uint32_t)jp | (slot_dup[(size_t)r * 8 + s] ? 0x40000000u : 0u));
+            t.row_slots[((size_t)r * 8 + s) * 2] = src;
+            t.row_slots[((size_t)r * 8 + s) * 2 + 1] = pos;
+        }
+    }
+    // ---- contribution lists, longest first, so every round has a uniform length -------------------
+    auto pack_lists = [&](const std::vector<uint32_t>& ptr, const std::vector<uint32_t>& pairs, uint32_t count,
+                          std::vector<uint32_t>& len, std::vector<uint32_t>& first, std::vector<uint32_t>& dst,
+                          std::vector<uint32_t>& ops) {
+        std::vector<uint32_t> order(count);
+        for (uint32_t i = 0; i < count; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
+        });
+        uint32_t rounds = (count + T - 1) / T;
+        len.assign(rounds, 0); first.assign(rounds, 0); dst.assign((size_t)rounds * T, NOP);
+        ops.clear();
+        for (uint32_t rd = 0; rd < rounds; rd++) {
+            uint32_t L = 0;
+            for (uint32_t l = 0; l < T && rd * T + l < count; l++) {
+                uint32_t e = order[rd * T + l];
+                L = std::max(L, ptr[e + 1] - ptr[e]);
+                dst[(size_t)rd * T + l] = e;
+            }
+            len[rd] = L;
+            first[rd] = (uint32_t)(ops.size() / T);
+            ops.resize(ops.size() + (size_t)L * T, NOP);
+            for (uint32_t l = 0; l < T && rd * T + l < count; l++) {
+                uint32_t e = order[rd * T + l];
+                for (uint32_t q = ptr[e], k = 0; q < ptr[e + 1]; q++, k++)
+                    ops[((size_t)first[rd] + k) * T + l] = pairs[2 * (size_t)q] | (pairs[2 * (size_t)q + 1] << 16);
+            }
+        }
+    };
+    pack_lists(h_ptr, h_pairs, lnnz, t.asm_len, t.asm_first, t.asm_dst, t.asm_ops);
+    pack_lists(g_ptr, g_pairs, n, t.g_len, t.g_first, t.g_dst, t.g_ops);
+    // ---- LDLt updates per column ---------------------------------------------------------------------
+    t.f_hdr.assign((size_t)n * 2, 0);
+    t.f_ops.clear();
+    t.diag_pos.resize(n);
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t cnt = u_ptr[k + 1] - u_ptr[k];
+        uint32_t rounds = (cnt + T - 1) / T;
+        if (rounds >= 0xFFFF) { error = "column update list too long"; return FK_ERR_TOO_LARGE; }
+        t.diag_pos[k] = l_colptr[k];
+        t.f_hdr[2 * (size_t)k] = l_colptr[k] | (rounds << 16);
+        t.f_hdr[2 * (size_t)k + 1] = (uint32_t)(t.f_ops.size() / 2 / T);
+        size_t base = t.f_ops.size();
+        t.f_ops.resize(base + (size_t)rounds * T * 2, NOP);
+        for (uint32_t q = 0; q < cnt; q++) {
+            const uint32_t* tr = &u_trip[3 * (size_t)(u_ptr[k] + q)];
+            t.f_ops[base + 2 * (size_t)q] = tr[0] | (tr[1] << 16);
+            t.f_ops[base + 2 * (size_t)q + 1] = tr[2];
+        }
+    }
+    // ---- triangular solves: column k -> its off-diagonal entries ---------------------------------------
+    auto pack_cols = [&](bool backward, std::vector<uint32_t>& hdr, std::vector<uint32_t>& ops) {
+        hdr.assign((size_t)n * 2, 0);
+        ops.clear();
+        for (uint32_t k = 0; k < n; k++) {
+            std::vector<uint32_t> list;
+            if (!backward) {
+                for (uint32_t q = l_colptr[k] + 1; q < l_colptr[k + 1]; q++) list.push_back(l_rowidx[q] | (q << 16));
+            } else {
+                for (uint32_t q = r_colptr[k]; q + 1 < r_colptr[k + 1]; q++) list.push_back(r_rowidx[q] | (r_lpos[q] << 16));
+            }
+            uint32_t rounds = ((uint32_t)list.size() + T - 1) / T;
+            hdr[2 * (size_t)k] = rounds;
+            hdr[2 * (size_t)k + 1] = (uint32_t)(ops.size() / T);
+            size_t base = ops.size();
+            ops.resize(base + (size_t)rounds * T, NOP);
+            for (size_t q = 0; q < list.size(); q++) ops[base + q] = list[q];
+        }
+    };
+    pack_cols(false, t.s_hdr, t.s_ops);
+    pack_cols(true, t.b_hdr, t.b_ops);
     return FK_OK;
 }
 

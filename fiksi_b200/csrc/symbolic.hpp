@@ -71,6 +71,30 @@ struct Topology {
 
     uint32_t path = 0, tile = 32, smem_bytes = 0;
 
+    // ---- lane-padded, packed op tables of the shared-memory kernel (built for `tile` lanes) ----------
+    // Every phase of the kernel is a sequence of "rounds"; in a round each lane executes at most one
+    // packed op (0xFFFFFFFF.. = no-op), so the device loops have uniform trip counts and no
+    // data-dependent branches.  All positions are 16-bit offsets into per-sketch shared arrays.
+    struct Tables {
+        int32_t uniform_kind = -1;          // all rows share this kind (specialised evaluator), else -1
+        uint32_t eval_rounds = 0;           // ceil(m / tile)
+        std::vector<uint32_t> row_hdr;      // [eval_rounds*tile] kind | expr << 8, NOP for padding
+        std::vector<uint32_t> row_slots;    // [rows][8][2]: {source, jpos}: source = col | 0x80000000|var
+        std::vector<uint32_t> asm_len;      // [asm_rounds] products per entry in this round
+        std::vector<uint32_t> asm_first;    // [asm_rounds] first op slab
+        std::vector<uint32_t> asm_dst;      // [asm_rounds*tile] H0 position or NOP
+        std::vector<uint32_t> asm_ops;      // [slabs*tile] ja | jb << 16
+        std::vector<uint32_t> g_len, g_first, g_dst, g_ops;  // same for g: jpos | row << 16
+        std::vector<uint32_t> f_hdr;        // [n][2]: {diag position | rounds << 16, first round}
+        std::vector<uint32_t> f_ops;        // [rounds*tile][2]: {dst | a << 16, b}
+        std::vector<uint32_t> s_hdr;        // [n][2]: forward substitution {rounds, first round}
+        std::vector<uint32_t> s_ops;        // [rounds*tile]: row | lpos << 16
+        std::vector<uint32_t> b_hdr;        // [n][2]: backward substitution
+        std::vector<uint32_t> b_ops;        // [rounds*tile]: row | lpos << 16
+        std::vector<uint32_t> diag_pos;     // [n]
+    } tab;
+    int build_tables();
+
     std::string error;
 
     // Runs the whole pipeline.  Returns FK_OK or an error status (message in `error`).
