@@ -76,11 +76,11 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
         return at;
     };
     const fk::Topology::Tables& tb = t.tab;
-    size_t o_free = add(t.free_vars), o_perm = add(t.perm), o_rh = add(tb.row_hdr), o_rs = add(tb.row_slots),
-           o_al = add(tb.asm_len), o_af = add(tb.asm_first), o_ad = add(tb.asm_dst), o_ao = add(tb.asm_ops),
-           o_gl = add(tb.g_len), o_gf = add(tb.g_first), o_gd = add(tb.g_dst), o_go = add(tb.g_ops),
-           o_fh = add(tb.f_hdr), o_fo = add(tb.f_ops), o_sh = add(tb.s_hdr), o_so = add(tb.s_ops),
-           o_bh = add(tb.b_hdr), o_bo = add(tb.b_ops), o_dp = add(tb.diag_pos);
+    size_t o_free = add(t.free_vars), o_rh = add(tb.row_hdr), o_rs = add(tb.row_slots),
+           o_af = add(tb.a_flags), o_ao = add(tb.a_ops), o_ad = add(tb.a_dst),
+           o_gf = add(tb.g_flags), o_go = add(tb.g_ops), o_gd = add(tb.g_dst),
+           o_fs = add(tb.f_steps), o_fo = add(tb.f_ops), o_ss = add(tb.s_steps), o_so = add(tb.s_ops),
+           o_bs = add(tb.b_steps), o_bo = add(tb.b_ops);
     std::vector<unsigned char> host(off + 16, 0);
     for (const Item& it : items)
         if (it.bytes) std::memcpy(host.data() + it.at, it.src, it.bytes);
@@ -91,17 +91,15 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
     fk::DevProgram& v = out.view;
     v.n_vars = t.n_vars; v.n_expr = t.n_expr; v.n = t.n_free; v.m = t.n_rows;
     v.jnnz = t.jac_nnz; v.lnnz = (uint32_t)t.l_rowidx.size(); v.tile = t.tile; v.uniform_kind = tb.uniform_kind;
-    v.eval_rounds = tb.eval_rounds; v.asm_rounds = (uint32_t)tb.asm_len.size(); v.g_rounds = (uint32_t)tb.g_len.size(); v.pad_ = 0;
-    v.free_vars = (const uint32_t*)(b + o_free); v.perm = (const int32_t*)(b + o_perm);
+    v.eval_rounds = tb.eval_rounds; v.a_nsteps = tb.a_nsteps; v.g_nsteps = tb.g_nsteps;
+    v.f_nsteps = tb.f_nsteps; v.s_nsteps = tb.s_nsteps; v.b_nsteps = tb.b_nsteps;
+    v.free_vars = (const uint32_t*)(b + o_free);
     v.row_hdr = (const uint32_t*)(b + o_rh); v.row_slots = (const uint2*)(b + o_rs);
-    v.asm_len = (const uint32_t*)(b + o_al); v.asm_first = (const uint32_t*)(b + o_af);
-    v.asm_dst = (const uint32_t*)(b + o_ad); v.asm_ops = (const uint32_t*)(b + o_ao);
-    v.g_len = (const uint32_t*)(b + o_gl); v.g_first = (const uint32_t*)(b + o_gf);
-    v.g_dst = (const uint32_t*)(b + o_gd); v.g_ops = (const uint32_t*)(b + o_go);
-    v.f_hdr = (const uint2*)(b + o_fh); v.f_ops = (const uint2*)(b + o_fo);
-    v.s_hdr = (const uint2*)(b + o_sh); v.s_ops = (const uint32_t*)(b + o_so);
-    v.b_hdr = (const uint2*)(b + o_bh); v.b_ops = (const uint32_t*)(b + o_bo);
-    v.diag_pos = (const uint32_t*)(b + o_dp);
+    v.a_flags = (const uint32_t*)(b + o_af); v.a_ops = (const uint32_t*)(b + o_ao); v.a_dst = (const uint32_t*)(b + o_ad);
+    v.g_flags = (const uint32_t*)(b + o_gf); v.g_ops = (const uint32_t*)(b + o_go); v.g_dst = (const uint32_t*)(b + o_gd);
+    v.f_steps = (const uint32_t*)(b + o_fs); v.f_ops = (const uint2*)(b + o_fo);
+    v.s_steps = (const uint2*)(b + o_ss); v.s_ops = (const uint32_t*)(b + o_so);
+    v.b_steps = (const uint2*)(b + o_bs); v.b_ops = (const uint32_t*)(b + o_bo);
     return FK_OK;
 }
 

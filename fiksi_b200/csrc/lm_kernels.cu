@@ -82,101 +82,112 @@ __device__ __forceinline__ double sum_squares_seq(const double* v, uint32_t n) {
     return s;
 }
 
-// K3: H0 = JᵀJ in L storage (permuted, lower) and g = Jᵀ rneg (permuted).  Each output entry is
-// the sum of its precomputed contribution list in row order — a segmented reduction without
-// atomics; entries are grouped longest list first so that a round has one trip count.
-template <int TILE>
-__device__ __forceinline__ void assemble_tile(const DevProgram& P, int lane, const double* J,
-                                              const double* rneg, double* H0, double* g) {
-    for (uint32_t rd = 0; rd < P.asm_rounds; rd++) {
-        const uint32_t dst = __ldg(P.asm_dst + rd * TILE + lane);
-        const uint32_t len = __ldg(P.asm_len + rd);
-        const uint32_t* ops = P.asm_ops + (size_t)__ldg(P.asm_first + rd) * TILE + lane;
-        double s = 0.0;
-        for (uint32_t t = 0; t < len; t++) {
-            const uint32_t op = __ldg(ops + t * TILE);
-            if (op != kNop) s = fma(J[op & 0xFFFFu], J[op >> 16], s);
-        }
-        if (dst != kNop) H0[dst] = s;
-    }
-    for (uint32_t rd = 0; rd < P.g_rounds; rd++) {
-        const uint32_t dst = __ldg(P.g_dst + rd * TILE + lane);
-        const uint32_t len = __ldg(P.g_len + rd);
-        const uint32_t* ops = P.g_ops + (size_t)__ldg(P.g_first + rd) * TILE + lane;
-        double s = 0.0;
-        for (uint32_t t = 0; t < len; t++) {
-            const uint32_t op = __ldg(ops + t * TILE);
-            if (op != kNop) s = fma(J[op & 0xFFFFu], rneg[op >> 16], s);
-        }
-        if (dst != kNop) g[dst] = s;
+constexpr uint32_t kFirst = 1u << 16, kLast = 1u << 17;
+
+// K3: L storage := JᵀJ (permuted, lower; the damping is added when a pivot is read) and
+// g = -Jᵀ r (permuted).  Each output entry is the sum of its precomputed contribution list in
+// row order — a segmented reduction without atomics.  The lists are laid out as flat steps (one
+// packed op per lane per step, longest lists first); step s+1 is prefetched while step s runs.
+template <int TILE, bool NEGATE>
+__device__ __forceinline__ void accumulate_steps(uint32_t nsteps, const uint32_t* __restrict__ flags,
+                                                 const uint32_t* __restrict__ ops, const uint32_t* __restrict__ dsts,
+                                                 int lane, const double* A, const double* B, double* out) {
+    uint32_t fl = __ldg(flags), op = __ldg(ops + lane), dst = __ldg(dsts + lane);
+    double acc = 0.0;
+    for (uint32_t s = 0; s < nsteps; s++) {
+        const uint32_t nfl = __ldg(flags + s + 1);
+        const uint32_t nop = __ldg(ops + (s + 1) * TILE + lane);
+        const uint32_t ndst = __ldg(dsts + (s + 1) * TILE + lane);
+        if (fl & kFirst) acc = 0.0;
+        if (op != kNop) acc = fma(A[op & 0xFFFFu], B[op >> 16], acc);
+        if ((fl & kLast) && dst != kNop) out[dst] = NEGATE ? -acc : acc;
+        fl = nfl; op = nop; dst = ndst;
     }
 }
 
-// LDLᵀ of (work + lam2 I) in place: column k keeps the unscaled entries (L D)(i,k); invd[k] =
-// 1/D(k).  Right-looking; per column every lane applies at most one packed update per round.
+// LDLᵀ of (L + lam2 I) in place: column k keeps the unscaled entries (L D)(i,k) and 1/D(k) on
+// its diagonal slot.  Right-looking; per step every lane applies at most one packed update.
 // Returns 0 ok, 1 non-positive pivot, 2 NaN pivot.
 template <int TILE>
-__device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsigned msk, double lam2,
-                                           double* work, double* invd) {
-    for (uint32_t k = 0; k < P.n; k++) {
-        const uint2 hdr = __ldg(P.f_hdr + k);
-        const double d = work[hdr.x & 0xFFFFu] + lam2;
-        if (d != d) return 2;
-        if (!(d > 0.0) || d == INFINITY) return 1;
-        const double inv = 1.0 / d;
-        if (lane == 0) invd[k] = inv;
-        const uint32_t rounds = hdr.x >> 16;
-        const uint2* ops = P.f_ops + (size_t)hdr.y * TILE + lane;
-        for (uint32_t r = 0; r < rounds; r++) {
-            const uint2 op = __ldg(ops + r * TILE);
-            if (op.x != kNop) {
-                const uint32_t dst = op.x & 0xFFFFu;
-                work[dst] = fma(-(work[op.x >> 16] * inv), work[op.y], work[dst]);
-            }
+__device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsigned msk, double lam2, double* L) {
+    uint32_t hdr = __ldg(P.f_steps);
+    uint2 op = __ldg(P.f_ops + lane);
+    uint32_t prev_dpos = 0;
+    double inv = 0.0;
+    bool have_prev = false;
+    for (uint32_t s = 0; s < P.f_nsteps; s++) {
+        const uint32_t nhdr = __ldg(P.f_steps + s + 1);
+        const uint2 nop = __ldg(P.f_ops + (s + 1) * TILE + lane);
+        if (hdr & kFirst) {
+            const uint32_t dpos = hdr & 0xFFFFu;
+            const double d = L[dpos] + lam2;
+            // the previous pivot slot is free now (every lane passed the barrier that ended its column)
+            if (have_prev && lane == 0) L[prev_dpos] = inv;
+            if (d != d) return 2;
+            if (!(d > 0.0) || d == INFINITY) return 1;
+            inv = 1.0 / d;
+            prev_dpos = dpos;
+            have_prev = true;
         }
-        TileOps<TILE>::sync(msk);
+        if (op.x != kNop) {
+            const uint32_t dst = op.x & 0xFFFFu;
+            L[dst] = fma(-(L[op.x >> 16] * inv), L[op.y], L[dst]);
+        }
+        if (TILE > 1 && (hdr & kLast)) TileOps<TILE>::sync(msk);
+        hdr = nhdr; op = nop;
     }
+    if (have_prev && lane == 0) L[prev_dpos] = inv;
+    if (TILE > 1) TileOps<TILE>::sync(msk);
     return 0;
 }
 
 // Solve (L D Lᵀ) z = g.  w holds g on entry (permuted order); the solution is written in
 // variable order (delta[perm[k]] = z[k], the P_c z of qr.rs:354) into `delta`.
 template <int TILE>
-__device__ __forceinline__ void solve_tile(const DevProgram& P, int lane, unsigned msk, const double* work,
-                                           const double* invd, double* w, double* delta) {
-    // forward: unit lower triangular L' = (L D) D^-1, column oriented
-    for (uint32_t k = 0; k < P.n; k++) {
-        const uint2 hdr = __ldg(P.s_hdr + k);
-        const double t = w[k] * invd[k];
-        const uint32_t* ops = P.s_ops + (size_t)hdr.y * TILE + lane;
-        for (uint32_t r = 0; r < hdr.x; r++) {
-            const uint32_t op = __ldg(ops + r * TILE);
+__device__ __forceinline__ void solve_tile(const DevProgram& P, int lane, unsigned msk, const double* L,
+                                           double* w, double* delta) {
+    {   // forward: unit lower triangular L' = (L D) D^-1, column oriented
+        uint2 hdr = __ldg(P.s_steps);
+        uint32_t op = __ldg(P.s_ops + lane);
+        double t = 0.0;
+        for (uint32_t s = 0; s < P.s_nsteps; s++) {
+            const uint2 nhdr = __ldg(P.s_steps + s + 1);
+            const uint32_t nop = __ldg(P.s_ops + (s + 1) * TILE + lane);
+            if (hdr.x & kFirst) t = w[hdr.y] * L[hdr.x & 0xFFFFu];
             if (op != kNop) {
                 const uint32_t i = op & 0xFFFFu;
-                w[i] = fma(-work[op >> 16], t, w[i]);
+                w[i] = fma(-L[op >> 16], t, w[i]);
             }
+            if (TILE > 1 && (hdr.x & kLast)) TileOps<TILE>::sync(msk);
+            hdr = nhdr; op = nop;
         }
-        TileOps<TILE>::sync(msk);
     }
-    // backward: D Lᵀ z = y column by column over R = Lᵀ: z_k = y_k / d_k, then y_j -= (L D)(k,j) z_k
-    for (uint32_t kk = P.n; kk-- > 0;) {
-        const uint2 hdr = __ldg(P.b_hdr + kk);
-        const double zk = w[kk] * invd[kk];
-        if (lane == 0) delta[__ldg(P.perm + kk)] = zk;
-        const uint32_t* ops = P.b_ops + (size_t)hdr.y * TILE + lane;
-        for (uint32_t r = 0; r < hdr.x; r++) {
-            const uint32_t op = __ldg(ops + r * TILE);
+    {   // backward: D Lᵀ z = y column by column over R = Lᵀ: z_k = y_k / d_k, then y_j -= (L D)(k,j) z_k
+        uint2 hdr = __ldg(P.b_steps);
+        uint32_t op = __ldg(P.b_ops + lane);
+        double zk = 0.0;
+        for (uint32_t s = 0; s < P.b_nsteps; s++) {
+            const uint2 nhdr = __ldg(P.b_steps + s + 1);
+            const uint32_t nop = __ldg(P.b_ops + (s + 1) * TILE + lane);
+            if (hdr.x & kFirst) {
+                zk = w[hdr.y & 0xFFFFu] * L[hdr.x & 0xFFFFu];
+                if (lane == 0) delta[hdr.y >> 16] = zk;
+            }
             if (op != kNop) {
                 const uint32_t j = op & 0xFFFFu;
-                w[j] = fma(-work[op >> 16], zk, w[j]);
+                w[j] = fma(-L[op >> 16], zk, w[j]);
             }
+            if (TILE > 1 && (hdr.x & kLast)) TileOps<TILE>::sync(msk);
+            hdr = nhdr; op = nop;
         }
-        TileOps<TILE>::sync(msk);
     }
 }
 
 __device__ __forceinline__ uint64_t trace_push(uint64_t h, uint32_t code) { return h * 3ull + code + 1ull; }
 
+// The whole LM solve of one sketch by one tile.  The reference's nested loops (outer <= 100,
+// unbounded damping loop) are flattened into one loop over damping iterations with the outer
+// bookkeeping done at accept time, so that sketches sharing a warp (TILE < 32) stay in step.
 template <int TILE, int KIND>
 __global__ void __launch_bounds__(TILE > 128 ? TILE : 128)
 fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doubles,
@@ -190,109 +201,109 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
     if (sketch >= n_sketches) return;
     const unsigned msk = TileOps<TILE>::mask();
     const uint32_t n = P.n, m = P.m;
+    const uint32_t wlen = n > m ? n : m;
 
+    // per-sketch shared arrays; the stride is odd so that tiles of one warp touching the same
+    // element index land in different banks
     double* x = smem + (size_t)tile_id * stride_doubles;
     double* xs = x + n;
     double* g = xs + n;
-    double* w = g + n;
-    double* invd = w + n;
-    double* rneg = invd + n;
-    double* rs = rneg + m;
-    double* H0 = rs + m;
-    double* work = H0 + P.lnnz;
+    double* w = g + n;          // solve vector; the trial residuals live here outside the solve
+    double* rs = w;
+    double* J = w + wlen;       // Jacobian values at the accepted point (CSC order)
+    double* L = J + P.jnnz;     // LDLt factor; receives the trial Jacobian after the solve
 
     const double* vars = vars_all + (size_t)sketch * P.n_vars;
     const double* params = params_all + (size_t)sketch * P.n_expr;
 
     for (uint32_t i = lane; i < n; i += TILE) x[i] = __ldg(vars + __ldg(P.free_vars + i));
-    TileOps<TILE>::sync(msk);
+    if (TILE > 1) TileOps<TILE>::sync(msk);
 
-    // lm.rs:80-106: initial residuals + Jacobian, r := -r, ssr
-    for (uint32_t rd = 0; rd < P.eval_rounds; rd++) eval_row<KIND, true>(P, rd * TILE + lane, x, vars, params, rs, work);
-    TileOps<TILE>::sync(msk);
+    // lm.rs:80-106: initial residuals + Jacobian, ssr, g = J^T(-r)
+    for (uint32_t rd = 0; rd < P.eval_rounds; rd++) eval_row<KIND, true>(P, rd * TILE + lane, x, vars, params, rs, J);
+    if (TILE > 1) TileOps<TILE>::sync(msk);
     double ssr = sum_squares_seq(rs, m);
-    for (uint32_t i = lane; i < m; i += TILE) rneg[i] = -rs[i];
-    TileOps<TILE>::sync(msk);
-    assemble_tile<TILE>(P, lane, work, rneg, H0, g);
-    TileOps<TILE>::sync(msk);
+    accumulate_steps<TILE, true>(P.g_nsteps, P.g_flags, P.g_ops, P.g_dst, lane, J, rs, g);
+    if (TILE > 1) TileOps<TILE>::sync(msk);
 
     double lambda = 0.5;  // lm.rs:108
     uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
     uint64_t trace = 0;
-    bool done = false;
+    bool active = true;
+    if (ssr < 1e-8) {  // lm.rs:110-112 on the first outer iteration
+        exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+        active = false;
+    } else {
+        outer_iters = 1;
+    }
 
-    for (int outer = 0; outer < 100 && !done; outer++) {  // lm.rs:109
-        if (ssr < 1e-8) {                                   // lm.rs:110-112
-            exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+    while (active) {  // one pass == one iteration of the damping loop, lm.rs:115-191
+        if (!isfinite(lambda)) {
+            exit_reason = FK_EXIT_LAMBDA_OVERFLOW;
             break;
         }
-        outer_iters++;
-        for (;;) {  // lm.rs:115, unbounded in the reference
-            if (!isfinite(lambda)) {
-                exit_reason = FK_EXIT_LAMBDA_OVERFLOW;
-                done = true;
-                break;
-            }
-            // lm.rs:119-125: the damping entries are sqrt(lambda); their square lands on diag(H)
-            const double sl = sqrt(lambda);
-            const double lam2 = sl * sl;
-            for (uint32_t p = lane; p < P.lnnz; p += TILE) work[p] = H0[p];
-            for (uint32_t k = lane; k < n; k += TILE) w[k] = g[k];
-            TileOps<TILE>::sync(msk);
+        // lm.rs:119-125: the damping entries are sqrt(lambda); their square lands on diag(H)
+        const double sl = sqrt(lambda);
+        const double lam2 = sl * sl;
+        accumulate_steps<TILE, false>(P.a_nsteps, P.a_flags, P.a_ops, P.a_dst, lane, J, J, L);
+        for (uint32_t k = lane; k < n; k += TILE) w[k] = g[k];
+        if (TILE > 1) TileOps<TILE>::sync(msk);
 
-            const int fstat = factor_tile<TILE>(P, lane, msk, lam2, work, invd);  // replaces lm.rs:128
-            factorizations++;
-            if (fstat == 1) {  // lm.rs:134-137 (`!solved`)
-                lambda *= 8.0;
-                trace = trace_push(trace, 0);
-                TileOps<TILE>::sync(msk);
-                continue;
-            }
-            double ssr_s = NAN;
-            if (fstat == 0) {
-                solve_tile<TILE>(P, lane, msk, work, invd, w, xs);  // replaces lm.rs:130-132
-                if (sum_squares_seq(xs, n) < 1e-12) {               // lm.rs:139-142
-                    exit_reason = FK_EXIT_SMALL_STEP;
-                    done = true;
-                    break;
-                }
-                TileOps<TILE>::sync(msk);
-                for (uint32_t i = lane; i < n; i += TILE) xs[i] = x[i] + xs[i];  // lm.rs:144-146
-                TileOps<TILE>::sync(msk);
-                // lm.rs:148-149 (+ the Jacobian the accept branch would recompute at lm.rs:173-185)
-                for (uint32_t rd = 0; rd < P.eval_rounds; rd++)
-                    eval_row<KIND, true>(P, rd * TILE + lane, xs, vars, params, rs, work);
-                TileOps<TILE>::sync(msk);
-                ssr_s = sum_squares_seq(rs, m);
-            }
-            if (ssr_s < ssr) {  // lm.rs:151 (strict; NaN rejects)
-                lambda *= 0.125;
-                if (lambda < 1e-50) lambda = 1e-50;
-                accepted++;
-                trace = trace_push(trace, 1);
-                for (uint32_t i = lane; i < n; i += TILE) x[i] = xs[i];
-                if ((ssr - ssr_s) / ssr <= 1e-6) {  // lm.rs:164-168
-                    ssr = ssr_s;
-                    exit_reason = FK_EXIT_STALLED;
-                    done = true;
-                    TileOps<TILE>::sync(msk);
-                    break;
-                }
-                ssr = ssr_s;
-                for (uint32_t i = lane; i < m; i += TILE) rneg[i] = -rs[i];
-                TileOps<TILE>::sync(msk);
-                assemble_tile<TILE>(P, lane, work, rneg, H0, g);
-                TileOps<TILE>::sync(msk);
+        const int fstat = factor_tile<TILE>(P, lane, msk, lam2, L);  // replaces lm.rs:128
+        factorizations++;
+        if (fstat == 1) {  // lm.rs:134-137 (`!solved`)
+            lambda *= 8.0;
+            trace = trace_push(trace, 0);
+            if (TILE > 1) TileOps<TILE>::sync(msk);
+            continue;
+        }
+        double ssr_s = NAN;
+        if (fstat == 0) {
+            solve_tile<TILE>(P, lane, msk, L, w, xs);  // replaces lm.rs:130-132
+            if (sum_squares_seq(xs, n) < 1e-12) {      // lm.rs:139-142
+                exit_reason = FK_EXIT_SMALL_STEP;
                 break;
-            } else {  // lm.rs:187-190
-                lambda *= 2.0;
-                trace = trace_push(trace, 2);
-                TileOps<TILE>::sync(msk);
             }
+            if (TILE > 1) TileOps<TILE>::sync(msk);
+            for (uint32_t i = lane; i < n; i += TILE) xs[i] = x[i] + xs[i];  // lm.rs:144-146
+            if (TILE > 1) TileOps<TILE>::sync(msk);
+            // lm.rs:148-149 (+ the Jacobian the accept branch would recompute at lm.rs:173-185)
+            for (uint32_t rd = 0; rd < P.eval_rounds; rd++)
+                eval_row<KIND, true>(P, rd * TILE + lane, xs, vars, params, rs, L);
+            if (TILE > 1) TileOps<TILE>::sync(msk);
+            ssr_s = sum_squares_seq(rs, m);
+        }
+        if (ssr_s < ssr) {  // lm.rs:151 (strict; NaN rejects)
+            lambda *= 0.125;
+            if (lambda < 1e-50) lambda = 1e-50;
+            accepted++;
+            trace = trace_push(trace, 1);
+            for (uint32_t i = lane; i < n; i += TILE) x[i] = xs[i];
+            const bool stalled = (ssr - ssr_s) / ssr <= 1e-6;  // lm.rs:164-168
+            ssr = ssr_s;
+            if (stalled) {
+                exit_reason = FK_EXIT_STALLED;
+                break;
+            }
+            for (uint32_t i = lane; i < P.jnnz; i += TILE) J[i] = L[i];
+            if (TILE > 1) TileOps<TILE>::sync(msk);
+            accumulate_steps<TILE, true>(P.g_nsteps, P.g_flags, P.g_ops, P.g_dst, lane, J, rs, g);
+            if (TILE > 1) TileOps<TILE>::sync(msk);
+            // next outer iteration, lm.rs:109-112
+            if (outer_iters == 100) break;  // FK_EXIT_MAX_OUTER: the 100th outer iteration has ended
+            if (ssr < 1e-8) {
+                exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+                break;
+            }
+            outer_iters++;
+        } else {  // lm.rs:187-190
+            lambda *= 2.0;
+            trace = trace_push(trace, 2);
+            if (TILE > 1) TileOps<TILE>::sync(msk);
         }
     }
 
-    TileOps<TILE>::sync(msk);
+    if (TILE > 1) TileOps<TILE>::sync(msk);
     double* out = free_out + (size_t)sketch * n;
     for (uint32_t i = lane; i < n; i += TILE) out[i] = x[i];
     if (lane == 0) {
@@ -392,15 +403,18 @@ int measure_fp64_peak(double* tflops) {
 template <int TILE, int KIND>
 static int launch_lm_t(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                        double* free_out, fk_report* reports, cudaStream_t stream) {
-    const uint32_t stride = lm_smem_doubles(prog.n, prog.m, prog.jnnz, prog.lnnz);
+    const uint32_t stride = lm_smem_doubles(prog.n, prog.m, prog.jnnz, prog.lnnz) | 1u;  // odd: see kernel
     const size_t bytes_per_sketch = (size_t)stride * sizeof(double);
     int tiles_per_cta;
     if (TILE > 32) {
         tiles_per_cta = 1;
     } else {
-        tiles_per_cta = 128 / TILE;
-        const size_t budget = 64 * 1024;  // keep several CTAs resident per SM
-        while (tiles_per_cta > 1 && bytes_per_sketch * tiles_per_cta > budget) tiles_per_cta >>= 1;
+        // whole warps; as many as fit in ~1/3 of an SM's shared memory, at most 4 warps
+        const int tiles_per_warp = 32 / TILE;
+        int warps = 4;
+        while (warps > 1 && bytes_per_sketch * tiles_per_warp * warps > 72 * 1024) warps >>= 1;
+        tiles_per_cta = tiles_per_warp * warps;
+        if (bytes_per_sketch * tiles_per_cta > 220 * 1024) return (int)cudaErrorInvalidConfiguration;
     }
     const size_t smem = bytes_per_sketch * tiles_per_cta;
     cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_kernel<TILE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -422,6 +436,9 @@ int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* v
     if (n_sketches == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (prog.tile) {
+        case 1: return launch_lm_k<1>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 2: return launch_lm_k<2>(prog, n_sketches, vars, params, free_out, reports, s);
+        case 4: return launch_lm_k<4>(prog, n_sketches, vars, params, free_out, reports, s);
         case 8: return launch_lm_k<8>(prog, n_sketches, vars, params, free_out, reports, s);
         case 16: return launch_lm_k<16>(prog, n_sketches, vars, params, free_out, reports, s);
         case 32: return launch_lm_k<32>(prog, n_sketches, vars, params, free_out, reports, s);

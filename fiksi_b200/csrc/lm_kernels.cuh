@@ -13,32 +13,28 @@ namespace fk {
 struct DevProgram {
     uint32_t n_vars, n_expr, n, m, jnnz, lnnz, tile;
     int32_t uniform_kind;
-    uint32_t eval_rounds, asm_rounds, g_rounds, pad_;
+    uint32_t eval_rounds, a_nsteps, g_nsteps, f_nsteps, s_nsteps, b_nsteps;
     const uint32_t* free_vars;  // [n]
-    const int32_t* perm;        // [n]
     const uint32_t* row_hdr;    // [eval_rounds*tile]
     const uint2* row_slots;     // [rows][8] {source, jpos}
-    const uint32_t* asm_len;    // [asm_rounds]
-    const uint32_t* asm_first;
-    const uint32_t* asm_dst;    // [asm_rounds*tile]
-    const uint32_t* asm_ops;
-    const uint32_t* g_len;
-    const uint32_t* g_first;
-    const uint32_t* g_dst;
+    const uint32_t* a_flags;    // [a_nsteps+1]
+    const uint32_t* a_ops;      // [(a_nsteps+1)*tile]
+    const uint32_t* a_dst;
+    const uint32_t* g_flags;
     const uint32_t* g_ops;
-    const uint2* f_hdr;         // [n]
+    const uint32_t* g_dst;
+    const uint32_t* f_steps;    // [f_nsteps+1]
     const uint2* f_ops;
-    const uint2* s_hdr;         // [n]
+    const uint2* s_steps;       // [s_nsteps+1]
     const uint32_t* s_ops;
-    const uint2* b_hdr;         // [n]
+    const uint2* b_steps;       // [b_nsteps+1]
     const uint32_t* b_ops;
-    const uint32_t* diag_pos;   // [n]
 };
 
-// Shared-memory doubles one sketch needs: x, xs, g, w, invd (5n) + rneg, rs (2m) + H0 (lnnz) +
-// work (max(jnnz, lnnz)).
+// Shared-memory doubles one sketch needs: x, xs, g (3n) + w / trial residuals (max(n, m)) + J
+// (jnnz) + L / trial Jacobian (max(lnnz, jnnz)).
 __host__ __device__ inline uint32_t lm_smem_doubles(uint32_t n, uint32_t m, uint32_t jnnz, uint32_t lnnz) {
-    return 5u * n + 2u * m + lnnz + (jnnz > lnnz ? jnnz : lnnz);
+    return 3u * n + (n > m ? n : m) + jnnz + (jnnz > lnnz ? jnnz : lnnz);
 }
 
 // Launchers (defined in lm_kernels.cu).  `stream` is a cudaStream_t.

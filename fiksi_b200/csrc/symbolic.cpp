@@ -209,13 +209,13 @@ int Topology::build(const fk_problem& p) {
     // ---- path selection -----------------------------------------------------------------------------
     {
         uint64_t work = std::max<uint64_t>(jac_nnz, lnnz);
-        uint64_t dbl = 5ull * n + 2ull * m + lnnz + work;  // == lm_smem_doubles()
+        uint64_t dbl = 3ull * n + std::max(n, m) + jac_nnz + work;  // == lm_smem_doubles()
         uint64_t bytes = dbl * 8;
         smem_bytes = (uint32_t)std::min<uint64_t>(bytes, 0xFFFFFFFFu);
         uint32_t w = std::max(m, n);
         if (bytes <= 24 * 1024 && n_updates < (1u << 22)) {
             path = 0;
-            tile = w <= 10 ? 8 : (w <= 20 ? 16 : 32);
+            tile = w <= 12 ? 8 : (w <= 96 ? 16 : 32);  // measured on B200: 16 lanes beat 8 and 32 on the 20-point truss
         } else if (bytes <= 200 * 1024 && n_updates < (1u << 25)) {
             path = 1;
             tile = 256;
@@ -225,7 +225,7 @@ int Topology::build(const fk_problem& p) {
         }
         if (const char* t = std::getenv("FK_TILE")) {
             int v = std::atoi(t);
-            if (path == 0 && (v == 8 || v == 16 || v == 32)) tile = (uint32_t)v;
+            if (path == 0 && (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32)) tile = (uint32_t)v;
         }
     }
 
@@ -331,77 +331,83 @@ int Topology::build_tables() {
             t.row_slots[((size_t)r * 8 + s) * 2 + 1] = pos;
         }
     }
-    // ---- contribution lists, longest first, so every round has a uniform length -------------------
+    const uint32_t FIRST = 1u << 16, LAST = 1u << 17;
+    // ---- contribution lists, longest first, so that the lanes of a step group finish together -----
     auto pack_lists = [&](const std::vector<uint32_t>& ptr, const std::vector<uint32_t>& pairs, uint32_t count,
-                          std::vector<uint32_t>& len, std::vector<uint32_t>& first, std::vector<uint32_t>& dst,
-                          std::vector<uint32_t>& ops) {
+                          uint32_t& nsteps, std::vector<uint32_t>& flags, std::vector<uint32_t>& ops,
+                          std::vector<uint32_t>& dst) {
         std::vector<uint32_t> order(count);
         for (uint32_t i = 0; i < count; i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
             return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
         });
-        uint32_t rounds = (count + T - 1) / T;
-        len.assign(rounds, 0); first.assign(rounds, 0); dst.assign((size_t)rounds * T, NOP);
-        ops.clear();
-        for (uint32_t rd = 0; rd < rounds; rd++) {
-            uint32_t L = 0;
-            for (uint32_t l = 0; l < T && rd * T + l < count; l++) {
-                uint32_t e = order[rd * T + l];
-                L = std::max(L, ptr[e + 1] - ptr[e]);
-                dst[(size_t)rd * T + l] = e;
-            }
-            len[rd] = L;
-            first[rd] = (uint32_t)(ops.size() / T);
-            ops.resize(ops.size() + (size_t)L * T, NOP);
-            for (uint32_t l = 0; l < T && rd * T + l < count; l++) {
-                uint32_t e = order[rd * T + l];
+        flags.clear(); ops.clear(); dst.clear();
+        for (uint32_t at = 0; at < count; at += T) {
+            uint32_t lanes = std::min(T, count - at), len = 1;
+            for (uint32_t l = 0; l < lanes; l++) len = std::max(len, ptr[order[at + l] + 1] - ptr[order[at + l]]);
+            size_t base = flags.size();
+            for (uint32_t k = 0; k < len; k++) flags.push_back((k == 0 ? FIRST : 0) | (k + 1 == len ? LAST : 0));
+            ops.resize((base + len) * T, NOP);
+            dst.resize((base + len) * T, NOP);
+            for (uint32_t l = 0; l < lanes; l++) {
+                uint32_t e = order[at + l];
                 for (uint32_t q = ptr[e], k = 0; q < ptr[e + 1]; q++, k++)
-                    ops[((size_t)first[rd] + k) * T + l] = pairs[2 * (size_t)q] | (pairs[2 * (size_t)q + 1] << 16);
+                    ops[(base + k) * T + l] = pairs[2 * (size_t)q] | (pairs[2 * (size_t)q + 1] << 16);
+                dst[(base + len - 1) * T + l] = e;
             }
         }
+        nsteps = (uint32_t)flags.size();
+        flags.push_back(0);  // prefetch padding
+        ops.resize(ops.size() + T, NOP);
+        dst.resize(dst.size() + T, NOP);
     };
-    pack_lists(h_ptr, h_pairs, lnnz, t.asm_len, t.asm_first, t.asm_dst, t.asm_ops);
-    pack_lists(g_ptr, g_pairs, n, t.g_len, t.g_first, t.g_dst, t.g_ops);
-    // ---- LDLt updates per column ---------------------------------------------------------------------
-    t.f_hdr.assign((size_t)n * 2, 0);
-    t.f_ops.clear();
-    t.diag_pos.resize(n);
+    pack_lists(h_ptr, h_pairs, lnnz, t.a_nsteps, t.a_flags, t.a_ops, t.a_dst);
+    pack_lists(g_ptr, g_pairs, n, t.g_nsteps, t.g_flags, t.g_ops, t.g_dst);
+    // ---- LDLt: one or more steps per column --------------------------------------------------------
+    t.f_steps.clear(); t.f_ops.clear();
     for (uint32_t k = 0; k < n; k++) {
         uint32_t cnt = u_ptr[k + 1] - u_ptr[k];
-        uint32_t rounds = (cnt + T - 1) / T;
-        if (rounds >= 0xFFFF) { error = "column update list too long"; return FK_ERR_TOO_LARGE; }
-        t.diag_pos[k] = l_colptr[k];
-        t.f_hdr[2 * (size_t)k] = l_colptr[k] | (rounds << 16);
-        t.f_hdr[2 * (size_t)k + 1] = (uint32_t)(t.f_ops.size() / 2 / T);
-        size_t base = t.f_ops.size();
-        t.f_ops.resize(base + (size_t)rounds * T * 2, NOP);
+        uint32_t rounds = std::max(1u, (cnt + T - 1) / T);
+        size_t base = t.f_steps.size();
+        for (uint32_t r = 0; r < rounds; r++)
+            t.f_steps.push_back(l_colptr[k] | (r == 0 ? FIRST : 0) | (r + 1 == rounds ? LAST : 0));
+        t.f_ops.resize((base + rounds) * T * 2, NOP);
         for (uint32_t q = 0; q < cnt; q++) {
             const uint32_t* tr = &u_trip[3 * (size_t)(u_ptr[k] + q)];
-            t.f_ops[base + 2 * (size_t)q] = tr[0] | (tr[1] << 16);
-            t.f_ops[base + 2 * (size_t)q + 1] = tr[2];
+            t.f_ops[(base * T + q) * 2] = tr[0] | (tr[1] << 16);
+            t.f_ops[(base * T + q) * 2 + 1] = tr[2];
         }
     }
-    // ---- triangular solves: column k -> its off-diagonal entries ---------------------------------------
-    auto pack_cols = [&](bool backward, std::vector<uint32_t>& hdr, std::vector<uint32_t>& ops) {
-        hdr.assign((size_t)n * 2, 0);
-        ops.clear();
-        for (uint32_t k = 0; k < n; k++) {
+    t.f_nsteps = (uint32_t)t.f_steps.size();
+    t.f_steps.push_back(0);
+    t.f_ops.resize(t.f_ops.size() + (size_t)T * 2, NOP);
+    // ---- triangular solves ---------------------------------------------------------------------------
+    auto pack_cols = [&](bool backward, uint32_t& nsteps, std::vector<uint32_t>& steps, std::vector<uint32_t>& ops) {
+        steps.clear(); ops.clear();
+        for (uint32_t kk = 0; kk < n; kk++) {
+            uint32_t k = backward ? n - 1 - kk : kk;
             std::vector<uint32_t> list;
             if (!backward) {
                 for (uint32_t q = l_colptr[k] + 1; q < l_colptr[k + 1]; q++) list.push_back(l_rowidx[q] | (q << 16));
+                if (list.empty()) continue;  // nothing below the diagonal: w[k] is already final
             } else {
                 for (uint32_t q = r_colptr[k]; q + 1 < r_colptr[k + 1]; q++) list.push_back(r_rowidx[q] | (r_lpos[q] << 16));
             }
-            uint32_t rounds = ((uint32_t)list.size() + T - 1) / T;
-            hdr[2 * (size_t)k] = rounds;
-            hdr[2 * (size_t)k + 1] = (uint32_t)(ops.size() / T);
-            size_t base = ops.size();
-            ops.resize(base + (size_t)rounds * T, NOP);
-            for (size_t q = 0; q < list.size(); q++) ops[base + q] = list[q];
+            uint32_t rounds = std::max<uint32_t>(1, ((uint32_t)list.size() + T - 1) / T);
+            size_t base = steps.size() / 2;
+            for (uint32_t r = 0; r < rounds; r++) {
+                steps.push_back(l_colptr[k] | (r == 0 ? FIRST : 0) | (r + 1 == rounds ? LAST : 0));
+                steps.push_back(backward ? (k | ((uint32_t)perm[k] << 16)) : k);
+            }
+            ops.resize((base + rounds) * T, NOP);
+            for (size_t q = 0; q < list.size(); q++) ops[base * T + q] = list[q];
         }
+        nsteps = (uint32_t)(steps.size() / 2);
+        steps.push_back(0); steps.push_back(0);
+        ops.resize(ops.size() + T, NOP);
     };
-    pack_cols(false, t.s_hdr, t.s_ops);
-    pack_cols(true, t.b_hdr, t.b_ops);
+    pack_cols(false, t.s_nsteps, t.s_steps, t.s_ops);
+    pack_cols(true, t.b_nsteps, t.b_steps, t.b_ops);
     return FK_OK;
 }
 

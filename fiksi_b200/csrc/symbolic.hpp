@@ -80,18 +80,18 @@ struct Topology {
         uint32_t eval_rounds = 0;           // ceil(m / tile)
         std::vector<uint32_t> row_hdr;      // [eval_rounds*tile] kind | expr << 8, NOP for padding
         std::vector<uint32_t> row_slots;    // [rows][8][2]: {source, jpos}: source = col | 0x80000000|var
-        std::vector<uint32_t> asm_len;      // [asm_rounds] products per entry in this round
-        std::vector<uint32_t> asm_first;    // [asm_rounds] first op slab
-        std::vector<uint32_t> asm_dst;      // [asm_rounds*tile] H0 position or NOP
-        std::vector<uint32_t> asm_ops;      // [slabs*tile] ja | jb << 16
-        std::vector<uint32_t> g_len, g_first, g_dst, g_ops;  // same for g: jpos | row << 16
-        std::vector<uint32_t> f_hdr;        // [n][2]: {diag position | rounds << 16, first round}
-        std::vector<uint32_t> f_ops;        // [rounds*tile][2]: {dst | a << 16, b}
-        std::vector<uint32_t> s_hdr;        // [n][2]: forward substitution {rounds, first round}
-        std::vector<uint32_t> s_ops;        // [rounds*tile]: row | lpos << 16
-        std::vector<uint32_t> b_hdr;        // [n][2]: backward substitution
-        std::vector<uint32_t> b_ops;        // [rounds*tile]: row | lpos << 16
-        std::vector<uint32_t> diag_pos;     // [n]
+        // Every sequential phase is a flat list of steps; step s executes ops[s*tile + lane].  Step
+        // flags: bit 16 = first step of a column / accumulation, bit 17 = last (barrier / store).
+        // Each list carries one padding step at the end so the kernel can prefetch step s+1.
+        uint32_t a_nsteps = 0, g_nsteps = 0, f_nsteps = 0, s_nsteps = 0, b_nsteps = 0;
+        std::vector<uint32_t> a_flags, a_ops, a_dst;  // H = JtJ: ops ja | jb << 16, dst = L position
+        std::vector<uint32_t> g_flags, g_ops, g_dst;  // g = Jt r: ops jpos | row << 16, dst = column
+        std::vector<uint32_t> f_steps;      // LDLt: diag position | flags
+        std::vector<uint32_t> f_ops;        // [steps*tile][2]: {dst | a << 16, b}
+        std::vector<uint32_t> s_steps;      // forward substitution [steps][2]: {diag position | flags, k}
+        std::vector<uint32_t> s_ops;        // row | lpos << 16
+        std::vector<uint32_t> b_steps;      // backward substitution [steps][2]: {diag position | flags, k | perm[k] << 16}
+        std::vector<uint32_t> b_ops;        // row | lpos << 16
     } tab;
     int build_tables();
 

@@ -135,7 +135,7 @@ def test_tile_variants_agree():
     w = wl.cad_mix(1024)
     v, p, scale = w.prepare()
     outs = []
-    for tile in ("8", "16", "32"):
+    for tile in ("1", "2", "4", "8", "16", "32"):
         os.environ["FK_TILE"] = tile
         topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
         assert topo.info["tile"] == int(tile)
@@ -146,11 +146,11 @@ def test_tile_variants_agree():
 
 
 def test_cta_path_hinged64(oracle):
-    # 258 free variables: one CTA per sketch (path 1)
-    w = wl.hinged_triangles(64, n_sketches=3)
+    # 514 free variables, ~50 KB of shared state: one CTA per sketch (path 1)
+    w = wl.hinged_triangles(128, n_sketches=3)
     v, p, scale = w.prepare()
     topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
-    assert topo.info["path"] == 1
+    assert topo.info["path"] == 1 and topo.info["tile"] == 256
     xg, rg = topo.batch_solve(v, p)
     op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
     xo, ro, _ = oracle.lm_solve_batch_uniform(op, v, p)

@@ -35,7 +35,7 @@ def test_truss_topology(oracle):
     topo = _compare(oracle, (v[0], w.kind, w.idx, p[0], w.free_vars, w.rows))
     i = topo.info
     assert (i["n_free"], i["n_rows"], i["jac_nnz"], i["aug_nnz"]) == (40, 37, 148, 188)
-    assert i["path"] == 0 and i["tile"] == 32
+    assert i["path"] == 0 and i["tile"] == 16
 
 
 def test_cad_mix_topology_matches_reference_example(oracle):
