@@ -51,6 +51,7 @@ EXPORTS = [
     "fk_batch_plan_run", "fk_batch_plan_download", "fk_batch_plan_device_ptrs",
     "fk_batch_plan_launches", "fk_host_alloc", "fk_host_free", "fk_batch_plan_eval",
     "fk_batch_plan_eval_download", "fk_batch_solve_device", "fk_fp64_peak_tflops",
+    "fk_topology_lm_solve", "fk_topology_eval", "fk_topology_last_timing",
 ]
 
 _lib = None

@@ -61,6 +61,32 @@ class Topology:
         check(lib().fk_batch_solve_device(self._h, device, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr),
                                           C.c_void_p(out_ptr), C.c_void_p(rep_ptr)))
 
+    def lm_solve(self, vars_, param, free_values):
+        """fk_topology_lm_solve: one system, symbolic analysis reused."""
+        vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+        param = np.ascontiguousarray(param, dtype=np.float64)
+        x = np.array(free_values, dtype=np.float64)
+        rep = FkReport()
+        check(lib().fk_topology_lm_solve(self._h, ptr(vars_, C.c_double), ptr(param, C.c_double), ptr(x, C.c_double), C.byref(rep)))
+        return x, report_dict(rep)
+
+    def eval_large(self, vars_, param, free_values, repeats=0, want_j=True):
+        vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+        param = np.ascontiguousarray(param, dtype=np.float64)
+        x = np.ascontiguousarray(free_values, dtype=np.float64)
+        r = np.zeros(max(self.info["n_rows"], 1))
+        j = np.zeros(max(self.info["jac_nnz"], 1)) if want_j else None
+        ms = C.c_float(0.0)
+        check(lib().fk_topology_eval(self._h, ptr(vars_, C.c_double), ptr(param, C.c_double), ptr(x, C.c_double),
+                                     ptr(r, C.c_double), ptr(j, C.c_double) if want_j else None, repeats, C.byref(ms)))
+        return r[:self.info["n_rows"]], (j[:self.info["jac_nnz"]] if want_j else None), ms.value
+
+    def last_timing(self):
+        out = (C.c_float * 8)()
+        check(lib().fk_topology_last_timing(self._h, out))
+        return {"eval_ms": out[0], "assemble_ms": out[1], "factor_ms": out[2], "tri_ms": out[3],
+                "evals": int(out[4]), "factors": int(out[5])}
+
     def plan(self, capacity, device=0):
         return BatchPlan(self, capacity, device)
 

@@ -14,6 +14,7 @@
 
 #include "../../include/fiksi_b200.h"
 #include "lm_kernels.cuh"
+#include "sparse_path.cuh"
 #include "symbolic.hpp"
 
 namespace {
@@ -123,6 +124,20 @@ struct fk_topology {
     std::mutex mu;
     std::map<int, std::unique_ptr<DeviceProgram>> programs;
     std::map<int, std::unique_ptr<DevicePipeline>> pipelines;
+    std::map<int, std::unique_ptr<fk::SparseSolver>> sparse;  // path 2: one solver per device
+
+    int sparse_for(int device, fk::SparseSolver** out, std::string* err) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto& p = sparse[device];
+        if (!p) {
+            std::unique_ptr<fk::SparseSolver> s(new fk::SparseSolver());
+            int rc = s->init(t, device, err);
+            if (rc != FK_OK) return rc;
+            p = std::move(s);
+        }
+        *out = p.get();
+        return FK_OK;
+    }
 
     DevicePipeline* pipeline_for(int device) {
         std::lock_guard<std::mutex> lock(mu);
@@ -420,6 +435,59 @@ int fk_batch_solve(const fk_topology* topo_c, uint32_t n, const double* vars, co
     return FK_OK;
 }
 
+// ---- single system with a cached topology (any path) --------------------------------------------------
+int fk_topology_lm_solve(fk_topology* topo, const double* vars, const double* param, double* free_values,
+                         fk_report* report) {
+    if (!topo || !free_values || (!vars && topo->t.n_vars)) return fail(FK_ERR_INVALID, "null argument");
+    int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    const fk::Topology& t = topo->t;
+    if (t.path == 2) {
+        fk::SparseSolver* sp = nullptr;
+        std::string err;
+        int rc = topo->sparse_for(cur, &sp, &err);
+        if (rc != FK_OK) return fail(rc, err);
+        // the caller's free values are the starting point (== `variables` of lm.rs:21)
+        rc = sp->solve(vars, param, free_values, report, &err);
+        return rc == FK_OK ? FK_OK : fail(rc, err);
+    }
+    std::vector<double> v(vars, vars + t.n_vars), out(std::max<uint32_t>(1, t.n_free));
+    for (uint32_t f = 0; f < t.n_free; f++) v[t.free_vars[f]] = free_values[f];
+    std::vector<double> zero;
+    if (!param && t.n_expr) zero.assign(t.n_expr, 0.0);
+    int rc = run_device_range(topo, cur, 0, 1, v.data(), param ? param : zero.data(), out.data(), report, nullptr);
+    if (rc == FK_OK && t.n_free) std::memcpy(free_values, out.data(), sizeof(double) * t.n_free);
+    return rc;
+}
+
+int fk_topology_eval(fk_topology* topo, const double* vars, const double* param, const double* free_values,
+                     double* out_r, double* out_j, int repeats, float* ms_per_eval) {
+    if (!topo || !vars || !free_values) return fail(FK_ERR_INVALID, "null argument");
+    if (usable_devices() == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (topo->t.path != 2) return fail(FK_ERR_INVALID, "fk_topology_eval serves the global sparse path; use fk_batch_plan_eval");
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    fk::SparseSolver* sp = nullptr;
+    std::string err;
+    int rc = topo->sparse_for(cur, &sp, &err);
+    if (rc == FK_OK) rc = sp->eval_once(vars, param, free_values, out_r, out_j, repeats, ms_per_eval, &err);
+    return rc == FK_OK ? FK_OK : fail(rc, err);
+}
+
+int fk_topology_last_timing(fk_topology* topo, float* out8) {
+    if (!topo || !out8) return fail(FK_ERR_INVALID, "null argument");
+    std::memset(out8, 0, 8 * sizeof(float));
+    std::lock_guard<std::mutex> lock(topo->mu);
+    for (auto& kv : topo->sparse) {
+        const auto& l = kv.second->last;
+        out8[0] = l.eval_ms; out8[1] = l.assemble_ms; out8[2] = l.factor_ms; out8[3] = l.tri_ms;
+        out8[4] = (float)l.evals; out8[5] = (float)l.factors;
+    }
+    return FK_OK;
+}
+
 // ---- general entry points ------------------------------------------------------------------------------
 int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* const* free_values, fk_report* reports,
                       int n_gpus) {
@@ -472,7 +540,14 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
     for (Group& gr : groups) {
         const fk::Topology& t = gr.topo->t;
         const size_t cnt = gr.members.size();
-        if (t.path == 2) return fail(FK_ERR_TOO_LARGE, "problem needs the global sparse path, which fk_lm_solve_batch does not take");
+        if (t.path == 2) {  // large systems: one after the other through the global sparse path
+            for (uint32_t i : gr.members) {
+                int rc = fk_topology_lm_solve(gr.topo.get(), problems[i]->vars, problems[i]->param, free_values[i],
+                                              reports ? &reports[i] : nullptr);
+                if (rc != FK_OK) return rc;
+            }
+            continue;
+        }
         std::vector<double> vars(cnt * t.n_vars), param(cnt * std::max<uint32_t>(t.n_expr, 1)), out(cnt * std::max<uint32_t>(t.n_free, 1));
         std::vector<fk_report> reps(cnt);
         for (size_t k = 0; k < cnt; k++) {

@@ -223,6 +223,9 @@ int Topology::build(const fk_problem& p) {
             path = 2;
             tile = 0;
         }
+        if (const char* f = std::getenv("FK_FORCE_PATH")) {
+            if (std::atoi(f) == 2) { path = 2; tile = 0; }
+        }
         if (const char* t = std::getenv("FK_TILE")) {
             int v = std::atoi(t);
             if (path == 0 && (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32)) tile = (uint32_t)v;
@@ -300,15 +303,15 @@ int Topology::build(const fk_problem& p) {
             u_ptr[k + 1] = (uint32_t)(u_trip.size() / 3);
         }
     }
-    return path == 2 ? FK_OK : build_tables();
+    return build_tables();
 }
 
 // Lane-padded op tables for the shared-memory kernel (see Topology::Tables).
 int Topology::build_tables() {
-    const uint32_t n = n_free, m = n_rows, T = tile;
+    const uint32_t n = n_free, m = n_rows, T = path == 2 ? 1 : tile;
     const uint32_t NOP = 0xFFFFFFFFu;
     const uint32_t lnnz = (uint32_t)l_rowidx.size();
-    if (lnnz >= 0xFFFF || jac_nnz >= 0xFFFF || n >= 0xFFFF || m >= 0xFFFF || n_expr >= (1u << 24)) {
+    if (path != 2 && (lnnz >= 0xFFFF || jac_nnz >= 0xFFFF || n >= 0xFFFF || m >= 0xFFFF || n_expr >= (1u << 24))) {
         error = "problem too large for the 16-bit shared-memory tables";
         return FK_ERR_TOO_LARGE;
     }
@@ -331,6 +334,7 @@ int Topology::build_tables() {
             t.row_slots[((size_t)r * 8 + s) * 2 + 1] = pos;
         }
     }
+    if (path == 2) return FK_OK;  // the global sparse path builds its own schedules (sparse_path.cu)
     const uint32_t FIRST = 1u << 16, LAST = 1u << 17;
     // ---- contribution lists, longest first, so that the lanes of a step group finish together -----
     auto pack_lists = [&](const std::vector<uint32_t>& ptr, const std::vector<uint32_t>& pairs, uint32_t count,

@@ -138,6 +138,21 @@ FK_API int fk_symbolic(const fk_problem* problem, uint32_t* aug_colptr, uint32_t
                        int32_t* colamd_perm, int32_t* etree_parent, uint32_t* r_colptr,
                        uint32_t* r_rowidx);
 
+/* Solve one system with an existing topology (symbolic analysis reused across calls).  Takes the
+ * batched shared-memory kernel with n = 1 or, for large systems (info.path == 2), the global
+ * sparse path: K1/K2 evaluation, K3 normal-equation assembly and K5 sparse LDL^T on the device with
+ * a thin host loop for the accept/reject decisions. */
+FK_API int fk_topology_lm_solve(fk_topology* topo, const double* vars, const double* param,
+                                double* free_values, fk_report* report);
+/* Large systems only: one residual + Jacobian evaluation at free_values (out_r[n_rows],
+ * out_j[jac_nnz] in CSC order, either may be NULL), timed over `repeats` launches. */
+FK_API int fk_topology_eval(fk_topology* topo, const double* vars, const double* param,
+                            const double* free_values, double* out_r, double* out_j, int repeats,
+                            float* ms_per_eval);
+/* Phase times of the last large-system solve: out8 = {eval ms, assemble ms, factor ms,
+ * triangular-solve ms, evaluations, factorisations, 0, 0}. */
+FK_API int fk_topology_last_timing(fk_topology* topo, float* out8);
+
 /* ---- Levenberg–Marquardt ----------------------------------------------------------------- */
 /* == levenberg_marquardt(problem, variables), fiksi/src/solve/lm.rs:21.  free_values in/out,
  * length n_free.  Picks the batched kernel (n = 1) or the large sparse path by size. */

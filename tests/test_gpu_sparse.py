@@ -1,0 +1,109 @@
+"""GPU parity of the large single-system path (BASELINE config 3): global-memory evaluation (K1/K2),
+normal-equation assembly (K3) and the tree-scheduled sparse LDL^T with sync-free triangular solves
+(K5), driven by fk_topology_lm_solve.  Small problems are forced onto this path with
+FK_FORCE_PATH=2 so that the CPU oracle can check them."""
+import os
+
+import numpy as np
+import pytest
+
+import scenarios as sc
+import fiksi_b200 as fk
+from fiksi_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+REL = 1e-9
+
+
+@pytest.fixture
+def force_sparse():
+    os.environ["FK_FORCE_PATH"] = "2"
+    yield
+    os.environ.pop("FK_FORCE_PATH", None)
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if len(b) else 0.0
+
+
+def _check_against_oracle(oracle, keep, scale=1.0):
+    vars_, kind, idx, param, free_vars, rows = keep
+    op, okeep = oracle.make_problem(*keep)
+    x0 = vars_[free_vars]
+    xo, ro, trace = oracle.lm_solve(op, x0)
+    topo = fk.Topology.from_arrays(len(vars_), kind, idx, free_vars, rows)
+    assert topo.info["path"] == 2
+    xg, rg = topo.lm_solve(vars_, param, x0)
+    assert rg["exit_reason"] == ro["exit_reason"], (trace, rg, ro)
+    assert rg["trace_hash"] == ro["trace_hash"], (trace, rg, ro)
+    assert (rg["outer_iters"], rg["factorizations"], rg["accepted"]) == (ro["outer_iters"], ro["factorizations"], ro["accepted"])
+    assert rg["lambda"] == ro["lambda"]
+    assert _rel(xg, xo) <= REL, _rel(xg, xo)
+    assert abs(rg["ssr"] - ro["ssr"]) <= REL * max(ro["ssr"], 1.0)
+    return topo
+
+
+@pytest.mark.parametrize("name", sorted(sc.ALL))
+def test_reference_scenarios_on_sparse_path(oracle, force_sparse, name):
+    b = sc.ALL[name](oracle.System)
+    for prob, scale, keep in b["s"].prepare(perturb=True):
+        _check_against_oracle(oracle, keep)
+
+
+@pytest.mark.parametrize("nx,ny", [(5, 4), (12, 9)])
+def test_small_lattices_forced(oracle, force_sparse, nx, ny):
+    w = wl.lattice(nx, ny)
+    v, p, scale = w.prepare()
+    _check_against_oracle(oracle, (v[0], w.kind, w.idx, p[0], w.free_vars, w.rows))
+
+
+def test_medium_lattice_natural_path(oracle):
+    w = wl.lattice(30, 20)  # 1,200 free variables: takes the sparse path by size
+    v, p, scale = w.prepare()
+    topo = _check_against_oracle(oracle, (v[0], w.kind, w.idx, p[0], w.free_vars, w.rows))
+    t = topo.last_timing()
+    assert t["factors"] >= 1 and t["evals"] == t["factors"] + 1
+
+
+def test_large_eval_bit_exact(oracle):
+    w = wl.lattice(40, 30)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    assert topo.info["path"] == 2
+    r, j, ms = topo.eval_large(v[0], p[0], v[0][w.free_vars], repeats=3)
+    op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+    ro, jo = oracle.evaluate(op, v[0][w.free_vars], jac_nnz=topo.info["jac_nnz"])
+    assert np.array_equal(r, ro) and np.array_equal(j, jo) and ms > 0
+
+
+def test_batch_entry_routes_large_problems(oracle):
+    w = wl.lattice(30, 20)
+    v, p, scale = w.prepare()
+    fp, keep = fk.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+    x0 = v[0][w.free_vars]
+    xg, rg = fk.lm_solve(fp, x0)
+    op, okeep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+    xo, ro, _ = oracle.lm_solve(op, x0)
+    assert rg["trace_hash"] == ro["trace_hash"] and _rel(xg, xo) <= REL
+
+
+def test_config3_full_lattice_properties():
+    """BASELINE config 3 at full size (200,000 variables, 298,701 rows).  The oracle cannot run it
+    (O(m n) scratch per factorisation); size-independent checks: residual exit, every edge at its
+    length, a second solve from the solution is a fixed point, deterministic re-run."""
+    w = wl.lattice(400, 250)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    i = topo.info
+    assert (i["n_free"], i["n_rows"], i["jac_nnz"]) == (200000, 298701, 1194804)
+    x0 = v[0][w.free_vars]
+    x, rep = topo.lm_solve(v[0], p[0], x0)
+    assert rep["exit_reason"] == 0 and rep["ssr"] < 1e-8
+    v1 = v[0].copy(); v1[w.free_vars] = x
+    r, _, _ = topo.eval_large(v1, p[0], x, want_j=False)
+    assert abs(float(np.sum(r * r)) - rep["ssr"]) <= 1e-12 * max(rep["ssr"], 1e-30) + 1e-24
+    assert np.max(np.abs(r)) < 1e-4
+    x2, rep2 = topo.lm_solve(v1, p[0], x)
+    assert rep2["factorizations"] == 0 and np.array_equal(x2, x)
+    x3, rep3 = topo.lm_solve(v[0], p[0], x0)
+    assert np.array_equal(x3, x) and rep3["trace_hash"] == rep["trace_hash"]
