@@ -5,3 +5,4 @@ ctypes face used by the tests and the benchmark.
 """
 from ._lib import FiksiError, FkProblem, FkReport, REPORT_DTYPE, LIB_PATH, lib, make_problem  # noqa: F401
 from .api import BatchPlan, Topology, device_count, fp64_peak_tflops, lm_solve, lm_solve_batch  # noqa: F401
+from .system import System  # noqa: F401

@@ -51,7 +51,12 @@ EXPORTS = [
     "fk_batch_plan_run", "fk_batch_plan_download", "fk_batch_plan_device_ptrs",
     "fk_batch_plan_launches", "fk_host_alloc", "fk_host_free", "fk_batch_plan_eval",
     "fk_batch_plan_eval_download", "fk_batch_solve_device", "fk_fp64_peak_tflops",
-    "fk_topology_lm_solve", "fk_topology_eval", "fk_topology_last_timing",
+    "fk_topology_lm_solve", "fk_topology_eval", "fk_topology_last_timing", "fk_batch_plan_sync",
+    "fk_system_create", "fk_system_destroy", "fk_system_add_length", "fk_system_add_point", "fk_system_add_line",
+    "fk_system_add_circle", "fk_system_fix", "fk_system_add_constraint", "fk_system_num_variables",
+    "fk_system_num_constraints", "fk_system_element_variable", "fk_system_get_variables", "fk_system_set_variable",
+    "fk_system_set_parameter", "fk_system_solve", "fk_system_residuals", "fk_system_num_components",
+    "fk_system_component",
 ]
 
 _lib = None

@@ -310,6 +310,13 @@ int fk_batch_plan_device_ptrs(fk_batch_plan* plan, void** vars, void** param, vo
 
 uint64_t fk_batch_plan_launches(const fk_batch_plan* plan) { return plan ? plan->launches : 0; }
 
+int fk_batch_plan_sync(fk_batch_plan* plan) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    CU(cudaSetDevice(plan->device));
+    CU(cudaDeviceSynchronize());
+    return FK_OK;
+}
+
 int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream) {
     if (!plan) return fail(FK_ERR_INVALID, "null plan");
     const fk::Topology& t = plan->topo->t;

@@ -16,7 +16,9 @@ namespace fk {
 namespace {
 
 constexpr uint32_t kNop = 0xFFFFFFFFu;
-constexpr int kFactorThreads = 256;
+constexpr int kFactorThreads = 512;
+constexpr int kMaxTeam = 16;           // CTAs that may share one column of the factorisation
+constexpr uint32_t kTeamWork = 16384;   // multiply-adds per CTA above which a column is split
 constexpr int kFactorWarps = kFactorThreads / 32;
 
 struct SparseDev {
@@ -42,6 +44,12 @@ struct SparseDev {
     const uint32_t* nchildren;
     const uint32_t* order_up;    // columns by ascending height above the leaves
     const uint32_t* order_down;  // reverse
+    const uint2* tasks;          // factor tasks {column, part | parts << 16}, by ascending height
+    uint32_t n_tasks, pad0;
+    const uint64_t* team_off;    // [n] offset of a split column's partial accumulators (doubles), ~0 if not split
+    double* team_acc;            // partial accumulators of split columns
+    int* arrive;                 // [n] parts of a split column that have delivered
+    double* Rval;                // [lnnz] (L D) D^-1 in row-major (R = L^T CSC) order for the forward solve
     // mutable state
     double* Lval;
     double* invd;
@@ -107,6 +115,7 @@ __global__ void __launch_bounds__(256) sparse_arm_kernel(SparseDev S, double lam
         S.pending[k] = c;
         S.pending_s[k] = c;
         S.done[k] = 0;
+        S.arrive[k] = 0;
     }
     if (blockIdx.x == 0 && threadIdx.x < 4) S.counters[threadIdx.x] = 0;
 }
@@ -121,16 +130,26 @@ sparse_gradient_kernel(SparseDev S, const double* __restrict__ J, const double* 
     }
 }
 
-// ---- K5: left-looking LDLt, one CTA per column, elimination-tree driven --------------------------------
+// ---- K5: left-looking LDLt, elimination-tree driven ------------------------------------------------
 // Column j of (L D): u(i,j) = H(i,j) - sum_{k in row j of L} u(i,k) * u(j,k) / d_k, i >= j.
-// A CTA claims columns in order of height above the leaves and starts a column once all of its
-// children (hence all descendants) are finished.  Warps take the k's round-robin and accumulate
-// into private shared-memory accumulators which are then summed in warp order, so the result does
-// not depend on timing.
+// A CTA claims tasks in order of height above the leaves and starts a column once all of its
+// children (hence all descendants) are finished.  Heavy columns (the dense chain at the top of the
+// tree) are split into up to kMaxTeam tasks that take the k's round-robin; every task sums its
+// warps' private shared-memory accumulators in warp order, split columns park the partial sums in
+// HBM and the last task to arrive adds them in part order — the result never depends on timing.
+__device__ __forceinline__ void finalize_column(const SparseDev& S, uint32_t j, uint32_t p0, uint32_t i, double v) {
+    S.Lval[p0 + i] = v;
+    if (i == 0) {
+        if (v != v) atomicMax(S.counters + 3, 2);
+        else if (!(v > 0.0) || v == INFINITY) atomicMax(S.counters + 3, 1);
+        S.invd[j] = 1.0 / v;
+    }
+}
+
 __global__ void __launch_bounds__(kFactorThreads)
 sparse_ldl_kernel(SparseDev S) {
     extern __shared__ double acc[];  // [kFactorWarps][acc_cap]
-    __shared__ int sh_task;
+    __shared__ int sh_task, sh_last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int* rowmap = S.rowmap + (size_t)blockIdx.x * S.n;
     double* my_acc = acc + (size_t)warp * S.acc_cap;
@@ -138,36 +157,66 @@ sparse_ldl_kernel(SparseDev S) {
         if (tid == 0) sh_task = atomicAdd(S.counters + 0, 1);
         __syncthreads();
         const int t = sh_task;
-        if (t >= (int)S.n) break;
-        const uint32_t j = __ldg(S.order_up + t);
+        if (t >= (int)S.n_tasks) break;
+        const uint2 task = __ldg(S.tasks + t);
+        const uint32_t j = task.x, part = task.y & 0xFFFFu, parts = task.y >> 16;
         const uint32_t p0 = __ldg(S.l_colptr + j), c = __ldg(S.l_colptr + j + 1) - p0;
         for (uint32_t i = tid; i < c; i += kFactorThreads) rowmap[__ldg(S.l_rowidx + p0 + i)] = (int)i;
         for (uint32_t w = 0; w < kFactorWarps; w++)
             for (uint32_t i = tid; i < c; i += kFactorThreads) acc[(size_t)w * S.acc_cap + i] = 0.0;
         if (tid == 0)
-            while (ld_volatile(S.pending + j) != 0) __nanosleep(40);
+            while (ld_volatile(S.pending + j) != 0) __nanosleep(20);
         __syncthreads();
         __threadfence();
         const uint32_t r0 = __ldg(S.r_colptr + j), r1 = __ldg(S.r_colptr + j + 1) - 1;  // diagonal is last
-        for (uint32_t q = r0 + warp; q < r1; q += kFactorWarps) {
+        for (uint32_t q = r0 + part + parts * warp; q < r1; q += parts * kFactorWarps) {
             const uint32_t k = __ldg(S.r_rowidx + q), pos = __ldg(S.r_lpos + q);
             const double f = __ldcg(S.Lval + pos) * __ldcg(S.invd + k);
             const uint32_t end = __ldg(S.l_colptr + k + 1);
-            for (uint32_t e = pos + lane; e < end; e += 32) {
-                const int slot = rowmap[__ldg(S.l_rowidx + e)];
-                my_acc[slot] = fma(-__ldcg(S.Lval + e), f, my_acc[slot]);
+            for (uint32_t e = pos + lane; e < end; e += 128) {  // 4 independent entries per lane in flight
+                uint32_t row[4];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t ee = e + 32 * u;
+                    row[u] = ee < end ? __ldg(S.l_rowidx + ee) : kNop;
+                    v[u] = ee < end ? __ldcg(S.Lval + ee) : 0.0;
+                }
+                int slot[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) slot[u] = row[u] != kNop ? rowmap[row[u]] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (slot[u] >= 0) my_acc[slot[u]] = fma(-v[u], f, my_acc[slot[u]]);
             }
         }
         __syncthreads();
-        for (uint32_t i = tid; i < c; i += kFactorThreads) {
-            double v = S.Lval[p0 + i];
+        if (parts == 1) {
+            for (uint32_t i = tid; i < c; i += kFactorThreads) {
+                double v = S.Lval[p0 + i];
 #pragma unroll
-            for (int w = 0; w < kFactorWarps; w++) v += acc[(size_t)w * S.acc_cap + i];
-            S.Lval[p0 + i] = v;
-            if (i == 0) {
-                if (v != v) atomicMax(S.counters + 3, 2);
-                else if (!(v > 0.0) || v == INFINITY) atomicMax(S.counters + 3, 1);
-                S.invd[j] = 1.0 / v;
+                for (int w = 0; w < kFactorWarps; w++) v += acc[(size_t)w * S.acc_cap + i];
+                finalize_column(S, j, p0, i, v);
+            }
+        } else {
+            double* mine = S.team_acc + __ldg(S.team_off + j) + (size_t)part * c;
+            for (uint32_t i = tid; i < c; i += kFactorThreads) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < kFactorWarps; w++) v += acc[(size_t)w * S.acc_cap + i];
+                mine[i] = v;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sh_last = atomicAdd(S.arrive + j, 1) == (int)parts - 1;
+            __syncthreads();
+            if (!sh_last) continue;  // uniform: another task of the team finishes the column
+            __threadfence();
+            const double* all = S.team_acc + __ldg(S.team_off + j);
+            for (uint32_t i = tid; i < c; i += kFactorThreads) {
+                double v = S.Lval[p0 + i];
+                for (uint32_t p = 0; p < parts; p++) v += __ldcg(all + (size_t)p * c + i);
+                finalize_column(S, j, p0, i, v);
             }
         }
         __threadfence();
@@ -176,6 +225,15 @@ sparse_ldl_kernel(SparseDev S) {
             const int p = __ldg(S.parent + j);
             if (p >= 0) atomicSub(S.pending + p, 1);
         }
+    }
+}
+
+// Row-major copy of the unit factor for the forward solve: Rval[q] = (L D)(i,k) / d_k for the q-th
+// entry (k, i) of R = L^T.
+__global__ void __launch_bounds__(256) sparse_transpose_kernel(SparseDev S) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) {
+        const uint32_t r0 = __ldg(S.r_colptr + i), r1 = __ldg(S.r_colptr + i + 1) - 1;
+        for (uint32_t q = r0; q < r1; q++) S.Rval[q] = S.Lval[__ldg(S.r_lpos + q)] * S.invd[__ldg(S.r_rowidx + q)];
     }
 }
 
@@ -202,9 +260,16 @@ sparse_forward_kernel(SparseDev S, double* __restrict__ w) {
         __threadfence();
         const uint32_t r0 = __ldg(S.r_colptr + i), r1 = __ldg(S.r_colptr + i + 1) - 1;
         double s = 0.0;
-        for (uint32_t q = r0 + lane; q < r1; q += 32) {
-            const uint32_t k = __ldg(S.r_rowidx + q);
-            s = fma(S.Lval[__ldg(S.r_lpos + q)] * S.invd[k], __ldcg(w + k), s);
+        for (uint32_t q = r0 + lane; q < r1; q += 128) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t qq = q + 32 * u;
+                a[u] = qq < r1 ? S.Rval[qq] : 0.0;
+                b[u] = qq < r1 ? __ldcg(w + __ldg(S.r_rowidx + qq)) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) s = fma(a[u], b[u], s);
         }
         s = warp_sum(s);
         if (lane == 0) {
@@ -233,7 +298,17 @@ sparse_backward_kernel(SparseDev S, double* __restrict__ w, double* __restrict__
         __threadfence();
         const uint32_t p0 = __ldg(S.l_colptr + k), p1 = __ldg(S.l_colptr + k + 1);
         double s = 0.0;
-        for (uint32_t e = p0 + 1 + lane; e < p1; e += 32) s = fma(S.Lval[e], __ldcg(w + __ldg(S.l_rowidx + e)), s);
+        for (uint32_t e = p0 + 1 + lane; e < p1; e += 128) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t ee = e + 32 * u;
+                a[u] = ee < p1 ? S.Lval[ee] : 0.0;
+                b[u] = ee < p1 ? __ldcg(w + __ldg(S.l_rowidx + ee)) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) s = fma(a[u], b[u], s);
+        }
         s = warp_sum(s);
         if (lane == 0) {
             const double z = (w[k] - s) * S.invd[k];
@@ -414,6 +489,38 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     SP_CU(upload(nchildren, &S.nchildren, I.owned));
     SP_CU(upload(order, &S.order_up, I.owned));
     SP_CU(upload(order_down, &S.order_down, I.owned));
+    // work per column = multiply-adds of its left-looking update = sum over the k's of row j of the
+    // length of column k from row j down; heavy columns are split into team tasks
+    std::vector<uint64_t> work(n, 0);
+    for (uint32_t j = 0; j < n; j++)
+        for (uint32_t q = t.r_colptr[j]; q + 1 < t.r_colptr[j + 1]; q++)
+            work[j] += t.l_colptr[t.r_rowidx[q] + 1] - t.r_lpos[q];
+    std::vector<uint32_t> tasks;
+    std::vector<uint64_t> team_off(n, ~0ull);
+    uint64_t team_doubles = 0;
+    for (uint32_t j : order) {
+        uint32_t parts = (uint32_t)std::min<uint64_t>(kMaxTeam, std::max<uint64_t>(1, (work[j] + kTeamWork - 1) / kTeamWork));
+        uint32_t nk = t.r_colptr[j + 1] - t.r_colptr[j] - 1;
+        parts = std::max(1u, std::min(parts, std::max(1u, nk / kFactorWarps)));
+        if (parts > 1) {
+            team_off[j] = team_doubles;
+            team_doubles += (uint64_t)parts * (t.l_colptr[j + 1] - t.l_colptr[j]);
+        }
+        for (uint32_t p = 0; p < parts; p++) {
+            tasks.push_back(j);
+            tasks.push_back(p | (parts << 16));
+        }
+    }
+    S.n_tasks = (uint32_t)(tasks.size() / 2);
+    {
+        const uint32_t* p = nullptr;
+        SP_CU(upload(tasks, &p, I.owned));
+        S.tasks = (const uint2*)p;
+    }
+    SP_CU(upload(team_off, &S.team_off, I.owned));
+    SP_CU(I.alloc(&S.team_acc, (size_t)team_doubles));
+    SP_CU(I.alloc(&S.arrive, n));
+    SP_CU(I.alloc(&S.Rval, lnnz));
 
     // factor launch geometry: per-warp accumulators of max column length
     S.acc_cap = max_c;
@@ -546,6 +653,7 @@ int SparseSolver::solve(const double* vars, const double* param, double* free_va
         last.factors++;
         SP_CU(phase(last.tri_ms, [&] {
             cudaMemcpyAsync(I.d_w, I.d_g, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
+            sparse_transpose_kernel<<<I.grid_for(n), 256, 0, st>>>(S);
             sparse_forward_kernel<<<I.sm_count * 4, 256, 0, st>>>(S, I.d_w);
             sparse_backward_kernel<<<I.sm_count * 4, 256, 0, st>>>(S, I.d_w, I.d_delta);
         }));

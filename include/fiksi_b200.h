@@ -198,6 +198,9 @@ FK_API uint64_t fk_batch_plan_launches(const fk_batch_plan* plan);
  * factorisation; MEASURED_PEAKS.json carries no FP64 figure). */
 FK_API int fk_fp64_peak_tflops(int device, double* out);
 
+/* Blocks until all work issued for this plan's device has finished. */
+FK_API int fk_batch_plan_sync(fk_batch_plan* plan);
+
 /* Pinned host memory helpers (so that callers without a CUDA binding can stage inputs). */
 FK_API void* fk_host_alloc(size_t bytes);
 FK_API void fk_host_free(void* p);
@@ -210,6 +213,51 @@ FK_API void fk_host_free(void* p);
  * residuals only (K2, subsystem.rs:93-104). */
 FK_API int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream);
 FK_API int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_j, void* stream);
+
+/* ---- fiksi::System mirror (host side above the solve boundary) ------------------------------- */
+/* Same operations, argument meaning and ordering rules as fiksi::System (fiksi/src/lib.rs:252-467):
+ * elements and constraints are created in order and get consecutive ids; lines and circles are
+ * flattened to their points / lengths at creation (constraints/mod.rs:481-487); connected
+ * components are maintained incrementally exactly as fiksi/src/graph.rs:178-225 does (including
+ * its stale-index behaviour); fk_system_solve == System::solve(SolvingOptions { optimizer:
+ * LevenbergMarquardt, decomposer: None, perturb }) with the scale, seeded perturbation and
+ * write-back of fiksi/src/assemble/mod.rs:32-167.  All components go to the GPU in one
+ * fk_lm_solve_batch call.  Functions returning an id return UINT32_MAX on invalid arguments. */
+typedef struct fk_system fk_system;
+typedef enum fk_constraint_tag { /* ConstraintTag order, fiksi/src/constraints/mod.rs:893-905 */
+    FK_C_POINT_POINT_COINCIDENCE = 0,       /* elements: point, point */
+    FK_C_POINT_POINT_DISTANCE = 1,          /* point, point; param = distance */
+    FK_C_POINT_POINT_POINT_ANGLE = 2,       /* point, point, point; param = angle (radians) */
+    FK_C_POINT_LINE_INCIDENCE = 3,          /* point, line */
+    FK_C_POINT_LINE_DISTANCE = 4,           /* point, line; param = signed distance */
+    FK_C_POINT_CIRCLE_INCIDENCE = 5,        /* point, circle */
+    FK_C_SEGMENT_SEGMENT_LENGTH_EQUALITY = 6, /* point, point, point, point */
+    FK_C_LINE_LINE_ANGLE = 7,               /* line, line; param = angle */
+    FK_C_LINE_LINE_PARALLELISM = 8,         /* line, line */
+    FK_C_LINE_LINE_PERPENDICULARITY = 9,    /* line, line */
+    FK_C_LINE_CIRCLE_TANGENCY = 10          /* line, circle */
+} fk_constraint_tag;
+
+FK_API int fk_system_create(fk_system** out);
+FK_API void fk_system_destroy(fk_system* s);
+FK_API uint32_t fk_system_add_length(fk_system* s, double length);               /* elements::Length::create */
+FK_API uint32_t fk_system_add_point(fk_system* s, double x, double y);           /* elements::Point::create */
+FK_API uint32_t fk_system_add_line(fk_system* s, uint32_t p1, uint32_t p2);      /* elements::Line::create */
+FK_API uint32_t fk_system_add_circle(fk_system* s, uint32_t center, uint32_t radius);
+FK_API int fk_system_fix(fk_system* s, uint32_t element, int fix);               /* ElementHandle::fix / unfix */
+FK_API uint32_t fk_system_add_constraint(fk_system* s, int tag, const uint32_t* elements,
+                                         uint32_t n_elements, double param);
+FK_API uint32_t fk_system_num_variables(const fk_system* s);
+FK_API uint32_t fk_system_num_constraints(const fk_system* s);
+FK_API uint32_t fk_system_element_variable(const fk_system* s, uint32_t element); /* first variable index */
+FK_API int fk_system_get_variables(const fk_system* s, double* out);
+FK_API int fk_system_set_variable(fk_system* s, uint32_t var, double value);     /* update_value */
+FK_API int fk_system_set_parameter(fk_system* s, uint32_t constraint, double value); /* update_parameter */
+FK_API int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved);
+FK_API int fk_system_residuals(fk_system* s, double* out /* [num_constraints] */); /* calculate_residual */
+FK_API uint32_t fk_system_num_components(const fk_system* s);
+FK_API int fk_system_component(const fk_system* s, uint32_t index, uint32_t* n_elements, uint32_t* elements,
+                               uint32_t* n_constraints, uint32_t* constraints);
 
 #ifdef __cplusplus
 }
