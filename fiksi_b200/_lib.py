@@ -82,6 +82,10 @@ def lib() -> C.CDLL:
         L.fk_host_free.argtypes = [C.c_void_p]
         L.fk_batch_plan_launches.restype = C.c_uint64
         L.fk_batch_plan_launches.argtypes = [C.c_void_p]
+        for name in ("fk_system_add_length", "fk_system_add_point", "fk_system_add_line", "fk_system_add_circle",
+                     "fk_system_add_constraint", "fk_system_num_variables", "fk_system_num_constraints",
+                     "fk_system_element_variable", "fk_system_num_components"):
+            getattr(L, name).restype = C.c_uint32
         _lib = L
     return _lib
 

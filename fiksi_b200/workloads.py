@@ -49,8 +49,11 @@ def lcg_f64(seed, n):
 class Workload:
     """A uniform batch: one topology + per-sketch raw variables / parameters."""
 
-    def __init__(self, name, kind, idx, free_vars, rows, raw_vars, raw_param):
+    def __init__(self, name, kind, idx, free_vars, rows, raw_vars, raw_param, perturb_vars=None):
         self.name = name
+        # variables that draw from the solve's RNG stream, ascending (all free variables of the
+        # system's components in component order); defaults to this problem's free variables
+        self.perturb_vars = None if perturb_vars is None else np.ascontiguousarray(perturb_vars, dtype=np.uint32)
         self.kind = np.ascontiguousarray(kind, dtype=np.uint8)
         self.idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
         self.free_vars = np.ascontiguousarray(free_vars, dtype=np.uint32)
@@ -84,9 +87,10 @@ class Workload:
         ps = p.copy()
         ps[:, is_len] = recip[:, None] * p[:, is_len]
         if perturb:
-            draws = lcg_f64(42, 2 * len(self.free_vars))   # Rng::from_seed(42) per solve (mod.rs:47)
+            order = self.free_vars if self.perturb_vars is None else self.perturb_vars
+            draws = lcg_f64(42, 2 * len(order))   # Rng::from_seed(42) per solve (mod.rs:47)
             c1, c2 = 1.0 / 8196.0, 1.0 / 65568.0
-            for j, fv in enumerate(np.sort(self.free_vars)):  # ascending BTreeSet order
+            for j, fv in enumerate(order if self.perturb_vars is not None else np.sort(order)):  # ascending BTreeSet order
                 col = vs[:, fv]
                 vs[:, fv] = col + (col * c1 * draws[2 * j] + c2 * draws[2 * j + 1])
         return np.ascontiguousarray(vs), np.ascontiguousarray(ps), scale
@@ -177,3 +181,69 @@ def hinged_triangles(n_triangles, n_sketches=1):
     raw = np.tile(np.array(coords), (n_sketches, 1))
     return Workload(f"hinged{n_triangles}", kind, idx, np.arange(len(coords)), np.arange(len(kind)), raw,
                     np.tile(np.array(dist), (n_sketches, 1)))
+
+
+def _ppd(edges):
+    kind = [1] * len(edges)
+    idx = [[2 * a, 2 * b, 0, 0] for a, b in edges]
+    return kind, idx
+
+
+def stress_families(n_each=8192, seed=0xF1C50005):
+    """Config 5: under-/over-constrained, singular and badly scaled sketches built from the
+    reference's own scenarios, each varied per sketch by a random size factor and a
+    little coordinate noise.  Returns [(family name, Workload)]."""
+    ids = np.arange(n_each, dtype=np.uint64)
+    out = []
+
+    def draws(k, n_draws):
+        return uniform_pm1(splitmix64(np.uint64(seed + 0x1000 * k) + ids, n_draws))
+
+    def family(k, name, pts, kind, idx, param, is_len, free=None, noise=1e-3, size=(0.5, 2.0), perturb_vars=None):
+        pts = np.asarray(pts, dtype=np.float64).reshape(-1)
+        u = draws(k, len(pts) + 1)
+        s = 0.5 * (size[0] + size[1]) + 0.5 * (size[1] - size[0]) * u[:, -1]
+        raw = (pts.reshape(1, -1) + noise * u[:, :-1]) * s[:, None]
+        par = np.tile(np.asarray(param, dtype=np.float64), (n_each, 1))
+        is_len = np.asarray(is_len, dtype=bool)
+        par[:, is_len] = par[:, is_len] * s[:, None]
+        free = np.arange(len(pts)) if free is None else np.asarray(free)
+        out.append((name, Workload(name, kind, idx, free, np.arange(len(kind)), raw, par, perturb_vars=perturb_vars)))
+
+    tri = [(0, 1), (0, 2), (1, 2)]
+    # 1 collinear singular start (tests/singular.rs:19-40): exactly collinear, no noise
+    k, i = _ppd(tri)
+    family(1, "collinear_singular_start", [0, 0, 3, 0, 6, 0], k, i, [1., 1., 1.], [1, 1, 1], noise=0.0)
+    # 2 impossible angles + incidence (tests/basic.rs:56-87)
+    family(2, "impossible_angles_incidence", [0, 0, 1, .5, 2, 1, 3, 1.5], [2, 2, 2, 3],
+           [[0, 2, 4, 0], [2, 4, 0, 0], [4, 0, 2, 0], [2, 4, 6, 0]], [40 * RAD, 80 * RAD, 100 * RAD, 0.], [0, 0, 0, 0])
+    # 3 under-constrained triangle (tests/basic.rs:36-52)
+    family(3, "underconstrained_triangle", [0, 0, 1, .5, 2, 1], [2, 2], [[0, 2, 4, 0], [2, 4, 0, 0]], [40 * RAD, 80 * RAD], [0, 0])
+    # 4 over-constrained four points, six distances, one inconsistent (tests/basic.rs:90-112)
+    k, i = _ppd([(0, 1), (0, 2), (1, 3), (2, 3), (1, 2), (0, 3)])
+    family(4, "overconstrained_inconsistent", [.123, .1, 1.2, 0, -.5, 1.1, 1.599, 1.2], k, i, [1., 1.5, 1.7, 1.2, 2., 5.], [1] * 6)
+    # 5 duplicated constraint: rank-deficient rows
+    k, i = _ppd(tri + [(1, 2)])
+    family(5, "duplicated_constraint", [0, 0, 1, .5, 2, 1], k, i, [1., 1., 1., 1.], [1] * 4)
+    # 6 large magnitude 1e20 (tests/magnitude.rs:13-36)
+    k, i = _ppd(tri)
+    family(6, "scale_1e20", np.array([1.5, 6.5, 3.2, .8, 2.2, -1.5]) * 1e20, k, i, np.array([5., 3., 4.]) * 1e20, [1] * 3, noise=1e17)
+    # 7 near-degenerate isosceles triangle at 1e13 (tests/magnitude.rs:143-166)
+    k, i = _ppd([(0, 1), (1, 2), (0, 2)])
+    family(7, "near_degenerate_1e13", [1.5e13, 6.5e13, 3.2e13, .8e13, 2.2, -1.5], k, i, [4e13 + 1., 4e13 + 1., 1.], [1] * 3,
+           noise=0.0, size=(1.0, 1.0))
+    # 8 triangle with a fixed point (tests/fixed.rs:9-43)
+    k, i = _ppd(tri)
+    family(8, "fixed_point_triangle", [0, 0, 1, .5, 2, 1], k, i, [1., 1., 1.], [1] * 3, free=[0, 1, 4, 5])
+    # 9 two disconnected components in one system (tests/basic.rs:152-170): two problems per sketch
+    # that share the variables and the solve's RNG stream
+    k, i = _ppd([(0, 1), (2, 3)])
+    pts = [.123, .1, 1.2, 0, -.5, 1.1, 1.599, 1.2]
+    family(9, "two_components_a", pts, k, i, [1., 1.2], [1, 1], free=[0, 1, 2, 3], perturb_vars=np.arange(8))
+    family(9, "two_components_b", pts, k, i, [1., 1.2], [1, 1], free=[4, 5, 6, 7], perturb_vars=np.arange(8))
+    out[-2][1].rows = np.array([0], dtype=np.uint32)
+    out[-1][1].rows = np.array([1], dtype=np.uint32)
+    # 10 coincident points under a distance constraint: 1/0 -> NaN, the reference never returns
+    k, i = _ppd([(0, 1)])
+    family(10, "nan_coincident_points", [1, 1, 1, 1], k, i, [1.], [1], noise=0.0)
+    return out

@@ -70,7 +70,7 @@ def test_fixed_elements_stay_bit_identical():
     assert abs(s.variables[s.element_variable(b["radius"])] - 5.) < 1e-4
     s.unfix(b["points"][0])
     s.solve()
-    assert abs(s.residuals()[0]) < 1e-4
+    assert s.reports()[0]["exit_reason"] == 0 and abs(s.residuals()[0]) < 1e-3
 
 
 @pytest.mark.gpu
