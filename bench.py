@@ -119,7 +119,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the assembly / FP64 side measurements")
@@ -237,7 +237,7 @@ def main():
         avg_s = (total_ms / args.steps) * 1e-3 if world == 1 else (float(sum(step_ms)) / args.steps) * 1e-3
         achieved = alg_bytes / avg_s / 1e9
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "fk_batch_lm_kernel<32>", "peak_source": peak_src,
+                            "traffic": None, "kernel": "fk_batch_lm_kernel<%d,%d>" % (info["tile"], 1), "peak_source": peak_src,
                             "note": "latency/FP64-bound kernel: whole LM loop runs out of shared memory; see fp64 + assembly"}
         if not args.no_extras:
             try:
