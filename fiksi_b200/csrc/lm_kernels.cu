@@ -82,6 +82,18 @@ __device__ __forceinline__ double sum_squares_seq(const double* v, uint32_t n) {
     return s;
 }
 
+// 1/d for a positive finite pivot: hardware seed + two Newton steps (relative error ~1e-16; the
+// LDLt is not compared bit-wise with anything, it only has to be deterministic).
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 constexpr uint32_t kFirst = 1u << 16, kLast = 1u << 17;
 
 // K3: L storage := JᵀJ (permuted, lower; the damping is added when a pivot is read) and
@@ -115,6 +127,11 @@ __device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsign
     uint32_t prev_dpos = 0;
     double inv = 0.0;
     bool have_prev = false;
+    // First bad pivot in column order (kNop if none): its kind decides between "not solved" and NaN.
+    // A bad pivot only poisons later columns, so checking after the fact finds the same first one.
+    uint32_t bad_col = kNop;
+    bool bad_nan = false;
+    uint32_t col = 0;
     for (uint32_t s = 0; s < P.f_nsteps; s++) {
         const uint32_t nhdr = __ldg(P.f_steps + s + 1);
         const uint2 nop = __ldg(P.f_ops + (s + 1) * TILE + lane);
@@ -123,11 +140,14 @@ __device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsign
             const double d = L[dpos] + lam2;
             // the previous pivot slot is free now (every lane passed the barrier that ended its column)
             if (have_prev && lane == 0) L[prev_dpos] = inv;
-            if (d != d) return 2;
-            if (!(d > 0.0) || d == INFINITY) return 1;
-            inv = 1.0 / d;
+            if (!(d > 0.0 && d < INFINITY) && bad_col == kNop) {
+                bad_col = col;
+                bad_nan = d != d;
+            }
+            inv = fast_rcp(d);
             prev_dpos = dpos;
             have_prev = true;
+            col++;
         }
         if (op.x != kNop) {
             const uint32_t dst = op.x & 0xFFFFu;
@@ -138,7 +158,7 @@ __device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsign
     }
     if (have_prev && lane == 0) L[prev_dpos] = inv;
     if (TILE > 1) TileOps<TILE>::sync(msk);
-    return 0;
+    return bad_col == kNop ? 0 : (bad_nan ? 2 : 1);
 }
 
 // Solve (L D Lᵀ) z = g.  w holds g on entry (permuted order); the solution is written in
@@ -146,22 +166,7 @@ __device__ __forceinline__ int factor_tile(const DevProgram& P, int lane, unsign
 template <int TILE>
 __device__ __forceinline__ void solve_tile(const DevProgram& P, int lane, unsigned msk, const double* L,
                                            double* w, double* delta) {
-    {   // forward: unit lower triangular L' = (L D) D^-1, column oriented
-        uint2 hdr = __ldg(P.s_steps);
-        uint32_t op = __ldg(P.s_ops + lane);
-        double t = 0.0;
-        for (uint32_t s = 0; s < P.s_nsteps; s++) {
-            const uint2 nhdr = __ldg(P.s_steps + s + 1);
-            const uint32_t nop = __ldg(P.s_ops + (s + 1) * TILE + lane);
-            if (hdr.x & kFirst) t = w[hdr.y] * L[hdr.x & 0xFFFFu];
-            if (op != kNop) {
-                const uint32_t i = op & 0xFFFFu;
-                w[i] = fma(-L[op >> 16], t, w[i]);
-            }
-            if (TILE > 1 && (hdr.x & kLast)) TileOps<TILE>::sync(msk);
-            hdr = nhdr; op = nop;
-        }
-    }
+    // (the forward substitution has already been applied to w by the factorisation steps)
     {   // backward: D Lᵀ z = y column by column over R = Lᵀ: z_k = y_k / d_k, then y_j -= (L D)(k,j) z_k
         uint2 hdr = __ldg(P.b_steps);
         uint32_t op = __ldg(P.b_ops + lane);
@@ -201,17 +206,17 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
     if (sketch >= n_sketches) return;
     const unsigned msk = TileOps<TILE>::mask();
     const uint32_t n = P.n, m = P.m;
-    const uint32_t wlen = n > m ? n : m;
 
     // per-sketch shared arrays; the stride is odd so that tiles of one warp touching the same
     // element index land in different banks
     double* x = smem + (size_t)tile_id * stride_doubles;
     double* xs = x + n;
     double* g = xs + n;
-    double* w = g + n;          // solve vector; the trial residuals live here outside the solve
-    double* rs = w;
-    double* J = w + wlen;       // Jacobian values at the accepted point (CSC order)
+    double* J = g + n;          // Jacobian values at the accepted point (CSC order)
     double* L = J + P.jnnz;     // LDLt factor; receives the trial Jacobian after the solve
+    double* w = L + (P.lnnz > P.jnnz ? P.lnnz : P.jnnz);  // right-hand side / solve vector, addressed
+    double* rs = w;                                        // as L[wbase + i] by the factor steps; the
+                                                           // trial residuals live here outside the solve
 
     const double* vars = vars_all + (size_t)sketch * P.n_vars;
     const double* params = params_all + (size_t)sketch * P.n_expr;

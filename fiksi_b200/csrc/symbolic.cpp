@@ -367,19 +367,29 @@ int Topology::build_tables() {
     };
     pack_lists(h_ptr, h_pairs, lnnz, t.a_nsteps, t.a_flags, t.a_ops, t.a_dst);
     pack_lists(g_ptr, g_pairs, n, t.g_nsteps, t.g_flags, t.g_ops, t.g_dst);
-    // ---- LDLt: one or more steps per column --------------------------------------------------------
+    // ---- LDLt: one or more steps per column.  The forward substitution rides along: the right-hand
+    // side w lives right behind L in shared memory (position wbase + i), and "w[i] -= (L D)(i,k) / d_k *
+    // w[k]" has exactly the shape of a factor update with dst = w[i], a = (i,k), b = w[k]. ------------------
+    const uint32_t wbase = std::max(lnnz, jac_nnz);
+    if (wbase + n >= 0xFFFF) { error = "problem too large for the 16-bit shared-memory tables"; return FK_ERR_TOO_LARGE; }
     t.f_steps.clear(); t.f_ops.clear();
     for (uint32_t k = 0; k < n; k++) {
-        uint32_t cnt = u_ptr[k + 1] - u_ptr[k];
+        std::vector<uint32_t> ops3;
+        for (uint32_t q = u_ptr[k]; q < u_ptr[k + 1]; q++) {
+            ops3.push_back(u_trip[3 * (size_t)q]); ops3.push_back(u_trip[3 * (size_t)q + 1]); ops3.push_back(u_trip[3 * (size_t)q + 2]);
+        }
+        for (uint32_t q = l_colptr[k] + 1; q < l_colptr[k + 1]; q++) {
+            ops3.push_back(wbase + l_rowidx[q]); ops3.push_back(q); ops3.push_back(wbase + k);
+        }
+        uint32_t cnt = (uint32_t)(ops3.size() / 3);
         uint32_t rounds = std::max(1u, (cnt + T - 1) / T);
         size_t base = t.f_steps.size();
         for (uint32_t r = 0; r < rounds; r++)
             t.f_steps.push_back(l_colptr[k] | (r == 0 ? FIRST : 0) | (r + 1 == rounds ? LAST : 0));
         t.f_ops.resize((base + rounds) * T * 2, NOP);
         for (uint32_t q = 0; q < cnt; q++) {
-            const uint32_t* tr = &u_trip[3 * (size_t)(u_ptr[k] + q)];
-            t.f_ops[(base * T + q) * 2] = tr[0] | (tr[1] << 16);
-            t.f_ops[(base * T + q) * 2 + 1] = tr[2];
+            t.f_ops[(base * T + q) * 2] = ops3[3 * q] | (ops3[3 * q + 1] << 16);
+            t.f_ops[(base * T + q) * 2 + 1] = ops3[3 * q + 2];
         }
     }
     t.f_nsteps = (uint32_t)t.f_steps.size();
