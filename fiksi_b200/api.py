@@ -85,7 +85,7 @@ class Topology:
         out = (C.c_float * 8)()
         check(lib().fk_topology_last_timing(self._h, out))
         return {"eval_ms": out[0], "assemble_ms": out[1], "factor_ms": out[2], "tri_ms": out[3],
-                "evals": int(out[4]), "factors": int(out[5])}
+                "evals": int(out[4]), "factors": int(out[5]), "fwd_ms": out[6], "bwd_ms": out[7]}
 
     def plan(self, capacity, device=0):
         return BatchPlan(self, capacity, device)

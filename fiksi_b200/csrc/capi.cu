@@ -490,7 +490,7 @@ int fk_topology_last_timing(fk_topology* topo, float* out8) {
     for (auto& kv : topo->sparse) {
         const auto& l = kv.second->last;
         out8[0] = l.eval_ms; out8[1] = l.assemble_ms; out8[2] = l.factor_ms; out8[3] = l.tri_ms;
-        out8[4] = (float)l.evals; out8[5] = (float)l.factors;
+        out8[4] = (float)l.evals; out8[5] = (float)l.factors; out8[6] = l.fwd_ms; out8[7] = l.bwd_ms;
     }
     return FK_OK;
 }

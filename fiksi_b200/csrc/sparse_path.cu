@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -17,8 +18,8 @@ namespace {
 
 constexpr uint32_t kNop = 0xFFFFFFFFu;
 constexpr int kFactorThreads = 512;
-constexpr int kMaxTeam = 16;           // CTAs that may share one column of the factorisation
-constexpr uint32_t kTeamWork = 16384;   // multiply-adds per CTA above which a column is split
+constexpr int kMaxTeamDefault = 16;          // CTAs that may share one column of the factorisation
+constexpr uint32_t kTeamWorkDefault = 16384;  // multiply-adds per CTA above which a column is split
 constexpr int kFactorWarps = kFactorThreads / 32;
 
 struct SparseDev {
@@ -61,6 +62,14 @@ struct SparseDev {
 };
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *(const volatile int*)p; }
+// Spin until *p == want, backing off so that thousands of waiting warps do not flood the L2.
+__device__ __forceinline__ void spin_until(const int* p, int want) {
+    unsigned ns = 32;
+    while (ld_volatile(p) != want) {
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+    }
+}
 
 // ---- K1 / K2 -----------------------------------------------------------------------------------
 template <bool WITH_JACOBIAN>
@@ -165,7 +174,7 @@ sparse_ldl_kernel(SparseDev S) {
         for (uint32_t w = 0; w < kFactorWarps; w++)
             for (uint32_t i = tid; i < c; i += kFactorThreads) acc[(size_t)w * S.acc_cap + i] = 0.0;
         if (tid == 0)
-            while (ld_volatile(S.pending + j) != 0) __nanosleep(20);
+            spin_until(S.pending + j, 0);
         __syncthreads();
         __threadfence();
         const uint32_t r0 = __ldg(S.r_colptr + j), r1 = __ldg(S.r_colptr + j + 1) - 1;  // diagonal is last
@@ -255,7 +264,7 @@ sparse_forward_kernel(SparseDev S, double* __restrict__ w) {
         if (t >= (int)S.n) break;
         const uint32_t i = __ldg(S.order_up + t);
         if (lane == 0)
-            while (ld_volatile(S.pending_s + i) != 0) __nanosleep(40);
+            spin_until(S.pending_s + i, 0);
         __syncwarp();
         __threadfence();
         const uint32_t r0 = __ldg(S.r_colptr + i), r1 = __ldg(S.r_colptr + i + 1) - 1;
@@ -293,7 +302,7 @@ sparse_backward_kernel(SparseDev S, double* __restrict__ w, double* __restrict__
         const uint32_t k = __ldg(S.order_down + t);
         const int p = __ldg(S.parent + k);
         if (lane == 0 && p >= 0)
-            while (ld_volatile(S.done + p) == 0) __nanosleep(40);
+            spin_until(S.done + p, 1);
         __syncwarp();
         __threadfence();
         const uint32_t p0 = __ldg(S.l_colptr + k), p1 = __ldg(S.l_colptr + k + 1);
@@ -374,7 +383,7 @@ struct SparseSolver::Impl {
     double *d_r = nullptr, *d_rs = nullptr, *d_J = nullptr, *d_Jt = nullptr, *d_g = nullptr, *d_w = nullptr;
     double *d_delta = nullptr, *d_partial = nullptr, *d_scalars = nullptr;
     double* h_scalars = nullptr;  // pinned: [0] dn, [1] ssr, [2] factor status
-    int ldl_grid = 0, sm_count = 0;
+    int ldl_grid = 0, sm_count = 0, solve_grid = 148;
     size_t ldl_smem = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -432,6 +441,8 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     cudaDeviceProp prop;
     SP_CU(cudaGetDeviceProperties(&prop, device));
     I.sm_count = prop.multiProcessorCount;
+    I.solve_grid = I.sm_count;
+    if (const char* e = std::getenv("FK_SOLVE_GRID")) I.solve_grid = std::max(1, std::atoi(e));
     const uint32_t n = t.n_free, m = t.n_rows, lnnz = (uint32_t)t.l_rowidx.size();
     if (t.jac_nnz >= (1u << 24) || t.n_expr >= (1u << 24)) {
         if (err) *err = "problem exceeds the 24-bit position fields of the evaluation tables";
@@ -495,6 +506,9 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     for (uint32_t j = 0; j < n; j++)
         for (uint32_t q = t.r_colptr[j]; q + 1 < t.r_colptr[j + 1]; q++)
             work[j] += t.l_colptr[t.r_rowidx[q] + 1] - t.r_lpos[q];
+    uint64_t kMaxTeam = kMaxTeamDefault, kTeamWork = kTeamWorkDefault;
+    if (const char* e = std::getenv("FK_TEAM_MAX")) kMaxTeam = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("FK_TEAM_WORK")) kTeamWork = std::max(256, std::atoi(e));
     std::vector<uint32_t> tasks;
     std::vector<uint64_t> team_off(n, ~0ull);
     uint64_t team_doubles = 0;
@@ -651,12 +665,13 @@ int SparseSolver::solve(const double* vars, const double* param, double* free_va
         SP_CU(phase(last.factor_ms, [&] { sparse_ldl_kernel<<<I.ldl_grid, kFactorThreads, I.ldl_smem, st>>>(S); }));
         factorizations++;
         last.factors++;
-        SP_CU(phase(last.tri_ms, [&] {
+        SP_CU(phase(last.transpose_ms, [&] {
             cudaMemcpyAsync(I.d_w, I.d_g, sizeof(double) * n, cudaMemcpyDeviceToDevice, st);
             sparse_transpose_kernel<<<I.grid_for(n), 256, 0, st>>>(S);
-            sparse_forward_kernel<<<I.sm_count * 4, 256, 0, st>>>(S, I.d_w);
-            sparse_backward_kernel<<<I.sm_count * 4, 256, 0, st>>>(S, I.d_w, I.d_delta);
         }));
+        SP_CU(phase(last.fwd_ms, [&] { sparse_forward_kernel<<<I.solve_grid, 128, 0, st>>>(S, I.d_w); }));
+        SP_CU(phase(last.bwd_ms, [&] { sparse_backward_kernel<<<I.solve_grid, 128, 0, st>>>(S, I.d_w, I.d_delta); }));
+        last.tri_ms = last.transpose_ms + last.fwd_ms + last.bwd_ms;
         SP_CU(I.sumsq(I.d_delta, n, I.d_scalars + 0));
         add_kernel<<<I.grid_for(n), 256, 0, st>>>(x, I.d_delta, xs, n);
         SP_CU(phase(last.eval_ms, [&] { I.eval(xs, rs, Jt); }));

@@ -150,7 +150,7 @@ FK_API int fk_topology_eval(fk_topology* topo, const double* vars, const double*
                             const double* free_values, double* out_r, double* out_j, int repeats,
                             float* ms_per_eval);
 /* Phase times of the last large-system solve: out8 = {eval ms, assemble ms, factor ms,
- * triangular-solve ms, evaluations, factorisations, 0, 0}. */
+ * triangular-solve ms, evaluations, factorisations, forward ms, backward ms}. */
 FK_API int fk_topology_last_timing(fk_topology* topo, float* out8);
 
 /* ---- Levenberg–Marquardt ----------------------------------------------------------------- */
