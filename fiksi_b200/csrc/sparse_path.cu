@@ -54,21 +54,31 @@ struct SparseDev {
     // mutable state
     double* Lval;
     double* invd;
-    int* pending;      // [n] children still running (factor)
-    int* pending_s;    // [n] children still running (forward substitution)
-    int* done;         // [n] backward flags
+    int* done_f;       // [n] column factorised
+    int* done_s;       // [n] forward substitution finished for this row
+    int* done;         // [n] backward substitution finished for this column
     int* counters;     // [4] task counters + fail flag
     int* rowmap;       // [grid][n]
 };
 
-__device__ __forceinline__ int ld_volatile(const int* p) { return *(const volatile int*)p; }
-// Spin until *p == want, backing off so that thousands of waiting warps do not flood the L2.
-__device__ __forceinline__ void spin_until(const int* p, int want) {
-    unsigned ns = 32;
-    while (ld_volatile(p) != want) {
-        __nanosleep(ns);
-        if (ns < 1024) ns <<= 1;
-    }
+// Release/acquire flags at GPU scope: a producer publishes a finished column / row with
+// st.release after its data stores (a barrier first when other threads of the CTA wrote them);
+// consumers spin with ld.acquire and then read the data past L1 (__ldcg).
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void wait_flag(const int* p) {
+    while (ld_acquire(p) == 0) __nanosleep(32);
 }
 
 // ---- K1 / K2 -----------------------------------------------------------------------------------
@@ -120,9 +130,8 @@ sparse_assemble_kernel(SparseDev S, const double* __restrict__ J) {
 __global__ void __launch_bounds__(256) sparse_arm_kernel(SparseDev S, double lam2) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < S.n; k += gridDim.x * blockDim.x) {
         S.Lval[__ldg(S.l_colptr + k)] += lam2;
-        const int c = (int)__ldg(S.nchildren + k);
-        S.pending[k] = c;
-        S.pending_s[k] = c;
+        S.done_f[k] = 0;
+        S.done_s[k] = 0;
         S.done[k] = 0;
         S.arrive[k] = 0;
     }
@@ -155,10 +164,13 @@ __device__ __forceinline__ void finalize_column(const SparseDev& S, uint32_t j, 
     }
 }
 
+constexpr int kStage = 1024;  // k's of a column staged in shared memory at a time
+
 __global__ void __launch_bounds__(kFactorThreads)
 sparse_ldl_kernel(SparseDev S) {
     extern __shared__ double acc[];  // [kFactorWarps][acc_cap]
     __shared__ int sh_task, sh_last;
+    __shared__ uint32_t st_k[kStage], st_pos[kStage], st_end[kStage];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int* rowmap = S.rowmap + (size_t)blockIdx.x * S.n;
     double* my_acc = acc + (size_t)warp * S.acc_cap;
@@ -173,33 +185,64 @@ sparse_ldl_kernel(SparseDev S) {
         for (uint32_t i = tid; i < c; i += kFactorThreads) rowmap[__ldg(S.l_rowidx + p0 + i)] = (int)i;
         for (uint32_t w = 0; w < kFactorWarps; w++)
             for (uint32_t i = tid; i < c; i += kFactorThreads) acc[(size_t)w * S.acc_cap + i] = 0.0;
-        if (tid == 0)
-            spin_until(S.pending + j, 0);
-        __syncthreads();
-        __threadfence();
         const uint32_t r0 = __ldg(S.r_colptr + j), r1 = __ldg(S.r_colptr + j + 1) - 1;  // diagonal is last
-        for (uint32_t q = r0 + part + parts * warp; q < r1; q += parts * kFactorWarps) {
-            const uint32_t k = __ldg(S.r_rowidx + q), pos = __ldg(S.r_lpos + q);
-            const double f = __ldcg(S.Lval + pos) * __ldcg(S.invd + k);
-            const uint32_t end = __ldg(S.l_colptr + k + 1);
-            for (uint32_t e = pos + lane; e < end; e += 128) {  // 4 independent entries per lane in flight
-                uint32_t row[4];
-                double v[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t ee = e + 32 * u;
-                    row[u] = ee < end ? __ldg(S.l_rowidx + ee) : kNop;
-                    v[u] = ee < end ? __ldcg(S.Lval + ee) : 0.0;
+        // Work items are 128-entry chunks of the sub-columns (k, rows >= j); chunk ch of the q-th k
+        // belongs to warp slot (q + ch) mod slots, so short k's go round-robin and a long k (the
+        // dense chain right below j) is spread over every warp of every part.  A warp waits for a
+        // column k only when it is about to read it: everything older than the last few columns is
+        // long finished, so column j overlaps with the tail of its predecessors (look-ahead).
+        const uint32_t slots = parts * kFactorWarps, slot = part * kFactorWarps + warp;
+        for (uint32_t base = r0; base < r1; base += kStage) {
+            const uint32_t cnt = min((uint32_t)kStage, r1 - base);
+            __syncthreads();
+            for (uint32_t i = tid; i < cnt; i += kFactorThreads) {
+                const uint32_t k = __ldg(S.r_rowidx + base + i);
+                st_k[i] = k;
+                st_pos[i] = __ldg(S.r_lpos + base + i);
+                st_end[i] = __ldg(S.l_colptr + k + 1);
+            }
+            __syncthreads();
+            // 32 k's at a time: every lane tests one k for a chunk owned by this warp (slots is a
+            // power of two), then the warp walks the owned ones together
+            for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                uint32_t ch0 = 0, nch = 0;
+                if (i < cnt) {
+                    nch = (st_end[i] - st_pos[i] + 127) >> 7;
+                    ch0 = (slot - (base - r0 + i)) & (slots - 1);
                 }
-                int slot[4];
+                unsigned owned = __ballot_sync(0xFFFFFFFFu, ch0 < nch);
+                while (owned) {
+                    const int src = __ffs(owned) - 1;
+                    owned &= owned - 1;
+                    const uint32_t k = st_k[i0 + src], pos = st_pos[i0 + src], end = st_end[i0 + src];
+                    const uint32_t nch_k = __shfl_sync(0xFFFFFFFFu, nch, src);
+                    uint32_t ch = __shfl_sync(0xFFFFFFFFu, ch0, src);
+                    if (lane == 0) wait_flag(S.done_f + k);
+                    __syncwarp();
+                    const double f = __ldcg(S.Lval + pos) * __ldcg(S.invd + k);
+                    for (; ch < nch_k; ch += slots) {
+                        const uint32_t e = pos + (ch << 7) + lane;
+                        uint32_t row[4];
+                        double v[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) slot[u] = row[u] != kNop ? rowmap[row[u]] : -1;
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t ee = e + 32 * u;
+                            row[u] = ee < end ? __ldg(S.l_rowidx + ee) : kNop;
+                            v[u] = ee < end ? __ldcg(S.Lval + ee) : 0.0;
+                        }
+                        int sl[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (slot[u] >= 0) my_acc[slot[u]] = fma(-v[u], f, my_acc[slot[u]]);
+                        for (int u = 0; u < 4; u++) sl[u] = row[u] != kNop ? rowmap[row[u]] : -1;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (sl[u] >= 0) my_acc[sl[u]] = fma(-v[u], f, my_acc[sl[u]]);
+                    }
+                }
             }
         }
         __syncthreads();
+        bool finished = true;
         if (parts == 1) {
             for (uint32_t i = tid; i < c; i += kFactorThreads) {
                 double v = S.Lval[p0 + i];
@@ -215,25 +258,21 @@ sparse_ldl_kernel(SparseDev S) {
                 for (int w = 0; w < kFactorWarps; w++) v += acc[(size_t)w * S.acc_cap + i];
                 mine[i] = v;
             }
-            __threadfence();
             __syncthreads();
-            if (tid == 0) sh_last = atomicAdd(S.arrive + j, 1) == (int)parts - 1;
+            if (tid == 0) sh_last = atom_add_acq_rel(S.arrive + j, 1) == (int)parts - 1;
             __syncthreads();
-            if (!sh_last) continue;  // uniform: another task of the team finishes the column
-            __threadfence();
-            const double* all = S.team_acc + __ldg(S.team_off + j);
-            for (uint32_t i = tid; i < c; i += kFactorThreads) {
-                double v = S.Lval[p0 + i];
-                for (uint32_t p = 0; p < parts; p++) v += __ldcg(all + (size_t)p * c + i);
-                finalize_column(S, j, p0, i, v);
+            finished = sh_last != 0;  // uniform: otherwise another task of the team finishes the column
+            if (finished) {
+                const double* all = S.team_acc + __ldg(S.team_off + j);
+                for (uint32_t i = tid; i < c; i += kFactorThreads) {
+                    double v = S.Lval[p0 + i];
+                    for (uint32_t p = 0; p < parts; p++) v += __ldcg(all + (size_t)p * c + i);
+                    finalize_column(S, j, p0, i, v);
+                }
             }
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) {
-            const int p = __ldg(S.parent + j);
-            if (p >= 0) atomicSub(S.pending + p, 1);
-        }
+        if (finished && tid == 0) st_release(S.done_f + j, 1);
     }
 }
 
@@ -252,9 +291,10 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Forward substitution with the unit lower factor L' = (L D) D^-1, row oriented, one warp per row.
-// `pending` has been re-armed with the children counts by the host before this launch.
-__global__ void __launch_bounds__(256)
+// Forward substitution with the unit lower factor L' = (L D) D^-1, row oriented, one warp per row:
+// y_i = g_i - sum_k L'(i,k) y_k.  Every lane waits for exactly the y_k it is about to read (its k's
+// are descendants of i, claimed earlier); the factor values and indices are fetched before the wait.
+__global__ void __launch_bounds__(128)
 sparse_forward_kernel(SparseDev S, double* __restrict__ w) {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -263,19 +303,24 @@ sparse_forward_kernel(SparseDev S, double* __restrict__ w) {
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= (int)S.n) break;
         const uint32_t i = __ldg(S.order_up + t);
-        if (lane == 0)
-            spin_until(S.pending_s + i, 0);
-        __syncwarp();
-        __threadfence();
         const uint32_t r0 = __ldg(S.r_colptr + i), r1 = __ldg(S.r_colptr + i + 1) - 1;
         double s = 0.0;
         for (uint32_t q = r0 + lane; q < r1; q += 128) {
             double a[4], b[4];
+            uint32_t k[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t qq = q + 32 * u;
                 a[u] = qq < r1 ? S.Rval[qq] : 0.0;
-                b[u] = qq < r1 ? __ldcg(w + __ldg(S.r_rowidx + qq)) : 0.0;
+                k[u] = qq < r1 ? __ldg(S.r_rowidx + qq) : kNop;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                b[u] = 0.0;
+                if (k[u] != kNop) {
+                    wait_flag(S.done_s + k[u]);
+                    b[u] = __ldcg(w + k[u]);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) s = fma(a[u], b[u], s);
@@ -283,15 +328,15 @@ sparse_forward_kernel(SparseDev S, double* __restrict__ w) {
         s = warp_sum(s);
         if (lane == 0) {
             w[i] = w[i] - s;
-            __threadfence();
-            const int p = __ldg(S.parent + i);
-            if (p >= 0) atomicSub(S.pending_s + p, 1);
+            st_release(S.done_s + i, 1);
         }
     }
 }
 
 // Backward substitution D L^T z = y, column oriented gather, one warp per column, parents first.
-__global__ void __launch_bounds__(256)
+// The column is walked from its last row (an early ancestor) to its first (the parent, the last
+// one to finish), each lane waiting only for the z it reads.
+__global__ void __launch_bounds__(128)
 sparse_backward_kernel(SparseDev S, double* __restrict__ w, double* __restrict__ delta) {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -300,20 +345,26 @@ sparse_backward_kernel(SparseDev S, double* __restrict__ w, double* __restrict__
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= (int)S.n) break;
         const uint32_t k = __ldg(S.order_down + t);
-        const int p = __ldg(S.parent + k);
-        if (lane == 0 && p >= 0)
-            spin_until(S.done + p, 1);
-        __syncwarp();
-        __threadfence();
-        const uint32_t p0 = __ldg(S.l_colptr + k), p1 = __ldg(S.l_colptr + k + 1);
+        const uint32_t p0 = __ldg(S.l_colptr + k) + 1, p1 = __ldg(S.l_colptr + k + 1);
         double s = 0.0;
-        for (uint32_t e = p0 + 1 + lane; e < p1; e += 128) {
+        for (uint32_t off = lane; p0 + off < p1; off += 128) {
             double a[4], b[4];
+            uint32_t row[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t ee = e + 32 * u;
-                a[u] = ee < p1 ? S.Lval[ee] : 0.0;
-                b[u] = ee < p1 ? __ldcg(w + __ldg(S.l_rowidx + ee)) : 0.0;
+                const uint32_t o = off + 32 * u;
+                const bool ok = p0 + o < p1;
+                const uint32_t e = p1 - 1 - o;
+                a[u] = ok ? S.Lval[e] : 0.0;
+                row[u] = ok ? __ldg(S.l_rowidx + e) : kNop;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                b[u] = 0.0;
+                if (row[u] != kNop) {
+                    wait_flag(S.done + row[u]);
+                    b[u] = __ldcg(w + row[u]);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) s = fma(a[u], b[u], s);
@@ -323,8 +374,7 @@ sparse_backward_kernel(SparseDev S, double* __restrict__ w, double* __restrict__
             const double z = (w[k] - s) * S.invd[k];
             w[k] = z;
             delta[__ldg(S.perm + k)] = z;
-            __threadfence();
-            atomicExch(S.done + k, 1);
+            st_release(S.done + k, 1);
         }
     }
 }
@@ -516,6 +566,7 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
         uint32_t parts = (uint32_t)std::min<uint64_t>(kMaxTeam, std::max<uint64_t>(1, (work[j] + kTeamWork - 1) / kTeamWork));
         uint32_t nk = t.r_colptr[j + 1] - t.r_colptr[j] - 1;
         parts = std::max(1u, std::min(parts, std::max(1u, nk / kFactorWarps)));
+        while (parts & (parts - 1)) parts &= parts - 1;  // power of two: chunk ownership uses a mask
         if (parts > 1) {
             team_off[j] = team_doubles;
             team_doubles += (uint64_t)parts * (t.l_colptr[j + 1] - t.l_colptr[j]);
@@ -551,8 +602,8 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
 
     SP_CU(I.alloc(&S.Lval, lnnz));
     SP_CU(I.alloc(&S.invd, n));
-    SP_CU(I.alloc(&S.pending, n));
-    SP_CU(I.alloc(&S.pending_s, n));
+    SP_CU(I.alloc(&S.done_f, n));
+    SP_CU(I.alloc(&S.done_s, n));
     SP_CU(I.alloc(&S.done, n));
     SP_CU(I.alloc(&S.counters, 4));
     SP_CU(I.alloc(&S.rowmap, (size_t)I.ldl_grid * n));
