@@ -17,7 +17,7 @@ namespace fk {
 namespace {
 
 constexpr uint32_t kNop = 0xFFFFFFFFu;
-constexpr int kFactorThreads = 512;
+constexpr int kFactorThreads = 128;
 constexpr int kMaxTeamDefault = 16;          // CTAs that may share one column of the factorisation
 constexpr uint32_t kTeamWorkDefault = 16384;  // multiply-adds per CTA above which a column is split
 constexpr int kFactorWarps = kFactorThreads / 32;

@@ -3,7 +3,7 @@ import numpy as np, fiksi_b200 as fk
 from fiksi_b200 import workloads as wl
 w=wl.lattice(400,250); v,p,s=w.prepare()
 x0=v[0][w.free_vars]
-for tm,tw in ((16,16384),(64,4096)):
+for tm,tw in ((8,32768),(16,16384)):
     os.environ['FK_TEAM_MAX']=str(tm); os.environ['FK_TEAM_WORK']=str(tw)
     topo=fk.Topology.from_arrays(w.n_vars,w.kind,w.idx,w.free_vars,w.rows)
     topo.lm_solve(v[0],p[0],x0)
