@@ -293,7 +293,7 @@ def assembly_bandwidth(fk, wl, torch, device, peak):
         times.append(a.elapsed_time(b))
     ms = sum(times) / len(times)
     alg = topo.info["eval_bytes"] * n
-    out = {"kernel": "fk_batch_eval_kernel<true>", "workload": "config 4 topology, 1,000,000 sketches",
+    out = {"kernel": "fk_batch_eval_tiled_kernel<64,true>", "workload": "config 4 topology, 1,000,000 sketches",
            "algorithmic_bytes": alg, "ms": ms, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
     out["frac"] = out["achieved"] / peak
     plan.close()

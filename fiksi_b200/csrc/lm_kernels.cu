@@ -8,8 +8,10 @@
 // Compiled with -fmad=false: every a*b+c below is two roundings unless it is an explicit fma().
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "expressions.cuh"
 #include "lm_kernels.cuh"
@@ -366,6 +368,168 @@ fk_batch_eval_kernel(const DevProgram P, uint32_t n_sketches, const double* __re
     }
 }
 
+// K1 / K2, tile-staged: a CTA owns S consecutive sketches at a time.  Their variables and
+// parameters are one contiguous chunk of the caller's [sketch][var] arrays; the CTA reads the chunk
+// with fully coalesced loads and transposes it on the fly into shared memory as [var][sketch]
+// (row stride S+1 doubles: odd, so both the transposing writes and the per-sketch reads are
+// bank-conflict free).  Work items are (row, sketch) pairs with the sketch index fastest, so a warp
+// evaluates ONE row for 32 sketches: the slot table entries are warp-uniform broadcasts, there is
+// no divergence between expression kinds, and every gather / scatter is a conflict-free shared
+// memory access.  Residuals and Jacobian values are collected in shared memory ([pos][sketch]) and
+// leave as contiguous, coalesced stores.  HBM sees each input and output byte exactly once.
+constexpr int kEvalThreads = 128;
+
+// Row table decoded once per CTA into shared memory: all offsets are premultiplied by the tile's
+// leading dimension, so the inner loop is `value = sv[voff + sketch]`.
+struct alignas(16) EvalRow {
+    uint32_t kind;      // bit 8: the row has a fixed or a duplicated slot (slow scatter path)
+    uint32_t poff;      // parameter offset
+    uint32_t pad0, pad1;
+    uint32_t voff[8];   // variable offsets
+    uint32_t joff[8];   // Jacobian offsets; kNop: no entry (fixed variable); bit 31: add (duplicate column)
+};
+
+template <int KIND, bool WITH_JACOBIAN, bool SPECIAL>
+__device__ __forceinline__ void eval_tiled_row(const EvalRow& T, uint32_t sk, uint32_t roff, const double* sv,
+                                               const double* sp, double* sr, double* sj) {
+    constexpr int A = (int)((0x78888566642ull >> (4 * KIND)) & 0xF);
+    double v[8], g[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) v[s] = s < A ? sv[T.voff[s] + sk] : 0.0;
+    sr[roff + sk] = dev::eval_expression(KIND, v, sp[T.poff + sk], g);
+    if (WITH_JACOBIAN) {
+#pragma unroll
+        for (int s = 0; s < A; s++) {
+            if (SPECIAL) {
+                const uint32_t j = T.joff[s];
+                if (j != kNop) {
+                    const uint32_t pos = (j & 0x7FFFFFFFu) + sk;
+                    if (j >> 31) sj[pos] += g[s];
+                    else sj[pos] = g[s];
+                }
+            } else {
+                sj[T.joff[s] + sk] = g[s];
+            }
+        }
+    }
+}
+
+template <int S, bool WITH_JACOBIAN>
+__global__ void __launch_bounds__(kEvalThreads, 8)
+fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
+                           const double* __restrict__ params_all, double* __restrict__ out_r, double* __restrict__ out_j) {
+    extern __shared__ __align__(16) double smem_eval[];
+    double* smem = smem_eval;
+    constexpr uint32_t LD = S + 1;
+    const uint32_t nv = P.n_vars, ne = P.n_expr, m = P.m, jn = P.jnnz;
+    double* sv = smem;                 // [nv][LD]
+    double* sp = sv + (size_t)nv * LD;  // [ne][LD]
+    double* sr = sp + (size_t)ne * LD;  // [m][LD]
+    double* sj = sr + (size_t)m * LD;   // [jn][LD]
+    EvalRow* tab = reinterpret_cast<EvalRow*>(sj + (WITH_JACOBIAN ? (size_t)jn * LD : 0) + ((nv + ne + m + (WITH_JACOBIAN ? jn : 0)) & 1u));
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_tiles = (n_sketches + S - 1) / S;
+
+    for (uint32_t row = tid; row < m; row += kEvalThreads) {
+        const uint32_t hdr = __ldg(P.row_hdr + row);
+        const int kind = (int)(hdr & 0xFFu);
+        const int a = dev::arity_of(kind);
+        EvalRow t;
+        bool special = false;
+        for (int s = 0; s < 8; s++) {
+            t.voff[s] = 0;
+            t.joff[s] = kNop;
+            if (s < a) {
+                const uint2 sl = __ldg(P.row_slots + row * 8 + s);
+                const uint32_t var = (int32_t)sl.x >= 0 ? __ldg(P.free_vars + sl.x) : (sl.x & 0x7FFFFFFFu);
+                t.voff[s] = var * LD;
+                if (sl.y == kNop) special = true;
+                else {
+                    t.joff[s] = (sl.y & 0xFFFFFFu) * LD;
+                    if (sl.y & 0x40000000u) { t.joff[s] |= 0x80000000u; special = true; }
+                }
+            }
+        }
+        t.kind = (uint32_t)kind | (special ? 0x100u : 0u);
+        t.poff = (hdr >> 8) * LD;
+        t.pad0 = t.pad1 = 0;
+        tab[row] = t;
+    }
+
+    // Flat element i of a [count][width] chunk lives at [i % width][i / width] of the transposed tile;
+    // the division is a multiply-high by ceil(2^32 / width) (exact while i * width < 2^32, which the
+    // launcher checks), so the loops carry no dependency and unroll four deep.
+    auto transpose_in = [&](const double* __restrict__ src, double* dst, uint32_t width, uint32_t total) {
+        if (width == 0) return;
+        const uint32_t M = width == 1 ? 0u : 0xFFFFFFFFu / width + 1u;
+        uint32_t i = tid;
+        for (; i + 3 * kEvalThreads < total; i += 4 * kEvalThreads) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldcs(src + i + u * kEvalThreads);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t e = i + u * kEvalThreads, q = width == 1 ? e : __umulhi(e, M);
+                dst[(e - q * width) * LD + q] = v[u];
+            }
+        }
+        for (; i < total; i += kEvalThreads) {
+            const uint32_t q = width == 1 ? i : __umulhi(i, M);
+            dst[(i - q * width) * LD + q] = __ldcs(src + i);
+        }
+    };
+    auto transpose_out = [&](const double* src, double* __restrict__ dst, uint32_t width, uint32_t total) {
+        if (width == 0) return;
+        const uint32_t M = width == 1 ? 0u : 0xFFFFFFFFu / width + 1u;
+        uint32_t i = tid;
+        for (; i + 3 * kEvalThreads < total; i += 4 * kEvalThreads) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t e = i + u * kEvalThreads, q = width == 1 ? e : __umulhi(e, M);
+                v[u] = src[(e - q * width) * LD + q];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) __stcs(dst + i + u * kEvalThreads, v[u]);
+        }
+        for (; i < total; i += kEvalThreads) {
+            const uint32_t q = width == 1 ? i : __umulhi(i, M);
+            __stcs(dst + i, src[(i - q * width) * LD + q]);
+        }
+    };
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t first = tile * S;
+        const uint32_t count = min((uint32_t)S, n_sketches - first);
+        transpose_in(vars_all + (size_t)first * nv, sv, nv, count * nv);
+        transpose_in(params_all + (size_t)first * ne, sp, ne, count * ne);
+        __syncthreads();
+        for (uint32_t item = tid; item < m * S; item += kEvalThreads) {
+            const uint32_t row = item / S, sk = item % S;  // S is a power of two >= 32: row is warp-uniform
+            if (sk >= count) continue;
+            const EvalRow& T = tab[row];
+            const uint32_t roff = row * LD;
+#define FK_ROW(K)                                                                                   \
+    case K:                                                                                         \
+        eval_tiled_row<K, WITH_JACOBIAN, false>(T, sk, roff, sv, sp, sr, sj);                       \
+        break;                                                                                      \
+    case 0x100 | K:                                                                                 \
+        eval_tiled_row<K, WITH_JACOBIAN, true>(T, sk, roff, sv, sp, sr, sj);                        \
+        break;
+            switch (T.kind) {
+                FK_ROW(0) FK_ROW(1) FK_ROW(2) FK_ROW(3) FK_ROW(4) FK_ROW(5)
+                FK_ROW(6) FK_ROW(7) FK_ROW(8) FK_ROW(9) FK_ROW(10)
+                default: break;
+            }
+#undef FK_ROW
+        }
+        __syncthreads();
+        transpose_out(sr, out_r + (size_t)first * m, m, count * m);
+        if (WITH_JACOBIAN) transpose_out(sj, out_j + (size_t)first * jn, jn, count * jn);
+        __syncthreads();
+    }
+}
+
 const char* lm_kernel_name() { return "fk_batch_lm_kernel"; }
 
 // FP64 roofline denominator: 8 independent DFMA chains per thread, enough warps to fill every SMSP.
@@ -456,6 +620,46 @@ int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double*
                       double* out_r, double* out_j, int mode, void* stream) {
     if (n_sketches == 0 || prog.m == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    // tile-staged kernel whenever S >= 32 sketches fit in shared memory with >= 2 CTAs per SM
+    {
+        const size_t per_sketch_rows = (size_t)prog.n_vars + prog.n_expr + prog.m + (mode == 0 ? prog.jnnz : 0);
+        auto bytes_for = [&](int S) { return (per_sketch_rows * (size_t)(S + 1) + 1) * sizeof(double) + (size_t)prog.m * sizeof(EvalRow); };
+        // largest tile that keeps >= 5 CTAs (20 warps) per SM; measured best on the config-4 topology:
+        // the kernel is latency bound (FP64 div / sqrt / atan2 chains), not capacity bound
+        int S = 0;
+        for (int cand : {32, 64, 128})
+            if (bytes_for(cand) <= 40 * 1024) S = cand;
+        if (S == 0)
+            for (int cand : {128, 64, 32})
+                if (bytes_for(cand) <= 110 * 1024) { S = cand; break; }
+        if (const char* e = std::getenv("FK_EVAL_S")) {
+            const int f = std::atoi(e);
+            if ((f == 32 || f == 64 || f == 128) && bytes_for(f) <= 200 * 1024) S = f;
+        }
+        {   // exactness bound of the multiply-high division in the transposes
+            const uint64_t wmax = std::max<uint64_t>(std::max(prog.n_vars, prog.n_expr), std::max(prog.m, prog.jnnz));
+            if (S != 0 && wmax * wmax * (uint64_t)S >= (1ull << 32)) S = 0;
+        }
+        if (S != 0) {
+            const size_t smem = bytes_for(S);
+            const int ctas_per_sm = (int)std::min<size_t>(16, (226 * 1024) / (smem + 1024));
+            const uint32_t tiles = (n_sketches + S - 1) / S;
+            const uint32_t grid = std::min<uint32_t>(tiles, 148u * (uint32_t)ctas_per_sm);
+            cudaError_t e = cudaSuccess;
+#define FK_EVAL_TILED(SV, JV)                                                                                          \
+    do {                                                                                                               \
+        e = cudaFuncSetAttribute(fk_batch_eval_tiled_kernel<SV, JV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess)                                                                                          \
+            fk_batch_eval_tiled_kernel<SV, JV><<<grid, kEvalThreads, smem, s>>>(prog, n_sketches, vars, params, out_r, out_j); \
+    } while (0)
+            if (S == 128) { if (mode == 0) FK_EVAL_TILED(128, true); else FK_EVAL_TILED(128, false); }
+            else if (S == 64) { if (mode == 0) FK_EVAL_TILED(64, true); else FK_EVAL_TILED(64, false); }
+            else { if (mode == 0) FK_EVAL_TILED(32, true); else FK_EVAL_TILED(32, false); }
+#undef FK_EVAL_TILED
+            if (e != cudaSuccess) return (int)e;
+            return (int)cudaGetLastError();
+        }
+    }
     const uint64_t total = (uint64_t)n_sketches * prog.m;
     uint64_t blocks = (total + 255) / 256;
     const uint64_t cap = 148ull * 8 * 4;  // a few waves of resident CTAs, grid-stride beyond that

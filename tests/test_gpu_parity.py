@@ -76,7 +76,7 @@ def test_uniform_batch_matches_oracle(oracle, maker, n):
 
 def test_eval_kernels_bit_exact_where_possible(oracle):
     for maker in (wl.truss, wl.cad_mix):
-        w = maker(512)
+        w = maker(500)  # ragged last tile of the tile-staged kernel (S = 32 / 128)
         v, p, scale = w.prepare()
         topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
         plan = topo.plan(w.n)
