@@ -1,0 +1,795 @@
+// See multifrontal.cuh.  Compiled with -fmad=false like the rest of the library; the linear algebra
+// uses explicit fma().
+#include "multifrontal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+#include "symbolic.hpp"
+
+namespace fk {
+
+namespace {
+
+constexpr int kSmallFront = 32;   // fronts up to this order are factorised by one warp in shared memory
+constexpr int kSmallLd = kSmallFront + 1;
+constexpr int kWarpsPerCta = 8;
+constexpr int TB = 64;            // tile order of the big path
+constexpr int KC = 16;            // pivot columns staged per step of the micro-kernel
+constexpr int kTileThreads = 256;
+constexpr int kCsLd = TB + 1;
+
+__device__ __forceinline__ void flag_pivot(int* status, double d) {
+    if (d != d) atomicMax(status, 2);
+    else if (!(d > 0.0) || d == INFINITY) atomicMax(status, 1);
+}
+
+// ---- small subtrees: one warp per subtree, supernodes in ascending (= topological) order ---------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+mf_small_factor_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint32_t* __restrict__ sub_list, uint32_t nsub) {
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sub = blockIdx.x * kWarpsPerCta + warp;
+    if (sub >= nsub) return;
+    double* F = sm + warp * (kSmallFront * kSmallLd);  // F[i][j], j <= i
+    const uint32_t i = lane;
+    for (uint32_t q = __ldg(sub_ptr + sub); q < __ldg(sub_ptr + sub + 1); q++) {
+        const uint32_t s = __ldg(sub_list + q);
+        const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
+        double* P = D.pan + __ldg(D.pan_off + s);
+        if (i < f)
+            for (uint32_t j = 0; j <= i; j++) F[i * kSmallLd + j] = j < ns ? P[(size_t)j * f + i] : 0.0;
+        __syncwarp();
+        // extend-add of the children's update matrices, children in ascending order
+        for (uint32_t cq = __ldg(D.child_ptr + s); cq < __ldg(D.child_ptr + s + 1); cq++) {
+            const uint32_t c = __ldg(D.child + cq);
+            const uint32_t rc = __ldg(D.f + c) - __ldg(D.ns + c);
+            const double* U = D.upd + __ldg(D.upd_off + c);
+            const uint32_t ta = i < rc ? __ldg(D.rel + __ldg(D.rel_off + c) + i) : 0u;
+            for (uint32_t b = 0; b < rc; b++) {
+                const uint32_t tb = __shfl_sync(0xFFFFFFFFu, ta, b);
+                if (i >= b && i < rc) F[ta * kSmallLd + tb] += U[(size_t)b * rc + i];
+            }
+            __syncwarp();
+        }
+        // LDLt of the pivot columns; the trailing block receives the Schur complement
+        for (uint32_t k = 0; k < ns; k++) {
+            const double d = F[k * kSmallLd + k];
+            if (lane == 0) flag_pivot(D.status, d);
+            const double inv = 1.0 / d;
+            double li = 0.0;
+            if (i > k && i < f) {
+                li = F[i * kSmallLd + k] * inv;
+                for (uint32_t j = k + 1; j <= i; j++)
+                    F[i * kSmallLd + j] = fma(-li, F[j * kSmallLd + k], F[i * kSmallLd + j]);
+            }
+            __syncwarp();
+            if (i > k && i < f) F[i * kSmallLd + k] = li;
+            __syncwarp();
+        }
+        if (i < f)
+            for (uint32_t j = 0; j <= i && j < ns; j++) P[(size_t)j * f + i] = F[i * kSmallLd + j];
+        if (i >= ns && i < f) {
+            double* U = D.upd + __ldg(D.upd_off + s);
+            for (uint32_t j = ns; j <= i; j++) U[(size_t)(j - ns) * r + (i - ns)] = F[i * kSmallLd + j];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- big path -----------------------------------------------------------------------------------------
+// Assembly of one block of front columns [lo, hi) of supernode s: zero the block's part of U_s,
+// then add the children's update matrices in ascending child order.  Blocks of one front have
+// disjoint targets, so the kernel needs no atomics and the summation order is fixed.
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ a, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+mf_asm_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, lo = t.y, hi = t.z;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
+    double* P = D.pan + __ldg(D.pan_off + s);
+    double* U = D.upd + __ldg(D.upd_off + s);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t col = max(lo, ns) + warp; col < hi; col += 8)
+        for (uint32_t row = col + lane; row < f; row += 32) U[(size_t)(col - ns) * r + (row - ns)] = 0.0;
+    __syncthreads();
+    for (uint32_t cq = __ldg(D.child_ptr + s); cq < __ldg(D.child_ptr + s + 1); cq++) {
+        const uint32_t c = __ldg(D.child + cq);
+        const uint32_t rc = __ldg(D.f + c) - __ldg(D.ns + c);
+        const double* Uc = D.upd + __ldg(D.upd_off + c);
+        const uint32_t* relc = D.rel + __ldg(D.rel_off + c);
+        const uint32_t b_lo = lower_bound_u32(relc, rc, lo), b_hi = lower_bound_u32(relc, rc, hi);
+        for (uint32_t b = b_lo + warp; b < b_hi; b += 8) {
+            const uint32_t tb = __ldg(relc + b);
+            double* dst = tb < ns ? P + (size_t)tb * f : U + (size_t)(tb - ns) * r - ns;
+            const double* src = Uc + (size_t)b * rc;
+            for (uint32_t a = b + lane; a < rc; a += 32) dst[__ldg(relc + a)] += src[a];
+        }
+        __syncthreads();
+    }
+}
+
+// Register-blocked FP64 micro-kernel: acc(4x4 per thread, 64x64 per CTA) -= A * diag(d) * B^T over
+// the first K pivot columns of the panel P (column-major, leading dimension f), A = rows
+// rowA0..rowA0+nrA, B = rows rowB0..rowB0+nrB.  Thread (tid & 15) owns rows 4*(tid&15).., thread
+// (tid >> 4) owns columns 4*(tid>>4)...  Chunks of KC columns go through double-buffered shared
+// memory; the next chunk is fetched into registers while the current one is multiplied.
+struct TileBuf {
+    double A[2][KC][TB];
+    double B[2][KC][TB];
+};
+
+__device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __restrict__ P, uint32_t f, uint32_t rowA0,
+                                           uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, TileBuf& buf) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lk = tid >> 4, lr = (tid & 15) * 4;
+    const uint32_t r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
+    const uint32_t nchunks = (K + KC - 1) / KC;
+    double ra[4], rb[4];
+    auto gload = [&](uint32_t ch) {
+        const uint32_t k = ch * KC + lk;
+#pragma unroll
+        for (int u = 0; u < 4; u++) ra[u] = rb[u] = 0.0;
+        if (k < K) {
+            const double* col = P + (size_t)k * f;
+            const double dk = col[k];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (lr + u < nrA) ra[u] = col[rowA0 + lr + u] * dk;
+                if (lr + u < nrB) rb[u] = col[rowB0 + lr + u];
+            }
+        }
+    };
+    if (nchunks) gload(0);
+    for (uint32_t ch = 0; ch < nchunks; ch++) {
+        const uint32_t b = ch & 1;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            buf.A[b][lk][lr + u] = ra[u];
+            buf.B[b][lk][lr + u] = rb[u];
+        }
+        __syncthreads();
+        if (ch + 1 < nchunks) gload(ch + 1);
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            double a[4], bb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                a[u] = buf.A[b][k][r4 + u];
+                bb[u] = buf.B[b][k][c4 + u];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fma(-a[i], bb[j], acc[i][j]);
+        }
+    }
+    __syncthreads();
+}
+
+// Diagonal tile kb of supernode s: left-looking update with all earlier pivot columns, LDLt of the
+// tile in shared memory, W = D^-1 L^-1 of the tile for the panel kernel.
+__global__ void __launch_bounds__(kTileThreads)
+mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    TileBuf& buf = *reinterpret_cast<TileBuf*>(smraw);
+    double* Cs = reinterpret_cast<double*>(smraw + sizeof(TileBuf));  // [TB][kCsLd]
+    double* Xs = Cs + TB * kCsLd;                                      // [TB][kCsLd]
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
+    const uint32_t f = __ldg(D.f + s);
+    double* P = D.pan + __ldg(D.pan_off + s);
+    const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t ii = r4 + i, jj = c4 + j;
+            acc[i][j] = (ii < nc && jj <= ii) ? P[(size_t)(col0 + jj) * f + col0 + ii] : 0.0;
+        }
+    tile_kloop(acc, P, f, col0, nc, col0, nc, col0, buf);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            Cs[(r4 + i) * kCsLd + c4 + j] = acc[i][j];
+            Xs[(r4 + i) * kCsLd + c4 + j] = (r4 + i == c4 + j) ? 1.0 : 0.0;
+        }
+    __syncthreads();
+    // LDLt, right-looking inside the tile: thread (i, jg) updates row i, columns j = k+1+jg, +4, ...
+    const uint32_t ti = tid & 63, jg = tid >> 6;
+    for (uint32_t k = 0; k < nc; k++) {
+        const double d = Cs[k * kCsLd + k];
+        if (tid == 0) flag_pivot(D.status, d);
+        const double inv = 1.0 / d;
+        const uint32_t i = k + 1 + ti;
+        double li = 0.0;
+        if (i < nc) {
+            li = Cs[i * kCsLd + k] * inv;
+            for (uint32_t j = k + 1 + jg; j <= i; j += 4)
+                Cs[i * kCsLd + j] = fma(-li, Cs[j * kCsLd + k], Cs[i * kCsLd + j]);
+        }
+        __syncthreads();
+        if (i < nc && jg == 0) Cs[i * kCsLd + k] = li;
+        __syncthreads();
+    }
+    // X = L^-1 by a right-looking sweep: row k of X is final after steps 0..k-1
+    for (uint32_t k = 0; k + 1 < nc; k++) {
+        const uint32_t i = k + 1 + ti;
+        if (i < nc) {
+            const double lik = Cs[i * kCsLd + k];
+            for (uint32_t c = jg; c <= k; c += 4) Xs[i * kCsLd + c] = fma(-lik, Xs[k * kCsLd + c], Xs[i * kCsLd + c]);
+        }
+        __syncthreads();
+    }
+    // write back: L below the diagonal, D on it; W[c][c'] = X[c][c'] / d_c (row-major, lower)
+    double* W = D.winv + ((size_t)__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
+    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
+        const uint32_t i = e & 63, j = e >> 6;  // i fastest: coalesced panel stores
+        if (i < nc && j <= i) P[(size_t)(col0 + j) * f + col0 + i] = Cs[i * kCsLd + j];
+        const uint32_t c = e >> 6, cp = e & 63;  // W row-major
+        W[e] = (c < nc && cp <= c) ? Xs[c * kCsLd + cp] / Cs[c * kCsLd + c] : 0.0;
+    }
+}
+
+// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): left-looking update, then
+// L = C * W^T with W = D^-1 L_kk^-1 of the diagonal tile.
+__global__ void __launch_bounds__(kTileThreads)
+mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    TileBuf& buf = *reinterpret_cast<TileBuf*>(smraw);
+    double* Cs = reinterpret_cast<double*>(smraw + sizeof(TileBuf));  // [TB][kCsLd]
+    double* Wt = Cs + TB * kCsLd;                                      // [TB][kCsLd]: Wt[c'][c] = W[c][c']
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, row0 = t.y, col0 = t.z, nr = t.w & 0xFFFFu, nc = t.w >> 16;
+    const uint32_t f = __ldg(D.f + s);
+    double* P = D.pan + __ldg(D.pan_off + s);
+    const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            acc[i][j] = (r4 + i < nr && c4 + j < nc) ? P[(size_t)(col0 + c4 + j) * f + row0 + r4 + i] : 0.0;
+    const double* W = D.winv + ((size_t)__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
+    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) Wt[(e & 63) * kCsLd + (e >> 6)] = W[e];
+    tile_kloop(acc, P, f, row0, nr, col0, nc, col0, buf);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) Cs[(r4 + i) * kCsLd + c4 + j] = acc[i][j];
+    __syncthreads();
+    double out[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[i][j] = 0.0;
+    for (uint32_t cp = 0; cp < nc; cp++) {
+        double a[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u] = Cs[(r4 + u) * kCsLd + cp];
+            w[u] = Wt[cp * kCsLd + c4 + u];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) out[i][j] = fma(a[i], w[j], out[i][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (r4 + i < nr && c4 + j < nc) P[(size_t)(col0 + c4 + j) * f + row0 + r4 + i] = out[i][j];
+}
+
+// Update tile of U_s: rows row0.., columns col0.. (front coordinates, both >= ns): U -= L D L^T over
+// all ns pivot columns.
+__global__ void __launch_bounds__(kTileThreads)
+mf_upd_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    __shared__ TileBuf buf;
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, row0 = t.y, col0 = t.z, nrA = t.w & 0xFFFFu, nrB = t.w >> 16;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    double* U = D.upd + __ldg(D.upd_off + s);
+    const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t gi = row0 + r4 + i, gj = col0 + c4 + j;
+            acc[i][j] = (r4 + i < nrA && c4 + j < nrB && gi >= gj) ? U[(size_t)(gj - ns) * r + (gi - ns)] : 0.0;
+        }
+    tile_kloop(acc, P, f, row0, nrA, col0, nrB, ns, buf);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t gi = row0 + r4 + i, gj = col0 + c4 + j;
+            if (r4 + i < nrA && c4 + j < nrB && gi >= gj) U[(size_t)(gj - ns) * r + (gi - ns)] = acc[i][j];
+        }
+}
+
+// ---- triangular solves ------------------------------------------------------------------------------------
+// Forward: y = L^-1 b with per-supernode update vectors (multifrontal style: a parent gathers its
+// children's vectors through the relative indices, in child order, so no atomics).  Backward:
+// z = L^-T D^-1 y, gathering the ancestors' solution through the front's row list.
+// G = threads cooperating on one supernode (32: a warp, 256: a CTA).
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    if (G == 32) __syncwarp();
+    else __syncthreads();
+}
+
+template <int G>
+__device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, double* __restrict__ w, double* t, double* tri,
+                                                  uint32_t gt) {
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    for (uint32_t i = gt; i < f; i += G) t[i] = i < ns ? w[c0 + i] : 0.0;
+    group_sync<G>();
+    for (uint32_t cq = __ldg(D.child_ptr + s); cq < __ldg(D.child_ptr + s + 1); cq++) {
+        const uint32_t c = __ldg(D.child + cq);
+        const uint32_t rc = __ldg(D.f + c) - __ldg(D.ns + c), ro = __ldg(D.rel_off + c);
+        for (uint32_t a = gt; a < rc; a += G) t[__ldg(D.rel + ro + a)] += D.ubuf[ro + a];
+        group_sync<G>();
+    }
+    for (uint32_t k0 = 0; k0 < ns; k0 += 32) {
+        const uint32_t nb = min(32u, ns - k0);
+        // stage the nb x nb unit-lower triangle: tri[i][k]
+        for (uint32_t e = gt; e < nb * 32; e += G) {
+            const uint32_t i = e & 31, k = e >> 5;
+            if (i < nb && i > k) tri[i * 33 + k] = P[(size_t)(k0 + k) * f + k0 + i];
+        }
+        group_sync<G>();
+        if (gt < 32) {
+            double ti = gt < nb ? t[k0 + gt] : 0.0;
+            for (uint32_t k = 0; k + 1 < nb; k++) {
+                const double yk = __shfl_sync(0xFFFFFFFFu, ti, k);
+                if (gt > k && gt < nb) ti = fma(-tri[gt * 33 + k], yk, ti);
+            }
+            if (gt < nb) t[k0 + gt] = ti;
+        }
+        group_sync<G>();
+        // rows below the block: t[i] -= L[i, block] . y[block]
+        for (uint32_t i = k0 + nb + gt; i < f; i += G) {
+            double acc = 0.0;
+            for (uint32_t k = 0; k < nb; k++) acc = fma(P[(size_t)(k0 + k) * f + i], t[k0 + k], acc);
+            t[i] -= acc;
+        }
+        group_sync<G>();
+    }
+    const uint32_t ro = __ldg(D.rel_off + s);
+    for (uint32_t i = gt; i < f; i += G) {
+        if (i < ns) w[c0 + i] = t[i];
+        else D.ubuf[ro + i - ns] = t[i];
+    }
+    group_sync<G>();
+}
+
+template <int G>
+__device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, double* __restrict__ w, double* __restrict__ delta,
+                                                   const int32_t* __restrict__ perm, double* t, double* tri, uint32_t gt) {
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    const uint32_t* rows = D.rows + __ldg(D.rows_off + s);
+    // t[i >= ns] = z of the ancestors; t[i < ns] = y_i / d_i
+    for (uint32_t i = gt; i < f; i += G) t[i] = i < ns ? w[c0 + i] / P[(size_t)i * f + i] : w[__ldg(rows + i)];
+    group_sync<G>();
+    const uint32_t nblk = (ns + 31) / 32;
+    for (uint32_t bi = nblk; bi-- > 0;) {
+        const uint32_t k0 = bi * 32, nb = min(32u, ns - k0);
+        // column dots with everything below the block: one warp per column
+        {
+            const uint32_t wp = gt >> 5, ln = gt & 31;
+            for (uint32_t k = wp; k < nb; k += G / 32) {
+                const double* col = P + (size_t)(k0 + k) * f;
+                double acc = 0.0;
+                for (uint32_t i = k0 + nb + ln; i < f; i += 32) acc = fma(col[i], t[i], acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                if (ln == 0) t[k0 + k] -= acc;
+            }
+        }
+        for (uint32_t e = gt; e < nb * 32; e += G) {
+            const uint32_t i = e & 31, k = e >> 5;
+            if (i < nb && i > k) tri[i * 33 + k] = P[(size_t)(k0 + k) * f + k0 + i];
+        }
+        group_sync<G>();
+        if (gt < 32) {
+            double zi = gt < nb ? t[k0 + gt] : 0.0;
+            for (uint32_t k = nb; k-- > 1;) {
+                const double zk = __shfl_sync(0xFFFFFFFFu, zi, k);
+                if (gt < k) zi = fma(-tri[k * 33 + gt], zk, zi);
+            }
+            if (gt < nb) t[k0 + gt] = zi;
+        }
+        group_sync<G>();
+    }
+    for (uint32_t i = gt; i < ns; i += G) {
+        const double z = t[i];
+        w[c0 + i] = z;
+        delta[__ldg(perm + c0 + i)] = z;
+    }
+    group_sync<G>();
+}
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+mf_small_solve_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint32_t* __restrict__ sub_list, uint32_t nsub,
+                      double* __restrict__ w, double* __restrict__ delta, const int32_t* __restrict__ perm) {
+    extern __shared__ double sms[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* tri = sms + warp * (32 * 33 + kSmallFront);
+    double* t = tri + 32 * 33;
+    const uint32_t sub = blockIdx.x * kWarpsPerCta + warp;
+    if (sub >= nsub) return;
+    const uint32_t q0 = __ldg(sub_ptr + sub), q1 = __ldg(sub_ptr + sub + 1);
+    if (FORWARD) {
+        for (uint32_t q = q0; q < q1; q++) forward_supernode<32>(D, __ldg(sub_list + q), w, t, tri, lane);
+    } else {
+        for (uint32_t q = q1; q-- > q0;) backward_supernode<32>(D, __ldg(sub_list + q), w, delta, perm, t, tri, lane);
+    }
+}
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(256)
+mf_big_solve_kernel(MfDev D, const uint32_t* __restrict__ list, double* __restrict__ w, double* __restrict__ delta,
+                    const int32_t* __restrict__ perm) {
+    extern __shared__ double smd[];
+    double* tri = smd;            // [32*33]
+    double* t = smd + 32 * 33;    // [max front]
+    const uint32_t s = __ldg(list + blockIdx.x);
+    if (FORWARD) forward_supernode<256>(D, s, w, t, tri, threadIdx.x);
+    else backward_supernode<256>(D, s, w, delta, perm, t, tri, threadIdx.x);
+}
+
+template <class T>
+cudaError_t upload_vec(const std::vector<T>& v, const T** out, std::vector<void*>& owned) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    owned.push_back(d);
+    if (!v.empty()) e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T*)d;
+    return e;
+}
+
+template <class T>
+cudaError_t alloc_vec(T** out, size_t count, std::vector<void*>& owned) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, std::max<size_t>(1, count) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    owned.push_back(d);
+    *out = (T*)d;
+    return e;
+}
+
+constexpr size_t kDiagSmem = sizeof(TileBuf) + 2 * TB * kCsLd * sizeof(double);
+constexpr size_t kSmallFactorSmem = (size_t)kWarpsPerCta * kSmallFront * kSmallLd * sizeof(double);
+constexpr size_t kSmallSolveSmem = (size_t)kWarpsPerCta * (32 * 33 + kSmallFront) * sizeof(double);
+
+}  // namespace
+
+Multifrontal::~Multifrontal() {
+    if (factor_graph_) cudaGraphExecDestroy(factor_graph_);
+    if (solve_graph_) cudaGraphExecDestroy(solve_graph_);
+    for (void* p : owned_) cudaFree(p);
+}
+
+#define MF_CU(call)                      \
+    do {                                 \
+        cudaError_t e_ = (call);         \
+        if (e_ != cudaSuccess) {         \
+            if (err) *err = #call;       \
+            return e_;                   \
+        }                                \
+    } while (0)
+
+cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::string* err) {
+    (void)stream;
+    const uint32_t n = t.n_free;
+    n_ = n;
+    const std::vector<uint32_t>& lc = t.l_colptr;
+    const std::vector<uint32_t>& lr = t.l_rowidx;
+    // ---- supernodes: column j joins its predecessor's supernode when parent[j-1] == j and
+    // struct(j) == struct(j-1) \ {j-1}
+    std::vector<uint32_t> c0, col2sn(n);
+    for (uint32_t j = 0; j < n; j++) {
+        const bool joins = j > 0 && t.parent[j - 1] == (int32_t)j && (lc[j + 1] - lc[j]) + 1 == (lc[j] - lc[j - 1]);
+        if (!joins) c0.push_back(j);
+        col2sn[j] = (uint32_t)c0.size() - 1;
+    }
+    const uint32_t S = (uint32_t)c0.size();
+    std::vector<uint32_t> ns(S), f(S), rows_off(S + 1, 0), rel_off(S + 1, 0);
+    std::vector<uint64_t> pan_off(S), upd_off(S);
+    std::vector<int32_t> sparent(S);
+    uint64_t pan_total = 0, upd_total = 0;
+    flops_ = 0;
+    for (uint32_t s = 0; s < S; s++) {
+        const uint32_t last = (s + 1 < S ? c0[s + 1] : n) - 1;
+        ns[s] = last - c0[s] + 1;
+        f[s] = lc[c0[s] + 1] - lc[c0[s]];
+        rows_off[s + 1] = rows_off[s] + f[s];
+        rel_off[s + 1] = rel_off[s] + (f[s] - ns[s]);
+        pan_off[s] = pan_total;
+        pan_total += (uint64_t)f[s] * ns[s];
+        upd_off[s] = upd_total;
+        upd_total += (uint64_t)(f[s] - ns[s]) * (f[s] - ns[s]);
+        sparent[s] = t.parent[last] >= 0 ? (int32_t)col2sn[t.parent[last]] : -1;
+    }
+    for (uint32_t j = 0; j < n; j++) flops_ += (uint64_t)(lc[j + 1] - lc[j]) * (lc[j + 1] - lc[j]);
+    pan_total_ = pan_total;
+    std::vector<uint32_t> rows(rows_off[S]);
+    for (uint32_t s = 0; s < S; s++) std::copy(lr.begin() + lc[c0[s]], lr.begin() + lc[c0[s]] + f[s], rows.begin() + rows_off[s]);
+    // L position -> panel offset; diagonal positions
+    lpos_map_.assign(lr.size(), 0);
+    diag_map_.assign(n, 0);
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t s = col2sn[j], k = j - c0[s];
+        const uint64_t base = pan_off[s] + (uint64_t)k * f[s] + k;
+        diag_map_[j] = base;
+        for (uint32_t q = lc[j]; q < lc[j + 1]; q++) lpos_map_[q] = base + (q - lc[j]);
+    }
+    // children (ascending) and relative indices
+    std::vector<uint32_t> child_ptr(S + 1, 0), child;
+    for (uint32_t s = 0; s < S; s++)
+        if (sparent[s] >= 0) child_ptr[sparent[s] + 1]++;
+    for (uint32_t s = 0; s < S; s++) child_ptr[s + 1] += child_ptr[s];
+    child.resize(child_ptr[S]);
+    {
+        std::vector<uint32_t> fill(child_ptr.begin(), child_ptr.end() - 1);
+        for (uint32_t s = 0; s < S; s++)
+            if (sparent[s] >= 0) child[fill[sparent[s]]++] = s;
+    }
+    std::vector<uint32_t> rel(rel_off[S]);
+    for (uint32_t s = 0; s < S; s++) {
+        if (sparent[s] < 0) {
+            if (f[s] != ns[s]) {
+                if (err) *err = "multifrontal: root supernode with an update block";
+                return cudaErrorInvalidValue;
+            }
+            continue;
+        }
+        const uint32_t p = (uint32_t)sparent[s];
+        const uint32_t* rp = rows.data() + rows_off[p];
+        const uint32_t* rs = rows.data() + rows_off[s] + ns[s];
+        uint32_t pos = 0;
+        for (uint32_t a = 0; a < f[s] - ns[s]; a++) {
+            while (pos < f[p] && rp[pos] < rs[a]) pos++;
+            if (pos >= f[p] || rp[pos] != rs[a]) {
+                if (err) *err = "multifrontal: update row missing from the parent front";
+                return cudaErrorInvalidValue;
+            }
+            rel[rel_off[s] + a] = pos;
+        }
+    }
+    // ---- small subtrees / big levels
+    std::vector<uint8_t> big(S, 0);
+    for (uint32_t s = 0; s < S; s++) {
+        if (f[s] > (uint32_t)kSmallFront) big[s] = 1;
+        if (big[s] && sparent[s] >= 0) big[sparent[s]] = 1;
+    }
+    std::vector<int32_t> sub_of(S, -1);
+    uint32_t nsub = 0;
+    for (uint32_t s = S; s-- > 0;) {
+        if (big[s]) continue;
+        if (sparent[s] < 0 || big[sparent[s]]) sub_of[s] = (int32_t)nsub++;
+        else sub_of[s] = sub_of[sparent[s]];
+    }
+    std::vector<uint64_t> sub_work(nsub, 0);
+    std::vector<uint32_t> sub_cnt(nsub, 0);
+    for (uint32_t s = 0; s < S; s++)
+        if (!big[s]) {
+            sub_work[sub_of[s]] += (uint64_t)f[s] * f[s] * ns[s] + 64;
+            sub_cnt[sub_of[s]]++;
+        }
+    std::vector<uint32_t> sub_order(nsub);
+    std::iota(sub_order.begin(), sub_order.end(), 0u);
+    std::stable_sort(sub_order.begin(), sub_order.end(), [&](uint32_t a, uint32_t b) { return sub_work[a] > sub_work[b]; });
+    std::vector<uint32_t> sub_rank(nsub), sub_ptr(nsub + 1, 0);
+    for (uint32_t k = 0; k < nsub; k++) sub_rank[sub_order[k]] = k;
+    for (uint32_t k = 0; k < nsub; k++) sub_ptr[k + 1] = sub_ptr[k] + sub_cnt[sub_order[k]];
+    std::vector<uint32_t> sub_list(sub_ptr[nsub]);
+    {
+        std::vector<uint32_t> fill(sub_ptr.begin(), sub_ptr.end() - 1);
+        for (uint32_t s = 0; s < S; s++)
+            if (!big[s]) sub_list[fill[sub_rank[sub_of[s]]]++] = s;
+    }
+    nsub_ = nsub;
+    std::vector<uint32_t> level(S, 0), winv_blk(S, 0);
+    uint32_t nlevels = 0, nbig = 0, max_front = 1, winv_blocks = 0;
+    for (uint32_t s = 0; s < S; s++) {
+        max_front = std::max(max_front, f[s]);
+        if (!big[s]) continue;
+        nbig++;
+        winv_blk[s] = winv_blocks;
+        winv_blocks += (ns[s] + TB - 1) / TB;
+        nlevels = std::max(nlevels, level[s] + 1);
+        if (sparent[s] >= 0) level[sparent[s]] = std::max(level[sparent[s]], level[s] + 1);
+    }
+    std::vector<std::vector<uint32_t>> by_level(nlevels);
+    for (uint32_t s = 0; s < S; s++)
+        if (big[s]) by_level[level[s]].push_back(s);
+    // ---- task lists of the factorisation
+    std::vector<uint32_t> tasks;  // uint4 each
+    auto push_task = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        tasks.push_back(a); tasks.push_back(b); tasks.push_back(c); tasks.push_back(d);
+    };
+    factor_seq_.clear();
+    level_ptr_.assign(1, 0);
+    std::vector<uint32_t> level_list;
+    for (uint32_t l = 0; l < nlevels; l++) {
+        const std::vector<uint32_t>& L = by_level[l];
+        for (uint32_t s : L) level_list.push_back(s);
+        level_ptr_.push_back((uint32_t)level_list.size());
+        uint32_t first = (uint32_t)(tasks.size() / 4), maxnsb = 0;
+        for (uint32_t s : L) {
+            maxnsb = std::max(maxnsb, (ns[s] + TB - 1) / TB);
+            const bool has_children = child_ptr[s + 1] > child_ptr[s];
+            for (uint32_t lo = 0; lo < f[s]; lo += TB) {
+                const uint32_t hi = std::min(f[s], lo + TB);
+                if (!has_children && hi <= ns[s]) continue;  // nothing to zero, nothing to add
+                push_task(s, lo, hi, 0);
+            }
+        }
+        uint32_t count = (uint32_t)(tasks.size() / 4) - first;
+        if (count) factor_seq_.push_back({0, first, count});
+        for (uint32_t kb = 0; kb < maxnsb; kb++) {
+            first = (uint32_t)(tasks.size() / 4);
+            for (uint32_t s : L)
+                if (kb * TB < ns[s]) push_task(s, kb * TB, kb * TB, std::min<uint32_t>(TB, ns[s] - kb * TB) << 16);
+            count = (uint32_t)(tasks.size() / 4) - first;
+            if (count) factor_seq_.push_back({1, first, count});
+            first = (uint32_t)(tasks.size() / 4);
+            for (uint32_t s : L) {
+                if (kb * TB >= ns[s]) continue;
+                const uint32_t nc = std::min<uint32_t>(TB, ns[s] - kb * TB);
+                for (uint32_t row0 = kb * TB + nc; row0 < f[s]; row0 += TB)
+                    push_task(s, row0, kb * TB, std::min<uint32_t>(TB, f[s] - row0) | (nc << 16));
+            }
+            count = (uint32_t)(tasks.size() / 4) - first;
+            if (count) factor_seq_.push_back({2, first, count});
+        }
+        first = (uint32_t)(tasks.size() / 4);
+        for (uint32_t s : L)
+            for (uint32_t col0 = ns[s]; col0 < f[s]; col0 += TB)
+                for (uint32_t row0 = col0; row0 < f[s]; row0 += TB)
+                    push_task(s, row0, col0, std::min<uint32_t>(TB, f[s] - row0) | (std::min<uint32_t>(TB, f[s] - col0) << 16));
+        count = (uint32_t)(tasks.size() / 4) - first;
+        if (count) factor_seq_.push_back({3, first, count});
+    }
+    factor_launches_ = factor_seq_.size() + (nsub ? 1 : 0);
+    stats.supernodes = S; stats.small_subtrees = nsub; stats.big = nbig; stats.levels = nlevels;
+    stats.max_front = max_front; stats.upd_doubles = upd_total;
+
+    // ---- upload
+    dev_.S = S;
+    MF_CU(upload_vec(c0, &dev_.c0, owned_));
+    MF_CU(upload_vec(ns, &dev_.ns, owned_));
+    MF_CU(upload_vec(f, &dev_.f, owned_));
+    MF_CU(upload_vec(rows_off, &dev_.rows_off, owned_));
+    MF_CU(upload_vec(rows, &dev_.rows, owned_));
+    MF_CU(upload_vec(pan_off, &dev_.pan_off, owned_));
+    MF_CU(upload_vec(upd_off, &dev_.upd_off, owned_));
+    MF_CU(upload_vec(rel_off, &dev_.rel_off, owned_));
+    MF_CU(upload_vec(rel, &dev_.rel, owned_));
+    MF_CU(upload_vec(child_ptr, &dev_.child_ptr, owned_));
+    MF_CU(upload_vec(child, &dev_.child, owned_));
+    MF_CU(upload_vec(winv_blk, &dev_.winv_blk, owned_));
+    MF_CU(upload_vec(sub_ptr, &d_sub_ptr_, owned_));
+    MF_CU(upload_vec(sub_list, &d_sub_list_, owned_));
+    MF_CU(upload_vec(level_list, &d_level_list_, owned_));
+    {
+        const uint32_t* p = nullptr;
+        MF_CU(upload_vec(tasks, &p, owned_));
+        d_tasks_ = (const uint4*)p;
+    }
+    MF_CU(alloc_vec(&dev_.pan, pan_total, owned_));
+    MF_CU(alloc_vec(&dev_.upd, upd_total, owned_));
+    MF_CU(alloc_vec(&dev_.winv, (size_t)winv_blocks * TB * TB, owned_));
+    MF_CU(alloc_vec(&dev_.ubuf, rel_off[S], owned_));
+    MF_CU(alloc_vec(&dev_.status, 1, owned_));
+    MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
+    MF_CU(cudaFuncSetAttribute(mf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
+    MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
+    MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
+    MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
+    const size_t big_solve_smem = (32 * 33 + (size_t)max_front) * sizeof(double);
+    if (big_solve_smem > 200 * 1024) {
+        if (err) *err = "multifrontal: a front is too large for the shared-memory solve vector";
+        return cudaErrorInvalidValue;
+    }
+    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    return cudaSuccess;
+}
+
+cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
+    if (nsub_) {
+        const uint32_t grid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
+        mf_small_factor_kernel<<<grid, kWarpsPerCta * 32, kSmallFactorSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_);
+    }
+    for (const Launch& l : factor_seq_) {
+        const uint4* tk = d_tasks_ + l.first;
+        switch (l.kind) {
+            case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
+            case 1: mf_diag_kernel<<<l.count, kTileThreads, kDiagSmem, st>>>(dev_, tk); break;
+            case 2: mf_col_kernel<<<l.count, kTileThreads, kDiagSmem, st>>>(dev_, tk); break;
+            default: mf_upd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t st) {
+    const uint32_t sgrid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t smem = (32 * 33 + (size_t)stats.max_front) * sizeof(double);
+    const uint32_t nlevels = (uint32_t)level_ptr_.size() - 1;
+    if (nsub_) mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
+    for (uint32_t l = 0; l < nlevels; l++)
+        mf_big_solve_kernel<true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm);
+    for (uint32_t l = nlevels; l-- > 0;)
+        mf_big_solve_kernel<false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm);
+    if (nsub_) mf_small_solve_kernel<false><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
+    return cudaGetLastError();
+}
+
+// The launch sequences are static: captured once into CUDA graphs and replayed.
+cudaError_t Multifrontal::factor(cudaStream_t st) {
+    static const bool no_graph = std::getenv("FK_NO_GRAPH") != nullptr;
+    if (no_graph || factor_launches_ < 8) return enqueue_factor(st);
+    if (!factor_graph_) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return e;
+        cudaError_t e1 = enqueue_factor(st);
+        e = cudaStreamEndCapture(st, &g);
+        if (e1 != cudaSuccess) return e1;
+        if (e != cudaSuccess) return e;
+        e = cudaGraphInstantiate(&factor_graph_, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaGraphLaunch(factor_graph_, st);
+}
+
+cudaError_t Multifrontal::solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t st) {
+    static const bool no_graph = std::getenv("FK_NO_GRAPH") != nullptr;
+    if (no_graph || level_ptr_.size() < 5) return enqueue_solve(w, delta, d_perm, st);
+    if (solve_graph_ && (w != solve_w_ || delta != solve_delta_ || d_perm != solve_perm_)) {
+        cudaGraphExecDestroy(solve_graph_);
+        solve_graph_ = nullptr;
+    }
+    if (!solve_graph_) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return e;
+        cudaError_t e1 = enqueue_solve(w, delta, d_perm, st);
+        e = cudaStreamEndCapture(st, &g);
+        if (e1 != cudaSuccess) return e1;
+        if (e != cudaSuccess) return e;
+        e = cudaGraphInstantiate(&solve_graph_, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return e;
+        solve_w_ = w; solve_delta_ = delta; solve_perm_ = d_perm;
+    }
+    return cudaGraphLaunch(solve_graph_, st);
+}
+
+}  // namespace fk

@@ -1,0 +1,96 @@
+// K5, second generation: supernodal multifrontal LDLᵀ of H = JᵀJ + lambda I in the COLAMD order,
+// and the two triangular solves, for the large single-system path (BASELINE config 3).
+//
+// Replaces Qr::factorize / Qr::solve_mut (solvi/src/decomposition/sparse/qr.rs:281-356) on the
+// pattern that SymbolicQr::build produces (qr.rs:118-206; R = Lᵀ, cholesky.rs:359-595).
+//
+// Symbolic side (host, once per topology): columns of L with nested patterns are merged into
+// supernodes; each supernode s owns a dense frontal matrix of order f_s = |struct(first column)|
+// whose first ns_s columns (the "panel", stored column-major with leading dimension f_s) become
+// columns of L and whose trailing (f_s-ns_s)² block U_s is the update ("Schur complement") that
+// its parent in the supernodal elimination tree assembles through a relative-index list.
+//
+// Numeric side: complete subtrees of small fronts (f <= 32) are factorised by ONE WARP each with the
+// front in shared memory (one launch for all of them); the remaining "big" part of the tree — for
+// the 400x250 lattice 6.6 k supernodes in 56 levels holding 99 % of the flops — runs level by level:
+// an assembly kernel (extend-add of the children, parallel over disjoint target column blocks, so
+// no atomics and a fixed summation order), then per 64-column pivot block a diagonal-tile kernel
+// (left-looking update, LDLᵀ of the 64x64 tile in shared memory, inverse of its unit factor) and a
+// panel kernel (left-looking update + multiplication with that inverse), then one kernel that
+// applies the rank-ns update to all 64x64 tiles of U.  All tile kernels share one register-blocked
+// FP64 micro-kernel (4x4 per thread, operands staged through shared memory).  The launch sequence is
+// static per topology and is replayed as a CUDA graph.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace fk {
+
+struct Topology;
+
+struct MfDev {
+    uint32_t S = 0;               // supernodes
+    const uint32_t* c0 = nullptr;        // [S] first column (permuted index)
+    const uint32_t* ns = nullptr;        // [S] pivot columns
+    const uint32_t* f = nullptr;         // [S] front order
+    const uint32_t* rows_off = nullptr;  // [S+1]
+    const uint32_t* rows = nullptr;      // front row lists (ascending permuted column indices)
+    const uint64_t* pan_off = nullptr;   // [S] panel offset (doubles)
+    const uint64_t* upd_off = nullptr;   // [S] update-matrix offset (doubles)
+    const uint32_t* rel_off = nullptr;   // [S+1] offsets into rel and into ubuf
+    const uint32_t* rel = nullptr;       // position of every update row in the parent's front
+    const uint32_t* child_ptr = nullptr; // [S+1]
+    const uint32_t* child = nullptr;     // children in ascending order
+    const uint32_t* winv_blk = nullptr;  // [S] index of the supernode's first 64x64 inverse block
+    double* pan = nullptr;        // panels: L below the diagonal (unit lower), D on the diagonal
+    double* upd = nullptr;        // update matrices (lower triangles used)
+    double* winv = nullptr;       // D^-1 L^-1 of every 64x64 diagonal tile of the big fronts
+    double* ubuf = nullptr;       // update vectors of the forward solve
+    int* status = nullptr;        // 0 ok, 1 non-positive pivot, 2 NaN pivot
+};
+
+class Multifrontal {
+public:
+    ~Multifrontal();
+    // Builds the supernodal structures from the topology's L pattern and uploads them.
+    cudaError_t init(const Topology& t, cudaStream_t stream, std::string* err);
+    // L position (Topology::l_rowidx order) -> offset in the panel storage.
+    const std::vector<uint64_t>& lpos_to_panel() const { return lpos_map_; }
+    const std::vector<uint64_t>& diag_panel() const { return diag_map_; }  // [n] panel offset of d_k
+    size_t panel_doubles() const { return pan_total_; }
+    double* panels() const { return dev_.pan; }
+    int* status() const { return dev_.status; }
+    // Numeric factorisation of the assembled panels (H entries in place, zeros elsewhere).
+    cudaError_t factor(cudaStream_t stream);
+    // w (permuted right-hand side, overwritten with the permuted solution); delta[perm[k]] = z[k].
+    cudaError_t solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t stream);
+    uint64_t flops() const { return flops_; }
+    uint32_t launches_per_factor() const { return (uint32_t)factor_launches_; }
+
+    struct Stats { uint32_t supernodes = 0, small_subtrees = 0, big = 0, levels = 0, max_front = 0; uint64_t upd_doubles = 0; } stats;
+
+private:
+    struct Launch { int kind; uint32_t first, count; };  // kind: 0 asm, 1 diag, 2 col, 3 upd
+    MfDev dev_;
+    std::vector<void*> owned_;
+    std::vector<uint64_t> lpos_map_, diag_map_;
+    size_t pan_total_ = 0;
+    uint64_t flops_ = 0;
+    uint32_t n_ = 0, nsub_ = 0;
+    const uint32_t *d_sub_ptr_ = nullptr, *d_sub_list_ = nullptr;
+    const uint4* d_tasks_ = nullptr;
+    std::vector<Launch> factor_seq_;
+    size_t factor_launches_ = 0;
+    // big supernodes by level (solve kernels)
+    const uint32_t* d_level_list_ = nullptr;
+    std::vector<uint32_t> level_ptr_;
+    cudaGraphExec_t factor_graph_ = nullptr, solve_graph_ = nullptr;
+    double* solve_w_ = nullptr; double* solve_delta_ = nullptr; const int32_t* solve_perm_ = nullptr;
+    cudaError_t enqueue_factor(cudaStream_t stream);
+    cudaError_t enqueue_solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t stream);
+};
+
+}  // namespace fk
