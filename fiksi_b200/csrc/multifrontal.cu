@@ -132,7 +132,7 @@ struct TileBuf {
 };
 
 __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __restrict__ P, uint32_t f, uint32_t rowA0,
-                                           uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, TileBuf& buf) {
+                                           uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, uint32_t diag0, TileBuf& buf) {
     const uint32_t tid = threadIdx.x;
     const uint32_t lk = tid >> 4, lr = (tid & 15) * 4;
     const uint32_t r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
@@ -144,7 +144,7 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
         for (int u = 0; u < 4; u++) ra[u] = rb[u] = 0.0;
         if (k < K) {
             const double* col = P + (size_t)k * f;
-            const double dk = col[k];
+            const double dk = col[diag0 + k];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (lr + u < nrA) ra[u] = col[rowA0 + lr + u] * dk;
@@ -179,98 +179,150 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
     __syncthreads();
 }
 
-// Diagonal tile kb of supernode s: left-looking update with all earlier pivot columns, LDLt of the
-// tile in shared memory, W = D^-1 L^-1 of the tile for the panel kernel.
+// Diagonal tile (pivot block at col0, nc <= 64 columns) of supernode s: LDLt of the tile in shared
+// memory, blocked by 16 columns (diagonal 16x16 block by half a warp, panel rows by substitution,
+// trailing update by all threads: three barriers per 16 columns), then W = D^-1 L^-1 of the tile
+// (block recurrence) for the panel kernel and the triangular solves.  Right-looking: the tile has
+// already received the updates of all earlier pivot blocks (mf_rupd_kernel).
+constexpr int SB = 16;
 __global__ void __launch_bounds__(kTileThreads)
 mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    TileBuf& buf = *reinterpret_cast<TileBuf*>(smraw);
-    double* Cs = reinterpret_cast<double*>(smraw + sizeof(TileBuf));  // [TB][kCsLd]
-    double* Xs = Cs + TB * kCsLd;                                      // [TB][kCsLd]
+    extern __shared__ __align__(16) double smd_diag[];
+    double* Cs = smd_diag;            // [TB][kCsLd] tile, lower; becomes L (unit lower), D on the diagonal
+    double* Xs = Cs + TB * kCsLd;     // [TB][kCsLd] L^-1
+    double* Ys = Xs + TB * kCsLd;     // [TB][SB+1] unscaled panel rows of the current 16-column step / scratch
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
     double* P = D.pan + __ldg(D.pan_off + s);
-    const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t ii = r4 + i, jj = c4 + j;
-            acc[i][j] = (ii < nc && jj <= ii) ? P[(size_t)(col0 + jj) * f + col0 + ii] : 0.0;
-        }
-    tile_kloop(acc, P, f, col0, nc, col0, nc, col0, buf);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            Cs[(r4 + i) * kCsLd + c4 + j] = acc[i][j];
-            Xs[(r4 + i) * kCsLd + c4 + j] = (r4 + i == c4 + j) ? 1.0 : 0.0;
-        }
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
+        const uint32_t i = e & 63, j = e >> 6;
+        Cs[i * kCsLd + j] = (i < nc && j <= i) ? P[(size_t)(col0 + j) * f + col0 + i] : 0.0;
+        Xs[i * kCsLd + j] = i == j ? 1.0 : 0.0;
+    }
     __syncthreads();
-    // LDLt, right-looking inside the tile: thread (i, jg) updates row i, columns j = k+1+jg, +4, ...
-    const uint32_t ti = tid & 63, jg = tid >> 6;
-    for (uint32_t k = 0; k < nc; k++) {
-        const double d = Cs[k * kCsLd + k];
-        if (tid == 0) flag_pivot(D.status, d);
-        const double inv = 1.0 / d;
-        const uint32_t i = k + 1 + ti;
-        double li = 0.0;
-        if (i < nc) {
-            li = Cs[i * kCsLd + k] * inv;
-            for (uint32_t j = k + 1 + jg; j <= i; j += 4)
-                Cs[i * kCsLd + j] = fma(-li, Cs[j * kCsLd + k], Cs[i * kCsLd + j]);
+    for (uint32_t b0 = 0; b0 < nc; b0 += SB) {
+        const uint32_t bw = min((uint32_t)SB, nc - b0), b1 = b0 + bw;
+        if (tid < 32) {  // (1) diagonal block, rows on lanes 0..bw-1
+            const uint32_t i = b0 + tid;
+            for (uint32_t k = b0; k < b1; k++) {
+                const double d = Cs[k * kCsLd + k];
+                if (tid == 0) flag_pivot(D.status, d);
+                const double inv = 1.0 / d;
+                double li = 0.0;
+                if (i > k && i < b1) {
+                    li = Cs[i * kCsLd + k] * inv;
+                    for (uint32_t j = k + 1; j <= i; j++) Cs[i * kCsLd + j] = fma(-li, Cs[j * kCsLd + k], Cs[i * kCsLd + j]);
+                }
+                __syncwarp();
+                if (i > k && i < b1) Cs[i * kCsLd + k] = li;
+                __syncwarp();
+            }
         }
         __syncthreads();
-        if (i < nc && jg == 0) Cs[i * kCsLd + k] = li;
-        __syncthreads();
+        if (b1 < nc) {
+            // (2) rows below: y = C[i, b0..b1) L_bb^-T (unscaled, kept in Ys), l = y / d
+            if (tid < nc - b1) {
+                const uint32_t i = b1 + tid;
+                double y[SB];
+#pragma unroll
+                for (int c = 0; c < SB; c++) {
+                    y[c] = 0.0;
+                    if ((uint32_t)c < bw) {
+                        double v = Cs[i * kCsLd + b0 + c];
+#pragma unroll
+                        for (int cp = 0; cp < c; cp++) v = fma(-y[cp], Cs[(b0 + c) * kCsLd + b0 + cp], v);
+                        y[c] = v;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < SB; c++)
+                    if ((uint32_t)c < bw) {
+                        Ys[tid * (SB + 1) + c] = y[c];
+                        Cs[i * kCsLd + b0 + c] = y[c] / Cs[(b0 + c) * kCsLd + b0 + c];
+                    }
+            }
+            __syncthreads();
+            // (3) trailing update: C[i][j] -= sum_c l_ic * y_jc for b1 <= j <= i < nc
+            {
+                const uint32_t i = b1 + (tid & 63);
+                if (i < nc) {
+                    double l[SB];
+#pragma unroll
+                    for (int c = 0; c < SB; c++) l[c] = (uint32_t)c < bw ? Cs[i * kCsLd + b0 + c] : 0.0;
+                    for (uint32_t j = b1 + (tid >> 6); j <= i; j += 4) {
+                        double v = Cs[i * kCsLd + j];
+                        const double* yj = Ys + (j - b1) * (SB + 1);
+#pragma unroll
+                        for (int c = 0; c < SB; c++)
+                            if ((uint32_t)c < bw) v = fma(-l[c], yj[c], v);
+                        Cs[i * kCsLd + j] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
-    // X = L^-1 by a right-looking sweep: row k of X is final after steps 0..k-1
-    for (uint32_t k = 0; k + 1 < nc; k++) {
-        const uint32_t i = k + 1 + ti;
-        if (i < nc) {
-            const double lik = Cs[i * kCsLd + k];
-            for (uint32_t c = jg; c <= k; c += 4) Xs[i * kCsLd + c] = fma(-lik, Xs[k * kCsLd + c], Xs[i * kCsLd + c]);
+    // ---- X = L^-1 (unit lower): diagonal 16x16 blocks by substitution, one thread per column
+    if (tid < nc) {
+        const uint32_t c = tid, bend = min(nc, (c / SB + 1) * SB);
+        for (uint32_t i = c + 1; i < bend; i++) {
+            double v = 0.0;
+            for (uint32_t k = c; k < i; k++) v = fma(-Cs[i * kCsLd + k], Xs[k * kCsLd + c], v);
+            Xs[i * kCsLd + c] = v;
+        }
+    }
+    __syncthreads();
+    // off-diagonal blocks, block row by block row: X_ij = -X_ii * (sum_{k=j..i-1} L_ik X_kj)
+    for (uint32_t bi = SB; bi < nc; bi += SB) {
+        const uint32_t bh = min((uint32_t)SB, nc - bi);
+        // T[r][c] for r in block row bi (bh rows), c in 0..bi: thread per entry
+        for (uint32_t e = tid; e < bh * bi; e += kTileThreads) {
+            const uint32_t r = e % bh, c = e / bh, i = bi + r;
+            double v = 0.0;
+            for (uint32_t k = c; k < bi; k++) v = fma(Cs[i * kCsLd + k], Xs[k * kCsLd + c], v);
+            Xs[i * kCsLd + c] = v;  // temporarily T, in place (rows bi.. of X are not read by this loop)
         }
         __syncthreads();
+        // X_ij = -X_ii T : column c of the block row, thread per entry, in place through registers
+        for (uint32_t e = tid; e < bh * bi; e += kTileThreads) {
+            const uint32_t r = e % bh, c = e / bh, i = bi + r;
+            double v = 0.0;
+            for (uint32_t k = 0; k <= r; k++) v = fma(-Xs[i * kCsLd + bi + k], Xs[(bi + k) * kCsLd + c], v);
+            Ys[e] = v;
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < bh * bi; e += kTileThreads) Xs[(bi + e % bh) * kCsLd + e / bh] = Ys[e];
+        __syncthreads();
     }
-    // write back: L below the diagonal, D on it; W[c][c'] = X[c][c'] / d_c (row-major, lower)
     double* W = D.winv + ((size_t)__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
     for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
         const uint32_t i = e & 63, j = e >> 6;  // i fastest: coalesced panel stores
         if (i < nc && j <= i) P[(size_t)(col0 + j) * f + col0 + i] = Cs[i * kCsLd + j];
-        const uint32_t c = e >> 6, cp = e & 63;  // W row-major
+        const uint32_t c = e >> 6, cp = e & 63;  // W row-major: W[c][cp] = X[c][cp] / d_c
         W[e] = (c < nc && cp <= c) ? Xs[c * kCsLd + cp] / Cs[c * kCsLd + c] : 0.0;
     }
 }
 
-// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): left-looking update, then
-// L = C * W^T with W = D^-1 L_kk^-1 of the diagonal tile.
+// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C * W^T with
+// W = D^-1 L_kk^-1 of the diagonal tile.
 __global__ void __launch_bounds__(kTileThreads)
 mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    TileBuf& buf = *reinterpret_cast<TileBuf*>(smraw);
-    double* Cs = reinterpret_cast<double*>(smraw + sizeof(TileBuf));  // [TB][kCsLd]
-    double* Wt = Cs + TB * kCsLd;                                      // [TB][kCsLd]: Wt[c'][c] = W[c][c']
+    extern __shared__ __align__(16) double smd_col[];
+    double* Cs = smd_col;             // [TB][kCsLd]
+    double* Wt = Cs + TB * kCsLd;     // [TB][kCsLd]: Wt[c'][c] = W[c][c']
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, row0 = t.y, col0 = t.z, nr = t.w & 0xFFFFu, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
     double* P = D.pan + __ldg(D.pan_off + s);
     const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
-    double acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            acc[i][j] = (r4 + i < nr && c4 + j < nc) ? P[(size_t)(col0 + c4 + j) * f + row0 + r4 + i] : 0.0;
     const double* W = D.winv + ((size_t)__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
-    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) Wt[(e & 63) * kCsLd + (e >> 6)] = W[e];
-    tile_kloop(acc, P, f, row0, nr, col0, nc, col0, buf);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) Cs[(r4 + i) * kCsLd + c4 + j] = acc[i][j];
+    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
+        const uint32_t i = e & 63, j = e >> 6;
+        Cs[i * kCsLd + j] = (i < nr && j < nc) ? P[(size_t)(col0 + j) * f + row0 + i] : 0.0;
+        Wt[(e & 63) * kCsLd + (e >> 6)] = W[e];
+    }
     __syncthreads();
     double out[4][4];
 #pragma unroll
@@ -296,32 +348,44 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
             if (r4 + i < nr && c4 + j < nc) P[(size_t)(col0 + c4 + j) * f + row0 + r4 + i] = out[i][j];
 }
 
-// Update tile of U_s: rows row0.., columns col0.. (front coordinates, both >= ns): U -= L D L^T over
-// all ns pivot columns.
+// Right-looking update with pivot block kb (columns pc0..pc0+K of the panel, K <= 64) of one
+// 64x64 tile to its lower right: target rows row0.., target columns tcol0.. (front coordinates);
+// the target lives in the panel when tcol0 < ns and in U_s otherwise.  t.w packs nrA | nrB << 8 |
+// K << 16 | (pc0 / 64) << 24.
 __global__ void __launch_bounds__(kTileThreads)
-mf_upd_kernel(MfDev D, const uint4* __restrict__ tasks) {
+mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
     __shared__ TileBuf buf;
     const uint4 t = __ldg(tasks + blockIdx.x);
-    const uint32_t s = t.x, row0 = t.y, col0 = t.z, nrA = t.w & 0xFFFFu, nrB = t.w >> 16;
+    const uint32_t s = t.x, row0 = t.y, tcol0 = t.z;
+    const uint32_t nrA = (t.w & 0xFFu) + 1, nrB = ((t.w >> 8) & 0xFFu) + 1, K = ((t.w >> 16) & 0xFFu) + 1, pc0 = (t.w >> 24) * TB;
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
-    const double* P = D.pan + __ldg(D.pan_off + s);
-    double* U = D.upd + __ldg(D.upd_off + s);
+    double* P = D.pan + __ldg(D.pan_off + s);
+    double* T;      // target tile base: element (i, j) at T[j * ld + i]
+    uint32_t ld;
+    if (tcol0 < ns) {
+        T = P + (size_t)tcol0 * f + row0;
+        ld = f;
+    } else {
+        T = D.upd + __ldg(D.upd_off + s) + (size_t)(tcol0 - ns) * r + (row0 - ns);
+        ld = r;
+    }
+    const bool diag_tile = row0 == tcol0;
     const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t gi = row0 + r4 + i, gj = col0 + c4 + j;
-            acc[i][j] = (r4 + i < nrA && c4 + j < nrB && gi >= gj) ? U[(size_t)(gj - ns) * r + (gi - ns)] : 0.0;
+            const bool ok = r4 + i < nrA && c4 + j < nrB && (!diag_tile || r4 + i >= c4 + j);
+            acc[i][j] = ok ? T[(size_t)(c4 + j) * ld + r4 + i] : 0.0;
         }
-    tile_kloop(acc, P, f, row0, nrA, col0, nrB, ns, buf);
+    tile_kloop(acc, P + (size_t)pc0 * f, f, row0, nrA, tcol0, nrB, K, pc0, buf);
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const uint32_t gi = row0 + r4 + i, gj = col0 + c4 + j;
-            if (r4 + i < nrA && c4 + j < nrB && gi >= gj) U[(size_t)(gj - ns) * r + (gi - ns)] = acc[i][j];
+            const bool ok = r4 + i < nrA && c4 + j < nrB && (!diag_tile || r4 + i >= c4 + j);
+            if (ok) T[(size_t)(c4 + j) * ld + r4 + i] = acc[i][j];
         }
 }
 
@@ -480,7 +544,8 @@ cudaError_t alloc_vec(T** out, size_t count, std::vector<void*>& owned) {
     return e;
 }
 
-constexpr size_t kDiagSmem = sizeof(TileBuf) + 2 * TB * kCsLd * sizeof(double);
+constexpr size_t kDiagSmem = (2 * TB * kCsLd + TB * (16 + 1)) * sizeof(double);
+constexpr size_t kColSmem = 2 * TB * kCsLd * sizeof(double);
 constexpr size_t kSmallFactorSmem = (size_t)kWarpsPerCta * kSmallFront * kSmallLd * sizeof(double);
 constexpr size_t kSmallSolveSmem = (size_t)kWarpsPerCta * (32 * 33 + kSmallFront) * sizeof(double);
 
@@ -532,6 +597,10 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         upd_off[s] = upd_total;
         upd_total += (uint64_t)(f[s] - ns[s]) * (f[s] - ns[s]);
         sparent[s] = t.parent[last] >= 0 ? (int32_t)col2sn[t.parent[last]] : -1;
+        if (ns[s] > 255u * TB) {
+            if (err) *err = "multifrontal: supernode wider than 16,320 columns";
+            return cudaErrorInvalidValue;
+        }
     }
     for (uint32_t j = 0; j < n; j++) flops_ += (uint64_t)(lc[j + 1] - lc[j]) * (lc[j + 1] - lc[j]);
     pan_total_ = pan_total;
@@ -642,14 +711,22 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         for (uint32_t s : L) {
             maxnsb = std::max(maxnsb, (ns[s] + TB - 1) / TB);
             const bool has_children = child_ptr[s + 1] > child_ptr[s];
-            for (uint32_t lo = 0; lo < f[s]; lo += TB) {
-                const uint32_t hi = std::min(f[s], lo + TB);
+            const uint32_t cbw = f[s] > 256 ? 8 : TB;  // big fronts: one warp per target column, many CTAs
+            for (uint32_t lo = 0; lo < f[s]; lo += cbw) {
+                const uint32_t hi = std::min(f[s], lo + cbw);
                 if (!has_children && hi <= ns[s]) continue;  // nothing to zero, nothing to add
                 push_task(s, lo, hi, 0);
             }
         }
         uint32_t count = (uint32_t)(tasks.size() / 4) - first;
         if (count) factor_seq_.push_back({0, first, count});
+        // blocks of a front after pivot block kb: later pivot blocks, then 64-row blocks of the update part
+        auto blocks_after = [&](uint32_t s, uint32_t kb, std::vector<std::pair<uint32_t, uint32_t>>& out) {
+            out.clear();
+            for (uint32_t r0 = (kb + 1) * TB; r0 < ns[s]; r0 += TB) out.push_back({r0, std::min<uint32_t>(TB, ns[s] - r0)});
+            for (uint32_t r0 = ns[s]; r0 < f[s]; r0 += TB) out.push_back({r0, std::min<uint32_t>(TB, f[s] - r0)});
+        };
+        std::vector<std::pair<uint32_t, uint32_t>> blk;
         for (uint32_t kb = 0; kb < maxnsb; kb++) {
             first = (uint32_t)(tasks.size() / 4);
             for (uint32_t s : L)
@@ -660,19 +737,24 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
             for (uint32_t s : L) {
                 if (kb * TB >= ns[s]) continue;
                 const uint32_t nc = std::min<uint32_t>(TB, ns[s] - kb * TB);
-                for (uint32_t row0 = kb * TB + nc; row0 < f[s]; row0 += TB)
-                    push_task(s, row0, kb * TB, std::min<uint32_t>(TB, f[s] - row0) | (nc << 16));
+                blocks_after(s, kb, blk);
+                for (auto& b : blk) push_task(s, b.first, kb * TB, b.second | (nc << 16));
             }
             count = (uint32_t)(tasks.size() / 4) - first;
             if (count) factor_seq_.push_back({2, first, count});
+            first = (uint32_t)(tasks.size() / 4);
+            for (uint32_t s : L) {
+                if (kb * TB >= ns[s]) continue;
+                const uint32_t nc = std::min<uint32_t>(TB, ns[s] - kb * TB);
+                blocks_after(s, kb, blk);
+                for (size_t bj = 0; bj < blk.size(); bj++)
+                    for (size_t bi = bj; bi < blk.size(); bi++)
+                        push_task(s, blk[bi].first, blk[bj].first,
+                                  (blk[bi].second - 1) | ((blk[bj].second - 1) << 8) | ((nc - 1) << 16) | (kb << 24));
+            }
+            count = (uint32_t)(tasks.size() / 4) - first;
+            if (count) factor_seq_.push_back({3, first, count});
         }
-        first = (uint32_t)(tasks.size() / 4);
-        for (uint32_t s : L)
-            for (uint32_t col0 = ns[s]; col0 < f[s]; col0 += TB)
-                for (uint32_t row0 = col0; row0 < f[s]; row0 += TB)
-                    push_task(s, row0, col0, std::min<uint32_t>(TB, f[s] - row0) | (std::min<uint32_t>(TB, f[s] - col0) << 16));
-        count = (uint32_t)(tasks.size() / 4) - first;
-        if (count) factor_seq_.push_back({3, first, count});
     }
     factor_launches_ = factor_seq_.size() + (nsub ? 1 : 0);
     stats.supernodes = S; stats.small_subtrees = nsub; stats.big = nbig; stats.levels = nlevels;
@@ -707,7 +789,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     MF_CU(alloc_vec(&dev_.status, 1, owned_));
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
     MF_CU(cudaFuncSetAttribute(mf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
-    MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
+    MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     const size_t big_solve_smem = (32 * 33 + (size_t)max_front) * sizeof(double);
@@ -730,8 +812,8 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
         switch (l.kind) {
             case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
             case 1: mf_diag_kernel<<<l.count, kTileThreads, kDiagSmem, st>>>(dev_, tk); break;
-            case 2: mf_col_kernel<<<l.count, kTileThreads, kDiagSmem, st>>>(dev_, tk); break;
-            default: mf_upd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
+            case 2: mf_col_kernel<<<l.count, kTileThreads, kColSmem, st>>>(dev_, tk); break;
+            default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
         }
     }
     return cudaGetLastError();
