@@ -20,11 +20,21 @@ constexpr int kWarpsPerCta = 8;
 constexpr int TB = 64;            // tile order of the big path
 constexpr int KC = 16;            // pivot columns staged per step of the micro-kernel
 constexpr int kTileThreads = 256;
-constexpr int kCsLd = TB + 1;
 
 __device__ __forceinline__ void flag_pivot(int* status, double d) {
     if (d != d) atomicMax(status, 2);
     else if (!(d > 0.0) || d == INFINITY) atomicMax(status, 1);
+}
+
+// 1/d: hardware seed + two Newton steps (relative error ~1e-16, no slow path, no branches).
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
 }
 
 // ---- small subtrees: one warp per subtree, supernodes in ascending (= topological) order ---------------
@@ -179,173 +189,90 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
     __syncthreads();
 }
 
-// Diagonal tile (pivot block at col0, nc <= 64 columns) of supernode s: LDLt of the tile in shared
-// memory, blocked by 16 columns (diagonal 16x16 block by half a warp, panel rows by substitution,
-// trailing update by all threads: three barriers per 16 columns), then W = D^-1 L^-1 of the tile
-// (block recurrence) for the panel kernel and the triangular solves.  Right-looking: the tile has
-// already received the updates of all earlier pivot blocks (mf_rupd_kernel).
-constexpr int SB = 16;
-__global__ void __launch_bounds__(kTileThreads)
+// Diagonal tile (pivot block at col0, nc <= 64 columns) of supernode s, right-looking (the tile has
+// already received the updates of all earlier pivot blocks).  One CTA of 64 threads: thread i keeps
+// ROW i of the tile in registers (fully unrolled), column k is broadcast through a double-buffered
+// shared-memory vector, one barrier per column.  The dependent chain per column is
+// LDS -> reciprocal -> multiply -> fma (about 125 cycles), the rank-1 updates are register FMAs.
+// Output: L (unit lower) with D on the diagonal, in place in the panel.
+constexpr int kDiagThreads = 64;
+
+template <int NC>
+__device__ __forceinline__ void diag_body(double* __restrict__ T, uint32_t f, uint32_t nc, int* status, double (*colbuf)[TB]) {
+    const uint32_t i = threadIdx.x;
+    double r[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+        r[j] = (i < nc && (uint32_t)j <= i && (uint32_t)j < nc) ? T[(size_t)j * f + i] : ((uint32_t)j == i ? 1.0 : 0.0);
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        if ((uint32_t)k >= nc) break;
+        colbuf[k & 1][i] = r[k];
+        __syncthreads();
+        const double d = colbuf[k & 1][k];
+        if (i == 0) flag_pivot(status, d);
+        const double li = r[k] * fast_rcp(d);
+#pragma unroll
+        for (int j = k + 1; j < NC; j++) r[j] = fma(-li, colbuf[k & 1][j], r[j]);  // rows below j only matter
+        if (i > (uint32_t)k) r[k] = li;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+        if (i < nc && (uint32_t)j <= i && (uint32_t)j < nc) T[(size_t)j * f + i] = r[j];
+}
+
+__global__ void __launch_bounds__(kDiagThreads)
 mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    extern __shared__ __align__(16) double smd_diag[];
-    double* Cs = smd_diag;            // [TB][kCsLd] tile, lower; becomes L (unit lower), D on the diagonal
-    double* Xs = Cs + TB * kCsLd;     // [TB][kCsLd] L^-1
-    double* Ys = Xs + TB * kCsLd;     // [TB][SB+1] unscaled panel rows of the current 16-column step / scratch
+    __shared__ double colbuf[2][TB];
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
-    double* P = D.pan + __ldg(D.pan_off + s);
-    const uint32_t tid = threadIdx.x;
-    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
-        const uint32_t i = e & 63, j = e >> 6;
-        Cs[i * kCsLd + j] = (i < nc && j <= i) ? P[(size_t)(col0 + j) * f + col0 + i] : 0.0;
-        Xs[i * kCsLd + j] = i == j ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    for (uint32_t b0 = 0; b0 < nc; b0 += SB) {
-        const uint32_t bw = min((uint32_t)SB, nc - b0), b1 = b0 + bw;
-        if (tid < 32) {  // (1) diagonal block, rows on lanes 0..bw-1
-            const uint32_t i = b0 + tid;
-            for (uint32_t k = b0; k < b1; k++) {
-                const double d = Cs[k * kCsLd + k];
-                if (tid == 0) flag_pivot(D.status, d);
-                const double inv = 1.0 / d;
-                double li = 0.0;
-                if (i > k && i < b1) {
-                    li = Cs[i * kCsLd + k] * inv;
-                    for (uint32_t j = k + 1; j <= i; j++) Cs[i * kCsLd + j] = fma(-li, Cs[j * kCsLd + k], Cs[i * kCsLd + j]);
-                }
-                __syncwarp();
-                if (i > k && i < b1) Cs[i * kCsLd + k] = li;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        if (b1 < nc) {
-            // (2) rows below: y = C[i, b0..b1) L_bb^-T (unscaled, kept in Ys), l = y / d
-            if (tid < nc - b1) {
-                const uint32_t i = b1 + tid;
-                double y[SB];
-#pragma unroll
-                for (int c = 0; c < SB; c++) {
-                    y[c] = 0.0;
-                    if ((uint32_t)c < bw) {
-                        double v = Cs[i * kCsLd + b0 + c];
-#pragma unroll
-                        for (int cp = 0; cp < c; cp++) v = fma(-y[cp], Cs[(b0 + c) * kCsLd + b0 + cp], v);
-                        y[c] = v;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < SB; c++)
-                    if ((uint32_t)c < bw) {
-                        Ys[tid * (SB + 1) + c] = y[c];
-                        Cs[i * kCsLd + b0 + c] = y[c] / Cs[(b0 + c) * kCsLd + b0 + c];
-                    }
-            }
-            __syncthreads();
-            // (3) trailing update: C[i][j] -= sum_c l_ic * y_jc for b1 <= j <= i < nc
-            {
-                const uint32_t i = b1 + (tid & 63);
-                if (i < nc) {
-                    double l[SB];
-#pragma unroll
-                    for (int c = 0; c < SB; c++) l[c] = (uint32_t)c < bw ? Cs[i * kCsLd + b0 + c] : 0.0;
-                    for (uint32_t j = b1 + (tid >> 6); j <= i; j += 4) {
-                        double v = Cs[i * kCsLd + j];
-                        const double* yj = Ys + (j - b1) * (SB + 1);
-#pragma unroll
-                        for (int c = 0; c < SB; c++)
-                            if ((uint32_t)c < bw) v = fma(-l[c], yj[c], v);
-                        Cs[i * kCsLd + j] = v;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    // ---- X = L^-1 (unit lower): diagonal 16x16 blocks by substitution, one thread per column
-    if (tid < nc) {
-        const uint32_t c = tid, bend = min(nc, (c / SB + 1) * SB);
-        for (uint32_t i = c + 1; i < bend; i++) {
-            double v = 0.0;
-            for (uint32_t k = c; k < i; k++) v = fma(-Cs[i * kCsLd + k], Xs[k * kCsLd + c], v);
-            Xs[i * kCsLd + c] = v;
-        }
-    }
-    __syncthreads();
-    // off-diagonal blocks, block row by block row: X_ij = -X_ii * (sum_{k=j..i-1} L_ik X_kj)
-    for (uint32_t bi = SB; bi < nc; bi += SB) {
-        const uint32_t bh = min((uint32_t)SB, nc - bi);
-        // T[r][c] for r in block row bi (bh rows), c in 0..bi: thread per entry
-        for (uint32_t e = tid; e < bh * bi; e += kTileThreads) {
-            const uint32_t r = e % bh, c = e / bh, i = bi + r;
-            double v = 0.0;
-            for (uint32_t k = c; k < bi; k++) v = fma(Cs[i * kCsLd + k], Xs[k * kCsLd + c], v);
-            Xs[i * kCsLd + c] = v;  // temporarily T, in place (rows bi.. of X are not read by this loop)
-        }
-        __syncthreads();
-        // X_ij = -X_ii T : column c of the block row, thread per entry, in place through registers
-        for (uint32_t e = tid; e < bh * bi; e += kTileThreads) {
-            const uint32_t r = e % bh, c = e / bh, i = bi + r;
-            double v = 0.0;
-            for (uint32_t k = 0; k <= r; k++) v = fma(-Xs[i * kCsLd + bi + k], Xs[(bi + k) * kCsLd + c], v);
-            Ys[e] = v;
-        }
-        __syncthreads();
-        for (uint32_t e = tid; e < bh * bi; e += kTileThreads) Xs[(bi + e % bh) * kCsLd + e / bh] = Ys[e];
-        __syncthreads();
-    }
-    double* W = D.winv + ((size_t)__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
-    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
-        const uint32_t i = e & 63, j = e >> 6;  // i fastest: coalesced panel stores
-        if (i < nc && j <= i) P[(size_t)(col0 + j) * f + col0 + i] = Cs[i * kCsLd + j];
-        const uint32_t c = e >> 6, cp = e & 63;  // W row-major: W[c][cp] = X[c][cp] / d_c
-        W[e] = (c < nc && cp <= c) ? Xs[c * kCsLd + cp] / Cs[c * kCsLd + c] : 0.0;
-    }
+    double* T = D.pan + __ldg(D.pan_off + s) + (size_t)col0 * f + col0;
+    if (nc <= 8) diag_body<8>(T, f, nc, D.status, colbuf);
+    else if (nc <= 16) diag_body<16>(T, f, nc, D.status, colbuf);
+    else if (nc <= 32) diag_body<32>(T, f, nc, D.status, colbuf);
+    else diag_body<64>(T, f, nc, D.status, colbuf);
 }
 
-// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C * W^T with
-// W = D^-1 L_kk^-1 of the diagonal tile.
-__global__ void __launch_bounds__(kTileThreads)
+// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C L_kk^-T D^-1 by forward
+// substitution, thread i keeps row i of the tile in registers; the entries of L_kk are warp-uniform
+// loads (the 32 KB diagonal tile stays in L1).
+template <int NC>
+__device__ __forceinline__ void col_body(double* __restrict__ C, const double* __restrict__ Lkk, uint32_t f, uint32_t nr, uint32_t nc,
+                                         const double* invd) {
+    const uint32_t i = threadIdx.x;
+    double r[NC];
+#pragma unroll
+    for (int j = 0; j < NC; j++) r[j] = (i < nr && (uint32_t)j < nc) ? C[(size_t)j * f + i] : 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        if ((uint32_t)c >= nc) break;
+        const double y = r[c];
+        const double* Lc = Lkk + (size_t)c * f;  // column c of L_kk: Lc[c'] = L_kk[c'][c]
+#pragma unroll
+        for (int cp = c + 1; cp < NC; cp++)
+            if ((uint32_t)cp < nc) r[cp] = fma(-y, __ldg(Lc + cp), r[cp]);
+    }
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+        if (i < nr && (uint32_t)j < nc) C[(size_t)j * f + i] = r[j] * invd[j];
+}
+
+__global__ void __launch_bounds__(kDiagThreads)
 mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    extern __shared__ __align__(16) double smd_col[];
-    double* Cs = smd_col;             // [TB][kCsLd]
-    double* Wt = Cs + TB * kCsLd;     // [TB][kCsLd]: Wt[c'][c] = W[c][c']
+    __shared__ double invd[TB];
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, row0 = t.y, col0 = t.z, nr = t.w & 0xFFFFu, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
     double* P = D.pan + __ldg(D.pan_off + s);
-    const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
-    const double* W = D.winv + ((size_t)__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
-    for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
-        const uint32_t i = e & 63, j = e >> 6;
-        Cs[i * kCsLd + j] = (i < nr && j < nc) ? P[(size_t)(col0 + j) * f + row0 + i] : 0.0;
-        Wt[(e & 63) * kCsLd + (e >> 6)] = W[e];
-    }
+    const double* Lkk = P + (size_t)col0 * f + col0;
+    double* C = P + (size_t)col0 * f + row0;
+    if (threadIdx.x < nc) invd[threadIdx.x] = fast_rcp(Lkk[(size_t)threadIdx.x * f + threadIdx.x]);
     __syncthreads();
-    double out[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) out[i][j] = 0.0;
-    for (uint32_t cp = 0; cp < nc; cp++) {
-        double a[4], w[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            a[u] = Cs[(r4 + u) * kCsLd + cp];
-            w[u] = Wt[cp * kCsLd + c4 + u];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) out[i][j] = fma(a[i], w[j], out[i][j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (r4 + i < nr && c4 + j < nc) P[(size_t)(col0 + c4 + j) * f + row0 + r4 + i] = out[i][j];
+    if (nc <= 8) col_body<8>(C, Lkk, f, nr, nc, invd);
+    else if (nc <= 16) col_body<16>(C, Lkk, f, nr, nc, invd);
+    else if (nc <= 32) col_body<32>(C, Lkk, f, nr, nc, invd);
+    else col_body<64>(C, Lkk, f, nr, nc, invd);
 }
 
 // Right-looking update with pivot block kb (columns pc0..pc0+K of the panel, K <= 64) of one
@@ -402,7 +329,7 @@ __device__ __forceinline__ void group_sync() {
 
 template <int G>
 __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, double* __restrict__ w, double* t, double* tri,
-                                                  uint32_t gt) {
+                                                  uint32_t gt, bool split = false) {
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
     const double* P = D.pan + __ldg(D.pan_off + s);
     for (uint32_t i = gt; i < f; i += G) t[i] = i < ns ? w[c0 + i] : 0.0;
@@ -413,6 +340,7 @@ __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, do
         for (uint32_t a = gt; a < rc; a += G) t[__ldg(D.rel + ro + a)] += D.ubuf[ro + a];
         group_sync<G>();
     }
+    const uint32_t rlim = split ? ns : f;  // split: the rows below the pivot block are updated by mf_fwd_upd_kernel
     for (uint32_t k0 = 0; k0 < ns; k0 += 32) {
         const uint32_t nb = min(32u, ns - k0);
         // stage the nb x nb unit-lower triangle: tri[i][k]
@@ -431,8 +359,9 @@ __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, do
         }
         group_sync<G>();
         // rows below the block: t[i] -= L[i, block] . y[block]
-        for (uint32_t i = k0 + nb + gt; i < f; i += G) {
+        for (uint32_t i = k0 + nb + gt; i < rlim; i += G) {
             double acc = 0.0;
+#pragma unroll 8
             for (uint32_t k = 0; k < nb; k++) acc = fma(P[(size_t)(k0 + k) * f + i], t[k0 + k], acc);
             t[i] -= acc;
         }
@@ -448,12 +377,18 @@ __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, do
 
 template <int G>
 __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, double* __restrict__ w, double* __restrict__ delta,
-                                                   const int32_t* __restrict__ perm, double* t, double* tri, uint32_t gt) {
+                                                   const int32_t* __restrict__ perm, double* t, double* tri, uint32_t gt,
+                                                   bool split = false, const double* __restrict__ tmp = nullptr) {
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
     const double* P = D.pan + __ldg(D.pan_off + s);
     const uint32_t* rows = D.rows + __ldg(D.rows_off + s);
-    // t[i >= ns] = z of the ancestors; t[i < ns] = y_i / d_i
-    for (uint32_t i = gt; i < f; i += G) t[i] = i < ns ? w[c0 + i] / P[(size_t)i * f + i] : w[__ldg(rows + i)];
+    // t[i >= ns] = z of the ancestors; t[i < ns] = y_i / d_i  (split: the ancestors' part was
+    // already reduced into tmp by mf_bwd_dot_kernel)
+    const uint32_t rlim = split ? ns : f;
+    for (uint32_t i = gt; i < rlim; i += G) {
+        if (i < ns) t[i] = w[c0 + i] / P[(size_t)i * f + i] - (split ? tmp[c0 + i] : 0.0);
+        else t[i] = w[__ldg(rows + i)];
+    }
     group_sync<G>();
     const uint32_t nblk = (ns + 31) / 32;
     for (uint32_t bi = nblk; bi-- > 0;) {
@@ -464,7 +399,7 @@ __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, d
             for (uint32_t k = wp; k < nb; k += G / 32) {
                 const double* col = P + (size_t)(k0 + k) * f;
                 double acc = 0.0;
-                for (uint32_t i = k0 + nb + ln; i < f; i += 32) acc = fma(col[i], t[i], acc);
+                for (uint32_t i = k0 + nb + ln; i < rlim; i += 32) acc = fma(col[i], t[i], acc);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
                 if (ln == 0) t[k0 + k] -= acc;
@@ -511,16 +446,75 @@ mf_small_solve_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint3
     }
 }
 
+// Supernodes whose panel below the pivot block is large are "split": the pivot-block part runs in
+// mf_big_solve_kernel (one CTA), the (f - ns) x ns rectangle in the two kernels below on many CTAs.
+constexpr uint32_t kSplitEntries = 16384;
+__device__ __forceinline__ bool is_split(uint32_t f, uint32_t ns) { return (f - ns) * ns > kSplitEntries; }
+
 template <bool FORWARD>
 __global__ void __launch_bounds__(256)
 mf_big_solve_kernel(MfDev D, const uint32_t* __restrict__ list, double* __restrict__ w, double* __restrict__ delta,
-                    const int32_t* __restrict__ perm) {
+                    const int32_t* __restrict__ perm, const double* __restrict__ tmp) {
     extern __shared__ double smd[];
     double* tri = smd;            // [32*33]
     double* t = smd + 32 * 33;    // [max front]
     const uint32_t s = __ldg(list + blockIdx.x);
-    if (FORWARD) forward_supernode<256>(D, s, w, t, tri, threadIdx.x);
-    else backward_supernode<256>(D, s, w, delta, perm, t, tri, threadIdx.x);
+    const bool split = is_split(__ldg(D.f + s), __ldg(D.ns + s));
+    if (FORWARD) forward_supernode<256>(D, s, w, t, tri, threadIdx.x, split);
+    else backward_supernode<256>(D, s, w, delta, perm, t, tri, threadIdx.x, split, tmp);
+}
+
+// Forward, split supernodes: u_s[r0 .. r0+64) -= L21[rows, :] y_s.  256 threads = 64 rows x 4
+// interleaved column quarters; the quarters are summed in fixed order.
+__global__ void __launch_bounds__(256)
+mf_fwd_upd_kernel(MfDev D, const uint4* __restrict__ tasks, const double* __restrict__ w) {
+    extern __shared__ double smd[];
+    __shared__ double part[4][64];
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, r0 = t.y, nrows = t.z;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    double* ys = smd;
+    for (uint32_t k = threadIdx.x; k < ns; k += 256) ys[k] = w[c0 + k];
+    __syncthreads();
+    const uint32_t row = threadIdx.x & 63, q = threadIdx.x >> 6;
+    double acc = 0.0;
+    if (row < nrows) {
+        const double* base = P + ns + r0 + row;
+#pragma unroll 8
+        for (uint32_t k = q; k < ns; k += 4) acc = fma(base[(size_t)k * f], ys[k], acc);
+    }
+    part[q][row] = acc;
+    __syncthreads();
+    if (q == 0 && row < nrows) {
+        double* u = D.ubuf + __ldg(D.rel_off + s) + r0 + row;
+        *u -= ((part[0][row] + part[1][row]) + part[2][row]) + part[3][row];
+    }
+}
+
+// Backward, split supernodes: tmp[c0 + j] = sum_{i >= ns} L[i][j] z[rows[i]] for 32 pivot columns per
+// CTA, one warp per column at a time.
+__global__ void __launch_bounds__(256)
+mf_bwd_dot_kernel(MfDev D, const uint4* __restrict__ tasks, const double* __restrict__ w, double* __restrict__ tmp) {
+    extern __shared__ double smd[];
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, j0 = t.y, ncols = t.z;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s), r = f - ns;
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    const uint32_t* rows = D.rows + __ldg(D.rows_off + s) + ns;
+    double* zt = smd;
+    for (uint32_t a = threadIdx.x; a < r; a += 256) zt[a] = w[__ldg(rows + a)];
+    __syncthreads();
+    const uint32_t wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (uint32_t jj = wp; jj < ncols; jj += 8) {
+        const double* col = P + (size_t)(j0 + jj) * f + ns;
+        double acc = 0.0;
+#pragma unroll 4
+        for (uint32_t a = ln; a < r; a += 32) acc = fma(col[a], zt[a], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if (ln == 0) tmp[c0 + j0 + jj] = acc;
+    }
 }
 
 template <class T>
@@ -544,8 +538,6 @@ cudaError_t alloc_vec(T** out, size_t count, std::vector<void*>& owned) {
     return e;
 }
 
-constexpr size_t kDiagSmem = (2 * TB * kCsLd + TB * (16 + 1)) * sizeof(double);
-constexpr size_t kColSmem = 2 * TB * kCsLd * sizeof(double);
 constexpr size_t kSmallFactorSmem = (size_t)kWarpsPerCta * kSmallFront * kSmallLd * sizeof(double);
 constexpr size_t kSmallSolveSmem = (size_t)kWarpsPerCta * (32 * 33 + kSmallFront) * sizeof(double);
 
@@ -701,12 +693,26 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         tasks.push_back(a); tasks.push_back(b); tasks.push_back(c); tasks.push_back(d);
     };
     factor_seq_.clear();
+    fwd_tasks_.clear();
+    bwd_tasks_.clear();
     level_ptr_.assign(1, 0);
     std::vector<uint32_t> level_list;
     for (uint32_t l = 0; l < nlevels; l++) {
         const std::vector<uint32_t>& L = by_level[l];
         for (uint32_t s : L) level_list.push_back(s);
         level_ptr_.push_back((uint32_t)level_list.size());
+        {   // solve tasks of the split supernodes of this level
+            uint32_t first = (uint32_t)(tasks.size() / 4);
+            for (uint32_t s : L)
+                if ((uint64_t)(f[s] - ns[s]) * ns[s] > kSplitEntries)
+                    for (uint32_t r0 = 0; r0 < f[s] - ns[s]; r0 += 64) push_task(s, r0, std::min<uint32_t>(64, f[s] - ns[s] - r0), 0);
+            fwd_tasks_.push_back({first, (uint32_t)(tasks.size() / 4) - first});
+            first = (uint32_t)(tasks.size() / 4);
+            for (uint32_t s : L)
+                if ((uint64_t)(f[s] - ns[s]) * ns[s] > kSplitEntries)
+                    for (uint32_t j0 = 0; j0 < ns[s]; j0 += 32) push_task(s, j0, std::min<uint32_t>(32, ns[s] - j0), 0);
+            bwd_tasks_.push_back({first, (uint32_t)(tasks.size() / 4) - first});
+        }
         uint32_t first = (uint32_t)(tasks.size() / 4), maxnsb = 0;
         for (uint32_t s : L) {
             maxnsb = std::max(maxnsb, (ns[s] + TB - 1) / TB);
@@ -784,12 +790,11 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     }
     MF_CU(alloc_vec(&dev_.pan, pan_total, owned_));
     MF_CU(alloc_vec(&dev_.upd, upd_total, owned_));
-    MF_CU(alloc_vec(&dev_.winv, (size_t)winv_blocks * TB * TB, owned_));
+    MF_CU(alloc_vec(&dev_.winv, 1, owned_));  // (inverse blocks are no longer used)
     MF_CU(alloc_vec(&dev_.ubuf, rel_off[S], owned_));
     MF_CU(alloc_vec(&dev_.status, 1, owned_));
+    MF_CU(alloc_vec(&d_tmp_, n, owned_));
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
-    MF_CU(cudaFuncSetAttribute(mf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
-    MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     const size_t big_solve_smem = (32 * 33 + (size_t)max_front) * sizeof(double);
@@ -799,6 +804,8 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     }
     MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
     MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_fwd_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_bwd_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
     return cudaSuccess;
 }
 
@@ -811,8 +818,8 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
         const uint4* tk = d_tasks_ + l.first;
         switch (l.kind) {
             case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
-            case 1: mf_diag_kernel<<<l.count, kTileThreads, kDiagSmem, st>>>(dev_, tk); break;
-            case 2: mf_col_kernel<<<l.count, kTileThreads, kColSmem, st>>>(dev_, tk); break;
+            case 1: mf_diag_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
+            case 2: mf_col_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
             default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
         }
     }
@@ -822,12 +829,17 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
 cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t st) {
     const uint32_t sgrid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t smem = (32 * 33 + (size_t)stats.max_front) * sizeof(double);
+    const size_t vsmem = (size_t)stats.max_front * sizeof(double);
     const uint32_t nlevels = (uint32_t)level_ptr_.size() - 1;
     if (nsub_) mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
-    for (uint32_t l = 0; l < nlevels; l++)
-        mf_big_solve_kernel<true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm);
-    for (uint32_t l = nlevels; l-- > 0;)
-        mf_big_solve_kernel<false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm);
+    for (uint32_t l = 0; l < nlevels; l++) {
+        mf_big_solve_kernel<true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_);
+        if (fwd_tasks_[l].second) mf_fwd_upd_kernel<<<fwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + fwd_tasks_[l].first, w);
+    }
+    for (uint32_t l = nlevels; l-- > 0;) {
+        if (bwd_tasks_[l].second) mf_bwd_dot_kernel<<<bwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + bwd_tasks_[l].first, w, d_tmp_);
+        mf_big_solve_kernel<false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_);
+    }
     if (nsub_) mf_small_solve_kernel<false><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -87,6 +88,8 @@ private:
     // big supernodes by level (solve kernels)
     const uint32_t* d_level_list_ = nullptr;
     std::vector<uint32_t> level_ptr_;
+    std::vector<std::pair<uint32_t, uint32_t>> fwd_tasks_, bwd_tasks_;  // per level: {first task, count}
+    double* d_tmp_ = nullptr;
     cudaGraphExec_t factor_graph_ = nullptr, solve_graph_ = nullptr;
     double* solve_w_ = nullptr; double* solve_delta_ = nullptr; const int32_t* solve_perm_ = nullptr;
     cudaError_t enqueue_factor(cudaStream_t stream);
