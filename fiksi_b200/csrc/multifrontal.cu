@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -190,76 +191,56 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
 }
 
 // Diagonal tile (pivot block at col0, nc <= 64 columns) of supernode s, right-looking (the tile has
-// already received the updates of all earlier pivot blocks).  One CTA of 64 threads: thread i keeps
-// ROW i of the tile in registers (fully unrolled), column k is broadcast through a double-buffered
-// shared-memory vector, one barrier per column.  The dependent chain per column is
-// LDS -> reciprocal -> multiply -> fma (about 125 cycles), the rank-1 updates are register FMAs.
-// Output: L (unit lower) with D on the diagonal, in place in the panel.
-constexpr int kDiagThreads = 64;
-
-template <int NC>
-__device__ __forceinline__ void diag_body(double* __restrict__ T, uint32_t f, uint32_t nc, int* status, double (*colbuf)[TB]) {
-    const uint32_t i = threadIdx.x;
-    double r[NC];
-#pragma unroll
-    for (int j = 0; j < NC; j++)
-        r[j] = (i < nc && (uint32_t)j <= i && (uint32_t)j < nc) ? T[(size_t)j * f + i] : ((uint32_t)j == i ? 1.0 : 0.0);
-#pragma unroll
-    for (int k = 0; k < NC; k++) {
-        if ((uint32_t)k >= nc) break;
-        colbuf[k & 1][i] = r[k];
-        __syncthreads();
-        const double d = colbuf[k & 1][k];
-        if (i == 0) flag_pivot(status, d);
-        const double li = r[k] * fast_rcp(d);
-#pragma unroll
-        for (int j = k + 1; j < NC; j++) r[j] = fma(-li, colbuf[k & 1][j], r[j]);  // rows below j only matter
-        if (i > (uint32_t)k) r[k] = li;
-    }
-#pragma unroll
-    for (int j = 0; j < NC; j++)
-        if (i < nc && (uint32_t)j <= i && (uint32_t)j < nc) T[(size_t)j * f + i] = r[j];
-}
+// already received the updates of all earlier pivot blocks).  The tile lives in shared memory with
+// UNSCALED columns; 128 threads = 64 rows x 2 interleaved column halves.  One barrier per column: after
+// it every thread reads the pivot, forms its multiplier l_ik = c_ik / d_k, streams it to the panel
+// (coalesced) and applies the rank-1 update to its half of row i.  Small rolled loops on purpose: a
+// fully unrolled register version is an order of magnitude slower here because every instruction is
+// executed once and the kernel becomes instruction-fetch bound.
+constexpr int kDiagThreads = 128;
+constexpr int kTsLd = TB + 1;
 
 __global__ void __launch_bounds__(kDiagThreads)
 mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    __shared__ double colbuf[2][TB];
+    __shared__ double Cs[TB * kTsLd];
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
     double* T = D.pan + __ldg(D.pan_off + s) + (size_t)col0 * f + col0;
-    if (nc <= 8) diag_body<8>(T, f, nc, D.status, colbuf);
-    else if (nc <= 16) diag_body<16>(T, f, nc, D.status, colbuf);
-    else if (nc <= 32) diag_body<32>(T, f, nc, D.status, colbuf);
-    else diag_body<64>(T, f, nc, D.status, colbuf);
+    const uint32_t tid = threadIdx.x, i = tid & 63, h = tid >> 6;
+    for (uint32_t e = tid; e < nc * TB; e += kDiagThreads) {
+        const uint32_t ii = e & 63, j = e >> 6;
+        if (ii < nc && j <= ii) Cs[ii * kTsLd + j] = T[(size_t)j * f + ii];
+    }
+    for (uint32_t k = 0; k < nc; k++) {
+        __syncthreads();
+        const double d = Cs[k * kTsLd + k];
+        if (tid == 0) {
+            flag_pivot(D.status, d);
+            T[(size_t)k * f + k] = d;
+        }
+        if (i > k && i < nc) {
+            const double li = Cs[i * kTsLd + k] * fast_rcp(d);
+            if (h == 0) T[(size_t)k * f + i] = li;
+            double* row = Cs + i * kTsLd;
+            const double* colk = Cs + k;
+#pragma unroll 4
+            for (uint32_t j = k + 1 + h; j <= i; j += 2) row[j] = fma(-li, colk[j * kTsLd], row[j]);
+        }
+    }
 }
 
 // Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C L_kk^-T D^-1 by forward
-// substitution, thread i keeps row i of the tile in registers; the entries of L_kk are warp-uniform
-// loads (the 32 KB diagonal tile stays in L1).
-template <int NC>
-__device__ __forceinline__ void col_body(double* __restrict__ C, const double* __restrict__ Lkk, uint32_t f, uint32_t nr, uint32_t nc,
-                                         const double* invd) {
-    const uint32_t i = threadIdx.x;
-    double r[NC];
-#pragma unroll
-    for (int j = 0; j < NC; j++) r[j] = (i < nr && (uint32_t)j < nc) ? C[(size_t)j * f + i] : 0.0;
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-        if ((uint32_t)c >= nc) break;
-        const double y = r[c];
-        const double* Lc = Lkk + (size_t)c * f;  // column c of L_kk: Lc[c'] = L_kk[c'][c]
-#pragma unroll
-        for (int cp = c + 1; cp < NC; cp++)
-            if ((uint32_t)cp < nc) r[cp] = fma(-y, __ldg(Lc + cp), r[cp]);
-    }
-#pragma unroll
-    for (int j = 0; j < NC; j++)
-        if (i < nr && (uint32_t)j < nc) C[(size_t)j * f + i] = r[j] * invd[j];
-}
-
-__global__ void __launch_bounds__(kDiagThreads)
+// substitution in shared memory.  256 threads = 64 rows x 4 interleaved column quarters; the four
+// threads of a row sit in one warp (lanes 4i..4i+3 hold row 8w+i), so a __syncwarp per column is the
+// only synchronisation.
+constexpr int kColThreads = 256;
+constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (row, quarter) hit distinct banks
+__global__ void __launch_bounds__(kColThreads)
 mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    extern __shared__ __align__(16) double smd_col[];
+    double* Cs = smd_col;            // [TB][kYsLd] rows of the tile (Y, unscaled)
+    double* Ls = Cs + TB * kYsLd;    // [TB][kTsLd] L_kk (unit lower), D on the diagonal
     __shared__ double invd[TB];
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, row0 = t.y, col0 = t.z, nr = t.w & 0xFFFFu, nc = t.w >> 16;
@@ -267,12 +248,30 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
     double* P = D.pan + __ldg(D.pan_off + s);
     const double* Lkk = P + (size_t)col0 * f + col0;
     double* C = P + (size_t)col0 * f + row0;
-    if (threadIdx.x < nc) invd[threadIdx.x] = fast_rcp(Lkk[(size_t)threadIdx.x * f + threadIdx.x]);
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t e = tid; e < nc * TB; e += kColThreads) {
+        const uint32_t ii = e & 63, j = e >> 6;
+        Cs[ii * kYsLd + j] = ii < nr ? C[(size_t)j * f + ii] : 0.0;
+        if (ii < nc && j <= ii) Ls[ii * kTsLd + j] = Lkk[(size_t)j * f + ii];
+    }
+    if (tid < nc) invd[tid] = fast_rcp(Lkk[(size_t)tid * f + tid]);
     __syncthreads();
-    if (nc <= 8) col_body<8>(C, Lkk, f, nr, nc, invd);
-    else if (nc <= 16) col_body<16>(C, Lkk, f, nr, nc, invd);
-    else if (nc <= 32) col_body<32>(C, Lkk, f, nr, nc, invd);
-    else col_body<64>(C, Lkk, f, nr, nc, invd);
+    {
+        const uint32_t i = tid >> 2, q = tid & 3;
+        double* row = Cs + i * kYsLd;
+        for (uint32_t c = 0; c + 1 < nc; c++) {
+            const double y = row[c];
+            const double* Lc = Ls + c;  // L_kk[cp][c] = Lc[cp * kTsLd]
+#pragma unroll 4
+            for (uint32_t cp = c + 1 + q; cp < nc; cp += 4) row[cp] = fma(-y, Lc[cp * kTsLd], row[cp]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < nc * TB; e += kColThreads) {
+        const uint32_t ii = e & 63, j = e >> 6;
+        if (ii < nr) C[(size_t)j * f + ii] = Cs[ii * kYsLd + j] * invd[j];
+    }
 }
 
 // Right-looking update with pivot block kb (columns pc0..pc0+K of the panel, K <= 64) of one
@@ -538,6 +537,7 @@ cudaError_t alloc_vec(T** out, size_t count, std::vector<void*>& owned) {
     return e;
 }
 
+constexpr size_t kColSmem = (TB * kYsLd + TB * kTsLd) * sizeof(double);
 constexpr size_t kSmallFactorSmem = (size_t)kWarpsPerCta * kSmallFront * kSmallLd * sizeof(double);
 constexpr size_t kSmallSolveSmem = (size_t)kWarpsPerCta * (32 * 33 + kSmallFront) * sizeof(double);
 
@@ -795,6 +795,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     MF_CU(alloc_vec(&dev_.status, 1, owned_));
     MF_CU(alloc_vec(&d_tmp_, n, owned_));
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
+    MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     const size_t big_solve_smem = (32 * 33 + (size_t)max_front) * sizeof(double);
@@ -810,18 +811,43 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
 }
 
 cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
+    // FK_MF_TIMING=1 (debug, implies no graph): CUDA events around every launch, per-kind sums to stderr
+    static const bool timing = std::getenv("FK_MF_TIMING") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float sums[5] = {0, 0, 0, 0, 0}, maxs[5] = {0, 0, 0, 0, 0};
+    if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    auto timed = [&](int kind, auto&& launch) {
+        if (timing) cudaEventRecord(e0, st);
+        launch();
+        if (timing) {
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            sums[kind] += ms;
+            maxs[kind] = std::max(maxs[kind], ms);
+        }
+    };
     if (nsub_) {
         const uint32_t grid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
-        mf_small_factor_kernel<<<grid, kWarpsPerCta * 32, kSmallFactorSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_);
+        timed(4, [&] { mf_small_factor_kernel<<<grid, kWarpsPerCta * 32, kSmallFactorSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_); });
     }
     for (const Launch& l : factor_seq_) {
         const uint4* tk = d_tasks_ + l.first;
-        switch (l.kind) {
-            case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
-            case 1: mf_diag_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
-            case 2: mf_col_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
-            default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
-        }
+        timed(l.kind, [&] {
+            switch (l.kind) {
+                case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
+                case 1: mf_diag_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
+                case 2: mf_col_kernel<<<l.count, kColThreads, kColSmem, st>>>(dev_, tk); break;
+                default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
+            }
+        });
+    }
+    if (timing) {
+        fprintf(stderr, "[mf timing] asm %.3f (max %.3f)  diag %.3f (max %.3f)  col %.3f (max %.3f)  rupd %.3f (max %.3f)  small %.3f ms\n",
+                sums[0], maxs[0], sums[1], maxs[1], sums[2], maxs[2], sums[3], maxs[3], sums[4]);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
     }
     return cudaGetLastError();
 }
@@ -846,7 +872,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
 
 // The launch sequences are static: captured once into CUDA graphs and replayed.
 cudaError_t Multifrontal::factor(cudaStream_t st) {
-    static const bool no_graph = std::getenv("FK_NO_GRAPH") != nullptr;
+    static const bool no_graph = std::getenv("FK_NO_GRAPH") != nullptr || std::getenv("FK_MF_TIMING") != nullptr;
     if (no_graph || factor_launches_ < 8) return enqueue_factor(st);
     if (!factor_graph_) {
         cudaGraph_t g = nullptr;

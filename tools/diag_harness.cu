@@ -1,37 +1,42 @@
-// Debug harness: times the phases of mf_diag_kernel on one 64x64 SPD tile (build: see tools/run_diag_harness.sh)
+// Debug harness: runs mf_diag_kernel + mf_col_kernel on one 128x64 front, checks L D L^T = A and times them.
 #include "../fiksi_b200/csrc/multifrontal.cu"
 #include <cstdio>
 using namespace fk;
-int main() {
-    const uint32_t f = 64, ns = 64;
+int main(int argc, char** argv) {
+    const uint32_t f = 128, ns = argc > 1 ? atoi(argv[1]) : 64;
     std::vector<double> A(f * ns, 0.0);
     for (uint32_t j = 0; j < ns; j++) for (uint32_t i = j; i < f; i++) A[j * f + i] = (i == j) ? 70.0 + i : 1.0 / (1 + i - j);
     MfDev D{};
-    uint32_t h_c0 = 0, h_ns = ns, h_f = f, h_w = 0; uint64_t h_off = 0;
+    uint32_t h32[4] = {0, ns, f, 0}; uint64_t h_off = 0;
     uint32_t *d32; cudaMalloc(&d32, 64); uint64_t* d64; cudaMalloc(&d64, 64);
-    cudaMemcpy(d32, &h_c0, 4, cudaMemcpyHostToDevice); cudaMemcpy(d32 + 1, &h_ns, 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(d32 + 2, &h_f, 4, cudaMemcpyHostToDevice); cudaMemcpy(d32 + 3, &h_w, 4, cudaMemcpyHostToDevice);
-    cudaMemcpy(d64, &h_off, 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d32, h32, 16, cudaMemcpyHostToDevice); cudaMemcpy(d64, &h_off, 8, cudaMemcpyHostToDevice);
     D.S = 1; D.c0 = d32; D.ns = d32 + 1; D.f = d32 + 2; D.winv_blk = d32 + 3; D.pan_off = d64;
-    cudaMalloc(&D.pan, A.size() * 8); cudaMalloc(&D.winv, 4096 * 8); cudaMalloc(&D.ubuf, 64 * 8); cudaMalloc(&D.status, 4);
-    cudaMemset(D.status, 0, 4);
-    uint4 task{0, 0, 0, 64u << 16}; uint4* dt; cudaMalloc(&dt, 16); cudaMemcpy(dt, &task, 16, cudaMemcpyHostToDevice);
-    for (int rep = 0; rep < 3; rep++) {
+    cudaMalloc(&D.pan, A.size() * 8); cudaMalloc(&D.status, 4); cudaMemset(D.status, 0, 4);
+    uint4 tasks[2] = {{0, 0, 0, ns << 16}, {0, ns, 0, (f - ns) | (ns << 16)}};
+    uint4* dt; cudaMalloc(&dt, 32); cudaMemcpy(dt, tasks, 32, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem);
+    cudaEvent_t a, b, c; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventCreate(&c);
+    for (int rep = 0; rep < 4; rep++) {
         cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
-        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
         cudaEventRecord(a);
         mf_diag_kernel<<<1, kDiagThreads>>>(D, dt);
-        cudaEventRecord(b); cudaEventSynchronize(b);
-        float ms; cudaEventElapsedTime(&ms, a, b);
-        printf("rep %d: %.1f us (%s)\n", rep, ms * 1e3, cudaGetErrorString(cudaGetLastError()));
+        cudaEventRecord(b);
+        mf_col_kernel<<<1, kColThreads, kColSmem>>>(D, dt + 1);
+        cudaEventRecord(c); cudaEventSynchronize(c);
+        float m1, m2; cudaEventElapsedTime(&m1, a, b); cudaEventElapsedTime(&m2, b, c);
+        printf("rep %d: diag %.1f us, col %.1f us (%s)\n", rep, m1 * 1e3, m2 * 1e3, cudaGetErrorString(cudaGetLastError()));
     }
-    // check: L D L^T == A
-    std::vector<double> L(A.size()); cudaMemcpy(L.data(), D.pan, A.size() * 8, cudaMemcpyDeviceToHost);
+    // empty-kernel launch overhead reference
+    cudaEventRecord(a); mf_diag_kernel<<<0 + 1, kDiagThreads>>>(D, dt + 1 /* nc from task: harmless */); cudaEventRecord(b); cudaEventSynchronize(b);
+    std::vector<double> L(A.size()); cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+    mf_diag_kernel<<<1, kDiagThreads>>>(D, dt); mf_col_kernel<<<1, kColThreads, kColSmem>>>(D, dt + 1);
+    cudaMemcpy(L.data(), D.pan, A.size() * 8, cudaMemcpyDeviceToHost);
     double maxerr = 0;
-    for (uint32_t i = 0; i < f; i++) for (uint32_t j = 0; j <= i; j++) {
-        double sacc = 0; for (uint32_t k = 0; k <= j; k++) { double lik = (i == k) ? 1.0 : L[k * f + i], ljk = (j == k) ? 1.0 : L[k * f + j]; sacc += lik * L[k * f + k] * ljk; }
+    for (uint32_t i = 0; i < f; i++) for (uint32_t j = 0; j <= i && j < ns; j++) {
+        double sacc = 0;
+        for (uint32_t k = 0; k <= j; k++) { double lik = (i == k) ? 1.0 : L[k * f + i], ljk = (j == k) ? 1.0 : L[k * f + j]; sacc += lik * L[k * f + k] * ljk; }
         maxerr = fmax(maxerr, fabs(sacc - A[j * f + i]));
     }
-    printf("max |LDL^T - A| = %.3e\n", maxerr);
+    printf("ns=%u max |L D L^T - A| over the panel = %.3e\n", ns, maxerr);
     return 0;
 }
