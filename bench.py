@@ -236,9 +236,14 @@ def main():
         alg_bytes = h2d + d2h
         avg_s = (total_ms / args.steps) * 1e-3 if world == 1 else (float(sum(step_ms)) / args.steps) * 1e-3
         achieved = alg_bytes / avg_s / 1e9
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
+        # of this same command (profiles/r01_v3_lm_kernel_tile16_ncu_full_summary.csv): 40.44 MB + 0.64 MB
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "fk_batch_lm_kernel<%d,%d>" % (info["tile"], 1), "peak_source": peak_src,
-                            "note": "latency/FP64-bound kernel: whole LM loop runs out of shared memory; see fp64 + assembly"}
+                            "traffic": 41084416 if (n == 65536 and info["tile"] == 16) else None,
+                            "kernel": "fk_batch_lm_kernel<%d,%d>" % (info["tile"], 1), "peak_source": peak_src,
+                            "note": "issue/latency-bound kernel (ncu: 60 % issue slots busy, FP64 pipe 10.6 %, DRAM 0.3 %): the whole LM "
+                                    "loop runs out of shared memory, HBM only sees each sketch's inputs and outputs once; the HBM-bound "
+                                    "kernel of the path is K1, see `assembly`"}
         if not args.no_extras:
             try:
                 fp64_peak = fk.fp64_peak_tflops(local_rank)
@@ -293,17 +298,52 @@ def assembly_bandwidth(fk, wl, torch, device, peak):
         times.append(a.elapsed_time(b))
     ms = sum(times) / len(times)
     alg = topo.info["eval_bytes"] * n
+    i = topo.info
+    dram = 8 * n * (i["n_vars"] + i["n_expr"] + i["n_rows"] + i["jac_nnz"])  # every input and output byte once
     out = {"kernel": "fk_batch_eval_tiled_kernel<64,true>", "workload": "config 4 topology, 1,000,000 sketches",
            "algorithmic_bytes": alg, "ms": ms, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
     out["frac"] = out["achieved"] / peak
+    # SURVEY 8d's algorithmic bytes count every per-row gather (17 + 4k + 20a B/row); the tile-staged kernel
+    # reads each variable once per sketch, so the traffic HBM actually sees is smaller (ncu: 152 MB read +
+    # 366 MB written per launch, profiles/r01_k1_tiled_S64_ncu_full_summary.csv)
+    out["min_dram_bytes"] = dram
+    out["dram_gbs"] = dram / (ms * 1e-3) / 1e9
+    out["dram_frac_of_peak"] = out["dram_gbs"] / peak
+    out["traffic"] = 518283520
     plan.close()
+    # LM solve of the same 1,000,000 mixed-primitive sketches (config 4), device-resident
+    try:
+        plan = topo.plan(n, device=device)
+        plan.upload(v, p, stream)
+        plan.run(stream)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            plan.run(stream)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        import numpy as np
+        rep = np.zeros(n, dtype=fk.REPORT_DTYPE)
+        plan.download(None, rep, stream)
+        torch.cuda.synchronize()
+        lm_ms = sum(ts) / len(ts)
+        out["config4_lm"] = {"workload": "configs[3]: 1,000,000 mixed-primitive CAD sketches (11 variables, 8 rows of 6 kinds), 1 GPU",
+                             "ms": lm_ms, "sketches_per_s": n / (lm_ms * 1e-3), "tile_lanes": i["tile"],
+                             "fraction_converged": float(np.mean(rep["ssr"] < 1e-8)),
+                             "mean_factorizations": float(rep["factorizations"].mean())}
+        plan.close()
+    except Exception as e:  # noqa: BLE001
+        out["config4_lm"] = {"error": str(e)}
     return out
 
 
 def large_system(fk, wl, hbm_peak, fp64_peak):
     """Config 3: one 400x250 lattice (200,000 variables, 298,701 distance rows) through the global
-    sparse path: time per LM solve, phase split, FP64 rate of the sparse LDL^T, and the K1 assembly
-    rate on its 31.4 MB (L2-resident) table."""
+    sparse path: time per LM solve, phase split, FP64 rate of the supernodal multifrontal LDL^T
+    (K5), and the K1 assembly rate on its 31.4 MB (L2-resident) table."""
     w = wl.lattice(400, 250)
     v, p, scale = w.prepare()
     t0 = time.perf_counter()
