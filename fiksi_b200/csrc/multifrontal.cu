@@ -190,50 +190,110 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
     __syncthreads();
 }
 
+// ---- 8-column register micro-kernels ---------------------------------------------------------------------
+// The pivot chain of a 64-column tile is latency bound (measured on B200: DFMA 8.6, LDS ~29,
+// rcp+2 Newton 47 cycles, a CTA barrier ~100), so the tile kernels work on micro-panels of 8
+// columns: EVERY thread factorises the 8x8 diagonal block redundantly in registers (operands are
+// shared-memory broadcasts; static register indices, ~250 instructions, executed 8 times per tile,
+// so the code stays instruction-cache resident), then solves its own row against it — no
+// communication inside a micro-panel — and the rest of the tile receives a rank-8 update.
+constexpr int MB = 8;
+
+// LDLt of the 8x8 block at rows/cols k0.. of tile Cs (row stride ld): on return ll[a][b] (b < a)
+// holds the unit-lower factor, inv[k] = 1 / d_k, piv[k] = d_k.  Columns >= kw are treated as identity.
+__device__ __forceinline__ void micro_ldl(const double* Cs, uint32_t ld, uint32_t k0, uint32_t kw, double (&ll)[MB][MB],
+                                          double (&inv)[MB], double (&piv)[MB]) {
+#pragma unroll
+    for (int a = 0; a < MB; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++)
+            ll[a][b] = ((uint32_t)a < kw) ? Cs[(k0 + a) * ld + k0 + b] : (a == b ? 1.0 : 0.0);
+#pragma unroll
+    for (int k = 0; k < MB; k++) {
+        piv[k] = ll[k][k];
+        inv[k] = fast_rcp(piv[k]);
+#pragma unroll
+        for (int a = k + 1; a < MB; a++) {
+            const double la = ll[a][k] * inv[k];
+#pragma unroll
+            for (int b = k + 1; b <= a; b++) ll[a][b] = fma(-la, ll[b][k], ll[a][b]);  // ll[b][k] still unscaled
+        }
+#pragma unroll
+        for (int a = k + 1; a < MB; a++) ll[a][k] *= inv[k];
+    }
+}
+
 // Diagonal tile (pivot block at col0, nc <= 64 columns) of supernode s, right-looking (the tile has
-// already received the updates of all earlier pivot blocks).  The tile lives in shared memory with
-// UNSCALED columns; 128 threads = 64 rows x 2 interleaved column halves.  One barrier per column: after
-// it every thread reads the pivot, forms its multiplier l_ik = c_ik / d_k, streams it to the panel
-// (coalesced) and applies the rank-1 update to its half of row i.  Small rolled loops on purpose: a
-// fully unrolled register version is an order of magnitude slower here because every instruction is
-// executed once and the kernel becomes instruction-fetch bound.
-constexpr int kDiagThreads = 128;
+// already received the updates of all earlier pivot blocks).  256 threads = 64 rows x 4 column
+// quarters.  Per micro-panel: barrier, register LDLt of the 8x8 block + substitution of the own
+// row (all four threads of a row redundantly), barrier, rank-8 update of the trailing tile.
+constexpr int kDiagThreads = 256;
 constexpr int kTsLd = TB + 1;
 
 __global__ void __launch_bounds__(kDiagThreads)
 mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
     __shared__ double Cs[TB * kTsLd];
+    __shared__ double Ys[TB * (MB + 1)];  // unscaled multipliers of the current micro-panel
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
     double* T = D.pan + __ldg(D.pan_off + s) + (size_t)col0 * f + col0;
-    const uint32_t tid = threadIdx.x, i = tid & 63, h = tid >> 6;
+    const uint32_t tid = threadIdx.x, i = tid & 63, q = tid >> 6;
     for (uint32_t e = tid; e < nc * TB; e += kDiagThreads) {
         const uint32_t ii = e & 63, j = e >> 6;
         if (ii < nc && j <= ii) Cs[ii * kTsLd + j] = T[(size_t)j * f + ii];
     }
-    for (uint32_t k = 0; k < nc; k++) {
+    for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
+        const uint32_t kw = min((uint32_t)MB, nc - k0);
         __syncthreads();
-        const double d = Cs[k * kTsLd + k];
+        double ll[MB][MB], inv[MB], piv[MB], y[MB];
+        micro_ldl(Cs, kTsLd, k0, kw, ll, inv, piv);
         if (tid == 0) {
-            flag_pivot(D.status, d);
-            T[(size_t)k * f + k] = d;
+#pragma unroll
+            for (int k = 0; k < MB; k++)
+                if ((uint32_t)k < kw) flag_pivot(D.status, piv[k]);
         }
-        if (i > k && i < nc) {
-            const double li = Cs[i * kTsLd + k] * fast_rcp(d);
-            if (h == 0) T[(size_t)k * f + i] = li;
+        // own row against the block: y_c = p_c - sum_{c' < c} y_c' L88[c][c']  (unscaled multipliers; for a
+        // row inside the micro-panel y_c is its pivot at c == i - k0 and unused beyond)
+        const bool active = i >= k0 && i < nc;
+#pragma unroll
+        for (int c = 0; c < MB; c++) {
+            double v = (active && (uint32_t)c < kw && k0 + c <= i) ? Cs[i * kTsLd + k0 + c] : 0.0;
+#pragma unroll
+            for (int cp = 0; cp < c; cp++) v = fma(-y[cp], ll[c][cp], v);
+            y[c] = v;
+        }
+        if (q == 0 && active) {
+#pragma unroll
+            for (int c = 0; c < MB; c++) {
+                if ((uint32_t)c < kw && k0 + c <= i) {
+                    Ys[i * (MB + 1) + c] = y[c];
+                    T[(size_t)(k0 + c) * f + i] = (k0 + c == i) ? y[c] : y[c] * inv[c];
+                }
+            }
+        }
+        __syncthreads();
+        // rank-8 update of the rows below the micro-panel: C[i][j] -= sum_c l_ic * y_jc
+        if (i >= k0 + MB && i < nc) {
+            double l[MB];
+#pragma unroll
+            for (int c = 0; c < MB; c++) l[c] = y[c] * inv[c];
             double* row = Cs + i * kTsLd;
-            const double* colk = Cs + k;
-#pragma unroll 4
-            for (uint32_t j = k + 1 + h; j <= i; j += 2) row[j] = fma(-li, colk[j * kTsLd], row[j]);
+            for (uint32_t j = k0 + MB + q; j <= i; j += 4) {
+                const double* yj = Ys + j * (MB + 1);
+                double v = row[j];
+#pragma unroll
+                for (int c = 0; c < MB; c++) v = fma(-l[c], yj[c], v);
+                row[j] = v;
+            }
         }
     }
 }
 
-// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C L_kk^-T D^-1 by forward
-// substitution in shared memory.  256 threads = 64 rows x 4 interleaved column quarters; the four
-// threads of a row sit in one warp (lanes 4i..4i+3 hold row 8w+i), so a __syncwarp per column is the
-// only synchronisation.
+// Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C L_kk^-T D^-1 by blocked
+// forward substitution.  256 threads = 64 rows x 4 column quarters, the four threads of a row in
+// one warp (lanes 4r..4r+3): per micro-panel every thread solves its row's 8 entries in registers
+// (redundantly x4), then the four share the rank-8 update of the rest of the row; __syncwarp only.
 constexpr int kColThreads = 256;
 constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (row, quarter) hit distinct banks
 __global__ void __launch_bounds__(kColThreads)
@@ -249,21 +309,40 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
     const double* Lkk = P + (size_t)col0 * f + col0;
     double* C = P + (size_t)col0 * f + row0;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t e = tid; e < nc * TB; e += kColThreads) {
+    const uint32_t ncp = (nc + MB - 1) & ~(uint32_t)(MB - 1);
+    for (uint32_t e = tid; e < ncp * TB; e += kColThreads) {
         const uint32_t ii = e & 63, j = e >> 6;
-        Cs[ii * kYsLd + j] = ii < nr ? C[(size_t)j * f + ii] : 0.0;
-        if (ii < nc && j <= ii) Ls[ii * kTsLd + j] = Lkk[(size_t)j * f + ii];
+        Cs[ii * kYsLd + j] = (ii < nr && j < nc) ? C[(size_t)j * f + ii] : 0.0;
+        Ls[ii * kTsLd + j] = (ii < nc && j < ii) ? Lkk[(size_t)j * f + ii] : 0.0;  // strictly lower part, zero padded
     }
     if (tid < nc) invd[tid] = fast_rcp(Lkk[(size_t)tid * f + tid]);
     __syncthreads();
     {
         const uint32_t i = tid >> 2, q = tid & 3;
         double* row = Cs + i * kYsLd;
-        for (uint32_t c = 0; c + 1 < nc; c++) {
-            const double y = row[c];
-            const double* Lc = Ls + c;  // L_kk[cp][c] = Lc[cp * kTsLd]
-#pragma unroll 4
-            for (uint32_t cp = c + 1 + q; cp < nc; cp += 4) row[cp] = fma(-y, Lc[cp * kTsLd], row[cp]);
+        for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
+            double y[MB];
+#pragma unroll
+            for (int c = 0; c < MB; c++) {
+                double v = row[k0 + c];
+                const double* Lc = Ls + (k0 + c) * kTsLd + k0;
+#pragma unroll
+                for (int cp = 0; cp < c; cp++) v = fma(-y[cp], Lc[cp], v);
+                y[c] = v;
+            }
+            __syncwarp();  // all four threads of the row have read the block before it is overwritten
+            if (q == 0) {
+#pragma unroll
+                for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
+            }
+#pragma unroll 2
+            for (uint32_t cp = k0 + MB + q; cp < nc; cp += 4) {
+                const double* Lr = Ls + cp * kTsLd + k0;
+                double v = row[cp];
+#pragma unroll
+                for (int c = 0; c < MB; c++) v = fma(-y[c], Lr[c], v);
+                row[cp] = v;
+            }
             __syncwarp();
         }
     }
