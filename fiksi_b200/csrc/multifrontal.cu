@@ -405,9 +405,154 @@ __device__ __forceinline__ void group_sync() {
     else __syncthreads();
 }
 
-template <int G>
+// Pivot-block triangular solves of a wide supernode (ns >= 64) by one CTA of 256 threads, in
+// micro-panels of 8 columns: every thread solves the 8x8 block redundantly in registers, then
+// updates the rows it owns.  The panel entries of the NEXT micro-panel are fetched into registers
+// while the current one is processed (the loads do not depend on the solution), so the chain per
+// micro-panel is one barrier plus ~30 dependent FMAs instead of a DRAM round trip.
+constexpr int kPR = 4;  // prefetched rows per thread (covers 1024 rows below a micro-panel)
+
+// L y = t (unit lower, ns x ns, column-major with leading dimension f).  t is consumed; y receives
+// the solution.  l88[2][64] is scratch.
+__device__ __forceinline__ void pivot_forward_256(const double* __restrict__ P, uint32_t f, uint32_t ns, double* t, double* y,
+                                                  double* l88) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t pc = tid & 7, pcp = (tid >> 3) & 7;  // threads < 64 stage L88[pc][pcp]
+    double nb88 = 0.0, nl[kPR][MB];
+    auto prefetch = [&](uint32_t k0) {
+        nb88 = (tid < 64 && pcp < pc && k0 + pc < ns) ? P[(size_t)(k0 + pcp) * f + k0 + pc] : 0.0;
+#pragma unroll
+        for (int r = 0; r < kPR; r++) {
+            const uint32_t i = k0 + MB + tid + 256 * r;
+#pragma unroll
+            for (int c = 0; c < MB; c++) nl[r][c] = (i < ns && k0 + c < ns) ? P[(size_t)(k0 + c) * f + i] : 0.0;
+        }
+    };
+    prefetch(0);
+    for (uint32_t k0 = 0; k0 < ns; k0 += MB) {
+        double* lb = l88 + ((k0 >> 3) & 1) * 64;
+        double cl[kPR][MB];
+#pragma unroll
+        for (int r = 0; r < kPR; r++)
+#pragma unroll
+            for (int c = 0; c < MB; c++) cl[r][c] = nl[r][c];
+        if (tid < 64) lb[pc * 8 + pcp] = nb88;
+        if (k0 + MB < ns) prefetch(k0 + MB);
+        __syncthreads();
+        double yy[MB];
+#pragma unroll
+        for (int c = 0; c < MB; c++) {
+            double v = k0 + c < ns ? t[k0 + c] : 0.0;
+#pragma unroll
+            for (int cp = 0; cp < c; cp++) v = fma(-lb[c * 8 + cp], yy[cp], v);
+            yy[c] = v;
+        }
+        if (tid < MB && k0 + tid < ns) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < MB; c++) v = tid == (uint32_t)c ? yy[c] : v;
+            y[k0 + tid] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < kPR; r++) {
+            const uint32_t i = k0 + MB + tid + 256 * r;
+            if (i < ns) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c < MB; c++) acc = fma(cl[r][c], yy[c], acc);
+                t[i] -= acc;
+            }
+        }
+        for (uint32_t i = k0 + MB + tid + 256 * kPR; i < ns; i += 256) {  // very wide supernodes: direct loads
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < MB; c++)
+                if (k0 + c < ns) acc = fma(P[(size_t)(k0 + c) * f + i], yy[c], acc);
+            t[i] -= acc;
+        }
+    }
+    __syncthreads();
+}
+
+// L^T z = t (t already holds D^-1 y minus the contribution of the rows below the pivot block).
+// red[8][8] and l88[2][64] are scratch; z receives the solution.
+__device__ __forceinline__ void pivot_backward_256(const double* __restrict__ P, uint32_t f, uint32_t ns, const double* t, double* z,
+                                                   double* l88, double* red) {
+    const uint32_t tid = threadIdx.x, wp = tid >> 5, ln = tid & 31;
+    const uint32_t pc = tid & 7, pcp = (tid >> 3) & 7;
+    double nb88 = 0.0, nl[kPR][MB];
+    auto prefetch = [&](uint32_t k0) {
+        nb88 = (tid < 64 && pcp < pc && k0 + pc < ns) ? P[(size_t)(k0 + pcp) * f + k0 + pc] : 0.0;
+#pragma unroll
+        for (int r = 0; r < kPR; r++) {
+            const uint32_t i = k0 + MB + tid + 256 * r;
+#pragma unroll
+            for (int c = 0; c < MB; c++) nl[r][c] = (i < ns && k0 + c < ns) ? P[(size_t)(k0 + c) * f + i] : 0.0;
+        }
+    };
+    const uint32_t last = ((ns - 1) / MB) * MB;
+    prefetch(last);
+    for (uint32_t kk = 0; kk <= last; kk += MB) {
+        const uint32_t k0 = last - kk;
+        double* lb = l88 + ((k0 >> 3) & 1) * 64;
+        double part[MB];
+#pragma unroll
+        for (int c = 0; c < MB; c++) part[c] = 0.0;
+        // the z of the rows below this micro-panel are final (written before the previous barrier)
+#pragma unroll
+        for (int r = 0; r < kPR; r++) {
+            const uint32_t i = k0 + MB + tid + 256 * r;
+            if (i < ns) {
+                const double zi = z[i];
+#pragma unroll
+                for (int c = 0; c < MB; c++) part[c] = fma(nl[r][c], zi, part[c]);
+            }
+        }
+        for (uint32_t i = k0 + MB + tid + 256 * kPR; i < ns; i += 256) {
+            const double zi = z[i];
+#pragma unroll
+            for (int c = 0; c < MB; c++)
+                if (k0 + c < ns) part[c] = fma(P[(size_t)(k0 + c) * f + i], zi, part[c]);
+        }
+        if (tid < 64) lb[pc * 8 + pcp] = nb88;
+        if (k0 >= MB) prefetch(k0 - MB);
+#pragma unroll
+        for (int c = 0; c < MB; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part[c] += __shfl_xor_sync(0xFFFFFFFFu, part[c], o);
+        }
+        if (ln == 0) {
+#pragma unroll
+            for (int c = 0; c < MB; c++) red[wp * 8 + c] = part[c];
+        }
+        __syncthreads();
+        double zz[MB];
+#pragma unroll
+        for (int c = MB - 1; c >= 0; c--) {
+            double v = 0.0;
+            if (k0 + c < ns) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; w8++) sum += red[w8 * 8 + c];
+                v = t[k0 + c] - sum;
+            }
+#pragma unroll
+            for (int cq = c + 1; cq < MB; cq++) v = fma(-lb[cq * 8 + c], zz[cq], v);
+            zz[c] = v;
+        }
+        if (tid < MB && k0 + tid < ns) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < MB; c++) v = tid == (uint32_t)c ? zz[c] : v;
+            z[k0 + tid] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <int G, bool WIDE = false>
 __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, double* __restrict__ w, double* t, double* tri,
-                                                  uint32_t gt, bool split = false) {
+                                                  uint32_t gt, bool split = false, double* wide = nullptr) {
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
     const double* P = D.pan + __ldg(D.pan_off + s);
     for (uint32_t i = gt; i < f; i += G) t[i] = i < ns ? w[c0 + i] : 0.0;
@@ -419,6 +564,19 @@ __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, do
         group_sync<G>();
     }
     const uint32_t rlim = split ? ns : f;  // split: the rows below the pivot block are updated by mf_fwd_upd_kernel
+    if (WIDE && G == 256 && ns >= 64) {  // wide pivot block: micro-panel solve with register prefetch
+        double* y2 = wide;
+        pivot_forward_256(P, f, ns, t, y2, tri);
+        for (uint32_t i = gt; i < ns; i += G) t[i] = y2[i];
+        group_sync<G>();
+        for (uint32_t i = ns + gt; i < rlim; i += G) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (uint32_t k = 0; k < ns; k++) acc = fma(P[(size_t)k * f + i], t[k], acc);
+            t[i] -= acc;
+        }
+        group_sync<G>();
+    } else
     for (uint32_t k0 = 0; k0 < ns; k0 += 32) {
         const uint32_t nb = min(32u, ns - k0);
         // stage the nb x nb unit-lower triangle: tri[i][k]
@@ -453,10 +611,10 @@ __device__ __forceinline__ void forward_supernode(const MfDev& D, uint32_t s, do
     group_sync<G>();
 }
 
-template <int G>
+template <int G, bool WIDE = false>
 __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, double* __restrict__ w, double* __restrict__ delta,
                                                    const int32_t* __restrict__ perm, double* t, double* tri, uint32_t gt,
-                                                   bool split = false, const double* __restrict__ tmp = nullptr) {
+                                                   bool split = false, const double* __restrict__ tmp = nullptr, double* wide = nullptr) {
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s);
     const double* P = D.pan + __ldg(D.pan_off + s);
     const uint32_t* rows = D.rows + __ldg(D.rows_off + s);
@@ -469,6 +627,22 @@ __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, d
     }
     group_sync<G>();
     const uint32_t nblk = (ns + 31) / 32;
+    if (WIDE && G == 256 && ns >= 64) {  // wide pivot block
+        const uint32_t wp = gt >> 5, ln = gt & 31;
+        for (uint32_t k = wp; k < ns && rlim > ns; k += G / 32) {  // rows below the pivot block (not split)
+            const double* col = P + (size_t)k * f;
+            double acc = 0.0;
+            for (uint32_t i = ns + ln; i < rlim; i += 32) acc = fma(col[i], t[i], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+            if (ln == 0) t[k] -= acc;
+        }
+        group_sync<G>();
+        double* z2 = wide;
+        pivot_backward_256(P, f, ns, t, z2, tri, tri + 128);
+        for (uint32_t i = gt; i < ns; i += G) t[i] = z2[i];
+        group_sync<G>();
+    } else
     for (uint32_t bi = nblk; bi-- > 0;) {
         const uint32_t k0 = bi * 32, nb = min(32u, ns - k0);
         // column dots with everything below the block: one warp per column
@@ -529,17 +703,18 @@ mf_small_solve_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint3
 constexpr uint32_t kSplitEntries = 16384;
 __device__ __forceinline__ bool is_split(uint32_t f, uint32_t ns) { return (f - ns) * ns > kSplitEntries; }
 
-template <bool FORWARD>
+template <bool FORWARD, bool WIDE>
 __global__ void __launch_bounds__(256)
 mf_big_solve_kernel(MfDev D, const uint32_t* __restrict__ list, double* __restrict__ w, double* __restrict__ delta,
-                    const int32_t* __restrict__ perm, const double* __restrict__ tmp) {
+                    const int32_t* __restrict__ perm, const double* __restrict__ tmp, uint32_t max_front) {
     extern __shared__ double smd[];
-    double* tri = smd;            // [32*33]
+    double* tri = smd;            // [32*33] (wide pivot blocks: L88 staging + reduction scratch)
     double* t = smd + 32 * 33;    // [max front]
+    double* wide = t + max_front; // [max front] second vector of the wide pivot-block solves
     const uint32_t s = __ldg(list + blockIdx.x);
     const bool split = is_split(__ldg(D.f + s), __ldg(D.ns + s));
-    if (FORWARD) forward_supernode<256>(D, s, w, t, tri, threadIdx.x, split);
-    else backward_supernode<256>(D, s, w, delta, perm, t, tri, threadIdx.x, split, tmp);
+    if (FORWARD) forward_supernode<256, WIDE>(D, s, w, t, tri, threadIdx.x, split, wide);
+    else backward_supernode<256, WIDE>(D, s, w, delta, perm, t, tri, threadIdx.x, split, tmp, wide);
 }
 
 // Forward, split supernodes: u_s[r0 .. r0+64) -= L21[rows, :] y_s.  256 threads = 64 rows x 4
@@ -773,6 +948,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     };
     factor_seq_.clear();
     fwd_tasks_.clear();
+    level_wide_.clear();
     bwd_tasks_.clear();
     level_ptr_.assign(1, 0);
     std::vector<uint32_t> level_list;
@@ -780,6 +956,11 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         const std::vector<uint32_t>& L = by_level[l];
         for (uint32_t s : L) level_list.push_back(s);
         level_ptr_.push_back((uint32_t)level_list.size());
+        {
+            bool wide = false;
+            for (uint32_t s : L) wide = wide || ns[s] >= 64;
+            level_wide_.push_back(wide);
+        }
         {   // solve tasks of the split supernodes of this level
             uint32_t first = (uint32_t)(tasks.size() / 4);
             for (uint32_t s : L)
@@ -877,13 +1058,15 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
-    const size_t big_solve_smem = (32 * 33 + (size_t)max_front) * sizeof(double);
+    const size_t big_solve_smem = (32 * 33 + 2 * (size_t)max_front) * sizeof(double);
     if (big_solve_smem > 200 * 1024) {
         if (err) *err = "multifrontal: a front is too large for the shared-memory solve vector";
         return cudaErrorInvalidValue;
     }
-    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
-    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
+    MF_CU(cudaFuncSetAttribute(mf_big_solve_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
     MF_CU(cudaFuncSetAttribute(mf_fwd_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
     MF_CU(cudaFuncSetAttribute(mf_bwd_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_solve_smem));
     return cudaSuccess;
@@ -933,17 +1116,19 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
 
 cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t st) {
     const uint32_t sgrid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t smem = (32 * 33 + (size_t)stats.max_front) * sizeof(double);
+    const size_t smem = (32 * 33 + 2 * (size_t)stats.max_front) * sizeof(double);
     const size_t vsmem = (size_t)stats.max_front * sizeof(double);
     const uint32_t nlevels = (uint32_t)level_ptr_.size() - 1;
     if (nsub_) mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
     for (uint32_t l = 0; l < nlevels; l++) {
-        mf_big_solve_kernel<true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_);
+        if (level_wide_[l]) mf_big_solve_kernel<true, true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
+        else mf_big_solve_kernel<true, false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
         if (fwd_tasks_[l].second) mf_fwd_upd_kernel<<<fwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + fwd_tasks_[l].first, w);
     }
     for (uint32_t l = nlevels; l-- > 0;) {
         if (bwd_tasks_[l].second) mf_bwd_dot_kernel<<<bwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + bwd_tasks_[l].first, w, d_tmp_);
-        mf_big_solve_kernel<false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_);
+        if (level_wide_[l]) mf_big_solve_kernel<false, true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
+        else mf_big_solve_kernel<false, false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
     }
     if (nsub_) mf_small_solve_kernel<false><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
     return cudaGetLastError();
