@@ -1115,22 +1115,52 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
 }
 
 cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t st) {
+    static const bool timing = std::getenv("FK_MF_TIMING") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float sums[6] = {0, 0, 0, 0, 0, 0}, maxs[6] = {0, 0, 0, 0, 0, 0};
+    if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    auto timed = [&](int kind, auto&& launch) {
+        if (timing) cudaEventRecord(e0, st);
+        launch();
+        if (timing) {
+            cudaEventRecord(e1, st);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            sums[kind] += ms;
+            maxs[kind] = std::max(maxs[kind], ms);
+        }
+    };
     const uint32_t sgrid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t smem = (32 * 33 + 2 * (size_t)stats.max_front) * sizeof(double);
     const size_t vsmem = (size_t)stats.max_front * sizeof(double);
     const uint32_t nlevels = (uint32_t)level_ptr_.size() - 1;
-    if (nsub_) mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
+    if (nsub_) timed(0, [&] { mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm); });
     for (uint32_t l = 0; l < nlevels; l++) {
-        if (level_wide_[l]) mf_big_solve_kernel<true, true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
-        else mf_big_solve_kernel<true, false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
-        if (fwd_tasks_[l].second) mf_fwd_upd_kernel<<<fwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + fwd_tasks_[l].first, w);
+        const uint32_t cnt = level_ptr_[l + 1] - level_ptr_[l];
+        const uint32_t* list = d_level_list_ + level_ptr_[l];
+        timed(1, [&] {
+            if (level_wide_[l]) mf_big_solve_kernel<true, true><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
+            else mf_big_solve_kernel<true, false><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
+        });
+        if (fwd_tasks_[l].second) timed(2, [&] { mf_fwd_upd_kernel<<<fwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + fwd_tasks_[l].first, w); });
     }
     for (uint32_t l = nlevels; l-- > 0;) {
-        if (bwd_tasks_[l].second) mf_bwd_dot_kernel<<<bwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + bwd_tasks_[l].first, w, d_tmp_);
-        if (level_wide_[l]) mf_big_solve_kernel<false, true><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
-        else mf_big_solve_kernel<false, false><<<level_ptr_[l + 1] - level_ptr_[l], 256, smem, st>>>(dev_, d_level_list_ + level_ptr_[l], w, delta, d_perm, d_tmp_, stats.max_front);
+        const uint32_t cnt = level_ptr_[l + 1] - level_ptr_[l];
+        const uint32_t* list = d_level_list_ + level_ptr_[l];
+        if (bwd_tasks_[l].second) timed(3, [&] { mf_bwd_dot_kernel<<<bwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + bwd_tasks_[l].first, w, d_tmp_); });
+        timed(4, [&] {
+            if (level_wide_[l]) mf_big_solve_kernel<false, true><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
+            else mf_big_solve_kernel<false, false><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
+        });
     }
-    if (nsub_) mf_small_solve_kernel<false><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm);
+    if (nsub_) timed(5, [&] { mf_small_solve_kernel<false><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm); });
+    if (timing) {
+        fprintf(stderr, "[mf solve timing] small fwd %.3f  big fwd %.3f (max %.3f)  fwd upd %.3f (max %.3f)  bwd dot %.3f (max %.3f)  big bwd %.3f (max %.3f)  small bwd %.3f ms\n",
+                sums[0], sums[1], maxs[1], sums[2], maxs[2], sums[3], maxs[3], sums[4], maxs[4], sums[5]);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     return cudaGetLastError();
 }
 
@@ -1154,7 +1184,7 @@ cudaError_t Multifrontal::factor(cudaStream_t st) {
 }
 
 cudaError_t Multifrontal::solve(double* w, double* delta, const int32_t* d_perm, cudaStream_t st) {
-    static const bool no_graph = std::getenv("FK_NO_GRAPH") != nullptr;
+    static const bool no_graph = std::getenv("FK_NO_GRAPH") != nullptr || std::getenv("FK_MF_TIMING") != nullptr;
     if (no_graph || level_ptr_.size() < 5) return enqueue_solve(w, delta, d_perm, st);
     if (solve_graph_ && (w != solve_w_ || delta != solve_delta_ || d_perm != solve_perm_)) {
         cudaGraphExecDestroy(solve_graph_);
