@@ -45,6 +45,30 @@ class Topology:
         out["r_rowidx"] = out["r_rowidx"][:i["r_nnz"]]
         return out
 
+    def supernodal(self):
+        """fk_topology_supernodal: host-side analysis of the large-system path (no device needed)."""
+        class Info(C.Structure):
+            _fields_ = [(n, C.c_uint32) for n in ("n_supernodes", "n_small_subtrees", "n_big", "n_levels", "max_front",
+                                                  "n_tasks", "n_launches", "pad0")] + \
+                       [(n, C.c_uint64) for n in ("rows_total", "rel_total", "panel_doubles", "update_doubles")]
+        info = Info()
+        f = lib().fk_topology_supernodal
+        null = [None] * 9
+        check(f(self._h, C.byref(info), *null))
+        S = info.n_supernodes
+        out = {"sn_first": np.zeros(S + 1, np.uint32), "front": np.zeros(max(S, 1), np.uint32), "sn_parent": np.zeros(max(S, 1), np.int32),
+               "rows": np.zeros(max(info.rows_total, 1), np.uint32), "rel": np.zeros(max(info.rel_total, 1), np.uint32),
+               "big": np.zeros(max(S, 1), np.uint8), "level": np.zeros(max(S, 1), np.uint32),
+               "tasks": np.zeros(max(4 * info.n_tasks, 1), np.uint32), "launches": np.zeros(max(3 * info.n_launches, 1), np.uint32)}
+        check(f(self._h, C.byref(info), ptr(out["sn_first"], C.c_uint32), ptr(out["front"], C.c_uint32), ptr(out["sn_parent"], C.c_int32),
+                ptr(out["rows"], C.c_uint32), ptr(out["rel"], C.c_uint32), ptr(out["big"], C.c_uint8), ptr(out["level"], C.c_uint32),
+                ptr(out["tasks"], C.c_uint32), ptr(out["launches"], C.c_uint32)))
+        out["front"] = out["front"][:S]; out["sn_parent"] = out["sn_parent"][:S]; out["big"] = out["big"][:S]; out["level"] = out["level"][:S]
+        out["rows"] = out["rows"][:info.rows_total]; out["rel"] = out["rel"][:info.rel_total]
+        out["tasks"] = out["tasks"][:4 * info.n_tasks].reshape(-1, 4); out["launches"] = out["launches"][:3 * info.n_launches].reshape(-1, 3)
+        out["info"] = {n: getattr(info, n) for n, _ in Info._fields_}
+        return out
+
     def batch_solve(self, vars_, param, n_gpus=1):
         """fk_batch_solve on host buffers: vars[n][n_vars], param[n][n_expr] -> (free[n][n_free], reports)."""
         vars_ = np.ascontiguousarray(vars_, dtype=np.float64)

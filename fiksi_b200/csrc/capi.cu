@@ -14,6 +14,7 @@
 
 #include "../../include/fiksi_b200.h"
 #include "lm_kernels.cuh"
+#include "multifrontal.cuh"
 #include "sparse_path.cuh"
 #include "symbolic.hpp"
 
@@ -237,6 +238,38 @@ int fk_symbolic(const fk_problem* problem, uint32_t* aug_colptr, uint32_t* aug_r
     rc = fk_topology_symbolic(t, aug_colptr, aug_rowidx, colamd_perm, etree_parent, r_colptr, r_rowidx);
     fk_topology_destroy(t);
     return rc;
+}
+
+int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, uint32_t* sn_first, uint32_t* front,
+                           int32_t* sn_parent, uint32_t* rows, uint32_t* rel, uint8_t* big, uint32_t* level, uint32_t* tasks,
+                           uint32_t* launches) {
+    if (!topo || !info) return fail(FK_ERR_INVALID, "null argument");
+    fk::Multifrontal mf;
+    std::string err;
+    try {
+        if (mf.build_symbolic(topo->t, &err) != cudaSuccess) return fail(FK_ERR_TOO_LARGE, err);
+    } catch (const std::bad_alloc&) {
+        return fail(FK_ERR_OOM, "host allocation failed in the supernodal analysis");
+    }
+    const fk::MfSymbolic& y = mf.sym;
+    const auto seq = mf.factor_launches();
+    info->n_supernodes = y.S; info->n_small_subtrees = y.nsub; info->n_big = y.nbig; info->n_levels = y.nlevels;
+    info->max_front = y.max_front; info->n_tasks = (uint32_t)(y.tasks.size() / 4); info->n_launches = (uint32_t)seq.size(); info->pad0 = 0;
+    info->rows_total = y.rows.size(); info->rel_total = y.rel.size(); info->panel_doubles = y.pan_total; info->update_doubles = y.upd_total;
+    auto copy = [](auto* dst, const auto& v) {
+        if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+    };
+    if (sn_first) {
+        copy(sn_first, y.c0);
+        sn_first[y.S] = y.n;
+    }
+    copy(front, y.f); copy(sn_parent, y.sparent); copy(rows, y.rows); copy(rel, y.rel); copy(big, y.big); copy(level, y.level);
+    copy(tasks, y.tasks);
+    if (launches)
+        for (size_t k = 0; k < seq.size(); k++) {
+            launches[3 * k] = (uint32_t)seq[k].kind; launches[3 * k + 1] = seq[k].first; launches[3 * k + 2] = seq[k].count;
+        }
+    return FK_OK;
 }
 
 // ---- device-resident batch plan -----------------------------------------------------------------

@@ -812,24 +812,32 @@ Multifrontal::~Multifrontal() {
         }                                \
     } while (0)
 
-cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::string* err) {
-    (void)stream;
+// Host-only part of init(): supernodes, tree, relative indices, task lists (no CUDA calls; probed by
+// fk_topology_supernodal for the CPU tests).
+cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     const uint32_t n = t.n_free;
     n_ = n;
+    sym = MfSymbolic();
+    std::vector<uint32_t>&c0 = sym.c0, &ns = sym.ns, &f = sym.f, &rows_off = sym.rows_off, &rows = sym.rows, &rel_off = sym.rel_off,
+                         &rel = sym.rel, &child_ptr = sym.child_ptr, &child = sym.child, &winv_blk = sym.winv_blk, &sub_ptr = sym.sub_ptr,
+                         &sub_list = sym.sub_list, &level_list = sym.level_list, &level = sym.level, &tasks = sym.tasks;
+    std::vector<uint64_t>&pan_off = sym.pan_off, &upd_off = sym.upd_off;
+    std::vector<int32_t>& sparent = sym.sparent;
+    std::vector<uint8_t>& big = sym.big;
     const std::vector<uint32_t>& lc = t.l_colptr;
     const std::vector<uint32_t>& lr = t.l_rowidx;
     // ---- supernodes: column j joins its predecessor's supernode when parent[j-1] == j and
     // struct(j) == struct(j-1) \ {j-1}
-    std::vector<uint32_t> c0, col2sn(n);
+    std::vector<uint32_t> col2sn(n);
     for (uint32_t j = 0; j < n; j++) {
         const bool joins = j > 0 && t.parent[j - 1] == (int32_t)j && (lc[j + 1] - lc[j]) + 1 == (lc[j] - lc[j - 1]);
         if (!joins) c0.push_back(j);
         col2sn[j] = (uint32_t)c0.size() - 1;
     }
     const uint32_t S = (uint32_t)c0.size();
-    std::vector<uint32_t> ns(S), f(S), rows_off(S + 1, 0), rel_off(S + 1, 0);
-    std::vector<uint64_t> pan_off(S), upd_off(S);
-    std::vector<int32_t> sparent(S);
+    ns.assign(S, 0); f.assign(S, 0); rows_off.assign(S + 1, 0); rel_off.assign(S + 1, 0);
+    pan_off.assign(S, 0); upd_off.assign(S, 0);
+    sparent.assign(S, -1);
     uint64_t pan_total = 0, upd_total = 0;
     flops_ = 0;
     for (uint32_t s = 0; s < S; s++) {
@@ -850,7 +858,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     }
     for (uint32_t j = 0; j < n; j++) flops_ += (uint64_t)(lc[j + 1] - lc[j]) * (lc[j + 1] - lc[j]);
     pan_total_ = pan_total;
-    std::vector<uint32_t> rows(rows_off[S]);
+    rows.assign(rows_off[S], 0);
     for (uint32_t s = 0; s < S; s++) std::copy(lr.begin() + lc[c0[s]], lr.begin() + lc[c0[s]] + f[s], rows.begin() + rows_off[s]);
     // L position -> panel offset; diagonal positions
     lpos_map_.assign(lr.size(), 0);
@@ -862,7 +870,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         for (uint32_t q = lc[j]; q < lc[j + 1]; q++) lpos_map_[q] = base + (q - lc[j]);
     }
     // children (ascending) and relative indices
-    std::vector<uint32_t> child_ptr(S + 1, 0), child;
+    child_ptr.assign(S + 1, 0);
     for (uint32_t s = 0; s < S; s++)
         if (sparent[s] >= 0) child_ptr[sparent[s] + 1]++;
     for (uint32_t s = 0; s < S; s++) child_ptr[s + 1] += child_ptr[s];
@@ -872,7 +880,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         for (uint32_t s = 0; s < S; s++)
             if (sparent[s] >= 0) child[fill[sparent[s]]++] = s;
     }
-    std::vector<uint32_t> rel(rel_off[S]);
+    rel.assign(rel_off[S], 0);
     for (uint32_t s = 0; s < S; s++) {
         if (sparent[s] < 0) {
             if (f[s] != ns[s]) {
@@ -895,7 +903,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         }
     }
     // ---- small subtrees / big levels
-    std::vector<uint8_t> big(S, 0);
+    big.assign(S, 0);
     for (uint32_t s = 0; s < S; s++) {
         if (f[s] > (uint32_t)kSmallFront) big[s] = 1;
         if (big[s] && sparent[s] >= 0) big[sparent[s]] = 1;
@@ -917,17 +925,18 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     std::vector<uint32_t> sub_order(nsub);
     std::iota(sub_order.begin(), sub_order.end(), 0u);
     std::stable_sort(sub_order.begin(), sub_order.end(), [&](uint32_t a, uint32_t b) { return sub_work[a] > sub_work[b]; });
-    std::vector<uint32_t> sub_rank(nsub), sub_ptr(nsub + 1, 0);
+    std::vector<uint32_t> sub_rank(nsub);
+    sub_ptr.assign(nsub + 1, 0);
     for (uint32_t k = 0; k < nsub; k++) sub_rank[sub_order[k]] = k;
     for (uint32_t k = 0; k < nsub; k++) sub_ptr[k + 1] = sub_ptr[k] + sub_cnt[sub_order[k]];
-    std::vector<uint32_t> sub_list(sub_ptr[nsub]);
+    sub_list.assign(sub_ptr[nsub], 0);
     {
         std::vector<uint32_t> fill(sub_ptr.begin(), sub_ptr.end() - 1);
         for (uint32_t s = 0; s < S; s++)
             if (!big[s]) sub_list[fill[sub_rank[sub_of[s]]]++] = s;
     }
     nsub_ = nsub;
-    std::vector<uint32_t> level(S, 0), winv_blk(S, 0);
+    level.assign(S, 0); winv_blk.assign(S, 0);
     uint32_t nlevels = 0, nbig = 0, max_front = 1, winv_blocks = 0;
     for (uint32_t s = 0; s < S; s++) {
         max_front = std::max(max_front, f[s]);
@@ -942,7 +951,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     for (uint32_t s = 0; s < S; s++)
         if (big[s]) by_level[level[s]].push_back(s);
     // ---- task lists of the factorisation
-    std::vector<uint32_t> tasks;  // uint4 each
+    tasks.clear();  // uint4 each
     auto push_task = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
         tasks.push_back(a); tasks.push_back(b); tasks.push_back(c); tasks.push_back(d);
     };
@@ -951,7 +960,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     level_wide_.clear();
     bwd_tasks_.clear();
     level_ptr_.assign(1, 0);
-    std::vector<uint32_t> level_list;
+    level_list.clear();
     for (uint32_t l = 0; l < nlevels; l++) {
         const std::vector<uint32_t>& L = by_level[l];
         for (uint32_t s : L) level_list.push_back(s);
@@ -1025,7 +1034,20 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     factor_launches_ = factor_seq_.size() + (nsub ? 1 : 0);
     stats.supernodes = S; stats.small_subtrees = nsub; stats.big = nbig; stats.levels = nlevels;
     stats.max_front = max_front; stats.upd_doubles = upd_total;
+    sym.n = n; sym.S = S; sym.nsub = nsub; sym.nlevels = nlevels; sym.nbig = nbig; sym.max_front = max_front;
+    sym.winv_blocks = winv_blocks; sym.pan_total = pan_total; sym.upd_total = upd_total;
+    return cudaSuccess;
+}
 
+cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::string* err) {
+    (void)stream;
+    MF_CU(build_symbolic(t, err));
+    const uint32_t n = sym.n, S = sym.S, max_front = sym.max_front;
+    const uint64_t pan_total = sym.pan_total, upd_total = sym.upd_total;
+    const std::vector<uint32_t>&c0 = sym.c0, &ns = sym.ns, &f = sym.f, &rows_off = sym.rows_off, &rows = sym.rows, &rel_off = sym.rel_off,
+                               &rel = sym.rel, &child_ptr = sym.child_ptr, &child = sym.child, &winv_blk = sym.winv_blk, &sub_ptr = sym.sub_ptr,
+                               &sub_list = sym.sub_list, &level_list = sym.level_list, &tasks = sym.tasks;
+    const std::vector<uint64_t>&pan_off = sym.pan_off, &upd_off = sym.upd_off;
     // ---- upload
     dev_.S = S;
     MF_CU(upload_vec(c0, &dev_.c0, owned_));

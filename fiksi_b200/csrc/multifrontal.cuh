@@ -53,8 +53,28 @@ struct MfDev {
     int* status = nullptr;        // 0 ok, 1 non-positive pivot, 2 NaN pivot
 };
 
+// Host-side symbolic structures of the multifrontal factorisation (everything init() uploads).
+struct MfSymbolic {
+    uint32_t n = 0, S = 0, nsub = 0, nlevels = 0, nbig = 0, max_front = 1, winv_blocks = 0;
+    uint64_t pan_total = 0, upd_total = 0;
+    std::vector<uint32_t> c0, ns, f, rows_off, rows, rel_off, rel, child_ptr, child, winv_blk, sub_ptr, sub_list, level_list, level, tasks;
+    std::vector<uint64_t> pan_off, upd_off;
+    std::vector<int32_t> sparent;
+    std::vector<uint8_t> big;  // 1: level-scheduled tiled path, 0: member of a one-warp subtree
+};
+
 class Multifrontal {
 public:
+    struct Launch { int kind; uint32_t first, count; };  // kind: 0 asm, 1 diag, 2 col, 3 right-looking update
+    MfSymbolic sym;
+    // Host-only symbolic analysis (no CUDA calls).
+    cudaError_t build_symbolic(const Topology& t, std::string* err);
+    struct LaunchInfo { int kind; uint32_t first, count; };
+    std::vector<LaunchInfo> factor_launches() const {
+        std::vector<LaunchInfo> v;
+        for (const Launch& l : factor_seq_) v.push_back({l.kind, l.first, l.count});
+        return v;
+    }
     ~Multifrontal();
     // Builds the supernodal structures from the topology's L pattern and uploads them.
     cudaError_t init(const Topology& t, cudaStream_t stream, std::string* err);
@@ -74,7 +94,6 @@ public:
     struct Stats { uint32_t supernodes = 0, small_subtrees = 0, big = 0, levels = 0, max_front = 0; uint64_t upd_doubles = 0; } stats;
 
 private:
-    struct Launch { int kind; uint32_t first, count; };  // kind: 0 asm, 1 diag, 2 col, 3 upd
     MfDev dev_;
     std::vector<void*> owned_;
     std::vector<uint64_t> lpos_map_, diag_map_;

@@ -153,6 +153,26 @@ FK_API int fk_topology_eval(fk_topology* topo, const double* vars, const double*
  * triangular-solve ms, evaluations, factorisations, forward ms, backward ms}. */
 FK_API int fk_topology_last_timing(fk_topology* topo, float* out8);
 
+/* Parity / structure probe of the large-system path (host only, no device needed): the supernodal
+ * multifrontal analysis built on top of the R pattern of SymbolicQr::build (qr.rs:118-206).
+ * Call once with all array pointers NULL to get the sizes, then with arrays of
+ *   sn_first[n_supernodes+1]  first permuted column of every supernode (last entry = n_free)
+ *   front[n_supernodes]       order of the frontal matrix (= column count of the first column of L)
+ *   sn_parent[n_supernodes]   supernodal elimination tree (-1 root)
+ *   rows[rows_total]          row lists of the fronts, concatenated in supernode order
+ *   rel[rel_total]            for every update row of every supernode its position in the parent's front
+ *   big[n_supernodes]         1: level-scheduled tiled path, 0: member of a one-warp subtree
+ *   level[n_supernodes]       level of a big supernode (0 = no big child)
+ *   tasks[4*n_tasks], launches[3*n_launches]  static task lists {supernode,row0,col0,packed} and the
+ *                             launch sequence {kind (0 asm,1 diag,2 panel,3 update), first task, count}. */
+typedef struct fk_supernodal_info {
+    uint32_t n_supernodes, n_small_subtrees, n_big, n_levels, max_front, n_tasks, n_launches, pad0;
+    uint64_t rows_total, rel_total, panel_doubles, update_doubles;
+} fk_supernodal_info;
+FK_API int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, uint32_t* sn_first, uint32_t* front,
+                                  int32_t* sn_parent, uint32_t* rows, uint32_t* rel, uint8_t* big, uint32_t* level,
+                                  uint32_t* tasks, uint32_t* launches);
+
 /* ---- Levenberg–Marquardt ----------------------------------------------------------------- */
 /* == levenberg_marquardt(problem, variables), fiksi/src/solve/lm.rs:21.  free_values in/out,
  * length n_free.  Picks the batched kernel (n = 1) or the large sparse path by size. */
