@@ -133,63 +133,84 @@ mf_asm_kernel(MfDev D, const uint4* __restrict__ tasks) {
 }
 
 // Register-blocked FP64 micro-kernel: acc(4x4 per thread, 64x64 per CTA) -= A * diag(d) * B^T over
-// the first K pivot columns of the panel P (column-major, leading dimension f), A = rows
-// rowA0..rowA0+nrA, B = rows rowB0..rowB0+nrB.  Thread (tid & 15) owns rows 4*(tid&15).., thread
-// (tid >> 4) owns columns 4*(tid>>4)...  Chunks of KC columns go through double-buffered shared
-// memory; the next chunk is fetched into registers while the current one is multiplied.
+// K pivot columns of the panel P (column-major, leading dimension f), A = rows rowA0..rowA0+nrA,
+// B = rows rowB0..rowB0+nrB.  Thread tx = tid & 15 owns the INTERLEAVED rows tx, tx+16, tx+32, tx+48
+// (a warp's A-operand loads are 16 consecutive doubles: one conflict-free wavefront each; with four
+// consecutive rows per thread the 16-byte loads hit only half of the banks, 4 wavefronts each, and
+// ncu showed the kernel stalled on shared memory), thread ty = tid >> 4 owns columns 4ty..4ty+3
+// (two broadcast 16-byte loads).  Chunks of KC columns go through double-buffered shared memory;
+// the next chunk is fetched into registers while the current one is multiplied, and the operands
+// of step k+1 are loaded while step k is multiplied (explicit register double buffering).
 struct TileBuf {
     double A[2][KC][TB];
     double B[2][KC][TB];
 };
 
+__device__ __forceinline__ uint32_t tile_row(uint32_t tx, int i) { return tx + 16u * (uint32_t)i; }
+
 __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __restrict__ P, uint32_t f, uint32_t rowA0,
                                            uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, uint32_t diag0, TileBuf& buf) {
     const uint32_t tid = threadIdx.x;
-    const uint32_t lk = tid >> 4, lr = (tid & 15) * 4;
-    const uint32_t r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
+    const uint32_t lk = tid >> 4, lr = (tid & 15) * 4;   // staging: column lk of the chunk, rows lr..lr+3
+    const uint32_t tx = tid & 15, c4 = (tid >> 4) * 4;   // compute mapping
     const uint32_t nchunks = (K + KC - 1) / KC;
-    double ra[4], rb[4];
+    double ra[4], rb[4], rdk = 0.0;
     auto gload = [&](uint32_t ch) {
         const uint32_t k = ch * KC + lk;
 #pragma unroll
         for (int u = 0; u < 4; u++) ra[u] = rb[u] = 0.0;
+        rdk = 0.0;
         if (k < K) {
             const double* col = P + (size_t)k * f;
-            const double dk = col[diag0 + k];
+            rdk = col[diag0 + k];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (lr + u < nrA) ra[u] = col[rowA0 + lr + u] * dk;
+                if (lr + u < nrA) ra[u] = col[rowA0 + lr + u];
                 if (lr + u < nrB) rb[u] = col[rowB0 + lr + u];
             }
         }
+    };
+    auto lds = [&](uint32_t b, int k, double (&a)[4], double (&bb)[4]) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            a[u] = buf.A[b][k][tile_row(tx, u)];
+            bb[u] = buf.B[b][k][c4 + u];
+        }
+    };
+    auto mac = [&](const double (&a)[4], const double (&bb)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fma(-a[i], bb[j], acc[i][j]);
     };
     if (nchunks) gload(0);
     for (uint32_t ch = 0; ch < nchunks; ch++) {
         const uint32_t b = ch & 1;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            buf.A[b][lk][lr + u] = ra[u];
+            buf.A[b][lk][lr + u] = ra[u] * rdk;
             buf.B[b][lk][lr + u] = rb[u];
         }
         __syncthreads();
         if (ch + 1 < nchunks) gload(ch + 1);
+        double a0[4], b0[4], a1[4], b1[4];
+        lds(b, 0, a0, b0);
 #pragma unroll
-        for (int k = 0; k < KC; k++) {
-            double a[4], bb[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                a[u] = buf.A[b][k][r4 + u];
-                bb[u] = buf.B[b][k][c4 + u];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fma(-a[i], bb[j], acc[i][j]);
+        for (int k = 0; k < KC; k += 2) {
+            lds(b, k + 1, a1, b1);
+            mac(a0, b0);
+            if (k + 2 < KC) lds(b, k + 2, a0, b0);
+            mac(a1, b1);
         }
     }
     __syncthreads();
 }
 
+#ifdef FK_DIAG_PROFILE
+#define FK_STAMP(k) do { if (threadIdx.x == 0) ((long long*)D.ubuf)[k] = clock64(); } while (0)
+#else
+#define FK_STAMP(k) do { } while (0)
+#endif
 // ---- 8-column register micro-kernels ---------------------------------------------------------------------
 // The pivot chain of a 64-column tile is latency bound (measured on B200: DFMA 8.6, LDS ~29,
 // rcp+2 Newton 47 cycles, a CTA barrier ~100), so the tile kernels work on micro-panels of 8
@@ -243,11 +264,14 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
         const uint32_t ii = e & 63, j = e >> 6;
         if (ii < nc && j <= ii) Cs[ii * kTsLd + j] = T[(size_t)j * f + ii];
     }
+    FK_STAMP(0);
     for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
         const uint32_t kw = min((uint32_t)MB, nc - k0);
         __syncthreads();
+        FK_STAMP(1 + 4 * (k0 / MB));
         double ll[MB][MB], inv[MB], piv[MB], y[MB];
         micro_ldl(Cs, kTsLd, k0, kw, ll, inv, piv);
+        FK_STAMP(2 + 4 * (k0 / MB));
         if (tid == 0) {
 #pragma unroll
             for (int k = 0; k < MB; k++)
@@ -272,22 +296,29 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
                 }
             }
         }
+        FK_STAMP(3 + 4 * (k0 / MB));
         __syncthreads();
+        FK_STAMP(4 + 4 * (k0 / MB));
         // rank-8 update of the rows below the micro-panel: C[i][j] -= sum_c l_ic * y_jc
         if (i >= k0 + MB && i < nc) {
             double l[MB];
 #pragma unroll
             for (int c = 0; c < MB; c++) l[c] = y[c] * inv[c];
             double* row = Cs + i * kTsLd;
+#pragma unroll 4
             for (uint32_t j = k0 + MB + q; j <= i; j += 4) {
                 const double* yj = Ys + j * (MB + 1);
-                double v = row[j];
+                double v0 = row[j], v1 = 0.0;  // two partial sums: half the dependent-FMA chain
 #pragma unroll
-                for (int c = 0; c < MB; c++) v = fma(-l[c], yj[c], v);
-                row[j] = v;
+                for (int c = 0; c < MB; c += 2) {
+                    v0 = fma(-l[c], yj[c], v0);
+                    v1 = fma(-l[c + 1], yj[c + 1], v1);
+                }
+                row[j] = v0 + v1;
             }
         }
     }
+    FK_STAMP(33);
 }
 
 // Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C L_kk^-T D^-1 by blocked
@@ -335,13 +366,16 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
 #pragma unroll
                 for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
             }
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t cp = k0 + MB + q; cp < nc; cp += 4) {
                 const double* Lr = Ls + cp * kTsLd + k0;
-                double v = row[cp];
+                double v0 = row[cp], v1 = 0.0;
 #pragma unroll
-                for (int c = 0; c < MB; c++) v = fma(-y[c], Lr[c], v);
-                row[cp] = v;
+                for (int c = 0; c < MB; c += 2) {
+                    v0 = fma(-y[c], Lr[c], v0);
+                    v1 = fma(-y[c + 1], Lr[c + 1], v1);
+                }
+                row[cp] = v0 + v1;
             }
             __syncwarp();
         }
@@ -360,6 +394,7 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
 __global__ void __launch_bounds__(kTileThreads)
 mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
     __shared__ TileBuf buf;
+    FK_STAMP(40);
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, row0 = t.y, tcol0 = t.z;
     const uint32_t nrA = (t.w & 0xFFu) + 1, nrB = ((t.w >> 8) & 0xFFu) + 1, K = ((t.w >> 16) & 0xFFu) + 1, pc0 = (t.w >> 24) * TB;
@@ -375,23 +410,28 @@ mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
         ld = r;
     }
     const bool diag_tile = row0 == tcol0;
-    const uint32_t tid = threadIdx.x, r4 = (tid & 15) * 4, c4 = (tid >> 4) * 4;
+    const uint32_t tid = threadIdx.x, tx = tid & 15, c4 = (tid >> 4) * 4;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const bool ok = r4 + i < nrA && c4 + j < nrB && (!diag_tile || r4 + i >= c4 + j);
-            acc[i][j] = ok ? T[(size_t)(c4 + j) * ld + r4 + i] : 0.0;
+            const uint32_t ri = tile_row(tx, i);
+            const bool ok = ri < nrA && c4 + j < nrB && (!diag_tile || ri >= c4 + j);
+            acc[i][j] = ok ? T[(size_t)(c4 + j) * ld + ri] : 0.0;
         }
+    FK_STAMP(41);
     tile_kloop(acc, P + (size_t)pc0 * f, f, row0, nrA, tcol0, nrB, K, pc0, buf);
+    FK_STAMP(42);
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const bool ok = r4 + i < nrA && c4 + j < nrB && (!diag_tile || r4 + i >= c4 + j);
-            if (ok) T[(size_t)(c4 + j) * ld + r4 + i] = acc[i][j];
+            const uint32_t ri = tile_row(tx, i);
+            const bool ok = ri < nrA && c4 + j < nrB && (!diag_tile || ri >= c4 + j);
+            if (ok) T[(size_t)(c4 + j) * ld + ri] = acc[i][j];
         }
+    FK_STAMP(43);
 }
 
 // ---- triangular solves ------------------------------------------------------------------------------------

@@ -1,4 +1,5 @@
 // Debug harness: runs mf_diag_kernel + mf_col_kernel on one 128x64 front, checks L D L^T = A and times them.
+#define FK_DIAG_PROFILE 1
 #include "../fiksi_b200/csrc/multifrontal.cu"
 #include <cstdio>
 using namespace fk;
@@ -11,9 +12,10 @@ int main(int argc, char** argv) {
     uint32_t *d32; cudaMalloc(&d32, 64); uint64_t* d64; cudaMalloc(&d64, 64);
     cudaMemcpy(d32, h32, 16, cudaMemcpyHostToDevice); cudaMemcpy(d64, &h_off, 8, cudaMemcpyHostToDevice);
     D.S = 1; D.c0 = d32; D.ns = d32 + 1; D.f = d32 + 2; D.winv_blk = d32 + 3; D.pan_off = d64;
-    cudaMalloc(&D.pan, A.size() * 8); cudaMalloc(&D.status, 4); cudaMemset(D.status, 0, 4);
-    uint4 tasks[2] = {{0, 0, 0, ns << 16}, {0, ns, 0, (f - ns) | (ns << 16)}};
-    uint4* dt; cudaMalloc(&dt, 32); cudaMemcpy(dt, tasks, 32, cudaMemcpyHostToDevice);
+    cudaMalloc(&D.pan, A.size() * 8); cudaMalloc(&D.ubuf, 64 * 8); cudaMalloc(&D.status, 4); cudaMemset(D.status, 0, 4);
+    uint4 tasks[3] = {{0, 0, 0, ns << 16}, {0, ns, 0, (f - ns) | (ns << 16)}, {0, ns, ns, (f - ns - 1) | ((f - ns - 1) << 8) | ((ns - 1) << 16)}};
+    uint4* dt; cudaMalloc(&dt, 48); cudaMemcpy(dt, tasks, 48, cudaMemcpyHostToDevice);
+    cudaMalloc(&D.upd, (f - ns) * (f - ns) * 8); cudaMemset(D.upd, 0, (f - ns) * (f - ns) * 8); cudaMemcpy(d64 + 1, &h_off, 8, cudaMemcpyHostToDevice); D.upd_off = d64 + 1;
     cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem);
     cudaEvent_t a, b, c; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventCreate(&c);
     for (int rep = 0; rep < 4; rep++) {
@@ -22,9 +24,13 @@ int main(int argc, char** argv) {
         mf_diag_kernel<<<1, kDiagThreads>>>(D, dt);
         cudaEventRecord(b);
         mf_col_kernel<<<1, kColThreads, kColSmem>>>(D, dt + 1);
-        cudaEventRecord(c); cudaEventSynchronize(c);
-        float m1, m2; cudaEventElapsedTime(&m1, a, b); cudaEventElapsedTime(&m2, b, c);
+        cudaEventRecord(c);
+        mf_rupd_kernel<<<1, kTileThreads>>>(D, dt + 2);
+        cudaEvent_t d3; cudaEventCreate(&d3); cudaEventRecord(d3); cudaEventSynchronize(d3);
+        float m1, m2, m3; cudaEventElapsedTime(&m1, a, b); cudaEventElapsedTime(&m2, b, c); cudaEventElapsedTime(&m3, c, d3);
+        printf("   rupd %.1f us\n", m3 * 1e3);
         printf("rep %d: diag %.1f us, col %.1f us (%s)\n", rep, m1 * 1e3, m2 * 1e3, cudaGetErrorString(cudaGetLastError()));
+        if (rep == 3) { long long st[48]; cudaMemcpy(st, D.ubuf, sizeof(st), cudaMemcpyDeviceToHost); for (int k = 41; k <= 43; k++) printf("  rupd stamp %2d: +%lld\n", k, st[k] - st[k - 1]); for (int k = 1; k <= 0; k++) printf("  stamp %2d: +%lld\n", k, st[k] - st[k - 1]); }
     }
     // empty-kernel launch overhead reference
     cudaEventRecord(a); mf_diag_kernel<<<0 + 1, kDiagThreads>>>(D, dt + 1 /* nc from task: harmless */); cudaEventRecord(b); cudaEventSynchronize(b);
