@@ -69,6 +69,16 @@ class Topology:
         out["info"] = {n: getattr(info, n) for n, _ in Info._fields_}
         return out
 
+    def batch_analyze(self, vars_, param, device=0):
+        """fk_batch_analyze: System::analyze's per-expression "independent" flags for n sketches
+        (UNSCALED variables / parameters; all variables free, all expressions)."""
+        vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+        param = np.ascontiguousarray(param, dtype=np.float64)
+        n = vars_.shape[0]
+        out = np.zeros((n, max(self.info["n_expr"], 1)), dtype=np.uint8)
+        check(lib().fk_batch_analyze(self._h, device, n, ptr(vars_, C.c_double), ptr(param, C.c_double), ptr(out, C.c_uint8)))
+        return out[:, :self.info["n_expr"]].astype(bool)
+
     def batch_solve(self, vars_, param, n_gpus=1):
         """fk_batch_solve on host buffers: vars[n][n_vars], param[n][n_expr] -> (free[n][n_free], reports)."""
         vars_ = np.ascontiguousarray(vars_, dtype=np.float64)

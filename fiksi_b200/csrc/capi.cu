@@ -272,6 +272,58 @@ int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, ui
     return FK_OK;
 }
 
+// ---- System::analyze on a batch -----------------------------------------------------------------
+int fk_batch_analyze(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param, uint8_t* independent) {
+    if (!topo || (n && (!vars || !independent || (!param && topo->t.n_expr)))) return fail(FK_ERR_INVALID, "null argument");
+    const int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    const fk::Topology& t = topo->t;
+    if (n == 0 || t.n_expr == 0) return FK_OK;
+    CU(cudaSetDevice(device));
+    std::vector<uint32_t> slot_var((size_t)t.n_expr * 8, 0);
+    for (uint32_t e = 0; e < t.n_expr; e++) {
+        uint32_t sv[8];
+        const int a = fk::expand_slots(t.kind[e], &t.idx[4 * (size_t)e], sv);
+        for (int k = 0; k < a; k++) slot_var[(size_t)e * 8 + k] = sv[k];
+    }
+    uint8_t *d_kind = nullptr, *d_out = nullptr;
+    uint32_t* d_slot = nullptr;
+    double *d_vars = nullptr, *d_param = nullptr;
+    int rc = FK_OK;
+    auto cleanup = [&] { cudaFree(d_kind); cudaFree(d_out); cudaFree(d_slot); cudaFree(d_vars); cudaFree(d_param); };
+#define AN_CU(call)                                   \
+    do {                                              \
+        cudaError_t e_ = (call);                      \
+        if (e_ != cudaSuccess) {                      \
+            cleanup();                                \
+            return cuda_fail(e_, #call);              \
+        }                                             \
+    } while (0)
+    AN_CU(cudaMalloc(&d_kind, t.n_expr));
+    AN_CU(cudaMalloc(&d_slot, slot_var.size() * sizeof(uint32_t)));
+    AN_CU(cudaMalloc(&d_vars, sizeof(double) * (size_t)n * t.n_vars));
+    AN_CU(cudaMalloc(&d_param, sizeof(double) * (size_t)n * t.n_expr));
+    AN_CU(cudaMalloc(&d_out, (size_t)n * t.n_expr));
+    AN_CU(cudaMemcpy(d_kind, t.kind.data(), t.n_expr, cudaMemcpyHostToDevice));
+    AN_CU(cudaMemcpy(d_slot, slot_var.data(), slot_var.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    AN_CU(cudaMemcpy(d_vars, vars, sizeof(double) * (size_t)n * t.n_vars, cudaMemcpyHostToDevice));
+    AN_CU(cudaMemcpy(d_param, param, sizeof(double) * (size_t)n * t.n_expr, cudaMemcpyHostToDevice));
+    const int e = fk::launch_batch_analyze(t.n_vars, t.n_expr, d_kind, d_slot, n, d_vars, d_param, d_out, nullptr);
+    if (e == (int)cudaErrorInvalidConfiguration) {
+        cleanup();
+        return fail(FK_ERR_TOO_LARGE, "the expression x variable matrix of one sketch does not fit shared memory");
+    }
+    if (e != 0) {
+        cleanup();
+        return cuda_fail((cudaError_t)e, "launch fk_batch_analyze_kernel");
+    }
+    AN_CU(cudaMemcpy(independent, d_out, (size_t)n * t.n_expr, cudaMemcpyDeviceToHost));
+#undef AN_CU
+    cleanup();
+    return rc;
+}
+
 // ---- device-resident batch plan -----------------------------------------------------------------
 int fk_batch_plan_create(const fk_topology* topo_c, uint32_t capacity, int device, fk_batch_plan** out) {
     fk_topology* topo = const_cast<fk_topology*>(topo_c);

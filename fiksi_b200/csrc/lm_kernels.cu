@@ -530,6 +530,112 @@ fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double
     }
 }
 
+// System::analyze on a batch: per sketch the dense Jacobian over ALL variables
+// (find_overconstraints, fiksi/src/analyze/numerical/mod.rs:123-147; gradient entries are ASSIGNED
+// per slot, expressions.rs:1003-1007) followed by the row-by-row Gauss-Jordan elimination with
+// tracked column swaps (incremental_gauss_jordan_elimination, :33-117).  One warp per sketch, the
+// matrix in shared memory, lanes across the columns; every floating-point operation is the
+// reference's (multiply, then subtract; one IEEE reciprocal per pivot row), so the flags are
+// bit-for-bit those of the CPU restatement.  out[sketch][row] = 1 iff the row increased the rank.
+constexpr int kAnalyzeWarps = 4;
+__global__ void __launch_bounds__(kAnalyzeWarps * 32)
+fk_batch_analyze_kernel(uint32_t n_vars, uint32_t n_expr, const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ slot_var,
+                        uint32_t n_sketches, const double* __restrict__ vars_all, const double* __restrict__ params_all,
+                        uint8_t* __restrict__ out, uint32_t warp_doubles, uint32_t warps_per_cta) {
+    extern __shared__ __align__(16) double smem_an[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sketch = blockIdx.x * warps_per_cta + warp;
+    if (warp >= warps_per_cta || sketch >= n_sketches) return;
+    const uint32_t m = n_expr, n = n_vars;
+    double* M = smem_an + (size_t)warp * warp_doubles;
+    uint32_t* ci = reinterpret_cast<uint32_t*>(M + (size_t)m * n);
+    uint32_t* inc = ci + n;
+    const double* vars = vars_all + (size_t)sketch * n_vars;
+    const double* params = params_all + (size_t)sketch * n_expr;
+    for (uint32_t e = lane; e < m * n; e += 32) M[e] = 0.0;
+    for (uint32_t k = lane; k < n; k += 32) ci[k] = k;
+    for (uint32_t r = lane; r < m; r += 32) inc[r] = 0;
+    __syncwarp();
+    for (uint32_t row = lane; row < m; row += 32) {
+        const int kind = (int)__ldg(kinds + row);
+        const int a = dev::arity_of(kind);
+        double v[8], g[8];
+        uint32_t var[8];
+#pragma unroll
+        for (int sl = 0; sl < 8; sl++) {
+            var[sl] = sl < a ? __ldg(slot_var + row * 8 + sl) : 0u;
+            v[sl] = sl < a ? __ldg(vars + var[sl]) : 0.0;
+        }
+        dev::eval_expression(kind, v, __ldg(params + row), g);
+#pragma unroll
+        for (int sl = 0; sl < 8; sl++)
+            if (sl < a) M[(size_t)row * n + var[sl]] = g[sl];
+    }
+    __syncwarp();
+    uint32_t current_col = 0;
+    const uint32_t nsteps = m < n ? m : n;
+    for (uint32_t row = 0; row < nsteps; row++) {
+        double* Mr = M + (size_t)row * n;
+        uint32_t rank = 0;
+        for (uint32_t row_idx = 0; row_idx < row; row_idx++) {
+            const double factor = Mr[ci[rank]];
+            __syncwarp();
+            const double* Mi = M + (size_t)row_idx * n;
+            for (uint32_t col = lane; col < n; col += 32) Mr[col] -= factor * Mi[col];
+            __syncwarp();
+            if (inc[row_idx]) rank++;
+        }
+        uint32_t found = 0xFFFFFFFFu;
+        for (uint32_t base = current_col; base < n; base += 32) {
+            const uint32_t idx = base + lane;
+            const bool ok = idx < n && fabs(Mr[ci[idx]]) > 1e-8;
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, ok);
+            if (b) {
+                found = base + (uint32_t)__ffs(b) - 1u;
+                break;
+            }
+        }
+        if (found == 0xFFFFFFFFu) continue;
+        if (lane == 0) {
+            const uint32_t tmp = ci[current_col];
+            ci[current_col] = ci[found];
+            ci[found] = tmp;
+        }
+        __syncwarp();
+        const uint32_t column_idx = ci[current_col];
+        const double inv = 1.0 / Mr[column_idx];
+        __syncwarp();
+        for (uint32_t col = lane; col < n; col += 32) Mr[col] *= inv;
+        __syncwarp();
+        for (uint32_t row_idx = 0; row_idx < row; row_idx++) {
+            double* Mi = M + (size_t)row_idx * n;
+            const double f2 = Mi[column_idx];
+            __syncwarp();
+            for (uint32_t col = lane; col < n; col += 32) Mi[col] -= f2 * Mr[col];
+            __syncwarp();
+        }
+        current_col++;
+        if (lane == 0) inc[row] = 1;
+        __syncwarp();
+    }
+    for (uint32_t r = lane; r < m; r += 32) out[(size_t)sketch * m + r] = (uint8_t)inc[r];
+}
+
+int launch_batch_analyze(uint32_t n_vars, uint32_t n_expr, const uint8_t* kinds, const uint32_t* slot_var, uint32_t n_sketches,
+                         const double* vars, const double* params, uint8_t* out, void* stream) {
+    if (n_sketches == 0 || n_expr == 0) return 0;
+    const size_t per_warp = (((size_t)n_expr * n_vars * sizeof(double) + ((size_t)n_vars + n_expr) * sizeof(uint32_t)) + 15) & ~(size_t)15;
+    if (per_warp > 200 * 1024) return (int)cudaErrorInvalidConfiguration;
+    const uint32_t wpc = (uint32_t)std::max<size_t>(1, std::min<size_t>(kAnalyzeWarps, (200 * 1024) / per_warp));
+    const size_t smem = per_warp * wpc;
+    cudaError_t e = cudaFuncSetAttribute(fk_batch_analyze_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const uint32_t grid = (n_sketches + wpc - 1) / wpc;
+    fk_batch_analyze_kernel<<<grid, kAnalyzeWarps * 32, smem, (cudaStream_t)stream>>>(n_vars, n_expr, kinds, slot_var, n_sketches, vars, params, out,
+                                                                                       (uint32_t)(per_warp / sizeof(double)), wpc);
+    return (int)cudaGetLastError();
+}
+
 const char* lm_kernel_name() { return "fk_batch_lm_kernel"; }
 
 // FP64 roofline denominator: 8 independent DFMA chains per thread, enough warps to fill every SMSP.

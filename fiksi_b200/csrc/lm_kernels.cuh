@@ -42,6 +42,10 @@ int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* v
                     double* free_out, fk_report* reports, void* stream);
 int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double* vars,
                       const double* params, double* out_r, double* out_j, int mode, void* stream);
+// System::analyze on a batch: kinds[n_expr], slot_var[n_expr][8] device tables; out[n][n_expr].
+// Returns cudaErrorInvalidConfiguration when one n_expr x n_vars matrix does not fit shared memory.
+int launch_batch_analyze(uint32_t n_vars, uint32_t n_expr, const uint8_t* kinds, const uint32_t* slot_var, uint32_t n_sketches,
+                         const double* vars, const double* params, uint8_t* out, void* stream);
 const char* lm_kernel_name();
 // DFMA throughput microbenchmark on the current device (TFLOP/s, 2 flops per DFMA).
 int measure_fp64_peak(double* tflops);

@@ -344,6 +344,42 @@ int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32_t cap,
     return FK_OK;
 }
 
+// == System::analyze (lib.rs:454-458, analyze/numerical/mod.rs:123-163): the dense Jacobian + the
+// incremental Gauss-Jordan run on the GPU (fk_batch_analyze with a batch of one); the host maps
+// dependent expressions back to their constraints (:149-160).
+int fk_system_analyze(fk_system* s, uint32_t* constraints, uint32_t cap, uint32_t* n_found) {
+    if (!s) return FK_ERR_INVALID;
+    if (n_found) *n_found = 0;
+    const uint32_t ne = (uint32_t)s->kind.size();
+    if (ne == 0) return FK_OK;
+    std::vector<uint32_t> all_vars(s->vars.size()), all_rows(ne);
+    for (uint32_t i = 0; i < all_vars.size(); i++) all_vars[i] = i;
+    for (uint32_t i = 0; i < ne; i++) all_rows[i] = i;
+    fk_problem p{};
+    p.n_vars = (uint32_t)s->vars.size(); p.vars = s->vars.data();
+    p.n_expr = ne; p.kind = s->kind.data(); p.idx = s->idx.data(); p.param = s->param.data();
+    p.n_free = p.n_vars; p.free_vars = all_vars.data();
+    p.n_rows = ne; p.rows = all_rows.data();
+    fk_topology* t = nullptr;
+    int rc = fk_topology_create(&p, &t);
+    if (rc != FK_OK) return rc;
+    std::vector<uint8_t> independent(ne, 0);
+    rc = fk_batch_analyze(t, 0, 1, s->vars.data(), s->param.data(), independent.data());
+    fk_topology_destroy(t);
+    if (rc != FK_OK) return rc;
+    std::vector<uint32_t> expr_to_constraint(ne, 0);
+    for (uint32_t c = 0; c < s->constrs.size(); c++)
+        for (uint8_t k = 0; k < s->constrs[c].n_expr; k++) expr_to_constraint[s->constrs[c].first_expr + k] = c;
+    uint32_t found = 0;
+    for (uint32_t e = 0; e < ne; e++)
+        if (!independent[e]) {
+            if (constraints && found < cap) constraints[found] = expr_to_constraint[e];
+            found++;
+        }
+    if (n_found) *n_found = found;
+    return FK_OK;
+}
+
 // Residual of every constraint at the current (unscaled) variables == ConstraintHandle::
 // calculate_residual (constraints/mod.rs:88-110): the expression residual, or the 2-norm of the two
 // equalities of a coincidence.  Evaluated by the K2 kernel.

@@ -82,6 +82,14 @@ class System:
         check(lib().fk_system_residuals(self._h, ptr(out, C.c_double)))
         return out[:n]
 
+    def analyze(self):
+        """System::analyze (lib.rs:454-458): ids of the constraints flagged as over-constraining."""
+        cap = max(1, 2 * self.num_constraints())
+        out = np.zeros(cap, dtype=np.uint32)
+        n = C.c_uint32(0)
+        check(lib().fk_system_analyze(self._h, ptr(out, C.c_uint32), cap, C.byref(n)))
+        return out[:n.value].tolist()
+
     def calculate_residual(self, c):
         return float(self.residuals()[c])
 

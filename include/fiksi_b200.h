@@ -234,6 +234,18 @@ FK_API void fk_host_free(void* p);
 FK_API int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream);
 FK_API int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_j, void* stream);
 
+/* ---- System::analyze: over-constraint detection -------------------------------------- */
+/* == find_overconstraints (fiksi/src/analyze/numerical/mod.rs:123-163) for n sketches sharing one
+ * topology: the dense Jacobian of ALL n_expr expressions with respect to ALL n_vars variables (the
+ * reference treats every variable as free here, :124) at the UNSCALED variables vars[n][n_vars] /
+ * parameters param[n][n_expr], reduced by incremental_gauss_jordan_elimination (:33-117, epsilon 1e-8).
+ * independent[n][n_expr] receives 1 for an expression that increases the rank, 0 for a dependent one
+ * (the constraint owning a dependent expression is what System::analyze reports as overconstrained).
+ * The topology's free set and row list are not used.  One warp per sketch on `device`; returns
+ * FK_ERR_TOO_LARGE when one n_expr x n_vars matrix does not fit shared memory. */
+FK_API int fk_batch_analyze(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param,
+                            uint8_t* independent);
+
 /* ---- fiksi::System mirror (host side above the solve boundary) ------------------------------- */
 /* Same operations, argument meaning and ordering rules as fiksi::System (fiksi/src/lib.rs:252-467):
  * elements and constraints are created in order and get consecutive ids; lines and circles are
@@ -275,6 +287,9 @@ FK_API int fk_system_set_variable(fk_system* s, uint32_t var, double value);    
 FK_API int fk_system_set_parameter(fk_system* s, uint32_t constraint, double value); /* update_parameter */
 FK_API int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved);
 FK_API int fk_system_residuals(fk_system* s, double* out /* [num_constraints] */); /* calculate_residual */
+/* == System::analyze (lib.rs:454-458): ids of the constraints that own a dependent expression, in
+ * expression order, up to `cap`; *n_found receives their number. */
+FK_API int fk_system_analyze(fk_system* s, uint32_t* constraints, uint32_t cap, uint32_t* n_found);
 FK_API uint32_t fk_system_num_components(const fk_system* s);
 FK_API int fk_system_component(const fk_system* s, uint32_t index, uint32_t* n_elements, uint32_t* elements,
                                uint32_t* n_constraints, uint32_t* constraints);

@@ -78,7 +78,7 @@ def lib() -> C.CDLL:
                      "orc_line_line_parallelism", "orc_line_line_perpendicularity",
                      "orc_line_circle_tangency", "orc_num_variables", "orc_num_expressions",
                      "orc_num_constraints", "orc_num_reports", "orc_num_components",
-                     "orc_component_sizes", "orc_prepared_count", "orc_element_variable"):
+                     "orc_component_sizes", "orc_prepared_count", "orc_element_variable", "orc_system_analyze"):
             getattr(L, name).restype = C.c_uint32
         _lib = L
     return _lib
@@ -260,6 +260,29 @@ def expr_slots(kind):
     return lib().orc_expr_slots(int(kind))
 
 
+def analyze(vars_, kind, idx, param):
+    """find_overconstraints' per-expression "independent" flags (analyze/numerical/mod.rs:123-147)."""
+    vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+    kind = np.ascontiguousarray(kind, dtype=np.uint8)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
+    param = np.ascontiguousarray(param, dtype=np.float64)
+    out = np.zeros(max(len(kind), 1), dtype=np.uint8)
+    lib().orc_analyze(C.c_uint32(len(vars_)), _p(vars_, C.c_double), C.c_uint32(len(kind)), _p(kind, C.c_uint8),
+                      _p(idx, C.c_uint32), _p(param, C.c_double), _p(out, C.c_uint8))
+    return out[:len(kind)].astype(bool)
+
+
+def gauss_jordan(matrix, column_indices=None):
+    """incremental_gauss_jordan_elimination (analyze/numerical/mod.rs:33-117): returns (reduced matrix,
+    column order, increases-rank flags)."""
+    m = np.array(matrix, dtype=np.float64, order="C")
+    nr, nc = m.shape
+    ci = np.arange(nc, dtype=np.uint64) if column_indices is None else np.array(column_indices, dtype=np.uint64)
+    out = np.zeros(max(nr, 1), dtype=np.uint8)
+    lib().orc_gauss_jordan(_p(m, C.c_double), C.c_uint64(nr), C.c_uint64(nc), _p(ci, C.c_uint64), _p(out, C.c_uint8))
+    return m, ci, out[:nr].astype(bool)
+
+
 def lm_solve(problem, free_values):
     """levenberg_marquardt on a flattened problem.  Returns (x, report dict, trace string)."""
     x = np.array(free_values, dtype=np.float64)
@@ -355,6 +378,12 @@ class System:
     def calculate_residual(self, c): return self._c("orc_calculate_residual", c)
     def num_constraints(self): return self._c("orc_num_constraints")
     def system_scale(self): return self._c("orc_system_scale")
+
+    def analyze(self):
+        """System::analyze (lib.rs:454-458): ids of the constraints flagged as over-constraining."""
+        out = np.zeros(max(self.num_constraints() * 2, 1), dtype=np.uint32)
+        n = self._c("orc_system_analyze", _p(out, C.c_uint32), C.c_uint32(len(out)))
+        return out[:n].tolist()
 
     def point(self, e):
         i = self.element_variable(e)

@@ -496,6 +496,69 @@ struct SolvingOptions {
     bool perturb = true;  // lib.rs:232-236
 };
 
+// ---- System::analyze: over-constraint detection (fiksi/src/analyze/numerical/mod.rs) ---------------
+// analyze/numerical/mod.rs:33-117.  Row-by-row Gauss-Jordan elimination with column swaps tracked in
+// `column_indices`; returns for every row whether it increased the rank.  Rows beyond
+// min(nrows, ncols) are never examined and stay `false` (as in the reference loop bound, :64).
+static const double ANALYZE_EPSILON = 1e-8;  // :8
+inline std::vector<uint8_t> incremental_gauss_jordan_elimination(std::vector<double>& matrix, size_t nrows, size_t ncols,
+                                                                 std::vector<size_t>& column_indices) {
+    const size_t constraints = nrows, variables = ncols;
+    std::vector<uint8_t> constraint_increases_rank(constraints, 0);
+    size_t current_col = 0;
+    for (size_t row = 0; row < std::min(constraints, variables); row++) {
+        size_t rank = 0;
+        for (size_t row_idx = 0; row_idx < row; row_idx++) {  // :66-77
+            const size_t column_idx = column_indices[rank];
+            const double factor = matrix[row * variables + column_idx];
+            for (size_t col = 0; col < variables; col++)
+                matrix[row * variables + col] -= factor * matrix[row_idx * variables + col];
+            if (constraint_increases_rank[row_idx]) rank += 1;
+        }
+        bool pivot_found = false;  // :81-90: first entry above EPSILON in the remaining column order
+        for (size_t idx = current_col; idx < variables; idx++) {
+            const size_t real_idx = column_indices[idx];
+            if (std::fabs(matrix[row * variables + real_idx]) > ANALYZE_EPSILON) {
+                std::swap(column_indices[current_col], column_indices[idx]);
+                pivot_found = true;
+                break;
+            }
+        }
+        if (!pivot_found) continue;  // :93-95
+        const double factor = matrix[row * variables + column_indices[current_col]];
+        for (size_t col = 0; col < variables; col++) matrix[row * variables + col] *= 1. / factor;  // :97-100
+        const size_t column_idx = column_indices[current_col];
+        for (size_t row_idx = 0; row_idx < row; row_idx++) {  // :104-110
+            const double f2 = matrix[row_idx * variables + column_idx];
+            for (size_t col = 0; col < variables; col++)
+                matrix[row_idx * variables + col] -= f2 * matrix[row * variables + col];
+        }
+        current_col += 1;
+        constraint_increases_rank[row] = 1;
+    }
+    return constraint_increases_rank;
+}
+
+// analyze/numerical/mod.rs:123-147: dense Jacobian over ALL variables (IdentityVariableMap: every
+// variable is free, fixed ones included, :124), gradient entries ASSIGNED per slot
+// (expressions.rs:1003-1007: a variable that fills two slots keeps the later slot's value), then
+// the elimination.  Returns the per-expression "independent" flags.
+inline std::vector<uint8_t> analyze_expressions(const std::vector<double>& variables, const std::vector<Expression>& expressions) {
+    const size_t m = expressions.size(), n = variables.size();
+    std::vector<double> jacobian(m * n, 0.0);
+    for (size_t row = 0; row < m; row++) {
+        uint32_t vi[8];
+        double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8];
+        const int a = variable_indices(expressions[row], vi);
+        for (int k = 0; k < a; k++) vals[k] = variables[vi[k]];
+        compute_residual_and_gradient(expressions[row], vals, grad);
+        for (int k = 0; k < a; k++) jacobian[row * n + vi[k]] = grad[k];
+    }
+    std::vector<size_t> column_pivots(n);
+    for (size_t k = 0; k < n; k++) column_pivots[k] = k;
+    return incremental_gauss_jordan_elimination(jacobian, m, n, column_pivots);
+}
+
 struct System {
     Graph graph;
     std::vector<EncodedElement> elements;
@@ -733,6 +796,20 @@ struct System {
                 variables[cp.free_variables[k]] = system_scale * free_values[k];
             last_reports.push_back(std::move(rep));
         });
+    }
+
+    // lib.rs:454-458 + analyze/numerical/mod.rs:149-160: constraints owning a dependent expression, in
+    // expression order (a two-expression constraint can be listed twice, as in the reference).
+    std::vector<uint32_t> analyze() const {
+        const std::vector<uint8_t> independent = analyze_expressions(variables, expressions);
+        std::vector<uint32_t> expression_to_constraint(expressions.size(), 0);
+        for (uint32_t c = 0; c < constraints.size(); c++)
+            for (int off = 0; off < valency_of(constraints[c].tag); off++)
+                expression_to_constraint[constraints[c].expressions_idx + off] = c;
+        std::vector<uint32_t> dependent;
+        for (size_t e = 0; e < independent.size(); e++)
+            if (!independent[e]) dependent.push_back(expression_to_constraint[e]);
+        return dependent;
     }
 };
 

@@ -305,6 +305,31 @@ ORC_API double orc_lm_solve_batch_uniform(const fk_problem* topo, uint32_t n, co
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- System::analyze ------------------------------------------------------------------------
+// analyze/numerical/mod.rs:123-147 on a flattened problem: all n_vars variables are columns, all
+// n_expr expressions are rows (in order).  out_independent[n_expr].
+ORC_API void orc_analyze(uint32_t n_vars, const double* vars, uint32_t n_expr, const uint8_t* kind, const uint32_t* idx,
+                         const double* param, uint8_t* out_independent) {
+    std::vector<double> v(vars, vars + n_vars);
+    std::vector<fiksi::Expression> ex(n_expr);
+    for (uint32_t e = 0; e < n_expr; e++) {
+        ex[e].kind = kind[e];
+        for (int k = 0; k < 4; k++) ex[e].idx[k] = idx[4 * e + k];
+        ex[e].param = param[e];
+    }
+    const std::vector<uint8_t> r = fiksi::analyze_expressions(v, ex);
+    memcpy(out_independent, r.data(), r.size());
+}
+// Gauss-Jordan on its own (row-major matrix in/out, column order in/out).
+ORC_API void orc_gauss_jordan(double* matrix, uint64_t nrows, uint64_t ncols, uint64_t* column_indices, uint8_t* out_increases_rank) {
+    std::vector<double> m(matrix, matrix + nrows * ncols);
+    std::vector<size_t> ci(column_indices, column_indices + ncols);
+    const std::vector<uint8_t> r = fiksi::incremental_gauss_jordan_elimination(m, nrows, ncols, ci);
+    memcpy(matrix, m.data(), m.size() * sizeof(double));
+    for (uint64_t k = 0; k < ncols; k++) column_indices[k] = ci[k];
+    memcpy(out_increases_rank, r.data(), r.size());
+}
+
 // ---- fiksi: System mirror ------------------------------------------------------------------
 ORC_API void* orc_system_new() { return new fiksi::System(); }
 ORC_API void orc_system_free(void* s) { delete (fiksi::System*)s; }
@@ -335,6 +360,11 @@ ORC_API uint32_t orc_element_variable(void* s, uint32_t e) { return SYS->element
 ORC_API void orc_set_parameter(void* s, uint32_t constraint, double v) { SYS->expressions[SYS->constraints[constraint].expressions_idx].param = v; }
 ORC_API double orc_calculate_residual(void* s, uint32_t c) { return SYS->calculate_residual(c); }
 ORC_API double orc_system_scale(void* s) { return SYS->calculate_system_scale(); }
+ORC_API uint32_t orc_system_analyze(void* s, uint32_t* out, uint32_t cap) {
+    const std::vector<uint32_t> d = SYS->analyze();
+    for (uint32_t k = 0; k < d.size() && k < cap; k++) out[k] = d[k];
+    return (uint32_t)d.size();
+}
 ORC_API void orc_solve(void* s, int perturb, int keep_artifacts) {
     fiksi::SolvingOptions o;
     o.perturb = perturb != 0;

@@ -41,3 +41,37 @@ def test_exit_reason_histogram_covers_non_convergence(oracle):
         hist += np.bincount(rep["exit_reason"], minlength=5)
     # converged, small step, stalled and the guard all occur; 100 outer iterations never does here
     assert hist[0] > 0 and hist[1] > 0 and hist[2] > 0 and hist[4] == N
+
+
+def test_batch_analyze_matches_oracle_bit_for_bit(oracle):
+    """SURVEY 8f-2: System::analyze on the GPU (fk_batch_analyze) vs the CPU restatement of
+    analyze/numerical/mod.rs on the same unscaled inputs: identical flags for every sketch."""
+    import fiksi_b200 as fk
+    from fiksi_b200 import workloads as wl
+    for maker, n in ((wl.truss, 257), (wl.cad_mix, 515)):
+        w = maker(n)
+        topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+        got = topo.batch_analyze(w.raw_vars, w.raw_param)
+        for s in range(0, n, 7):
+            ref = oracle.analyze(w.raw_vars[s], w.kind, w.idx, w.raw_param[s])
+            assert np.array_equal(got[s], ref), (maker.__name__, s)
+    # the truss: 37 rows, rank 37 of 40 columns -> every expression independent; duplicating a row flags it
+    w = wl.truss(8)
+    kind = np.concatenate([w.kind, w.kind[:1]]); idx = np.vstack([w.idx, w.idx[:1]])
+    param = np.hstack([w.raw_param, w.raw_param[:, :1]])
+    topo = fk.Topology.from_arrays(w.n_vars, kind, idx, w.free_vars, np.arange(len(kind), dtype=np.uint32))
+    got = topo.batch_analyze(w.raw_vars, param)
+    assert got[:, :-1].all() and not got[:, -1].any()
+
+
+def test_system_analyze_reference_scenario(oracle):
+    """fiksi/src/tests/basic.rs:90-112 through fk_system_analyze."""
+    import fiksi_b200.system as fsys
+    for System in (fsys.System, oracle.System):
+        s = System()
+        p = [s.add_point(0.123, 0.1), s.add_point(1.2, 0.0), s.add_point(-0.5, 1.1), s.add_point(1.599, 1.2)]
+        s.point_point_distance(p[0], p[1], 1.0); s.point_point_distance(p[0], p[2], 1.5)
+        s.point_point_distance(p[1], p[3], 1.7); s.point_point_distance(p[2], p[3], 1.2)
+        s.point_point_distance(p[1], p[2], 2.0)
+        last = s.point_point_distance(p[0], p[3], 5.0)
+        assert s.analyze() == [last]
