@@ -28,7 +28,10 @@ for name, w in wl.stress_families(n_each):
     err = 0.0
     if same.any() and name != "nan_coincident_points":
         err = float(np.max(np.max(np.abs(x[:sub][same] - xo[same]), axis=1) / np.max(np.abs(xo[same]), axis=1)))
-    rows.append({"family": name, "n": n_each, "tile": topo.info["tile"], "exit_hist": np.bincount(rep["exit_reason"], minlength=5).tolist(),
+    flagged = ~topo.batch_analyze(w.raw_vars, w.raw_param)          # System::analyze: dependent expressions
+    ref_flag = ~np.array([oracle.analyze(w.raw_vars[k], w.kind, w.idx, w.raw_param[k]) for k in range(min(sub, 64))])
+    rows.append({"family": name, "analyze_overconstrained_frac": float(flagged.any(axis=1).mean()),
+                 "analyze_equal_oracle": bool(np.array_equal(flagged[:len(ref_flag)], ref_flag)), "n": n_each, "tile": topo.info["tile"], "exit_hist": np.bincount(rep["exit_reason"], minlength=5).tolist(),
                  "mean_factorizations": float(rep["factorizations"].mean()), "gpu_e2e_sketches_per_s": n_each / dt,
                  "cpu_port_sketches_per_s": sub / secs, "trace_equal_frac": float(same.mean()), "max_rel_coord_err_where_equal": err})
     print(json.dumps(rows[-1]))
