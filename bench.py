@@ -341,6 +341,7 @@ def assembly_bandwidth(fk, wl, torch, device, peak):
 
 
 def large_system(fk, wl, hbm_peak, fp64_peak):
+    import numpy as np
     """Config 3: one 400x250 lattice (200,000 variables, 298,701 distance rows) through the global
     sparse path: time per LM solve, phase split, FP64 rate of the supernodal multifrontal LDL^T
     (K5), and the K1 assembly rate on its 31.4 MB (L2-resident) table."""
@@ -366,7 +367,28 @@ def large_system(fk, wl, hbm_peak, fp64_peak):
            "factor_frac_of_fp64_peak": (flops / (tm["factor_ms"] * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
            "eval_ms": eval_ms, "eval_algorithmic_bytes": info["eval_bytes"],
            "eval_gbs": info["eval_bytes"] / (eval_ms * 1e-3) / 1e9, "eval_frac_of_hbm_peak": info["eval_bytes"] / (eval_ms * 1e-3) / 1e9 / hbm_peak,
-           "note": "31.4 MB per evaluation is L2-resident; the CPU reference needs O(m n) scratch stores per factorisation at this size and is not timed"}
+           "note": "31.4 MB per evaluation is L2-resident; the CPU reference needs O(m n) scratch stores per factorisation "
+                   "(qr.rs:286-287) and is timed on the smaller lattices of `sweep` only (10,000 points take 67 s on one core)"}
+    # size sweep with the CPU reference algorithm (oracle port, 1 core: the reference is single-threaded) beside the GPU
+    import oracle
+    sweep = []
+    for nx, ny in ((32, 32), (64, 50)):
+        ws = wl.lattice(nx, ny)
+        vs, ps, _ = ws.prepare()
+        ts = fk.Topology.from_arrays(ws.n_vars, ws.kind, ws.idx, ws.free_vars, ws.rows)
+        xs0 = vs[0][ws.free_vars]
+        ts.lm_solve(vs[0], ps[0], xs0)
+        t0 = time.perf_counter()
+        xg, rg = ts.lm_solve(vs[0], ps[0], xs0)
+        gpu_s = time.perf_counter() - t0
+        op, keep = oracle.make_problem(vs[0], ws.kind, ws.idx, ps[0], ws.free_vars, ws.rows)
+        t0 = time.perf_counter()
+        xo, ro, _ = oracle.lm_solve(op, xs0)
+        cpu_s = time.perf_counter() - t0
+        sweep.append({"lattice": f"{nx}x{ny}", "variables": int(len(ws.free_vars)), "gpu_lm_solve_s": gpu_s, "cpu_port_lm_solve_s_1core": cpu_s,
+                      "same_trace": bool(rg["trace_hash"] == ro["trace_hash"]),
+                      "max_rel_coord_diff": float(np.max(np.abs(xg - xo)) / np.max(np.abs(xo)))})
+    out["sweep"] = sweep
     return out
 
 
