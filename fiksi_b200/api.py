@@ -69,6 +69,17 @@ class Topology:
         out["info"] = {n: getattr(info, n) for n, _ in Info._fields_}
         return out
 
+    def batch_solve_lbfgs(self, vars_, param, device=0):
+        """fk_batch_solve_lbfgs: Optimizer::LBfgs (fiksi/src/solve/lbfgs.rs) on a uniform batch."""
+        vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+        param = np.ascontiguousarray(param, dtype=np.float64)
+        n = vars_.shape[0]
+        out = np.zeros((n, self.info["n_free"]), dtype=np.float64)
+        reports = np.zeros(n, dtype=REPORT_DTYPE)
+        check(lib().fk_batch_solve_lbfgs(self._h, device, n, ptr(vars_, C.c_double), ptr(param, C.c_double), ptr(out, C.c_double),
+                                         reports.ctypes.data_as(C.POINTER(FkReport))))
+        return out, reports
+
     def batch_analyze(self, vars_, param, device=0):
         """fk_batch_analyze: System::analyze's per-expression "independent" flags for n sketches
         (UNSCALED variables / parameters; all variables free, all expressions)."""

@@ -272,6 +272,64 @@ int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, ui
     return FK_OK;
 }
 
+// ---- L-BFGS on a uniform batch -------------------------------------------------------------------
+int fk_batch_solve_lbfgs(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param, double* free_out,
+                         fk_report* reports) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    if (n == 0) return FK_OK;
+    if (!vars || !free_out || !reports || (!param && topo->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
+    const int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    const fk::Topology& t = topo->t;
+    if (t.path != 0) return fail(FK_ERR_TOO_LARGE, "L-BFGS is built for the shared-memory tile paths only");
+    CU(cudaSetDevice(device));
+    const fk::DevProgram* prog = nullptr;
+    int rc = topo->program_for(device, &prog);
+    if (rc != FK_OK) return rc;
+    std::vector<uint32_t> jcolptr(t.n_free + 1), jrow(t.jac_nnz);
+    for (uint32_t c = 0; c <= t.n_free; c++) jcolptr[c] = t.aug_colptr[c] - c;
+    for (uint32_t c = 0; c < t.n_free; c++)
+        for (uint32_t q = t.aug_colptr[c]; q + 1 < t.aug_colptr[c + 1]; q++) jrow[q - c] = t.aug_rowidx[q];
+    uint32_t *d_cp = nullptr, *d_jr = nullptr;
+    double *d_vars = nullptr, *d_param = nullptr, *d_out = nullptr;
+    fk_report* d_rep = nullptr;
+    auto cleanup = [&] { cudaFree(d_cp); cudaFree(d_jr); cudaFree(d_vars); cudaFree(d_param); cudaFree(d_out); cudaFree(d_rep); };
+#define LB_CU(call)                                   \
+    do {                                              \
+        cudaError_t e_ = (call);                      \
+        if (e_ != cudaSuccess) {                      \
+            cleanup();                                \
+            return cuda_fail(e_, #call);              \
+        }                                             \
+    } while (0)
+    LB_CU(cudaMalloc(&d_cp, jcolptr.size() * sizeof(uint32_t)));
+    LB_CU(cudaMalloc(&d_jr, std::max<size_t>(1, jrow.size()) * sizeof(uint32_t)));
+    LB_CU(cudaMalloc(&d_vars, sizeof(double) * std::max<size_t>(1, (size_t)n * t.n_vars)));
+    LB_CU(cudaMalloc(&d_param, sizeof(double) * std::max<size_t>(1, (size_t)n * t.n_expr)));
+    LB_CU(cudaMalloc(&d_out, sizeof(double) * std::max<size_t>(1, (size_t)n * t.n_free)));
+    LB_CU(cudaMalloc(&d_rep, sizeof(fk_report) * (size_t)n));
+    LB_CU(cudaMemcpy(d_cp, jcolptr.data(), jcolptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!jrow.empty()) LB_CU(cudaMemcpy(d_jr, jrow.data(), jrow.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (t.n_vars) LB_CU(cudaMemcpy(d_vars, vars, sizeof(double) * (size_t)n * t.n_vars, cudaMemcpyHostToDevice));
+    if (t.n_expr) LB_CU(cudaMemcpy(d_param, param, sizeof(double) * (size_t)n * t.n_expr, cudaMemcpyHostToDevice));
+    const int e = fk::launch_batch_lbfgs(*prog, d_cp, d_jr, n, d_vars, d_param, d_out, d_rep, nullptr);
+    if (e == (int)cudaErrorInvalidConfiguration) {
+        cleanup();
+        return fail(FK_ERR_TOO_LARGE, "the L-BFGS state of one sketch does not fit the tile path");
+    }
+    if (e != 0) {
+        cleanup();
+        return cuda_fail((cudaError_t)e, "launch fk_batch_lbfgs_kernel");
+    }
+    if (t.n_free) LB_CU(cudaMemcpy(free_out, d_out, sizeof(double) * (size_t)n * t.n_free, cudaMemcpyDeviceToHost));
+    LB_CU(cudaMemcpy(reports, d_rep, sizeof(fk_report) * (size_t)n, cudaMemcpyDeviceToHost));
+#undef LB_CU
+    cleanup();
+    return FK_OK;
+}
+
 // ---- System::analyze on a batch -----------------------------------------------------------------
 int fk_batch_analyze(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param, uint8_t* independent) {
     if (!topo || (n && (!vars || !independent || (!param && topo->t.n_expr)))) return fail(FK_ERR_INVALID, "null argument");

@@ -37,6 +37,10 @@ __host__ __device__ inline uint32_t lm_smem_doubles(uint32_t n, uint32_t m, uint
     return 3u * n + (n > m ? n : m) + jnnz + (jnnz > lnnz ? jnnz : lnnz);
 }
 
+// Shared-memory doubles of one sketch in the L-BFGS kernel: x, xs, g, direction (4n) + s / y history
+// (10n) + residuals (m) + Jacobian values (jnnz) + rho, alpha (10).
+__host__ __device__ inline uint32_t lbfgs_smem_doubles(uint32_t n, uint32_t m, uint32_t jnnz) { return 14u * n + m + jnnz + 10u; }
+
 // Launchers (defined in lm_kernels.cu).  `stream` is a cudaStream_t.
 int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                     double* free_out, fk_report* reports, void* stream);
@@ -46,6 +50,10 @@ int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double*
 // Returns cudaErrorInvalidConfiguration when one n_expr x n_vars matrix does not fit shared memory.
 int launch_batch_analyze(uint32_t n_vars, uint32_t n_expr, const uint8_t* kinds, const uint32_t* slot_var, uint32_t n_sketches,
                          const double* vars, const double* params, uint8_t* out, void* stream);
+// L-BFGS on a uniform batch (tile paths with 8 / 16 / 32 lanes only); d_jcolptr[n+1], d_jrow[jnnz]: CSC
+// of the Jacobian.  Returns cudaErrorInvalidConfiguration when the topology does not take a tile path.
+int launch_batch_lbfgs(const DevProgram& prog, const uint32_t* d_jcolptr, const uint32_t* d_jrow, uint32_t n_sketches, const double* vars,
+                       const double* params, double* free_out, fk_report* reports, void* stream);
 const char* lm_kernel_name();
 // DFMA throughput microbenchmark on the current device (TFLOP/s, 2 flops per DFMA).
 int measure_fp64_peak(double* tflops);

@@ -234,6 +234,18 @@ FK_API void fk_host_free(void* p);
 FK_API int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream);
 FK_API int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_j, void* stream);
 
+/* ---- L-BFGS ----------------------------------------------------------------------------- */
+/* == lbfgs(problem, variables), fiksi/src/solve/lbfgs.rs:20 (Optimizer::LBfgs, assemble/mod.rs:155-157)
+ * for n sketches sharing one topology: vars[n][n_vars] / param[n][n_expr] scaled and perturbed exactly
+ * as for the LM entry points, free_out[n][n_free].  reports[k]: exit_reason 0 initial sum of squares
+ * < 1e-4 (lbfgs.rs:53-56), 1 change < 1e-10 (:177-179), 2 sum of squares < 1e-6 (:180-182), 3 100
+ * iterations, 4 guard (the reference's unbounded bisection loop, :338-351, would not return);
+ * outer_iters = line searches, factorizations = residual+Jacobian evaluations, ssr, lambda = last step
+ * size, trace_hash = h*31 + evaluations per line search.  Shared-memory tile paths only
+ * (FK_ERR_TOO_LARGE otherwise). */
+FK_API int fk_batch_solve_lbfgs(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param,
+                                double* free_out, fk_report* reports);
+
 /* ---- System::analyze: over-constraint detection -------------------------------------- */
 /* == find_overconstraints (fiksi/src/analyze/numerical/mod.rs:123-163) for n sketches sharing one
  * topology: the dense Jacobian of ALL n_expr expressions with respect to ALL n_vars variables (the

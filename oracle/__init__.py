@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         L.orc_system_scale.restype = C.c_double
         L.orc_prepared_problem.restype = C.c_double
         L.orc_lm_solve_batch_uniform.restype = C.c_double
+        L.orc_lbfgs_solve_batch_uniform.restype = C.c_double
         L.orc_system_new.restype = C.c_void_p
         L.orc_prepare.restype = C.c_void_p
         L.orc_sym_build.restype = C.c_void_p
@@ -258,6 +259,25 @@ def expr_eval(kind, param, vars8):
 
 def expr_slots(kind):
     return lib().orc_expr_slots(int(kind))
+
+
+def lbfgs_solve(problem, free_values):
+    """lbfgs(problem, variables) (fiksi/src/solve/lbfgs.rs:20): returns (x, report dict)."""
+    x = np.array(free_values, dtype=np.float64)
+    rep = FkReport()
+    lib().orc_lbfgs_solve(C.byref(problem), _p(x, C.c_double), C.byref(rep))
+    return x, report_dict(rep)
+
+
+def lbfgs_solve_batch_uniform(topo_problem, vars_, param, threads=1):
+    vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
+    param = np.ascontiguousarray(param, dtype=np.float64)
+    n = vars_.shape[0]
+    out = np.zeros((n, topo_problem.n_free), dtype=np.float64)
+    reports = np.zeros(n, dtype=REPORT_DTYPE)
+    secs = lib().orc_lbfgs_solve_batch_uniform(C.byref(topo_problem), n, _p(vars_, C.c_double), _p(param, C.c_double),
+                                               _p(out, C.c_double), reports.ctypes.data_as(C.POINTER(FkReport)), threads)
+    return out, reports, secs
 
 
 def analyze(vars_, kind, idx, param):

@@ -290,6 +290,24 @@ struct Subsystem {
             residuals[row] = compute_residual_and_gradient(e, vals, grad);
         }
     }
+    // subsystem.rs:106-124 + expressions.rs:962-1090: dense row-major Jacobian (rows x free variables).
+    // Entries are ASSIGNED per slot (expressions.rs:1003-1007) and the buffer is never cleared, so a
+    // variable that fills two slots of a row keeps the later slot's value.
+    void calculate_residuals_and_jacobian(const double* variables, double* residuals, double* jacobian) const {
+        uint32_t vi[8];
+        double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t n = free_variables.size();
+        for (size_t row = 0; row < expressions.size(); row++) {
+            const Expression& e = all_expressions[expressions[row]];
+            int a = variable_indices(e, vi);
+            for (int k = 0; k < a; k++) vals[k] = value_of(vi[k], variables);
+            residuals[row] = compute_residual_and_gradient(e, vals, grad);
+            for (int k = 0; k < a; k++) {
+                int32_t f = var_to_free[vi[k]];
+                if (f >= 0) jacobian[row * n + (size_t)f] = grad[k];
+            }
+        }
+    }
     // subsystem.rs:126-166
     void calculate_residuals_and_sparse_jacobian(const double* variables, double* residuals,
                                                  solvi::TripletMat& jac) const {
@@ -495,6 +513,215 @@ inline uint8_t valency_of(uint8_t constraint_tag) { return constraint_tag == 0 ?
 struct SolvingOptions {
     bool perturb = true;  // lib.rs:232-236
 };
+
+// ---- L-BFGS (fiksi/src/solve/lbfgs.rs) -------------------------------------------------------------
+// Exit reasons of the restatement (the reference returns `()`):
+enum LbfgsExit : uint32_t {
+    LBFGS_EXIT_INITIAL = 0,     // initial sum of squares < 1e-4              lbfgs.rs:53-56
+    LBFGS_EXIT_CONVERGED = 1,   // |change of the sum of squares| < 1e-10     lbfgs.rs:177-179
+    LBFGS_EXIT_RESIDUAL = 2,    // sum of squares < 1e-6                      lbfgs.rs:180-182
+    LBFGS_EXIT_MAX_ITER = 3,    // 100 iterations                             lbfgs.rs:77
+    LBFGS_EXIT_GUARD = 4,       // the unbounded bisection of `update` (U3, lbfgs.rs:338-351) exceeded 200 steps:
+                                // the reference would keep spinning (NaN / non-descent direction)
+};
+
+struct LbfgsReport {
+    uint32_t exit_reason = 0;
+    uint32_t iterations = 0;    // line searches performed
+    uint32_t evaluations = 0;   // calls of calculate_phi (residual + Jacobian + gradient evaluations)
+    double ssr = 0.0;           // sum of squared residuals at the returned variables
+    double step = 0.0;          // last accepted step size
+    uint64_t trace_hash = 0;    // h = 31 h + (evaluations of the line search) per iteration
+};
+
+namespace lbfgs_detail {
+struct Param { double p, phi, dphi; };  // lbfgs.rs:249-256
+
+// lbfgs.rs:201-212: gradient[i] = sum over rows c (ascending) of J[c][i] * r[c], starting from 0.0
+inline void compute_gradient(const double* jacobian, const double* residuals, double* gradient, size_t nvars, size_t nexpr) {
+    for (size_t i = 0; i < nvars; i++) {
+        double g = 0.0;
+        for (size_t c = 0; c < nexpr; c++) g += jacobian[c * nvars + i] * residuals[c];
+        gradient[i] = g;
+    }
+}
+inline double dot_product(const double* a, const double* b, size_t n) {  // lbfgs.rs:214-216 (sequential sum from 0.0)
+    double s = 0.0;
+    for (size_t i = 0; i < n; i++) s += a[i] * b[i];
+    return s;
+}
+inline double ssq_seq(const double* v, size_t n) {  // utils.rs:12-20
+    double s = 0.0;
+    for (size_t i = 0; i < n; i++) s += v[i] * v[i];
+    return s;
+}
+
+struct LineSearch {  // lbfgs.rs:218-506 (mod hager_zhang)
+    static constexpr double DELTA = 1e-4, SIGMA = 0.9, EPSILON = 1e-6, THETA = 0.5, GAMMA = 0.66;
+    static constexpr int MAX_ITERATIONS = 100, U3_GUARD = 200;
+    const Subsystem& problem;
+    const double* variables;
+    double* variables_scratch;
+    double* jacobian;
+    double* residuals;
+    double* gradient;
+    const double* direction;
+    size_t n, m;
+    double phi0 = 0, dphi0 = 0;
+    uint32_t evaluations = 0;
+    bool guard_hit = false;
+
+    Param calculate_phi(double p) {  // :270-286
+        for (size_t idx = 0; idx < n; idx++) variables_scratch[idx] = variables[idx] + p * direction[idx];
+        problem.calculate_residuals_and_jacobian(variables_scratch, residuals, jacobian);
+        compute_gradient(jacobian, residuals, gradient, n, m);
+        evaluations++;
+        Param out{p, ssq_seq(residuals, m), dot_product(gradient, direction, n)};
+#ifdef FK_LBFGS_DEBUG
+        fprintf(stderr, "cpu p=%a phi=%a dphi=%a\n", p, out.phi, out.dphi);
+#endif
+        return out;
+    }
+    static double secant(Param a, Param b) { return (a.p * b.dphi - b.p * a.dphi) / (b.dphi - a.dphi); }  // :291-293
+    bool satisfies_wolfe(Param c) const {  // :307-322
+        if ((c.phi <= phi0 + c.p * (DELTA * dphi0)) && (c.dphi >= SIGMA * dphi0)) return true;
+        if (c.phi <= phi0 + EPSILON && (2. * DELTA - 1.) * dphi0 >= c.dphi && c.dphi >= SIGMA * dphi0) return true;
+        return false;
+    }
+    void update(Param a, Param b, Param c, Param& oa, Param& ob) {  // :325-353
+        if (c.p < a.p || c.p > b.p) { oa = a; ob = b; return; }       // U0
+        if (c.dphi >= 0.) { oa = a; ob = c; return; }                  // U1
+        if (c.phi <= phi0 + EPSILON) { oa = c; ob = b; return; }       // U2
+        Param aa = a, bb = c;                                          // U3
+        for (int it = 0;; it++) {
+            if (it >= U3_GUARD) { guard_hit = true; oa = aa; ob = bb; return; }
+            Param d = calculate_phi((1. - THETA) * aa.p + THETA * bb.p);
+            if (d.dphi >= 0.) { oa = aa; ob = d; return; }
+            else if (d.phi <= phi0 + EPSILON) aa = d;
+            else bb = d;
+        }
+    }
+    // :360-398.  Returns true (and c_out) when a point satisfying the Wolfe conditions was found.
+    bool secant2(Param a, Param b, Param& c_out, Param& oa, Param& ob) {
+        Param c = calculate_phi(secant(a, b));
+        if (satisfies_wolfe(c)) { c_out = c; return true; }
+        Param a_, b_;
+        update(a, b, c, a_, b_);
+        if (guard_hit) { oa = a_; ob = b_; return false; }
+        if (c.p == b_.p) {
+            Param c_ = calculate_phi(secant(b, b_));
+            if (satisfies_wolfe(c_)) { c_out = c_; return true; }
+            update(a_, b_, c_, oa, ob);
+            return false;
+        } else if (c.p == a_.p) {
+            Param c_ = calculate_phi(secant(a, a_));
+            if (satisfies_wolfe(c_)) { c_out = c_; return true; }
+            update(a_, b_, c_, oa, ob);
+            return false;
+        }
+        oa = a_; ob = b_;
+        return false;
+    }
+    Param run() {  // :447-458, bracket :401-410, search :414-443
+        Param c = calculate_phi(1.);
+        if (satisfies_wolfe(c)) return c;
+        Param a{0., phi0, dphi0};
+        Param b = calculate_phi(5.);
+        for (int it = 0; it < MAX_ITERATIONS; it++) {
+            Param found, a_, b_;
+            if (secant2(a, b, found, a_, b_)) return found;
+            if (guard_hit) break;
+            if (b_.p - a_.p > GAMMA * (b.p - a.p)) {
+                c = calculate_phi(0.5 * (a.p + b.p));
+                if (satisfies_wolfe(c)) return c;
+                Param na, nb;
+                update(a, b, c, na, nb);
+                a = na; b = nb;
+                if (guard_hit) break;
+            } else {
+                a = a_; b = b_;
+            }
+        }
+        return calculate_phi(c.p);  // :440-442: leave the buffers at c
+    }
+};
+}  // namespace lbfgs_detail
+
+// fiksi/src/solve/lbfgs.rs:20-195
+inline void lbfgs(const Subsystem& problem, double* variables, LbfgsReport& rep) {
+    using namespace lbfgs_detail;
+    const int MAX_HISTORY = 5, MAX_ITERATIONS = 100;
+    const double CONVERGENCE_THRESHOLD = 1e-10, RESIDUAL_THRESHOLD = 1e-6;
+    const size_t n = problem.num_variables(), m = problem.num_residuals();
+    std::vector<double> residuals(m, 0.), jacobian(m * n, 0.), gradient(n, 0.);
+    problem.calculate_residuals_and_jacobian(variables, residuals.data(), jacobian.data());
+    rep = LbfgsReport();
+    rep.evaluations = 1;
+    double prev_ssr = ssq_seq(residuals.data(), m);
+    rep.ssr = prev_ssr;
+    if (prev_ssr < 1e-4) { rep.exit_reason = LBFGS_EXIT_INITIAL; return; }
+    compute_gradient(jacobian.data(), residuals.data(), gradient.data(), n, m);
+    std::vector<double> s_history(n * MAX_HISTORY, 0.), y_history(n * MAX_HISTORY, 0.), rho_history(MAX_HISTORY, 0.), alpha(MAX_HISTORY, 0.);
+    std::vector<double> direction(n, 0.), variables_scratch(n, 0.);
+    rep.exit_reason = LBFGS_EXIT_MAX_ITER;
+    for (int k = 0; k < MAX_ITERATIONS; k++) {
+        const int history_len = std::min(k, MAX_HISTORY);
+        for (size_t j = 0; j < n; j++) direction[j] = gradient[j];
+        for (int i = history_len - 1; i >= 0; i--) {  // :83-99
+            const size_t h = (size_t)((k + i) % MAX_HISTORY);
+            const double* s_i = &s_history[h * n];
+            const double* y_i = &y_history[h * n];
+            double dp = 0.;
+            for (size_t j = 0; j < n; j++) dp += s_i[j] * direction[j];
+            alpha[i] = rho_history[h] * dp;
+            for (size_t j = 0; j < n; j++) direction[j] -= alpha[i] * y_i[j];
+        }
+        if (k > 0) {  // :101-121
+            const size_t hp = (size_t)((k - 1) % MAX_HISTORY);
+            double s_dot_y = 0., y_dot_y = 0.;
+            for (size_t j = 0; j < n; j++) {
+                s_dot_y += s_history[hp * n + j] * y_history[hp * n + j];
+                y_dot_y += y_history[hp * n + j] * y_history[hp * n + j];
+            }
+            if (y_dot_y > 0.) {
+                const double scale = s_dot_y / y_dot_y;
+                for (size_t j = 0; j < n; j++) direction[j] *= scale;
+            }
+        }
+        for (int i = 0; i < history_len; i++) {  // :123-139
+            const size_t h = (size_t)((k + i) % MAX_HISTORY);
+            double dp = 0.;
+            for (size_t j = 0; j < n; j++) dp += y_history[h * n + j] * direction[j];
+            const double beta = rho_history[h] * dp;
+            for (size_t j = 0; j < n; j++) direction[j] += s_history[h * n + j] * (alpha[i] - beta);
+        }
+        for (size_t j = 0; j < n; j++) direction[j] *= -1.;  // :141-143
+        const size_t h = (size_t)(k % MAX_HISTORY);
+        for (size_t j = 0; j < n; j++) y_history[h * n + j] = gradient[j];  // :149-150
+        for (size_t j = 0; j < n; j++) variables_scratch[j] = variables[j];
+        LineSearch ls{problem, variables, variables_scratch.data(), jacobian.data(), residuals.data(), gradient.data(), direction.data(), n, m};
+        ls.phi0 = prev_ssr;                                              // :489
+        ls.dphi0 = dot_product(gradient.data(), direction.data(), n);    // :490
+        const Param res = ls.run();
+        rep.evaluations += ls.evaluations;
+        rep.iterations++;
+        rep.trace_hash = rep.trace_hash * 31u + ls.evaluations;
+        for (size_t j = 0; j < n; j++) variables[j] = variables_scratch[j];  // :169
+        rep.step = res.p;
+        rep.ssr = res.phi;
+        if (ls.guard_hit) { rep.exit_reason = LBFGS_EXIT_GUARD; return; }
+        double s_dot_y = 0.;  // :171-180
+        for (size_t i = 0; i < n; i++) {
+            s_history[h * n + i] = res.p * direction[i];
+            y_history[h * n + i] = gradient[i] - y_history[h * n + i];
+            s_dot_y += s_history[h * n + i] * y_history[h * n + i];
+        }
+        rho_history[h] = 1.0 / s_dot_y;
+        if (std::fabs(prev_ssr - res.phi) < CONVERGENCE_THRESHOLD) { rep.exit_reason = LBFGS_EXIT_CONVERGED; return; }
+        if (res.phi < RESIDUAL_THRESHOLD) { rep.exit_reason = LBFGS_EXIT_RESIDUAL; return; }
+        prev_ssr = res.phi;
+    }
+}
 
 // ---- System::analyze: over-constraint detection (fiksi/src/analyze/numerical/mod.rs) ---------------
 // analyze/numerical/mod.rs:33-117.  Row-by-row Gauss-Jordan elimination with column swaps tracked in

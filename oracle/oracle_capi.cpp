@@ -305,6 +305,51 @@ ORC_API double orc_lm_solve_batch_uniform(const fk_problem* topo, uint32_t n, co
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- L-BFGS -----------------------------------------------------------------------------------
+// == lbfgs(problem, variables) (fiksi/src/solve/lbfgs.rs:20).  report: exit_reason = LbfgsExit,
+// outer_iters = line searches, factorizations = function evaluations, ssr, lambda = last step size,
+// trace_hash = rolling hash of the evaluations per line search.
+ORC_API int orc_lbfgs_solve(const fk_problem* p, double* free_values, fk_report* report) {
+    std::vector<fiksi::Expression> ex(p->n_expr);
+    for (uint32_t e = 0; e < p->n_expr; e++) {
+        ex[e].kind = p->kind[e];
+        for (int k = 0; k < 4; k++) ex[e].idx[k] = p->idx[4 * e + k];
+        ex[e].param = p->param[e];
+    }
+    std::vector<uint32_t> fv(p->free_vars, p->free_vars + p->n_free), rows(p->rows, p->rows + p->n_rows);
+    fiksi::Subsystem sub(p->vars, p->n_vars, ex.data(), fv, rows);
+    fiksi::LbfgsReport rep;
+    fiksi::lbfgs(sub, free_values, rep);
+    if (report) {
+        report->exit_reason = rep.exit_reason; report->outer_iters = rep.iterations; report->factorizations = rep.evaluations;
+        report->accepted = rep.iterations; report->ssr = rep.ssr; report->lambda = rep.step; report->trace_hash = rep.trace_hash;
+    }
+    return 0;
+}
+// Uniform batch on `threads` host threads; returns seconds.
+ORC_API double orc_lbfgs_solve_batch_uniform(const fk_problem* topo, uint32_t n, const double* vars, const double* param,
+                                             double* free_out, fk_report* reports, int threads) {
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t s = lo; s < hi; s++) {
+            fk_problem p = *topo;
+            p.vars = vars + (size_t)s * topo->n_vars;
+            p.param = param + (size_t)s * topo->n_expr;
+            double* x = free_out + (size_t)s * topo->n_free;
+            for (uint32_t k = 0; k < topo->n_free; k++) x[k] = p.vars[topo->free_vars[k]];
+            orc_lbfgs_solve(&p, x, reports + s);
+        }
+    };
+    if (threads <= 1) work(0, n);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back(work, (uint32_t)((uint64_t)n * t / threads), (uint32_t)((uint64_t)n * (t + 1) / threads));
+        for (auto& th : pool) th.join();
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 // ---- System::analyze ------------------------------------------------------------------------
 // analyze/numerical/mod.rs:123-147 on a flattened problem: all n_vars variables are columns, all
 // n_expr expressions are rows (in order).  out_independent[n_expr].
