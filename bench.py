@@ -263,6 +263,10 @@ def main():
                 line["large_system"] = large_system(fk, wl, peak, line["fp64"].get("peak_tflops"))
             except Exception as e:  # noqa: BLE001
                 line["large_system"] = {"error": str(e)}
+            try:
+                line["lbfgs"] = lbfgs_side(fk, wl, local_rank)
+            except Exception as e:  # noqa: BLE001
+                line["lbfgs"] = {"error": str(e)}
             cores = os.cpu_count() or 1
             n_cpu = 65536
             rate, secs, _ = cpu_reference_run(n_cpu, cores)
@@ -273,6 +277,31 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def lbfgs_side(fk, wl, device):
+    """the reference's second optimizer (fiksi/src/solve/lbfgs.rs) on the same truss batch,
+    through the host-buffer C-ABI call (H2D + D2H inside), beside the CPU restatement."""
+    import numpy as np
+    import oracle
+    n = 65536
+    w = wl.truss(n)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    topo.batch_solve_lbfgs(v[:1024], p[:1024], device)
+    t0 = time.perf_counter()
+    x, rep = topo.batch_solve_lbfgs(v, p, device)
+    gpu_s = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    ns = 4096
+    op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+    xo, ro, cpu_s = oracle.lbfgs_solve_batch_uniform(op, v[:ns], p[:ns], threads=cores)
+    same = (rep["trace_hash"][:ns] == ro["trace_hash"]) & (rep["exit_reason"][:ns] == ro["exit_reason"])
+    return {"workload": "configs[1] truss batch, Optimizer::LBfgs", "gpu_e2e_sketches_per_s": n / gpu_s,
+            "mean_line_searches": float(rep["outer_iters"].mean()), "mean_evaluations": float(rep["factorizations"].mean()),
+            "fraction_residual_exit": float(np.mean(rep["exit_reason"] == 2)),
+            "cpu_port_sketches_per_s": ns / cpu_s, "cpu_cores": cores, "cpu_sample": ns,
+            "trace_equal_frac": float(same.mean()), "max_abs_coord_diff": float(np.max(np.abs(x[:ns] - xo)))}
 
 
 def assembly_bandwidth(fk, wl, torch, device, peak):
