@@ -169,6 +169,9 @@ class BatchPlan:
     def run(self, stream=0):
         check(lib().fk_batch_plan_run(self._h, C.c_void_p(stream)))
 
+    def run_lbfgs(self, stream=0):
+        check(lib().fk_batch_plan_run_lbfgs(self._h, C.c_void_p(stream)))
+
     def download(self, free_out, reports, stream=0):
         check(lib().fk_batch_plan_download(self._h, C.c_void_p(free_out.ctypes.data if free_out is not None else 0),
                                            C.c_void_p(reports.ctypes.data if reports is not None else 0), C.c_void_p(stream)))

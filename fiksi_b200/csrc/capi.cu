@@ -50,6 +50,7 @@ struct DeviceProgram {
     int device = -1;
     void* buf = nullptr;
     fk::DevProgram view{};
+    const uint32_t *jcolptr = nullptr, *jrow = nullptr;  // CSC of the Jacobian (L-BFGS)
     ~DeviceProgram() {
         if (buf) {
             cudaSetDevice(device);
@@ -78,6 +79,11 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
         return at;
     };
     const fk::Topology::Tables& tb = t.tab;
+    std::vector<uint32_t> jcolptr(t.n_free + 1), jrow(t.jac_nnz);  // CSC of the Jacobian without damping rows (L-BFGS gradient)
+    for (uint32_t c = 0; c <= t.n_free; c++) jcolptr[c] = t.aug_colptr[c] - c;
+    for (uint32_t c = 0; c < t.n_free; c++)
+        for (uint32_t q = t.aug_colptr[c]; q + 1 < t.aug_colptr[c + 1]; q++) jrow[q - c] = t.aug_rowidx[q];
+    const size_t o_jcp = add(jcolptr), o_jrow = add(jrow);
     size_t o_free = add(t.free_vars), o_rh = add(tb.row_hdr), o_rs = add(tb.row_slots),
            o_af = add(tb.a_flags), o_ao = add(tb.a_ops), o_ad = add(tb.a_dst),
            o_gf = add(tb.g_flags), o_go = add(tb.g_ops), o_gd = add(tb.g_dst),
@@ -102,6 +108,7 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
     v.f_steps = (const uint32_t*)(b + o_fs); v.f_ops = (const uint2*)(b + o_fo);
     v.s_steps = (const uint2*)(b + o_ss); v.s_ops = (const uint32_t*)(b + o_so);
     v.b_steps = (const uint2*)(b + o_bs); v.b_ops = (const uint32_t*)(b + o_bo);
+    out.jcolptr = (const uint32_t*)(b + o_jcp); out.jrow = (const uint32_t*)(b + o_jrow);
     return FK_OK;
 }
 
@@ -150,7 +157,7 @@ struct fk_topology {
         return p.get();
     }
 
-    int program_for(int device, const fk::DevProgram** out) {
+    int program_for(int device, const fk::DevProgram** out, const DeviceProgram** full = nullptr) {
         std::lock_guard<std::mutex> lock(mu);
         auto it = programs.find(device);
         if (it == programs.end()) {
@@ -160,6 +167,7 @@ struct fk_topology {
             it = programs.emplace(device, std::move(p)).first;
         }
         *out = &it->second->view;
+        if (full) *full = it->second.get();
         return FK_OK;
     }
 };
@@ -169,6 +177,7 @@ struct fk_batch_plan {
     int device = 0;
     uint32_t capacity = 0, n = 0;
     const fk::DevProgram* prog = nullptr;
+    const DeviceProgram* full = nullptr;
     double *d_vars = nullptr, *d_params = nullptr, *d_out = nullptr, *d_er = nullptr, *d_ej = nullptr;
     fk_report* d_rep = nullptr;
     uint64_t launches = 0;
@@ -275,59 +284,19 @@ int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, ui
 // ---- L-BFGS on a uniform batch -------------------------------------------------------------------
 int fk_batch_solve_lbfgs(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param, double* free_out,
                          fk_report* reports) {
-    fk_topology* topo = const_cast<fk_topology*>(topo_c);
-    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    if (!topo_c) return fail(FK_ERR_INVALID, "null topology");
     if (n == 0) return FK_OK;
-    if (!vars || !free_out || !reports || (!param && topo->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
-    const int ndev = usable_devices();
-    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
-    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
-    const fk::Topology& t = topo->t;
-    if (t.path != 0) return fail(FK_ERR_TOO_LARGE, "L-BFGS is built for the shared-memory tile paths only");
-    CU(cudaSetDevice(device));
-    const fk::DevProgram* prog = nullptr;
-    int rc = topo->program_for(device, &prog);
+    if (!vars || !free_out || !reports || (!param && topo_c->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
+    if (topo_c->t.path != 0) return fail(FK_ERR_TOO_LARGE, "L-BFGS is built for the shared-memory tile paths only");
+    fk_batch_plan* plan = nullptr;
+    int rc = fk_batch_plan_create(topo_c, n, device, &plan);
     if (rc != FK_OK) return rc;
-    std::vector<uint32_t> jcolptr(t.n_free + 1), jrow(t.jac_nnz);
-    for (uint32_t c = 0; c <= t.n_free; c++) jcolptr[c] = t.aug_colptr[c] - c;
-    for (uint32_t c = 0; c < t.n_free; c++)
-        for (uint32_t q = t.aug_colptr[c]; q + 1 < t.aug_colptr[c + 1]; q++) jrow[q - c] = t.aug_rowidx[q];
-    uint32_t *d_cp = nullptr, *d_jr = nullptr;
-    double *d_vars = nullptr, *d_param = nullptr, *d_out = nullptr;
-    fk_report* d_rep = nullptr;
-    auto cleanup = [&] { cudaFree(d_cp); cudaFree(d_jr); cudaFree(d_vars); cudaFree(d_param); cudaFree(d_out); cudaFree(d_rep); };
-#define LB_CU(call)                                   \
-    do {                                              \
-        cudaError_t e_ = (call);                      \
-        if (e_ != cudaSuccess) {                      \
-            cleanup();                                \
-            return cuda_fail(e_, #call);              \
-        }                                             \
-    } while (0)
-    LB_CU(cudaMalloc(&d_cp, jcolptr.size() * sizeof(uint32_t)));
-    LB_CU(cudaMalloc(&d_jr, std::max<size_t>(1, jrow.size()) * sizeof(uint32_t)));
-    LB_CU(cudaMalloc(&d_vars, sizeof(double) * std::max<size_t>(1, (size_t)n * t.n_vars)));
-    LB_CU(cudaMalloc(&d_param, sizeof(double) * std::max<size_t>(1, (size_t)n * t.n_expr)));
-    LB_CU(cudaMalloc(&d_out, sizeof(double) * std::max<size_t>(1, (size_t)n * t.n_free)));
-    LB_CU(cudaMalloc(&d_rep, sizeof(fk_report) * (size_t)n));
-    LB_CU(cudaMemcpy(d_cp, jcolptr.data(), jcolptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (!jrow.empty()) LB_CU(cudaMemcpy(d_jr, jrow.data(), jrow.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (t.n_vars) LB_CU(cudaMemcpy(d_vars, vars, sizeof(double) * (size_t)n * t.n_vars, cudaMemcpyHostToDevice));
-    if (t.n_expr) LB_CU(cudaMemcpy(d_param, param, sizeof(double) * (size_t)n * t.n_expr, cudaMemcpyHostToDevice));
-    const int e = fk::launch_batch_lbfgs(*prog, d_cp, d_jr, n, d_vars, d_param, d_out, d_rep, nullptr);
-    if (e == (int)cudaErrorInvalidConfiguration) {
-        cleanup();
-        return fail(FK_ERR_TOO_LARGE, "the L-BFGS state of one sketch does not fit the tile path");
-    }
-    if (e != 0) {
-        cleanup();
-        return cuda_fail((cudaError_t)e, "launch fk_batch_lbfgs_kernel");
-    }
-    if (t.n_free) LB_CU(cudaMemcpy(free_out, d_out, sizeof(double) * (size_t)n * t.n_free, cudaMemcpyDeviceToHost));
-    LB_CU(cudaMemcpy(reports, d_rep, sizeof(fk_report) * (size_t)n, cudaMemcpyDeviceToHost));
-#undef LB_CU
-    cleanup();
-    return FK_OK;
+    rc = fk_batch_plan_upload(plan, n, vars, param, nullptr);
+    if (rc == FK_OK) rc = fk_batch_plan_run_lbfgs(plan, nullptr);
+    if (rc == FK_OK) rc = fk_batch_plan_download(plan, free_out, reports, nullptr);
+    if (rc == FK_OK) rc = fk_batch_plan_sync(plan);
+    fk_batch_plan_destroy(plan);
+    return rc;
 }
 
 // ---- System::analyze on a batch -----------------------------------------------------------------
@@ -397,7 +366,7 @@ int fk_batch_plan_create(const fk_topology* topo_c, uint32_t capacity, int devic
     if (prop.major != 10) return fail(FK_ERR_NO_DEVICE, "device is not sm_100 class; kernels are built for sm_100a only");
     std::unique_ptr<fk_batch_plan> p(new fk_batch_plan());
     p->topo = topo; p->device = device; p->capacity = capacity;
-    int rc = topo->program_for(device, &p->prog);
+    int rc = topo->program_for(device, &p->prog, &p->full);
     if (rc != FK_OK) return rc;
     const fk::Topology& t = topo->t;
     CU(cudaMalloc(&p->d_vars, sizeof(double) * std::max<size_t>(1, (size_t)capacity * t.n_vars)));
@@ -427,6 +396,18 @@ int fk_batch_plan_run(fk_batch_plan* plan, void* stream) {
     int e = fk::launch_batch_lm(*plan->prog, plan->n, plan->d_vars, plan->d_params, plan->d_out,
                                 plan->d_rep, stream);
     if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_lm_kernel");
+    if (plan->n) plan->launches++;
+    return FK_OK;
+}
+
+int fk_batch_plan_run_lbfgs(fk_batch_plan* plan, void* stream) {
+    if (!plan) return fail(FK_ERR_INVALID, "null plan");
+    if (plan->topo->t.path != 0) return fail(FK_ERR_TOO_LARGE, "L-BFGS is built for the shared-memory tile paths only");
+    CU(cudaSetDevice(plan->device));
+    const int e = fk::launch_batch_lbfgs(*plan->prog, plan->full->jcolptr, plan->full->jrow, plan->n, plan->d_vars, plan->d_params,
+                                         plan->d_out, plan->d_rep, stream);
+    if (e == (int)cudaErrorInvalidConfiguration) return fail(FK_ERR_TOO_LARGE, "the L-BFGS state of one sketch does not fit the tile path");
+    if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_lbfgs_kernel");
     if (plan->n) plan->launches++;
     return FK_OK;
 }

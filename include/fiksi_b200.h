@@ -245,6 +245,8 @@ FK_API int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, doubl
  * (FK_ERR_TOO_LARGE otherwise). */
 FK_API int fk_batch_solve_lbfgs(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param,
                                 double* free_out, fk_report* reports);
+/* Same on the resident sketches of a batch plan (fk_batch_plan_upload / _download around it). */
+FK_API int fk_batch_plan_run_lbfgs(fk_batch_plan* plan, void* stream);
 
 /* ---- System::analyze: over-constraint detection -------------------------------------- */
 /* == find_overconstraints (fiksi/src/analyze/numerical/mod.rs:123-163) for n sketches sharing one
