@@ -979,6 +979,10 @@ static int launch_lm_t(const DevProgram& prog, uint32_t n_sketches, const double
         const int tiles_per_warp = 32 / TILE;
         int warps = 4;
         while (warps > 1 && bytes_per_sketch * tiles_per_warp * warps > 72 * 1024) warps >>= 1;
+        if (const char* e = std::getenv("FK_LM_WARPS")) {  // tuning knob: warps per CTA (1..4)
+            const int v = std::atoi(e);
+            if (v >= 1 && v <= 4) warps = v;
+        }
         tiles_per_cta = tiles_per_warp * warps;
         if (bytes_per_sketch * tiles_per_cta > 220 * 1024) return (int)cudaErrorInvalidConfiguration;
     }
