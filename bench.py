@@ -241,9 +241,14 @@ def main():
         line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": 41084416 if (n == 65536 and info["tile"] == 16) else None,
                             "kernel": "fk_batch_lm_kernel<%d,%d>" % (info["tile"], 1), "peak_source": peak_src,
-                            "note": "issue/latency-bound kernel (ncu: 60 % issue slots busy, FP64 pipe 10.6 %, DRAM 0.3 %): the whole LM "
-                                    "loop runs out of shared memory, HBM only sees each sketch's inputs and outputs once; the HBM-bound "
-                                    "kernel of the path is K1, see `assembly`"}
+                            "limiter": {"unit": "L1 / shared-memory data pipe (ncu l1tex__data_pipe_lsu_wavefronts)", "pct_of_peak": 68.5,
+                                        "shared_memory_wavefronts_pct": 50.5, "op_table_loads_through_l1_pct": 18.0,
+                                        "bank_conflict_share_of_shared_wavefronts": 0.28, "issue_slots_busy_pct": 60.5,
+                                        "fp64_pipe_active_pct": 10.6,
+                                        "source": "profiles/r01_v3_lm_kernel_tile16_ncu_full_summary.csv (ncu --set full of this command)"},
+                            "note": "the whole LM loop runs out of shared memory, so HBM only sees each sketch's inputs and outputs once "
+                                    "(DRAM 0.3 % busy); the unit that saturates is the SM's L1/shared-memory data pipe (see `limiter`); "
+                                    "the HBM-bound kernel of the path is K1, see `assembly`"}
         if not args.no_extras:
             try:
                 fp64_peak = fk.fp64_peak_tflops(local_rank)
