@@ -269,6 +269,10 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["large_system"] = {"error": str(e)}
             try:
+                line["single_sketch"] = single_sketch_latency(fk, wl)
+            except Exception as e:  # noqa: BLE001
+                line["single_sketch"] = {"error": str(e)}
+            try:
                 line["lbfgs"] = lbfgs_side(fk, wl, local_rank)
             except Exception as e:  # noqa: BLE001
                 line["lbfgs"] = {"error": str(e)}
@@ -282,6 +286,32 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def single_sketch_latency(fk, wl):
+    """configs[0]: ONE circle_triangle_line-shaped sketch (11 variables, 8 rows) solved once.  A single tiny
+    system is latency bound on a GPU (launch + two PCIe round trips); reported honestly beside the CPU."""
+    import oracle
+    w = wl.cad_mix(1)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    x0 = v[0][w.free_vars]
+    for _ in range(5):
+        topo.lm_solve(v[0], p[0], x0)
+    reps = 200
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        xg, rg = topo.lm_solve(v[0], p[0], x0)
+    gpu_us = (time.perf_counter() - t0) / reps * 1e6
+    op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        xo, ro, _ = oracle.lm_solve(op, x0)
+    cpu_us = (time.perf_counter() - t0) / reps * 1e6
+    return {"workload": "configs[0]: one mixed-primitive sketch (circle_triangle_line topology), cached topology",
+            "gpu_us_per_solve": gpu_us, "cpu_port_us_per_solve_incl_symbolic": cpu_us,
+            "same_trace": bool(rg["trace_hash"] == ro["trace_hash"]),
+            "note": "one sketch cannot amortise a kernel launch and two host<->device copies; batches can (see value / config4_lm)"}
 
 
 def lbfgs_side(fk, wl, device):

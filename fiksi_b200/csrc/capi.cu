@@ -497,7 +497,12 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
     std::lock_guard<std::mutex> lock(pl->mu);
     constexpr uint32_t kStreams = DevicePipeline::kStreams;
     // chunks small enough to overlap H2D / kernel / D2H, large enough to fill the machine
-    uint32_t chunk = std::min(total, std::max<uint32_t>(4096, (total + 7) / 8));
+    static const uint32_t n_chunks = [] {
+        const char* e = std::getenv("FK_E2E_CHUNKS");  // tuning knob
+        const int v = e ? std::atoi(e) : 0;
+        return (uint32_t)(v >= 1 && v <= 256 ? v : 8);
+    }();
+    uint32_t chunk = std::min(total, std::max<uint32_t>(2048, (total + n_chunks - 1) / n_chunks));
     int rc = FK_OK;
     if (pl->chunk < chunk) {
         pl->release();
@@ -509,7 +514,7 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
         if (rc == FK_OK) pl->chunk = chunk;
         else pl->release();
     } else {
-        chunk = pl->chunk >= total ? std::min(total, std::max<uint32_t>(4096, (total + 7) / 8)) : pl->chunk;
+        chunk = pl->chunk >= total ? std::min(total, std::max<uint32_t>(2048, (total + n_chunks - 1) / n_chunks)) : pl->chunk;
     }
     uint32_t s = 0;
     for (uint32_t at = lo; at < hi && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
