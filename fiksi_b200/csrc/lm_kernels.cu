@@ -921,7 +921,7 @@ int launch_batch_lbfgs(const DevProgram& prog, const uint32_t* d_jcolptr, const 
         return prog.uniform_kind == 1 ? launch_lbfgs_t<TL, 1>(prog, T, n_sketches, vars, params, free_out, reports, s) \
                                       : launch_lbfgs_t<TL, -1>(prog, T, n_sketches, vars, params, free_out, reports, s);
     switch (prog.tile) {
-        FK_LBFGS(8) FK_LBFGS(16) FK_LBFGS(32)
+        FK_LBFGS(4) FK_LBFGS(8) FK_LBFGS(16) FK_LBFGS(32)
         default: return (int)cudaErrorInvalidConfiguration;
     }
 #undef FK_LBFGS

@@ -215,7 +215,13 @@ int Topology::build(const fk_problem& p) {
         uint32_t w = std::max(m, n);
         if (bytes <= 24 * 1024 && n_updates < (1u << 22)) {
             path = 0;
-            tile = w <= 12 ? 8 : (w <= 96 ? 16 : 32);  // measured on B200: 16 lanes beat 8 and 32 on the 20-point truss
+            // Lanes per sketch, measured on B200 (tools/tile_probe.py; M sketches/s at 4 / 8 / 16 lanes): config-4
+            // topology (1.1 KB of shared state) 140 / 117 / 74; 10-point truss (2.0 KB) 93 / 121 / 83; 14-point truss
+            // (2.8 KB) - / 61.5 / 62.1; 20-point truss (4.1 KB) 20 / 30 / 37.6.  Fewer lanes mean more sketches per
+            // instruction (less table walking and fewer shared-memory wavefronts per sketch) but more shared memory per
+            // warp, i.e. fewer resident warps; the crossover follows the per-sketch footprint.
+            (void)w;
+            tile = bytes <= 1300 ? 4 : (bytes <= 2600 ? 8 : (std::max(m, n) <= 96 ? 16 : 32));
         } else if (bytes <= 200 * 1024 && n_updates < (1u << 25)) {
             path = 1;
             tile = 256;
