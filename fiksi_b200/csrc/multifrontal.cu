@@ -743,8 +743,10 @@ mf_small_solve_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint3
 constexpr uint32_t kSplitEntries = 16384;
 __device__ __forceinline__ bool is_split(uint32_t f, uint32_t ns) { return (f - ns) * ns > kSplitEntries; }
 
-template <bool FORWARD, bool WIDE>
-__global__ void __launch_bounds__(256)
+// G threads per supernode: 256 in general, 64 on levels whose fronts all have order <= 64 (the many
+// small fronts near the leaves: four times as many supernodes per SM).
+template <bool FORWARD, bool WIDE, int G = 256>
+__global__ void __launch_bounds__(G)
 mf_big_solve_kernel(MfDev D, const uint32_t* __restrict__ list, double* __restrict__ w, double* __restrict__ delta,
                     const int32_t* __restrict__ perm, const double* __restrict__ tmp, uint32_t max_front) {
     extern __shared__ double smd[];
@@ -753,8 +755,8 @@ mf_big_solve_kernel(MfDev D, const uint32_t* __restrict__ list, double* __restri
     double* wide = t + max_front; // [max front] second vector of the wide pivot-block solves
     const uint32_t s = __ldg(list + blockIdx.x);
     const bool split = is_split(__ldg(D.f + s), __ldg(D.ns + s));
-    if (FORWARD) forward_supernode<256, WIDE>(D, s, w, t, tri, threadIdx.x, split, wide);
-    else backward_supernode<256, WIDE>(D, s, w, delta, perm, t, tri, threadIdx.x, split, tmp, wide);
+    if (FORWARD) forward_supernode<G, WIDE>(D, s, w, t, tri, threadIdx.x, split, wide);
+    else backward_supernode<G, WIDE>(D, s, w, delta, perm, t, tri, threadIdx.x, split, tmp, wide);
 }
 
 // Forward, split supernodes: u_s[r0 .. r0+64) -= L21[rows, :] y_s.  256 threads = 64 rows x 4
@@ -998,6 +1000,7 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     factor_seq_.clear();
     fwd_tasks_.clear();
     level_wide_.clear();
+    level_narrow_.clear();
     bwd_tasks_.clear();
     level_ptr_.assign(1, 0);
     level_list.clear();
@@ -1009,6 +1012,9 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             bool wide = false;
             for (uint32_t s : L) wide = wide || ns[s] >= 64;
             level_wide_.push_back(wide);
+            bool narrow = true;
+            for (uint32_t s : L) narrow = narrow && f[s] <= 64;
+            level_narrow_.push_back(narrow);
         }
         {   // solve tasks of the split supernodes of this level
             uint32_t first = (uint32_t)(tasks.size() / 4);
@@ -1196,6 +1202,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
     const uint32_t sgrid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t smem = (32 * 33 + 2 * (size_t)stats.max_front) * sizeof(double);
     const size_t vsmem = (size_t)stats.max_front * sizeof(double);
+    const size_t nsmem = (32 * 33 + 2 * 64) * sizeof(double);  // narrow levels: fronts of order <= 64
     const uint32_t nlevels = (uint32_t)level_ptr_.size() - 1;
     if (nsub_) timed(0, [&] { mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm); });
     for (uint32_t l = 0; l < nlevels; l++) {
@@ -1203,6 +1210,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
         const uint32_t* list = d_level_list_ + level_ptr_[l];
         timed(1, [&] {
             if (level_wide_[l]) mf_big_solve_kernel<true, true><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
+            else if (level_narrow_[l]) mf_big_solve_kernel<true, false, 64><<<cnt, 64, nsmem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, 64);
             else mf_big_solve_kernel<true, false><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
         });
         if (fwd_tasks_[l].second) timed(2, [&] { mf_fwd_upd_kernel<<<fwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + fwd_tasks_[l].first, w); });
@@ -1213,6 +1221,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
         if (bwd_tasks_[l].second) timed(3, [&] { mf_bwd_dot_kernel<<<bwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + bwd_tasks_[l].first, w, d_tmp_); });
         timed(4, [&] {
             if (level_wide_[l]) mf_big_solve_kernel<false, true><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
+            else if (level_narrow_[l]) mf_big_solve_kernel<false, false, 64><<<cnt, 64, nsmem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, 64);
             else mf_big_solve_kernel<false, false><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
         });
     }

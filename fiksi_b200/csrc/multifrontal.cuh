@@ -110,6 +110,7 @@ private:
     std::vector<std::pair<uint32_t, uint32_t>> fwd_tasks_, bwd_tasks_;  // per level: {first task, count}
     double* d_tmp_ = nullptr;
     std::vector<bool> level_wide_;  // a supernode of the level has >= 64 pivot columns
+    std::vector<bool> level_narrow_;  // every front of the level has order <= 64
     cudaGraphExec_t factor_graph_ = nullptr, solve_graph_ = nullptr;
     double* solve_w_ = nullptr; double* solve_delta_ = nullptr; const int32_t* solve_perm_ = nullptr;
     cudaError_t enqueue_factor(cudaStream_t stream);
