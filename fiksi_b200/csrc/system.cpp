@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/fiksi_b200.h"
+#include "single_pass.hpp"
 #include "symbolic.hpp"
 
 namespace {
@@ -341,6 +342,157 @@ int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32_t cap,
         for (size_t k = 0; k < L->free_global.size(); k++) s->vars[L->free_global[k]] = scale * L->x[k];
     for (size_t k = 0; k < locals.size() && reports && k < cap; k++) reports[k] = reps[k];
     if (n_solved) *n_solved = (uint32_t)locals.size();
+    return FK_OK;
+}
+
+// ---- Decomposer::SinglePass ------------------------------------------------------------
+namespace {
+
+// The equation graph of lib.rs:262,395,434.
+void equation_graph(const fk_system* s, std::vector<std::vector<uint32_t>>& var_exprs, std::vector<std::vector<uint32_t>>& expr_vars) {
+    var_exprs.assign(s->vars.size(), {});
+    expr_vars.assign(s->kind.size(), {});
+    for (uint32_t e = 0; e < s->kind.size(); e++) {
+        uint32_t sv[8];
+        const int a = fk::expand_slots(s->kind[e], &s->idx[4 * (size_t)e], sv);
+        expr_vars[e].assign(sv, sv + a);
+        for (int k = 0; k < a; k++) var_exprs[sv[k]].push_back(e);
+    }
+}
+
+std::vector<uint32_t> component_free_variables(const fk_system* s, const fk_system::Comp& c) {
+    std::set<uint32_t> free_set;
+    for (uint32_t e : c.elements) {
+        uint32_t v[4];
+        const int n = s->element_vars(e, v);
+        for (int k = 0; k < n; k++)
+            if (!s->fixed[v[k]]) free_set.insert(v[k]);
+    }
+    return std::vector<uint32_t>(free_set.begin(), free_set.end());
+}
+
+// One compact fk_problem: `free_sorted` free, `exprs` as rows (in that order), every other referenced
+// variable fixed at its current value in `vt`.
+struct LocalProblem {
+    std::vector<double> vars, param, x;
+    std::vector<uint8_t> kind;
+    std::vector<uint32_t> idx, free_local, rows, free_global;
+    fk_problem prob;
+};
+void build_local(const fk_system* s, const std::vector<double>& vt, const std::vector<double>& pt, const std::vector<uint32_t>& free_sorted,
+                 const std::vector<uint32_t>& exprs, LocalProblem& L) {
+    std::set<uint32_t> used(free_sorted.begin(), free_sorted.end());
+    for (uint32_t e : exprs) {
+        uint32_t sv[8];
+        const int a = fk::expand_slots(s->kind[e], &s->idx[4 * (size_t)e], sv);
+        for (int k = 0; k < a; k++) used.insert(sv[k]);
+    }
+    std::map<uint32_t, uint32_t> local;
+    for (uint32_t g : used) {
+        local.emplace(g, (uint32_t)L.vars.size());
+        L.vars.push_back(vt[g]);
+    }
+    for (uint32_t g : free_sorted) {
+        L.free_global.push_back(g);
+        L.free_local.push_back(local[g]);
+        L.x.push_back(vt[g]);
+    }
+    static const int stored[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
+    for (uint32_t e : exprs) {
+        L.rows.push_back((uint32_t)L.kind.size());
+        L.kind.push_back(s->kind[e]);
+        L.param.push_back(pt[e]);
+        for (int q = 0; q < 4; q++) L.idx.push_back(q < stored[s->kind[e]] ? local[s->idx[4 * (size_t)e + q]] : 0);
+    }
+    fk_problem& p = L.prob;
+    p.n_vars = (uint32_t)L.vars.size(); p.vars = L.vars.data();
+    p.n_expr = (uint32_t)L.kind.size(); p.kind = L.kind.data(); p.idx = L.idx.data(); p.param = L.param.data();
+    p.n_free = (uint32_t)L.free_local.size(); p.free_vars = L.free_local.data();
+    p.n_rows = (uint32_t)L.rows.size(); p.rows = L.rows.data();
+}
+
+}  // namespace
+
+// The sequence of sub-problems SinglePass solves, all components in order (host only, no device):
+// call with NULL arrays for sizes3 = {steps, total free variables, total expressions}, then with
+// free_ptr[steps+1], free_vars, expr_ptr[steps+1], exprs.
+int fk_system_single_pass_plan(const fk_system* s, uint32_t* sizes3, uint32_t* free_ptr, uint32_t* free_vars, uint32_t* expr_ptr,
+                               uint32_t* exprs) {
+    if (!s) return FK_ERR_INVALID;
+    std::vector<std::vector<uint32_t>> var_exprs, expr_vars;
+    equation_graph(s, var_exprs, expr_vars);
+    fk::SinglePassPlanner planner(var_exprs, expr_vars);
+    std::vector<fk::SinglePassStep> all;
+    for (const fk_system::Comp& c : s->comps) {
+        if (c.elements.empty()) continue;
+        for (fk::SinglePassStep& st : planner.plan(component_free_variables(s, c))) all.push_back(std::move(st));
+    }
+    uint32_t nf = 0, ne = 0;
+    for (const auto& st : all) { nf += (uint32_t)st.free_variables.size(); ne += (uint32_t)st.expressions.size(); }
+    if (sizes3) { sizes3[0] = (uint32_t)all.size(); sizes3[1] = nf; sizes3[2] = ne; }
+    if (!free_ptr || !free_vars || !expr_ptr || !exprs) return FK_OK;
+    uint32_t af = 0, ae = 0;
+    for (size_t k = 0; k < all.size(); k++) {
+        free_ptr[k] = af; expr_ptr[k] = ae;
+        for (uint32_t v : all[k].free_variables) free_vars[af++] = v;
+        for (uint32_t e : all[k].expressions) exprs[ae++] = e;
+    }
+    free_ptr[all.size()] = af; expr_ptr[all.size()] = ae;
+    return FK_OK;
+}
+
+// == System::solve(SolvingOptions { optimizer: LevenbergMarquardt, decomposer, perturb }).
+// decomposer 0: None (== fk_system_solve); 1: SinglePass (assemble/mod.rs:169-210): the strongly
+// connected expression sets of every component are solved one after the other on the GPU, each seeing
+// the variables solved before it as fixed values.  reports: one per solved sub-problem.
+int fk_system_solve_opts(fk_system* s, int decomposer, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved) {
+    if (!s) return FK_ERR_INVALID;
+    if (decomposer == 0) return fk_system_solve(s, perturb, reports, cap, n_solved);
+    if (decomposer != 1) return FK_ERR_INVALID;
+    if (n_solved) *n_solved = 0;
+    const size_t nv = s->vars.size();
+    double sum = 0.0;
+    size_t cnt = 0;
+    for (double v : s->vars) { sum += v * v; cnt++; }
+    for (size_t e = 0; e < s->kind.size(); e++)
+        if (s->kind[e] == FK_POINT_POINT_DISTANCE || s->kind[e] == FK_POINT_LINE_DISTANCE) { sum += s->param[e] * s->param[e]; cnt++; }
+    const double scale = std::sqrt(sum / (double)cnt);
+    const double recip = 1.0 / scale;
+    std::vector<double> vt(nv);
+    for (size_t i = 0; i < nv; i++) vt[i] = s->vars[i] * recip;
+    std::vector<double> pt(s->param);
+    for (size_t e = 0; e < pt.size(); e++)
+        if (s->kind[e] == FK_POINT_POINT_DISTANCE || s->kind[e] == FK_POINT_LINE_DISTANCE) pt[e] = recip * s->param[e];
+    std::vector<std::vector<uint32_t>> var_exprs, expr_vars;
+    equation_graph(s, var_exprs, expr_vars);
+    fk::SinglePassPlanner planner(var_exprs, expr_vars);
+    Lcg rng{42};
+    uint32_t solved = 0;
+    for (const fk_system::Comp& c : s->comps) {
+        if (c.elements.empty()) continue;
+        const std::vector<uint32_t> free_sorted = component_free_variables(s, c);
+        if (perturb) {
+            for (uint32_t fv : free_sorted) {
+                const double r1 = rng.next();
+                const double r2 = rng.next();
+                vt[fv] += vt[fv] * (1.0 / 8196.0) * r1 + (1.0 / 65568.0) * r2;
+            }
+        }
+        for (const fk::SinglePassStep& st : planner.plan(free_sorted)) {
+            LocalProblem L;
+            build_local(s, vt, pt, st.free_variables, st.expressions, L);
+            fk_report rep{};
+            const int rc = fk_lm_solve(&L.prob, L.x.data(), &rep);
+            if (rc != FK_OK) return rc;
+            for (size_t k = 0; k < L.free_global.size(); k++) {  // assemble/mod.rs:201-208
+                vt[L.free_global[k]] = L.x[k];
+                s->vars[L.free_global[k]] = scale * L.x[k];
+            }
+            if (reports && solved < cap) reports[solved] = rep;
+            solved++;
+        }
+    }
+    if (n_solved) *n_solved = solved;
     return FK_OK;
 }
 

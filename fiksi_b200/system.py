@@ -73,6 +73,25 @@ class System:
         check(lib().fk_system_solve(self._h, int(perturb), reps.ctypes.data_as(C.POINTER(FkReport)), cap, C.byref(n)))
         self._reports = reps[:n.value]
 
+    def solve_single_pass(self, perturb=True):
+        """System::solve with Decomposer::SinglePass (assemble/mod.rs:169-210) on the GPU."""
+        cap = max(1, len(self.single_pass_plan()))
+        reps = np.zeros(cap, dtype=REPORT_DTYPE)
+        n = C.c_uint32(0)
+        check(lib().fk_system_solve_opts(self._h, 1, int(perturb), reps.ctypes.data_as(C.POINTER(FkReport)), cap, C.byref(n)))
+        self._reports = reps[:n.value]
+
+    def single_pass_plan(self):
+        """[(free variables, expressions), ...] of fk_system_single_pass_plan (host only)."""
+        sizes = np.zeros(3, dtype=np.uint32)
+        check(lib().fk_system_single_pass_plan(self._h, ptr(sizes, C.c_uint32), None, None, None, None))
+        n, nf, ne = (int(x) for x in sizes)
+        fp = np.zeros(n + 1, np.uint32); fv = np.zeros(max(nf, 1), np.uint32)
+        ep = np.zeros(n + 1, np.uint32); ex = np.zeros(max(ne, 1), np.uint32)
+        check(lib().fk_system_single_pass_plan(self._h, ptr(sizes, C.c_uint32), ptr(fp, C.c_uint32), ptr(fv, C.c_uint32),
+                                               ptr(ep, C.c_uint32), ptr(ex, C.c_uint32)))
+        return [(fv[fp[k]:fp[k + 1]].tolist(), ex[ep[k]:ep[k + 1]].tolist()) for k in range(n)]
+
     def reports(self):
         return [{k: r[k].item() for k in REPORT_DTYPE.names} for r in self._reports]
 

@@ -300,6 +300,16 @@ FK_API int fk_system_get_variables(const fk_system* s, double* out);
 FK_API int fk_system_set_variable(fk_system* s, uint32_t var, double value);     /* update_value */
 FK_API int fk_system_set_parameter(fk_system* s, uint32_t constraint, double value); /* update_parameter */
 FK_API int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved);
+/* == System::solve(SolvingOptions { optimizer: LevenbergMarquardt, decomposer, perturb }), lib.rs:205-237.
+ * decomposer 0: Decomposer::None (== fk_system_solve); 1: Decomposer::SinglePass (assemble/mod.rs:169-210;
+ * maximum matching + strongly connected expression sets of analyze/graph/equations.rs on the host, every
+ * set solved by the GPU LM in sequence).  reports: one per solved sub-problem, up to `cap`. */
+FK_API int fk_system_solve_opts(fk_system* s, int decomposer, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved);
+/* Host-only probe of the SinglePass plan (no device needed): call with NULL arrays for
+ * sizes3 = {steps, total free variables, total expressions}; then free_ptr[steps+1], free_vars (ascending
+ * per step), expr_ptr[steps+1], exprs (row order per step). */
+FK_API int fk_system_single_pass_plan(const fk_system* s, uint32_t* sizes3, uint32_t* free_ptr, uint32_t* free_vars,
+                                      uint32_t* expr_ptr, uint32_t* exprs);
 FK_API int fk_system_residuals(fk_system* s, double* out /* [num_constraints] */); /* calculate_residual */
 /* == System::analyze (lib.rs:454-458): ids of the constraints that own a dependent expression, in
  * expression order, up to `cap`; *n_found receives their number. */

@@ -399,6 +399,20 @@ class System:
     def num_constraints(self): return self._c("orc_num_constraints")
     def system_scale(self): return self._c("orc_system_scale")
 
+    def solve_single_pass(self, perturb=True):
+        """System::solve with Decomposer::SinglePass (assemble/mod.rs:169-210), LM optimizer."""
+        self._c("orc_solve_single_pass", int(perturb))
+
+    def single_pass_plan(self):
+        """[(free variables, expressions), ...]: the sequence of sub-problems SinglePass solves."""
+        sizes = np.zeros(3, dtype=np.uint32)
+        self._c("orc_single_pass_plan", _p(sizes, C.c_uint32), None, None, None, None)
+        n, nf, ne = (int(x) for x in sizes)
+        fp = np.zeros(n + 1, np.uint32); fv = np.zeros(max(nf, 1), np.uint32)
+        ep = np.zeros(n + 1, np.uint32); ex = np.zeros(max(ne, 1), np.uint32)
+        self._c("orc_single_pass_plan", _p(sizes, C.c_uint32), _p(fp, C.c_uint32), _p(fv, C.c_uint32), _p(ep, C.c_uint32), _p(ex, C.c_uint32))
+        return [(fv[fp[k]:fp[k + 1]].tolist(), ex[ep[k]:ep[k + 1]].tolist()) for k in range(n)]
+
     def analyze(self):
         """System::analyze (lib.rs:454-458): ids of the constraints flagged as over-constraining."""
         out = np.zeros(max(self.num_constraints() * 2, 1), dtype=np.uint32)

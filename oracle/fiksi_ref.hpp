@@ -21,6 +21,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <deque>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -786,6 +788,180 @@ inline std::vector<uint8_t> analyze_expressions(const std::vector<double>& varia
     return incremental_gauss_jordan_elimination(jacobian, m, n, column_pivots);
 }
 
+// ---- Decomposer::SinglePass: equation graph, maximum matching, strongly connected expressions ----------
+// fiksi/src/analyze/graph/equations.rs.  `variables[v]` lists the expressions of variable v in
+// insertion order, `expressions[e]` the variables of expression e (variable_indices order).
+struct ExpressionGraph {  // equations.rs:146-182
+    std::vector<std::vector<uint32_t>> variables, expressions;
+    void insert_variables(int n) { for (int k = 0; k < n; k++) variables.emplace_back(); }
+    void insert_expression(const uint32_t* vars, int n) {
+        uint32_t id = (uint32_t)expressions.size();
+        expressions.emplace_back(vars, vars + n);
+        for (uint32_t v : expressions.back()) variables[v].push_back(id);
+    }
+};
+
+// Minimal insertion-ordered map (the reference uses indexmap::IndexMap, equations.rs:96-101): inserting
+// an existing key replaces the value and keeps the position.
+struct OrderedMapU32 {
+    std::vector<std::pair<uint32_t, uint32_t>> items;
+    std::map<uint32_t, size_t> pos;
+    bool contains(uint32_t k) const { return pos.count(k) != 0; }
+    const uint32_t* get(uint32_t k) const {
+        auto it = pos.find(k);
+        return it == pos.end() ? nullptr : &items[it->second].second;
+    }
+    void insert(uint32_t k, uint32_t v) {
+        auto it = pos.find(k);
+        if (it == pos.end()) { pos[k] = items.size(); items.push_back({k, v}); }
+        else items[it->second].second = v;
+    }
+};
+
+struct Matching { OrderedMapU32 a_to_b, b_to_a; };  // equations.rs:96-101
+
+struct StronglyConnectedExpressions {  // equations.rs:154-157
+    std::vector<uint32_t> free_variables, expressions;
+};
+
+struct SinglePassPlanner {
+    const ExpressionGraph& graph;
+    const std::set<uint32_t>& free_variables;  // vertices of set A (ascending, BTreeSet)
+    SinglePassPlanner(const ExpressionGraph& g, const std::set<uint32_t>& f) : graph(g), free_variables(f) {}
+    Matching matching;
+    OrderedMapU32 distance;  // keyed by free variable, insertion order == ascending
+    uint32_t dummy_a_distance = UINT32_MAX;
+
+    static uint32_t sat_add1(uint32_t v) { return v == UINT32_MAX ? v : v + 1; }
+
+    bool bfs() {  // equations.rs:325-369
+        std::deque<uint32_t> queue;
+        for (auto& kv : distance.items) {
+            if (matching.a_to_b.contains(kv.first)) kv.second = UINT32_MAX;
+            else { kv.second = 0; queue.push_back(kv.first); }
+        }
+        dummy_a_distance = UINT32_MAX;
+        while (!queue.empty()) {
+            uint32_t a = queue.front();
+            queue.pop_front();
+            uint32_t a_distance = *distance.get(a);
+            if (a_distance >= dummy_a_distance) continue;
+            uint32_t new_dist = sat_add1(a_distance);
+            for (uint32_t b : graph.variables[a]) {
+                const uint32_t* matched_a = matching.b_to_a.get(b);
+                if (!matched_a) {
+                    if (dummy_a_distance == UINT32_MAX) dummy_a_distance = new_dist;
+                } else if (*distance.get(*matched_a) == UINT32_MAX) {
+                    distance.insert(*matched_a, new_dist);
+                    queue.push_back(*matched_a);
+                }
+            }
+        }
+        return dummy_a_distance != UINT32_MAX;
+    }
+    bool dfs(uint32_t a) {  // equations.rs:371-402
+        uint32_t a_distance_plus_one = sat_add1(*distance.get(a));
+        for (uint32_t b : graph.variables[a]) {
+            const uint32_t* matched_a = matching.b_to_a.get(b);
+            if (!matched_a) {
+                if (dummy_a_distance == a_distance_plus_one) {
+                    matching.a_to_b.insert(a, b);
+                    matching.b_to_a.insert(b, a);
+                    return true;
+                }
+            } else {
+                uint32_t ma = *matched_a;
+                if (*distance.get(ma) == a_distance_plus_one && dfs(ma)) {
+                    matching.a_to_b.insert(a, b);
+                    matching.b_to_a.insert(b, a);
+                    return true;
+                }
+            }
+        }
+        distance.insert(a, UINT32_MAX);
+        return false;
+    }
+    void find_maximum_matching() {  // equations.rs:301-322
+        for (uint32_t a : free_variables) distance.insert(a, UINT32_MAX);
+        while (bfs())
+            for (uint32_t a : free_variables)
+                if (!matching.a_to_b.contains(a)) dfs(a);
+    }
+    // MatchedBipartiteGraph::neighbors, equations.rs:438-448
+    std::vector<uint32_t> neighbors(uint32_t vertex) const {
+        std::vector<uint32_t> out;
+        uint32_t matched_a = *matching.b_to_a.get(vertex);
+        for (uint32_t a : graph.expressions[vertex]) {
+            if (!free_variables.count(a)) continue;  // MaskedExpressionGraph::neighbors_of_b, :272-286
+            if (!(a == matched_a || !matching.a_to_b.contains(a))) continue;
+            for (uint32_t b : graph.variables[a])
+                if (b != vertex && matching.b_to_a.contains(b)) out.push_back(b);
+        }
+        return out;
+    }
+    // tarjan::tarjan_pearce + visit, equations.rs:470-567
+    uint32_t index = 1, c = 0;
+    std::map<uint32_t, uint32_t> root_index;
+    std::vector<uint32_t> stack;
+    std::vector<std::vector<uint32_t>> sccs;
+    void visit(uint32_t vertex) {
+        bool root = true;
+        uint32_t vertex_index = index;
+        root_index[vertex] = vertex_index;
+        index += 1;
+        for (uint32_t neighbor : neighbors(vertex)) {
+            if (!root_index.count(neighbor)) visit(neighbor);
+            uint32_t neighbor_index = root_index[neighbor];
+            if (neighbor_index < vertex_index) {
+                vertex_index = neighbor_index;
+                root_index[vertex] = vertex_index;
+                root = false;
+            }
+        }
+        if (root) {
+            std::vector<uint32_t> scc{vertex};
+            index -= 1;
+            while (!stack.empty()) {
+                uint32_t top = stack.back();
+                if (vertex_index > root_index[top]) break;
+                stack.pop_back();
+                scc.push_back(top);
+                root_index[top] = c;
+                index -= 1;
+            }
+            vertex_index = c;
+            root_index[vertex] = vertex_index;
+            c = c - 1;  // wrapping, :560
+            sccs.push_back(std::move(scc));
+        } else {
+            stack.push_back(vertex);
+        }
+    }
+    // find_strongly_connected_expressions, equations.rs:186-221.  The reference collects an SCC's free
+    // variables in a HashSet and hands them out in hash order (unspecified); this restatement sorts them
+    // ascending (the order only permutes the columns of the sub-problem).
+    std::vector<StronglyConnectedExpressions> plan() {
+        find_maximum_matching();
+        c = (uint32_t)matching.b_to_a.items.size() - 1u;  // wrapping_sub(1), :476-478
+        for (auto& kv : matching.b_to_a.items)
+            if (!root_index.count(kv.first)) visit(kv.first);
+        std::vector<StronglyConnectedExpressions> out;
+        for (size_t k = sccs.size(); k-- > 0;) {
+            StronglyConnectedExpressions sc;
+            sc.expressions = sccs[k];
+            std::set<uint32_t> fv;
+            for (uint32_t e : sc.expressions) {
+                uint32_t matched_var = *matching.b_to_a.get(e);
+                for (uint32_t var : graph.expressions[e])
+                    if (var == matched_var || (!matching.a_to_b.contains(var) && free_variables.count(var))) fv.insert(var);
+            }
+            sc.free_variables.assign(fv.begin(), fv.end());
+            out.push_back(std::move(sc));
+        }
+        return out;
+    }
+};
+
 struct System {
     Graph graph;
     std::vector<EncodedElement> elements;
@@ -1022,6 +1198,47 @@ struct System {
             for (size_t k = 0; k < cp.free_variables.size(); k++)
                 variables[cp.free_variables[k]] = system_scale * free_values[k];
             last_reports.push_back(std::move(rep));
+        });
+    }
+
+    // The equation graph of lib.rs:262,395,434: variables in creation order, one vertex per expression.
+    ExpressionGraph equation_graph() const {
+        ExpressionGraph g;
+        g.insert_variables((int)variables.size());
+        for (const Expression& e : expressions) {
+            uint32_t vi[8];
+            int a = variable_indices(e, vi);
+            g.insert_expression(vi, a);
+        }
+        return g;
+    }
+
+    // assemble/mod.rs:169-210 (Decomposer::SinglePass, Optimizer::LevenbergMarquardt): every connected
+    // component is split into strongly connected sets of expressions which are solved in sequence, each
+    // with its own free variables; later sets see the variables solved by earlier ones as fixed values.
+    // `plan_out` (optional) receives the sequence of (free variables, expressions) of all components.
+    void solve_single_pass(const SolvingOptions& opts, std::vector<StronglyConnectedExpressions>* plan_out = nullptr,
+                           bool dry_run = false) {
+        last_reports.clear();
+        const ExpressionGraph eg = equation_graph();
+        for_each_component(opts, [&](const ComponentProblem& cp, double system_scale) {
+            std::set<uint32_t> free_set(cp.free_variables.begin(), cp.free_variables.end());
+            SinglePassPlanner planner(eg, free_set);
+            for (const StronglyConnectedExpressions& scc : planner.plan()) {
+                if (plan_out) plan_out->push_back(scc);
+                if (dry_run) continue;
+                std::vector<double> free_values;
+                for (uint32_t fv : scc.free_variables) free_values.push_back(variables_transformed[fv]);
+                Subsystem sub(variables_transformed.data(), variables_transformed.size(), expressions_transformed.data(),
+                              scc.free_variables, scc.expressions);
+                LmReport rep;
+                levenberg_marquardt(sub, free_values.data(), rep, false);
+                for (size_t k = 0; k < scc.free_variables.size(); k++) {
+                    variables_transformed[scc.free_variables[k]] = free_values[k];
+                    variables[scc.free_variables[k]] = system_scale * free_values[k];
+                }
+                last_reports.push_back(std::move(rep));
+            }
         });
     }
 

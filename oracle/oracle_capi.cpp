@@ -415,6 +415,32 @@ ORC_API void orc_solve(void* s, int perturb, int keep_artifacts) {
     o.perturb = perturb != 0;
     SYS->solve(o, keep_artifacts != 0);
 }
+// Decomposer::SinglePass (assemble/mod.rs:169-210)
+ORC_API void orc_solve_single_pass(void* s, int perturb) {
+    fiksi::SolvingOptions o;
+    o.perturb = perturb != 0;
+    SYS->solve_single_pass(o);
+}
+// The sequence of strongly connected expression sets of all components: call with NULL arrays for the
+// sizes (n_steps, total free variables, total expressions), then with arrays.
+ORC_API void orc_single_pass_plan(void* s, uint32_t* sizes3, uint32_t* free_ptr, uint32_t* free_vars, uint32_t* expr_ptr,
+                                  uint32_t* exprs) {
+    std::vector<fiksi::StronglyConnectedExpressions> plan;
+    fiksi::System copy = *SYS;  // the dry run still scales / perturbs: keep the caller's system untouched
+    fiksi::SolvingOptions o;
+    copy.solve_single_pass(o, &plan, true);
+    uint32_t nf = 0, ne = 0;
+    for (auto& p : plan) { nf += (uint32_t)p.free_variables.size(); ne += (uint32_t)p.expressions.size(); }
+    if (sizes3) { sizes3[0] = (uint32_t)plan.size(); sizes3[1] = nf; sizes3[2] = ne; }
+    if (!free_ptr || !free_vars || !expr_ptr || !exprs) return;
+    uint32_t af = 0, ae = 0;
+    for (size_t k = 0; k < plan.size(); k++) {
+        free_ptr[k] = af; expr_ptr[k] = ae;
+        for (uint32_t v : plan[k].free_variables) free_vars[af++] = v;
+        for (uint32_t e : plan[k].expressions) exprs[ae++] = e;
+    }
+    free_ptr[plan.size()] = af; expr_ptr[plan.size()] = ae;
+}
 ORC_API uint32_t orc_num_reports(void* s) { return (uint32_t)SYS->last_reports.size(); }
 ORC_API void orc_get_report(void* s, uint32_t i, fk_report* out, char* trace, uint32_t cap) {
     const fiksi::LmReport& r = SYS->last_reports[i];
