@@ -273,6 +273,10 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["single_sketch"] = {"error": str(e)}
             try:
+                line["single_pass"] = single_pass_side(fk, wl)
+            except Exception as e:  # noqa: BLE001
+                line["single_pass"] = {"error": str(e)}
+            try:
                 line["lbfgs"] = lbfgs_side(fk, wl, local_rank)
             except Exception as e:  # noqa: BLE001
                 line["lbfgs"] = {"error": str(e)}
@@ -312,6 +316,39 @@ def single_sketch_latency(fk, wl):
             "gpu_us_per_solve": gpu_us, "cpu_port_us_per_solve_incl_symbolic": cpu_us,
             "same_trace": bool(rg["trace_hash"] == ro["trace_hash"]),
             "note": "one sketch cannot amortise a kernel launch and two host<->device copies; batches can (see value / config4_lm)"}
+
+
+def single_pass_side(fk, wl):
+    """SURVEY 8f-1: Decomposer::SinglePass on a batch of hinged-triangle chains (fiksi_bench.rs shape, 16
+    triangles = 34 variables): one batched LM launch per strongly connected set, beside Decomposer::None on
+    the same batch and the CPU restatement of the SinglePass loop."""
+    import numpy as np
+    import oracle
+    n = 16384
+    w = wl.hinged_triangles(16, n)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    topo.batch_solve_single_pass(v[:256], p[:256])
+    t0 = time.perf_counter()
+    vg, rg = topo.batch_solve_single_pass(v, p)
+    sp_s = time.perf_counter() - t0
+    topo.batch_solve(v[:256], p[:256])
+    t0 = time.perf_counter()
+    x, rep = topo.batch_solve(v, p)
+    none_s = time.perf_counter() - t0
+    ns = 512
+    op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+    t0 = time.perf_counter()
+    same = True
+    for k in range(ns):
+        opk, keepk = oracle.make_problem(v[k], w.kind, w.idx, p[k], w.free_vars, w.rows)
+        vo, ro = oracle.single_pass_problem(opk, v[k])
+        same = same and np.array_equal(ro["trace_hash"], rg[k]["trace_hash"])
+    cpu_s = time.perf_counter() - t0
+    return {"workload": "16,384 hinged chains of 16 triangles (34 variables, 48 rows)", "steps": int(rg.shape[1]),
+            "gpu_single_pass_sketches_per_s": n / sp_s, "gpu_decomposer_none_sketches_per_s": n / none_s,
+            "cpu_port_single_pass_sketches_per_s_1core": ns / cpu_s, "traces_equal_on_sample": bool(same),
+            "fraction_converged_single_pass": float(np.mean(rg["ssr"] < 1e-8))}
 
 
 def lbfgs_side(fk, wl, device):

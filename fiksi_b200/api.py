@@ -69,6 +69,19 @@ class Topology:
         out["info"] = {n: getattr(info, n) for n, _ in Info._fields_}
         return out
 
+    def batch_solve_single_pass(self, vars_, param, n_gpus=1):
+        """fk_batch_solve_single_pass: Decomposer::SinglePass on a uniform batch; returns (vars after the
+        pass [n][n_vars], reports [n][steps])."""
+        v = np.array(vars_, dtype=np.float64, order="C")
+        param = np.ascontiguousarray(param, dtype=np.float64)
+        n = v.shape[0]
+        steps = C.c_uint32(0)
+        check(lib().fk_batch_solve_single_pass(self._h, 0, None, None, None, C.byref(steps), n_gpus))
+        reports = np.zeros((n, max(steps.value, 1)), dtype=REPORT_DTYPE)
+        check(lib().fk_batch_solve_single_pass(self._h, n, ptr(v, C.c_double), ptr(param, C.c_double),
+                                               reports.ctypes.data_as(C.POINTER(FkReport)), C.byref(steps), n_gpus))
+        return v, reports[:, :steps.value]
+
     def batch_solve_lbfgs(self, vars_, param, device=0):
         """fk_batch_solve_lbfgs: Optimizer::LBfgs (fiksi/src/solve/lbfgs.rs) on a uniform batch."""
         vars_ = np.ascontiguousarray(vars_, dtype=np.float64)

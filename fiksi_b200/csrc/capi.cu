@@ -15,6 +15,7 @@
 #include "../../include/fiksi_b200.h"
 #include "lm_kernels.cuh"
 #include "multifrontal.cuh"
+#include "single_pass.hpp"
 #include "sparse_path.cuh"
 #include "symbolic.hpp"
 
@@ -278,6 +279,47 @@ int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, ui
         for (size_t k = 0; k < seq.size(); k++) {
             launches[3 * k] = (uint32_t)seq[k].kind; launches[3 * k + 1] = seq[k].first; launches[3 * k + 2] = seq[k].count;
         }
+    return FK_OK;
+}
+
+// ---- Decomposer::SinglePass on a uniform batch ---------------------------------------------------------
+int fk_batch_solve_single_pass(const fk_topology* topo, uint32_t n, double* vars, const double* param, fk_report* reports,
+                               uint32_t* n_steps, int n_gpus) {
+    if (!topo || (n && (!vars || (!param && topo->t.n_expr)))) return fail(FK_ERR_INVALID, "null argument");
+    const fk::Topology& t = topo->t;
+    std::vector<std::vector<uint32_t>> var_exprs(t.n_vars), expr_vars(t.n_expr);
+    for (uint32_t e = 0; e < t.n_expr; e++) {
+        uint32_t sv[8];
+        const int a = fk::expand_slots(t.kind[e], &t.idx[4 * (size_t)e], sv);
+        expr_vars[e].assign(sv, sv + a);
+        for (int k = 0; k < a; k++) var_exprs[sv[k]].push_back(e);
+    }
+    fk::SinglePassPlanner planner(var_exprs, expr_vars);
+    const std::vector<fk::SinglePassStep> plan = planner.plan(t.free_vars);
+    if (n_steps) *n_steps = (uint32_t)plan.size();
+    if (n == 0) return FK_OK;
+    std::vector<double> out;
+    std::vector<fk_report> reps;
+    for (size_t st = 0; st < plan.size(); st++) {
+        const fk::SinglePassStep& step = plan[st];
+        fk_problem p{};
+        p.n_vars = t.n_vars; p.vars = vars;  // structure only
+        p.n_expr = t.n_expr; p.kind = t.kind.data(); p.idx = t.idx.data(); p.param = param;
+        p.n_free = (uint32_t)step.free_variables.size(); p.free_vars = step.free_variables.data();
+        p.n_rows = (uint32_t)step.expressions.size(); p.rows = step.expressions.data();
+        fk_topology* sub = nullptr;
+        int rc = fk_topology_create(&p, &sub);
+        if (rc != FK_OK) return rc;
+        out.assign((size_t)n * p.n_free, 0.0);
+        reps.assign(n, fk_report{});
+        rc = fk_batch_solve(sub, n, vars, param, out.data(), reps.data(), n_gpus);
+        fk_topology_destroy(sub);
+        if (rc != FK_OK) return rc;
+        for (uint32_t k = 0; k < n; k++) {  // assemble/mod.rs:201-208: later sets read these as fixed values
+            for (uint32_t f = 0; f < p.n_free; f++) vars[(size_t)k * t.n_vars + step.free_variables[f]] = out[(size_t)k * p.n_free + f];
+            if (reports) reports[(size_t)k * plan.size() + st] = reps[k];
+        }
+    }
     return FK_OK;
 }
 

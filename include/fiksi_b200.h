@@ -234,6 +234,16 @@ FK_API void fk_host_free(void* p);
 FK_API int fk_batch_plan_eval(fk_batch_plan* plan, int mode, void* stream);
 FK_API int fk_batch_plan_eval_download(fk_batch_plan* plan, double* out_r, double* out_j, void* stream);
 
+/* ---- Decomposer::SinglePass on a uniform batch ------------------------------------------ */
+/* The loop of fiksi/src/assemble/mod.rs:169-210 for n sketches sharing one topology whose free set is one
+ * connected component: the plan (maximum matching + strongly connected expression sets,
+ * analyze/graph/equations.rs, over ALL n_expr expressions of the topology) is computed once on the host,
+ * then every set is ONE batched LM launch over all n sketches, later sets seeing earlier results as fixed
+ * values.  vars[n][n_vars] is updated in place (scaled / perturbed by the caller as for fk_batch_solve);
+ * reports[n][steps] (may be NULL), *n_steps receives the number of sets. */
+FK_API int fk_batch_solve_single_pass(const fk_topology* topo, uint32_t n, double* vars, const double* param,
+                                      fk_report* reports, uint32_t* n_steps, int n_gpus);
+
 /* ---- L-BFGS ----------------------------------------------------------------------------- */
 /* == lbfgs(problem, variables), fiksi/src/solve/lbfgs.rs:20 (Optimizer::LBfgs, assemble/mod.rs:155-157)
  * for n sketches sharing one topology: vars[n][n_vars] / param[n][n_expr] scaled and perturbed exactly

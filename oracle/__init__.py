@@ -79,7 +79,8 @@ def lib() -> C.CDLL:
                      "orc_line_line_parallelism", "orc_line_line_perpendicularity",
                      "orc_line_circle_tangency", "orc_num_variables", "orc_num_expressions",
                      "orc_num_constraints", "orc_num_reports", "orc_num_components",
-                     "orc_component_sizes", "orc_prepared_count", "orc_element_variable", "orc_system_analyze"):
+                     "orc_component_sizes", "orc_prepared_count", "orc_element_variable", "orc_system_analyze",
+                     "orc_single_pass_problem"):
             getattr(L, name).restype = C.c_uint32
         _lib = L
     return _lib
@@ -278,6 +279,14 @@ def lbfgs_solve_batch_uniform(topo_problem, vars_, param, threads=1):
     secs = lib().orc_lbfgs_solve_batch_uniform(C.byref(topo_problem), n, _p(vars_, C.c_double), _p(param, C.c_double),
                                                _p(out, C.c_double), reports.ctypes.data_as(C.POINTER(FkReport)), threads)
     return out, reports, secs
+
+
+def single_pass_problem(problem, vars_, cap=4096):
+    """assemble/mod.rs:169-210 on one flattened component: returns (vars after the pass, reports)."""
+    v = np.array(vars_, dtype=np.float64)
+    reports = np.zeros(cap, dtype=REPORT_DTYPE)
+    n = lib().orc_single_pass_problem(C.byref(problem), _p(v, C.c_double), reports.ctypes.data_as(C.POINTER(FkReport)), C.c_uint32(cap))
+    return v, reports[:n]
 
 
 def analyze(vars_, kind, idx, param):

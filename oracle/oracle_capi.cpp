@@ -350,6 +350,42 @@ ORC_API double orc_lbfgs_solve_batch_uniform(const fk_problem* topo, uint32_t n,
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ---- Decomposer::SinglePass on a flattened problem ---------------------------------------------------
+// The loop of assemble/mod.rs:169-210 for ONE component given as fk_problem (all n_expr expressions form
+// the equation graph, free_vars is the component's free set): vars_io[n_vars] in/out (scaled,
+// perturbed by the caller), reports: one per strongly connected set, up to cap; returns their number.
+ORC_API uint32_t orc_single_pass_problem(const fk_problem* p, double* vars_io, fk_report* reports, uint32_t cap) {
+    std::vector<fiksi::Expression> ex(p->n_expr);
+    fiksi::ExpressionGraph g;
+    g.insert_variables((int)p->n_vars);
+    for (uint32_t e = 0; e < p->n_expr; e++) {
+        ex[e].kind = p->kind[e];
+        for (int k = 0; k < 4; k++) ex[e].idx[k] = p->idx[4 * e + k];
+        ex[e].param = p->param[e];
+        uint32_t vi[8];
+        int a = fiksi::variable_indices(ex[e], vi);
+        g.insert_expression(vi, a);
+    }
+    std::set<uint32_t> free_set(p->free_vars, p->free_vars + p->n_free);
+    fiksi::SinglePassPlanner planner(g, free_set);
+    uint32_t count = 0;
+    for (const fiksi::StronglyConnectedExpressions& scc : planner.plan()) {
+        std::vector<double> x;
+        for (uint32_t fv : scc.free_variables) x.push_back(vars_io[fv]);
+        fiksi::Subsystem sub(vars_io, p->n_vars, ex.data(), scc.free_variables, scc.expressions);
+        fiksi::LmReport rep;
+        fiksi::levenberg_marquardt(sub, x.data(), rep, false);
+        for (size_t k = 0; k < scc.free_variables.size(); k++) vars_io[scc.free_variables[k]] = x[k];
+        if (reports && count < cap) {
+            fk_report& r = reports[count];
+            r.exit_reason = rep.exit_reason; r.outer_iters = rep.outer_iters; r.factorizations = rep.factorizations;
+            r.accepted = rep.accepted; r.ssr = rep.ssr; r.lambda = rep.lambda; r.trace_hash = rep.trace_hash;
+        }
+        count++;
+    }
+    return count;
+}
+
 // ---- System::analyze ------------------------------------------------------------------------
 // analyze/numerical/mod.rs:123-147 on a flattened problem: all n_vars variables are columns, all
 // n_expr expressions are rows (in order).  out_independent[n_expr].

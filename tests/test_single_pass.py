@@ -84,3 +84,24 @@ def test_single_pass_chain_reaches_the_reference_threshold(oracle):
     assert np.sqrt(np.mean(res ** 2)) < 1e-4                      # fiksi/src/tests/mod.rs:13
     assert np.max(np.abs(np.asarray(so.variables) - np.asarray(sp.variables))) <= 1e-9 * np.max(np.abs(so.variables))
     assert len(sp.reports()) == len(so.reports()) == len(so.single_pass_plan())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("maker", ["truss", "cad_mix", "hinged"])
+def test_batched_single_pass_matches_oracle(oracle, maker):
+    """fk_batch_solve_single_pass: one batched LM launch per strongly connected set, over all sketches, vs
+    the oracle running assemble/mod.rs:169-210 sketch by sketch on the same prepared inputs."""
+    import fiksi_b200 as fk
+    from fiksi_b200 import workloads as wl
+    w = {"truss": lambda: wl.truss(96), "cad_mix": lambda: wl.cad_mix(200), "hinged": lambda: wl.hinged_triangles(8, 64)}[maker]()
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    vg, rg = topo.batch_solve_single_pass(v, p)
+    for s in range(0, w.n, 9):
+        op, keep = oracle.make_problem(v[s], w.kind, w.idx, p[s], w.free_vars, w.rows)
+        vo, ro = oracle.single_pass_problem(op, v[s])
+        assert len(ro) == rg.shape[1]
+        assert np.array_equal(ro["trace_hash"], rg[s]["trace_hash"]) and np.array_equal(ro["exit_reason"], rg[s]["exit_reason"])
+        assert np.max(np.abs(vg[s] - vo)) <= 1e-9 * np.max(np.abs(vo))
+    if maker == "hinged":
+        assert rg.shape[1] > 1          # the chain really decomposes
