@@ -324,18 +324,21 @@ def single_pass_side(fk, wl):
     the same batch and the CPU restatement of the SinglePass loop."""
     import numpy as np
     import oracle
-    n = 16384
+    n = 131072
     w = wl.hinged_triangles(16, n)
     v, p, scale = w.prepare()
     topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
     topo.batch_solve_single_pass(v[:256], p[:256])
-    t0 = time.perf_counter()
-    vg, rg = topo.batch_solve_single_pass(v, p)
-    sp_s = time.perf_counter() - t0
+    sp_s = none_s = float("inf")
+    for _ in range(3):  # host buffers are pageable here: best of three
+        t0 = time.perf_counter()
+        vg, rg = topo.batch_solve_single_pass(v, p)
+        sp_s = min(sp_s, time.perf_counter() - t0)
     topo.batch_solve(v[:256], p[:256])
-    t0 = time.perf_counter()
-    x, rep = topo.batch_solve(v, p)
-    none_s = time.perf_counter() - t0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        x, rep = topo.batch_solve(v, p)
+        none_s = min(none_s, time.perf_counter() - t0)
     ns = 512
     op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
     t0 = time.perf_counter()
@@ -345,7 +348,7 @@ def single_pass_side(fk, wl):
         vo, ro = oracle.single_pass_problem(opk, v[k])
         same = same and np.array_equal(ro["trace_hash"], rg[k]["trace_hash"])
     cpu_s = time.perf_counter() - t0
-    return {"workload": "16,384 hinged chains of 16 triangles (34 variables, 48 rows)", "steps": int(rg.shape[1]),
+    return {"workload": "131,072 hinged chains of 16 triangles (34 variables, 48 rows), host buffers, device-resident between sets", "steps": int(rg.shape[1]),
             "gpu_single_pass_sketches_per_s": n / sp_s, "gpu_decomposer_none_sketches_per_s": n / none_s,
             "cpu_port_single_pass_sketches_per_s_1core": ns / cpu_s, "traces_equal_on_sample": bool(same),
             "fraction_converged_single_pass": float(np.mean(rg["ssr"] < 1e-8))}

@@ -134,6 +134,10 @@ struct fk_topology {
     std::map<int, std::unique_ptr<DeviceProgram>> programs;
     std::map<int, std::unique_ptr<DevicePipeline>> pipelines;
     std::map<int, std::unique_ptr<fk::SparseSolver>> sparse;  // path 2: one solver per device
+    std::mutex sp_mu;                   // SinglePass plan: one sub-topology per strongly connected set
+    bool sp_planned = false;
+    std::vector<fk_topology*> sp_subs;
+    ~fk_topology();
 
     int sparse_for(int device, fk::SparseSolver** out, std::string* err) {
         std::lock_guard<std::mutex> lock(mu);
@@ -187,6 +191,10 @@ struct fk_batch_plan {
         cudaFree(d_vars); cudaFree(d_params); cudaFree(d_out); cudaFree(d_er); cudaFree(d_ej); cudaFree(d_rep);
     }
 };
+
+fk_topology::~fk_topology() {
+    for (fk_topology* s : sp_subs) delete s;
+}
 
 void DevicePipeline::release() {
     if (device >= 0) cudaSetDevice(device);
@@ -283,43 +291,133 @@ int fk_topology_supernodal(const fk_topology* topo, fk_supernodal_info* info, ui
 }
 
 // ---- Decomposer::SinglePass on a uniform batch ---------------------------------------------------------
-int fk_batch_solve_single_pass(const fk_topology* topo, uint32_t n, double* vars, const double* param, fk_report* reports,
-                               uint32_t* n_steps, int n_gpus) {
-    if (!topo || (n && (!vars || (!param && topo->t.n_expr)))) return fail(FK_ERR_INVALID, "null argument");
-    const fk::Topology& t = topo->t;
-    std::vector<std::vector<uint32_t>> var_exprs(t.n_vars), expr_vars(t.n_expr);
-    for (uint32_t e = 0; e < t.n_expr; e++) {
-        uint32_t sv[8];
-        const int a = fk::expand_slots(t.kind[e], &t.idx[4 * (size_t)e], sv);
-        expr_vars[e].assign(sv, sv + a);
-        for (int k = 0; k < a; k++) var_exprs[sv[k]].push_back(e);
-    }
-    fk::SinglePassPlanner planner(var_exprs, expr_vars);
-    const std::vector<fk::SinglePassStep> plan = planner.plan(t.free_vars);
-    if (n_steps) *n_steps = (uint32_t)plan.size();
-    if (n == 0) return FK_OK;
-    std::vector<double> out;
-    std::vector<fk_report> reps;
-    for (size_t st = 0; st < plan.size(); st++) {
-        const fk::SinglePassStep& step = plan[st];
-        fk_problem p{};
-        p.n_vars = t.n_vars; p.vars = vars;  // structure only
-        p.n_expr = t.n_expr; p.kind = t.kind.data(); p.idx = t.idx.data(); p.param = param;
-        p.n_free = (uint32_t)step.free_variables.size(); p.free_vars = step.free_variables.data();
-        p.n_rows = (uint32_t)step.expressions.size(); p.rows = step.expressions.data();
-        fk_topology* sub = nullptr;
-        int rc = fk_topology_create(&p, &sub);
-        if (rc != FK_OK) return rc;
-        out.assign((size_t)n * p.n_free, 0.0);
-        reps.assign(n, fk_report{});
-        rc = fk_batch_solve(sub, n, vars, param, out.data(), reps.data(), n_gpus);
-        fk_topology_destroy(sub);
-        if (rc != FK_OK) return rc;
-        for (uint32_t k = 0; k < n; k++) {  // assemble/mod.rs:201-208: later sets read these as fixed values
-            for (uint32_t f = 0; f < p.n_free; f++) vars[(size_t)k * t.n_vars + step.free_variables[f]] = out[(size_t)k * p.n_free + f];
-            if (reports) reports[(size_t)k * plan.size() + st] = reps[k];
+// The plan (one sub-topology per strongly connected set) is built once per topology and cached.  Variables
+// and parameters of a shard stay resident on its device for the whole pass: per set one batched LM launch over
+// all sketches and one scatter of the solved values back into the variable rows (assemble/mod.rs:201-208).
+static int single_pass_plan_for(fk_topology* topo, const std::vector<fk_topology*>** out) {
+    std::lock_guard<std::mutex> lock(topo->sp_mu);
+    if (!topo->sp_planned) {
+        const fk::Topology& t = topo->t;
+        std::vector<std::vector<uint32_t>> var_exprs(t.n_vars), expr_vars(t.n_expr);
+        for (uint32_t e = 0; e < t.n_expr; e++) {
+            uint32_t sv[8];
+            const int a = fk::expand_slots(t.kind[e], &t.idx[4 * (size_t)e], sv);
+            expr_vars[e].assign(sv, sv + a);
+            for (int k = 0; k < a; k++) var_exprs[sv[k]].push_back(e);
         }
+        fk::SinglePassPlanner planner(var_exprs, expr_vars);
+        const std::vector<fk::SinglePassStep> plan = planner.plan(t.free_vars);
+        std::vector<fk_topology*> subs;
+        for (const fk::SinglePassStep& step : plan) {
+            fk_problem p{};
+            p.n_vars = t.n_vars; p.n_expr = t.n_expr; p.kind = t.kind.data(); p.idx = t.idx.data();
+            p.n_free = (uint32_t)step.free_variables.size(); p.free_vars = step.free_variables.data();
+            p.n_rows = (uint32_t)step.expressions.size(); p.rows = step.expressions.data();
+            fk_topology* sub = nullptr;
+            int rc = fk_topology_create(&p, &sub);
+            if (rc == FK_OK && sub->t.path == 2) {
+                fk_topology_destroy(sub);
+                rc = fail(FK_ERR_TOO_LARGE, "a strongly connected set needs the global sparse path; use fk_system_solve_opts");
+            }
+            if (rc != FK_OK) {
+                for (fk_topology* s : subs) fk_topology_destroy(s);
+                return rc;
+            }
+            subs.push_back(sub);
+        }
+        topo->sp_subs = std::move(subs);
+        topo->sp_planned = true;
     }
+    *out = &topo->sp_subs;
+    return FK_OK;
+}
+
+static int single_pass_device_range(fk_topology* topo, const std::vector<fk_topology*>& subs, int device, uint32_t lo, uint32_t hi,
+                                    double* vars, const double* param, fk_report* reports, std::string* err) {
+    const fk::Topology& t = topo->t;
+    const size_t steps = subs.size();
+    uint32_t max_free = 1;
+    for (const fk_topology* s : subs) max_free = std::max(max_free, s->t.n_free);
+    int rc = FK_OK;
+    double *d_vars = nullptr, *d_params = nullptr, *d_out = nullptr;
+    fk_report *d_rep = nullptr, *d_rep_t = nullptr;
+    cudaStream_t stream = nullptr;
+    auto done = [&](int code) {
+        if (stream) cudaStreamDestroy(stream);
+        cudaFree(d_vars); cudaFree(d_params); cudaFree(d_out); cudaFree(d_rep); cudaFree(d_rep_t);
+        if (code != FK_OK && err) *err = g_error;
+        return code;
+    };
+#define SP_CU(call)                                              \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return done(cuda_fail(e_, #call)); \
+    } while (0)
+    SP_CU(cudaSetDevice(device));
+    // bound the resident set of one chunk to ~8 GiB
+    const size_t per_sketch = sizeof(double) * ((size_t)t.n_vars + t.n_expr + max_free) + 2 * sizeof(fk_report) * std::max<size_t>(1, steps);
+    const uint32_t chunk = (uint32_t)std::min<uint64_t>(hi - lo, std::max<uint64_t>(1, (8ull << 30) / per_sketch));
+    SP_CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    SP_CU(cudaMalloc(&d_vars, sizeof(double) * std::max<size_t>(1, (size_t)chunk * t.n_vars)));
+    SP_CU(cudaMalloc(&d_params, sizeof(double) * std::max<size_t>(1, (size_t)chunk * t.n_expr)));
+    SP_CU(cudaMalloc(&d_out, sizeof(double) * (size_t)chunk * max_free));
+    SP_CU(cudaMalloc(&d_rep, sizeof(fk_report) * std::max<size_t>(1, (size_t)chunk * steps)));
+    if (reports) SP_CU(cudaMalloc(&d_rep_t, sizeof(fk_report) * std::max<size_t>(1, (size_t)chunk * steps)));
+    std::vector<const fk::DevProgram*> progs(steps, nullptr);
+    for (size_t st = 0; st < steps; st++) {
+        rc = subs[st]->program_for(device, &progs[st]);
+        if (rc != FK_OK) return done(rc);
+    }
+    for (uint32_t at = lo; at < hi; at += chunk) {
+        const uint32_t cnt = std::min(chunk, hi - at);
+        SP_CU(cudaMemcpyAsync(d_vars, vars + (size_t)at * t.n_vars, sizeof(double) * (size_t)cnt * t.n_vars, cudaMemcpyHostToDevice, stream));
+        if (t.n_expr) SP_CU(cudaMemcpyAsync(d_params, param + (size_t)at * t.n_expr, sizeof(double) * (size_t)cnt * t.n_expr, cudaMemcpyHostToDevice, stream));
+        for (size_t st = 0; st < steps; st++) {
+            int e = fk::launch_batch_lm(*progs[st], cnt, d_vars, d_params, d_out, d_rep + st * (size_t)cnt, stream);
+            if (e == 0) e = fk::launch_scatter_free(progs[st]->free_vars, progs[st]->n, t.n_vars, cnt, d_out, d_vars, stream);
+            if (e != 0) return done(cuda_fail((cudaError_t)e, "launch SinglePass set"));
+        }
+        SP_CU(cudaMemcpyAsync(vars + (size_t)at * t.n_vars, d_vars, sizeof(double) * (size_t)cnt * t.n_vars, cudaMemcpyDeviceToHost, stream));
+        if (reports && steps) {
+            const int e = fk::launch_transpose_reports(d_rep, d_rep_t, cnt, (uint32_t)steps, stream);
+            if (e != 0) return done(cuda_fail((cudaError_t)e, "launch fk_transpose_reports_kernel"));
+            SP_CU(cudaMemcpyAsync(reports + (size_t)at * steps, d_rep_t, sizeof(fk_report) * (size_t)cnt * steps, cudaMemcpyDeviceToHost, stream));
+        }
+        SP_CU(cudaStreamSynchronize(stream));
+    }
+#undef SP_CU
+    return done(FK_OK);
+}
+
+int fk_batch_solve_single_pass(const fk_topology* topo_c, uint32_t n, double* vars, const double* param, fk_report* reports,
+                               uint32_t* n_steps, int n_gpus) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo || (n && (!vars || (!param && topo->t.n_expr)))) return fail(FK_ERR_INVALID, "null argument");
+    const std::vector<fk_topology*>* subs = nullptr;
+    int rc = single_pass_plan_for(topo, &subs);
+    if (rc != FK_OK) return rc;
+    if (n_steps) *n_steps = (uint32_t)subs->size();
+    if (n == 0) return FK_OK;
+    const int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
+    if (n_gpus == 1) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+        return single_pass_device_range(topo, *subs, cur, 0, n, vars, param, reports, nullptr);
+    }
+    std::vector<int> rcs(n_gpus, FK_OK);
+    std::vector<std::string> errs(n_gpus);
+    std::vector<std::thread> pool;
+    for (int g = 0; g < n_gpus; g++) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * g / n_gpus), hi = (uint32_t)((uint64_t)n * (g + 1) / n_gpus);
+        pool.emplace_back([=, &rcs, &errs]() {
+            if (hi > lo) rcs[g] = single_pass_device_range(topo, *subs, g, lo, hi, vars, param, reports, &errs[g]);
+        });
+    }
+    for (auto& th : pool) th.join();
+    for (int g = 0; g < n_gpus; g++)
+        if (rcs[g] != FK_OK) return fail(rcs[g], errs[g]);
     return FK_OK;
 }
 

@@ -1017,6 +1017,45 @@ int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* v
     }
 }
 
+__global__ void fk_scatter_free_kernel(const uint32_t* __restrict__ free_vars, uint32_t n_free, uint32_t n_vars, uint64_t total,
+                                       const double* __restrict__ free_out, double* __restrict__ vars) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = i / n_free;
+        const uint32_t f = (uint32_t)(i - k * n_free);
+        vars[k * n_vars + free_vars[f]] = free_out[i];
+    }
+}
+
+int launch_scatter_free(const uint32_t* d_free_vars, uint32_t n_free, uint32_t n_vars, uint32_t n_sketches, const double* free_out,
+                        double* vars, void* stream) {
+    const uint64_t total = (uint64_t)n_sketches * n_free;
+    if (total == 0) return 0;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, 148u * 8u);
+    fk_scatter_free_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_free_vars, n_free, n_vars, total, free_out, vars);
+    return (int)cudaGetLastError();
+}
+
+__global__ void fk_transpose_reports_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n, uint32_t steps) {
+    constexpr uint32_t W = sizeof(fk_report) / 8;
+    const uint64_t total = (uint64_t)n * steps * W;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(i % W);
+        const uint64_t ks = i / W;  // k * steps + st
+        const uint64_t k = ks / steps;
+        const uint32_t st = (uint32_t)(ks - k * steps);
+        out[i] = in[((uint64_t)st * n + k) * W + w];
+    }
+}
+
+int launch_transpose_reports(const fk_report* in, fk_report* out, uint32_t n_sketches, uint32_t steps, void* stream) {
+    static_assert(sizeof(fk_report) % 8 == 0, "fk_report is moved as 64-bit words");
+    const uint64_t total = (uint64_t)n_sketches * steps * (sizeof(fk_report) / 8);
+    if (total == 0) return 0;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, 148u * 16u);
+    fk_transpose_reports_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint64_t*)in, (uint64_t*)out, n_sketches, steps);
+    return (int)cudaGetLastError();
+}
+
 int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                       double* out_r, double* out_j, int mode, void* stream) {
     if (n_sketches == 0 || prog.m == 0) return 0;

@@ -54,6 +54,12 @@ int launch_batch_analyze(uint32_t n_vars, uint32_t n_expr, const uint8_t* kinds,
 // of the Jacobian.  Returns cudaErrorInvalidConfiguration when the topology does not take a tile path.
 int launch_batch_lbfgs(const DevProgram& prog, const uint32_t* d_jcolptr, const uint32_t* d_jrow, uint32_t n_sketches, const double* vars,
                        const double* params, double* free_out, fk_report* reports, void* stream);
+// SinglePass (fiksi/src/assemble/mod.rs:201-208): writes the solved free values of one set back into the
+// resident variable rows so that later sets read them as fixed values.  vars[k][free_vars[f]] = free_out[k][f].
+int launch_scatter_free(const uint32_t* d_free_vars, uint32_t n_free, uint32_t n_vars, uint32_t n_sketches, const double* free_out,
+                        double* vars, void* stream);
+// reports_out[k][st] = reports_in[st][k] (per-set report planes -> the caller's per-sketch rows).
+int launch_transpose_reports(const fk_report* in, fk_report* out, uint32_t n_sketches, uint32_t steps, void* stream);
 const char* lm_kernel_name();
 // DFMA throughput microbenchmark on the current device (TFLOP/s, 2 flops per DFMA).
 int measure_fp64_peak(double* tflops);
