@@ -21,6 +21,7 @@ constexpr int kWarpsPerCta = 8;
 constexpr int TB = 64;            // tile order of the big path
 constexpr int KC = 16;            // pivot columns staged per step of the micro-kernel
 constexpr int kTileThreads = 256;
+constexpr uint32_t kChainMaxCtas = 128;  // chained solve levels: all chunk CTAs resident at once
 
 __device__ __forceinline__ void flag_pivot(int* status, double d) {
     if (d != d) atomicMax(status, 2);
@@ -720,6 +721,224 @@ __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, d
     group_sync<G>();
 }
 
+// ---- chained solves of the wide levels near the root -------------------------------------------------
+// Near the root a level holds a handful of supernodes with hundreds of pivot columns each; one CTA per
+// supernode (mf_big_solve_kernel) then walks a long dependent chain alone.  Here a front is cut into
+// 64-row chunks, one CTA each, all resident at once (the host only takes this path when the level
+// needs fewer CTAs than the device has SMs).  Forward: the CTA of pivot chunk c applies the updates of
+// the pivot blocks b < c as their solutions are published (polled in place, see below; the panel tile
+// of the next block is prefetched into registers while waiting), multiplies with the
+// precomputed inverse of its own 64x64 unit triangle (mf_chain_inv_kernel, once per factorisation)
+// and publishes y_c; the CTAs of the rows below the pivot block consume all blocks and leave the
+// update vector.  Backward mirrors it from the last pivot block up.  A thread owns a quarter of one
+// row (lanes 4r..4r+3), so every reduction is two shuffles in a fixed order and the loop over the
+// awaited blocks has no CTA barrier; one link of the chain costs about a microsecond.
+#ifdef FK_CHAIN_PROFILE
+__device__ __forceinline__ long long global_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+    return v;
+}
+#define FK_CSTAMP(k) do { if (threadIdx.x == 0) ((long long*)D.upd)[blockIdx.x * 8 + (k)] = global_ns(); } while (0)
+#else
+#define FK_CSTAMP(k) do { } while (0)
+#endif
+// Published solution values are polled in place: the buffer is filled with an all-ones bit pattern (a NaN
+// no computation produces) before the solve, a producer stores each 8-byte value once, and a consumer
+// re-reads its values at GPU scope until none of them is the sentinel.  A value is either absent or
+// final, so no fence, flag or second round trip is needed.
+__device__ __forceinline__ double ld_relaxed(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool is_unpublished(double v) { return __double_as_longlong(v) == -1ll; }
+// the 16 values q, q+4, ... of a published 64-vector (entries >= count read as zero)
+__device__ __forceinline__ void poll16(const double* base, uint32_t q, uint32_t count, double (&v)[16]) {
+    bool missing;
+    do {
+        missing = false;
+#pragma unroll
+        for (int u = 0; u < 16; u++) v[u] = q + 4u * u < count ? ld_relaxed(base + q + 4 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) missing = missing || is_unpublished(v[u]);
+    } while (missing);
+}
+__device__ __forceinline__ double quad_sum(const double (&a4)[4]) {
+    double v = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+    return v;
+}
+
+// X = L_kk^-1 of one 64x64 unit-lower pivot tile (row-major, zero / identity padded), one thread per column.
+constexpr size_t kChainInvSmem = 2 * (size_t)TB * kTsLd * sizeof(double);
+__global__ void __launch_bounds__(TB)
+mf_chain_inv_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    extern __shared__ double smi[];
+    double* Ls = smi;
+    double* Xs = smi + TB * kTsLd;
+    const uint4 tk = __ldg(tasks + blockIdx.x);
+    const uint32_t s = tk.x, col0 = tk.y, nc = tk.z;
+    const uint32_t f = __ldg(D.f + s);
+    const double* Lkk = D.pan + __ldg(D.pan_off + s) + (size_t)col0 * f + col0;
+    const uint32_t j = threadIdx.x;
+    for (uint32_t e = j; e < TB * TB; e += TB) {
+        const uint32_t ii = e & 63, k = e >> 6;
+        Ls[ii * kTsLd + k] = (ii < nc && k < ii) ? Lkk[(size_t)k * f + ii] : 0.0;
+    }
+    for (uint32_t i = 0; i < TB; i++) Xs[i * kTsLd + j] = i == j ? 1.0 : 0.0;
+    __syncthreads();
+    for (uint32_t i = j + 1; i < TB; i++) {
+        double a0 = 0.0, a1 = 0.0;
+        uint32_t k = j;
+        for (; k + 1 < i; k += 2) {
+            a0 = fma(Ls[i * kTsLd + k], Xs[k * kTsLd + j], a0);
+            a1 = fma(Ls[i * kTsLd + k + 1], Xs[(k + 1) * kTsLd + j], a1);
+        }
+        if (k < i) a0 = fma(Ls[i * kTsLd + k], Xs[k * kTsLd + j], a0);
+        Xs[i * kTsLd + j] = -(a0 + a1);
+    }
+    __syncthreads();
+    double* X = D.winv + (size_t)(__ldg(D.winv_blk + s) + col0 / TB) * (TB * TB);
+    for (uint32_t e = j; e < TB * TB; e += TB) X[e] = Xs[(e >> 6) * kTsLd + (e & 63)];
+}
+
+__global__ void __launch_bounds__(256)
+mf_chain_fwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ w, double* __restrict__ pub) {
+    __shared__ double t[TB];
+    const uint4 tk = __ldg(tasks + blockIdx.x);
+    const uint32_t s = tk.x, row0 = tk.y, nr = tk.z;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s), blk0 = __ldg(D.winv_blk + s);
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    const uint32_t B = (ns + TB - 1) / TB;
+    const bool pivot = row0 < ns;
+    const uint32_t nwait = pivot ? row0 / TB : B;
+    const uint32_t tid = threadIdx.x, row = tid >> 2, q = tid & 3;
+    double nl[16], li[16];
+    auto prefetch = [&](uint32_t b) {
+        const uint32_t nc = min((uint32_t)TB, ns - TB * b);
+        const double* base = P + (size_t)(TB * b) * f + row0 + row;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const uint32_t k = q + 4u * u;
+            nl[u] = (row < nr && k < nc) ? __ldg(base + (size_t)k * f) : 0.0;
+        }
+    };
+    FK_CSTAMP(0);
+    if (nwait) prefetch(0);
+    if (pivot) {
+        const double* X = D.winv + (size_t)(blk0 + row0 / TB) * (TB * TB) + row * TB + q;
+#pragma unroll
+        for (int u = 0; u < 16; u++) li[u] = __ldg(X + 4 * u);
+    }
+    // the chunk's part of the front vector: right-hand side (pivot rows) + the children's update vectors
+    if (tid < TB) t[tid] = (pivot && tid < nr) ? w[c0 + row0 + tid] : 0.0;
+    __syncthreads();
+    for (uint32_t cq = __ldg(D.child_ptr + s); cq < __ldg(D.child_ptr + s + 1); cq++) {
+        const uint32_t c = __ldg(D.child + cq);
+        const uint32_t rc = __ldg(D.f + c) - __ldg(D.ns + c), ro = __ldg(D.rel_off + c);
+        // the child's rows inside this chunk (distinct targets; no dependent searches: every thread
+        // scans a strided part of the child's list)
+        for (uint32_t a = tid; a < rc; a += 256) {
+            const uint32_t r = __ldg(D.rel + ro + a) - row0;
+            if (r < nr) t[r] += D.ubuf[ro + a];
+        }
+        __syncthreads();
+    }
+    double tr = t[row];
+    for (uint32_t b = 0; b < nwait; b++) {
+        double cl[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) cl[u] = nl[u];
+        if (b + 1 < nwait) prefetch(b + 1);
+        if (b + 1 == nwait) FK_CSTAMP(1);
+        double yv[16];
+        poll16(pub + c0 + TB * b, q, min((uint32_t)TB, ns - TB * b), yv);
+        if (b + 1 == nwait) FK_CSTAMP(2);
+        double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 16; u++) a4[u & 3] = fma(cl[u], yv[u], a4[u & 3]);
+        tr -= quad_sum(a4);
+    }
+    FK_CSTAMP(3);
+    if (pivot) {
+        __syncthreads();  // (the gather phase's reads of t are long done; this orders the writes below)
+        if (q == 0) t[row] = tr;
+        __syncthreads();
+        double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 16; u++) a4[u & 3] = fma(li[u], t[q + 4 * u], a4[u & 3]);
+        const double yr = quad_sum(a4);
+        FK_CSTAMP(4);
+        if (q == 0 && row < nr) {
+            st_relaxed(pub + c0 + row0 + row, yr);
+            w[c0 + row0 + row] = yr;
+        }
+        FK_CSTAMP(5);
+    } else if (q == 0 && row < nr) {
+        D.ubuf[__ldg(D.rel_off + s) + row0 - ns + row] = tr;
+    }
+}
+
+// tasks: pivot chunks only, the last chunk of a supernode first.  tmp[c0 + j] holds the dot products of
+// column j with the ancestors' solution (mf_bwd_dot_kernel) when the front has rows below the pivot block.
+__global__ void __launch_bounds__(256)
+mf_chain_bwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ w, double* __restrict__ delta,
+                    const int32_t* __restrict__ perm, const double* __restrict__ tmp, double* __restrict__ pub) {
+    __shared__ double t[TB];
+    const uint4 tk = __ldg(tasks + blockIdx.x);
+    const uint32_t s = tk.x, col0 = tk.y, nc = tk.z;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s), blk0 = __ldg(D.winv_blk + s);
+    const double* P = D.pan + __ldg(D.pan_off + s);
+    const uint32_t B = (ns + TB - 1) / TB, c = col0 / TB;
+    const uint32_t tid = threadIdx.x, col = tid >> 2, q = tid & 3;
+    double nl[16], li[16];
+    auto prefetch = [&](uint32_t b) {  // L(rows of block b, my column), rows q, q+4, ...
+        const uint32_t nrb = min((uint32_t)TB, ns - TB * b);
+        const double* base = P + (size_t)(col0 + col) * f + TB * b + q;
+#pragma unroll
+        for (int u = 0; u < 16; u++) nl[u] = (col < nc && q + 4u * u < nrb) ? __ldg(base + 4 * u) : 0.0;
+    };
+    if (c + 1 < B) prefetch(B - 1);
+    {   // column `col` of L_cc^-1 (= row of its transpose), rows q, q+4, ...
+        const double* X = D.winv + (size_t)(blk0 + c) * (TB * TB) + (size_t)q * TB + col;
+#pragma unroll
+        for (int u = 0; u < 16; u++) li[u] = __ldg(X + 4 * u * TB);
+    }
+    double tr = 0.0;
+    if (col < nc) {
+        tr = w[c0 + col0 + col] / __ldg(P + (size_t)(col0 + col) * f + col0 + col);
+        if (f > ns) tr -= tmp[c0 + col0 + col];
+    }
+    for (uint32_t b = B - 1; b > c; b--) {
+        double cl[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) cl[u] = nl[u];
+        if (b - 1 > c) prefetch(b - 1);
+        double zv[16];
+        poll16(pub + c0 + TB * b, q, min((uint32_t)TB, ns - TB * b), zv);
+        double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 16; u++) a4[u & 3] = fma(cl[u], zv[u], a4[u & 3]);
+        tr -= quad_sum(a4);
+    }
+    if (q == 0) t[col] = tr;
+    __syncthreads();
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int u = 0; u < 16; u++) a4[u & 3] = fma(li[u], t[q + 4 * u], a4[u & 3]);
+    const double zz = quad_sum(a4);
+    if (q == 0 && col < nc) {
+        st_relaxed(pub + c0 + col0 + col, zz);
+        w[c0 + col0 + col] = zz;
+        delta[__ldg(perm + c0 + col0 + col)] = zz;
+    }
+}
+
 template <bool FORWARD>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 mf_small_solve_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint32_t* __restrict__ sub_list, uint32_t nsub,
@@ -1077,6 +1296,53 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             if (count) factor_seq_.push_back({3, first, count});
         }
     }
+    // ---- chained solves: wide levels whose 64-row chunks all fit on the device at once
+    chain_.assign(nlevels, ChainLevel());
+    chain_tasks_.clear();
+    std::fill(winv_blk.begin(), winv_blk.end(), 0u);
+    winv_blocks = 0;
+    inv_first_ = inv_count_ = 0;
+    {
+        static const bool off = std::getenv("FK_NO_CHAIN") != nullptr;  // debug / A-B knob
+        auto push_chain = [&](uint32_t a, uint32_t b, uint32_t c) {
+            chain_tasks_.push_back(a); chain_tasks_.push_back(b); chain_tasks_.push_back(c); chain_tasks_.push_back(0);
+        };
+        std::vector<uint32_t> chained;
+        for (uint32_t l = 0; l < nlevels && !off; l++) {
+            if (!level_wide_[l]) continue;
+            const std::vector<uint32_t>& L = by_level[l];
+            uint64_t ctas = 0;
+            for (uint32_t s : L) ctas += (ns[s] + TB - 1) / TB + (f[s] - ns[s] + TB - 1) / TB;
+            if (ctas > kChainMaxCtas) continue;
+            ChainLevel& c = chain_[l];
+            c.on = true;
+            for (uint32_t s : L) {
+                chained.push_back(s);
+                winv_blk[s] = winv_blocks;  // first 64x64 inverse block / first flag of the supernode
+                winv_blocks += (ns[s] + TB - 1) / TB;
+            }
+            c.fwd_first = (uint32_t)(chain_tasks_.size() / 4);
+            for (uint32_t s : L) {
+                for (uint32_t r0 = 0; r0 < ns[s]; r0 += TB) push_chain(s, r0, std::min<uint32_t>(TB, ns[s] - r0));
+                for (uint32_t r0 = ns[s]; r0 < f[s]; r0 += TB) push_chain(s, r0, std::min<uint32_t>(TB, f[s] - r0));
+            }
+            c.fwd_count = (uint32_t)(chain_tasks_.size() / 4) - c.fwd_first;
+            c.dot_first = (uint32_t)(chain_tasks_.size() / 4);
+            for (uint32_t s : L)
+                if (f[s] > ns[s])
+                    for (uint32_t j0 = 0; j0 < ns[s]; j0 += 8) push_chain(s, j0, std::min<uint32_t>(8, ns[s] - j0));
+            c.dot_count = (uint32_t)(chain_tasks_.size() / 4) - c.dot_first;
+            c.bwd_first = (uint32_t)(chain_tasks_.size() / 4);
+            for (uint32_t s : L)
+                for (uint32_t b = (ns[s] + TB - 1) / TB; b-- > 0;) push_chain(s, b * TB, std::min<uint32_t>(TB, ns[s] - b * TB));
+            c.bwd_count = (uint32_t)(chain_tasks_.size() / 4) - c.bwd_first;
+        }
+        inv_first_ = (uint32_t)(chain_tasks_.size() / 4);
+        for (uint32_t s : chained)
+            for (uint32_t r0 = 0; r0 < ns[s]; r0 += TB) push_chain(s, r0, std::min<uint32_t>(TB, ns[s] - r0));
+        inv_count_ = (uint32_t)(chain_tasks_.size() / 4) - inv_first_;
+    }
+    n_chain_flags_ = winv_blocks;
     factor_launches_ = factor_seq_.size() + (nsub ? 1 : 0);
     stats.supernodes = S; stats.small_subtrees = nsub; stats.big = nbig; stats.levels = nlevels;
     stats.max_front = max_front; stats.upd_doubles = upd_total;
@@ -1118,10 +1384,24 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     }
     MF_CU(alloc_vec(&dev_.pan, pan_total, owned_));
     MF_CU(alloc_vec(&dev_.upd, upd_total, owned_));
-    MF_CU(alloc_vec(&dev_.winv, 1, owned_));  // (inverse blocks are no longer used)
+    MF_CU(alloc_vec(&dev_.winv, std::max<size_t>(1, (size_t)sym.winv_blocks * TB * TB), owned_));  // chained levels only
     MF_CU(alloc_vec(&dev_.ubuf, rel_off[S], owned_));
     MF_CU(alloc_vec(&dev_.status, 1, owned_));
     MF_CU(alloc_vec(&d_tmp_, n, owned_));
+    {
+        const uint32_t* p = nullptr;
+        MF_CU(upload_vec(chain_tasks_, &p, owned_));
+        d_chain_tasks_ = (const uint4*)p;
+        MF_CU(alloc_vec(&d_chain_pub_, 2 * (size_t)std::max<uint32_t>(1, n), owned_));
+        int dev = 0, sms = 0;
+        MF_CU(cudaGetDevice(&dev));
+        MF_CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if ((uint32_t)sms < kChainMaxCtas + 8) {  // the chunks of a chained level must all be resident at once
+            for (ChainLevel& c : chain_) c.on = false;
+            inv_count_ = 0;
+        }
+        MF_CU(cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem));
+    }
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
     MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
@@ -1173,6 +1453,7 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
             }
         });
     }
+    if (inv_count_) timed(4, [&] { mf_chain_inv_kernel<<<inv_count_, TB, kChainInvSmem, st>>>(dev_, d_chain_tasks_ + inv_first_); });
     if (timing) {
         fprintf(stderr, "[mf timing] asm %.3f (max %.3f)  diag %.3f (max %.3f)  col %.3f (max %.3f)  rupd %.3f (max %.3f)  small %.3f ms\n",
                 sums[0], maxs[0], sums[1], maxs[1], sums[2], maxs[2], sums[3], maxs[3], sums[4]);
@@ -1187,6 +1468,8 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     float sums[6] = {0, 0, 0, 0, 0, 0}, maxs[6] = {0, 0, 0, 0, 0, 0};
     if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    static const bool detail = timing && std::atoi(std::getenv("FK_MF_TIMING")) >= 2;
+    int cur_level = -1;
     auto timed = [&](int kind, auto&& launch) {
         if (timing) cudaEventRecord(e0, st);
         launch();
@@ -1197,6 +1480,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
             cudaEventElapsedTime(&ms, e0, e1);
             sums[kind] += ms;
             maxs[kind] = std::max(maxs[kind], ms);
+            if (detail) fprintf(stderr, "[mf solve launch] level %d kind %d %.1f us\n", cur_level, kind, ms * 1e3f);
         }
     };
     const uint32_t sgrid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -1204,10 +1488,21 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
     const size_t vsmem = (size_t)stats.max_front * sizeof(double);
     const size_t nsmem = (32 * 33 + 2 * 64) * sizeof(double);  // narrow levels: fronts of order <= 64
     const uint32_t nlevels = (uint32_t)level_ptr_.size() - 1;
+    bool any_chain = false;
+    for (const ChainLevel& c : chain_) any_chain = any_chain || c.on;
+    if (any_chain) {
+        const cudaError_t e = cudaMemsetAsync(d_chain_pub_, 0xFF, 2 * (size_t)n_ * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+    }
     if (nsub_) timed(0, [&] { mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm); });
     for (uint32_t l = 0; l < nlevels; l++) {
         const uint32_t cnt = level_ptr_[l + 1] - level_ptr_[l];
         const uint32_t* list = d_level_list_ + level_ptr_[l];
+        cur_level = (int)l;
+        if (chain_[l].on) {
+            timed(1, [&] { mf_chain_fwd_kernel<<<chain_[l].fwd_count, 256, 0, st>>>(dev_, d_chain_tasks_ + chain_[l].fwd_first, w, d_chain_pub_); });
+            continue;
+        }
         timed(1, [&] {
             if (level_wide_[l]) mf_big_solve_kernel<true, true><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
             else if (level_narrow_[l]) mf_big_solve_kernel<true, false, 64><<<cnt, 64, nsmem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, 64);
@@ -1218,6 +1513,16 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
     for (uint32_t l = nlevels; l-- > 0;) {
         const uint32_t cnt = level_ptr_[l + 1] - level_ptr_[l];
         const uint32_t* list = d_level_list_ + level_ptr_[l];
+        cur_level = (int)l;
+        if (chain_[l].on) {
+            if (chain_[l].dot_count)
+                timed(3, [&] { mf_bwd_dot_kernel<<<chain_[l].dot_count, 256, vsmem, st>>>(dev_, d_chain_tasks_ + chain_[l].dot_first, w, d_tmp_); });
+            timed(4, [&] {
+                mf_chain_bwd_kernel<<<chain_[l].bwd_count, 256, 0, st>>>(dev_, d_chain_tasks_ + chain_[l].bwd_first, w, delta, d_perm, d_tmp_,
+                                                                      d_chain_pub_ + n_);
+            });
+            continue;
+        }
         if (bwd_tasks_[l].second) timed(3, [&] { mf_bwd_dot_kernel<<<bwd_tasks_[l].second, 256, vsmem, st>>>(dev_, d_tasks_ + bwd_tasks_[l].first, w, d_tmp_); });
         timed(4, [&] {
             if (level_wide_[l]) mf_big_solve_kernel<false, true><<<cnt, 256, smem, st>>>(dev_, list, w, delta, d_perm, d_tmp_, stats.max_front);
