@@ -3,6 +3,7 @@
 #include "multifrontal.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -122,12 +123,34 @@ mf_asm_kernel(MfDev D, const uint4* __restrict__ tasks) {
         const uint32_t rc = __ldg(D.f + c) - __ldg(D.ns + c);
         const double* Uc = D.upd + __ldg(D.upd_off + c);
         const uint32_t* relc = D.rel + __ldg(D.rel_off + c);
-        const uint32_t b_lo = lower_bound_u32(relc, rc, lo), b_hi = lower_bound_u32(relc, rc, hi);
+        // child columns whose target lies in [lo, hi): rel is ascending, so the range is
+        // [#entries < lo, #entries < hi) -- counted by the whole CTA in parallel (a binary search
+        // would be ten dependent L2 round trips per bound)
+        uint32_t b_lo = 0, b_hi = 0;
+        for (uint32_t base = 0; base < rc; base += 256) {
+            const uint32_t v = base + threadIdx.x < rc ? __ldg(relc + base + threadIdx.x) : 0xFFFFFFFFu;
+            b_lo += (uint32_t)__syncthreads_count(v < lo);
+            b_hi += (uint32_t)__syncthreads_count(v < hi);
+        }
         for (uint32_t b = b_lo + warp; b < b_hi; b += 8) {
             const uint32_t tb = __ldg(relc + b);
             double* dst = tb < ns ? P + (size_t)tb * f : U + (size_t)(tb - ns) * r - ns;
-            const double* src = Uc + (size_t)b * rc;
-            for (uint32_t a = b + lane; a < rc; a += 32) dst[__ldg(relc + a)] += src[a];
+            const double* __restrict__ src = Uc + (size_t)b * rc;
+            uint32_t a = b + lane;
+            for (; a + 96 < rc; a += 128) {  // four independent gather / add / scatter chains in flight
+                uint32_t ix[4];
+                double sv[4], dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    ix[u] = __ldg(relc + a + 32 * u);
+                    sv[u] = src[a + 32 * u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) dv[u] = dst[ix[u]];
+#pragma unroll
+                for (int u = 0; u < 4; u++) dst[ix[u]] = dv[u] + sv[u];
+            }
+            for (; a < rc; a += 32) dst[__ldg(relc + a)] += src[a];
         }
         __syncthreads();
     }
@@ -1079,6 +1102,14 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     const uint32_t n = t.n_free;
     n_ = n;
     sym = MfSymbolic();
+    static const bool sym_timing = std::getenv("FK_SYM_TIMING") != nullptr;
+    auto sym_t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!sym_timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mf symbolic] %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - sym_t0).count());
+        sym_t0 = now;
+    };
     std::vector<uint32_t>&c0 = sym.c0, &ns = sym.ns, &f = sym.f, &rows_off = sym.rows_off, &rows = sym.rows, &rel_off = sym.rel_off,
                          &rel = sym.rel, &child_ptr = sym.child_ptr, &child = sym.child, &winv_blk = sym.winv_blk, &sub_ptr = sym.sub_ptr,
                          &sub_list = sym.sub_list, &level_list = sym.level_list, &level = sym.level, &tasks = sym.tasks;
@@ -1121,15 +1152,15 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     pan_total_ = pan_total;
     rows.assign(rows_off[S], 0);
     for (uint32_t s = 0; s < S; s++) std::copy(lr.begin() + lc[c0[s]], lr.begin() + lc[c0[s]] + f[s], rows.begin() + rows_off[s]);
+    lap("supernodes");
     // L position -> panel offset; diagonal positions
-    lpos_map_.assign(lr.size(), 0);
     diag_map_.assign(n, 0);
     for (uint32_t j = 0; j < n; j++) {
         const uint32_t s = col2sn[j], k = j - c0[s];
         const uint64_t base = pan_off[s] + (uint64_t)k * f[s] + k;
         diag_map_[j] = base;
-        for (uint32_t q = lc[j]; q < lc[j + 1]; q++) lpos_map_[q] = base + (q - lc[j]);
     }
+    lap("position maps");
     // children (ascending) and relative indices
     child_ptr.assign(S + 1, 0);
     for (uint32_t s = 0; s < S; s++)
@@ -1163,6 +1194,7 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             rel[rel_off[s] + a] = pos;
         }
     }
+    lap("children, relative indices");
     // ---- small subtrees / big levels
     big.assign(S, 0);
     for (uint32_t s = 0; s < S; s++) {
@@ -1211,6 +1243,7 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     std::vector<std::vector<uint32_t>> by_level(nlevels);
     for (uint32_t s = 0; s < S; s++)
         if (big[s]) by_level[level[s]].push_back(s);
+    lap("subtrees, levels");
     // ---- task lists of the factorisation
     tasks.clear();  // uint4 each
     auto push_task = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -1296,6 +1329,7 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             if (count) factor_seq_.push_back({3, first, count});
         }
     }
+    lap("factor task lists");
     // ---- chained solves: wide levels whose 64-row chunks all fit on the device at once
     chain_.assign(nlevels, ChainLevel());
     chain_tasks_.clear();
@@ -1343,6 +1377,7 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
         inv_count_ = (uint32_t)(chain_tasks_.size() / 4) - inv_first_;
     }
     n_chain_flags_ = winv_blocks;
+    lap("chain task lists");
     factor_launches_ = factor_seq_.size() + (nsub ? 1 : 0);
     stats.supernodes = S; stats.small_subtrees = nsub; stats.big = nbig; stats.levels = nlevels;
     stats.max_front = max_front; stats.upd_doubles = upd_total;
@@ -1426,6 +1461,9 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     float sums[5] = {0, 0, 0, 0, 0}, maxs[5] = {0, 0, 0, 0, 0};
     if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    static const bool detail = timing && std::atoi(std::getenv("FK_MF_TIMING")) >= 3;
+    int seq_no = -1;
+    uint32_t cur_count = 0;
     auto timed = [&](int kind, auto&& launch) {
         if (timing) cudaEventRecord(e0, st);
         launch();
@@ -1436,6 +1474,7 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
             cudaEventElapsedTime(&ms, e0, e1);
             sums[kind] += ms;
             maxs[kind] = std::max(maxs[kind], ms);
+            if (detail) fprintf(stderr, "[mf factor launch] #%d kind %d ctas %u %.1f us\n", seq_no, kind, cur_count, ms * 1e3f);
         }
     };
     if (nsub_) {
@@ -1444,6 +1483,8 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
     }
     for (const Launch& l : factor_seq_) {
         const uint4* tk = d_tasks_ + l.first;
+        seq_no++;
+        cur_count = l.count;
         timed(l.kind, [&] {
             switch (l.kind) {
                 case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;

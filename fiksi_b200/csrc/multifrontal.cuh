@@ -78,8 +78,7 @@ public:
     ~Multifrontal();
     // Builds the supernodal structures from the topology's L pattern and uploads them.
     cudaError_t init(const Topology& t, cudaStream_t stream, std::string* err);
-    // L position (Topology::l_rowidx order) -> offset in the panel storage.
-    const std::vector<uint64_t>& lpos_to_panel() const { return lpos_map_; }
+    // Entry k of L column j (Topology::l_rowidx order: diagonal first) lives at diag_panel()[j] + k in the panel storage.
     const std::vector<uint64_t>& diag_panel() const { return diag_map_; }  // [n] panel offset of d_k
     size_t panel_doubles() const { return pan_total_; }
     double* panels() const { return dev_.pan; }
@@ -96,7 +95,7 @@ public:
 private:
     MfDev dev_;
     std::vector<void*> owned_;
-    std::vector<uint64_t> lpos_map_, diag_map_;
+    std::vector<uint64_t> diag_map_;
     size_t pan_total_ = 0;
     uint64_t flops_ = 0;
     uint32_t n_ = 0, nsub_ = 0;

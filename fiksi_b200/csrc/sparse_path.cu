@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -206,6 +207,14 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     Impl& I = *impl_;
     I.t = &t;
     I.device = device;
+    static const bool sym_timing = std::getenv("FK_SYM_TIMING") != nullptr;
+    auto lap_t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!sym_timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sparse init] %-26s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - lap_t0).count());
+        lap_t0 = now;
+    };
     SP_CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     SP_CU(cudaGetDeviceProperties(&prop, device));
@@ -233,6 +242,7 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     SP_CU(upload(jcolptr, &S.jcolptr, I.owned));
     SP_CU(upload(jrow, &S.jrow, I.owned));
     SP_CU(upload(t.perm, &S.perm, I.owned));
+    lap("context, evaluation tables");
     // supernodal multifrontal factorisation (K5): symbolic structures, panel storage
     {
         std::string merr;
@@ -246,16 +256,18 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
         if (err) *err = "panel storage exceeds the 32-bit offsets of the assembly lists";
         return FK_ERR_TOO_LARGE;
     }
+    lap("multifrontal init");
     S.pan = I.mf.panels();
     S.status = I.mf.status();
     // compacted H contribution lists, addressed by panel offset
-    const std::vector<uint64_t>& lmap = I.mf.lpos_to_panel();
+    const std::vector<uint64_t>& dmap = I.mf.diag_panel();
     std::vector<uint32_t> he_pos, he_ptr, diag_pos(n);
-    for (uint32_t p = 0; p < lnnz; p++)
-        if (t.h_ptr[p + 1] > t.h_ptr[p]) {
-            he_pos.push_back((uint32_t)lmap[p]);
-            he_ptr.push_back(t.h_ptr[p]);  // h_pairs is ordered by L position: lists stay contiguous
-        }
+    for (uint32_t j = 0; j < n; j++)
+        for (uint32_t p = t.l_colptr[j]; p < t.l_colptr[j + 1]; p++)
+            if (t.h_ptr[p + 1] > t.h_ptr[p]) {
+                he_pos.push_back((uint32_t)(dmap[j] + (p - t.l_colptr[j])));
+                he_ptr.push_back(t.h_ptr[p]);  // h_pairs is ordered by L position: lists stay contiguous
+            }
     he_ptr.push_back(t.h_ptr[lnnz]);
     for (uint32_t k = 0; k < n; k++) diag_pos[k] = (uint32_t)I.mf.diag_panel()[k];
     S.n_hent = (uint32_t)he_pos.size();
@@ -263,6 +275,7 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     SP_CU(upload(he_ptr, &S.he_ptr, I.owned));
     SP_CU(upload(t.h_pairs, &S.he_pairs, I.owned));
     SP_CU(upload(diag_pos, &S.diag_pos, I.owned));
+    lap("assembly lists");
     SP_CU(I.alloc(&I.d_x, n));
     SP_CU(I.alloc(&I.d_xs, n));
     SP_CU(I.alloc(&I.d_vars, t.n_vars));
@@ -280,6 +293,7 @@ int SparseSolver::init(const Topology& t, int device, std::string* err) {
     SP_CU(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
     SP_CU(cudaEventCreate(&I.ev[0]));
     SP_CU(cudaEventCreate(&I.ev[1]));
+    lap("work vectors, stream");
     return FK_OK;
 }
 

@@ -1,8 +1,12 @@
 #include "symbolic.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
 
 #include "colamd_order.hpp"
 
@@ -21,6 +25,35 @@ int expand_slots(uint8_t kind, const uint32_t idx[4], uint32_t out[8]) {
     return n;
 }
 
+// Host threads for the phases of the symbolic pipeline that are independent per column / per row
+// (large systems only; the reference is single-threaded and repeats this work on every LM call).
+static unsigned symbolic_threads(uint64_t work) {
+    if (work < (1u << 18)) return 1;
+    unsigned t = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("FK_SYM_THREADS")) t = (unsigned)std::max(1, std::atoi(e));
+    return std::min(std::max(t, 1u), 32u);
+}
+
+// f(thread, begin, end) over [0, n) in chunks handed out dynamically (balanced for uneven work per index).
+template <class F>
+static void parallel_chunks(uint32_t n, uint32_t chunk, unsigned threads, F&& f) {
+    if (threads <= 1 || n <= chunk) {
+        f(0u, 0u, n);
+        return;
+    }
+    std::atomic<uint32_t> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++)
+        pool.emplace_back([&, t] {
+            for (;;) {
+                const uint32_t b = next.fetch_add(chunk);
+                if (b >= n) break;
+                f(t, b, std::min(n, b + chunk));
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
 static uint64_t mix(uint64_t h, uint64_t v) {
     h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h *= 0xFF51AFD7ED558CCDull;
@@ -28,6 +61,15 @@ static uint64_t mix(uint64_t h, uint64_t v) {
 }
 
 int Topology::build(const fk_problem& p) {
+    // FK_SYM_TIMING=1: wall time of every phase of the host symbolic pipeline to stderr
+    static const bool sym_timing = std::getenv("FK_SYM_TIMING") != nullptr;
+    auto sym_t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!sym_timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[symbolic] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - sym_t0).count());
+        sym_t0 = now;
+    };
     if ((p.n_expr && (!p.kind || !p.idx)) || (p.n_free && !p.free_vars) || (p.n_rows && !p.rows)) {
         error = "null array in fk_problem";
         return FK_ERR_INVALID;
@@ -87,6 +129,7 @@ int Topology::build(const fk_problem& p) {
         eval_bytes += 1 + 4 * stored_idx[kd] + 8 + 8 * a + 4 * f + 8 + 8 * f;
     }
 
+    lap("slot tables");
     // ---- augmented CSC pattern ----------------------------------------------------------------
     aug_colptr.assign(n + 1, 0);
     for (uint32_t c = 0; c < n; c++) aug_colptr[c + 1] = aug_colptr[c] + col_count[c] + 1;
@@ -118,11 +161,13 @@ int Topology::build(const fk_problem& p) {
         }
     }
 
+    lap("augmented pattern");
     // ---- fill-reducing ordering -----------------------------------------------------------------
     perm = ColamdOrder::order((int)(m + n), (int)n, aug_colptr.data(), aug_rowidx.data());
     iperm.assign(n, 0);
     for (uint32_t k = 0; k < n; k++) iperm[perm[k]] = (int32_t)k;
 
+    lap("colamd");
     // ---- column elimination tree of A*P (tree of (AP)ᵀ(AP), never formed) -------------------------
     // Liu's algorithm with path compression; `last_col[i]` links row i to the previous column that
     // held it, which is all of the product's structure that matters.
@@ -154,30 +199,58 @@ int Topology::build(const fk_problem& p) {
         }
     }
 
+    lap("elimination tree");
     // ---- pattern of R = Lᵀ: union of row subtrees (columns of A*P walked up the tree) ------------
+    // Columns are independent given the tree: pass 1 counts, pass 2 writes each sorted list in place
+    // (threads own private mark arrays; chunks are handed out dynamically).
     r_colptr.assign(n + 1, 0);
     r_rowidx.clear();
     {
-        std::vector<int32_t> mark(n, -1);
-        std::vector<uint32_t> col;
-        for (uint32_t j = 0; j < n; j++) {
+        const unsigned T = symbolic_threads((uint64_t)aug_colptr[n] * 8);
+        std::vector<std::vector<int32_t>> marks(T);
+        std::vector<std::vector<uint32_t>> cols(T);
+        auto walk = [&](unsigned t, uint32_t j, std::vector<uint32_t>& col) {
+            std::vector<int32_t>& mark = marks[t];
             col.clear();
             mark[j] = (int32_t)j;
-            uint32_t src = (uint32_t)perm[j];
-            for (uint32_t q = aug_colptr[src]; q < aug_colptr[src + 1]; q++) {
+            const uint32_t src = (uint32_t)perm[j];
+            for (uint32_t q = aug_colptr[src]; q < aug_colptr[src + 1]; q++)
                 for (int32_t k = first_col[aug_rowidx[q]]; k != -1 && k < (int32_t)j && mark[k] != (int32_t)j; k = parent[k]) {
                     mark[k] = (int32_t)j;
                     col.push_back((uint32_t)k);
                 }
+        };
+        auto reset = [&](unsigned t) {
+            if (marks[t].size() != n) marks[t].assign(n, -1);
+            else std::fill(marks[t].begin(), marks[t].end(), -1);
+        };
+        std::vector<std::atomic<bool>> started(T);
+        for (auto& b : started) b = false;
+        parallel_chunks(n, 512, T, [&](unsigned t, uint32_t b, uint32_t e) {
+            if (!started[t].exchange(true)) reset(t);
+            for (uint32_t j = b; j < e; j++) {
+                walk(t, j, cols[t]);
+                r_colptr[j + 1] = (uint32_t)cols[t].size() + 1;
             }
-            std::sort(col.begin(), col.end());
-            r_rowidx.insert(r_rowidx.end(), col.begin(), col.end());
-            r_rowidx.push_back(j);
-            r_colptr[j + 1] = (uint32_t)r_rowidx.size();
-        }
+        });
+        for (uint32_t j = 0; j < n; j++) r_colptr[j + 1] += r_colptr[j];
+        r_rowidx.resize(r_colptr[n]);
+        for (auto& b : started) b = false;
+        parallel_chunks(n, 512, T, [&](unsigned t, uint32_t b, uint32_t e) {
+            if (!started[t].exchange(true)) reset(t);
+            for (uint32_t j = b; j < e; j++) {
+                std::vector<uint32_t>& col = cols[t];
+                walk(t, j, col);
+                std::sort(col.begin(), col.end());
+                uint32_t* dst = r_rowidx.data() + r_colptr[j];
+                std::copy(col.begin(), col.end(), dst);
+                dst[col.size()] = j;
+            }
+        });
     }
     const uint32_t lnnz = (uint32_t)r_rowidx.size();
 
+    lap("R pattern");
     // ---- L in CSC (transpose of R): diagonal first, then ascending rows ---------------------------
     l_colptr.assign(n + 1, 0);
     for (uint32_t q = 0; q < lnnz; q++) l_colptr[r_rowidx[q] + 1]++;
@@ -185,15 +258,39 @@ int Topology::build(const fk_problem& p) {
     l_rowidx.assign(lnnz, 0);
     r_lpos.assign(lnnz, 0);
     {
-        std::vector<uint32_t> fill(l_colptr.begin(), l_colptr.begin() + n);
-        for (uint32_t k = 0; k < n; k++) l_rowidx[fill[k]++] = k;  // diagonal
-        for (uint32_t j = 0; j < n; j++)
-            for (uint32_t q = r_colptr[j]; q < r_colptr[j + 1]; q++) {
-                uint32_t i = r_rowidx[q];  // R(i, j) == L(j, i)
-                if (i == j) { r_lpos[q] = l_colptr[j]; continue; }
-                r_lpos[q] = fill[i];
-                l_rowidx[fill[i]++] = j;
+        // transpose by ranges of target columns: a thread owns the L columns [k0, k1) and finds its part of
+        // every (sorted) R column by binary search, so no two threads write the same list
+        const unsigned T = symbolic_threads(lnnz);
+        std::vector<uint32_t> bound(T + 1, n);
+        bound[0] = 0;
+        for (unsigned t = 1; t < T; t++) {
+            const uint32_t want = (uint32_t)((uint64_t)lnnz * t / T);
+            bound[t] = (uint32_t)(std::upper_bound(l_colptr.begin(), l_colptr.end(), want) - l_colptr.begin() - 1);
+            bound[t] = std::max(bound[t], bound[t - 1]);
+        }
+        auto part = [&](unsigned t) {
+            const uint32_t k0 = bound[t], k1 = bound[t + 1];
+            if (k0 >= k1) return;
+            std::vector<uint32_t> fill(l_colptr.begin() + k0, l_colptr.begin() + k1);
+            for (uint32_t k = k0; k < k1; k++) l_rowidx[fill[k - k0]++] = k;  // diagonal
+            for (uint32_t j = k0; j < n; j++) {  // R(i, j) has i <= j: columns before k0 hold nothing of this range
+                const uint32_t* b = r_rowidx.data() + r_colptr[j];
+                const uint32_t* e = r_rowidx.data() + r_colptr[j + 1];
+                const uint32_t* lo = T > 1 ? std::lower_bound(b, e, k0) : b;
+                for (const uint32_t* it = lo; it != e && *it < k1; ++it) {
+                    const uint32_t i = *it, q = (uint32_t)(it - r_rowidx.data());  // R(i, j) == L(j, i)
+                    if (i == j) { r_lpos[q] = l_colptr[j]; continue; }
+                    r_lpos[q] = fill[i - k0];
+                    l_rowidx[fill[i - k0]++] = j;
+                }
             }
+        };
+        if (T <= 1) part(0);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < T; t++) pool.emplace_back(part, t);
+            for (auto& th : pool) th.join();
+        }
     }
     chol_flops = 0;
     uint64_t n_updates = 0;
@@ -206,6 +303,7 @@ int Topology::build(const fk_problem& p) {
         max_col_updates = std::max<uint32_t>(max_col_updates, (uint32_t)std::min<uint64_t>(u, 0xFFFFFFFFu));
     }
 
+    lap("L transpose");
     // ---- path selection -----------------------------------------------------------------------------
     {
         uint64_t work = std::max<uint64_t>(jac_nnz, lnnz);
@@ -238,6 +336,7 @@ int Topology::build(const fk_problem& p) {
         }
     }
 
+    lap("path selection");
     // ---- contribution lists of H = JᵀJ in L storage, and of g = Jᵀ(-r) ----------------------------------
     auto l_find = [&](uint32_t row, uint32_t col) -> int64_t {  // position of L(row, col), row >= col
         const uint32_t* b = l_rowidx.data() + l_colptr[col] + 1;
@@ -247,36 +346,52 @@ int Topology::build(const fk_problem& p) {
         return (it != e && *it == row) ? (int64_t)(it - l_rowidx.data()) : -1;
     };
     h_ptr.assign((size_t)lnnz + 1, 0);
-    for (int pass = 0; pass < 2; pass++) {
-        std::vector<uint32_t> fill;
-        if (pass == 1) {
-            for (uint32_t q = 0; q < lnnz; q++) h_ptr[q + 1] += h_ptr[q];
-            h_pairs.assign(2 * (size_t)h_ptr[lnnz], 0);
-            fill.assign(h_ptr.begin(), h_ptr.begin() + lnnz);
-        }
+    {
+        // the L position of every (row, a, b) product, looked up once (in parallel over the rows), then
+        // counted and filled in row order so that every list keeps the reference's summation order
+        std::vector<uint32_t> pair_ptr((size_t)m + 1, 0);
         for (uint32_t r = 0; r < m; r++) {
-            int32_t cs[8], ps[8];
-            int cnt = 0;
-            for (int s = 0; s < 8; s++) {
-                int32_t c = slot_col[(size_t)r * 8 + s];
-                if (c < 0 || slot_dup[(size_t)r * 8 + s]) continue;
-                cs[cnt] = iperm[c];
-                ps[cnt++] = slot_pos[(size_t)r * 8 + s];
-            }
-            for (int a = 0; a < cnt; a++)
-                for (int b = 0; b <= a; b++) {
-                    uint32_t hi = (uint32_t)std::max(cs[a], cs[b]), lo = (uint32_t)std::min(cs[a], cs[b]);
-                    int64_t pos = l_find(hi, lo);
-                    if (pos < 0) { error = "internal: JtJ entry outside the L pattern"; return FK_ERR_INTERNAL; }
-                    if (pass == 0) h_ptr[pos + 1]++;
-                    else {
-                        h_pairs[2 * (size_t)fill[pos]] = (uint32_t)ps[a];
-                        h_pairs[2 * (size_t)fill[pos] + 1] = (uint32_t)ps[b];
-                        fill[pos]++;
-                    }
+            uint32_t cnt = 0;
+            for (int s = 0; s < 8; s++) cnt += (slot_col[(size_t)r * 8 + s] >= 0 && !slot_dup[(size_t)r * 8 + s]) ? 1u : 0u;
+            pair_ptr[r + 1] = pair_ptr[r] + cnt * (cnt + 1) / 2;
+        }
+        std::vector<int64_t> pair_pos(pair_ptr[m]);
+        std::vector<uint32_t> pair_ab(2 * (size_t)pair_ptr[m]);
+        std::atomic<bool> bad{false};
+        parallel_chunks(m, 2048, symbolic_threads((uint64_t)pair_ptr[m] * 8), [&](unsigned, uint32_t rb, uint32_t re) {
+            for (uint32_t r = rb; r < re; r++) {
+                int32_t cs[8], ps[8];
+                int cnt = 0;
+                for (int s = 0; s < 8; s++) {
+                    int32_t c = slot_col[(size_t)r * 8 + s];
+                    if (c < 0 || slot_dup[(size_t)r * 8 + s]) continue;
+                    cs[cnt] = iperm[c];
+                    ps[cnt++] = slot_pos[(size_t)r * 8 + s];
                 }
+                size_t at = pair_ptr[r];
+                for (int a = 0; a < cnt; a++)
+                    for (int b = 0; b <= a; b++, at++) {
+                        uint32_t hi = (uint32_t)std::max(cs[a], cs[b]), lo = (uint32_t)std::min(cs[a], cs[b]);
+                        pair_pos[at] = l_find(hi, lo);
+                        if (pair_pos[at] < 0) bad = true;
+                        pair_ab[2 * at] = (uint32_t)ps[a];
+                        pair_ab[2 * at + 1] = (uint32_t)ps[b];
+                    }
+            }
+        });
+        lap("H lookups");
+        if (bad) { error = "internal: JtJ entry outside the L pattern"; return FK_ERR_INTERNAL; }
+        for (size_t at = 0; at < pair_pos.size(); at++) h_ptr[pair_pos[at] + 1]++;
+        for (uint32_t q = 0; q < lnnz; q++) h_ptr[q + 1] += h_ptr[q];
+        h_pairs.assign(2 * (size_t)h_ptr[lnnz], 0);
+        std::vector<uint32_t> fill(h_ptr.begin(), h_ptr.begin() + lnnz);
+        for (size_t at = 0; at < pair_pos.size(); at++) {
+            const uint32_t w = fill[pair_pos[at]]++;
+            h_pairs[2 * (size_t)w] = pair_ab[2 * at];
+            h_pairs[2 * (size_t)w + 1] = pair_ab[2 * at + 1];
         }
     }
+    lap("H lists");
     g_ptr.assign(n + 1, 0);
     g_pairs.clear();
     for (uint32_t k = 0; k < n; k++) {
@@ -289,6 +404,7 @@ int Topology::build(const fk_problem& p) {
         g_ptr[k + 1] = (uint32_t)(g_pairs.size() / 2);
     }
 
+    lap("H and g lists");
     // ---- LDLᵀ update schedule (shared-memory paths only) ------------------------------------------
     u_ptr.assign(n + 1, 0);
     u_trip.clear();
@@ -309,7 +425,10 @@ int Topology::build(const fk_problem& p) {
             u_ptr[k + 1] = (uint32_t)(u_trip.size() / 3);
         }
     }
-    return build_tables();
+    lap("update schedule");
+    const int rc_tables = build_tables();
+    lap("kernel tables");
+    return rc_tables;
 }
 
 // Lane-padded op tables for the shared-memory kernel (see Topology::Tables).

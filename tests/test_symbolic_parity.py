@@ -125,3 +125,25 @@ def test_library_exports_every_declared_symbol():
     L = fk.lib()
     for name in declared:
         assert hasattr(L, name), name
+
+
+def test_threaded_symbolic_matches_single_thread_and_oracle(oracle, monkeypatch):
+    """Large systems run the R pattern, the L transposition and the H lookups on host threads
+    (csrc/symbolic.cpp); the arrays must not depend on the thread count, and must still be the
+    reference's (cholesky.rs:359-595 via the oracle)."""
+    w = wl.lattice(120, 100)  # 24,000 variables: every threaded phase is active
+    v, p, scale = w.prepare()
+    outs = []
+    for threads in ("1", "7"):
+        monkeypatch.setenv("FK_SYM_THREADS", threads)
+        topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+        assert topo.info["path"] == 2
+        outs.append((topo.symbolic(), topo.supernodal()))
+    (s1, n1), (s7, n7) = outs
+    for key in ("aug_colptr", "aug_rowidx", "perm", "etree_parent", "r_colptr", "r_rowidx"):
+        assert np.array_equal(s1[key], s7[key]), key
+    for key in ("sn_first", "front", "sn_parent", "rows", "rel", "big", "level", "tasks", "launches"):
+        assert np.array_equal(n1[key], n7[key]), key
+    ref = oracle.symbolic(oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)[0])
+    assert np.array_equal(ref["perm"], s7["perm"])
+    assert np.array_equal(ref["r_colptr"], s7["r_colptr"]) and np.array_equal(ref["r_rowidx"], s7["r_rowidx"])
