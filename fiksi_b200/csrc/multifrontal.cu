@@ -165,6 +165,20 @@ mf_asm_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // (two broadcast 16-byte loads).  Chunks of KC columns go through double-buffered shared memory;
 // the next chunk is fetched into registers while the current one is multiplied, and the operands
 // of step k+1 are loaded while step k is multiplied (explicit register double buffering).
+// Published values are polled in place (see the chained solves / the tile dataflow factorisation below): a buffer is
+// filled with an all-ones bit pattern (a NaN no computation produces), a producer stores each 8-byte value
+// once, and a consumer re-reads its values at GPU scope until none of them is the sentinel.  A value is either
+// absent or final, so no fence, flag or second round trip is needed.
+__device__ __forceinline__ double ld_relaxed(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool is_unpublished(double v) { return __double_as_longlong(v) == -1ll; }
+
 struct TileBuf {
     double A[2][KC][TB];
     double B[2][KC][TB];
@@ -172,6 +186,7 @@ struct TileBuf {
 
 __device__ __forceinline__ uint32_t tile_row(uint32_t tx, int i) { return tx + 16u * (uint32_t)i; }
 
+template <bool POLL = false>
 __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __restrict__ P, uint32_t f, uint32_t rowA0,
                                            uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, uint32_t diag0, TileBuf& buf) {
     const uint32_t tid = threadIdx.x;
@@ -186,11 +201,24 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
         rdk = 0.0;
         if (k < K) {
             const double* col = P + (size_t)k * f;
-            rdk = col[diag0 + k];
+            if (POLL) {  // operands published by other CTAs of this launch: re-read until every value is there
+                bool missing;
+                do {
+                    rdk = ld_relaxed(col + diag0 + k);
+                    missing = is_unpublished(rdk);
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (lr + u < nrA) ra[u] = col[rowA0 + lr + u];
-                if (lr + u < nrB) rb[u] = col[rowB0 + lr + u];
+                    for (int u = 0; u < 4; u++) {
+                        if (lr + u < nrA) { ra[u] = ld_relaxed(col + rowA0 + lr + u); missing = missing || is_unpublished(ra[u]); }
+                        if (lr + u < nrB) { rb[u] = ld_relaxed(col + rowB0 + lr + u); missing = missing || is_unpublished(rb[u]); }
+                    }
+                } while (missing);
+            } else {
+                rdk = col[diag0 + k];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (lr + u < nrA) ra[u] = col[rowA0 + lr + u];
+                    if (lr + u < nrB) rb[u] = col[rowB0 + lr + u];
+                }
             }
         }
     };
@@ -275,31 +303,20 @@ __device__ __forceinline__ void micro_ldl(const double* Cs, uint32_t ld, uint32_
 constexpr int kDiagThreads = 256;
 constexpr int kTsLd = TB + 1;
 
-__global__ void __launch_bounds__(kDiagThreads)
-mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    __shared__ double Cs[TB * kTsLd];
-    __shared__ double Ys[TB * (MB + 1)];  // unscaled multipliers of the current micro-panel
-    const uint4 t = __ldg(tasks + blockIdx.x);
-    const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
-    const uint32_t f = __ldg(D.f + s);
-    double* T = D.pan + __ldg(D.pan_off + s) + (size_t)col0 * f + col0;
+// LDLt of the nc x nc tile whose lower part sits in Cs (row stride kTsLd).  Writes the unit factor (scaled)
+// and D (diagonal) to T (column-major, leading dimension f) and, when PUB, to Tp for the CTAs polling it.
+template <bool PUB>
+__device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_t nc, double* T, double* Tp, uint32_t f, int* status) {
     const uint32_t tid = threadIdx.x, i = tid & 63, q = tid >> 6;
-    for (uint32_t e = tid; e < nc * TB; e += kDiagThreads) {
-        const uint32_t ii = e & 63, j = e >> 6;
-        if (ii < nc && j <= ii) Cs[ii * kTsLd + j] = T[(size_t)j * f + ii];
-    }
-    FK_STAMP(0);
     for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
         const uint32_t kw = min((uint32_t)MB, nc - k0);
         __syncthreads();
-        FK_STAMP(1 + 4 * (k0 / MB));
         double ll[MB][MB], inv[MB], piv[MB], y[MB];
         micro_ldl(Cs, kTsLd, k0, kw, ll, inv, piv);
-        FK_STAMP(2 + 4 * (k0 / MB));
         if (tid == 0) {
 #pragma unroll
             for (int k = 0; k < MB; k++)
-                if ((uint32_t)k < kw) flag_pivot(D.status, piv[k]);
+                if ((uint32_t)k < kw) flag_pivot(status, piv[k]);
         }
         // own row against the block: y_c = p_c - sum_{c' < c} y_c' L88[c][c']  (unscaled multipliers; for a
         // row inside the micro-panel y_c is its pivot at c == i - k0 and unused beyond)
@@ -316,13 +333,13 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
             for (int c = 0; c < MB; c++) {
                 if ((uint32_t)c < kw && k0 + c <= i) {
                     Ys[i * (MB + 1) + c] = y[c];
-                    T[(size_t)(k0 + c) * f + i] = (k0 + c == i) ? y[c] : y[c] * inv[c];
+                    const double out = (k0 + c == i) ? y[c] : y[c] * inv[c];
+                    T[(size_t)(k0 + c) * f + i] = out;
+                    if (PUB) st_relaxed(Tp + (size_t)(k0 + c) * f + i, out);
                 }
             }
         }
-        FK_STAMP(3 + 4 * (k0 / MB));
         __syncthreads();
-        FK_STAMP(4 + 4 * (k0 / MB));
         // rank-8 update of the rows below the micro-panel: C[i][j] -= sum_c l_ic * y_jc
         if (i >= k0 + MB && i < nc) {
             double l[MB];
@@ -342,7 +359,22 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
             }
         }
     }
-    FK_STAMP(33);
+}
+
+__global__ void __launch_bounds__(kDiagThreads)
+mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
+    __shared__ double Cs[TB * kTsLd];
+    __shared__ double Ys[TB * (MB + 1)];  // unscaled multipliers of the current micro-panel
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
+    const uint32_t f = __ldg(D.f + s);
+    double* T = D.pan + __ldg(D.pan_off + s) + (size_t)col0 * f + col0;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t e = tid; e < nc * TB; e += kDiagThreads) {
+        const uint32_t ii = e & 63, j = e >> 6;
+        if (ii < nc && j <= ii) Cs[ii * kTsLd + j] = T[(size_t)j * f + ii];
+    }
+    diag_tile_factor<false>(Cs, Ys, nc, T, nullptr, f, D.status);
 }
 
 // Panel tile (rows row0..row0+nr) x (pivot block at col0, nc columns): L = C L_kk^-T D^-1 by blocked
@@ -351,6 +383,44 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // (redundantly x4), then the four share the rank-8 update of the rest of the row; __syncwarp only.
 constexpr int kColThreads = 256;
 constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (row, quarter) hit distinct banks
+// Blocked forward substitution of the rows in Cs ([TB][kYsLd], zero padded) against the unit-lower tile in Ls
+// ([TB][kTsLd], strictly lower part, zero padded): on return Cs holds Y = C L_kk^-T (unscaled).
+__device__ __forceinline__ void col_tile_step(double* row, const double* Ls, uint32_t k0, uint32_t nc, uint32_t q) {
+    double y[MB];
+#pragma unroll
+    for (int c = 0; c < MB; c++) {
+        double v = row[k0 + c];
+        const double* Lc = Ls + (k0 + c) * kTsLd + k0;
+#pragma unroll
+        for (int cp = 0; cp < c; cp++) v = fma(-y[cp], Lc[cp], v);
+        y[c] = v;
+    }
+    __syncwarp();  // all four threads of the row have read the block before it is overwritten
+    if (q == 0) {
+#pragma unroll
+        for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
+    }
+#pragma unroll 4
+    for (uint32_t cp = k0 + MB + q; cp < nc; cp += 4) {
+        const double* Lr = Ls + cp * kTsLd + k0;
+        double v0 = row[cp], v1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < MB; c += 2) {
+            v0 = fma(-y[c], Lr[c], v0);
+            v1 = fma(-y[c + 1], Lr[c + 1], v1);
+        }
+        row[cp] = v0 + v1;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void col_tile_solve(double* Cs, const double* Ls, uint32_t nc) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t i = tid >> 2, q = tid & 3;
+    double* row = Cs + i * kYsLd;
+    for (uint32_t k0 = 0; k0 < nc; k0 += MB) col_tile_step(row, Ls, k0, nc, q);
+}
+
 __global__ void __launch_bounds__(kColThreads)
 mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
     extern __shared__ __align__(16) double smd_col[];
@@ -372,38 +442,7 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
     }
     if (tid < nc) invd[tid] = fast_rcp(Lkk[(size_t)tid * f + tid]);
     __syncthreads();
-    {
-        const uint32_t i = tid >> 2, q = tid & 3;
-        double* row = Cs + i * kYsLd;
-        for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
-            double y[MB];
-#pragma unroll
-            for (int c = 0; c < MB; c++) {
-                double v = row[k0 + c];
-                const double* Lc = Ls + (k0 + c) * kTsLd + k0;
-#pragma unroll
-                for (int cp = 0; cp < c; cp++) v = fma(-y[cp], Lc[cp], v);
-                y[c] = v;
-            }
-            __syncwarp();  // all four threads of the row have read the block before it is overwritten
-            if (q == 0) {
-#pragma unroll
-                for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
-            }
-#pragma unroll 4
-            for (uint32_t cp = k0 + MB + q; cp < nc; cp += 4) {
-                const double* Lr = Ls + cp * kTsLd + k0;
-                double v0 = row[cp], v1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < MB; c += 2) {
-                    v0 = fma(-y[c], Lr[c], v0);
-                    v1 = fma(-y[c + 1], Lr[c + 1], v1);
-                }
-                row[cp] = v0 + v1;
-            }
-            __syncwarp();
-        }
-    }
+    col_tile_solve(Cs, Ls, nc);
     __syncthreads();
     for (uint32_t e = tid; e < nc * TB; e += kColThreads) {
         const uint32_t ii = e & 63, j = e >> 6;
@@ -456,6 +495,131 @@ mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
             if (ok) T[(size_t)(c4 + j) * ld + ri] = acc[i][j];
         }
     FK_STAMP(43);
+}
+
+// ---- tile dataflow factorisation of the levels near the root ---------------------------------------------
+// On the levels that hold a few wide supernodes the launch-per-step schedule (diag, panel, update per 64
+// pivot columns: 16 launches for a 260-column supernode) is a chain of short kernels separated by launch
+// gaps.  Here every 64x64 tile of a front is owned by ONE CTA for its whole life (left-looking per tile):
+// it loads the assembled tile into registers, subtracts the products of the finished pivot blocks to its
+// left as their panel tiles are published (polled in place, operands staged through shared memory by the
+// same register-blocked micro-kernel as mf_rupd_kernel), then factorises it (diagonal tile), solves it
+// against the published diagonal tile (panel tile) or stores it (update-matrix tile).  Tiles are numbered
+// column by column, so a CTA only ever waits for CTAs with a smaller block index: the schedule cannot
+// deadlock however many CTAs are resident.  One launch per level instead of 1 + 3 per pivot block.
+constexpr size_t kFlowSmem = (TB * kYsLd + TB * kTsLd + TB) * sizeof(double);
+static_assert(kFlowSmem >= sizeof(TileBuf), "the staging buffers alias the solve tiles");
+
+__global__ void __launch_bounds__(kTileThreads)
+mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pub) {
+    extern __shared__ __align__(16) double smf[];
+    TileBuf& buf = *reinterpret_cast<TileBuf*>(smf);
+    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t s = t.x, row0 = t.y, tcol0 = t.z;
+    const uint32_t nrA = (t.w & 0xFFu) + 1, nrB = ((t.w >> 8) & 0xFFu) + 1;
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
+    const uint64_t po = __ldg(D.pan_off + s);
+    double* P = D.pan + po;
+    double* Pp = pub + po;
+    const bool in_panel = tcol0 < ns;
+    const uint32_t nwait = in_panel ? tcol0 / TB : (ns + TB - 1) / TB;
+    double* T;      // target tile base: element (i, j) at T[j * ld + i]
+    uint32_t ld;
+    if (in_panel) {
+        T = P + (size_t)tcol0 * f + row0;
+        ld = f;
+    } else {
+        T = D.upd + __ldg(D.upd_off + s) + (size_t)(tcol0 - ns) * r + (row0 - ns);
+        ld = r;
+    }
+    const bool diag_tile = row0 == tcol0;
+    const uint32_t tid = threadIdx.x, tx = tid & 15, c4 = (tid >> 4) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t ri = tile_row(tx, i);
+            const bool ok = ri < nrA && c4 + j < nrB && (!diag_tile || ri >= c4 + j);
+            acc[i][j] = ok ? T[(size_t)(c4 + j) * ld + ri] : 0.0;
+        }
+    for (uint32_t b = 0; b < nwait; b++)
+        tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf);
+    if (!in_panel) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t ri = tile_row(tx, i);
+                if (ri < nrA && c4 + j < nrB && (!diag_tile || ri >= c4 + j)) T[(size_t)(c4 + j) * ld + ri] = acc[i][j];
+            }
+        return;
+    }
+    const uint32_t nc = nrB;  // pivot columns of this block
+    if (diag_tile) {
+        double* Cs = smf;
+        double* Ys = smf + TB * kTsLd;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t ri = tile_row(tx, i);
+                if (ri < nc && c4 + j <= ri) Cs[ri * kTsLd + c4 + j] = acc[i][j];
+            }
+        diag_tile_factor<true>(Cs, Ys, nc, T, Pp + (size_t)tcol0 * f + row0, f, D.status);
+        return;
+    }
+    double* Cs = smf;                 // [TB][kYsLd]
+    double* Ls = Cs + TB * kYsLd;     // [TB][kTsLd]
+    double* invd = Ls + TB * kTsLd;   // [TB]
+    for (uint32_t e = tid; e < TB * kYsLd; e += kTileThreads) Cs[e] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t ri = tile_row(tx, i);
+            if (ri < nrA && c4 + j < nc) Cs[ri * kYsLd + c4 + j] = acc[i][j];
+        }
+    for (uint32_t e = tid; e < TB * kTsLd; e += kTileThreads) Ls[e] = 0.0;
+    {   // follow the diagonal tile micro-panel by micro-panel: its 8-column strip (rows >= k0: strictly lower
+        // part + D) is polled as the owner of the diagonal tile publishes it, then this tile's rows take the step
+        const double* Lkk = Pp + (size_t)tcol0 * f + tcol0;
+        const uint32_t ii = tid & 63, cA = tid >> 6;  // entries (ii, k0 + cA) and (ii, k0 + cA + 4)
+        double* row = Cs + (tid >> 2) * kYsLd;
+        for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
+            double v[2];
+            bool missing;
+            do {
+                missing = false;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint32_t j = k0 + cA + 4u * u;
+                    v[u] = (ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
+                    missing = missing || is_unpublished(v[u]);
+                }
+            } while (missing);
+            __syncthreads();  // (the zero fill / the previous step's readers are done)
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t j = k0 + cA + 4u * u;
+                if (j < ii) Ls[ii * kTsLd + j] = v[u];
+                else if (j == ii && ii < nc) invd[ii] = fast_rcp(v[u]);
+            }
+            __syncthreads();
+            col_tile_step(row, Ls, k0, nc, tid & 3);
+        }
+    }
+    __syncthreads();
+    double* Tp = Pp + (size_t)tcol0 * f + row0;
+    for (uint32_t e = tid; e < nc * TB; e += kTileThreads) {
+        const uint32_t ii = e & 63, j = e >> 6;
+        if (ii < nrA) {
+            const double v = Cs[ii * kYsLd + j] * invd[j];
+            T[(size_t)j * f + ii] = v;
+            st_relaxed(Tp + (size_t)j * f + ii, v);
+        }
+    }
 }
 
 // ---- triangular solves ------------------------------------------------------------------------------------
@@ -766,19 +930,6 @@ __device__ __forceinline__ long long global_ns() {
 #else
 #define FK_CSTAMP(k) do { } while (0)
 #endif
-// Published solution values are polled in place: the buffer is filled with an all-ones bit pattern (a NaN
-// no computation produces) before the solve, a producer stores each 8-byte value once, and a consumer
-// re-reads its values at GPU scope until none of them is the sentinel.  A value is either absent or
-// final, so no fence, flag or second round trip is needed.
-__device__ __forceinline__ double ld_relaxed(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(double* p, double v) {
-    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ bool is_unpublished(double v) { return __double_as_longlong(v) == -1ll; }
 // the 16 values q, q+4, ... of a published 64-vector (entries >= count read as zero)
 __device__ __forceinline__ void poll16(const double* base, uint32_t q, uint32_t count, double (&v)[16]) {
     bool missing;
@@ -1256,8 +1407,10 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     bwd_tasks_.clear();
     level_ptr_.assign(1, 0);
     level_list.clear();
+    level_seq_ptr_.clear();
     for (uint32_t l = 0; l < nlevels; l++) {
         const std::vector<uint32_t>& L = by_level[l];
+        level_seq_ptr_.push_back((uint32_t)factor_seq_.size());
         for (uint32_t s : L) level_list.push_back(s);
         level_ptr_.push_back((uint32_t)level_list.size());
         {
@@ -1330,12 +1483,15 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
         }
     }
     lap("factor task lists");
+    level_seq_ptr_.push_back((uint32_t)factor_seq_.size());
     // ---- chained solves: wide levels whose 64-row chunks all fit on the device at once
     chain_.assign(nlevels, ChainLevel());
     chain_tasks_.clear();
     std::fill(winv_blk.begin(), winv_blk.end(), 0u);
     winv_blocks = 0;
     inv_first_ = inv_count_ = 0;
+    flow_pub_lo_ = ~0ull;
+    flow_pub_hi_ = 0;
     {
         static const bool off = std::getenv("FK_NO_CHAIN") != nullptr;  // debug / A-B knob
         auto push_chain = [&](uint32_t a, uint32_t b, uint32_t c) {
@@ -1370,6 +1526,25 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             for (uint32_t s : L)
                 for (uint32_t b = (ns[s] + TB - 1) / TB; b-- > 0;) push_chain(s, b * TB, std::min<uint32_t>(TB, ns[s] - b * TB));
             c.bwd_count = (uint32_t)(chain_tasks_.size() / 4) - c.bwd_first;
+            // tile dataflow factorisation: tiles column by column (dependencies point to smaller indices)
+            static const bool no_flow = std::getenv("FK_NO_FLOW") != nullptr;  // debug / A-B knob
+            if (!no_flow) {
+                c.flow_first = (uint32_t)(chain_tasks_.size() / 4);
+                std::vector<std::pair<uint32_t, uint32_t>> blk;
+                for (uint32_t s : L) {
+                    blk.clear();
+                    for (uint32_t r0 = 0; r0 < ns[s]; r0 += TB) blk.push_back({r0, std::min<uint32_t>(TB, ns[s] - r0)});
+                    for (uint32_t r0 = ns[s]; r0 < f[s]; r0 += TB) blk.push_back({r0, std::min<uint32_t>(TB, f[s] - r0)});
+                    for (size_t bj = 0; bj < blk.size(); bj++)
+                        for (size_t bi = bj; bi < blk.size(); bi++) {
+                            chain_tasks_.push_back(s); chain_tasks_.push_back(blk[bi].first); chain_tasks_.push_back(blk[bj].first);
+                            chain_tasks_.push_back((blk[bi].second - 1) | ((blk[bj].second - 1) << 8));
+                        }
+                    flow_pub_lo_ = std::min<uint64_t>(flow_pub_lo_, pan_off[s]);
+                    flow_pub_hi_ = std::max<uint64_t>(flow_pub_hi_, pan_off[s] + (uint64_t)f[s] * ns[s]);
+                }
+                c.flow_count = (uint32_t)(chain_tasks_.size() / 4) - c.flow_first;
+            }
         }
         inv_first_ = (uint32_t)(chain_tasks_.size() / 4);
         for (uint32_t s : chained)
@@ -1436,6 +1611,12 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
             inv_count_ = 0;
         }
         MF_CU(cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem));
+        MF_CU(cudaFuncSetAttribute(mf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem));
+        bool any_flow = false;
+        for (const ChainLevel& c : chain_) any_flow = any_flow || (c.on && c.flow_count);
+        if (any_flow) {  // published panel tiles of the dataflow levels (addressed like the panel storage)
+            MF_CU(alloc_vec(&d_pan_pub_, (size_t)(flow_pub_hi_ - flow_pub_lo_), owned_));
+        }
     }
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
     MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
@@ -1481,18 +1662,37 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
         const uint32_t grid = (nsub_ + kWarpsPerCta - 1) / kWarpsPerCta;
         timed(4, [&] { mf_small_factor_kernel<<<grid, kWarpsPerCta * 32, kSmallFactorSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_); });
     }
-    for (const Launch& l : factor_seq_) {
-        const uint4* tk = d_tasks_ + l.first;
-        seq_no++;
-        cur_count = l.count;
-        timed(l.kind, [&] {
-            switch (l.kind) {
-                case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
-                case 1: mf_diag_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
-                case 2: mf_col_kernel<<<l.count, kColThreads, kColSmem, st>>>(dev_, tk); break;
-                default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
-            }
-        });
+    if (d_pan_pub_) {
+        const cudaError_t e = cudaMemsetAsync(d_pan_pub_, 0xFF, (size_t)(flow_pub_hi_ - flow_pub_lo_) * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+    }
+    const uint32_t nlv = (uint32_t)level_seq_ptr_.size() - 1;
+    for (uint32_t lv = 0; lv < nlv; lv++) {
+        const bool flow = d_pan_pub_ && chain_[lv].on && chain_[lv].flow_count;
+        for (uint32_t qi = level_seq_ptr_[lv]; qi < level_seq_ptr_[lv + 1]; qi++) {
+            const Launch& l = factor_seq_[qi];
+            if (flow && l.kind != 0) continue;  // the level's diag / panel / update launches are replaced below
+            const uint4* tk = d_tasks_ + l.first;
+            seq_no++;
+            cur_count = l.count;
+            timed(l.kind, [&] {
+                switch (l.kind) {
+                    case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
+                    case 1: mf_diag_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
+                    case 2: mf_col_kernel<<<l.count, kColThreads, kColSmem, st>>>(dev_, tk); break;
+                    default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
+                }
+            });
+        }
+        if (flow) {
+            seq_no++;
+            cur_count = chain_[lv].flow_count;
+            // the published buffer is addressed with the panel offsets: bias the base so that pub + pan_off lands in it
+            timed(3, [&] {
+                mf_flow_kernel<<<chain_[lv].flow_count, kTileThreads, kFlowSmem, st>>>(dev_, d_chain_tasks_ + chain_[lv].flow_first,
+                                                                                    d_pan_pub_ - flow_pub_lo_);
+            });
+        }
     }
     if (inv_count_) timed(4, [&] { mf_chain_inv_kernel<<<inv_count_, TB, kChainInvSmem, st>>>(dev_, d_chain_tasks_ + inv_first_); });
     if (timing) {
