@@ -175,10 +175,17 @@ __device__ __forceinline__ double ld_relaxed(const double* p) {
     return v;
 }
 __device__ __forceinline__ void st_relaxed(double* p, double v) {
-    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
 __device__ __forceinline__ bool is_unpublished(double v) { return __double_as_longlong(v) == -1ll; }
 
+#ifdef FK_CHAIN_PROFILE
+__device__ __forceinline__ long long global_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+    return v;
+}
+#endif
 struct TileBuf {
     double A[2][KC][TB];
     double B[2][KC][TB];
@@ -201,17 +208,14 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
         rdk = 0.0;
         if (k < K) {
             const double* col = P + (size_t)k * f;
-            if (POLL) {  // operands published by other CTAs of this launch: re-read until every value is there
-                bool missing;
-                do {
-                    rdk = ld_relaxed(col + diag0 + k);
-                    missing = is_unpublished(rdk);
+            if (POLL) {  // operands published by other CTAs of this launch: issued here, verified by gverify() after the
+                         // multiplication of the current chunk (a value still missing is re-read there)
+                rdk = ld_relaxed(col + diag0 + k);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (lr + u < nrA) { ra[u] = ld_relaxed(col + rowA0 + lr + u); missing = missing || is_unpublished(ra[u]); }
-                        if (lr + u < nrB) { rb[u] = ld_relaxed(col + rowB0 + lr + u); missing = missing || is_unpublished(rb[u]); }
-                    }
-                } while (missing);
+                for (int u = 0; u < 4; u++) {
+                    if (lr + u < nrA) ra[u] = ld_relaxed(col + rowA0 + lr + u);
+                    if (lr + u < nrB) rb[u] = ld_relaxed(col + rowB0 + lr + u);
+                }
             } else {
                 rdk = col[diag0 + k];
 #pragma unroll
@@ -219,6 +223,24 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
                     if (lr + u < nrA) ra[u] = col[rowA0 + lr + u];
                     if (lr + u < nrB) rb[u] = col[rowB0 + lr + u];
                 }
+            }
+        }
+    };
+    auto gverify = [&](uint32_t ch) {
+        if (!POLL) return;
+        const uint32_t k = ch * KC + lk;
+        if (k >= K) return;
+        const double* col = P + (size_t)k * f;
+        for (;;) {
+            bool missing = is_unpublished(rdk);
+#pragma unroll
+            for (int u = 0; u < 4; u++) missing = missing || (lr + u < nrA && is_unpublished(ra[u])) || (lr + u < nrB && is_unpublished(rb[u]));
+            if (!missing) break;
+            rdk = ld_relaxed(col + diag0 + k);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (lr + u < nrA) ra[u] = ld_relaxed(col + rowA0 + lr + u);
+                if (lr + u < nrB) rb[u] = ld_relaxed(col + rowB0 + lr + u);
             }
         }
     };
@@ -238,6 +260,7 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
     if (nchunks) gload(0);
     for (uint32_t ch = 0; ch < nchunks; ch++) {
         const uint32_t b = ch & 1;
+        gverify(ch);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             buf.A[b][lk][lr + u] = ra[u] * rdk;
@@ -305,14 +328,22 @@ constexpr int kTsLd = TB + 1;
 
 // LDLt of the nc x nc tile whose lower part sits in Cs (row stride kTsLd).  Writes the unit factor (scaled)
 // and D (diagonal) to T (column-major, leading dimension f) and, when PUB, to Tp for the CTAs polling it.
+#ifdef FK_CHAIN_PROFILE
+// harness only (status is a large buffer there): clock64 stamps of the first micro-panels of CTA 0
+#define FK_DSTAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && k0 < 3 * MB) ((long long*)status)[8 + (k0 / MB) * 8 + (k)] = clock64(); } while (0)
+#else
+#define FK_DSTAMP(k) do { } while (0)
+#endif
 template <bool PUB>
 __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_t nc, double* T, double* Tp, uint32_t f, int* status) {
     const uint32_t tid = threadIdx.x, i = tid & 63, q = tid >> 6;
     for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
         const uint32_t kw = min((uint32_t)MB, nc - k0);
         __syncthreads();
+        FK_DSTAMP(0);
         double ll[MB][MB], inv[MB], piv[MB], y[MB];
         micro_ldl(Cs, kTsLd, k0, kw, ll, inv, piv);
+        FK_DSTAMP(1);
         if (tid == 0) {
 #pragma unroll
             for (int k = 0; k < MB; k++)
@@ -328,10 +359,11 @@ __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_
             for (int cp = 0; cp < c; cp++) v = fma(-y[cp], ll[c][cp], v);
             y[c] = v;
         }
-        if (q == 0 && active) {
+        FK_DSTAMP(5);
+        if (active) {  // the four threads of a row hold the same y: each stores two of the eight columns
 #pragma unroll
             for (int c = 0; c < MB; c++) {
-                if ((uint32_t)c < kw && k0 + c <= i) {
+                if ((uint32_t)(c & 3) == q && (uint32_t)c < kw && k0 + c <= i) {
                     Ys[i * (MB + 1) + c] = y[c];
                     const double out = (k0 + c == i) ? y[c] : y[c] * inv[c];
                     T[(size_t)(k0 + c) * f + i] = out;
@@ -339,7 +371,9 @@ __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_
                 }
             }
         }
+        FK_DSTAMP(2);
         __syncthreads();
+        FK_DSTAMP(3);
         // rank-8 update of the rows below the micro-panel: C[i][j] -= sum_c l_ic * y_jc
         if (i >= k0 + MB && i < nc) {
             double l[MB];
@@ -358,6 +392,7 @@ __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_
                 row[j] = v0 + v1;
             }
         }
+        FK_DSTAMP(4);
     }
 }
 
@@ -507,6 +542,11 @@ mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // against the published diagonal tile (panel tile) or stores it (update-matrix tile).  Tiles are numbered
 // column by column, so a CTA only ever waits for CTAs with a smaller block index: the schedule cannot
 // deadlock however many CTAs are resident.  One launch per level instead of 1 + 3 per pivot block.
+#ifdef FK_CHAIN_PROFILE
+#define FK_FSTAMP(k) do { if (threadIdx.x == 0) ((long long*)D.ubuf)[blockIdx.x * 4 + (k)] = global_ns(); } while (0)
+#else
+#define FK_FSTAMP(k) do { } while (0)
+#endif
 constexpr size_t kFlowSmem = (TB * kYsLd + TB * kTsLd + TB) * sizeof(double);
 static_assert(kFlowSmem >= sizeof(TileBuf), "the staging buffers alias the solve tiles");
 
@@ -535,6 +575,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
     const bool diag_tile = row0 == tcol0;
     const uint32_t tid = threadIdx.x, tx = tid & 15, c4 = (tid >> 4) * 4;
     double acc[4][4];
+    FK_FSTAMP(0);
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -543,7 +584,10 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
             const bool ok = ri < nrA && c4 + j < nrB && (!diag_tile || ri >= c4 + j);
             acc[i][j] = ok ? T[(size_t)(c4 + j) * ld + ri] : 0.0;
         }
-    for (uint32_t b = 0; b < nwait; b++)
+    for (uint32_t b = 0; b + 1 < nwait; b++)
+        tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf);
+    FK_FSTAMP(1);
+    for (uint32_t b = nwait ? nwait - 1 : 0; b < nwait; b++)
         tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf);
     if (!in_panel) {
 #pragma unroll
@@ -555,6 +599,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
             }
         return;
     }
+    FK_FSTAMP(2);
     const uint32_t nc = nrB;  // pivot columns of this block
     if (diag_tile) {
         double* Cs = smf;
@@ -567,6 +612,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
                 if (ri < nc && c4 + j <= ri) Cs[ri * kTsLd + c4 + j] = acc[i][j];
             }
         diag_tile_factor<true>(Cs, Ys, nc, T, Pp + (size_t)tcol0 * f + row0, f, D.status);
+        FK_FSTAMP(3);
         return;
     }
     double* Cs = smf;                 // [TB][kYsLd]
@@ -620,6 +666,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
             st_relaxed(Tp + (size_t)j * f + ii, v);
         }
     }
+    FK_FSTAMP(3);
 }
 
 // ---- triangular solves ------------------------------------------------------------------------------------
@@ -921,11 +968,6 @@ __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, d
 // row (lanes 4r..4r+3), so every reduction is two shuffles in a fixed order and the loop over the
 // awaited blocks has no CTA barrier; one link of the chain costs about a microsecond.
 #ifdef FK_CHAIN_PROFILE
-__device__ __forceinline__ long long global_ns() {
-    long long v;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
-    return v;
-}
 #define FK_CSTAMP(k) do { if (threadIdx.x == 0) ((long long*)D.upd)[blockIdx.x * 8 + (k)] = global_ns(); } while (0)
 #else
 #define FK_CSTAMP(k) do { } while (0)
@@ -1526,25 +1568,43 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             for (uint32_t s : L)
                 for (uint32_t b = (ns[s] + TB - 1) / TB; b-- > 0;) push_chain(s, b * TB, std::min<uint32_t>(TB, ns[s] - b * TB));
             c.bwd_count = (uint32_t)(chain_tasks_.size() / 4) - c.bwd_first;
-            // tile dataflow factorisation: tiles column by column (dependencies point to smaller indices)
-            static const bool no_flow = std::getenv("FK_NO_FLOW") != nullptr;  // debug / A-B knob
-            if (!no_flow) {
-                c.flow_first = (uint32_t)(chain_tasks_.size() / 4);
-                std::vector<std::pair<uint32_t, uint32_t>> blk;
-                for (uint32_t s : L) {
-                    blk.clear();
-                    for (uint32_t r0 = 0; r0 < ns[s]; r0 += TB) blk.push_back({r0, std::min<uint32_t>(TB, ns[s] - r0)});
-                    for (uint32_t r0 = ns[s]; r0 < f[s]; r0 += TB) blk.push_back({r0, std::min<uint32_t>(TB, f[s] - r0)});
-                    for (size_t bj = 0; bj < blk.size(); bj++)
-                        for (size_t bi = bj; bi < blk.size(); bi++) {
-                            chain_tasks_.push_back(s); chain_tasks_.push_back(blk[bi].first); chain_tasks_.push_back(blk[bj].first);
-                            chain_tasks_.push_back((blk[bi].second - 1) | ((blk[bj].second - 1) << 8));
-                        }
-                    flow_pub_lo_ = std::min<uint64_t>(flow_pub_lo_, pan_off[s]);
-                    flow_pub_hi_ = std::max<uint64_t>(flow_pub_hi_, pan_off[s] + (uint64_t)f[s] * ns[s]);
-                }
-                c.flow_count = (uint32_t)(chain_tasks_.size() / 4) - c.flow_first;
+        }
+        // tile dataflow factorisation: every level whose fronts are larger than one tile (no residency condition:
+        // tiles are numbered column by column, dependencies point to smaller block indices)
+        static const bool no_flow = std::getenv("FK_NO_FLOW") != nullptr;  // debug / A-B knob
+        // Measured on the 400x250 lattice (5 factorisations): dataflow on the levels with <= ~1,000 tiles 26.1 ms, on
+        // every level with a front above 256 / 128 / 64 rows 26.7 / 27.0 / 27.5 ms, on none 30.3 ms: levels with many
+        // supernodes are throughput bound and better served by the wide launch-per-step kernels.
+        static const uint32_t flow_max_tiles = [] {
+            const char* e = std::getenv("FK_FLOW_MAX_TILES");
+            return (uint32_t)(e ? std::max(0, std::atoi(e)) : 1024);
+        }();
+        for (uint32_t l = 0; l < nlevels && !off && !no_flow; l++) {
+            const std::vector<uint32_t>& L = by_level[l];
+            uint64_t tiles = 0;
+            uint32_t fmax = 0;
+            for (uint32_t s : L) {
+                const uint64_t nb = (ns[s] + TB - 1) / TB + (f[s] - ns[s] + TB - 1) / TB;
+                tiles += nb * (nb + 1) / 2;
+                fmax = std::max(fmax, f[s]);
             }
+            if (fmax <= (uint32_t)TB || tiles > flow_max_tiles) continue;
+            ChainLevel& c = chain_[l];
+            c.flow_first = (uint32_t)(chain_tasks_.size() / 4);
+            std::vector<std::pair<uint32_t, uint32_t>> blk;
+            for (uint32_t s : L) {
+                blk.clear();
+                for (uint32_t r0 = 0; r0 < ns[s]; r0 += TB) blk.push_back({r0, std::min<uint32_t>(TB, ns[s] - r0)});
+                for (uint32_t r0 = ns[s]; r0 < f[s]; r0 += TB) blk.push_back({r0, std::min<uint32_t>(TB, f[s] - r0)});
+                for (size_t bj = 0; bj < blk.size(); bj++)
+                    for (size_t bi = bj; bi < blk.size(); bi++) {
+                        chain_tasks_.push_back(s); chain_tasks_.push_back(blk[bi].first); chain_tasks_.push_back(blk[bj].first);
+                        chain_tasks_.push_back((blk[bi].second - 1) | ((blk[bj].second - 1) << 8));
+                    }
+                flow_pub_lo_ = std::min<uint64_t>(flow_pub_lo_, pan_off[s]);
+                flow_pub_hi_ = std::max<uint64_t>(flow_pub_hi_, pan_off[s] + (uint64_t)f[s] * ns[s]);
+            }
+            c.flow_count = (uint32_t)(chain_tasks_.size() / 4) - c.flow_first;
         }
         inv_first_ = (uint32_t)(chain_tasks_.size() / 4);
         for (uint32_t s : chained)
@@ -1613,7 +1673,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         MF_CU(cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem));
         MF_CU(cudaFuncSetAttribute(mf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem));
         bool any_flow = false;
-        for (const ChainLevel& c : chain_) any_flow = any_flow || (c.on && c.flow_count);
+        for (const ChainLevel& c : chain_) any_flow = any_flow || c.flow_count;
         if (any_flow) {  // published panel tiles of the dataflow levels (addressed like the panel storage)
             MF_CU(alloc_vec(&d_pan_pub_, (size_t)(flow_pub_hi_ - flow_pub_lo_), owned_));
         }
@@ -1668,7 +1728,7 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
     }
     const uint32_t nlv = (uint32_t)level_seq_ptr_.size() - 1;
     for (uint32_t lv = 0; lv < nlv; lv++) {
-        const bool flow = d_pan_pub_ && chain_[lv].on && chain_[lv].flow_count;
+        const bool flow = d_pan_pub_ && chain_[lv].flow_count;
         for (uint32_t qi = level_seq_ptr_[lv]; qi < level_seq_ptr_[lv + 1]; qi++) {
             const Launch& l = factor_seq_[qi];
             if (flow && l.kind != 0) continue;  // the level's diag / panel / update launches are replaced below
