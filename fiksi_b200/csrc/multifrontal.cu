@@ -352,13 +352,14 @@ __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_
         // own row against the block: y_c = p_c - sum_{c' < c} y_c' L88[c][c']  (unscaled multipliers; for a
         // row inside the micro-panel y_c is its pivot at c == i - k0 and unused beyond)
         const bool active = i >= k0 && i < nc;
+        // (column-oriented: once y[cp] is final, all later entries take its term -- the same sum order per entry as the
+        // row-oriented loop, but the FMAs of one step are independent; a dependent DFMA costs ~45 cycles here)
 #pragma unroll
-        for (int c = 0; c < MB; c++) {
-            double v = (active && (uint32_t)c < kw && k0 + c <= i) ? Cs[i * kTsLd + k0 + c] : 0.0;
+        for (int c = 0; c < MB; c++) y[c] = (active && (uint32_t)c < kw && k0 + c <= i) ? Cs[i * kTsLd + k0 + c] : 0.0;
 #pragma unroll
-            for (int cp = 0; cp < c; cp++) v = fma(-y[cp], ll[c][cp], v);
-            y[c] = v;
-        }
+        for (int cp = 0; cp + 1 < MB; cp++)
+#pragma unroll
+            for (int c = cp + 1; c < MB; c++) y[c] = fma(-y[cp], ll[c][cp], y[c]);
         FK_DSTAMP(5);
         if (active) {  // the four threads of a row hold the same y: each stores two of the eight columns
 #pragma unroll
@@ -423,13 +424,11 @@ constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (ro
 __device__ __forceinline__ void col_tile_step(double* row, const double* Ls, uint32_t k0, uint32_t nc, uint32_t q) {
     double y[MB];
 #pragma unroll
-    for (int c = 0; c < MB; c++) {
-        double v = row[k0 + c];
-        const double* Lc = Ls + (k0 + c) * kTsLd + k0;
+    for (int c = 0; c < MB; c++) y[c] = row[k0 + c];
 #pragma unroll
-        for (int cp = 0; cp < c; cp++) v = fma(-y[cp], Lc[cp], v);
-        y[c] = v;
-    }
+    for (int cp = 0; cp + 1 < MB; cp++)  // column-oriented substitution: independent FMAs per step, same sum order per entry
+#pragma unroll
+        for (int c = cp + 1; c < MB; c++) y[c] = fma(-y[cp], Ls[(k0 + c) * kTsLd + k0 + cp], y[c]);
     __syncwarp();  // all four threads of the row have read the block before it is overwritten
     if (q == 0) {
 #pragma unroll
@@ -716,12 +715,11 @@ __device__ __forceinline__ void pivot_forward_256(const double* __restrict__ P, 
         __syncthreads();
         double yy[MB];
 #pragma unroll
-        for (int c = 0; c < MB; c++) {
-            double v = k0 + c < ns ? t[k0 + c] : 0.0;
+        for (int c = 0; c < MB; c++) yy[c] = k0 + c < ns ? t[k0 + c] : 0.0;
 #pragma unroll
-            for (int cp = 0; cp < c; cp++) v = fma(-lb[c * 8 + cp], yy[cp], v);
-            yy[c] = v;
-        }
+        for (int cp = 0; cp + 1 < MB; cp++)
+#pragma unroll
+            for (int c = cp + 1; c < MB; c++) yy[c] = fma(-lb[c * 8 + cp], yy[cp], yy[c]);
         if (tid < MB && k0 + tid < ns) {
             double v = 0.0;
 #pragma unroll
