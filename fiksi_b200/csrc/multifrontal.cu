@@ -550,7 +550,8 @@ constexpr size_t kFlowSmem = (TB * kYsLd + TB * kTsLd + TB) * sizeof(double);
 static_assert(kFlowSmem >= sizeof(TileBuf), "the staging buffers alias the solve tiles");
 
 __global__ void __launch_bounds__(kTileThreads)
-mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pub) {
+mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pub, const uint32_t* __restrict__ asm_ptr,
+               const uint4* __restrict__ asm_ent) {
     extern __shared__ __align__(16) double smf[];
     TileBuf& buf = *reinterpret_cast<TileBuf*>(smf);
     const uint4 t = __ldg(tasks + blockIdx.x);
@@ -575,14 +576,37 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
     const uint32_t tid = threadIdx.x, tx = tid & 15, c4 = (tid >> 4) * 4;
     double acc[4][4];
     FK_FSTAMP(0);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t ri = tile_row(tx, i);
-            const bool ok = ri < nrA && c4 + j < nrB && (!diag_tile || ri >= c4 + j);
-            acc[i][j] = ok ? T[(size_t)(c4 + j) * ld + ri] : 0.0;
+    {
+        // Extend-add of the children (replaces mf_asm_kernel on these levels): the tile's assembled values go to
+        // shared memory, every child adds the part of its update matrix that lands in this tile (index ranges
+        // precomputed on the host; children in ascending order, distinct targets within a child), and the sum is
+        // the tile's starting value.  Update-matrix tiles start from zero, so U_s needs no separate clearing.
+        double* S = smf;  // [TB][kTsLd]
+        const uint32_t e0 = __ldg(asm_ptr + blockIdx.x), e1 = __ldg(asm_ptr + blockIdx.x + 1);
+        for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
+            const uint32_t ri = e & 63, cj = e >> 6;
+            const bool ok = in_panel && ri < nrA && cj < nrB && (!diag_tile || ri >= cj);
+            S[ri * kTsLd + cj] = ok ? T[(size_t)cj * ld + ri] : 0.0;
         }
+        __syncthreads();
+        for (uint32_t q = e0; q < e1; q++) {
+            const uint4 A = __ldg(asm_ent + q);
+            const uint32_t c = A.x, a0 = A.y & 0xFFFFu, na = A.y >> 16, b0 = A.z & 0xFFFFu, nb = A.z >> 16;
+            const uint32_t rc = __ldg(D.f + c) - __ldg(D.ns + c);
+            const double* Uc = D.upd + __ldg(D.upd_off + c);
+            const uint32_t* relc = D.rel + __ldg(D.rel_off + c);
+            for (uint32_t x = tid; x < na * nb; x += kTileThreads) {
+                const uint32_t a = a0 + x % na, b = b0 + x / na;
+                if (a >= b) S[(__ldg(relc + a) - row0) * kTsLd + (__ldg(relc + b) - tcol0)] += Uc[(size_t)b * rc + a];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = S[tile_row(tx, i) * kTsLd + c4 + j];
+        __syncthreads();  // S aliases the staging buffers of the update loop
+    }
     for (uint32_t b = 0; b + 1 < nwait; b++)
         tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf);
     FK_FSTAMP(1);
@@ -1530,6 +1554,8 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
     std::fill(winv_blk.begin(), winv_blk.end(), 0u);
     winv_blocks = 0;
     inv_first_ = inv_count_ = 0;
+    flow_asm_ptr_.clear();
+    flow_asm_.clear();
     flow_pub_lo_ = ~0ull;
     flow_pub_hi_ = 0;
     {
@@ -1603,6 +1629,27 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
                 flow_pub_hi_ = std::max<uint64_t>(flow_pub_hi_, pan_off[s] + (uint64_t)f[s] * ns[s]);
             }
             c.flow_count = (uint32_t)(chain_tasks_.size() / 4) - c.flow_first;
+            // extend-add ranges of every (tile, child): rows / columns of the child's update matrix inside the tile
+            c.asm_first = (uint32_t)flow_asm_ptr_.size();
+            for (uint32_t q = c.flow_first; q < c.flow_first + c.flow_count; q++) {
+                const uint32_t s = chain_tasks_[4 * (size_t)q], row0 = chain_tasks_[4 * (size_t)q + 1], tcol0 = chain_tasks_[4 * (size_t)q + 2];
+                const uint32_t w = chain_tasks_[4 * (size_t)q + 3], nrA = (w & 0xFFu) + 1, nrB = ((w >> 8) & 0xFFu) + 1;
+                flow_asm_ptr_.push_back((uint32_t)(flow_asm_.size() / 4));
+                for (uint32_t cq = child_ptr[s]; cq < child_ptr[s + 1]; cq++) {
+                    const uint32_t ch = child[cq];
+                    const uint32_t* rb = rel.data() + rel_off[ch];
+                    const uint32_t* re = rel.data() + rel_off[ch + 1];
+                    const uint32_t a0 = (uint32_t)(std::lower_bound(rb, re, row0) - rb), a1 = (uint32_t)(std::lower_bound(rb, re, row0 + nrA) - rb);
+                    const uint32_t b0 = (uint32_t)(std::lower_bound(rb, re, tcol0) - rb), b1 = (uint32_t)(std::lower_bound(rb, re, tcol0 + nrB) - rb);
+                    if (a1 <= a0 || b1 <= b0 || a1 - 1 < b0) continue;  // nothing of this child in the tile's lower part
+                    if (a0 >= (1u << 16) || b0 >= (1u << 16)) {
+                        if (err) *err = "multifrontal: update matrix too large for the packed extend-add ranges";
+                        return cudaErrorInvalidValue;
+                    }
+                    flow_asm_.push_back(ch); flow_asm_.push_back(a0 | ((a1 - a0) << 16)); flow_asm_.push_back(b0 | ((b1 - b0) << 16)); flow_asm_.push_back(0);
+                }
+            }
+            flow_asm_ptr_.push_back((uint32_t)(flow_asm_.size() / 4));
         }
         inv_first_ = (uint32_t)(chain_tasks_.size() / 4);
         for (uint32_t s : chained)
@@ -1674,6 +1721,10 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         for (const ChainLevel& c : chain_) any_flow = any_flow || c.flow_count;
         if (any_flow) {  // published panel tiles of the dataflow levels (addressed like the panel storage)
             MF_CU(alloc_vec(&d_pan_pub_, (size_t)(flow_pub_hi_ - flow_pub_lo_), owned_));
+            MF_CU(upload_vec(flow_asm_ptr_, &d_flow_asm_ptr_, owned_));
+            const uint32_t* pe = nullptr;
+            MF_CU(upload_vec(flow_asm_, &pe, owned_));
+            d_flow_asm_ = (const uint4*)pe;
         }
     }
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
@@ -1729,7 +1780,7 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
         const bool flow = d_pan_pub_ && chain_[lv].flow_count;
         for (uint32_t qi = level_seq_ptr_[lv]; qi < level_seq_ptr_[lv + 1]; qi++) {
             const Launch& l = factor_seq_[qi];
-            if (flow && l.kind != 0) continue;  // the level's diag / panel / update launches are replaced below
+            if (flow) continue;  // the level's assembly / diag / panel / update launches are replaced below
             const uint4* tk = d_tasks_ + l.first;
             seq_no++;
             cur_count = l.count;
@@ -1748,7 +1799,8 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
             // the published buffer is addressed with the panel offsets: bias the base so that pub + pan_off lands in it
             timed(3, [&] {
                 mf_flow_kernel<<<chain_[lv].flow_count, kTileThreads, kFlowSmem, st>>>(dev_, d_chain_tasks_ + chain_[lv].flow_first,
-                                                                                    d_pan_pub_ - flow_pub_lo_);
+                                                                                    d_pan_pub_ - flow_pub_lo_, d_flow_asm_ptr_ + chain_[lv].asm_first,
+                                                                                    d_flow_asm_);
             });
         }
     }

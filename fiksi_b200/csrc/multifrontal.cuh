@@ -111,7 +111,7 @@ private:
     std::vector<bool> level_wide_;  // a supernode of the level has >= 64 pivot columns
     std::vector<bool> level_narrow_;  // every front of the level has order <= 64
     // chained solves of the wide levels near the root (64-row chunks, one CTA each, values polled in place)
-    struct ChainLevel { bool on = false; uint32_t fwd_first = 0, fwd_count = 0, dot_first = 0, dot_count = 0, bwd_first = 0, bwd_count = 0, flow_first = 0, flow_count = 0; };
+    struct ChainLevel { bool on = false; uint32_t fwd_first = 0, fwd_count = 0, dot_first = 0, dot_count = 0, bwd_first = 0, bwd_count = 0, flow_first = 0, flow_count = 0, asm_first = 0; };
     std::vector<ChainLevel> chain_;
     std::vector<uint32_t> chain_tasks_;
     const uint4* d_chain_tasks_ = nullptr;
@@ -120,6 +120,9 @@ private:
     // tile dataflow factorisation of the chained levels: published panel tiles [flow_pub_lo_, flow_pub_hi_) of the panel storage
     std::vector<uint32_t> level_seq_ptr_;
     double* d_pan_pub_ = nullptr;
+    std::vector<uint32_t> flow_asm_ptr_, flow_asm_;  // per dataflow tile: extend-add ranges of its children (uint4 entries)
+    const uint32_t* d_flow_asm_ptr_ = nullptr;
+    const uint4* d_flow_asm_ = nullptr;
     uint64_t flow_pub_lo_ = ~0ull, flow_pub_hi_ = 0;
     cudaGraphExec_t factor_graph_ = nullptr, solve_graph_ = nullptr;
     double* solve_w_ = nullptr; double* solve_delta_ = nullptr; const int32_t* solve_perm_ = nullptr;

@@ -20,6 +20,7 @@ int main() {
     for (uint32_t bj = 0; bj < B; bj++) for (uint32_t bi = bj; bi < B; bi++) tasks.push_back({0, bi * 64, bj * 64, 63u | (63u << 8)});
     uint4* dt; cudaMalloc(&dt, tasks.size() * 16); cudaMemcpy(dt, tasks.data(), tasks.size() * 16, cudaMemcpyHostToDevice);
     double* pub; cudaMalloc(&pub, A.size() * 8);
+    uint32_t* aptr; cudaMalloc(&aptr, (tasks.size() + 1) * 4); cudaMemset(aptr, 0, (tasks.size() + 1) * 4);  // no children
     cudaFuncSetAttribute(mf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
     long long* dst = (long long*)D.status + 8;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -27,10 +28,22 @@ int main() {
         cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
         cudaMemset(pub, 0xFF, A.size() * 8);
         cudaEventRecord(a);
-        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub);
+        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr);
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b);
         printf("rep %d: flow factor %.1f us, %zu tiles (%s)\n", rep, ms * 1e3, tasks.size(), cudaGetErrorString(cudaGetLastError()));
+    }
+    {   // the first diagonal tile alone: one CTA, nothing else on the device
+        cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+        cudaMemset(pub, 0xFF, A.size() * 8);
+        mf_flow_kernel<<<1, kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr);
+        cudaDeviceSynchronize();
+        long long one[4]; cudaMemcpy(one, D.ubuf, sizeof(one), cudaMemcpyDeviceToHost);
+        printf("tile (0,0) alone: %lld ns from the end of the update loop to the end (%s)\n", one[3] - one[2], cudaGetErrorString(cudaGetLastError()));
+        cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+        cudaMemset(pub, 0xFF, A.size() * 8);
+        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr);
+        cudaDeviceSynchronize();
     }
     std::vector<long long> st(tasks.size() * 4);
     cudaMemcpy(st.data(), D.ubuf, st.size() * 8, cudaMemcpyDeviceToHost);
