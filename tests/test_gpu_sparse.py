@@ -107,3 +107,39 @@ def test_config3_full_lattice_properties():
     assert rep2["factorizations"] == 0 and np.array_equal(x2, x)
     x3, rep3 = topo.lm_solve(v[0], p[0], x0)
     assert np.array_equal(x3, x) and rep3["trace_hash"] == rep["trace_hash"]
+
+
+_SCHEDULE_SCRIPT = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+import fiksi_b200 as fk
+from fiksi_b200 import workloads as wl
+w = wl.lattice(150, 120)
+v, p, scale = w.prepare()
+topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+x, rep = topo.lm_solve(v[0], p[0], v[0][w.free_vars])
+np.save(sys.argv[1], x)
+print(int(rep["exit_reason"]), int(rep["factorizations"]), int(rep["trace_hash"]), repr(float(rep["ssr"])))
+"""
+
+
+def test_dataflow_and_chained_schedules_match_the_launch_per_step_schedule(tmp_path):
+    """The levels near the root are factorised by the tile dataflow kernel and solved by the chained multi-CTA
+    kernels (csrc/multifrontal.cu).  Against the launch-per-step schedule (FK_NO_FLOW / FK_NO_CHAIN; the knobs are
+    read once per process, hence the subprocesses): the dataflow factorisation keeps every summation order, so the
+    LM solve is bit-identical; the chained solves use the inverse of the 64x64 pivot triangles, so the coordinates
+    agree to rounding."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("default", {}), ("no_flow", {"FK_NO_FLOW": "1"}), ("no_chain", {"FK_NO_CHAIN": "1"})):
+        path = str(tmp_path / (name + ".npy"))
+        e = dict(os.environ, **env)
+        r = subprocess.run([sys.executable, "-c", _SCHEDULE_SCRIPT % root, path], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = (r.stdout.strip().splitlines()[-1], np.load(path))
+    assert outs["default"][0].split()[0] == "0"
+    assert outs["no_flow"][0] == outs["default"][0] and np.array_equal(outs["no_flow"][1], outs["default"][1])
+    assert outs["no_chain"][0].split()[:3] == outs["default"][0].split()[:3]
+    assert _rel(outs["no_chain"][1], outs["default"][1]) <= 1e-11
