@@ -300,6 +300,10 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["single_sketch"] = {"error": str(e)}
             try:
+                line["hinged_triangles"] = hinged_triangles_side(fk, wl)
+            except Exception as e:  # noqa: BLE001
+                line["hinged_triangles"] = {"error": str(e)}
+            try:
                 line["single_pass"] = single_pass_side(fk, wl)
             except Exception as e:  # noqa: BLE001
                 line["single_pass"] = {"error": str(e)}
@@ -345,9 +349,51 @@ def single_sketch_latency(fk, wl):
             "note": "one sketch cannot amortise a kernel launch and two host<->device copies; batches can (see value / config4_lm)"}
 
 
+def hinged_triangles_side(fk, wl):
+    """The reference's own criterion shapes (fiksi/benches/fiksi_bench.rs:15-40: chains of 1 / 4 / 16 / 64 hinged
+    triangles, Decomposer::None): one system at a time on the CPU restatement (one core, symbolic analysis inside every
+    call as in the reference) and on the GPU (cached topology), and a batch of 16,384 perturbed copies on the GPU."""
+    import numpy as np
+    import oracle
+    out = []
+    for nt in (1, 4, 16, 64):
+        w1 = wl.hinged_triangles(nt)
+        v, p, scale = w1.prepare()
+        topo = fk.Topology.from_arrays(w1.n_vars, w1.kind, w1.idx, w1.free_vars, w1.rows)
+        x0 = v[0][w1.free_vars]
+        for _ in range(3):
+            topo.lm_solve(v[0], p[0], x0)
+        reps = 50
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            xg, rg = topo.lm_solve(v[0], p[0], x0)
+        gpu_us = (time.perf_counter() - t0) / reps * 1e6
+        op, keep = oracle.make_problem(v[0], w1.kind, w1.idx, p[0], w1.free_vars, w1.rows)
+        creps = max(3, min(200, 2000 // nt))
+        t0 = time.perf_counter()
+        for _ in range(creps):
+            xo, ro, _ = oracle.lm_solve(op, x0)
+        cpu_us = (time.perf_counter() - t0) / creps * 1e6
+        nb = 16384
+        wb = wl.hinged_triangles(nt, nb)
+        vb, pb, _ = wb.prepare()
+        topo.batch_solve(vb[:256], pb[:256])
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            xb, rb = topo.batch_solve(vb, pb)
+            best = min(best, time.perf_counter() - t0)
+        out.append({"triangles": nt, "variables": int(len(w1.free_vars)), "rows": int(len(w1.rows)), "path": int(topo.info["path"]),
+                    "cpu_port_us_per_solve_1core": cpu_us, "gpu_us_per_solve_single_system": gpu_us,
+                    "gpu_batch_sketches_per_s": nb / best, "gpu_batch_us_per_sketch": best / nb * 1e6,
+                    "same_trace": bool(rg["trace_hash"] == ro["trace_hash"]),
+                    "batch_fraction_converged": float(np.mean(rb["ssr"] < 1e-8))})
+    return out
+
+
 def single_pass_side(fk, wl):
     """SURVEY 8f-1: Decomposer::SinglePass on a batch of hinged-triangle chains (fiksi_bench.rs shape, 16
-    triangles = 34 variables): one batched LM launch per strongly connected set, beside Decomposer::None on
+    triangles = 66 variables): one batched LM launch per strongly connected set, beside Decomposer::None on
     the same batch and the CPU restatement of the SinglePass loop."""
     import numpy as np
     import oracle
@@ -375,7 +421,7 @@ def single_pass_side(fk, wl):
         vo, ro = oracle.single_pass_problem(opk, v[k])
         same = same and np.array_equal(ro["trace_hash"], rg[k]["trace_hash"])
     cpu_s = time.perf_counter() - t0
-    return {"workload": "131,072 hinged chains of 16 triangles (34 variables, 48 rows), host buffers, device-resident between sets", "steps": int(rg.shape[1]),
+    return {"workload": "131,072 hinged chains of 16 triangles (66 variables, 48 rows), host buffers, device-resident between sets", "steps": int(rg.shape[1]),
             "gpu_single_pass_sketches_per_s": n / sp_s, "gpu_decomposer_none_sketches_per_s": n / none_s,
             "cpu_port_single_pass_sketches_per_s_1core": ns / cpu_s, "traces_equal_on_sample": bool(same),
             "fraction_converged_single_pass": float(np.mean(rg["ssr"] < 1e-8))}
