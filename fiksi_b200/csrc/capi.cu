@@ -124,6 +124,11 @@ struct DevicePipeline {
     uint32_t chunk = 0;
     fk_batch_plan* plans[kStreams] = {nullptr, nullptr, nullptr};
     cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+    // small requests (one sketch, a handful): one pinned staging block, one device block, one copy each way
+    static constexpr size_t kSmallBytes = 64 * 1024;
+    unsigned char* small_h = nullptr;
+    unsigned char* small_d = nullptr;
+    cudaStream_t small_stream = nullptr;
     void release();
     ~DevicePipeline() { release(); }
 };
@@ -205,6 +210,11 @@ void DevicePipeline::release() {
         plans[s] = nullptr;
     }
     chunk = 0;
+    if (small_h) cudaFreeHost(small_h);
+    if (small_d) cudaFree(small_d);
+    if (small_stream) cudaStreamDestroy(small_stream);
+    small_h = small_d = nullptr;
+    small_stream = nullptr;
 }
 
 extern "C" {
@@ -635,6 +645,38 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
     if (total == 0) return FK_OK;
     DevicePipeline* pl = topo->pipeline_for(device);
     std::lock_guard<std::mutex> lock(pl->mu);
+    {
+        // Small request: the caller's (pageable) arrays go through ONE pinned staging block -- one copy in, the
+        // kernel, one copy out, one synchronisation -- instead of four pageable copies on the chunk pipeline
+        // (one mixed-primitive sketch: 159 us -> see bench.py `single_sketch`).
+        const size_t in_v = sizeof(double) * (size_t)total * t.n_vars, in_p = sizeof(double) * (size_t)total * t.n_expr;
+        const size_t out_x = sizeof(double) * (size_t)total * t.n_free, out_r = sizeof(fk_report) * (size_t)total;
+        const size_t in_al = (in_v + in_p + 15) & ~size_t(15);
+        if (in_al + out_x + out_r <= DevicePipeline::kSmallBytes) {
+            const fk::DevProgram* prog = nullptr;
+            int rc = topo->program_for(device, &prog);
+            if (rc != FK_OK) { if (err) *err = g_error; return rc; }
+            auto bad = [&](cudaError_t e, const char* what) { int c = cuda_fail(e, what); if (err) *err = g_error; return c; };
+            cudaError_t e = cudaSetDevice(device);
+            if (e != cudaSuccess) return bad(e, "cudaSetDevice");
+            if (!pl->small_h) {
+                if ((e = cudaMallocHost((void**)&pl->small_h, DevicePipeline::kSmallBytes)) != cudaSuccess) return bad(e, "cudaMallocHost");
+                if ((e = cudaMalloc((void**)&pl->small_d, DevicePipeline::kSmallBytes)) != cudaSuccess) return bad(e, "cudaMalloc");
+                if ((e = cudaStreamCreateWithFlags(&pl->small_stream, cudaStreamNonBlocking)) != cudaSuccess) return bad(e, "cudaStreamCreate");
+            }
+            std::memcpy(pl->small_h, vars + (size_t)lo * t.n_vars, in_v);
+            if (in_p) std::memcpy(pl->small_h + in_v, param + (size_t)lo * t.n_expr, in_p);
+            if ((e = cudaMemcpyAsync(pl->small_d, pl->small_h, in_v + in_p, cudaMemcpyHostToDevice, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+            const int le = fk::launch_batch_lm(*prog, total, (const double*)pl->small_d, (const double*)(pl->small_d + in_v), (double*)(pl->small_d + in_al),
+                                               (fk_report*)(pl->small_d + in_al + out_x), pl->small_stream);
+            if (le != 0) return bad((cudaError_t)le, "launch fk_batch_lm_kernel");
+            if ((e = cudaMemcpyAsync(pl->small_h + in_al, pl->small_d + in_al, out_x + out_r, cudaMemcpyDeviceToHost, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+            if ((e = cudaStreamSynchronize(pl->small_stream)) != cudaSuccess) return bad(e, "batch kernel / copy failed");
+            std::memcpy(free_out + (size_t)lo * t.n_free, pl->small_h + in_al, out_x);
+            if (reports) std::memcpy(reports + lo, pl->small_h + in_al + out_x, out_r);
+            return FK_OK;
+        }
+    }
     constexpr uint32_t kStreams = DevicePipeline::kStreams;
     // chunks small enough to overlap H2D / kernel / D2H, large enough to fill the machine
     static const uint32_t n_chunks = [] {
