@@ -139,6 +139,8 @@ struct fk_topology {
     std::map<int, std::unique_ptr<DeviceProgram>> programs;
     std::map<int, std::unique_ptr<DevicePipeline>> pipelines;
     std::map<int, std::unique_ptr<fk::SparseSolver>> sparse;  // path 2: one solver per device
+    std::unique_ptr<fk_topology> latency_twin;  // same topology with 32 lanes per sketch: single-system solves
+    bool twin_tried = false;
     std::mutex sp_mu;                   // SinglePass plan: one sub-topology per strongly connected set
     bool sp_planned = false;
     std::vector<fk_topology*> sp_subs;
@@ -775,7 +777,27 @@ int fk_topology_lm_solve(fk_topology* topo, const double* vars, const double* pa
     for (uint32_t f = 0; f < t.n_free; f++) v[t.free_vars[f]] = free_values[f];
     std::vector<double> zero;
     if (!param && t.n_expr) zero.assign(t.n_expr, 0.0);
-    int rc = run_device_range(topo, cur, 0, 1, v.data(), param ? param : zero.data(), out.data(), report, nullptr);
+    // One system is latency bound (one warp walks the whole LM loop): the lane count chosen for batch throughput
+    // (4-16 by footprint) leaves lanes of that warp idle.  A twin of the topology with all 32 lanes, built on the
+    // first single-system solve, serves these calls (same operations per entry, same results; tools/lat_probe.py:
+    // 144 -> 89 us on the mixed-primitive sketch).
+    fk_topology* exec = topo;
+    if (t.path == 0 && t.tile < 32) {
+        std::lock_guard<std::mutex> lock(topo->mu);
+        if (!topo->twin_tried) {
+            topo->twin_tried = true;
+            static const bool off = std::getenv("FK_NO_LATENCY_TWIN") != nullptr;
+            if (!off) {
+                fk_problem p{};
+                p.n_vars = t.n_vars; p.n_expr = t.n_expr; p.kind = t.kind.data(); p.idx = t.idx.data();
+                p.n_free = t.n_free; p.free_vars = t.free_vars.data(); p.n_rows = t.n_rows; p.rows = t.rows.data();
+                std::unique_ptr<fk_topology> tw(new (std::nothrow) fk_topology());
+                if (tw && tw->t.build(p, 32) == FK_OK && tw->t.path == 0) topo->latency_twin = std::move(tw);
+            }
+        }
+        if (topo->latency_twin) exec = topo->latency_twin.get();
+    }
+    int rc = run_device_range(exec, cur, 0, 1, v.data(), param ? param : zero.data(), out.data(), report, nullptr);
     if (rc == FK_OK && t.n_free) std::memcpy(free_values, out.data(), sizeof(double) * t.n_free);
     return rc;
 }

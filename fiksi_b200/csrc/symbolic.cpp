@@ -60,7 +60,7 @@ static uint64_t mix(uint64_t h, uint64_t v) {
     return h ^ (h >> 33);
 }
 
-int Topology::build(const fk_problem& p) {
+int Topology::build(const fk_problem& p, uint32_t lanes) {
     // FK_SYM_TIMING=1: wall time of every phase of the host symbolic pipeline to stderr
     static const bool sym_timing = std::getenv("FK_SYM_TIMING") != nullptr;
     auto sym_t0 = std::chrono::steady_clock::now();
@@ -334,6 +334,7 @@ int Topology::build(const fk_problem& p) {
             int v = std::atoi(t);
             if (path == 0 && (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32)) tile = (uint32_t)v;
         }
+        if (lanes && path == 0) tile = lanes;
     }
 
     lap("path selection");

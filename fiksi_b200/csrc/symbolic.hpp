@@ -98,7 +98,8 @@ struct Topology {
     std::string error;
 
     // Runs the whole pipeline.  Returns FK_OK or an error status (message in `error`).
-    int build(const fk_problem& p);
+    // `lanes` != 0 overrides the lanes per sketch of the tile path (the latency-oriented twin of a topology uses 32).
+    int build(const fk_problem& p, uint32_t lanes = 0);
     void fill_info(fk_topology_info* info) const;
 };
 
