@@ -141,7 +141,9 @@ FK_API int fk_symbolic(const fk_problem* problem, uint32_t* aug_colptr, uint32_t
 /* Solve one system with an existing topology (symbolic analysis reused across calls).  Takes the
  * batched shared-memory kernel with n = 1 or, for large systems (info.path == 2), the global
  * sparse path: K1/K2 evaluation, K3 normal-equation assembly and K5 sparse LDL^T on the device with
- * a thin host loop for the accept/reject decisions. */
+ * a thin host loop for the accept/reject decisions.  On the shared-memory path the first call builds a
+ * twin of the topology with 32 lanes per sketch (single systems are latency bound; the topology's own
+ * lane count is chosen for batch throughput); results do not depend on the lane count. */
 FK_API int fk_topology_lm_solve(fk_topology* topo, const double* vars, const double* param,
                                 double* free_values, fk_report* report);
 /* Large systems only: one residual + Jacobian evaluation at free_values (out_r[n_rows],
