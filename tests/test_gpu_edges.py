@@ -74,3 +74,19 @@ def test_ragged_batch_sizes(oracle):
         xo, ro, _ = oracle.lm_solve_batch_uniform(op, v, p, threads=2)
         assert np.array_equal(rep["trace_hash"], ro["trace_hash"]) and np.array_equal(rep["exit_reason"], ro["exit_reason"])
         assert np.max(np.abs(x - xo)) <= REL * np.max(np.abs(xo))
+
+
+@pytest.mark.parametrize("maker", [lambda: wl.cad_mix(3), lambda: wl.truss(3), lambda: wl.hinged_triangles(4, 3),
+                                   lambda: wl.hinged_triangles(16, 3)])
+def test_single_system_twin_matches_the_batch_lane_count(maker):
+    """fk_topology_lm_solve runs single systems on a 32-lane twin of the topology; the batch entry uses the
+    topology's own lane count (4-16 here).  Same operations per entry: coordinates and decisions are identical."""
+    w = maker()
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    assert topo.info["path"] == 0 and topo.info["tile"] < 32
+    xb, rb = topo.batch_solve(v, p)
+    for k in range(len(v)):
+        x1, r1 = topo.lm_solve(v[k], p[k], v[k][w.free_vars])
+        assert np.array_equal(x1, xb[k])
+        assert r1["trace_hash"] == rb[k]["trace_hash"] and r1["exit_reason"] == rb[k]["exit_reason"]
