@@ -143,3 +143,62 @@ def test_dataflow_and_chained_schedules_match_the_launch_per_step_schedule(tmp_p
     assert outs["no_flow"][0] == outs["default"][0] and np.array_equal(outs["no_flow"][1], outs["default"][1])
     assert outs["no_chain"][0].split()[:3] == outs["default"][0].split()[:3]
     assert _rel(outs["no_chain"][1], outs["default"][1]) <= 1e-11
+
+
+@pytest.mark.parametrize("seed,n_pts,extra", [(1, 150, 40), (2, 400, 150), (3, 700, 0)])
+def test_irregular_distance_graphs_on_sparse_path(oracle, force_sparse, seed, n_pts, extra):
+    """Irregular structure (not a lattice): random points, every point tied to two earlier nearby points
+    (Henneberg steps) plus random extra distances (over-constrained, consistent), a few points pinned; the fronts
+    are uneven, so supernodes, dataflow levels and chained solves get shapes the lattices never produce."""
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0.0, 10.0, size=(n_pts, 2))
+    edges = [(0, 1)]
+    for k in range(2, n_pts):
+        d = np.sum((pts[:k] - pts[k]) ** 2, axis=1)
+        a, b = np.argsort(d)[:2]
+        edges += [(int(a), k), (int(b), k)]
+    for _ in range(extra):
+        a, b = rng.choice(n_pts, size=2, replace=False)
+        edges.append((int(min(a, b)), int(max(a, b))))
+    kind = np.ones(len(edges), np.uint8)
+    idx = np.array([[2 * a, 2 * b, 0, 0] for a, b in edges], np.uint32)
+    dist = np.array([np.hypot(*(pts[a] - pts[b])) for a, b in edges])
+    noisy = pts + rng.uniform(-0.02, 0.02, size=pts.shape)
+    pinned = {0, 1, 2, 3}  # the first two points stay where they are
+    free_vars = np.array([q for q in range(2 * n_pts) if q not in pinned], np.uint32)
+    w = wl.Workload("irregular", kind, idx, free_vars, np.arange(len(edges)), noisy.reshape(1, -1), dist.reshape(1, -1))
+    v, p, scale = w.prepare()
+    _check_against_oracle(oracle, (v[0], w.kind, w.idx, p[0], w.free_vars, w.rows))
+
+
+def test_large_irregular_graph_properties():
+    """24,000 variables of irregular structure at a size the oracle cannot reach: residual exit, every distance met,
+    deterministic re-run (the dataflow / chained levels run with uneven fronts)."""
+    rng = np.random.default_rng(11)
+    n_pts = 12000
+    pts = rng.uniform(0.0, 100.0, size=(n_pts, 2))
+    order = np.argsort(pts[:, 0] + 0.37 * pts[:, 1], kind="stable")  # sweep order keeps the two neighbours close
+    pts = pts[order]
+    edges = [(0, 1)]
+    for k in range(2, n_pts):
+        lo = max(0, k - 400)
+        d = np.sum((pts[lo:k] - pts[k]) ** 2, axis=1)
+        near = np.argsort(d)[:4] + lo  # four ties per point: over-constrained but consistent, well conditioned
+        edges += [(int(a), k) for a in near]
+    kind = np.ones(len(edges), np.uint8)
+    idx = np.array([[2 * a, 2 * b, 0, 0] for a, b in edges], np.uint32)
+    dist = np.array([np.hypot(*(pts[a] - pts[b])) for a, b in edges])
+    noisy = pts + rng.uniform(-0.01, 0.01, size=pts.shape)
+    free_vars = np.arange(4, 2 * n_pts, dtype=np.uint32)
+    w = wl.Workload("irregular_large", kind, idx, free_vars, np.arange(len(edges)), noisy.reshape(1, -1), dist.reshape(1, -1))
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    assert topo.info["path"] == 2
+    x0 = v[0][w.free_vars]
+    x, rep = topo.lm_solve(v[0], p[0], x0)
+    assert rep["exit_reason"] in (0, 2) and rep["ssr"] < 1e-6, rep
+    v1 = v[0].copy(); v1[w.free_vars] = x
+    r, _, _ = topo.eval_large(v1, p[0], x, want_j=False)
+    assert abs(float(np.sum(r * r)) - rep["ssr"]) <= 1e-10 * max(rep["ssr"], 1e-30) + 1e-24
+    x2, rep2 = topo.lm_solve(v[0], p[0], x0)
+    assert np.array_equal(x2, x) and rep2["trace_hash"] == rep["trace_hash"]
