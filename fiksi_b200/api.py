@@ -145,6 +145,13 @@ class Topology:
         return {"eval_ms": out[0], "assemble_ms": out[1], "factor_ms": out[2], "tri_ms": out[3],
                 "evals": int(out[4]), "factors": int(out[5]), "fwd_ms": out[6], "bwd_ms": out[7]}
 
+    def sketch_kernel_info(self):
+        """fk_topology_sketch_kernel_info: does the topology have a sketch-per-thread LM kernel, its shared-memory
+        doubles per sketch and the 16-bit words of its parameter block."""
+        ok, ent, words = C.c_int(0), C.c_uint32(0), C.c_uint32(0)
+        check(lib().fk_topology_sketch_kernel_info(self._h, C.byref(ok), C.byref(ent), C.byref(words)))
+        return {"available": bool(ok.value), "state_doubles": ent.value, "table_words": words.value}
+
     def plan(self, capacity, device=0):
         return BatchPlan(self, capacity, device)
 
@@ -219,6 +226,23 @@ def fp64_peak_tflops(device=0) -> float:
     out = C.c_double(0.0)
     check(lib().fk_fp64_peak_tflops(device, C.byref(out)))
     return out.value
+
+
+class lm_kernel:
+    """Context manager around fk_set_lm_kernel: 'auto' | 'tile' | 'sketch' (tests and A/B measurements)."""
+    _CODES = {"auto": -1, "tile": 0, "sketch": 1}
+
+    def __init__(self, choice):
+        self.code = self._CODES[choice]
+
+    def __enter__(self):
+        self.prev = lib().fk_get_lm_kernel()
+        lib().fk_set_lm_kernel(self.code)
+        return self
+
+    def __exit__(self, *exc):
+        lib().fk_set_lm_kernel(self.prev)
+        return False
 
 
 def device_count() -> int:

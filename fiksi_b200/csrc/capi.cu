@@ -14,6 +14,7 @@
 
 #include "../../include/fiksi_b200.h"
 #include "lm_kernels.cuh"
+#include "lm_sketch.cuh"
 #include "multifrontal.cuh"
 #include "single_pass.hpp"
 #include "sparse_path.cuh"
@@ -52,6 +53,7 @@ struct DeviceProgram {
     void* buf = nullptr;
     fk::DevProgram view{};
     const uint32_t *jcolptr = nullptr, *jrow = nullptr;  // CSC of the Jacobian (L-BFGS)
+    std::unique_ptr<fk::SkProgram> sketch;               // parameter block of the sketch-per-thread LM kernel
     ~DeviceProgram() {
         if (buf) {
             cudaSetDevice(device);
@@ -90,6 +92,7 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
            o_gf = add(tb.g_flags), o_go = add(tb.g_ops), o_gd = add(tb.g_dst),
            o_fs = add(tb.f_steps), o_fo = add(tb.f_ops), o_ss = add(tb.s_steps), o_so = add(tb.s_ops),
            o_bs = add(tb.b_steps), o_bo = add(tb.b_ops);
+    const size_t o_sk = (t.sk.ok && fk::sk_fits(t.sk.entries, t.sk.tab.size())) ? add(t.sk.tab) : SIZE_MAX;
     std::vector<unsigned char> host(off + 16, 0);
     for (const Item& it : items)
         if (it.bytes) std::memcpy(host.data() + it.at, it.src, it.bytes);
@@ -110,6 +113,20 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
     v.s_steps = (const uint2*)(b + o_ss); v.s_ops = (const uint32_t*)(b + o_so);
     v.b_steps = (const uint2*)(b + o_bs); v.b_ops = (const uint32_t*)(b + o_bo);
     out.jcolptr = (const uint32_t*)(b + o_jcp); out.jrow = (const uint32_t*)(b + o_jrow);
+    v.sketch_prog = nullptr;
+    if (o_sk != SIZE_MAX) {
+        const fk::Topology::SketchTables& k = t.sk;
+        out.sketch.reset(new fk::SkProgram());
+        fk::SkProgram& p = *out.sketch;
+        std::memset(&p, 0, sizeof(p));
+        p.n_vars = t.n_vars; p.n_expr = t.n_expr; p.n = t.n_free; p.m = t.n_rows; p.lnnz = (uint32_t)t.l_rowidx.size(); p.entries = k.entries;
+        p.xa = k.xa; p.xb = k.xb; p.w = k.w; p.f = k.f; p.fx = k.fx; p.pr = k.pr; p.nfix = k.nfix; p.npar = k.npar;
+        p.off_free = k.off_free; p.off_fix = k.off_fix; p.off_par = k.off_par;
+        p.off_eval = k.off_eval; p.off_factor = k.off_factor; p.off_back = k.off_back;
+        p.tab_words = (uint32_t)k.tab.size();
+        p.tab = (const uint32_t*)(b + o_sk);
+        v.sketch_prog = out.sketch.get();
+    }
     return FK_OK;
 }
 
@@ -624,6 +641,17 @@ int fk_fp64_peak_tflops(int device, double* out) {
     int e = fk::measure_fp64_peak(&v);
     if (e != 0) return cuda_fail((cudaError_t)e, "fp64 peak microbenchmark");
     *out = v;
+    return FK_OK;
+}
+
+void fk_set_lm_kernel(int choice) { fk::lm_kernel_choice().store(choice < 0 ? -1 : (choice ? 1 : 0)); }
+int fk_get_lm_kernel(void) { return fk::lm_kernel_choice().load(); }
+int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint32_t* state_doubles, uint32_t* table_words) {
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    const fk::Topology::SketchTables& k = topo->t.sk;
+    if (available) *available = (k.ok && fk::sk_fits(k.entries, k.tab.size())) ? 1 : 0;
+    if (state_doubles) *state_doubles = k.entries;
+    if (table_words) *table_words = (uint32_t)k.tab.size();
     return FK_OK;
 }
 

@@ -9,12 +9,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
 #include "expressions.cuh"
 #include "lm_kernels.cuh"
+#include "lm_sketch.cuh"
 
 namespace fk {
 
@@ -1001,9 +1003,33 @@ static int launch_lm_k(const DevProgram& prog, uint32_t n_sketches, const double
     return launch_lm_t<TILE, -1>(prog, n_sketches, vars, params, free_out, reports, s);
 }
 
+std::atomic<int>& lm_kernel_choice() {
+    static std::atomic<int> choice{[] {
+        const char* e = std::getenv("FK_LM_KERNEL");
+        if (!e) return -1;
+        return e[0] == 's' ? 1 : (e[0] == 't' ? 0 : -1);
+    }()};
+    return choice;
+}
+
+// The sketch-per-thread kernel runs one warp per 32 sketches: it needs a batch that fills the machine.  Below
+// that the tile kernel (4-32 lanes per sketch) has more parallelism to offer.  FK_LM_KERNEL=tile|sketch forces one.
+int batch_lm_uses_sketch_kernel(const DevProgram& prog, uint32_t n_sketches) {
+    if (!prog.sketch_prog) return 0;
+    const int forced = lm_kernel_choice().load(std::memory_order_relaxed);
+    if (forced >= 0) return forced;
+    static const uint32_t min_batch = [] {
+        const char* e = std::getenv("FK_LM_SKETCH_MIN");
+        return (uint32_t)(e ? std::max(1, std::atoi(e)) : 4096);
+    }();
+    return n_sketches >= min_batch ? 1 : 0;
+}
+
 int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                     double* free_out, fk_report* reports, void* stream) {
     if (n_sketches == 0) return 0;
+    if (batch_lm_uses_sketch_kernel(prog, n_sketches))
+        return launch_batch_lm_sketch(*prog.sketch_prog, n_sketches, vars, params, free_out, reports, stream);
     cudaStream_t s = (cudaStream_t)stream;
     switch (prog.tile) {
         case 1: return launch_lm_k<1>(prog, n_sketches, vars, params, free_out, reports, s);

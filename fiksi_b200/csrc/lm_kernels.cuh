@@ -2,6 +2,7 @@
 // sub-warp, a warp, or a whole CTA) owns one sketch / connected component and runs the complete
 // LM loop of fiksi/src/solve/lm.rs:21-193 on it out of shared memory.
 #pragma once
+#include <atomic>
 #include <cstdint>
 
 #include "../../include/fiksi_b200.h"
@@ -29,6 +30,9 @@ struct DevProgram {
     const uint32_t* s_ops;
     const uint2* b_steps;       // [b_nsteps+1]
     const uint32_t* b_ops;
+    // HOST pointer: parameter block of the sketch-per-thread kernel (lm_sketch.cuh), null when the topology
+    // stays on the tile kernel.  launch_batch_lm picks between the two.
+    const struct SkProgram* sketch_prog;
 };
 
 // Shared-memory doubles one sketch needs: x, xs, g (3n) + w / trial residuals (max(n, m)) + J
@@ -44,6 +48,10 @@ __host__ __device__ inline uint32_t lbfgs_smem_doubles(uint32_t n, uint32_t m, u
 // Launchers (defined in lm_kernels.cu).  `stream` is a cudaStream_t.
 int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                     double* free_out, fk_report* reports, void* stream);
+// Which kernel launch_batch_lm takes for a batch of this size: 1 sketch-per-thread, 0 tile kernel.
+int batch_lm_uses_sketch_kernel(const DevProgram& prog, uint32_t n_sketches);
+// -1 automatic (by batch size), 0 tile kernel, 1 sketch-per-thread kernel where the topology has one.
+std::atomic<int>& lm_kernel_choice();
 int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double* vars,
                       const double* params, double* out_r, double* out_j, int mode, void* stream);
 // System::analyze on a batch: kinds[n_expr], slot_var[n_expr][8] device tables; out[n][n_expr].

@@ -1,0 +1,446 @@
+// See lm_sketch.cuh.  Compiled with -fmad=false: a*b+c is two roundings unless it is an explicit fma().
+#include "lm_sketch.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "expressions.cuh"
+
+namespace fk {
+
+namespace {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// 1/d for a positive finite pivot (the tile kernel's sequence: hardware seed + two Newton steps).
+__device__ __forceinline__ double sk_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Entry e of a lane's region lives at byte (e << 8) behind the lane's region pointer (32 lanes x 8 bytes per entry).
+__device__ __forceinline__ double ldp(const char* p, uint32_t off) { return *reinterpret_cast<const double*>(p + off); }
+__device__ __forceinline__ void stp(char* p, uint32_t off, double v) { *reinterpret_cast<double*>(p + off) = v; }
+
+__host__ __device__ constexpr int sk_arity(int kind) {
+    return kind == 0 ? 2 : kind == 1 ? 4 : kind <= 4 ? 6 : kind == 5 ? 5 : kind <= 9 ? 8 : 7;
+}
+__host__ __device__ constexpr bool sk_has_param(int kind) { return kind == 1 || kind == 2 || kind == 4 || kind == 7; }
+
+// N table words starting at the 16-byte aligned shared-memory address p (every lane reads the same address: one
+// broadcast wavefront per 4 words).  wd has room for the padding words of the last load.
+template <int N>
+__device__ __forceinline__ void ld_words(const uint32_t* p, uint32_t (&wd)[(N + 3) / 4 * 4]) {
+#pragma unroll
+    for (int i = 0; i < (N + 3) / 4; i++) {
+        const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+        wd[4 * i] = q.x; wd[4 * i + 1] = q.y; wd[4 * i + 2] = q.z; wd[4 * i + 3] = q.w;
+    }
+}
+
+// One expression row of fiksi/src/subsystem.rs:143-165 for this thread's sketch, fused with its contributions
+// to g = J^T(-r) and H = J^T J (rows arrive in ascending order and every sum starts from zero, so the sums
+// keep the tile kernel's order).  All targets of a row are distinct (rows naming a free variable twice stay on
+// the tile kernel), so they are fetched before the first FMA and stored afterwards: the accesses overlap
+// instead of forming a load-FMA-store chain.  SPECIAL: some slot of the row is a fixed variable.
+// rec: the row's record; h0: its first four words (already loaded).
+template <int KIND, bool SPECIAL>
+__device__ __forceinline__ void sk_eval_row(const uint32_t* rec, const uint4 h0, const char* x, const char* fx, const char* pr, char* w, char* f,
+                                            double& ssr) {
+    constexpr int A = sk_arity(KIND);
+    constexpr int NP = A * (A + 1) / 2;
+    constexpr int NW = 2 + 2 * A + NP;
+    uint32_t t[(NW + 3) / 4 * 4];
+    t[0] = h0.x; t[1] = h0.y; t[2] = h0.z; t[3] = h0.w;
+#pragma unroll
+    for (int i = 1; i < (NW + 3) / 4; i++) {
+        const uint4 q = reinterpret_cast<const uint4*>(rec)[i];
+        t[4 * i] = q.x; t[4 * i + 1] = q.y; t[4 * i + 2] = q.z; t[4 * i + 3] = q.w;
+    }
+    double v[8], g[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) v[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const uint32_t src = t[2 + s];
+        if (SPECIAL) v[s] = (src >> 31) ? ldp(fx, src & 0x7FFFFFFFu) : ldp(x, src);
+        else v[s] = ldp(x, src);
+    }
+    const double param = sk_has_param(KIND) ? ldp(pr, t[1]) : 0.0;
+    double* gp[A];
+    double* hp[NP];
+    double gv[A], hv[NP];
+    // the targets do not depend on the row's arithmetic: fetch them before it
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const uint32_t o = t[2 + A + s];
+        gp[s] = reinterpret_cast<double*>(w + o);
+        gv[s] = (!SPECIAL || o != kNone) ? *gp[s] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const uint32_t o = t[2 + 2 * A + q];
+        hp[q] = reinterpret_cast<double*>(f + o);
+        hv[q] = (!SPECIAL || o != kNone) ? *hp[q] : 0.0;
+    }
+    const double r = dev::eval_expression(KIND, v, param, g);
+    ssr = ssr + r * r;  // lm.rs:195-197: sequential, not fused
+    const double nr = -r;
+#pragma unroll
+    for (int s = 0; s < A; s++)
+        if (!SPECIAL || t[2 + A + s] != kNone) *gp[s] = fma(g[s], nr, gv[s]);
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < A; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++, q++)
+            if (!SPECIAL || t[2 + 2 * A + q] != kNone) *hp[q] = fma(g[a], g[b], hv[q]);
+}
+
+// Right-looking step of column k with C entries below the diagonal: the column is read once into registers,
+// every target (C(C+1)/2 entries of later columns, C entries of the right-hand side: the forward substitution
+// rides along) is fetched, updated with one FMA and stored.  Same operations as the tile kernel's
+// L[dst] = fma(-(L[a] * inv), L[b], L[dst]).  body: C positions in f, C positions in w, C(C+1)/2 targets in f.
+template <int C>
+__device__ __forceinline__ void sk_column(const uint32_t* body, char* f, char* w, double wk, double inv) {
+    constexpr int NP = C * (C + 1) / 2;
+    uint32_t t[(2 * C + NP + 3) / 4 * 4];
+    ld_words<2 * C + NP>(body, t);
+    double l[C], s[C], wv[C], d[NP];
+    double* wp[C];
+    double* dp[NP];
+#pragma unroll
+    for (int a = 0; a < C; a++) l[a] = ldp(f, t[a]);
+#pragma unroll
+    for (int a = 0; a < C; a++) {
+        wp[a] = reinterpret_cast<double*>(w + t[C + a]);
+        wv[a] = *wp[a];
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        dp[q] = reinterpret_cast<double*>(f + t[2 * C + q]);
+        d[q] = *dp[q];
+    }
+#pragma unroll
+    for (int a = 0; a < C; a++) s[a] = -(l[a] * inv);
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < C; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++, q++) *dp[q] = fma(s[a], l[b], d[q]);
+#pragma unroll
+    for (int a = 0; a < C; a++) *wp[a] = fma(s[a], wk, wv[a]);
+}
+
+// Columns with more than 8 entries below the diagonal: same operations, one at a time.
+__device__ __forceinline__ void sk_column_generic(const uint32_t* t, uint32_t C, char* f, char* w, double wk, double inv) {
+    uint32_t q = 0;
+    for (uint32_t a = 0; a < C; a++) {
+        const double la = ldp(f, t[a]);
+        const double sa = -(la * inv);
+        for (uint32_t b = 0; b <= a; b++, q++) {
+            double* dst = reinterpret_cast<double*>(f + t[2 * C + q]);
+            const double lb = b == a ? la : ldp(f, t[b]);
+            *dst = fma(sa, lb, *dst);
+        }
+        double* wr = reinterpret_cast<double*>(w + t[C + a]);
+        *wr = fma(sa, wk, *wr);
+    }
+}
+
+// acc - sum_{a} (L D)(row_a, k) z(row_a), rows descending as the tile kernel's scatter form applies them.
+template <int C>
+__device__ __forceinline__ double sk_back_column(const uint32_t* body, const char* f, const char* w, double acc) {
+    uint32_t t[(2 * C + 3) / 4 * 4];
+    ld_words<2 * C>(body, t);
+    double l[C], z[C];
+#pragma unroll
+    for (int a = 0; a < C; a++) {
+        l[a] = ldp(f, t[a]);
+        z[a] = ldp(w, t[C + a]);
+    }
+#pragma unroll
+    for (int a = C - 1; a >= 0; a--) acc = fma(-l[a], z[a], acc);
+    return acc;
+}
+
+__device__ __forceinline__ uint64_t sk_trace_push(uint64_t h, uint32_t code) { return h * 3ull + code + 1ull; }
+
+constexpr int kSkMaxWarps = 4;
+
+__global__ void __launch_bounds__(32 * kSkMaxWarps)
+fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
+                          const double* __restrict__ params_all, double* __restrict__ free_out, fk_report* __restrict__ reports) {
+    extern __shared__ __align__(16) char sk_smem[];
+    // the tables, once per CTA
+    uint32_t* const tab = reinterpret_cast<uint32_t*>(sk_smem);
+    for (uint32_t i = threadIdx.x; i < P.tab_words / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(tab)[i] = __ldg(reinterpret_cast<const uint4*>(P.tab) + i);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t sketch = (blockIdx.x * (blockDim.x >> 5) + warp) * 32u + lane;
+    if (sketch - lane >= n_sketches) return;  // a whole warp without work
+    const bool valid = sketch < n_sketches;
+    const uint32_t sk = valid ? sketch : n_sketches - 1;  // idle lanes shadow the last sketch and store nothing
+    char* const base = sk_smem + (size_t)P.tab_words * 4 + (size_t)warp * P.entries * 256u + lane * 8u;
+    const uint32_t n = P.n;
+    const double* vars = vars_all + (size_t)sk * P.n_vars;
+    const double* params = params_all + (size_t)sk * P.n_expr;
+
+    // accepted / trial point: the two roles swap per lane on accept (a register exchange instead of a copy)
+    char* xp = base + (P.xa << 8);
+    char* xsp = base + (P.xb << 8);
+    char* const w = base + (P.w << 8);
+    char* const f = base + (P.f << 8);
+    const char* const fx = base + (P.fx << 8);
+    const char* const pr = base + (P.pr << 8);
+
+    for (uint32_t i = 0; i < n; i++) stp(xp, i << 8, __ldg(vars + tab[P.off_free + i]));
+    for (uint32_t i = 0; i < P.nfix; i++) stp(base, (P.fx + i) << 8, __ldg(vars + tab[P.off_fix + i]));
+    for (uint32_t i = 0; i < P.npar; i++) stp(base, (P.pr + i) << 8, __ldg(params + tab[P.off_par + i]));
+
+    double ssr = 0.0, lambda = 0.5, dn = 0.0;  // lm.rs:108
+    uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
+    uint64_t trace = 0;
+    bool active = valid;
+    int fstat = 0;
+    // What the evaluation at the top of the loop is for (warp-uniform): the starting point (lm.rs:80-106), a
+    // trial point (lm.rs:148-149 and, for an accepted one, lm.rs:173-185), or the accepted point again after a
+    // rejected / unsolved step of some sketch of the warp (its H and g were consumed by the factorisation;
+    // sketches that accepted recompute the values they already hold).
+    enum { kInit, kTrial, kRestore } mode = kInit;
+    const char* xe = xp;
+
+    for (;;) {
+        // ---- residuals, g = -J^T r (into w), H = J^T J (into f) at xe; s = sum of squared residuals ----------
+        double s = 0.0;
+        {
+            uint32_t i = 0;
+            for (; i + 8 <= n; i += 8)
+#pragma unroll
+                for (int u = 0; u < 8; u++) stp(w, (i + u) << 8, 0.0);
+            for (; i < n; i++) stp(w, i << 8, 0.0);
+            for (i = 0; i + 8 <= P.lnnz; i += 8)
+#pragma unroll
+                for (int u = 0; u < 8; u++) stp(f, (i + u) << 8, 0.0);
+            for (; i < P.lnnz; i++) stp(f, i << 8, 0.0);
+            const uint32_t* rec = tab + P.off_eval;
+            uint4 hn = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t r = 0; r < P.m; r++) {
+                const uint32_t* cur = rec;
+                const uint4 h = hn;
+                rec += h.x >> 16;
+                hn = *reinterpret_cast<const uint4*>(rec);  // next row's header (a padding record follows the last row)
+#define FK_SK_ROW(K)                                                          \
+    case K: sk_eval_row<K, false>(cur, h, xe, fx, pr, w, f, s); break;        \
+    case 0x100 | K: sk_eval_row<K, true>(cur, h, xe, fx, pr, w, f, s); break;
+                switch (h.x & 0x1FFu) {
+                    FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
+                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
+                    default: break;
+                }
+#undef FK_SK_ROW
+            }
+        }
+        bool restore = false;
+        if (mode == kInit) {
+            ssr = s;
+            if (ssr < 1e-8) {  // lm.rs:110-112 on the first outer iteration
+                exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+                active = false;
+            } else {
+                outer_iters = 1;
+            }
+        } else if (mode == kTrial && active) {
+            factorizations++;
+            if (fstat == 1) {  // lm.rs:134-137 (`!solved`)
+                lambda *= 8.0;
+                trace = sk_trace_push(trace, 0);
+                restore = true;
+            } else if (fstat == 0 && dn < 1e-12) {  // lm.rs:139-142
+                exit_reason = FK_EXIT_SMALL_STEP;
+                active = false;
+            } else {
+                const double ssr_s = fstat == 0 ? s : NAN;
+                if (ssr_s < ssr) {  // lm.rs:151 (strict; NaN rejects)
+                    lambda *= 0.125;
+                    if (lambda < 1e-50) lambda = 1e-50;
+                    accepted++;
+                    trace = sk_trace_push(trace, 1);
+                    char* tmp = xp; xp = xsp; xsp = tmp;
+                    const bool stalled = (ssr - ssr_s) / ssr <= 1e-6;  // lm.rs:164-168
+                    ssr = ssr_s;
+                    if (stalled) {
+                        exit_reason = FK_EXIT_STALLED;
+                        active = false;
+                    } else if (outer_iters == 100) {
+                        active = false;  // FK_EXIT_MAX_OUTER: the 100th outer iteration has ended
+                    } else if (ssr < 1e-8) {  // lm.rs:109-112
+                        exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+                        active = false;
+                    } else {
+                        outer_iters++;
+                    }
+                } else {  // lm.rs:187-190
+                    lambda *= 2.0;
+                    trace = sk_trace_push(trace, 2);
+                    restore = true;
+                }
+            }
+        }
+        if (mode != kRestore && __any_sync(0xFFFFFFFFu, restore && active)) {
+            mode = kRestore;
+            xe = xp;
+            continue;
+        }
+        if (active && !isfinite(lambda)) {
+            exit_reason = FK_EXIT_LAMBDA_OVERFLOW;
+            active = false;
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+
+        // ---- one iteration of the damping loop (lm.rs:115-146) for every sketch of the warp ----------------------
+        const double sl = sqrt(lambda);  // lm.rs:119-125
+        const double lam2 = sl * sl;
+        {   // LDLt of (H + lam2 I) in place (column k keeps (L D)(i,k), and 1 / D(k) on its diagonal slot) and the
+            // forward substitution of g in w.  fstat: kind of the FIRST bad pivot in column order (tile kernel's rule).
+            fstat = 0;
+            const uint32_t* rec = tab + P.off_factor;
+            uint4 hn = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t c = 0; c < n; c++) {
+                const uint32_t C = hn.x;
+                double* dp = reinterpret_cast<double*>(f + hn.y);
+                const double wk = ldp(w, hn.z);
+                const uint32_t* body = rec + 4;
+                rec = body + ((2 * C + C * (C + 1) / 2 + 3u) & ~3u);
+                hn = *reinterpret_cast<const uint4*>(rec);  // next column's header
+                const double d = *dp + lam2;
+                if (fstat == 0 && !(d > 0.0 && d < INFINITY)) fstat = d != d ? 2 : 1;
+                const double inv = sk_rcp(d);
+                *dp = inv;
+                switch (C) {
+                    case 0: break;
+                    case 1: sk_column<1>(body, f, w, wk, inv); break;
+                    case 2: sk_column<2>(body, f, w, wk, inv); break;
+                    case 3: sk_column<3>(body, f, w, wk, inv); break;
+                    case 4: sk_column<4>(body, f, w, wk, inv); break;
+                    case 5: sk_column<5>(body, f, w, wk, inv); break;
+                    case 6: sk_column<6>(body, f, w, wk, inv); break;
+                    case 7: sk_column<7>(body, f, w, wk, inv); break;
+                    case 8: sk_column<8>(body, f, w, wk, inv); break;
+                    default: sk_column_generic(body, C, f, w, wk, inv); break;
+                }
+            }
+        }
+        {   // D L^T z = y in place in w; delta in variable order (qr.rs:354) into the trial point's slots
+            const uint32_t* rec = tab + P.off_back;
+            uint4 hn = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t c = 0; c < n; c++) {
+                const uint32_t C = hn.x;
+                const double inv = ldp(f, hn.y);
+                double* zp = reinterpret_cast<double*>(w + hn.z);
+                double* xd = reinterpret_cast<double*>(xsp + hn.w);
+                const uint32_t* body = rec + 4;
+                rec = body + ((2 * C + 3u) & ~3u);
+                hn = *reinterpret_cast<const uint4*>(rec);
+                double acc = *zp;
+                switch (C) {
+                    case 0: break;
+                    case 1: acc = sk_back_column<1>(body, f, w, acc); break;
+                    case 2: acc = sk_back_column<2>(body, f, w, acc); break;
+                    case 3: acc = sk_back_column<3>(body, f, w, acc); break;
+                    case 4: acc = sk_back_column<4>(body, f, w, acc); break;
+                    case 5: acc = sk_back_column<5>(body, f, w, acc); break;
+                    case 6: acc = sk_back_column<6>(body, f, w, acc); break;
+                    case 7: acc = sk_back_column<7>(body, f, w, acc); break;
+                    case 8: acc = sk_back_column<8>(body, f, w, acc); break;
+                    default:
+                        for (uint32_t a = C; a-- > 0;) acc = fma(-ldp(f, body[a]), ldp(w, body[C + a]), acc);
+                        break;
+                }
+                const double z = acc * inv;
+                *zp = z;
+                *xd = z;
+            }
+        }
+        {   // lm.rs:139 (sum of squared steps, in variable order) and lm.rs:144-146 (trial point)
+            dn = 0.0;
+            uint32_t i = 0;
+            for (; i + 4 <= n; i += 4) {
+                double d[4], x0[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    d[u] = ldp(xsp, (i + u) << 8);
+                    x0[u] = ldp(xp, (i + u) << 8);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    dn = dn + d[u] * d[u];
+                    stp(xsp, (i + u) << 8, x0[u] + d[u]);
+                }
+            }
+            for (; i < n; i++) {
+                const double d = ldp(xsp, i << 8);
+                dn = dn + d * d;
+                stp(xsp, i << 8, ldp(xp, i << 8) + d);
+            }
+        }
+        mode = kTrial;
+        xe = xsp;
+    }
+
+    if (!valid) return;
+    double* out = free_out + (size_t)sketch * n;
+    for (uint32_t i = 0; i < n; i++) out[i] = ldp(xp, i << 8);
+    fk_report rep;
+    rep.exit_reason = exit_reason;
+    rep.outer_iters = outer_iters;
+    rep.factorizations = factorizations;
+    rep.accepted = accepted;
+    rep.ssr = ssr;
+    rep.lambda = lambda;
+    rep.trace_hash = trace;
+    reports[sketch] = rep;
+}
+
+}  // namespace
+
+int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const double* vars, const double* params, double* free_out,
+                           fk_report* reports, void* stream) {
+    if (n_sketches == 0) return 0;
+    if (!sk_fits(prog.entries, prog.tab_words)) return (int)cudaErrorInvalidConfiguration;
+    // Warps per CTA (they share one copy of the tables): the choice that puts the most warps on an SM; 238 registers
+    // per thread allow 8.  228 KB of shared memory per SM, 1 KB of it reserved per resident CTA.
+    const size_t tab_bytes = (size_t)prog.tab_words * 4, state = (size_t)prog.entries * 256;
+    int best_w = 1, best_warps = 0;
+    for (int wpc = 1; wpc <= kSkMaxWarps; wpc++) {
+        const size_t per_cta = tab_bytes + wpc * state;
+        if (per_cta > 227 * 1024) break;
+        const int ctas = (int)std::min<size_t>(32, (228 * 1024) / (per_cta + 1024));
+        const int warps = std::min(8, ctas * wpc);
+        if (warps > best_warps || (warps == best_warps && wpc <= 2)) { best_warps = warps; best_w = wpc; }
+    }
+    if (const char* e = std::getenv("FK_SK_WARPS")) {  // tuning knob
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= kSkMaxWarps && tab_bytes + v * state <= 227 * 1024) best_w = v;
+    }
+    const size_t smem = tab_bytes + best_w * state;
+    cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fk_batch_lm_sketch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    const uint32_t per_cta = 32u * (uint32_t)best_w;
+    const uint32_t grid = (n_sketches + per_cta - 1) / per_cta;
+    fk_batch_lm_sketch_kernel<<<grid, per_cta, smem, (cudaStream_t)stream>>>(prog, n_sketches, vars, params, free_out, reports);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace fk

@@ -1,0 +1,46 @@
+// K4, second generation: the batched Levenberg-Marquardt solve with ONE THREAD PER SKETCH.
+//
+// The tile kernel (lm_kernels.cu) gives a sketch 4-32 lanes and a private shared-memory block; ncu showed
+// it bound by the SM's load/store pipe and by instruction issue (70 instructions per factor step of at most
+// 16 useful FMAs: per-lane table loads, unpacking, masked warp barriers, scattered accesses with bank
+// conflicts).  Here the 32 sketches of a warp are interleaved in shared memory (`entry * 32 + lane`):
+//   * every access of a warp is 32 consecutive doubles - two conflict-free wavefronts, the minimum;
+//   * the op tables are warp-uniform: one copy per CTA in shared memory, read with 16-byte broadcast loads
+//     (four table words per instruction, one wavefront) and prefetched one record ahead;
+//   * a pivot column's entries are loaded once into registers and reused by all of the column's updates
+//     (1 load + 1 store per FMA instead of 3 + 1), and the targets of a column are fetched before the first
+//     FMA, so one thread keeps up to 44 independent shared-memory accesses in flight;
+//   * the Jacobian is never stored: a row's gradient stays in registers and goes straight into g = -J^T r and
+//     H = J^T J; H is factorised in place and an accepted trial point leaves its own H and g behind, so the
+//     state of a sketch is 3 n + nnz(L) doubles (a rejected step re-evaluates the accepted point instead of
+//     keeping a copy of H);
+//   * there is no barrier anywhere: a sketch never leaves its thread.
+// Replaces fiksi/src/solve/lm.rs:21-193 + solvi qr.rs:281-356 exactly as the tile kernel does (same normal
+// equations, same LDLt operations in the same order, same LM control flow).
+#pragma once
+#include <cstdint>
+
+#include "../../include/fiksi_b200.h"
+
+namespace fk {
+
+// Launch descriptor (host struct, passed by value).  Field meanings: Topology::SketchTables (symbolic.hpp).
+struct SkProgram {
+    uint32_t n_vars, n_expr, n, m, lnnz, entries;
+    uint32_t xa, xb, w, f, fx, pr, nfix, npar;
+    uint32_t off_free, off_fix, off_par, off_eval, off_factor, off_back;
+    uint32_t tab_words;
+    const uint32_t* tab;  // DEVICE memory, 16-byte aligned; copied into shared memory by every CTA
+};
+
+// Limits: one warp (32 sketches x `entries` doubles) plus the tables must fit an SM's shared memory.
+constexpr uint32_t kSkMaxEntries = 840;
+constexpr uint32_t kSkMaxTabWords = 16384;
+inline bool sk_fits(uint32_t entries, size_t tab_words) {
+    return entries <= kSkMaxEntries && tab_words <= kSkMaxTabWords && (size_t)entries * 256 + tab_words * 4 <= 224 * 1024;
+}
+
+int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
+                           double* free_out, fk_report* reports, void* stream);
+
+}  // namespace fk

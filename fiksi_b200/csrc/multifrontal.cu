@@ -174,10 +174,54 @@ __device__ __forceinline__ double ld_relaxed(const double* p) {
     asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ bool is_unpublished(double v) { return __double_as_longlong(v) == -1ll; }
+// Publishing store.  FP64 arithmetic passes NaN payloads through, so an all-ones NaN in the caller's
+// variables or parameters could otherwise arrive here and look "absent" for ever: any value with the
+// sentinel's bit pattern is replaced by the canonical quiet NaN before it is stored.
 __device__ __forceinline__ void st_relaxed(double* p, double v) {
+    if (is_unpublished(v)) v = __longlong_as_double(0x7ff8000000000000ll);
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v));
 }
-__device__ __forceinline__ bool is_unpublished(double v) { return __double_as_longlong(v) == -1ll; }
+
+// Every polling loop is bounded: after kSpinBatch unsuccessful polls a thread looks at the status word
+// and at the wall clock; once a waiter has spun for kSpinLimitNs (or another waiter has already given
+// up: status >= kStatusStalled) it raises the status to kStatusStalled and leaves the loop with whatever
+// it read.  The kernel then runs to completion on NaN-poisoned data (its own publications still happen,
+// so nobody waits for it), and the host turns the status into an error instead of a hung device.
+constexpr int kStatusStalled = 3;
+constexpr uint32_t kSpinBatch = 1024;
+constexpr long long kSpinLimitNs = 4000000000ll;
+struct SpinGuard {
+    int* status;
+    uint32_t polls = 0;
+    long long t0 = 0;
+    __device__ __forceinline__ explicit SpinGuard(int* st) : status(st) {}
+    // call after an unsuccessful poll; true: give up
+    __device__ __forceinline__ bool expired() {
+        if (++polls < kSpinBatch) return false;
+        polls = 0;
+        long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        const int stv = *reinterpret_cast<volatile int*>(status);
+        if (stv >= kStatusStalled || now - t0 > kSpinLimitNs) {
+            atomicMax(status, kStatusStalled);
+            return true;
+        }
+        return false;
+    }
+};
+
+// Work items of the polling kernels are handed out by an atomic ticket instead of blockIdx: CUDA does not
+// promise that CTAs start in index order, but a CTA that holds ticket k knows that the CTAs holding every
+// ticket < k have started, and the task lists are ordered so that a task only waits for tasks before it.
+// Hence no residency condition and no dependence on dispatch order.
+__device__ __forceinline__ uint32_t take_ticket(uint32_t* counter) {
+    __shared__ uint32_t s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+    __syncthreads();
+    return s_ticket;
+}
 
 #ifdef FK_CHAIN_PROFILE
 __device__ __forceinline__ long long global_ns() {
@@ -195,7 +239,8 @@ __device__ __forceinline__ uint32_t tile_row(uint32_t tx, int i) { return tx + 1
 
 template <bool POLL = false>
 __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __restrict__ P, uint32_t f, uint32_t rowA0,
-                                           uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, uint32_t diag0, TileBuf& buf) {
+                                           uint32_t nrA, uint32_t rowB0, uint32_t nrB, uint32_t K, uint32_t diag0, TileBuf& buf,
+                                           int* status = nullptr) {
     const uint32_t tid = threadIdx.x;
     const uint32_t lk = tid >> 4, lr = (tid & 15) * 4;   // staging: column lk of the chunk, rows lr..lr+3
     const uint32_t tx = tid & 15, c4 = (tid >> 4) * 4;   // compute mapping
@@ -231,11 +276,12 @@ __device__ __forceinline__ void tile_kloop(double (&acc)[4][4], const double* __
         const uint32_t k = ch * KC + lk;
         if (k >= K) return;
         const double* col = P + (size_t)k * f;
+        SpinGuard guard(status);
         for (;;) {
             bool missing = is_unpublished(rdk);
 #pragma unroll
             for (int u = 0; u < 4; u++) missing = missing || (lr + u < nrA && is_unpublished(ra[u])) || (lr + u < nrB && is_unpublished(rb[u]));
-            if (!missing) break;
+            if (!missing || guard.expired()) break;
             rdk = ld_relaxed(col + diag0 + k);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -551,10 +597,11 @@ static_assert(kFlowSmem >= sizeof(TileBuf), "the staging buffers alias the solve
 
 __global__ void __launch_bounds__(kTileThreads)
 mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pub, const uint32_t* __restrict__ asm_ptr,
-               const uint4* __restrict__ asm_ent) {
+               const uint4* __restrict__ asm_ent, uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(16) double smf[];
     TileBuf& buf = *reinterpret_cast<TileBuf*>(smf);
-    const uint4 t = __ldg(tasks + blockIdx.x);
+    const uint32_t bid = take_ticket(ticket);
+    const uint4 t = __ldg(tasks + bid);
     const uint32_t s = t.x, row0 = t.y, tcol0 = t.z;
     const uint32_t nrA = (t.w & 0xFFu) + 1, nrB = ((t.w >> 8) & 0xFFu) + 1;
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
@@ -582,7 +629,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
         // precomputed on the host; children in ascending order, distinct targets within a child), and the sum is
         // the tile's starting value.  Update-matrix tiles start from zero, so U_s needs no separate clearing.
         double* S = smf;  // [TB][kTsLd]
-        const uint32_t e0 = __ldg(asm_ptr + blockIdx.x), e1 = __ldg(asm_ptr + blockIdx.x + 1);
+        const uint32_t e0 = __ldg(asm_ptr + bid), e1 = __ldg(asm_ptr + bid + 1);
         for (uint32_t e = tid; e < TB * TB; e += kTileThreads) {
             const uint32_t ri = e & 63, cj = e >> 6;
             const bool ok = in_panel && ri < nrA && cj < nrB && (!diag_tile || ri >= cj);
@@ -608,10 +655,10 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
         __syncthreads();  // S aliases the staging buffers of the update loop
     }
     for (uint32_t b = 0; b + 1 < nwait; b++)
-        tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf);
+        tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf, D.status);
     FK_FSTAMP(1);
     for (uint32_t b = nwait ? nwait - 1 : 0; b < nwait; b++)
-        tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf);
+        tile_kloop<true>(acc, Pp + (size_t)(TB * b) * f, f, row0, nrA, tcol0, nrB, min((uint32_t)TB, ns - TB * b), TB * b, buf, D.status);
     if (!in_panel) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -659,6 +706,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
         for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
             double v[2];
             bool missing;
+            SpinGuard guard(D.status);
             do {
                 missing = false;
 #pragma unroll
@@ -667,7 +715,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
                     v[u] = (ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
                     missing = missing || is_unpublished(v[u]);
                 }
-            } while (missing);
+            } while (missing && !guard.expired());
             __syncthreads();  // (the zero fill / the previous step's readers are done)
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -995,15 +1043,16 @@ __device__ __forceinline__ void backward_supernode(const MfDev& D, uint32_t s, d
 #define FK_CSTAMP(k) do { } while (0)
 #endif
 // the 16 values q, q+4, ... of a published 64-vector (entries >= count read as zero)
-__device__ __forceinline__ void poll16(const double* base, uint32_t q, uint32_t count, double (&v)[16]) {
+__device__ __forceinline__ void poll16(const double* base, uint32_t q, uint32_t count, double (&v)[16], int* status) {
     bool missing;
+    SpinGuard guard(status);
     do {
         missing = false;
 #pragma unroll
         for (int u = 0; u < 16; u++) v[u] = q + 4u * u < count ? ld_relaxed(base + q + 4 * u) : 0.0;
 #pragma unroll
         for (int u = 0; u < 16; u++) missing = missing || is_unpublished(v[u]);
-    } while (missing);
+    } while (missing && !guard.expired());
 }
 __device__ __forceinline__ double quad_sum(const double (&a4)[4]) {
     double v = (a4[0] + a4[1]) + (a4[2] + a4[3]);
@@ -1046,9 +1095,10 @@ mf_chain_inv_kernel(MfDev D, const uint4* __restrict__ tasks) {
 }
 
 __global__ void __launch_bounds__(256)
-mf_chain_fwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ w, double* __restrict__ pub) {
+mf_chain_fwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ w, double* __restrict__ pub,
+                    uint32_t* __restrict__ ticket) {
     __shared__ double t[TB];
-    const uint4 tk = __ldg(tasks + blockIdx.x);
+    const uint4 tk = __ldg(tasks + take_ticket(ticket));
     const uint32_t s = tk.x, row0 = tk.y, nr = tk.z;
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s), blk0 = __ldg(D.winv_blk + s);
     const double* P = D.pan + __ldg(D.pan_off + s);
@@ -1095,7 +1145,7 @@ mf_chain_fwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict
         if (b + 1 < nwait) prefetch(b + 1);
         if (b + 1 == nwait) FK_CSTAMP(1);
         double yv[16];
-        poll16(pub + c0 + TB * b, q, min((uint32_t)TB, ns - TB * b), yv);
+        poll16(pub + c0 + TB * b, q, min((uint32_t)TB, ns - TB * b), yv, D.status);
         if (b + 1 == nwait) FK_CSTAMP(2);
         double a4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -1126,9 +1176,10 @@ mf_chain_fwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict
 // column j with the ancestors' solution (mf_bwd_dot_kernel) when the front has rows below the pivot block.
 __global__ void __launch_bounds__(256)
 mf_chain_bwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ w, double* __restrict__ delta,
-                    const int32_t* __restrict__ perm, const double* __restrict__ tmp, double* __restrict__ pub) {
+                    const int32_t* __restrict__ perm, const double* __restrict__ tmp, double* __restrict__ pub,
+                    uint32_t* __restrict__ ticket) {
     __shared__ double t[TB];
-    const uint4 tk = __ldg(tasks + blockIdx.x);
+    const uint4 tk = __ldg(tasks + take_ticket(ticket));
     const uint32_t s = tk.x, col0 = tk.y, nc = tk.z;
     const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), c0 = __ldg(D.c0 + s), blk0 = __ldg(D.winv_blk + s);
     const double* P = D.pan + __ldg(D.pan_off + s);
@@ -1158,7 +1209,7 @@ mf_chain_bwd_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict
         for (int u = 0; u < 16; u++) cl[u] = nl[u];
         if (b - 1 > c) prefetch(b - 1);
         double zv[16];
-        poll16(pub + c0 + TB * b, q, min((uint32_t)TB, ns - TB * b), zv);
+        poll16(pub + c0 + TB * b, q, min((uint32_t)TB, ns - TB * b), zv, D.status);
         double a4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int u = 0; u < 16; u++) a4[u & 3] = fma(cl[u], zv[u], a4[u & 3]);
@@ -1711,10 +1762,12 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         int dev = 0, sms = 0;
         MF_CU(cudaGetDevice(&dev));
         MF_CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if ((uint32_t)sms < kChainMaxCtas + 8) {  // the chunks of a chained level must all be resident at once
-            for (ChainLevel& c : chain_) c.on = false;
-            inv_count_ = 0;
-        }
+        (void)sms;  // (no residency condition any more: the polling kernels take their tasks by ticket)
+        // one ticket counter per polling launch: [level] dataflow factorisation, [L + level] chained forward,
+        // [2L + level] chained backward; cleared by a memset node at the head of the factor / solve graph
+        n_tickets_ = 3 * (uint32_t)chain_.size() + 1;
+        MF_CU(alloc_vec(&d_tickets_, n_tickets_, owned_));
+        MF_CU(cudaMemset(d_tickets_, 0, sizeof(uint32_t) * n_tickets_));
         MF_CU(cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem));
         MF_CU(cudaFuncSetAttribute(mf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem));
         bool any_flow = false;
@@ -1772,7 +1825,9 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
         timed(4, [&] { mf_small_factor_kernel<<<grid, kWarpsPerCta * 32, kSmallFactorSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_); });
     }
     if (d_pan_pub_) {
-        const cudaError_t e = cudaMemsetAsync(d_pan_pub_, 0xFF, (size_t)(flow_pub_hi_ - flow_pub_lo_) * sizeof(double), st);
+        cudaError_t e = cudaMemsetAsync(d_pan_pub_, 0xFF, (size_t)(flow_pub_hi_ - flow_pub_lo_) * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(d_tickets_, 0, sizeof(uint32_t) * chain_.size(), st);
         if (e != cudaSuccess) return e;
     }
     const uint32_t nlv = (uint32_t)level_seq_ptr_.size() - 1;
@@ -1800,7 +1855,7 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
             timed(3, [&] {
                 mf_flow_kernel<<<chain_[lv].flow_count, kTileThreads, kFlowSmem, st>>>(dev_, d_chain_tasks_ + chain_[lv].flow_first,
                                                                                     d_pan_pub_ - flow_pub_lo_, d_flow_asm_ptr_ + chain_[lv].asm_first,
-                                                                                    d_flow_asm_);
+                                                                                    d_flow_asm_, d_tickets_ + lv);
             });
         }
     }
@@ -1842,7 +1897,9 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
     bool any_chain = false;
     for (const ChainLevel& c : chain_) any_chain = any_chain || c.on;
     if (any_chain) {
-        const cudaError_t e = cudaMemsetAsync(d_chain_pub_, 0xFF, 2 * (size_t)n_ * sizeof(double), st);
+        cudaError_t e = cudaMemsetAsync(d_chain_pub_, 0xFF, 2 * (size_t)n_ * sizeof(double), st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(d_tickets_ + chain_.size(), 0, sizeof(uint32_t) * 2 * chain_.size(), st);
         if (e != cudaSuccess) return e;
     }
     if (nsub_) timed(0, [&] { mf_small_solve_kernel<true><<<sgrid, kWarpsPerCta * 32, kSmallSolveSmem, st>>>(dev_, d_sub_ptr_, d_sub_list_, nsub_, w, delta, d_perm); });
@@ -1851,7 +1908,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
         const uint32_t* list = d_level_list_ + level_ptr_[l];
         cur_level = (int)l;
         if (chain_[l].on) {
-            timed(1, [&] { mf_chain_fwd_kernel<<<chain_[l].fwd_count, 256, 0, st>>>(dev_, d_chain_tasks_ + chain_[l].fwd_first, w, d_chain_pub_); });
+            timed(1, [&] { mf_chain_fwd_kernel<<<chain_[l].fwd_count, 256, 0, st>>>(dev_, d_chain_tasks_ + chain_[l].fwd_first, w, d_chain_pub_, d_tickets_ + chain_.size() + l); });
             continue;
         }
         timed(1, [&] {
@@ -1870,7 +1927,7 @@ cudaError_t Multifrontal::enqueue_solve(double* w, double* delta, const int32_t*
                 timed(3, [&] { mf_bwd_dot_kernel<<<chain_[l].dot_count, 256, vsmem, st>>>(dev_, d_chain_tasks_ + chain_[l].dot_first, w, d_tmp_); });
             timed(4, [&] {
                 mf_chain_bwd_kernel<<<chain_[l].bwd_count, 256, 0, st>>>(dev_, d_chain_tasks_ + chain_[l].bwd_first, w, delta, d_perm, d_tmp_,
-                                                                      d_chain_pub_ + n_);
+                                                                      d_chain_pub_ + n_, d_tickets_ + 2 * chain_.size() + l);
             });
             continue;
         }

@@ -50,7 +50,7 @@ struct MfDev {
     double* upd = nullptr;        // update matrices (lower triangles used)
     double* winv = nullptr;       // D^-1 L^-1 of every 64x64 diagonal tile of the big fronts
     double* ubuf = nullptr;       // update vectors of the forward solve
-    int* status = nullptr;        // 0 ok, 1 non-positive pivot, 2 NaN pivot
+    int* status = nullptr;        // 0 ok, 1 non-positive pivot, 2 NaN pivot, 3 a polling loop gave up (internal error)
 };
 
 // Host-side symbolic structures of the multifrontal factorisation (everything init() uploads).
@@ -120,6 +120,8 @@ private:
     // tile dataflow factorisation of the chained levels: published panel tiles [flow_pub_lo_, flow_pub_hi_) of the panel storage
     std::vector<uint32_t> level_seq_ptr_;
     double* d_pan_pub_ = nullptr;
+    uint32_t* d_tickets_ = nullptr;  // task tickets of the polling launches (see take_ticket)
+    uint32_t n_tickets_ = 0;
     std::vector<uint32_t> flow_asm_ptr_, flow_asm_;  // per dataflow tile: extend-add ranges of its children (uint4 entries)
     const uint32_t* d_flow_asm_ptr_ = nullptr;
     const uint4* d_flow_asm_ = nullptr;

@@ -32,7 +32,7 @@ public:
     // free_values[n_free] in/out.
     int solve(const double* vars, const double* param, double* free_values, fk_report* report, std::string* err);
     // Timings of the last solve (ms, CUDA events): eval, assemble, factor, solve.
-    struct Timing { float eval_ms = 0, assemble_ms = 0, factor_ms = 0, tri_ms = 0, transpose_ms = 0, fwd_ms = 0, bwd_ms = 0; uint32_t evals = 0, factors = 0; } last;
+    struct Timing { float eval_ms = 0, assemble_ms = 0, factor_ms = 0, tri_ms = 0, transpose_ms = 0, fwd_ms = 0, bwd_ms = 0; uint32_t evals = 0, factors = 0, exact_sums = 0; } last;
     // One residual+Jacobian evaluation at `free_values` (parity probe / assembly-bandwidth metric).
     int eval_once(const double* vars, const double* param, const double* free_values, double* out_r, double* out_j,
                   int repeats, float* ms_per_eval, std::string* err);

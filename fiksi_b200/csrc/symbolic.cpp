@@ -548,7 +548,112 @@ int Topology::build_tables() {
     };
     pack_cols(false, t.s_nsteps, t.s_steps, t.s_ops);
     pack_cols(true, t.b_nsteps, t.b_steps, t.b_ops);
+    build_sketch_tables();
     return FK_OK;
+}
+
+// Tables of the sketch-per-thread kernel (see Topology::SketchTables).  Summation orders are those of the tile
+// kernel's lists (H and g: rows ascending from zero; LDLt: columns ascending, each target once per column;
+// back substitution: rows descending), so the two kernels produce the same numbers bit for bit.
+void Topology::build_sketch_tables() {
+    SketchTables& k = sk;
+    k = SketchTables();
+    const uint32_t n = n_free, m = n_rows, lnnz = (uint32_t)l_rowidx.size();
+    auto refuse = [&](const char* why) { k.ok = false; k.why = why; k.tab.clear(); };
+    if (path == 2 || n == 0 || m == 0) return refuse("not a shared-memory topology");
+    if (lnnz >= (1u << 22) || n >= (1u << 22) || n_vars >= (1u << 22)) return refuse("exceeds the table words");
+    for (size_t q = 0; q < slot_dup.size(); q++)
+        if (slot_dup[q] && slot_col[q] >= 0) return refuse("a row names a free variable twice");
+    auto l_find = [&](uint32_t row, uint32_t col) -> int64_t {
+        if (row == col) return l_colptr[col];
+        const uint32_t* b = l_rowidx.data() + l_colptr[col] + 1;
+        const uint32_t* e = l_rowidx.data() + l_colptr[col + 1];
+        const uint32_t* it = std::lower_bound(b, e, row);
+        return (it != e && *it == row) ? (int64_t)(it - l_rowidx.data()) : -1;
+    };
+    const uint32_t NONE = 0xFFFFFFFFu;
+    auto pos = [](uint32_t entry) { return entry << 8; };  // byte offset of an entry inside its region
+    // fixed variables and parameters some row reads
+    std::vector<int32_t> fix_slot(n_vars, -1), par_slot(n_expr, -1);
+    std::vector<uint32_t> fix_list, par_list;
+    static const bool has_param[FK_NUM_KINDS] = {false, true, true, false, true, false, false, true, false, false, false};
+    for (uint32_t r = 0; r < m; r++) {
+        const int a = kind_arity(row_kind[r]);
+        for (int s = 0; s < a; s++)
+            if (slot_col[(size_t)r * 8 + s] < 0) {
+                const uint32_t v = slot_var[(size_t)r * 8 + s];
+                if (fix_slot[v] < 0) { fix_slot[v] = (int32_t)fix_list.size(); fix_list.push_back(v); }
+            }
+        if (has_param[row_kind[r]] && par_slot[row_expr[r]] < 0) {
+            par_slot[row_expr[r]] = (int32_t)par_list.size();
+            par_list.push_back(row_expr[r]);
+        }
+    }
+    k.nfix = (uint32_t)fix_list.size(); k.npar = (uint32_t)par_list.size();
+    k.xa = 0; k.xb = n; k.w = 2 * n; k.f = 3 * n; k.fx = 3 * n + lnnz; k.pr = k.fx + k.nfix; k.entries = k.pr + k.npar;
+    std::vector<uint32_t>& T = k.tab;
+    k.off_free = (uint32_t)T.size();
+    for (uint32_t c = 0; c < n; c++) T.push_back(free_vars[c]);
+    k.off_fix = (uint32_t)T.size();
+    T.insert(T.end(), fix_list.begin(), fix_list.end());
+    k.off_par = (uint32_t)T.size();
+    T.insert(T.end(), par_list.begin(), par_list.end());
+    // every record below starts on a 16-byte boundary and is padded to one (the kernel reads 4 words per load)
+    auto pad4 = [&] { while (T.size() & 3u) T.push_back(0); };
+    pad4();
+    k.off_eval = (uint32_t)T.size();
+    for (uint32_t r = 0; r < m; r++) {
+        const int a = kind_arity(row_kind[r]);
+        const uint32_t words = (2 + 2 * (uint32_t)a + (uint32_t)(a * (a + 1) / 2) + 3u) & ~3u;
+        bool special = false;
+        int32_t pc[8];
+        for (int s = 0; s < a; s++) {
+            const int32_t c = slot_col[(size_t)r * 8 + s];
+            pc[s] = c >= 0 ? iperm[c] : -1;
+            special = special || c < 0;
+        }
+        T.push_back(row_kind[r] | (special ? 0x100u : 0u) | (words << 16));
+        T.push_back(has_param[row_kind[r]] ? pos((uint32_t)par_slot[row_expr[r]]) : 0u);
+        for (int s = 0; s < a; s++) {
+            const int32_t c = slot_col[(size_t)r * 8 + s];
+            T.push_back(c >= 0 ? pos((uint32_t)c) : (0x80000000u | pos((uint32_t)fix_slot[slot_var[(size_t)r * 8 + s]])));
+        }
+        for (int s = 0; s < a; s++) T.push_back(pc[s] >= 0 ? pos((uint32_t)pc[s]) : NONE);
+        for (int s = 0; s < a; s++)
+            for (int b = 0; b <= s; b++) {
+                if (pc[s] < 0 || pc[b] < 0) { T.push_back(NONE); continue; }
+                const int64_t p = l_find((uint32_t)std::max(pc[s], pc[b]), (uint32_t)std::min(pc[s], pc[b]));
+                if (p < 0) return refuse("internal: JtJ entry outside the L pattern");
+                T.push_back(pos((uint32_t)p));
+            }
+        pad4();
+    }
+    T.insert(T.end(), 4, 0u);  // the kernel prefetches the header of the record after the last one
+    k.off_factor = (uint32_t)T.size();
+    for (uint32_t c = 0; c < n; c++) {
+        const uint32_t b0 = l_colptr[c] + 1, e0 = l_colptr[c + 1], C = e0 - b0;
+        T.push_back(C); T.push_back(pos(l_colptr[c])); T.push_back(pos(c)); T.push_back(0);
+        for (uint32_t q = b0; q < e0; q++) T.push_back(pos(q));
+        for (uint32_t q = b0; q < e0; q++) T.push_back(pos(l_rowidx[q]));
+        for (uint32_t qa = b0; qa < e0; qa++)
+            for (uint32_t qb = b0; qb <= qa; qb++) {
+                const int64_t dst = l_find(l_rowidx[qa], l_rowidx[qb]);
+                if (dst < 0) return refuse("internal: fill outside the L pattern");
+                T.push_back(pos((uint32_t)dst));
+            }
+        pad4();
+    }
+    T.insert(T.end(), 4, 0u);
+    k.off_back = (uint32_t)T.size();
+    for (uint32_t cc = n; cc-- > 0;) {
+        const uint32_t b0 = l_colptr[cc] + 1, e0 = l_colptr[cc + 1];
+        T.push_back(e0 - b0); T.push_back(pos(l_colptr[cc])); T.push_back(pos(cc)); T.push_back(pos((uint32_t)perm[cc]));
+        for (uint32_t q = b0; q < e0; q++) T.push_back(pos(q));
+        for (uint32_t q = b0; q < e0; q++) T.push_back(pos(l_rowidx[q]));
+        pad4();
+    }
+    T.insert(T.end(), 4, 0u);
+    k.ok = true;
 }
 
 void Topology::fill_info(fk_topology_info* info) const {

@@ -95,6 +95,37 @@ struct Topology {
     } tab;
     int build_tables();
 
+    // ---- tables of the sketch-per-thread LM kernel (lm_sketch.cu) -----------------------------------------
+    // One THREAD owns one sketch; the state of the 32 sketches of a warp is interleaved in shared memory
+    // (`entry * 32 + lane` doubles), so every access of a warp is 32 consecutive doubles (no bank conflicts)
+    // and the tables below are warp-uniform: a CTA keeps one copy in shared memory and every warp reads them
+    // with 16-byte broadcast loads.  Table words are 32 bit; positions are BYTE offsets (entry << 8) relative to the
+    // region they address.  Regions of a sketch's state, in entries (doubles):
+    //   xa, xb [n]   accepted / trial free values (the two roles swap per lane on accept)
+    //   w  [n]       g = -J^T r in permuted order, then right-hand side and solution of the solve
+    //   f  [lnnz]    H = J^T J in L storage, factorised in place
+    //   fx [nfix]    values of the fixed variables some row reads;  pr [npar] parameters some row reads
+    struct SketchTables {
+        bool ok = false;          // false: the topology stays on the tile kernel (reason in `why`)
+        std::string why;
+        uint32_t entries = 0;
+        uint32_t xa = 0, xb = 0, w = 0, f = 0, fx = 0, pr = 0, nfix = 0, npar = 0;
+        // sections of `tab` (offsets in words):
+        //   free   [n]      variable index of free column c
+        //   fix    [nfix]   variable index;  par [npar] expression index
+        //   (records of the three sections below start on 16-byte boundaries; header = first 4 words)
+        //   eval   per row: header (kind | 0x100 if a slot is fixed | words of this row << 16), parameter
+        //          position in pr, A sources (position in x; 0x80000000 | position in fx for a fixed variable),
+        //          A gradient targets in w (0xFFFFFFFF none), A(A+1)/2 targets in f ((a, b), b <= a; 0xFFFFFFFF none)
+        //   factor per column k: C (entries below the diagonal), diagonal position, position of k in w, 0,
+        //          C positions in f, C positions in w (rows), C(C+1)/2 update targets in f ((a, b), b <= a)
+        //   back   per column k descending: C, diagonal position, position of k in w, position of perm[k] in x,
+        //          C positions in f, C positions in w (rows)
+        uint32_t off_free = 0, off_fix = 0, off_par = 0, off_eval = 0, off_factor = 0, off_back = 0;
+        std::vector<uint32_t> tab;
+    } sk;
+    void build_sketch_tables();
+
     std::string error;
 
     // Runs the whole pipeline.  Returns FK_OK or an error status (message in `error`).

@@ -220,6 +220,16 @@ FK_API uint64_t fk_batch_plan_launches(const fk_batch_plan* plan);
  * factorisation; MEASURED_PEAKS.json carries no FP64 figure). */
 FK_API int fk_fp64_peak_tflops(int device, double* out);
 
+/* Which batched LM kernel fk_batch_plan_run / fk_batch_solve* launch: -1 automatic (the
+ * sketch-per-thread kernel for batches that fill the device, the tile kernel otherwise), 0 always the
+ * tile kernel, 1 the sketch-per-thread kernel whenever the topology has one.  Process-wide; meant for
+ * tests and A/B measurements (environment: FK_LM_KERNEL=tile|sketch). */
+FK_API void fk_set_lm_kernel(int choice);
+FK_API int fk_get_lm_kernel(void);
+/* Sketch-per-thread kernel of a topology: *available = 0/1, *state_doubles = shared-memory doubles per
+ * sketch, *table_words = 16-bit words of its parameter block.  Any pointer may be null. */
+FK_API int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint32_t* state_doubles, uint32_t* table_words);
+
 /* Blocks until all work issued for this plan's device has finished. */
 FK_API int fk_batch_plan_sync(fk_batch_plan* plan);
 

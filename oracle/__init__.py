@@ -312,6 +312,24 @@ def gauss_jordan(matrix, column_indices=None):
     return m, ci, out[:nr].astype(bool)
 
 
+class qr_fast:
+    """Context manager: run the oracle's sparse QR without the reference's per-column O(m) scratch fill
+    (solvi qr.rs:287).  Results are bit-identical (tests/test_oracle_fast_mode.py); the slow mode stays
+    the default because it is the reference's cost, which ``cpu_baseline`` times."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = lib().orc_get_qr_fast()
+        lib().orc_set_qr_fast(1 if self.on else 0)
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_qr_fast(self.prev)
+        return False
+
+
 def lm_solve(problem, free_values):
     """levenberg_marquardt on a flattened problem.  Returns (x, report dict, trace string)."""
     x = np.array(free_values, dtype=np.float64)

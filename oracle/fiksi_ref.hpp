@@ -21,6 +21,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <deque>
 #include <map>
 #include <set>
@@ -408,6 +410,8 @@ inline void levenberg_marquardt(const Subsystem& problem, double* variables, LmR
             for (size_t idx = 0; idx < ncols; idx++) xs[idx] = variables[idx] + delta[idx];
             problem.calculate_residuals(xs.data(), residuals_scratch.data());
             double ssr_s = sum_squares(residuals_scratch.data(), nrows);
+            if (std::getenv("ORC_PROGRESS"))  // long golden-generation runs only
+                std::fprintf(stderr, "[oracle lm] factorization %u lambda %a ssr %a -> %a\n", rep.factorizations, lambda, ssr, ssr_s);
             if (ssr_s < ssr) {
                 lambda *= 0.125;
                 if (lambda < 1e-50) lambda = 1e-50;

@@ -144,6 +144,10 @@ ORC_API void orc_qr_factorize(void* hh, const double* values) {
     a.values.assign(values, values + h->a.row_indices.size());
     h->qr->factorize(a);
 }
+// Scratch handling of Qr::factorize: 0 = the reference's per-column O(m) fill (the CPU-baseline cost),
+// 1 = reset only the written positions (bit-identical results; reaches config 3).  Process-wide.
+ORC_API void orc_set_qr_fast(int on) { solvi::qr_fast_mode().store(on ? 1 : 0); }
+ORC_API int orc_get_qr_fast() { return solvi::qr_fast_mode().load(); }
 ORC_API void orc_qr_r_values(void* hh, double* out) {
     SymHandle* h = (SymHandle*)hh;
     for (size_t k = 0; k < h->qr->r.values.size(); k++) out[k] = h->qr->r.values[k];

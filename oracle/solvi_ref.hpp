@@ -19,6 +19,7 @@
 //    (permutation.rs:41-80); a permutation moves values without arithmetic.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -506,6 +507,15 @@ inline void apply_householder(double* x, double beta, const size_t* rows, size_t
     for (size_t k = 0; k < nrows_h; k++) x[rows[k]] = x[rows[k]] - hv[k] * tau;
 }
 
+// Same operations in the same order over a 32-bit copy of the row indices (fast mode only: the factor
+// is memory bound on the index stream, results do not depend on the index width).
+inline void apply_householder32(double* x, double beta, const uint32_t* rows, size_t nrows_h, const double* hv) {
+    double tau = 0.0;
+    for (size_t k = 0; k < nrows_h; k++) tau = tau + hv[k] * x[rows[k]];
+    tau = tau * beta;
+    for (size_t k = 0; k < nrows_h; k++) x[rows[k]] = x[rows[k]] - hv[k] * tau;
+}
+
 // qr.rs:244-275
 inline void calculate_householder(double* v, size_t len, double* norm_out, double* beta_out) {
     double beta, norm;
@@ -525,6 +535,12 @@ inline void calculate_householder(double* v, size_t len, double* norm_out, doubl
     *beta_out = beta;
 }
 
+// Process-wide switch of Qr::factorize's scratch handling (0: the reference's per-column fill).
+inline std::atomic<int>& qr_fast_mode() {
+    static std::atomic<int> mode{0};
+    return mode;
+}
+
 // qr.rs:91-104,209-223,281-356
 struct Qr {
     const SymbolicQr* s;
@@ -539,7 +555,17 @@ struct Qr {
         x.assign(sym.h_structure.nrows, 0.0);
     }
 
+    // `fast` (qr_fast_mode(), test infrastructure for sizes the O(m*n) fill cannot reach): instead of
+    // clearing all of x before every column (qr.rs:287) only the positions this column WROTE are reset
+    // to +0.0 when the column is done.  x is all +0.0 when a column starts in either mode (constructor /
+    // full fill / reset of every written position), every arithmetic operation and its order are the
+    // same, so R, H, beta and every later result are bit-identical by construction; the test-suite
+    // also checks that on every size the slow mode reaches.
     void factorize(const SparseColMat& a) {
+        if (qr_fast_mode().load(std::memory_order_relaxed) != 0) {
+            factorize_fast(a);
+            return;
+        }
         std::fill(r.values.begin(), r.values.end(), 0.0);
         std::fill(h_values.begin(), h_values.end(), 0.0);
         size_t n = a.structure.ncols;
@@ -568,6 +594,62 @@ struct Qr {
             calculate_householder(h_values.data() + hlo, hhi - hlo, &norm, &beta);
             h_betas[j] = beta;
             r.values[rhi - 1] = norm;
+        }
+    }
+
+    // Fast mode (qr_fast_mode(); test infrastructure for the sizes the O(m*n) fill cannot reach).  The
+    // same column loop with two changes that cannot alter a bit of the result:
+    //  * instead of clearing all of x before every column (qr.rs:287), the positions this column WROTE
+    //    (its scattered entries and the rows of every reflector applied to it) are reset to +0.0 when
+    //    the column is done; x is all +0.0 at the start of a column in both modes, and only written
+    //    positions can differ from +0.0;
+    //  * the reflector rows are read from a 32-bit copy of h_structure.row_indices.
+    // Every floating-point operation and its order are those of factorize();
+    // tests/test_oracle_fast_mode.py compares R, H-derived solutions and LM traces on every size the
+    // slow mode reaches.
+    std::vector<uint32_t> h_rows32;
+    void factorize_fast(const SparseColMat& a) {
+        std::fill(r.values.begin(), r.values.end(), 0.0);
+        std::fill(h_values.begin(), h_values.end(), 0.0);
+        size_t n = a.structure.ncols;
+        const Structure& hs = s->h_structure;
+        if (h_rows32.size() != hs.row_indices.size()) {
+            if (hs.nrows > 0xFFFFFFFFull) throw std::runtime_error("fast mode: more than 2^32 rows");
+            h_rows32.resize(hs.row_indices.size());
+            for (size_t k = 0; k < h_rows32.size(); k++) h_rows32[k] = (uint32_t)hs.row_indices[k];
+        }
+        std::fill(x.begin(), x.end(), 0.0);  // once per factorisation
+        for (size_t j = 0; j < n; j++) {
+            size_t src = s->col_permutation[j];
+            for (size_t k = a.structure.column_pointers[src]; k < a.structure.column_pointers[src + 1]; k++)
+                x[s->row_permutation[a.structure.row_indices[k]]] = a.values[k];
+            size_t rlo = r.structure.column_pointers[j], rhi = r.structure.column_pointers[j + 1];
+            for (size_t k = rlo; k < rhi; k++) {
+                size_t r_row = r.structure.row_indices[k];
+                if (r_row == j) continue;
+                size_t hlo = hs.column_pointers[r_row], hhi = hs.column_pointers[r_row + 1];
+                apply_householder32(x.data(), h_betas[r_row], h_rows32.data() + hlo, hhi - hlo, h_values.data() + hlo);
+                r.values[k] = x[r_row];
+                x[r_row] = 0.0;
+            }
+            size_t hlo = hs.column_pointers[j], hhi = hs.column_pointers[j + 1];
+            for (size_t k = hlo; k < hhi; k++) {
+                h_values[k] = x[h_rows32[k]];
+                x[h_rows32[k]] = 0.0;
+            }
+            double norm, beta;
+            calculate_householder(h_values.data() + hlo, hhi - hlo, &norm, &beta);
+            h_betas[j] = beta;
+            r.values[rhi - 1] = norm;
+            for (size_t k = a.structure.column_pointers[src]; k < a.structure.column_pointers[src + 1]; k++)
+                x[s->row_permutation[a.structure.row_indices[k]]] = 0.0;
+            for (size_t k = rlo; k < rhi; k++) {
+                size_t r_row = r.structure.row_indices[k];
+                if (r_row == j) continue;
+                const uint32_t* rw = h_rows32.data() + hs.column_pointers[r_row];
+                const size_t cnt = hs.column_pointers[r_row + 1] - hs.column_pointers[r_row];
+                for (size_t q = 0; q < cnt; q++) x[rw[q]] = 0.0;
+            }
         }
     }
 
