@@ -30,6 +30,10 @@ __device__ __forceinline__ double sk_rcp(double d) {
 __device__ __forceinline__ double ldp(const char* p, uint32_t off) { return *reinterpret_cast<const double*>(p + off); }
 __device__ __forceinline__ void stp(char* p, uint32_t off, double v) { *reinterpret_cast<double*>(p + off) = v; }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 __host__ __device__ constexpr int sk_arity(int kind) {
     return kind == 0 ? 2 : kind == 1 ? 4 : kind <= 4 ? 6 : kind == 5 ? 5 : kind <= 9 ? 8 : 7;
 }
@@ -203,9 +207,13 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
     const char* const fx = base + (P.fx << 8);
     const char* const pr = base + (P.pr << 8);
 
-    for (uint32_t i = 0; i < n; i++) stp(xp, i << 8, __ldg(vars + tab[P.off_free + i]));
-    for (uint32_t i = 0; i < P.nfix; i++) stp(base, (P.fx + i) << 8, __ldg(vars + tab[P.off_fix + i]));
-    for (uint32_t i = 0; i < P.npar; i++) stp(base, (P.pr + i) << 8, __ldg(params + tab[P.off_par + i]));
+    // The caller's rows ([sketch][variable]) go straight into the interleaved layout with 8-byte asynchronous
+    // copies: all of a sketch's loads are in flight at once and the thread waits once (with one warp or two per
+    // SM nothing else would hide the DRAM latency of a load-then-store loop).
+    for (uint32_t i = 0; i < n; i++) cp_async8(xp + (i << 8), vars + tab[P.off_free + i]);
+    for (uint32_t i = 0; i < P.nfix; i++) cp_async8(base + ((P.fx + i) << 8), vars + tab[P.off_fix + i]);
+    for (uint32_t i = 0; i < P.npar; i++) cp_async8(base + ((P.pr + i) << 8), params + tab[P.off_par + i]);
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
 
     double ssr = 0.0, lambda = 0.5, dn = 0.0;  // lm.rs:108
     uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
