@@ -94,7 +94,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = 16384
+    n_sample = N_PER_GPU  # the same 65,536 sketches per step as our arm (one step is ~0.3 s on 16 host cores)
     times = []
     for k in range(args.warmup + args.steps):
         rate, secs, rep = cpu_reference_run(n_sample, threads, first=k * n_sample)
@@ -107,7 +107,8 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 20-point rigid distance truss batch (40 vars, 37 rows per sketch)",
-                   "sketches_per_step": n_sample, "note": "bounded sample of the 65,536-sketch workload per step"},
+                   "sketches_per_gpu": n_sample, "sketches_per_step": n_sample,
+                   "note": "the reference's CPU algorithm (oracle port; no Rust toolchain here) on all host threads, whole 65,536-sketch steps"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n_sample} sketches per step, {len(times)} steps, one sketch per task on {threads} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,6 +219,7 @@ def main():
     torch.cuda.synchronize()
     rep = hrep.numpy().view(fk.REPORT_DTYPE).reshape(-1)
     solved = float(np.mean(rep["ssr"] < 1e-8))
+    fact = float(rep["factorizations"].sum())  # (the host buffers are reused by the measurements below)
 
     # ---- end-to-end through the host-buffer C-ABI call ------------------------------------------------
     for _ in range(2):
@@ -230,65 +232,104 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    # ---- host-copy ceiling: the same bytes as one e2e step, H2D and D2H concurrently on two streams, every rank at
+    # once (what the box's host<->device path can carry when nothing is computed) ---------------------------------
+    h2d = 8 * n * (info["n_vars"] + info["n_expr"])
+    d2h = 8 * n * info["n_free"] + 40 * n
+    dv = torch.empty(v.shape, dtype=torch.float64, device="cuda")
+    dp = torch.empty(p.shape, dtype=torch.float64, device="cuda")
+    dout = torch.empty((n, info["n_free"]), dtype=torch.float64, device="cuda")
+    drep = torch.empty((n, 40), dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_step():
+        with torch.cuda.stream(s_in):
+            dv.copy_(hv, non_blocking=True)
+            dp.copy_(hp, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hout.copy_(dout, non_blocking=True)
+            hrep.copy_(drep, non_blocking=True)
+    for _ in range(2):
+        copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_step()
+    barrier()
+    copy_s = time.perf_counter() - t0
+    del dv, dp, dout, drep
+
+    t = torch.tensor([total_ms, e2e_s, copy_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(t[0]), float(t[1])
+    total_ms, e2e_s, copy_s = float(t[0]), float(t[1]), float(t[2])
 
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / e2e_s
-    h2d = 8 * n * (info["n_vars"] + info["n_expr"])
-    d2h = 8 * n * info["n_free"] + 40 * n
+    copy_ceiling = world * n * e2e_steps / copy_s
+    uses_sketch_kernel = topo.batch_kernel(n) == "sketch"
+    kernel_name = "fk_batch_lm_sketch_kernel (one thread per sketch)" if uses_sketch_kernel else "fk_batch_lm_kernel<%d,%d> (tile)" % (info["tile"], 1)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: batch of 65,536 perturbed 20-point rigid distance trusses per GPU "
-                               "(40 free vars, 37 PPD rows, 148 J nnz), one sketch per warp",
-                   "sketches_per_gpu": n, "tile_lanes": info["tile"], "smem_bytes_per_sketch": info["smem_bytes"],
+                               "(40 free vars, 37 PPD rows, 148 J nnz)",
+                   "sketches_per_gpu": n, "sketches_per_step": n, "kernel": kernel_name,
+                   "state_doubles_per_sketch": topo.sketch_kernel_info()["state_doubles"] if uses_sketch_kernel else info["smem_bytes"] // 8,
                    "l2": "flushed between timed steps (512 MB memset)", "parallelism": f"sketch-sharded x{world}, no data-path collective",
                    "fraction_converged": solved, "wall_s_timed_region": wall,
                    "host_affinity": f"rank bound to the {bound} cores NVML reports local to its GPU" if bound else "unbound"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "fk_batch_solve_device (pinned host buffers, 3-stream chunk pipeline)"},
+                "steps": e2e_steps, "api": "fk_batch_solve_device (pinned host buffers, 3-stream chunk pipeline)",
+                "copy_ceiling": {"value": copy_ceiling, "unit": UNIT, "gb_per_s_all_ranks": world * (h2d + d2h) * e2e_steps / copy_s / 1e9,
+                                 "how": "the step's H2D and D2H bytes copied concurrently on two streams by every rank, nothing computed"},
+                "frac_of_copy_ceiling": e2e_value / copy_ceiling},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks.summary(),
     }
 
+    # ---- configs[3] and configs[4] as north_star states them: every rank takes part -------------------------------
+    if not args.no_extras:
+        try:
+            line["config4"] = config4_sharded(fk, wl, torch, dist, rank, world, local_rank, barrier)
+        except Exception as e:  # noqa: BLE001
+            line["config4"] = {"error": str(e)}
+        try:
+            line["config5"] = config5_sharded(fk, wl, torch, dist, rank, world, local_rank, barrier)
+        except Exception as e:  # noqa: BLE001
+            line["config5"] = {"error": str(e)}
+
     if rank == 0:
-        # roofline of the dominant kernel (fk_batch_lm_kernel): algorithmic HBM bytes per launch are
-        # the sketch inputs and outputs only — everything else lives in shared memory.
+        # Roofline of the dominant kernel (the batched LM kernel).  Its state lives in shared memory, so HBM only sees
+        # each sketch's inputs and outputs once; the roof that bounds it is the FP64 pipe (north_star: "FP64 pipe
+        # utilisation for the factorisations").  achieved = algorithmic flops per launch (factorisations x (sum of
+        # squared column counts + 4 nnz(L))) / average launch time; peak = DFMA rate measured on this device
+        # by fk_fp64_peak_tflops (MEASURED_PEAKS.json carries no FP64 figure).
         peak, peak_src = _peaks()
         alg_bytes = h2d + d2h
         avg_s = (total_ms / args.steps) * 1e-3 if world == 1 else (float(sum(step_ms)) / args.steps) * 1e-3
-        achieved = alg_bytes / avg_s / 1e9
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
-        # of this same command (profiles/r01_v3_lm_kernel_tile16_ncu_full_summary.csv): 40.44 MB + 0.64 MB
-        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": 41084416 if (n == 65536 and info["tile"] == 16) else None,
-                            "kernel": "fk_batch_lm_kernel<%d,%d>" % (info["tile"], 1), "peak_source": peak_src,
-                            "limiter": {"unit": "L1 / shared-memory data pipe (ncu l1tex__data_pipe_lsu_wavefronts)", "pct_of_peak": 68.5,
-                                        "shared_memory_wavefronts_pct": 50.5, "op_table_loads_through_l1_pct": 18.0,
-                                        "bank_conflict_share_of_shared_wavefronts": 0.28, "issue_slots_busy_pct": 60.5,
-                                        "fp64_pipe_active_pct": 10.6,
-                                        "source": "profiles/r01_v3_lm_kernel_tile16_ncu_full_summary.csv (ncu --set full of this command)"},
-                            "note": "the whole LM loop runs out of shared memory, so HBM only sees each sketch's inputs and outputs once "
-                                    "(DRAM 0.3 % busy); the unit that saturates is the SM's L1/shared-memory data pipe (see `limiter`); "
-                                    "the HBM-bound kernel of the path is K1, see `assembly`"}
+        flops = fact * (info["chol_flops"] + 4.0 * info["r_nnz"])
+        try:
+            fp64_peak = fk.fp64_peak_tflops(local_rank)
+        except Exception:  # noqa: BLE001
+            fp64_peak = None
+        line["roofline"] = {"bound": "fp64", "achieved": flops / avg_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": (flops / avg_s / 1e12 / fp64_peak) if fp64_peak else None, "traffic": None,
+                            "kernel": kernel_name,
+                            "peak_source": "DFMA microbenchmark on this device (fk_fp64_peak_tflops; the driver's MEASURED_PEAKS.json has no FP64 figure)",
+                            "algorithmic_flops_per_launch": flops, "factorizations_per_launch": fact,
+                            "flops_per_factorization": info["chol_flops"] + 4.0 * info["r_nnz"],
+                            "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / avg_s / 1e9, "peak_gbs": peak,
+                                    "frac": alg_bytes / avg_s / 1e9 / peak, "peak_source": peak_src,
+                                    "note": "inputs + outputs once per sketch; not the limiter"},
+                            "profiles": "ncu --set full summaries of this command: profiles/r02_*lm_sketch*",
+                            "note": "latency bound: one warp solves 32 sketches out of shared memory and only one or two such warps fit an SM "
+                                    "for this topology; see DESIGN.md section 4 for the stall breakdown"}
         if not args.no_extras:
             try:
-                fp64_peak = fk.fp64_peak_tflops(local_rank)
-                fact = float(rep["factorizations"].sum())
-                # per factorisation: sparse LDL^T (sum colcount^2) + two triangular solves (4 nnz(L))
-                flops = fact * (info["chol_flops"] + 4.0 * info["r_nnz"])
-                line["fp64"] = {"achieved_tflops": flops / avg_s / 1e12, "peak_tflops": fp64_peak,
-                                "frac": flops / avg_s / 1e12 / fp64_peak, "peak_source": "measured DFMA microbenchmark (fk_fp64_peak_tflops)",
-                                "factorizations_per_step": fact, "flops_per_factorization": info["chol_flops"] + 4.0 * info["r_nnz"]}
-            except Exception as e:  # noqa: BLE001
-                line["fp64"] = {"error": str(e)}
-            try:
-                line["large_system"] = large_system(fk, wl, peak, line["fp64"].get("peak_tflops"))
+                line["large_system"] = large_system(fk, wl, peak, fp64_peak)
             except Exception as e:  # noqa: BLE001
                 line["large_system"] = {"error": str(e)}
             try:
@@ -326,6 +367,100 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _allreduce(torch, dist, world, values, op="sum"):
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return [float(x) for x in t]
+
+
+def config4_sharded(fk, wl, torch, dist, rank, world, local_rank, barrier):
+    """configs[3]: 1,000,000 mixed-primitive CAD sketches (circle_triangle_line topology) sharded by sketch over the
+    ranks (strong scaling: the total is fixed), through the host-buffer call fk_batch_solve_device from pinned memory,
+    and device resident for comparison.  Max over ranks of the timed region, every rank takes part."""
+    import numpy as np
+    total = 1_000_000
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    n = hi - lo
+    w = wl.cad_mix(n, first=lo)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    info = topo.info
+    hv, hp = torch.from_numpy(v).pin_memory(), torch.from_numpy(p).pin_memory()
+    hout = torch.empty((n, info["n_free"]), dtype=torch.float64).pin_memory()
+    hrep = torch.empty((n, 40), dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        topo.batch_solve_into(local_rank, n, hv.data_ptr(), hp.data_ptr(), hout.data_ptr(), hrep.data_ptr())
+    barrier()
+    steps = 5
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        topo.batch_solve_into(local_rank, n, hv.data_ptr(), hp.data_ptr(), hout.data_ptr(), hrep.data_ptr())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    rep = hrep.numpy().view(fk.REPORT_DTYPE).reshape(-1)
+    plan = topo.plan(n, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    plan.upload_ptr(n, hv.data_ptr(), hp.data_ptr(), stream)
+    for _ in range(2):
+        plan.run(stream)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        plan.run(stream)
+    b.record()
+    barrier()
+    dev_ms = a.elapsed_time(b)
+    plan.close()
+    e2e_s, dev_ms = _allreduce(torch, dist, world, [e2e_s, dev_ms], "max")
+    conv, fact = _allreduce(torch, dist, world, [float(np.sum(rep["ssr"] < 1e-8)), float(rep["factorizations"].sum())])
+    return {"workload": "configs[3]: 1,000,000 mixed-primitive CAD sketches (11 variables, 8 rows of 6 kinds), sharded by sketch",
+            "n_gpus": world, "scaling": "strong", "sketches_total": total,
+            "e2e_sketches_per_s": total * steps / e2e_s, "device_resident_sketches_per_s": total * steps / (dev_ms * 1e-3),
+            "h2d_bytes_per_sketch": 8 * (info["n_vars"] + info["n_expr"]), "d2h_bytes_per_sketch": 8 * info["n_free"] + 40,
+            "fraction_converged": conv / total, "mean_factorizations": fact / total,
+            "api": "fk_batch_solve_device from pinned host buffers (H2D + D2H inside the timed region)"}
+
+
+def config5_sharded(fk, wl, torch, dist, rank, world, local_rank, barrier):
+    """configs[4]: the stress families (under-/over-constrained, rank deficient, badly scaled, NaN),
+    8,192 sketches each, every family sharded by sketch over the ranks.  Reports throughput through the host-buffer
+    call, the exit-reason histogram per family and the rate at which the accept/reject trace and the exit equal the
+    oracle's on a sample of every rank's shard."""
+    import numpy as np
+    import oracle
+    n_each, sample = 8192, 96
+    fams = wl.stress_families(n_each)
+    out, total_s, total_n = {}, 0.0, 0
+    for name, w in fams:
+        lo, hi = n_each * rank // world, n_each * (rank + 1) // world
+        # (the NaN family must keep its points coincident: the solve's seeded perturbation would separate them)
+        v, p, scale = w.prepare(perturb=(name != "nan_coincident_points"))
+        v, p = np.ascontiguousarray(v[lo:hi]), np.ascontiguousarray(p[lo:hi])
+        topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+        topo.batch_solve(v[:64], p[:64])
+        barrier()
+        t0 = time.perf_counter()
+        x, rep = topo.batch_solve(v, p)
+        barrier()
+        secs = time.perf_counter() - t0
+        hist = np.bincount(rep["exit_reason"], minlength=5)[:5].astype(np.float64)
+        m = min(sample, hi - lo)
+        op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
+        xo, ro, _ = oracle.lm_solve_batch_uniform(op, v[:m], p[:m], threads=min(8, os.cpu_count() or 1))
+        same = float(np.sum((rep["trace_hash"][:m] == ro["trace_hash"]) & (rep["exit_reason"][:m] == ro["exit_reason"])))
+        red = _allreduce(torch, dist, world, list(hist) + [same, float(m)])
+        secs = _allreduce(torch, dist, world, [secs], "max")[0]
+        out[name] = {"exit_histogram": {k: int(c) for k, c in zip(("converged", "small_step", "stalled", "max_outer", "lambda_overflow"), red[:5])},
+                     "trace_and_exit_equal_to_oracle": red[5] / red[6], "oracle_sample": int(red[6]), "sketches_per_s": n_each / secs}
+        total_s += secs
+        total_n += n_each
+    return {"workload": "configs[4]: %d stress families x %d sketches, sharded by sketch" % (len(fams), n_each), "n_gpus": world,
+            "sketches_per_s_all_families": total_n / total_s, "families": out,
+            "api": "fk_batch_solve (pageable host buffers, H2D + D2H inside)"}
 
 
 def single_sketch_latency(fk, wl):
@@ -441,10 +576,12 @@ def lbfgs_side(fk, wl, device):
     w = wl.truss(n)
     v, p, scale = w.prepare()
     topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
-    topo.batch_solve_lbfgs(v[:1024], p[:1024], device)
-    t0 = time.perf_counter()
-    x, rep = topo.batch_solve_lbfgs(v, p, device)
-    gpu_s = time.perf_counter() - t0
+    topo.batch_solve_lbfgs(v, p, device)  # warm-up at the measured size: the pooled plans of the entry point grow once
+    gpu_s = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        x, rep = topo.batch_solve_lbfgs(v, p, device)
+        gpu_s = min(gpu_s, time.perf_counter() - t0)
     import torch
     plan = topo.plan(n, device=device)
     stream = torch.cuda.current_stream().cuda_stream
@@ -498,15 +635,15 @@ def assembly_bandwidth(fk, wl, torch, device, peak):
     i = topo.info
     dram = 8 * n * (i["n_vars"] + i["n_expr"] + i["n_rows"] + i["jac_nnz"])  # every input and output byte once
     out = {"kernel": "fk_batch_eval_tiled_kernel<64,true>", "workload": "config 4 topology, 1,000,000 sketches",
-           "algorithmic_bytes": alg, "ms": ms, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
-    out["frac"] = out["achieved"] / peak
+           "bound": "hbm", "algorithmic_bytes": alg, "ms": ms, "achieved_algorithmic_gbs": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
+    out["frac_algorithmic"] = out["achieved_algorithmic_gbs"] / peak
     # SURVEY 8d's algorithmic bytes count every per-row gather (17 + 4k + 20a B/row); the tile-staged kernel
     # reads each variable once per sketch, so the traffic HBM actually sees is smaller (ncu: 152 MB read +
     # 366 MB written per launch, profiles/r01_k1_tiled_S64_ncu_full_summary.csv)
     out["min_dram_bytes"] = dram
-    out["dram_gbs"] = dram / (ms * 1e-3) / 1e9
-    out["dram_frac_of_peak"] = out["dram_gbs"] / peak
-    out["traffic"] = 518283520
+    out["achieved"] = dram / (ms * 1e-3) / 1e9   # REAL bytes (every input and output byte once): the HBM fraction to quote
+    out["frac"] = out["achieved"] / peak
+    out["traffic"] = None  # one ncu --set full capture of this kernel: profiles/r01_k1_tiled_S64_ncu_full_summary.csv (152 MB read + 366 MB written)
     plan.close()
     # LM solve of the same 1,000,000 mixed-primitive sketches (config 4), device-resident
     try:

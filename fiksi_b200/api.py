@@ -152,6 +152,10 @@ class Topology:
         check(lib().fk_topology_sketch_kernel_info(self._h, C.byref(ok), C.byref(ent), C.byref(words)))
         return {"available": bool(ok.value), "state_doubles": ent.value, "table_words": words.value}
 
+    def batch_kernel(self, n_sketches):
+        """fk_topology_batch_kernel: 'sketch' or 'tile', the kernel a batched LM solve of this size launches."""
+        return "sketch" if lib().fk_topology_batch_kernel(self._h, int(n_sketches)) == 1 else "tile"
+
     def plan(self, capacity, device=0):
         return BatchPlan(self, capacity, device)
 
@@ -243,6 +247,21 @@ class lm_kernel:
     def __exit__(self, *exc):
         lib().fk_set_lm_kernel(self.prev)
         return False
+
+
+def topology_cache_stats():
+    """fk_topology_cache_stats: (hits, misses, entries) of the process-wide topology cache of fk_lm_solve*."""
+    h, m, e = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+    lib().fk_topology_cache_stats(C.byref(h), C.byref(m), C.byref(e))
+    return h.value, m.value, e.value
+
+
+def topology_cache_clear():
+    lib().fk_topology_cache_clear()
+
+
+def topology_cache_configure(capacity):
+    lib().fk_topology_cache_configure(int(capacity))
 
 
 def device_count() -> int:

@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <list>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -150,12 +152,31 @@ struct DevicePipeline {
     ~DevicePipeline() { release(); }
 };
 
+// Device tables and grow-only device buffers of fk_batch_analyze for one (topology, device).
+struct AnalyzePool {
+    int device = -1;
+    std::mutex mu;
+    uint8_t* d_kind = nullptr;
+    uint32_t* d_slot = nullptr;
+    double *d_vars = nullptr, *d_param = nullptr;
+    uint8_t* d_out = nullptr;
+    uint32_t capacity = 0;
+    cudaStream_t stream = nullptr;
+    ~AnalyzePool() {
+        if (device >= 0) cudaSetDevice(device);
+        cudaFree(d_kind); cudaFree(d_slot); cudaFree(d_vars); cudaFree(d_param); cudaFree(d_out);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct fk_topology {
     fk::Topology t;
     std::mutex mu;
     std::map<int, std::unique_ptr<DeviceProgram>> programs;
     std::map<int, std::unique_ptr<DevicePipeline>> pipelines;
     std::map<int, std::unique_ptr<fk::SparseSolver>> sparse;  // path 2: one solver per device
+    std::mutex sparse_mu;               // a SparseSolver owns one set of work vectors and CUDA graphs: one solve at a time
+    std::map<int, std::unique_ptr<struct AnalyzePool>> analyze_pools;  // fk_batch_analyze: tables + grow-only buffers
     std::unique_ptr<fk_topology> latency_twin;  // same topology with 32 lanes per sketch: single-system solves
     bool twin_tried = false;
     std::mutex sp_mu;                   // SinglePass plan: one sub-topology per strongly connected set
@@ -451,73 +472,73 @@ int fk_batch_solve_single_pass(const fk_topology* topo_c, uint32_t n, double* va
 }
 
 // ---- L-BFGS on a uniform batch -------------------------------------------------------------------
+static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars, const double* param,
+                            double* free_out, fk_report* reports, std::string* err, int optimizer = 0);
+
 int fk_batch_solve_lbfgs(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param, double* free_out,
                          fk_report* reports) {
     if (!topo_c) return fail(FK_ERR_INVALID, "null topology");
     if (n == 0) return FK_OK;
     if (!vars || !free_out || !reports || (!param && topo_c->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
     if (topo_c->t.path != 0) return fail(FK_ERR_TOO_LARGE, "L-BFGS is built for the shared-memory tile paths only");
-    fk_batch_plan* plan = nullptr;
-    int rc = fk_batch_plan_create(topo_c, n, device, &plan);
-    if (rc != FK_OK) return rc;
-    rc = fk_batch_plan_upload(plan, n, vars, param, nullptr);
-    if (rc == FK_OK) rc = fk_batch_plan_run_lbfgs(plan, nullptr);
-    if (rc == FK_OK) rc = fk_batch_plan_download(plan, free_out, reports, nullptr);
-    if (rc == FK_OK) rc = fk_batch_plan_sync(plan);
-    fk_batch_plan_destroy(plan);
-    return rc;
+    const int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    // same pooled plans / streams / pinned staging as the LM entry (no allocation per call)
+    return run_device_range(const_cast<fk_topology*>(topo_c), device, 0, n, vars, param, free_out, reports, nullptr, 1);
 }
 
 // ---- System::analyze on a batch -----------------------------------------------------------------
-int fk_batch_analyze(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param, uint8_t* independent) {
+int fk_batch_analyze(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param, uint8_t* independent) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
     if (!topo || (n && (!vars || !independent || (!param && topo->t.n_expr)))) return fail(FK_ERR_INVALID, "null argument");
     const int ndev = usable_devices();
     if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
     const fk::Topology& t = topo->t;
     if (n == 0 || t.n_expr == 0) return FK_OK;
+    AnalyzePool* pool;
+    {
+        std::lock_guard<std::mutex> lock(topo->mu);
+        auto& p = topo->analyze_pools[device];
+        if (!p) p.reset(new AnalyzePool());
+        pool = p.get();
+    }
+    std::lock_guard<std::mutex> lock(pool->mu);
     CU(cudaSetDevice(device));
-    std::vector<uint32_t> slot_var((size_t)t.n_expr * 8, 0);
-    for (uint32_t e = 0; e < t.n_expr; e++) {
-        uint32_t sv[8];
-        const int a = fk::expand_slots(t.kind[e], &t.idx[4 * (size_t)e], sv);
-        for (int k = 0; k < a; k++) slot_var[(size_t)e * 8 + k] = sv[k];
+    if (pool->device < 0) {  // tables: once per (topology, device)
+        std::vector<uint32_t> slot_var((size_t)t.n_expr * 8, 0);
+        for (uint32_t e = 0; e < t.n_expr; e++) {
+            uint32_t sv[8];
+            const int a = fk::expand_slots(t.kind[e], &t.idx[4 * (size_t)e], sv);
+            for (int k = 0; k < a; k++) slot_var[(size_t)e * 8 + k] = sv[k];
+        }
+        pool->device = device;
+        CU(cudaMalloc(&pool->d_kind, t.n_expr));
+        CU(cudaMalloc(&pool->d_slot, slot_var.size() * sizeof(uint32_t)));
+        CU(cudaStreamCreateWithFlags(&pool->stream, cudaStreamNonBlocking));
+        CU(cudaMemcpyAsync(pool->d_kind, t.kind.data(), t.n_expr, cudaMemcpyHostToDevice, pool->stream));
+        CU(cudaMemcpyAsync(pool->d_slot, slot_var.data(), slot_var.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, pool->stream));
+        CU(cudaStreamSynchronize(pool->stream));  // slot_var leaves scope
     }
-    uint8_t *d_kind = nullptr, *d_out = nullptr;
-    uint32_t* d_slot = nullptr;
-    double *d_vars = nullptr, *d_param = nullptr;
-    int rc = FK_OK;
-    auto cleanup = [&] { cudaFree(d_kind); cudaFree(d_out); cudaFree(d_slot); cudaFree(d_vars); cudaFree(d_param); };
-#define AN_CU(call)                                   \
-    do {                                              \
-        cudaError_t e_ = (call);                      \
-        if (e_ != cudaSuccess) {                      \
-            cleanup();                                \
-            return cuda_fail(e_, #call);              \
-        }                                             \
-    } while (0)
-    AN_CU(cudaMalloc(&d_kind, t.n_expr));
-    AN_CU(cudaMalloc(&d_slot, slot_var.size() * sizeof(uint32_t)));
-    AN_CU(cudaMalloc(&d_vars, sizeof(double) * (size_t)n * t.n_vars));
-    AN_CU(cudaMalloc(&d_param, sizeof(double) * (size_t)n * t.n_expr));
-    AN_CU(cudaMalloc(&d_out, (size_t)n * t.n_expr));
-    AN_CU(cudaMemcpy(d_kind, t.kind.data(), t.n_expr, cudaMemcpyHostToDevice));
-    AN_CU(cudaMemcpy(d_slot, slot_var.data(), slot_var.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    AN_CU(cudaMemcpy(d_vars, vars, sizeof(double) * (size_t)n * t.n_vars, cudaMemcpyHostToDevice));
-    AN_CU(cudaMemcpy(d_param, param, sizeof(double) * (size_t)n * t.n_expr, cudaMemcpyHostToDevice));
-    const int e = fk::launch_batch_analyze(t.n_vars, t.n_expr, d_kind, d_slot, n, d_vars, d_param, d_out, nullptr);
-    if (e == (int)cudaErrorInvalidConfiguration) {
-        cleanup();
+    if (pool->capacity < n) {  // grow-only
+        cudaFree(pool->d_vars); cudaFree(pool->d_param); cudaFree(pool->d_out);
+        pool->d_vars = pool->d_param = nullptr; pool->d_out = nullptr; pool->capacity = 0;
+        const uint32_t cap = std::max<uint32_t>(n, 1024);
+        CU(cudaMalloc(&pool->d_vars, sizeof(double) * (size_t)cap * std::max<uint32_t>(t.n_vars, 1)));
+        CU(cudaMalloc(&pool->d_param, sizeof(double) * (size_t)cap * t.n_expr));
+        CU(cudaMalloc(&pool->d_out, (size_t)cap * t.n_expr));
+        pool->capacity = cap;
+    }
+    CU(cudaMemcpyAsync(pool->d_vars, vars, sizeof(double) * (size_t)n * t.n_vars, cudaMemcpyHostToDevice, pool->stream));
+    CU(cudaMemcpyAsync(pool->d_param, param, sizeof(double) * (size_t)n * t.n_expr, cudaMemcpyHostToDevice, pool->stream));
+    const int e = fk::launch_batch_analyze(t.n_vars, t.n_expr, pool->d_kind, pool->d_slot, n, pool->d_vars, pool->d_param, pool->d_out, pool->stream);
+    if (e == (int)cudaErrorInvalidConfiguration)
         return fail(FK_ERR_TOO_LARGE, "the expression x variable matrix of one sketch does not fit shared memory");
-    }
-    if (e != 0) {
-        cleanup();
-        return cuda_fail((cudaError_t)e, "launch fk_batch_analyze_kernel");
-    }
-    AN_CU(cudaMemcpy(independent, d_out, (size_t)n * t.n_expr, cudaMemcpyDeviceToHost));
-#undef AN_CU
-    cleanup();
-    return rc;
+    if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_analyze_kernel");
+    CU(cudaMemcpyAsync(independent, pool->d_out, (size_t)n * t.n_expr, cudaMemcpyDeviceToHost, pool->stream));
+    CU(cudaStreamSynchronize(pool->stream));
+    return FK_OK;
 }
 
 // ---- device-resident batch plan -----------------------------------------------------------------
@@ -655,6 +676,15 @@ int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint
     return FK_OK;
 }
 
+int fk_topology_batch_kernel(const fk_topology* topo, uint32_t n_sketches) {
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    const fk::Topology::SketchTables& k = topo->t.sk;
+    static const fk::SkProgram probe{};
+    fk::DevProgram p{};
+    p.sketch_prog = (k.ok && fk::sk_fits(k.entries, k.tab.size())) ? &probe : nullptr;
+    return fk::batch_lm_uses_sketch_kernel(p, n_sketches);
+}
+
 void* fk_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
@@ -668,45 +698,101 @@ void fk_host_free(void* p) {
 }
 
 // ---- host-buffer batch: shard by sketch over the devices, pipeline chunks per device ----------------
-static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars,
-                            const double* param, double* free_out, fk_report* reports, std::string* err) {
+static int launch_optimizer(const fk::DevProgram& prog, const DeviceProgram& full, int optimizer, uint32_t n, const double* vars,
+                            const double* params, double* out, fk_report* reps, cudaStream_t st) {
+    if (optimizer == 1) return fk::launch_batch_lbfgs(prog, full.jcolptr, full.jrow, n, vars, params, out, reps, st);
+    return fk::launch_batch_lm(prog, n, vars, params, out, reps, st);
+}
+
+// Small request (one sketch, a handful): the caller's (pageable) arrays go through ONE pinned staging block -- one
+// copy in, the kernel, one copy out, one synchronisation -- instead of four pageable copies on the chunk pipeline.
+// Split in two halves so that a heterogeneous batch can have the requests of all its topologies in flight at once.
+struct SmallRequest {
+    DevicePipeline* pl = nullptr;
+    std::unique_lock<std::mutex> lock;  // the pipeline's staging block is ours until finish()
+    size_t in_al = 0, out_x = 0, out_r = 0;
+};
+static bool small_fits(const fk::Topology& t, uint32_t total) {
+    const size_t in_v = sizeof(double) * (size_t)total * t.n_vars, in_p = sizeof(double) * (size_t)total * t.n_expr;
+    const size_t out_x = sizeof(double) * (size_t)total * t.n_free, out_r = sizeof(fk_report) * (size_t)total;
+    return ((in_v + in_p + 15) & ~size_t(15)) + out_x + out_r <= DevicePipeline::kSmallBytes;
+}
+static int small_enqueue(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars, const double* param, int optimizer,
+                         SmallRequest& rq, std::string* err) {
+    const fk::Topology& t = topo->t;
+    const uint32_t total = hi - lo;
+    DevicePipeline* pl = topo->pipeline_for(device);
+    rq.lock = std::unique_lock<std::mutex>(pl->mu);
+    rq.pl = pl;
+    const size_t in_v = sizeof(double) * (size_t)total * t.n_vars, in_p = sizeof(double) * (size_t)total * t.n_expr;
+    rq.out_x = sizeof(double) * (size_t)total * t.n_free;
+    rq.out_r = sizeof(fk_report) * (size_t)total;
+    rq.in_al = (in_v + in_p + 15) & ~size_t(15);
+    const fk::DevProgram* prog = nullptr;
+    const DeviceProgram* full = nullptr;
+    int rc = topo->program_for(device, &prog, &full);
+    auto give_up = [&](int code) { if (err) *err = g_error; rq.lock.unlock(); rq.pl = nullptr; return code; };
+    if (rc != FK_OK) return give_up(rc);
+    auto bad = [&](cudaError_t e, const char* what) { return give_up(cuda_fail(e, what)); };
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return bad(e, "cudaSetDevice");
+    if (!pl->small_h || !pl->small_d || !pl->small_stream) {
+        // all three or none: a half-initialised block would poison every later call on this topology
+        if (pl->small_h) cudaFreeHost(pl->small_h);
+        if (pl->small_d) cudaFree(pl->small_d);
+        if (pl->small_stream) cudaStreamDestroy(pl->small_stream);
+        pl->small_h = pl->small_d = nullptr;
+        pl->small_stream = nullptr;
+        if ((e = cudaMallocHost((void**)&pl->small_h, DevicePipeline::kSmallBytes)) != cudaSuccess) { pl->small_h = nullptr; return bad(e, "cudaMallocHost"); }
+        if ((e = cudaMalloc((void**)&pl->small_d, DevicePipeline::kSmallBytes)) != cudaSuccess) {
+            cudaFreeHost(pl->small_h); pl->small_h = pl->small_d = nullptr;
+            return bad(e, "cudaMalloc");
+        }
+        if ((e = cudaStreamCreateWithFlags(&pl->small_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            cudaFreeHost(pl->small_h); cudaFree(pl->small_d); pl->small_h = pl->small_d = nullptr; pl->small_stream = nullptr;
+            return bad(e, "cudaStreamCreate");
+        }
+    }
+    std::memcpy(pl->small_h, vars + (size_t)lo * t.n_vars, in_v);
+    if (in_p) std::memcpy(pl->small_h + in_v, param + (size_t)lo * t.n_expr, in_p);
+    if ((e = cudaMemcpyAsync(pl->small_d, pl->small_h, in_v + in_p, cudaMemcpyHostToDevice, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+    const int le = launch_optimizer(*prog, *full, optimizer, total, (const double*)pl->small_d, (const double*)(pl->small_d + in_v),
+                                    (double*)(pl->small_d + rq.in_al), (fk_report*)(pl->small_d + rq.in_al + rq.out_x), pl->small_stream);
+    if (le == (int)cudaErrorInvalidConfiguration && optimizer == 1) { fail(FK_ERR_TOO_LARGE, "the L-BFGS state of one sketch does not fit the tile path"); return give_up(FK_ERR_TOO_LARGE); }
+    if (le != 0) return bad((cudaError_t)le, "launch batched solve kernel");
+    if ((e = cudaMemcpyAsync(pl->small_h + rq.in_al, pl->small_d + rq.in_al, rq.out_x + rq.out_r, cudaMemcpyDeviceToHost, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+    return FK_OK;
+}
+static int small_finish(const fk::Topology& t, uint32_t lo, SmallRequest& rq, double* free_out, fk_report* reports, std::string* err) {
+    if (!rq.pl) return FK_OK;
+    DevicePipeline* pl = rq.pl;
+    int rc = FK_OK;
+    const cudaError_t e = cudaStreamSynchronize(pl->small_stream);
+    if (e != cudaSuccess) {
+        rc = cuda_fail(e, "batch kernel / copy failed");
+        if (err) *err = g_error;
+    } else {
+        std::memcpy(free_out + (size_t)lo * t.n_free, pl->small_h + rq.in_al, rq.out_x);
+        if (reports) std::memcpy(reports + lo, pl->small_h + rq.in_al + rq.out_x, rq.out_r);
+    }
+    rq.lock.unlock();
+    rq.pl = nullptr;
+    return rc;
+}
+
+static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars, const double* param,
+                            double* free_out, fk_report* reports, std::string* err, int optimizer) {
     const fk::Topology& t = topo->t;
     const uint32_t total = hi - lo;
     if (total == 0) return FK_OK;
+    if (small_fits(t, total)) {
+        SmallRequest rq;
+        int rc = small_enqueue(topo, device, lo, hi, vars, param, optimizer, rq, err);
+        if (rc == FK_OK) rc = small_finish(t, lo, rq, free_out, reports, err);
+        return rc;
+    }
     DevicePipeline* pl = topo->pipeline_for(device);
     std::lock_guard<std::mutex> lock(pl->mu);
-    {
-        // Small request: the caller's (pageable) arrays go through ONE pinned staging block -- one copy in, the
-        // kernel, one copy out, one synchronisation -- instead of four pageable copies on the chunk pipeline
-        // (one mixed-primitive sketch: 159 us -> see bench.py `single_sketch`).
-        const size_t in_v = sizeof(double) * (size_t)total * t.n_vars, in_p = sizeof(double) * (size_t)total * t.n_expr;
-        const size_t out_x = sizeof(double) * (size_t)total * t.n_free, out_r = sizeof(fk_report) * (size_t)total;
-        const size_t in_al = (in_v + in_p + 15) & ~size_t(15);
-        if (in_al + out_x + out_r <= DevicePipeline::kSmallBytes) {
-            const fk::DevProgram* prog = nullptr;
-            int rc = topo->program_for(device, &prog);
-            if (rc != FK_OK) { if (err) *err = g_error; return rc; }
-            auto bad = [&](cudaError_t e, const char* what) { int c = cuda_fail(e, what); if (err) *err = g_error; return c; };
-            cudaError_t e = cudaSetDevice(device);
-            if (e != cudaSuccess) return bad(e, "cudaSetDevice");
-            if (!pl->small_h) {
-                if ((e = cudaMallocHost((void**)&pl->small_h, DevicePipeline::kSmallBytes)) != cudaSuccess) return bad(e, "cudaMallocHost");
-                if ((e = cudaMalloc((void**)&pl->small_d, DevicePipeline::kSmallBytes)) != cudaSuccess) return bad(e, "cudaMalloc");
-                if ((e = cudaStreamCreateWithFlags(&pl->small_stream, cudaStreamNonBlocking)) != cudaSuccess) return bad(e, "cudaStreamCreate");
-            }
-            std::memcpy(pl->small_h, vars + (size_t)lo * t.n_vars, in_v);
-            if (in_p) std::memcpy(pl->small_h + in_v, param + (size_t)lo * t.n_expr, in_p);
-            if ((e = cudaMemcpyAsync(pl->small_d, pl->small_h, in_v + in_p, cudaMemcpyHostToDevice, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
-            const int le = fk::launch_batch_lm(*prog, total, (const double*)pl->small_d, (const double*)(pl->small_d + in_v), (double*)(pl->small_d + in_al),
-                                               (fk_report*)(pl->small_d + in_al + out_x), pl->small_stream);
-            if (le != 0) return bad((cudaError_t)le, "launch fk_batch_lm_kernel");
-            if ((e = cudaMemcpyAsync(pl->small_h + in_al, pl->small_d + in_al, out_x + out_r, cudaMemcpyDeviceToHost, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
-            if ((e = cudaStreamSynchronize(pl->small_stream)) != cudaSuccess) return bad(e, "batch kernel / copy failed");
-            std::memcpy(free_out + (size_t)lo * t.n_free, pl->small_h + in_al, out_x);
-            if (reports) std::memcpy(reports + lo, pl->small_h + in_al + out_x, out_r);
-            return FK_OK;
-        }
-    }
     constexpr uint32_t kStreams = DevicePipeline::kStreams;
     // chunks small enough to overlap H2D / kernel / D2H, large enough to fill the machine
     static const uint32_t n_chunks = [] {
@@ -734,7 +820,7 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
         // a plan's buffers are reused only after its previous chunk has fully drained
         if (cudaStreamSynchronize(pl->streams[s]) != cudaSuccess) { rc = fail(FK_ERR_CUDA, "stream sync failed"); break; }
         rc = fk_batch_plan_upload(pl->plans[s], cnt, vars + (size_t)at * t.n_vars, param ? param + (size_t)at * t.n_expr : nullptr, pl->streams[s]);
-        if (rc == FK_OK) rc = fk_batch_plan_run(pl->plans[s], pl->streams[s]);
+        if (rc == FK_OK) rc = optimizer == 1 ? fk_batch_plan_run_lbfgs(pl->plans[s], pl->streams[s]) : fk_batch_plan_run(pl->plans[s], pl->streams[s]);
         if (rc == FK_OK) rc = fk_batch_plan_download(pl->plans[s], free_out + (size_t)at * t.n_free, reports ? reports + at : nullptr, pl->streams[s]);
     }
     for (uint32_t k = 0; k < kStreams; k++)
@@ -798,6 +884,8 @@ int fk_topology_lm_solve(fk_topology* topo, const double* vars, const double* pa
         int rc = topo->sparse_for(cur, &sp, &err);
         if (rc != FK_OK) return fail(rc, err);
         // the caller's free values are the starting point (== `variables` of lm.rs:21)
+        if (!param && t.n_expr) return fail(FK_ERR_INVALID, "null parameter array");
+        std::lock_guard<std::mutex> lock(topo->sparse_mu);
         rc = sp->solve(vars, param, free_values, report, &err);
         return rc == FK_OK ? FK_OK : fail(rc, err);
     }
@@ -840,7 +928,10 @@ int fk_topology_eval(fk_topology* topo, const double* vars, const double* param,
     fk::SparseSolver* sp = nullptr;
     std::string err;
     int rc = topo->sparse_for(cur, &sp, &err);
-    if (rc == FK_OK) rc = sp->eval_once(vars, param, free_values, out_r, out_j, repeats, ms_per_eval, &err);
+    if (rc == FK_OK) {
+        std::lock_guard<std::mutex> lock(topo->sparse_mu);
+        rc = sp->eval_once(vars, param, free_values, out_r, out_j, repeats, ms_per_eval, &err);
+    }
     return rc == FK_OK ? FK_OK : fail(rc, err);
 }
 
@@ -857,84 +948,239 @@ int fk_topology_last_timing(fk_topology* topo, float* out8) {
 }
 
 // ---- general entry points ------------------------------------------------------------------------------
+// "Symbolic analysis once per topology" for the callers that hand over flattened problems (fk_lm_solve,
+// fk_lm_solve_batch, fk_system_solve*): a process-wide LRU cache of fk_topology objects keyed by the structural
+// content of the problem (sizes, kinds, indices, free set, row list).  The reference repeats the analysis on every
+// LM call (fiksi/src/solve/lm.rs:98-104); an interactive solver re-solves the same sketch over and over.  Entries
+// are shared_ptrs: an evicted topology lives until the solves that use it have returned.
+namespace {
+
+struct TopologyCache {
+    struct Entry { uint64_t sig; std::shared_ptr<fk_topology> topo; };
+    std::mutex mu;
+    std::list<Entry> lru;  // front = most recently used
+    size_t capacity = [] {
+        const char* e = std::getenv("FK_TOPOLOGY_CACHE");
+        const int v = e ? std::atoi(e) : 64;
+        return (size_t)std::max(0, v);
+    }();
+    uint64_t hits = 0, misses = 0;
+};
+TopologyCache& topology_cache() {
+    static TopologyCache* c = new TopologyCache();  // never destroyed: CUDA may be gone by static-destruction time
+    return *c;
+}
+
+uint64_t structural_signature(const fk_problem& p) {
+    uint64_t sig = 1469598103934665603ull;
+    auto mixb = [&](const void* d, size_t bytes) {
+        const unsigned char* c = (const unsigned char*)d;
+        for (size_t k = 0; k < bytes; k++) sig = (sig ^ c[k]) * 1099511628211ull;
+    };
+    const uint32_t hdr[4] = {p.n_vars, p.n_expr, p.n_free, p.n_rows};
+    mixb(hdr, sizeof hdr);
+    if (p.n_expr) { mixb(p.kind, p.n_expr); mixb(p.idx, 16 * (size_t)p.n_expr); }
+    if (p.n_free) mixb(p.free_vars, 4 * (size_t)p.n_free);
+    if (p.n_rows) mixb(p.rows, 4 * (size_t)p.n_rows);
+    return sig;
+}
+bool same_structure(const fk::Topology& t, const fk_problem& p) {
+    return t.n_vars == p.n_vars && t.n_expr == p.n_expr && t.n_free == p.n_free && t.n_rows == p.n_rows &&
+           (!p.n_expr || (!std::memcmp(t.kind.data(), p.kind, p.n_expr) && !std::memcmp(t.idx.data(), p.idx, 16 * (size_t)p.n_expr))) &&
+           (!p.n_free || !std::memcmp(t.free_vars.data(), p.free_vars, 4 * (size_t)p.n_free)) &&
+           (!p.n_rows || !std::memcmp(t.rows.data(), p.rows, 4 * (size_t)p.n_rows));
+}
+bool problem_arrays_ok(const fk_problem& p) {
+    return !((p.n_vars && !p.vars) || (p.n_expr && (!p.kind || !p.idx)) || (p.n_free && !p.free_vars) || (p.n_rows && !p.rows));
+}
+
+std::shared_ptr<fk_topology> cache_lookup(uint64_t sig, const fk_problem& p) {
+    TopologyCache& c = topology_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (auto it = c.lru.begin(); it != c.lru.end(); ++it)
+        if (it->sig == sig && same_structure(it->topo->t, p)) {
+            c.lru.splice(c.lru.begin(), c.lru, it);
+            c.hits++;
+            return c.lru.front().topo;
+        }
+    c.misses++;
+    return nullptr;
+}
+void cache_insert(uint64_t sig, const std::shared_ptr<fk_topology>& topo) {
+    TopologyCache& c = topology_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.capacity == 0) return;
+    c.lru.push_front({sig, topo});
+    while (c.lru.size() > c.capacity) c.lru.pop_back();
+    // large single systems keep hundreds of megabytes of factor storage on the device: at most four of them stay
+    size_t large = 0;
+    for (auto it = c.lru.begin(); it != c.lru.end();) {
+        if (it->topo->t.path == 2 && ++large > 4) it = c.lru.erase(it);
+        else ++it;
+    }
+}
+
+}  // namespace
+
+void fk_topology_cache_configure(uint32_t capacity) {
+    TopologyCache& c = topology_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.capacity = capacity;
+    while (c.lru.size() > c.capacity) c.lru.pop_back();
+}
+void fk_topology_cache_clear(void) {
+    TopologyCache& c = topology_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    c.lru.clear();
+}
+void fk_topology_cache_stats(uint64_t* hits, uint64_t* misses, uint32_t* entries) {
+    TopologyCache& c = topology_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (hits) *hits = c.hits;
+    if (misses) *misses = c.misses;
+    if (entries) *entries = (uint32_t)c.lru.size();
+}
+
 int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* const* free_values, fk_report* reports,
                       int n_gpus) {
     if (n == 0) return FK_OK;
     if (!problems || !free_values) return fail(FK_ERR_INVALID, "null argument");
-    // group by topology: build each problem's topology key, reuse the first topology of a group
+    const int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (n_gpus <= 0 || n_gpus > ndev) n_gpus = ndev;
+    // ---- group the problems by topology -----------------------------------------------------------------
     struct Group {
-        std::unique_ptr<fk_topology, void (*)(fk_topology*)> topo{nullptr, fk_topology_destroy};
+        uint64_t sig = 0;
+        std::shared_ptr<fk_topology> topo;
         std::vector<uint32_t> members;
+        int rc = FK_OK;
+        std::string err;
+        // staging of the group's uniform batch
+        std::vector<double> vars, param, out;
+        std::vector<fk_report> reps;
+        SmallRequest small;
+        int device = 0;
     };
     std::vector<Group> groups;
     std::multimap<uint64_t, size_t> by_sig;
     for (uint32_t i = 0; i < n; i++) {
         const fk_problem* p = problems[i];
         if (!p || !free_values[i]) return fail(FK_ERR_INVALID, "null problem in batch");
-        // cheap structural signature (same mixing as Topology::build would be overkill here)
-        uint64_t sig = 1469598103934665603ull;
-        auto mixb = [&](const void* d, size_t bytes) {
-            const unsigned char* c = (const unsigned char*)d;
-            for (size_t k = 0; k < bytes; k++) sig = (sig ^ c[k]) * 1099511628211ull;
-        };
-        uint32_t hdr[4] = {p->n_vars, p->n_expr, p->n_free, p->n_rows};
-        mixb(hdr, sizeof hdr);
-        if (p->n_expr) { mixb(p->kind, p->n_expr); mixb(p->idx, 16 * (size_t)p->n_expr); }
-        if (p->n_free) mixb(p->free_vars, 4 * (size_t)p->n_free);
-        if (p->n_rows) mixb(p->rows, 4 * (size_t)p->n_rows);
+        if (!problem_arrays_ok(*p)) return fail(FK_ERR_INVALID, "null array in fk_problem");
+        const uint64_t sig = structural_signature(*p);
         size_t gi = SIZE_MAX;
         auto range = by_sig.equal_range(sig);
         for (auto it = range.first; it != range.second; ++it) {
-            const fk::Topology& t = groups[it->second].topo->t;
-            if (t.n_vars == p->n_vars && t.n_expr == p->n_expr && t.n_free == p->n_free && t.n_rows == p->n_rows &&
-                (!p->n_expr || (!std::memcmp(t.kind.data(), p->kind, p->n_expr) && !std::memcmp(t.idx.data(), p->idx, 16 * (size_t)p->n_expr))) &&
-                (!p->n_free || !std::memcmp(t.free_vars.data(), p->free_vars, 4 * (size_t)p->n_free)) &&
-                (!p->n_rows || !std::memcmp(t.rows.data(), p->rows, 4 * (size_t)p->n_rows))) {
+            const fk_problem& q = *problems[groups[it->second].members[0]];
+            const fk_problem& pp = *p;
+            if (q.n_vars == pp.n_vars && q.n_expr == pp.n_expr && q.n_free == pp.n_free && q.n_rows == pp.n_rows &&
+                (!pp.n_expr || (!std::memcmp(q.kind, pp.kind, pp.n_expr) && !std::memcmp(q.idx, pp.idx, 16 * (size_t)pp.n_expr))) &&
+                (!pp.n_free || !std::memcmp(q.free_vars, pp.free_vars, 4 * (size_t)pp.n_free)) &&
+                (!pp.n_rows || !std::memcmp(q.rows, pp.rows, 4 * (size_t)pp.n_rows))) {
                 gi = it->second;
                 break;
             }
         }
         if (gi == SIZE_MAX) {
-            fk_topology* t = nullptr;
-            int rc = fk_topology_create(p, &t);
-            if (rc != FK_OK) return rc;
             groups.emplace_back();
-            groups.back().topo.reset(t);
+            groups.back().sig = sig;
             gi = groups.size() - 1;
             by_sig.emplace(sig, gi);
         }
         groups[gi].members.push_back(i);
+    }
+    // ---- topologies: cache first, the misses are analysed on host threads ------------------------------------
+    std::vector<size_t> missing;
+    for (size_t g = 0; g < groups.size(); g++) {
+        groups[g].topo = cache_lookup(groups[g].sig, *problems[groups[g].members[0]]);
+        if (!groups[g].topo) missing.push_back(g);
+    }
+    if (!missing.empty()) {
+        auto build_one = [&](size_t g) {
+            fk_topology* t = nullptr;
+            groups[g].rc = fk_topology_create(problems[groups[g].members[0]], &t);
+            if (groups[g].rc != FK_OK) groups[g].err = g_error;
+            else groups[g].topo.reset(t, fk_topology_destroy);
+        };
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const size_t workers = std::min<size_t>(missing.size(), hw);
+        if (workers <= 1) {
+            for (size_t g : missing) build_one(g);
+        } else {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> pool;
+            for (size_t w = 0; w < workers; w++)
+                pool.emplace_back([&] {
+                    for (size_t k = next++; k < missing.size(); k = next++) build_one(missing[k]);
+                });
+            for (auto& th : pool) th.join();
+        }
+        for (size_t g : missing) {
+            if (groups[g].rc != FK_OK) return fail(groups[g].rc, groups[g].err);
+            cache_insert(groups[g].sig, groups[g].topo);
+        }
+    }
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    // ---- solve: small groups of all topologies are in flight together, one stream per (topology, device) ------
+    // With several devices and at least as many groups, whole groups go to devices round robin; otherwise every
+    // large group is sharded by sketch over the devices (fk_batch_solve).
+    const bool groups_to_devices = n_gpus > 1 && groups.size() >= (size_t)n_gpus;
+    size_t rr = 0;
+    int first_rc = FK_OK;
+    std::string first_err;
+    auto note = [&](int rc, const std::string& e) { if (rc != FK_OK && first_rc == FK_OK) { first_rc = rc; first_err = e; } };
+    for (Group& gr : groups) {
+        const fk::Topology& t = gr.topo->t;
+        const size_t cnt = gr.members.size();
+        if (t.path == 2) continue;  // large systems below
+        gr.vars.resize(cnt * t.n_vars); gr.param.resize(cnt * std::max<uint32_t>(t.n_expr, 1)); gr.out.resize(cnt * std::max<uint32_t>(t.n_free, 1));
+        gr.reps.resize(cnt);
+        for (size_t k = 0; k < cnt; k++) {
+            const fk_problem* p = problems[gr.members[k]];
+            if (t.n_vars) std::memcpy(&gr.vars[k * t.n_vars], p->vars, sizeof(double) * t.n_vars);
+            for (uint32_t f = 0; f < t.n_free; f++) gr.vars[k * t.n_vars + t.free_vars[f]] = free_values[gr.members[k]][f];
+            if (t.n_expr) {
+                if (p->param) std::memcpy(&gr.param[k * t.n_expr], p->param, sizeof(double) * t.n_expr);
+                else std::fill(gr.param.begin() + k * t.n_expr, gr.param.begin() + (k + 1) * t.n_expr, 0.0);
+            }
+        }
+        gr.device = groups_to_devices ? (int)(rr++ % (size_t)n_gpus) : cur;
+        if (small_fits(t, (uint32_t)cnt)) {
+            std::string e;
+            note(small_enqueue(gr.topo.get(), gr.device, 0, (uint32_t)cnt, gr.vars.data(), gr.param.data(), 0, gr.small, &e), e);
+        }
     }
     for (Group& gr : groups) {
         const fk::Topology& t = gr.topo->t;
         const size_t cnt = gr.members.size();
         if (t.path == 2) {  // large systems: one after the other through the global sparse path
             for (uint32_t i : gr.members) {
-                int rc = fk_topology_lm_solve(gr.topo.get(), problems[i]->vars, problems[i]->param, free_values[i],
-                                              reports ? &reports[i] : nullptr);
-                if (rc != FK_OK) return rc;
+                int rc = fk_topology_lm_solve(gr.topo.get(), problems[i]->vars, problems[i]->param, free_values[i], reports ? &reports[i] : nullptr);
+                if (rc != FK_OK) note(rc, g_error);
             }
             continue;
         }
-        std::vector<double> vars(cnt * t.n_vars), param(cnt * std::max<uint32_t>(t.n_expr, 1)), out(cnt * std::max<uint32_t>(t.n_free, 1));
-        std::vector<fk_report> reps(cnt);
-        for (size_t k = 0; k < cnt; k++) {
-            const fk_problem* p = problems[gr.members[k]];
-            if (t.n_vars) std::memcpy(&vars[k * t.n_vars], p->vars, sizeof(double) * t.n_vars);
-            for (uint32_t f = 0; f < t.n_free; f++) vars[k * t.n_vars + t.free_vars[f]] = free_values[gr.members[k]][f];
-            if (t.n_expr) {
-                if (p->param) std::memcpy(&param[k * t.n_expr], p->param, sizeof(double) * t.n_expr);
-                else std::fill(param.begin() + k * t.n_expr, param.begin() + (k + 1) * t.n_expr, 0.0);
-            }
+        int rc = FK_OK;
+        std::string e;
+        if (gr.small.pl) {
+            rc = small_finish(t, 0, gr.small, gr.out.data(), gr.reps.data(), &e);
+        } else if (small_fits(t, (uint32_t)cnt)) {
+            continue;  // its enqueue failed: already noted
+        } else if (groups_to_devices || n_gpus == 1) {
+            rc = run_device_range(gr.topo.get(), gr.device, 0, (uint32_t)cnt, gr.vars.data(), gr.param.data(), gr.out.data(), gr.reps.data(), &e, 0);
+        } else {
+            rc = fk_batch_solve(gr.topo.get(), (uint32_t)cnt, gr.vars.data(), gr.param.data(), gr.out.data(), gr.reps.data(), n_gpus);
+            if (rc != FK_OK) e = g_error;
         }
-        int rc = fk_batch_solve(gr.topo.get(), (uint32_t)cnt, vars.data(), param.data(), out.data(), reps.data(), n_gpus);
-        if (rc != FK_OK) return rc;
+        if (rc != FK_OK) { note(rc, e); continue; }
         for (size_t k = 0; k < cnt; k++) {
-            std::memcpy(free_values[gr.members[k]], &out[k * t.n_free], sizeof(double) * t.n_free);
-            if (reports) reports[gr.members[k]] = reps[k];
+            std::memcpy(free_values[gr.members[k]], &gr.out[k * t.n_free], sizeof(double) * t.n_free);
+            if (reports) reports[gr.members[k]] = gr.reps[k];
         }
     }
-    return FK_OK;
+    if (cudaSetDevice(cur) != cudaSuccess) cudaGetLastError();
+    return first_rc == FK_OK ? FK_OK : fail(first_rc, first_err);
 }
 
 int fk_lm_solve(const fk_problem* problem, double* free_values, fk_report* report) {

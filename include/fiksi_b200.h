@@ -230,6 +230,19 @@ FK_API int fk_get_lm_kernel(void);
  * sketch, *table_words = 16-bit words of its parameter block.  Any pointer may be null. */
 FK_API int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint32_t* state_doubles, uint32_t* table_words);
 
+/* Which kernel a batched LM solve of n_sketches sketches of this topology launches under the current
+ * fk_set_lm_kernel choice: 1 sketch-per-thread, 0 tile kernel (negative: error). */
+FK_API int fk_topology_batch_kernel(const fk_topology* topo, uint32_t n_sketches);
+
+/* Topology cache of fk_lm_solve / fk_lm_solve_batch / fk_system_solve*: the symbolic analysis of a flattened
+ * problem (the reference repeats it on every LM call, fiksi/src/solve/lm.rs:98-104) is kept in a process-wide
+ * LRU keyed by the problem's structure, so that re-solving a sketch costs no analysis.  Default capacity 64
+ * topologies (environment FK_TOPOLOGY_CACHE; 0 disables).  Cached topologies keep their device tables and
+ * staging buffers; _clear releases them. */
+FK_API void fk_topology_cache_configure(uint32_t capacity);
+FK_API void fk_topology_cache_clear(void);
+FK_API void fk_topology_cache_stats(uint64_t* hits, uint64_t* misses, uint32_t* entries);
+
 /* Blocks until all work issued for this plan's device has finished. */
 FK_API int fk_batch_plan_sync(fk_batch_plan* plan);
 
