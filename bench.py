@@ -221,31 +221,51 @@ def main():
     solved = float(np.mean(rep["ssr"] < 1e-8))
     fact = float(rep["factorizations"].sum())  # (the host buffers are reused by the measurements below)
 
-    # ---- end-to-end through the host-buffer C-ABI call ------------------------------------------------
-    for _ in range(2):
+    # ---- end-to-end through the host-buffer C-ABI calls ------------------------------------------------------
+    # (1) the System::solve-level call: RAW variables in, scale + seeded perturbation + LM + write-back on the device,
+    #     UNSCALED solved variables out (fk_batch_system_solve; the copies of a truss share one row of distances);
+    # (2) the levenberg_marquardt-level call on inputs the host has already scaled and perturbed (fk_batch_solve_device).
+    hraw = torch.from_numpy(w.raw_vars).pin_memory()
+    shared_row = bool(np.all(w.raw_param == w.raw_param[0]))
+    hrawp = torch.from_numpy(np.ascontiguousarray(w.raw_param[0] if shared_row else w.raw_param)).pin_memory()
+
+    def e2e_system():
+        topo.batch_system_solve_into(local_rank, n, hraw.data_ptr(), hrawp.data_ptr(), hout.data_ptr(), hrep.data_ptr(), shared_param=shared_row)
+
+    def e2e_prepared():
         topo.batch_solve_into(local_rank, n, hv.data_ptr(), hp.data_ptr(), hout.data_ptr(), hrep.data_ptr())
-    barrier()
     e2e_steps = max(3, args.steps)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        topo.batch_solve_into(local_rank, n, hv.data_ptr(), hp.data_ptr(), hout.data_ptr(), hrep.data_ptr())
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_secs = []
+    for fn in (e2e_system, e2e_prepared):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        barrier()
+        e2e_secs.append(time.perf_counter() - t0)
+    e2e_s, e2e_prep_s = e2e_secs
+    rep_sys = hrep.numpy().view(fk.REPORT_DTYPE).reshape(-1).copy()
+    e2e_system()
+    same_as_resident = bool(np.array_equal(hrep.numpy().view(fk.REPORT_DTYPE).reshape(-1)["trace_hash"], rep["trace_hash"]))
+    del rep_sys
 
     # ---- host-copy ceiling: the same bytes as one e2e step, H2D and D2H concurrently on two streams, every rank at
     # once (what the box's host<->device path can carry when nothing is computed) ---------------------------------
-    h2d = 8 * n * (info["n_vars"] + info["n_expr"])
+    h2d = 8 * n * info["n_vars"] + 8 * info["n_expr"] * (1 if shared_row else n)
     d2h = 8 * n * info["n_free"] + 40 * n
+    h2d_prepared = 8 * n * (info["n_vars"] + info["n_expr"])
     dv = torch.empty(v.shape, dtype=torch.float64, device="cuda")
-    dp = torch.empty(p.shape, dtype=torch.float64, device="cuda")
+    dp = torch.empty(hrawp.shape, dtype=torch.float64, device="cuda")
     dout = torch.empty((n, info["n_free"]), dtype=torch.float64, device="cuda")
     drep = torch.empty((n, 40), dtype=torch.uint8, device="cuda")
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     def copy_step():
         with torch.cuda.stream(s_in):
-            dv.copy_(hv, non_blocking=True)
-            dp.copy_(hp, non_blocking=True)
+            dv.copy_(hraw, non_blocking=True)
+            dp.copy_(hrawp, non_blocking=True)
         with torch.cuda.stream(s_out):
             hout.copy_(dout, non_blocking=True)
             hrep.copy_(drep, non_blocking=True)
@@ -259,10 +279,10 @@ def main():
     copy_s = time.perf_counter() - t0
     del dv, dp, dout, drep
 
-    t = torch.tensor([total_ms, e2e_s, copy_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s, copy_s, e2e_prep_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, copy_s = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_s, copy_s, e2e_prep_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / e2e_s
@@ -282,7 +302,12 @@ def main():
                    "fraction_converged": solved, "wall_s_timed_region": wall,
                    "host_affinity": f"rank bound to the {bound} cores NVML reports local to its GPU" if bound else "unbound"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "fk_batch_solve_device (pinned host buffers, 3-stream chunk pipeline)",
+                "steps": e2e_steps,
+                "api": "fk_batch_system_solve: raw variables in pinned host memory -> scale, seeded perturbation, LM solve and write-back on "
+                       "the device -> unscaled solved variables + reports in pinned host memory (3-stream chunk pipeline)",
+                "same_traces_as_device_resident_run": same_as_resident,
+                "prepared_inputs": {"value": world * n * e2e_steps / e2e_prep_s, "unit": UNIT, "h2d_bytes_per_step": h2d_prepared,
+                                    "api": "fk_batch_solve_device on inputs scaled and perturbed by the host (levenberg_marquardt-level call)"},
                 "copy_ceiling": {"value": copy_ceiling, "unit": UNIT, "gb_per_s_all_ranks": world * (h2d + d2h) * e2e_steps / copy_s / 1e9,
                                  "how": "the step's H2D and D2H bytes copied concurrently on two streams by every rank, nothing computed"},
                 "frac_of_copy_ceiling": e2e_value / copy_ceiling},

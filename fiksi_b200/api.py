@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import (FkProblem, FkReport, FkTopologyInfo, REPORT_DTYPE, check, lib, make_problem, ptr)
+from ._lib import (FkPrepareOpts, FkProblem, FkReport, FkTopologyInfo, REPORT_DTYPE, check, lib, make_problem, ptr)
 
 
 class Topology:
@@ -113,6 +113,34 @@ class Topology:
         check(lib().fk_batch_solve(self._h, n, ptr(vars_, C.c_double), ptr(param, C.c_double), ptr(out, C.c_double),
                                    reports.ctypes.data_as(C.POINTER(FkReport)), n_gpus))
         return out, reports
+
+    def batch_system_solve(self, raw_vars, raw_param, perturb=True, perturb_vars=None, shared_param=False, device=0, seed=42):
+        """fk_batch_system_solve: System::solve for n single-component sketches, scale / perturbation / write-back on
+        the device.  raw_param is [n][n_expr], or one row with shared_param.  Returns (unscaled free values, scales, reports)."""
+        raw_vars = np.ascontiguousarray(raw_vars, dtype=np.float64)
+        raw_param = np.ascontiguousarray(raw_param, dtype=np.float64)
+        n = raw_vars.shape[0]
+        out = np.zeros((n, self.info["n_free"]), dtype=np.float64)
+        scales = np.zeros(n, dtype=np.float64)
+        reports = np.zeros(n, dtype=REPORT_DTYPE)
+        o = FkPrepareOpts()
+        o.flags = (1 if shared_param else 0) | (2 if perturb else 0)
+        o.seed = seed
+        keep = None
+        if perturb_vars is not None:
+            keep = np.ascontiguousarray(perturb_vars, dtype=np.uint32)
+            o.n_perturb, o.perturb_vars = len(keep), ptr(keep, C.c_uint32)
+        check(lib().fk_batch_system_solve(self._h, device, n, ptr(raw_vars, C.c_double), ptr(raw_param, C.c_double), C.byref(o),
+                                          ptr(out, C.c_double), ptr(scales, C.c_double), reports.ctypes.data_as(C.POINTER(FkReport))))
+        return out, scales, reports
+
+    def batch_system_solve_into(self, device, n, raw_vars_ptr, raw_param_ptr, out_ptr, rep_ptr, shared_param=False, perturb=True):
+        """fk_batch_system_solve on caller-owned (ideally pinned) host buffers given as addresses."""
+        o = FkPrepareOpts()
+        o.flags = (1 if shared_param else 0) | (2 if perturb else 0)
+        o.seed = 42
+        check(lib().fk_batch_system_solve(self._h, device, n, C.c_void_p(raw_vars_ptr), C.c_void_p(raw_param_ptr), C.byref(o),
+                                          C.c_void_p(out_ptr), None, C.c_void_p(rep_ptr)))
 
     def batch_solve_into(self, device, n, vars_ptr, param_ptr, out_ptr, rep_ptr):
         """fk_batch_solve_device on caller-owned (ideally pinned) host buffers given as addresses."""

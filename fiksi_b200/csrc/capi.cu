@@ -169,6 +169,21 @@ struct AnalyzePool {
     }
 };
 
+// Device tables of assemble::solve's pre-processing for one (topology, device): expression kinds, the variables that
+// draw from the solve's generator (ascending) and the draws themselves (fiksi/src/rand.rs:24-39, two per variable).
+struct PrepareTables {
+    int device = -1;
+    std::vector<uint32_t> perturb_vars;
+    uint32_t seed = 0;
+    uint8_t* d_kind = nullptr;
+    uint32_t* d_perturb = nullptr;
+    double* d_draws = nullptr;
+    ~PrepareTables() {
+        if (device >= 0) cudaSetDevice(device);
+        cudaFree(d_kind); cudaFree(d_perturb); cudaFree(d_draws);
+    }
+};
+
 struct fk_topology {
     fk::Topology t;
     std::mutex mu;
@@ -177,6 +192,7 @@ struct fk_topology {
     std::map<int, std::unique_ptr<fk::SparseSolver>> sparse;  // path 2: one solver per device
     std::mutex sparse_mu;               // a SparseSolver owns one set of work vectors and CUDA graphs: one solve at a time
     std::map<int, std::unique_ptr<struct AnalyzePool>> analyze_pools;  // fk_batch_analyze: tables + grow-only buffers
+    std::map<int, std::unique_ptr<struct PrepareTables>> prepare_tables;  // fk_batch_system_solve: kinds, perturbation list, draws
     std::unique_ptr<fk_topology> latency_twin;  // same topology with 32 lanes per sketch: single-system solves
     bool twin_tried = false;
     std::mutex sp_mu;                   // SinglePass plan: one sub-topology per strongly connected set
@@ -230,10 +246,12 @@ struct fk_batch_plan {
     const DeviceProgram* full = nullptr;
     double *d_vars = nullptr, *d_params = nullptr, *d_out = nullptr, *d_er = nullptr, *d_ej = nullptr;
     fk_report* d_rep = nullptr;
+    double *d_raw_vars = nullptr, *d_raw_param = nullptr, *d_scales = nullptr;  // fk_batch_system_solve: unscaled input, scale per sketch
     uint64_t launches = 0;
     ~fk_batch_plan() {
         cudaSetDevice(device);
         cudaFree(d_vars); cudaFree(d_params); cudaFree(d_out); cudaFree(d_er); cudaFree(d_ej); cudaFree(d_rep);
+        cudaFree(d_raw_vars); cudaFree(d_raw_param); cudaFree(d_scales);
     }
 };
 
@@ -697,6 +715,23 @@ void fk_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+// Chunk of the host-buffer pipelines: about an eighth of the request (copies of one chunk overlap the kernels of the
+// others), at least 2,048 sketches, and whole waves of the sketch-per-thread kernel when that is the kernel in use.
+static uint32_t pipeline_chunk(fk_topology* topo, int device, uint32_t total, uint32_t n_chunks) {
+    uint32_t chunk = std::min(total, std::max<uint32_t>(2048, (total + n_chunks - 1) / n_chunks));
+    const fk::DevProgram* prog = nullptr;
+    if (topo->program_for(device, &prog) == FK_OK && fk::batch_lm_uses_sketch_kernel(*prog, total)) {
+        static int sms[64] = {0};
+        if (device >= 0 && device < 64 && sms[device] == 0) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) sms[device] = v;
+        }
+        const uint32_t wave = fk::sketch_kernel_wave(*prog->sketch_prog, (device >= 0 && device < 64 && sms[device]) ? sms[device] : 148);
+        if (wave && chunk > wave / 2) chunk = std::min(total, ((chunk + wave - 1) / wave) * wave);
+    }
+    return chunk;
+}
+
 // ---- host-buffer batch: shard by sketch over the devices, pipeline chunks per device ----------------
 static int launch_optimizer(const fk::DevProgram& prog, const DeviceProgram& full, int optimizer, uint32_t n, const double* vars,
                             const double* params, double* out, fk_report* reps, cudaStream_t st) {
@@ -800,7 +835,8 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
         const int v = e ? std::atoi(e) : 0;
         return (uint32_t)(v >= 1 && v <= 256 ? v : 8);
     }();
-    uint32_t chunk = std::min(total, std::max<uint32_t>(2048, (total + n_chunks - 1) / n_chunks));
+    uint32_t chunk = optimizer == 0 ? pipeline_chunk(topo, device, total, n_chunks)
+                                    : std::min(total, std::max<uint32_t>(2048, (total + n_chunks - 1) / n_chunks));
     int rc = FK_OK;
     if (pl->chunk < chunk) {
         pl->release();
@@ -812,7 +848,7 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
         if (rc == FK_OK) pl->chunk = chunk;
         else pl->release();
     } else {
-        chunk = pl->chunk >= total ? std::min(total, std::max<uint32_t>(2048, (total + n_chunks - 1) / n_chunks)) : pl->chunk;
+        if (pl->chunk < total) chunk = std::min(chunk, pl->chunk);  // (plans sized by an earlier, smaller request)
     }
     uint32_t s = 0;
     for (uint32_t at = lo; at < hi && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
@@ -827,6 +863,102 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
         if (pl->streams[k] && cudaStreamSynchronize(pl->streams[k]) != cudaSuccess && rc == FK_OK)
             rc = cuda_fail(cudaGetLastError(), "batch kernel / copy failed");
     if (rc != FK_OK && err) *err = g_error;
+    return rc;
+}
+
+// ---- System::solve level batch: scale, perturbation and write-back on the device -----------------------------
+static int prepare_tables_for(fk_topology* topo, int device, const fk_prepare_opts& o, PrepareTables** out) {
+    const fk::Topology& t = topo->t;
+    std::lock_guard<std::mutex> lock(topo->mu);
+    auto& p = topo->prepare_tables[device];
+    std::vector<uint32_t> list;
+    if (o.flags & FK_PREP_PERTURB) {
+        if (o.perturb_vars) list.assign(o.perturb_vars, o.perturb_vars + o.n_perturb);
+        else list = t.free_vars;
+        for (size_t q = 0; q < list.size(); q++)
+            if (list[q] >= t.n_vars || (q && list[q] <= list[q - 1]))
+                return fail(FK_ERR_INVALID, "perturbed variables must be in range, ascending and distinct");
+    }
+    if (p && p->perturb_vars == list && p->seed == o.seed) { *out = p.get(); return FK_OK; }
+    std::unique_ptr<PrepareTables> q(new PrepareTables());
+    CU(cudaSetDevice(device));
+    q->device = device; q->perturb_vars = list; q->seed = o.seed;
+    std::vector<double> draws(2 * list.size() + 1, 0.0);
+    uint32_t st = o.seed;
+    for (size_t k = 0; k < 2 * list.size(); k++) {  // rand.rs:24-39
+        st = st * 1664525u + 1013904223u;
+        draws[k] = (1.0 / 4294967295.0) * (double)st;
+    }
+    CU(cudaMalloc(&q->d_kind, std::max<uint32_t>(t.n_expr, 1)));
+    CU(cudaMalloc(&q->d_perturb, sizeof(uint32_t) * std::max<size_t>(list.size(), 1)));
+    CU(cudaMalloc(&q->d_draws, sizeof(double) * draws.size()));
+    if (t.n_expr) CU(cudaMemcpy(q->d_kind, t.kind.data(), t.n_expr, cudaMemcpyHostToDevice));
+    if (!list.empty()) CU(cudaMemcpy(q->d_perturb, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(q->d_draws, draws.data(), sizeof(double) * draws.size(), cudaMemcpyHostToDevice));
+    p = std::move(q);
+    *out = p.get();
+    return FK_OK;
+}
+
+int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, const double* raw_vars, const double* raw_param,
+                          const fk_prepare_opts* opts, double* free_out, double* scales_out, fk_report* reports) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo || !opts) return fail(FK_ERR_INVALID, "null argument");
+    if (n == 0) return FK_OK;
+    const fk::Topology& t = topo->t;
+    if (!raw_vars || !free_out || (!raw_param && t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
+    if (t.path == 2) return fail(FK_ERR_TOO_LARGE, "topology needs the global sparse path; use fk_system_solve");
+    const int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    PrepareTables* pt = nullptr;
+    int rc = prepare_tables_for(topo, device, *opts, &pt);
+    if (rc != FK_OK) return rc;
+    const bool shared = (opts->flags & FK_PREP_SHARED_PARAM) != 0;
+    DevicePipeline* pl = topo->pipeline_for(device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    constexpr uint32_t kStreams = DevicePipeline::kStreams;
+    uint32_t chunk = pipeline_chunk(topo, device, n, 8);
+    if (pl->chunk < chunk) {
+        pl->release();
+        for (uint32_t s = 0; s < kStreams && rc == FK_OK; s++) {
+            rc = fk_batch_plan_create(topo, chunk, device, &pl->plans[s]);
+            if (rc == FK_OK && cudaStreamCreateWithFlags(&pl->streams[s], cudaStreamNonBlocking) != cudaSuccess) rc = fail(FK_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        if (rc == FK_OK) pl->chunk = chunk;
+        else { pl->release(); return rc; }
+    }
+    CU(cudaSetDevice(device));
+    for (uint32_t s = 0; s < kStreams; s++) {  // unscaled input / scale buffers of the plans, on first use
+        fk_batch_plan* p = pl->plans[s];
+        if (!p->d_raw_vars) CU(cudaMalloc(&p->d_raw_vars, sizeof(double) * std::max<size_t>(1, (size_t)p->capacity * t.n_vars)));
+        if (!p->d_raw_param) CU(cudaMalloc(&p->d_raw_param, sizeof(double) * std::max<size_t>(1, (size_t)p->capacity * t.n_expr)));
+        if (!p->d_scales) CU(cudaMalloc(&p->d_scales, sizeof(double) * p->capacity));
+    }
+    uint32_t s = 0;
+    for (uint32_t at = 0; at < n && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
+        const uint32_t cnt = std::min(chunk, n - at);
+        fk_batch_plan* p = pl->plans[s];
+        cudaStream_t st = pl->streams[s];
+        CU(cudaStreamSynchronize(st));  // the plan's buffers are reused only after its previous chunk has drained
+        p->n = cnt;
+        if (t.n_vars) CU(cudaMemcpyAsync(p->d_raw_vars, raw_vars + (size_t)at * t.n_vars, sizeof(double) * (size_t)cnt * t.n_vars, cudaMemcpyHostToDevice, st));
+        if (t.n_expr) {
+            if (shared) CU(cudaMemcpyAsync(p->d_raw_param, raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemcpyAsync(p->d_raw_param, raw_param + (size_t)at * t.n_expr, sizeof(double) * (size_t)cnt * t.n_expr, cudaMemcpyHostToDevice, st));
+        }
+        int e = fk::launch_batch_prepare(cnt, t.n_vars, t.n_expr, pt->d_kind, shared, (uint32_t)pt->perturb_vars.size(), pt->d_perturb, pt->d_draws,
+                                         p->d_raw_vars, p->d_raw_param, p->d_vars, p->d_params, p->d_scales, st);
+        if (e == 0) e = fk::launch_batch_lm(*p->prog, cnt, p->d_vars, p->d_params, p->d_out, p->d_rep, st);
+        if (e == 0) e = fk::launch_batch_unscale(cnt, t.n_free, p->d_scales, p->d_out, st);
+        if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_system_solve kernels");
+        p->launches += 3;
+        if (t.n_free) CU(cudaMemcpyAsync(free_out + (size_t)at * t.n_free, p->d_out, sizeof(double) * (size_t)cnt * t.n_free, cudaMemcpyDeviceToHost, st));
+        if (scales_out) CU(cudaMemcpyAsync(scales_out + at, p->d_scales, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+        if (reports) CU(cudaMemcpyAsync(reports + at, p->d_rep, sizeof(fk_report) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (uint32_t k = 0; k < kStreams; k++)
+        if (pl->streams[k]) CU(cudaStreamSynchronize(pl->streams[k]));
     return rc;
 }
 

@@ -1082,6 +1082,95 @@ int launch_transpose_reports(const fk_report* in, fk_report* out, uint32_t n_ske
     return (int)cudaGetLastError();
 }
 
+// ---- assemble::solve's pre- and post-processing on the device -------------------------------------
+// One thread per sketch, every sum in the reference's order (fiksi/src/utils.rs:12-19 via assemble/mod.rs:32-44:
+// all variables left to right, then the distance parameters in expression order), one IEEE reciprocal, then
+// variables * recip, recip * distance (expressions.rs:195-211) and the seeded perturbation of the listed variables
+// (assemble/mod.rs:113-124; the generator is re-seeded per solve, so all sketches share one vector of draws).
+// Bit-identical to fiksi_b200.workloads.Workload.prepare / fk_system_solve's host loop (no FMA contraction here).
+__global__ void __launch_bounds__(32)
+fk_batch_prepare_kernel(uint32_t n_sketches, uint32_t n_vars, uint32_t n_expr, const uint8_t* __restrict__ kinds, uint32_t shared_param,
+                        uint32_t n_perturb, const uint32_t* __restrict__ perturb_vars, const double* __restrict__ draws,
+                        const double* __restrict__ raw_vars, const double* __restrict__ raw_param, double* __restrict__ vars,
+                        double* __restrict__ params, double* __restrict__ scales) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_sketches) return;
+    const double* rv = raw_vars + (size_t)k * n_vars;
+    const double* rp = raw_param + (shared_param ? 0 : (size_t)k * n_expr);
+    double sum = 0.0;
+    uint32_t cnt = n_vars;
+    {
+        uint32_t i = 0;
+        for (; i + 8 <= n_vars; i += 8) {  // eight loads in flight, the additions stay in order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldg(rv + i + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum = sum + v[u] * v[u];
+        }
+        for (; i < n_vars; i++) {
+            const double v = __ldg(rv + i);
+            sum = sum + v * v;
+        }
+    }
+    for (uint32_t e = 0; e < n_expr; e++) {
+        const uint32_t kd = __ldg(kinds + e);
+        if (kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE) {
+            const double q = __ldg(rp + e);
+            sum = sum + q * q;
+            cnt++;
+        }
+    }
+    const double scale = sqrt(sum / (double)cnt);
+    const double recip = 1.0 / scale;
+    double* ov = vars + (size_t)k * n_vars;
+    double* op = params + (size_t)k * n_expr;
+    // the perturbation list is ascending (a BTreeSet in the reference): one merge walk, every value is written once
+    uint32_t j = 0, next = n_perturb ? __ldg(perturb_vars) : 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < n_vars; i++) {
+        double col = __ldg(rv + i) * recip;
+        if (i == next) {
+            col = col + (col * (1.0 / 8196.0) * __ldg(draws + 2 * j) + (1.0 / 65568.0) * __ldg(draws + 2 * j + 1));
+            j++;
+            next = j < n_perturb ? __ldg(perturb_vars + j) : 0xFFFFFFFFu;
+        }
+        ov[i] = col;
+    }
+    for (uint32_t e = 0; e < n_expr; e++) {
+        const uint32_t kd = __ldg(kinds + e);
+        const double q = __ldg(rp + e);
+        op[e] = (kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE) ? recip * q : q;
+    }
+    scales[k] = scale;
+}
+
+// system.variables[var] = system_scale * x[k] (assemble/mod.rs:161-166), in place on the solved free values.
+__global__ void __launch_bounds__(256)
+fk_batch_unscale_kernel(uint32_t n_sketches, uint32_t n_free, const double* __restrict__ scales, double* __restrict__ free_values) {
+    const uint64_t total = (uint64_t)n_sketches * n_free;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        free_values[i] = __ldg(scales + i / n_free) * free_values[i];
+}
+
+int launch_batch_prepare(uint32_t n_sketches, uint32_t n_vars, uint32_t n_expr, const uint8_t* kinds, int shared_param, uint32_t n_perturb,
+                         const uint32_t* perturb_vars, const double* draws, const double* raw_vars, const double* raw_param, double* vars,
+                         double* params, double* scales, void* stream) {
+    if (n_sketches == 0) return 0;
+    // one warp per CTA: a chunk of a few thousand sketches still spreads over every SM, and each thread's dependent chain
+    // (the sequential sums) is short against the launch
+    fk_batch_prepare_kernel<<<(n_sketches + 31) / 32, 32, 0, (cudaStream_t)stream>>>(n_sketches, n_vars, n_expr, kinds, shared_param ? 1u : 0u, n_perturb,
+                                                                                        perturb_vars, draws, raw_vars, raw_param, vars, params, scales);
+    return (int)cudaGetLastError();
+}
+
+int launch_batch_unscale(uint32_t n_sketches, uint32_t n_free, const double* scales, double* free_values, void* stream) {
+    const uint64_t total = (uint64_t)n_sketches * n_free;
+    if (total == 0) return 0;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, 148u * 16u);
+    fk_batch_unscale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_sketches, n_free, scales, free_values);
+    return (int)cudaGetLastError();
+}
+
 int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                       double* out_r, double* out_j, int mode, void* stream) {
     if (n_sketches == 0 || prog.m == 0) return 0;

@@ -68,6 +68,13 @@ int launch_scatter_free(const uint32_t* d_free_vars, uint32_t n_free, uint32_t n
                         double* vars, void* stream);
 // reports_out[k][st] = reports_in[st][k] (per-set report planes -> the caller's per-sketch rows).
 int launch_transpose_reports(const fk_report* in, fk_report* out, uint32_t n_sketches, uint32_t steps, void* stream);
+// assemble::solve's scale + seeded perturbation (fiksi/src/assemble/mod.rs:32-44,58-79,113-124) for n sketches:
+// raw_vars[n][n_vars], raw_param [n][n_expr] (or one row when shared_param) -> vars, params (scaled), scales[n].
+int launch_batch_prepare(uint32_t n_sketches, uint32_t n_vars, uint32_t n_expr, const uint8_t* kinds, int shared_param, uint32_t n_perturb,
+                         const uint32_t* perturb_vars, const double* draws, const double* raw_vars, const double* raw_param, double* vars,
+                         double* params, double* scales, void* stream);
+// free_values[k][f] *= scales[k] (assemble/mod.rs:161-166).
+int launch_batch_unscale(uint32_t n_sketches, uint32_t n_free, const double* scales, double* free_values, void* stream);
 const char* lm_kernel_name();
 // DFMA throughput microbenchmark on the current device (TFLOP/s, 2 flops per DFMA).
 int measure_fp64_peak(double* tflops);

@@ -421,26 +421,43 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
 
 }  // namespace
 
+// Warps per CTA (they share one copy of the tables) and CTAs per SM: the choice that puts the most warps on an SM; 238
+// registers per thread allow 8.  228 KB of shared memory per SM, 1 KB of it reserved per resident CTA.
+static void sk_shape(const SkProgram& prog, int* warps_per_cta, int* ctas_per_sm) {
+    const size_t tab_bytes = (size_t)prog.tab_words * 4, state = (size_t)prog.entries * 256;
+    int best_w = 1, best_warps = 0, best_ctas = 1;
+    for (int wpc = 1; wpc <= kSkMaxWarps; wpc++) {
+        const size_t per_cta = tab_bytes + wpc * state;
+        if (per_cta > 227 * 1024) break;
+        const int ctas = std::max(1, std::min((int)std::min<size_t>(32, (228 * 1024) / (per_cta + 1024)), 8 / wpc));
+        const int warps = ctas * wpc;
+        if (warps > best_warps || (warps == best_warps && wpc <= 2)) { best_warps = warps; best_w = wpc; best_ctas = ctas; }
+    }
+    static const int forced = [] {  // tuning knob
+        const char* e = std::getenv("FK_SK_WARPS");
+        return e ? std::atoi(e) : 0;
+    }();
+    if (forced >= 1 && forced <= kSkMaxWarps && tab_bytes + forced * state <= 227 * 1024) {
+        best_w = forced;
+        best_ctas = std::max(1, std::min((int)((228 * 1024) / (tab_bytes + forced * state + 1024)), 8 / forced));
+    }
+    *warps_per_cta = best_w;
+    *ctas_per_sm = best_ctas;
+}
+
+uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count) {
+    int wpc, ctas;
+    sk_shape(prog, &wpc, &ctas);
+    return 32u * (uint32_t)wpc * (uint32_t)ctas * (uint32_t)sm_count;
+}
+
 int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const double* vars, const double* params, double* free_out,
                            fk_report* reports, void* stream) {
     if (n_sketches == 0) return 0;
     if (!sk_fits(prog.entries, prog.tab_words)) return (int)cudaErrorInvalidConfiguration;
-    // Warps per CTA (they share one copy of the tables): the choice that puts the most warps on an SM; 238 registers
-    // per thread allow 8.  228 KB of shared memory per SM, 1 KB of it reserved per resident CTA.
-    const size_t tab_bytes = (size_t)prog.tab_words * 4, state = (size_t)prog.entries * 256;
-    int best_w = 1, best_warps = 0;
-    for (int wpc = 1; wpc <= kSkMaxWarps; wpc++) {
-        const size_t per_cta = tab_bytes + wpc * state;
-        if (per_cta > 227 * 1024) break;
-        const int ctas = (int)std::min<size_t>(32, (228 * 1024) / (per_cta + 1024));
-        const int warps = std::min(8, ctas * wpc);
-        if (warps > best_warps || (warps == best_warps && wpc <= 2)) { best_warps = warps; best_w = wpc; }
-    }
-    if (const char* e = std::getenv("FK_SK_WARPS")) {  // tuning knob
-        const int v = std::atoi(e);
-        if (v >= 1 && v <= kSkMaxWarps && tab_bytes + v * state <= 227 * 1024) best_w = v;
-    }
-    const size_t smem = tab_bytes + best_w * state;
+    int best_w, ctas;
+    sk_shape(prog, &best_w, &ctas);
+    const size_t smem = (size_t)prog.tab_words * 4 + (size_t)best_w * prog.entries * 256;
     cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(fk_batch_lm_sketch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -42,5 +42,8 @@ inline bool sk_fits(uint32_t entries, size_t tab_words) {
 
 int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                            double* free_out, fk_report* reports, void* stream);
+// Sketches one full wave of the kernel holds on a device with sm_count SMs (callers that cut a batch into chunks
+// make the chunks whole waves: with one or two CTAs per SM a partial wave leaves SMs idle for a whole solve).
+uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count);
 
 }  // namespace fk

@@ -196,6 +196,27 @@ FK_API int fk_batch_solve(const fk_topology* topo, uint32_t n, const double* var
 FK_API int fk_batch_solve_device(const fk_topology* topo, int device, uint32_t n, const double* vars,
                                  const double* param, double* free_out, fk_report* reports);
 
+/* System::solve for a batch of single-component sketches that share one topology, pre- and post-processing
+ * included (fiksi/src/assemble/mod.rs:32-44,58-79,113-124,161-166): per sketch the RMS scale over all variables
+ * and distance parameters, variables and distances divided by it, the seeded perturbation of the listed variables
+ * (the reference re-seeds its generator with 42 on every solve, so every sketch sees the same draws), the LM solve,
+ * and the solved free variables multiplied by the scale again.  All of it runs on `device`; the host only copies
+ * raw_vars[n][n_vars] and raw_param ([n][n_expr], or ONE row with FK_PREP_SHARED_PARAM) in and free_out[n][n_free]
+ * (UNSCALED values, i.e. what System::solve writes into system.variables), scales_out[n] (optional) and reports out.
+ * Restriction: the sketch is one connected component whose problem names every variable and expression of the
+ * system (the scale is a property of the whole system). */
+enum { FK_PREP_SHARED_PARAM = 1, FK_PREP_PERTURB = 2 };
+typedef struct {
+    uint32_t flags;               /* FK_PREP_* */
+    uint32_t n_perturb;           /* variables that draw from the generator, ascending; with perturb_vars == NULL: */
+    const uint32_t* perturb_vars; /* the topology's free variables */
+    uint32_t seed;                /* 42 in the reference (assemble/mod.rs:47) */
+    uint32_t pad;
+} fk_prepare_opts;
+FK_API int fk_batch_system_solve(const fk_topology* topo, int device, uint32_t n, const double* raw_vars,
+                                 const double* raw_param, const fk_prepare_opts* opts, double* free_out,
+                                 double* scales_out, fk_report* reports);
+
 /* Device-resident batch plan (one device; used by bench.py and by fk_batch_solve internally). */
 typedef struct fk_batch_plan fk_batch_plan;
 FK_API int fk_batch_plan_create(const fk_topology* topo, uint32_t capacity, int device,

@@ -3,6 +3,7 @@ symbolic analysis once per topology through the process-wide cache, heterogeneou
 flight together, pooled buffers on the L-BFGS / analyze entries, concurrent callers."""
 import threading
 
+
 import numpy as np
 import pytest
 
@@ -141,3 +142,41 @@ def test_concurrent_callers_on_one_large_topology():
         t.join()
     for (x, r), (xr, rr) in zip(out, ref):
         assert np.array_equal(x, xr) and r == rr
+
+
+@pytest.mark.parametrize("maker,shared", [(wl.truss, True), (wl.truss, False), (wl.cad_mix, False),
+                                          (lambda n: wl.hinged_triangles(4, n), True)])
+def test_batch_system_solve_does_the_pre_and_post_processing_on_the_device(oracle, maker, shared):
+    """fk_batch_system_solve == Workload.prepare (the bit-exact numpy restatement of assemble::solve's scale and seeded
+    perturbation, itself pinned to the oracle by test_workload_prepare_matches_assemble) + fk_batch_solve + write-back:
+    same scales bit for bit, same traces, same unscaled coordinates bit for bit."""
+    n = 5000
+    w = maker(n)
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    x_ref, rep_ref = topo.batch_solve(v, p)
+    want = w.write_back(w.raw_vars, x_ref, scale)[:, w.free_vars]
+    raw_param = w.raw_param[0] if shared else w.raw_param
+    if shared:
+        assert np.all(w.raw_param == w.raw_param[0])
+    x, scales, rep = topo.batch_system_solve(w.raw_vars, raw_param, perturb=True, shared_param=shared)
+    assert np.array_equal(scales, scale)
+    for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash", "lambda", "ssr"):
+        assert np.array_equal(rep[key], rep_ref[key]), key
+    assert np.array_equal(x, want)
+    # without the perturbation
+    v0, p0, s0 = w.prepare(perturb=False)
+    x0_ref, rep0_ref = topo.batch_solve(v0, p0)
+    x0, sc0, rep0 = topo.batch_system_solve(w.raw_vars, raw_param, perturb=False, shared_param=shared)
+    assert np.array_equal(rep0["trace_hash"], rep0_ref["trace_hash"])
+    assert np.array_equal(x0, w.write_back(w.raw_vars, x0_ref, s0)[:, w.free_vars])
+
+
+def test_batch_system_solve_with_fixed_variables_and_a_custom_perturbation_list():
+    name, w = [f for f in wl.stress_families(n_each=700) if f[0] == "two_components_a"][0]
+    v, p, scale = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    x_ref, rep_ref = topo.batch_solve(v, p)
+    x, scales, rep = topo.batch_system_solve(w.raw_vars, w.raw_param, perturb=True, perturb_vars=w.perturb_vars)
+    assert np.array_equal(scales, scale) and np.array_equal(rep["trace_hash"], rep_ref["trace_hash"])
+    assert np.array_equal(x, scale[:, None] * x_ref)
