@@ -57,3 +57,34 @@ def test_second_device_explicitly():
     xl0, rl0 = topo.batch_solve_lbfgs(v, p, device=0)
     xl1, rl1 = topo.batch_solve_lbfgs(v, p, device=1)
     assert np.array_equal(xl0, xl1)
+
+
+def test_many_topologies_go_to_devices_as_whole_groups(oracle):
+    """More topologies than devices: fk_lm_solve_batch hands whole groups to the devices round robin; every problem
+    must still get the answer a single-device call gives."""
+    _need_two()
+    probs, x0s, keeps = [], [], []
+    for n_points in range(4, 16):
+        w = wl.truss(2, n_points=n_points)
+        v, p, s = w.prepare()
+        for j in range(2):
+            fp, keep = fk.make_problem(v[j], w.kind, w.idx, p[j], w.free_vars, w.rows)
+            probs.append(fp); keeps.append(keep); x0s.append(v[j][w.free_vars])
+    xa, ra = fk.lm_solve_batch(probs, x0s, n_gpus=1)
+    xb, rb = fk.lm_solve_batch(probs, x0s, n_gpus=2)
+    for a, b in zip(xa, xb):
+        assert np.array_equal(a, b)
+    assert np.array_equal(ra["trace_hash"], rb["trace_hash"]) and np.array_equal(ra["exit_reason"], rb["exit_reason"])
+
+
+def test_single_pass_and_system_solve_on_two_devices():
+    _need_two()
+    w = wl.hinged_triangles(8, 3000)
+    v, p, s = w.prepare()
+    topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+    v1, r1 = topo.batch_solve_single_pass(v, p, n_gpus=1)
+    v2, r2 = topo.batch_solve_single_pass(v, p, n_gpus=2)
+    assert np.array_equal(v1, v2) and np.array_equal(r1["trace_hash"], r2["trace_hash"])
+    xa, sa, ra = topo.batch_system_solve(w.raw_vars, w.raw_param, device=0)
+    xb, sb, rb = topo.batch_system_solve(w.raw_vars, w.raw_param, device=1)
+    assert np.array_equal(xa, xb) and np.array_equal(sa, sb) and np.array_equal(ra["trace_hash"], rb["trace_hash"])
