@@ -379,7 +379,6 @@ fk_batch_eval_kernel(const DevProgram P, uint32_t n_sketches, const double* __re
 // no divergence between expression kinds, and every gather / scatter is a conflict-free shared
 // memory access.  Residuals and Jacobian values are collected in shared memory ([pos][sketch]) and
 // leave as contiguous, coalesced stores.  HBM sees each input and output byte exactly once.
-constexpr int kEvalThreads = 128;
 
 // Row table decoded once per CTA into shared memory: all offsets are premultiplied by the tile's
 // leading dimension, so the inner loop is `value = sv[voff + sketch]`.
@@ -416,8 +415,8 @@ __device__ __forceinline__ void eval_tiled_row(const EvalRow& T, uint32_t sk, ui
     }
 }
 
-template <int S, bool WITH_JACOBIAN>
-__global__ void __launch_bounds__(kEvalThreads, 8)
+template <int S, bool WITH_JACOBIAN, int kEvalThreads>
+__global__ void __launch_bounds__(kEvalThreads, 1024 / kEvalThreads)
 fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
                            const double* __restrict__ params_all, double* __restrict__ out_r, double* __restrict__ out_j) {
     extern __shared__ __align__(16) double smem_eval[];
@@ -1179,11 +1178,13 @@ int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double*
     {
         const size_t per_sketch_rows = (size_t)prog.n_vars + prog.n_expr + prog.m + (mode == 0 ? prog.jnnz : 0);
         auto bytes_for = [&](int S) { return (per_sketch_rows * (size_t)(S + 1) + 1) * sizeof(double) + (size_t)prog.m * sizeof(EvalRow); };
-        // largest tile that keeps >= 5 CTAs (20 warps) per SM; measured best on the config-4 topology:
-        // the kernel is latency bound (FP64 div / sqrt / atan2 chains), not capacity bound
+        // 256-thread CTAs, largest tile that keeps three of them (24 warps) on an SM: measured on B200 (tools/bench_assembly.py,
+        // residual + Jacobian, M sketches of the config-4 topology / 262,144 trusses): 128 threads S=64 0.185 / 0.216 ms,
+        // 256 threads S=128 0.173 ms, S=32 (truss: the largest that fits) 0.163 ms.  The kernel is bound by instruction
+        // issue (IEEE divide / sqrt / atan2 sequences, ~3,200 thread instructions per config-4 sketch), not by bytes in flight.
         int S = 0;
         for (int cand : {32, 64, 128})
-            if (bytes_for(cand) <= 40 * 1024) S = cand;
+            if (bytes_for(cand) <= 76 * 1024) S = cand;
         if (S == 0)
             for (int cand : {128, 64, 32})
                 if (bytes_for(cand) <= 110 * 1024) { S = cand; break; }
@@ -1197,19 +1198,29 @@ int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double*
         }
         if (S != 0) {
             const size_t smem = bytes_for(S);
+            static const int threads = [] {  // CTA size of the tile-staged kernel (A/B knob)
+                const char* e = std::getenv("FK_EVAL_THREADS");
+                return (e && std::atoi(e) == 128) ? 128 : 256;
+            }();
             const int ctas_per_sm = (int)std::min<size_t>(16, (226 * 1024) / (smem + 1024));
             const uint32_t tiles = (n_sketches + S - 1) / S;
             const uint32_t grid = std::min<uint32_t>(tiles, 148u * (uint32_t)ctas_per_sm);
             cudaError_t e = cudaSuccess;
-#define FK_EVAL_TILED(SV, JV)                                                                                          \
+#define FK_EVAL_TILED_T(SV, JV, TH)                                                                                        \
     do {                                                                                                               \
-        e = cudaFuncSetAttribute(fk_batch_eval_tiled_kernel<SV, JV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        e = cudaFuncSetAttribute(fk_batch_eval_tiled_kernel<SV, JV, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e == cudaSuccess)                                                                                          \
-            fk_batch_eval_tiled_kernel<SV, JV><<<grid, kEvalThreads, smem, s>>>(prog, n_sketches, vars, params, out_r, out_j); \
+            fk_batch_eval_tiled_kernel<SV, JV, TH><<<grid, TH, smem, s>>>(prog, n_sketches, vars, params, out_r, out_j); \
+    } while (0)
+#define FK_EVAL_TILED(SV, JV)                          \
+    do {                                               \
+        if (threads == 256) FK_EVAL_TILED_T(SV, JV, 256); \
+        else FK_EVAL_TILED_T(SV, JV, 128);             \
     } while (0)
             if (S == 128) { if (mode == 0) FK_EVAL_TILED(128, true); else FK_EVAL_TILED(128, false); }
             else if (S == 64) { if (mode == 0) FK_EVAL_TILED(64, true); else FK_EVAL_TILED(64, false); }
             else { if (mode == 0) FK_EVAL_TILED(32, true); else FK_EVAL_TILED(32, false); }
+#undef FK_EVAL_TILED_T
 #undef FK_EVAL_TILED
             if (e != cudaSuccess) return (int)e;
             return (int)cudaGetLastError();
