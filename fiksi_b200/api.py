@@ -261,8 +261,8 @@ def fp64_peak_tflops(device=0) -> float:
 
 
 class lm_kernel:
-    """Context manager around fk_set_lm_kernel: 'auto' | 'tile' | 'sketch' (tests and A/B measurements)."""
-    _CODES = {"auto": -1, "tile": 0, "sketch": 1}
+    """Context manager around fk_set_lm_kernel: 'auto' | 'tile' | 'sketch' | 'sketch_solo' | 'sketch_pair' (tests, A/B)."""
+    _CODES = {"auto": -1, "tile": 0, "sketch": 1, "sketch_solo": 2, "sketch_pair": 3}
 
     def __init__(self, choice):
         self.code = self._CODES[choice]

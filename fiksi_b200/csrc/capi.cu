@@ -683,7 +683,7 @@ int fk_fp64_peak_tflops(int device, double* out) {
     return FK_OK;
 }
 
-void fk_set_lm_kernel(int choice) { fk::lm_kernel_choice().store(choice < 0 ? -1 : (choice ? 1 : 0)); }
+void fk_set_lm_kernel(int choice) { fk::lm_kernel_choice().store(choice < 0 || choice > 3 ? -1 : choice); }
 int fk_get_lm_kernel(void) { return fk::lm_kernel_choice().load(); }
 int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint32_t* state_doubles, uint32_t* table_words) {
     if (!topo) return fail(FK_ERR_INVALID, "null topology");

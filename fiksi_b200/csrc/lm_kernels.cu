@@ -1016,7 +1016,7 @@ std::atomic<int>& lm_kernel_choice() {
 int batch_lm_uses_sketch_kernel(const DevProgram& prog, uint32_t n_sketches) {
     if (!prog.sketch_prog) return 0;
     const int forced = lm_kernel_choice().load(std::memory_order_relaxed);
-    if (forced >= 0) return forced;
+    if (forced >= 0) return forced >= 1 ? 1 : 0;
     static const uint32_t min_batch = [] {
         const char* e = std::getenv("FK_LM_SKETCH_MIN");
         return (uint32_t)(e ? std::max(1, std::atoi(e)) : 4096);

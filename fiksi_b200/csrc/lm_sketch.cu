@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "expressions.cuh"
+#include "lm_kernels.cuh"
 
 namespace fk {
 
@@ -419,6 +420,434 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
     reports[sketch] = rep;
 }
 
+// ---- warp-pair variant ---------------------------------------------------------------------------------------
+// When a sketch's state is so large that only one or two warps fit an SM (the 20-point truss: 93 KB per warp), two of
+// the SM's four schedulers idle and the one warp per scheduler issues a dependent instruction every ~4 cycles.  Here a
+// CTA is TWO warps working on the SAME 32 sketches (thread l of both warps serves sketch l):
+//   * evaluation: the leader computes a row (loads, sqrt / divide / atan2) and leaves gradient and residual in a
+//     double-buffered staging area; the helper adds them into g and H while the leader is already on the next row;
+//   * factorisation: both warps read the pivot column into registers, each applies one half of the column's updates;
+//   * back substitution and the LM bookkeeping stay with the leader (dependent chains), the helper clears g and H
+//     for the next evaluation meanwhile.
+// One CTA barrier per row and per column hands the data over.  Operations and their order per entry are those of the
+// solo kernel, so the results are bit-identical.
+constexpr uint32_t kPairExtra = 20;  // entries behind the solo state: 2 x (8 gradients + residual) staging, lambda, pad
+
+template <int KIND, bool SPECIAL>
+__device__ __forceinline__ void sk_row_produce(const uint32_t* rec, const uint4 h0, const char* x, const char* fx, const char* pr, char* stage,
+                                               double& ssr) {
+    constexpr int A = sk_arity(KIND);
+    uint32_t t[(2 + A + 3) / 4 * 4];
+    t[0] = h0.x; t[1] = h0.y; t[2] = h0.z; t[3] = h0.w;
+#pragma unroll
+    for (int i = 1; i < (2 + A + 3) / 4; i++) {
+        const uint4 q = reinterpret_cast<const uint4*>(rec)[i];
+        t[4 * i] = q.x; t[4 * i + 1] = q.y; t[4 * i + 2] = q.z; t[4 * i + 3] = q.w;
+    }
+    double v[8], g[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) v[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const uint32_t src = t[2 + s];
+        if (SPECIAL) v[s] = (src >> 31) ? ldp(fx, src & 0x7FFFFFFFu) : ldp(x, src);
+        else v[s] = ldp(x, src);
+    }
+    const double param = sk_has_param(KIND) ? ldp(pr, t[1]) : 0.0;
+    const double r = dev::eval_expression(KIND, v, param, g);
+    ssr = ssr + r * r;  // lm.rs:195-197: sequential, not fused
+#pragma unroll
+    for (int s = 0; s < A; s++) stp(stage, (uint32_t)s << 8, g[s]);
+    stp(stage, 8u << 8, -r);
+}
+
+template <int KIND, bool SPECIAL>
+__device__ __forceinline__ void sk_row_consume(const uint32_t* rec, const char* stage, char* w, char* f) {
+    constexpr int A = sk_arity(KIND);
+    constexpr int NP = A * (A + 1) / 2;
+    constexpr int NW = 2 + 2 * A + NP;
+    uint32_t t[(NW + 3) / 4 * 4];
+    ld_words<NW>(rec, t);
+    double* gp[A];
+    double* hp[NP];
+    double gv[A], hv[NP], g[A];
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        const uint32_t o = t[2 + A + s];
+        gp[s] = reinterpret_cast<double*>(w + o);
+        gv[s] = (!SPECIAL || o != kNone) ? *gp[s] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const uint32_t o = t[2 + 2 * A + q];
+        hp[q] = reinterpret_cast<double*>(f + o);
+        hv[q] = (!SPECIAL || o != kNone) ? *hp[q] : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < A; s++) g[s] = ldp(stage, (uint32_t)s << 8);
+    const double nr = ldp(stage, 8u << 8);
+#pragma unroll
+    for (int s = 0; s < A; s++)
+        if (!SPECIAL || t[2 + A + s] != kNone) *gp[s] = fma(g[s], nr, gv[s]);
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < A; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++, q++)
+            if (!SPECIAL || t[2 + 2 * A + q] != kNone) *hp[q] = fma(g[a], g[b], hv[q]);
+}
+
+// One half of a column's updates (HALF 0: the first (NP + C + 1) / 2 targets in the order "pairs (a, b), then the C
+// right-hand-side entries", HALF 1: the rest).  Both halves read the whole column.
+template <int C, int HALF>
+__device__ __forceinline__ void sk_column_half(const uint32_t* body, char* f, char* w, double wk, double inv) {
+    constexpr int NP = C * (C + 1) / 2, NT = NP + C, H0 = (NT + 1) / 2;
+    constexpr int LO = HALF ? H0 : 0, HI = HALF ? NT : H0;
+    uint32_t t[(2 * C + NP + 3) / 4 * 4];
+    ld_words<2 * C + NP>(body, t);
+    double l[C], s[C], wv[C], d[NP];
+    double* wp[C];
+    double* dp[NP];
+#pragma unroll
+    for (int a = 0; a < C; a++) l[a] = ldp(f, t[a]);
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+        if (q >= LO && q < HI) {
+            dp[q] = reinterpret_cast<double*>(f + t[2 * C + q]);
+            d[q] = *dp[q];
+        }
+#pragma unroll
+    for (int a = 0; a < C; a++)
+        if (NP + a >= LO && NP + a < HI) {
+            wp[a] = reinterpret_cast<double*>(w + t[C + a]);
+            wv[a] = *wp[a];
+        }
+#pragma unroll
+    for (int a = 0; a < C; a++) s[a] = -(l[a] * inv);
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < C; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++, q++)
+            if (q >= LO && q < HI) *dp[q] = fma(s[a], l[b], d[q]);
+#pragma unroll
+    for (int a = 0; a < C; a++)
+        if (NP + a >= LO && NP + a < HI) *wp[a] = fma(s[a], wk, wv[a]);
+}
+
+__device__ __forceinline__ void sk_column_generic_half(const uint32_t* t, uint32_t C, int half, char* f, char* w, double wk, double inv) {
+    const uint32_t NP = C * (C + 1) / 2, NT = NP + C, H0 = (NT + 1) / 2;
+    const uint32_t lo = half ? H0 : 0, hi = half ? NT : H0;
+    uint32_t q = 0;
+    for (uint32_t a = 0; a < C; a++) {
+        const double la = ldp(f, t[a]);
+        const double sa = -(la * inv);
+        for (uint32_t b = 0; b <= a; b++, q++) {
+            if (q < lo || q >= hi) continue;
+            double* dst = reinterpret_cast<double*>(f + t[2 * C + q]);
+            const double lb = b == a ? la : ldp(f, t[b]);
+            *dst = fma(sa, lb, *dst);
+        }
+        if (NP + a >= lo && NP + a < hi) {
+            double* wr = reinterpret_cast<double*>(w + t[C + a]);
+            *wr = fma(sa, wk, *wr);
+        }
+    }
+}
+
+template <int HALF>
+__device__ __forceinline__ void sk_column_dispatch_half(uint32_t C, const uint32_t* body, char* f, char* w, double wk, double inv) {
+    switch (C) {
+        case 0: break;
+        case 1: sk_column_half<1, HALF>(body, f, w, wk, inv); break;
+        case 2: sk_column_half<2, HALF>(body, f, w, wk, inv); break;
+        case 3: sk_column_half<3, HALF>(body, f, w, wk, inv); break;
+        case 4: sk_column_half<4, HALF>(body, f, w, wk, inv); break;
+        case 5: sk_column_half<5, HALF>(body, f, w, wk, inv); break;
+        case 6: sk_column_half<6, HALF>(body, f, w, wk, inv); break;
+        case 7: sk_column_half<7, HALF>(body, f, w, wk, inv); break;
+        case 8: sk_column_half<8, HALF>(body, f, w, wk, inv); break;
+        default: sk_column_generic_half(body, C, HALF, f, w, wk, inv); break;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
+                               const double* __restrict__ params_all, double* __restrict__ free_out, fk_report* __restrict__ reports) {
+    extern __shared__ __align__(16) char sk_smem[];
+    __shared__ int ctrl;  // leader -> helper after an evaluation: 0 iterate, 1 evaluate the accepted point again, 2 done
+    uint32_t* const tab = reinterpret_cast<uint32_t*>(sk_smem);
+    for (uint32_t i = threadIdx.x; i < P.tab_words / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(tab)[i] = __ldg(reinterpret_cast<const uint4*>(P.tab) + i);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, role = threadIdx.x >> 5;
+    const uint32_t sketch = blockIdx.x * 32u + lane;
+    const bool valid = sketch < n_sketches;
+    const uint32_t sk = valid ? sketch : n_sketches - 1;
+    char* const base = sk_smem + (size_t)P.tab_words * 4 + lane * 8u;
+    const uint32_t n = P.n;
+    char* const w = base + (P.w << 8);
+    char* const f = base + (P.f << 8);
+    char* const stage = base + (P.entries << 8);  // [2][9] staging, then lambda
+
+    if (role == 1) {
+        // ---- helper ---------------------------------------------------------------------------------------
+        for (;;) {
+            uint32_t i = 0;
+            for (; i + 8 <= n; i += 8)
+#pragma unroll
+                for (int u = 0; u < 8; u++) stp(w, (i + u) << 8, 0.0);
+            for (; i < n; i++) stp(w, i << 8, 0.0);
+            for (i = 0; i + 8 <= P.lnnz; i += 8)
+#pragma unroll
+                for (int u = 0; u < 8; u++) stp(f, (i + u) << 8, 0.0);
+            for (; i < P.lnnz; i++) stp(f, i << 8, 0.0);
+            const uint32_t* rec = tab + P.off_eval;
+            uint32_t hx = rec[0];
+            for (uint32_t r = 0; r < P.m; r++) {
+                const uint32_t* cur = rec;
+                const uint32_t h = hx;
+                rec += h >> 16;
+                hx = rec[0];
+                const char* st = stage + ((r & 1u) * 9u << 8);
+                __syncthreads();  // the leader has staged row r
+#define FK_SK_ROW(K)                                                  \
+    case K: sk_row_consume<K, false>(cur, st, w, f); break;           \
+    case 0x100 | K: sk_row_consume<K, true>(cur, st, w, f); break;
+                switch (h & 0x1FFu) {
+                    FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
+                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
+                    default: break;
+                }
+#undef FK_SK_ROW
+            }
+            __syncthreads();  // g and H complete; the leader has decided
+            const int c = ctrl;
+            if (c == 2) break;
+            if (c == 1) continue;
+            const double lam2 = ldp(stage, 18u << 8);
+            const uint32_t* frec = tab + P.off_factor;
+            uint4 hn = *reinterpret_cast<const uint4*>(frec);
+            for (uint32_t col = 0; col < n; col++) {
+                const uint32_t C = hn.x;
+                const double* dp = reinterpret_cast<const double*>(f + hn.y);
+                const double wk = ldp(w, hn.z);
+                const uint32_t* body = frec + 4;
+                frec = body + ((2 * C + C * (C + 1) / 2 + 3u) & ~3u);
+                hn = *reinterpret_cast<const uint4*>(frec);
+                const double inv = sk_rcp(*dp + lam2);  // (the leader stores 1 / d one column later)
+                sk_column_dispatch_half<1>(C, body, f, w, wk, inv);
+                __syncthreads();
+            }
+            __syncthreads();  // the leader is through with the back substitution
+        }
+        return;
+    }
+
+    // ---- leader ---------------------------------------------------------------------------------------------
+    const double* vars = vars_all + (size_t)sk * P.n_vars;
+    const double* params = params_all + (size_t)sk * P.n_expr;
+    char* xp = base + (P.xa << 8);
+    char* xsp = base + (P.xb << 8);
+    const char* const fx = base + (P.fx << 8);
+    const char* const pr = base + (P.pr << 8);
+    for (uint32_t i = 0; i < n; i++) cp_async8(xp + (i << 8), vars + tab[P.off_free + i]);
+    for (uint32_t i = 0; i < P.nfix; i++) cp_async8(base + ((P.fx + i) << 8), vars + tab[P.off_fix + i]);
+    for (uint32_t i = 0; i < P.npar; i++) cp_async8(base + ((P.pr + i) << 8), params + tab[P.off_par + i]);
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+
+    double ssr = 0.0, lambda = 0.5, dn = 0.0;  // lm.rs:108
+    uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
+    uint64_t trace = 0;
+    bool active = valid;
+    int fstat = 0;
+    enum { kInit, kTrial, kRestore } mode = kInit;
+    const char* xe = xp;
+    for (;;) {
+        double s = 0.0;
+        {
+            const uint32_t* rec = tab + P.off_eval;
+            uint4 hn = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t r = 0; r < P.m; r++) {
+                const uint32_t* cur = rec;
+                const uint4 h = hn;
+                rec += h.x >> 16;
+                hn = *reinterpret_cast<const uint4*>(rec);
+                char* st = stage + ((r & 1u) * 9u << 8);
+#define FK_SK_ROW(K)                                                            \
+    case K: sk_row_produce<K, false>(cur, h, xe, fx, pr, st, s); break;         \
+    case 0x100 | K: sk_row_produce<K, true>(cur, h, xe, fx, pr, st, s); break;
+                switch (h.x & 0x1FFu) {
+                    FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
+                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
+                    default: break;
+                }
+#undef FK_SK_ROW
+                __syncthreads();  // row r is staged
+            }
+        }
+        bool restore = false;
+        if (mode == kInit) {
+            ssr = s;
+            if (ssr < 1e-8) {
+                exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+                active = false;
+            } else {
+                outer_iters = 1;
+            }
+        } else if (mode == kTrial && active) {
+            factorizations++;
+            if (fstat == 1) {
+                lambda *= 8.0;
+                trace = sk_trace_push(trace, 0);
+                restore = true;
+            } else if (fstat == 0 && dn < 1e-12) {
+                exit_reason = FK_EXIT_SMALL_STEP;
+                active = false;
+            } else {
+                const double ssr_s = fstat == 0 ? s : NAN;
+                if (ssr_s < ssr) {
+                    lambda *= 0.125;
+                    if (lambda < 1e-50) lambda = 1e-50;
+                    accepted++;
+                    trace = sk_trace_push(trace, 1);
+                    char* tmp = xp; xp = xsp; xsp = tmp;
+                    const bool stalled = (ssr - ssr_s) / ssr <= 1e-6;
+                    ssr = ssr_s;
+                    if (stalled) {
+                        exit_reason = FK_EXIT_STALLED;
+                        active = false;
+                    } else if (outer_iters == 100) {
+                        active = false;
+                    } else if (ssr < 1e-8) {
+                        exit_reason = FK_EXIT_CONVERGED_RESIDUAL;
+                        active = false;
+                    } else {
+                        outer_iters++;
+                    }
+                } else {
+                    lambda *= 2.0;
+                    trace = sk_trace_push(trace, 2);
+                    restore = true;
+                }
+            }
+        }
+        int c = 0;
+        if (mode != kRestore && __any_sync(0xFFFFFFFFu, restore && active)) {
+            c = 1;
+        } else {
+            if (active && !isfinite(lambda)) {
+                exit_reason = FK_EXIT_LAMBDA_OVERFLOW;
+                active = false;
+            }
+            if (!__any_sync(0xFFFFFFFFu, active)) c = 2;
+        }
+        const double sl = sqrt(lambda);  // lm.rs:119-125
+        const double lam2 = sl * sl;
+        if (c == 0) stp(stage, 18u << 8, lam2);
+        if (lane == 0) ctrl = c;
+        __syncthreads();  // decision published; g and H complete
+        if (c == 1) {
+            mode = kRestore;
+            xe = xp;
+            continue;
+        }
+        if (c == 2) break;
+        {
+            fstat = 0;
+            double* dp_prev = nullptr;
+            double inv_prev = 0.0;
+            const uint32_t* rec = tab + P.off_factor;
+            uint4 hn = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t col = 0; col < n; col++) {
+                const uint32_t C = hn.x;
+                double* dp = reinterpret_cast<double*>(f + hn.y);
+                const double wk = ldp(w, hn.z);
+                const uint32_t* body = rec + 4;
+                rec = body + ((2 * C + C * (C + 1) / 2 + 3u) & ~3u);
+                hn = *reinterpret_cast<const uint4*>(rec);
+                const double d = *dp + lam2;
+                if (fstat == 0 && !(d > 0.0 && d < INFINITY)) fstat = d != d ? 2 : 1;
+                const double inv = sk_rcp(d);
+                if (dp_prev) *dp_prev = inv_prev;  // the helper read that pivot before the last barrier
+                sk_column_dispatch_half<0>(C, body, f, w, wk, inv);
+                dp_prev = dp;
+                inv_prev = inv;
+                __syncthreads();
+            }
+            if (dp_prev) *dp_prev = inv_prev;
+        }
+        {
+            const uint32_t* rec = tab + P.off_back;
+            uint4 hn = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t col = 0; col < n; col++) {
+                const uint32_t C = hn.x;
+                const double inv = ldp(f, hn.y);
+                double* zp = reinterpret_cast<double*>(w + hn.z);
+                double* xd = reinterpret_cast<double*>(xsp + hn.w);
+                const uint32_t* body = rec + 4;
+                rec = body + ((2 * C + 3u) & ~3u);
+                hn = *reinterpret_cast<const uint4*>(rec);
+                double acc = *zp;
+                switch (C) {
+                    case 0: break;
+                    case 1: acc = sk_back_column<1>(body, f, w, acc); break;
+                    case 2: acc = sk_back_column<2>(body, f, w, acc); break;
+                    case 3: acc = sk_back_column<3>(body, f, w, acc); break;
+                    case 4: acc = sk_back_column<4>(body, f, w, acc); break;
+                    case 5: acc = sk_back_column<5>(body, f, w, acc); break;
+                    case 6: acc = sk_back_column<6>(body, f, w, acc); break;
+                    case 7: acc = sk_back_column<7>(body, f, w, acc); break;
+                    case 8: acc = sk_back_column<8>(body, f, w, acc); break;
+                    default:
+                        for (uint32_t a = C; a-- > 0;) acc = fma(-ldp(f, body[a]), ldp(w, body[C + a]), acc);
+                        break;
+                }
+                const double z = acc * inv;
+                *zp = z;
+                *xd = z;
+            }
+        }
+        __syncthreads();  // H and g are consumed: the helper clears them for the trial evaluation
+        {
+            dn = 0.0;
+            uint32_t i = 0;
+            for (; i + 4 <= n; i += 4) {
+                double d[4], x0[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    d[u] = ldp(xsp, (i + u) << 8);
+                    x0[u] = ldp(xp, (i + u) << 8);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    dn = dn + d[u] * d[u];
+                    stp(xsp, (i + u) << 8, x0[u] + d[u]);
+                }
+            }
+            for (; i < n; i++) {
+                const double d = ldp(xsp, i << 8);
+                dn = dn + d * d;
+                stp(xsp, i << 8, ldp(xp, i << 8) + d);
+            }
+        }
+        mode = kTrial;
+        xe = xsp;
+    }
+    if (!valid) return;
+    double* out = free_out + (size_t)sketch * n;
+    for (uint32_t i = 0; i < n; i++) out[i] = ldp(xp, i << 8);
+    fk_report rep;
+    rep.exit_reason = exit_reason;
+    rep.outer_iters = outer_iters;
+    rep.factorizations = factorizations;
+    rep.accepted = accepted;
+    rep.ssr = ssr;
+    rep.lambda = lambda;
+    rep.trace_hash = trace;
+    reports[sketch] = rep;
+}
+
 }  // namespace
 
 // Warps per CTA (they share one copy of the tables) and CTAs per SM: the choice that puts the most warps on an SM; 238
@@ -445,7 +874,30 @@ static void sk_shape(const SkProgram& prog, int* warps_per_cta, int* ctas_per_sm
     *ctas_per_sm = best_ctas;
 }
 
+// The warp-pair variant is used when the solo shape leaves schedulers idle (fewer than four warps per SM) and the
+// pair shape puts more warps on the SM.  FK_SK_PAIR=0|1 forces the choice (A/B knob).
+static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
+    const size_t per_cta = (size_t)prog.tab_words * 4 + ((size_t)prog.entries + kPairExtra) * 256;
+    if (per_cta > 227 * 1024) return false;
+    const int pair_ctas = (int)std::min<size_t>(8, (228 * 1024) / (per_cta + 1024));
+    *ctas_per_sm = pair_ctas;
+    static const int env_forced = [] {
+        const char* e = std::getenv("FK_SK_PAIR");
+        return e ? std::atoi(e) : -1;
+    }();
+    const int choice = lm_kernel_choice().load(std::memory_order_relaxed);  // 2: solo, 3: pair (fk_set_lm_kernel)
+    const int forced = choice == 2 ? 0 : (choice == 3 ? 1 : env_forced);
+    if (forced == 0) return false;
+    if (forced == 1) return true;
+    int wpc, ctas;
+    sk_shape(prog, &wpc, &ctas);
+    const int solo_warps = wpc * ctas;
+    return solo_warps < 4 && 2 * pair_ctas > solo_warps;
+}
+
 uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count) {
+    int pair_ctas = 0;
+    if (sk_use_pair(prog, &pair_ctas)) return 32u * (uint32_t)pair_ctas * (uint32_t)sm_count;
     int wpc, ctas;
     sk_shape(prog, &wpc, &ctas);
     return 32u * (uint32_t)wpc * (uint32_t)ctas * (uint32_t)sm_count;
@@ -455,6 +907,16 @@ int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const dou
                            fk_report* reports, void* stream) {
     if (n_sketches == 0) return 0;
     if (!sk_fits(prog.entries, prog.tab_words)) return (int)cudaErrorInvalidConfiguration;
+    int pair_ctas = 0;
+    if (sk_use_pair(prog, &pair_ctas)) {
+        const size_t smem = (size_t)prog.tab_words * 4 + ((size_t)prog.entries + kPairExtra) * 256;
+        cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_sketch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(fk_batch_lm_sketch_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        fk_batch_lm_sketch_pair_kernel<<<(n_sketches + 31) / 32, 64, smem, (cudaStream_t)stream>>>(prog, n_sketches, vars, params, free_out, reports);
+        return (int)cudaGetLastError();
+    }
     int best_w, ctas;
     sk_shape(prog, &best_w, &ctas);
     const size_t smem = (size_t)prog.tab_words * 4 + (size_t)best_w * prog.entries * 256;

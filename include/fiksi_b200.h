@@ -243,8 +243,9 @@ FK_API int fk_fp64_peak_tflops(int device, double* out);
 
 /* Which batched LM kernel fk_batch_plan_run / fk_batch_solve* launch: -1 automatic (the
  * sketch-per-thread kernel for batches that fill the device, the tile kernel otherwise), 0 always the
- * tile kernel, 1 the sketch-per-thread kernel whenever the topology has one.  Process-wide; meant for
- * tests and A/B measurements (environment: FK_LM_KERNEL=tile|sketch). */
+ * tile kernel, 1 the sketch-per-thread kernel whenever the topology has one (2: always its one-warp-per-32-sketches
+ * shape, 3: always its warp-pair shape when that fits).  Process-wide; meant for tests and A/B measurements
+ * (environment: FK_LM_KERNEL=tile|sketch, FK_SK_PAIR=0|1). */
 FK_API void fk_set_lm_kernel(int choice);
 FK_API int fk_get_lm_kernel(void);
 /* Sketch-per-thread kernel of a topology: *available = 0/1, *state_doubles = shared-memory doubles per

@@ -30,12 +30,13 @@ def test_sketch_kernel_equals_tile_kernel_and_oracle(oracle, maker, n):
     v, p, scale = w.prepare()
     topo = _topo(w)
     assert topo.sketch_kernel_info()["available"]
-    xs, rs = _solve(topo, v, p, "sketch")
+    xs, rs = _solve(topo, v, p, "sketch_solo")
     xt, rt = _solve(topo, v, p, "tile")
-    for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash", "lambda"):
+    xp, rp = _solve(topo, v, p, "sketch_pair")  # two warps per 32 sketches (falls back to solo when it does not fit)
+    for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash", "lambda", "ssr"):
         assert np.array_equal(rs[key], rt[key]), key
-    scale_x = np.maximum(np.max(np.abs(xt), axis=1), 1e-300)
-    assert np.max(np.max(np.abs(xs - xt), axis=1) / scale_x) <= 1e-12
+        assert np.array_equal(rs[key], rp[key]), key
+    assert np.array_equal(xs, xt) and np.array_equal(xs, xp)  # same operations in the same order: bit-identical
     op, keep = oracle.make_problem(v[0], w.kind, w.idx, p[0], w.free_vars, w.rows)
     m = min(n, 1500)
     xo, ro, _ = oracle.lm_solve_batch_uniform(op, v[:m], p[:m], threads=8)
@@ -53,10 +54,13 @@ def test_sketch_kernel_stress_families(oracle):
         topo = _topo(w)
         if not topo.sketch_kernel_info()["available"]:
             continue
-        xs, rs = _solve(topo, v, p, "sketch")
+        xs, rs = _solve(topo, v, p, "sketch_solo")
         xt, rt = _solve(topo, v, p, "tile")
+        xp, rp = _solve(topo, v, p, "sketch_pair")
         for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash"):
             assert np.array_equal(rs[key], rt[key]), (name, key)
+            assert np.array_equal(rs[key], rp[key]), (name, key)
+        assert np.array_equal(xs, xp, equal_nan=True), name
         assert np.array_equal(rs["lambda"], rt["lambda"], equal_nan=True), name
         fin = np.isfinite(xt).all(axis=1)
         assert np.array_equal(fin, np.isfinite(xs).all(axis=1)), name
@@ -71,9 +75,10 @@ def test_ragged_and_tiny_batches():
     topo = _topo(w)
     xt, rt = _solve(topo, v, p, "tile")
     for n in (1, 31, 32, 33, 70):
-        xs, rs = _solve(topo, v[:n], p[:n], "sketch")
-        assert np.array_equal(rs["trace_hash"], rt["trace_hash"][:n])
-        assert np.max(np.abs(xs - xt[:n])) <= 1e-12 * np.max(np.abs(xt))
+        for shape in ("sketch_solo", "sketch_pair"):
+            xs, rs = _solve(topo, v[:n], p[:n], shape)
+            assert np.array_equal(rs["trace_hash"], rt["trace_hash"][:n])
+            assert np.array_equal(xs, xt[:n])
 
 
 def test_rows_naming_a_variable_twice_stay_on_the_tile_kernel():

@@ -13,8 +13,8 @@ def run(name, w, reps=5):
     plan.upload(v, p)
     fk.lib().fk_batch_plan_sync(plan._h)
     out = {}
-    for kernel in ("tile", "sketch"):
-        if kernel == "sketch" and not info["available"]:
+    for kernel in ("tile", "sketch_solo", "sketch_pair"):
+        if kernel != "tile" and not info["available"]:
             continue
         with api.lm_kernel(kernel):
             for _ in range(2):
@@ -29,9 +29,9 @@ def run(name, w, reps=5):
     line = f"{name:24s} n={w.n:8d} state={info['state_doubles']:4d}"
     for k, (t, x, rep) in out.items():
         line += f"  {k}: {w.n / t / 1e6:8.2f} M/s ({t * 1e3:7.3f} ms)"
-    if len(out) == 2:
-        same = np.array_equal(out["tile"][2]["trace_hash"], out["sketch"][2]["trace_hash"])
-        line += f"  traces equal={same} max|dx|={np.max(np.abs(out['tile'][1] - out['sketch'][1])):.2e} fact/sketch={out['sketch'][2]['factorizations'].mean():.2f}"
+    if len(out) == 3:
+        same = np.array_equal(out["tile"][2]["trace_hash"], out["sketch_pair"][2]["trace_hash"]) and np.array_equal(out["tile"][2]["trace_hash"], out["sketch_solo"][2]["trace_hash"])
+        line += f"  traces equal={same} max|dx| solo {np.max(np.abs(out['tile'][1] - out['sketch_solo'][1])):.1e} pair {np.max(np.abs(out['tile'][1] - out['sketch_pair'][1])):.1e}"
     print(line, flush=True)
 
 if __name__ == "__main__":
