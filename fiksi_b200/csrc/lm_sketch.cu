@@ -431,7 +431,10 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
 //     for the next evaluation meanwhile.
 // One CTA barrier per row and per column hands the data over.  Operations and their order per entry are those of the
 // solo kernel, so the results are bit-identical.
-constexpr uint32_t kPairExtra = 20;  // entries behind the solo state: 2 x (8 gradients + residual) staging, lambda, pad
+#ifndef FK_SK_LEADER_PCT
+#define FK_SK_LEADER_PCT 30
+#endif
+constexpr uint32_t kPairExtra = 38;  // entries behind the solo state: 2 steps x 2 rows x (8 gradients + residual) staging, lambda, pad
 
 template <int KIND, bool SPECIAL>
 __device__ __forceinline__ void sk_row_produce(const uint32_t* rec, const uint4 h0, const char* x, const char* fx, const char* pr, char* stage,
@@ -459,6 +462,45 @@ __device__ __forceinline__ void sk_row_produce(const uint32_t* rec, const uint4 
 #pragma unroll
     for (int s = 0; s < A; s++) stp(stage, (uint32_t)s << 8, g[s]);
     stp(stage, 8u << 8, -r);
+}
+
+// Two consecutive rows of the same kind without fixed slots: their loads and their sqrt / divide chains are independent,
+// so issuing them together hides most of one row's latency behind the other's.
+template <int KIND>
+__device__ __forceinline__ void sk_rows_produce2(const uint32_t* rec0, const uint4 h0, const uint32_t* rec1, const uint4 h1, const char* x,
+                                                 const char* pr, char* st0, char* st1, double& ssr) {
+    constexpr int A = sk_arity(KIND);
+    constexpr int NWD = (2 + A + 3) / 4 * 4;
+    uint32_t t0[NWD], t1[NWD];
+    t0[0] = h0.x; t0[1] = h0.y; t0[2] = h0.z; t0[3] = h0.w;
+    t1[0] = h1.x; t1[1] = h1.y; t1[2] = h1.z; t1[3] = h1.w;
+#pragma unroll
+    for (int i = 1; i < NWD / 4; i++) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(rec0)[i], q1 = reinterpret_cast<const uint4*>(rec1)[i];
+        t0[4 * i] = q0.x; t0[4 * i + 1] = q0.y; t0[4 * i + 2] = q0.z; t0[4 * i + 3] = q0.w;
+        t1[4 * i] = q1.x; t1[4 * i + 1] = q1.y; t1[4 * i + 2] = q1.z; t1[4 * i + 3] = q1.w;
+    }
+    double v0[8], v1[8], g0[8], g1[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) v0[s] = v1[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        v0[s] = ldp(x, t0[2 + s]);
+        v1[s] = ldp(x, t1[2 + s]);
+    }
+    const double p0 = sk_has_param(KIND) ? ldp(pr, t0[1]) : 0.0;
+    const double p1 = sk_has_param(KIND) ? ldp(pr, t1[1]) : 0.0;
+    const double r0 = dev::eval_expression(KIND, v0, p0, g0);
+    const double r1 = dev::eval_expression(KIND, v1, p1, g1);
+    ssr = ssr + r0 * r0;  // lm.rs:195-197: sequential, not fused
+    ssr = ssr + r1 * r1;
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        stp(st0, (uint32_t)s << 8, g0[s]);
+        stp(st1, (uint32_t)s << 8, g1[s]);
+    }
+    stp(st0, 8u << 8, -r0);
+    stp(st1, 8u << 8, -r1);
 }
 
 template <int KIND, bool SPECIAL>
@@ -497,11 +539,16 @@ __device__ __forceinline__ void sk_row_consume(const uint32_t* rec, const char* 
             if (!SPECIAL || t[2 + 2 * A + q] != kNone) *hp[q] = fma(g[a], g[b], hv[q]);
 }
 
-// One half of a column's updates (HALF 0: the first (NP + C + 1) / 2 targets in the order "pairs (a, b), then the C
-// right-hand-side entries", HALF 1: the rest).  Both halves read the whole column.
+// The leader's share of a column's NT targets: less than half, because the leader also carries the pivot checks and,
+// alone, the back substitution, during which the helper waits (ncu: the helper spent 21 % of its time at that barrier
+// with an even split).
+__host__ __device__ constexpr int sk_leader_share(int nt) { return (nt * FK_SK_LEADER_PCT + 50) / 100; }
+
+// One part of a column's updates (HALF 0: the leader's first sk_leader_share(NT) targets in the order "pairs (a, b),
+// then the C right-hand-side entries", HALF 1: the rest).  Both parts read the whole column.
 template <int C, int HALF>
 __device__ __forceinline__ void sk_column_half(const uint32_t* body, char* f, char* w, double wk, double inv) {
-    constexpr int NP = C * (C + 1) / 2, NT = NP + C, H0 = (NT + 1) / 2;
+    constexpr int NP = C * (C + 1) / 2, NT = NP + C, H0 = sk_leader_share(NT);
     constexpr int LO = HALF ? H0 : 0, HI = HALF ? NT : H0;
     uint32_t t[(2 * C + NP + 3) / 4 * 4];
     ld_words<2 * C + NP>(body, t);
@@ -536,7 +583,7 @@ __device__ __forceinline__ void sk_column_half(const uint32_t* body, char* f, ch
 }
 
 __device__ __forceinline__ void sk_column_generic_half(const uint32_t* t, uint32_t C, int half, char* f, char* w, double wk, double inv) {
-    const uint32_t NP = C * (C + 1) / 2, NT = NP + C, H0 = (NT + 1) / 2;
+    const uint32_t NP = C * (C + 1) / 2, NT = NP + C, H0 = (uint32_t)sk_leader_share((int)NT);
     const uint32_t lo = half ? H0 : 0, hi = half ? NT : H0;
     uint32_t q = 0;
     for (uint32_t a = 0; a < C; a++) {
@@ -588,7 +635,7 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
     const uint32_t n = P.n;
     char* const w = base + (P.w << 8);
     char* const f = base + (P.f << 8);
-    char* const stage = base + (P.entries << 8);  // [2][9] staging, then lambda
+    char* const stage = base + (P.entries << 8);  // [2 steps][2 rows][9] staging, then lambda
 
     if (role == 1) {
         // ---- helper ---------------------------------------------------------------------------------------
@@ -602,18 +649,33 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
 #pragma unroll
                 for (int u = 0; u < 8; u++) stp(f, (i + u) << 8, 0.0);
             for (; i < P.lnnz; i++) stp(f, i << 8, 0.0);
+            // rows are taken one at a time, or two at a time when two consecutive rows share a kind and have no fixed
+            // slot (the leader evaluates such a pair together); both warps derive the grouping from the same headers
             const uint32_t* rec = tab + P.off_eval;
             uint32_t hx = rec[0];
-            for (uint32_t r = 0; r < P.m; r++) {
+            for (uint32_t r = 0, step = 0; r < P.m; step++) {
                 const uint32_t* cur = rec;
                 const uint32_t h = hx;
-                rec += h >> 16;
+                const uint32_t* rec1 = cur + (h >> 16);
+                const uint32_t h1 = rec1[0];
+                const bool two = r + 1 < P.m && (h & 0x1FFu) < 0x100u && (h1 & 0x1FFu) == (h & 0x1FFu);
+                const char* st0 = stage + ((step & 1u) * 18u << 8);
+                const char* st1 = st0 + (9u << 8);
+                if (two) {
+                    rec = rec1 + (h1 >> 16);
+                    r += 2;
+                } else {
+                    rec = rec1;
+                    r += 1;
+                }
                 hx = rec[0];
-                const char* st = stage + ((r & 1u) * 9u << 8);
-                __syncthreads();  // the leader has staged row r
-#define FK_SK_ROW(K)                                                  \
-    case K: sk_row_consume<K, false>(cur, st, w, f); break;           \
-    case 0x100 | K: sk_row_consume<K, true>(cur, st, w, f); break;
+                __syncthreads();  // the leader has staged this step's row(s)
+#define FK_SK_ROW(K)                                                   \
+    case K:                                                            \
+        sk_row_consume<K, false>(cur, st0, w, f);                      \
+        if (two) sk_row_consume<K, false>(rec1, st1, w, f);            \
+        break;                                                         \
+    case 0x100 | K: sk_row_consume<K, true>(cur, st0, w, f); break;
                 switch (h & 0x1FFu) {
                     FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
                     FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
@@ -625,7 +687,7 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
             const int c = ctrl;
             if (c == 2) break;
             if (c == 1) continue;
-            const double lam2 = ldp(stage, 18u << 8);
+            const double lam2 = ldp(stage, 36u << 8);
             const uint32_t* frec = tab + P.off_factor;
             uint4 hn = *reinterpret_cast<const uint4*>(frec);
             for (uint32_t col = 0; col < n; col++) {
@@ -667,23 +729,36 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
         double s = 0.0;
         {
             const uint32_t* rec = tab + P.off_eval;
-            uint4 hn = *reinterpret_cast<const uint4*>(rec);
-            for (uint32_t r = 0; r < P.m; r++) {
+            uint4 h = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t r = 0, step = 0; r < P.m; step++) {
                 const uint32_t* cur = rec;
-                const uint4 h = hn;
-                rec += h.x >> 16;
-                hn = *reinterpret_cast<const uint4*>(rec);
-                char* st = stage + ((r & 1u) * 9u << 8);
-#define FK_SK_ROW(K)                                                            \
-    case K: sk_row_produce<K, false>(cur, h, xe, fx, pr, st, s); break;         \
-    case 0x100 | K: sk_row_produce<K, true>(cur, h, xe, fx, pr, st, s); break;
+                const uint32_t* rec1 = cur + (h.x >> 16);
+                const uint4 h1 = *reinterpret_cast<const uint4*>(rec1);
+                const bool two = r + 1 < P.m && (h.x & 0x1FFu) < 0x100u && (h1.x & 0x1FFu) == (h.x & 0x1FFu);
+                char* st0 = stage + ((step & 1u) * 18u << 8);
+                char* st1 = st0 + (9u << 8);
+#define FK_SK_ROW(K)                                                                           \
+    case K:                                                                                    \
+        if (two) sk_rows_produce2<K>(cur, h, rec1, h1, xe, pr, st0, st1, s);                   \
+        else sk_row_produce<K, false>(cur, h, xe, fx, pr, st0, s);                             \
+        break;                                                                                 \
+    case 0x100 | K: sk_row_produce<K, true>(cur, h, xe, fx, pr, st0, s); break;
                 switch (h.x & 0x1FFu) {
                     FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
                     FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
                     default: break;
                 }
 #undef FK_SK_ROW
-                __syncthreads();  // row r is staged
+                if (two) {
+                    rec = rec1 + (h1.x >> 16);
+                    h = *reinterpret_cast<const uint4*>(rec);
+                    r += 2;
+                } else {
+                    rec = rec1;
+                    h = h1;
+                    r += 1;
+                }
+                __syncthreads();  // this step's row(s) are staged
             }
         }
         bool restore = false;
@@ -744,7 +819,7 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
         }
         const double sl = sqrt(lambda);  // lm.rs:119-125
         const double lam2 = sl * sl;
-        if (c == 0) stp(stage, 18u << 8, lam2);
+        if (c == 0) stp(stage, 36u << 8, lam2);
         if (lane == 0) ctrl = c;
         __syncthreads();  // decision published; g and H complete
         if (c == 1) {
@@ -875,7 +950,7 @@ static void sk_shape(const SkProgram& prog, int* warps_per_cta, int* ctas_per_sm
 }
 
 // The warp-pair variant is used when the solo shape leaves schedulers idle (fewer than four warps per SM) and the
-// pair shape puts more warps on the SM.  FK_SK_PAIR=0|1 forces the choice (A/B knob).
+// pair shape keeps as many sketches in flight.  FK_SK_PAIR=0|1 forces the choice (A/B knob).
 static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
     const size_t per_cta = (size_t)prog.tab_words * 4 + ((size_t)prog.entries + kPairExtra) * 256;
     if (per_cta > 227 * 1024) return false;
@@ -892,7 +967,10 @@ static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
     int wpc, ctas;
     sk_shape(prog, &wpc, &ctas);
     const int solo_warps = wpc * ctas;
-    return solo_warps < 4 && 2 * pair_ctas > solo_warps;
+    // measured (tools/lm_ab.py, M sketches/s solo / pair): 20-point truss (2 solo warps, 2 pair CTAs) 54 / 72; 14-point truss
+    // (3 solo warps, 2 pair CTAs) 128 / 117; 10-point truss (5, 3) 215 / 218: the pair pays when it keeps as many groups of 32
+    // sketches in flight as the solo shape does warps
+    return solo_warps < 4 && pair_ctas >= solo_warps;
 }
 
 uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count) {
