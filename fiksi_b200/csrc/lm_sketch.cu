@@ -110,6 +110,83 @@ __device__ __forceinline__ void sk_eval_row(const uint32_t* rec, const uint4 h0,
             if (!SPECIAL || t[2 + 2 * A + q] != kNone) *hp[q] = fma(g[a], g[b], hv[q]);
 }
 
+// Two consecutive rows of one kind without fixed slots: loads and sqrt / divide chains of the two rows are independent
+// and issue together; the accumulations stay in row order (row r's stores precede row r+1's target loads).
+template <int KIND>
+__device__ __forceinline__ void sk_eval_rows2(const uint32_t* rec0, const uint4 h0, const uint32_t* rec1, const uint4 h1, const char* x,
+                                              const char* pr, char* w, char* f, double& ssr) {
+    constexpr int A = sk_arity(KIND);
+    constexpr int NP = A * (A + 1) / 2;
+    constexpr int NW = 2 + 2 * A + NP;
+    constexpr int NWD = (NW + 3) / 4 * 4;
+    uint32_t t0[NWD], t1[NWD];
+    t0[0] = h0.x; t0[1] = h0.y; t0[2] = h0.z; t0[3] = h0.w;
+    t1[0] = h1.x; t1[1] = h1.y; t1[2] = h1.z; t1[3] = h1.w;
+#pragma unroll
+    for (int i = 1; i < NWD / 4; i++) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(rec0)[i], q1 = reinterpret_cast<const uint4*>(rec1)[i];
+        t0[4 * i] = q0.x; t0[4 * i + 1] = q0.y; t0[4 * i + 2] = q0.z; t0[4 * i + 3] = q0.w;
+        t1[4 * i] = q1.x; t1[4 * i + 1] = q1.y; t1[4 * i + 2] = q1.z; t1[4 * i + 3] = q1.w;
+    }
+    double v0[8], v1[8], g0[8], g1[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) v0[s] = v1[s] = 0.0;
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        v0[s] = ldp(x, t0[2 + s]);
+        v1[s] = ldp(x, t1[2 + s]);
+    }
+    const double p0 = sk_has_param(KIND) ? ldp(pr, t0[1]) : 0.0;
+    const double p1 = sk_has_param(KIND) ? ldp(pr, t1[1]) : 0.0;
+    double* gp[A];
+    double* hp[NP];
+    double gv[A], hv[NP];
+#pragma unroll
+    for (int s = 0; s < A; s++) {
+        gp[s] = reinterpret_cast<double*>(w + t0[2 + A + s]);
+        gv[s] = *gp[s];
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        hp[q] = reinterpret_cast<double*>(f + t0[2 + 2 * A + q]);
+        hv[q] = *hp[q];
+    }
+    const double r0 = dev::eval_expression(KIND, v0, p0, g0);
+    const double r1 = dev::eval_expression(KIND, v1, p1, g1);
+    ssr = ssr + r0 * r0;  // lm.rs:195-197: sequential, not fused
+    ssr = ssr + r1 * r1;
+    {
+        const double nr = -r0;
+#pragma unroll
+        for (int s = 0; s < A; s++) *gp[s] = fma(g0[s], nr, gv[s]);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < A; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++, q++) *hp[q] = fma(g0[a], g0[b], hv[q]);
+    }
+    {
+        const double nr = -r1;
+#pragma unroll
+        for (int s = 0; s < A; s++) {
+            gp[s] = reinterpret_cast<double*>(w + t1[2 + A + s]);
+            gv[s] = *gp[s];
+        }
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            hp[q] = reinterpret_cast<double*>(f + t1[2 + 2 * A + q]);
+            hv[q] = *hp[q];
+        }
+#pragma unroll
+        for (int s = 0; s < A; s++) *gp[s] = fma(g1[s], nr, gv[s]);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < A; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++, q++) *hp[q] = fma(g1[a], g1[b], hv[q]);
+    }
+}
+
 // Right-looking step of column k with C entries below the diagonal: the column is read once into registers,
 // every target (C(C+1)/2 entries of later columns, C entries of the right-hand side: the forward substitution
 // rides along) is fetched, updated with one FMA and stored.  Same operations as the tile kernel's
@@ -242,21 +319,37 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
                 for (int u = 0; u < 8; u++) stp(f, (i + u) << 8, 0.0);
             for (; i < P.lnnz; i++) stp(f, i << 8, 0.0);
             const uint32_t* rec = tab + P.off_eval;
-            uint4 hn = *reinterpret_cast<const uint4*>(rec);
-            for (uint32_t r = 0; r < P.m; r++) {
+            uint4 h = *reinterpret_cast<const uint4*>(rec);
+            for (uint32_t r = 0; r < P.m;) {
                 const uint32_t* cur = rec;
-                const uint4 h = hn;
-                rec += h.x >> 16;
-                hn = *reinterpret_cast<const uint4*>(rec);  // next row's header (a padding record follows the last row)
+                const uint32_t* rec1 = cur + (h.x >> 16);
+                const uint4 h1 = *reinterpret_cast<const uint4*>(rec1);  // next row's header (a padding record follows the last row)
+                const bool two = r + 1 < P.m && (h.x & 0x1FFu) <= 1u && (h1.x & 0x1FFu) == (h.x & 0x1FFu);
 #define FK_SK_ROW(K)                                                          \
     case K: sk_eval_row<K, false>(cur, h, xe, fx, pr, w, f, s); break;        \
     case 0x100 | K: sk_eval_row<K, true>(cur, h, xe, fx, pr, w, f, s); break;
-                switch (h.x & 0x1FFu) {
-                    FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
+#define FK_SK_ROW2(K)                                                         \
+    case K:                                                                   \
+        if (two) sk_eval_rows2<K>(cur, h, rec1, h1, xe, pr, w, f, s);         \
+        else sk_eval_row<K, false>(cur, h, xe, fx, pr, w, f, s);              \
+        break;                                                                \
+    case 0x100 | K: sk_eval_row<K, true>(cur, h, xe, fx, pr, w, f, s); break;
+                switch (h.x & 0x1FFu) {  // (pairs of rows only for the kinds whose two-row body fits the register file)
+                    FK_SK_ROW2(0) FK_SK_ROW2(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
                     FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
                     default: break;
                 }
 #undef FK_SK_ROW
+#undef FK_SK_ROW2
+                if (two) {
+                    rec = rec1 + (h1.x >> 16);
+                    h = *reinterpret_cast<const uint4*>(rec);
+                    r += 2;
+                } else {
+                    rec = rec1;
+                    h = h1;
+                    r += 1;
+                }
             }
         }
         bool restore = false;
