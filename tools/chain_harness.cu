@@ -22,7 +22,8 @@ int main() {
     uint4* dt; cudaMalloc(&dt, tasks.size() * 16); cudaMemcpy(dt, tasks.data(), tasks.size() * 16, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem);
     {
-        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernels take their tasks by ticket
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
         for (int rep = 0; rep < 3; rep++) {
             cudaEventRecord(a);
             mf_chain_inv_kernel<<<B, TB, kChainInvSmem>>>(D, dt);
@@ -38,8 +39,9 @@ int main() {
     for (int rep = 0; rep < 4; rep++) {
         cudaMemcpy(w, rhs.data(), ns * 8, cudaMemcpyHostToDevice);
         cudaMemset(pub, 0xFF, ns * 8);
+        cudaMemset(ticket, 0, 4);
         cudaEventRecord(a);
-        mf_chain_fwd_kernel<<<B, 256>>>(D, dt, w, pub);
+        mf_chain_fwd_kernel<<<B, 256>>>(D, dt, w, pub, ticket);
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b);
         printf("rep %d: chain fwd %.1f us (%s)\n", rep, ms * 1e3, cudaGetErrorString(cudaGetLastError()));

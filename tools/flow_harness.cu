@@ -23,12 +23,14 @@ int main() {
     uint32_t* aptr; cudaMalloc(&aptr, (tasks.size() + 1) * 4); cudaMemset(aptr, 0, (tasks.size() + 1) * 4);  // no children
     cudaFuncSetAttribute(mf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFlowSmem);
     long long* dst = (long long*)D.status + 8;
+    uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernel takes its tiles by ticket
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int rep = 0; rep < 4; rep++) {
         cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
         cudaMemset(pub, 0xFF, A.size() * 8);
         cudaEventRecord(a);
-        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr);
+        cudaMemset(ticket, 0, 4);
+        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr, ticket);
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b);
         printf("rep %d: flow factor %.1f us, %zu tiles (%s)\n", rep, ms * 1e3, tasks.size(), cudaGetErrorString(cudaGetLastError()));
@@ -36,13 +38,15 @@ int main() {
     {   // the first diagonal tile alone: one CTA, nothing else on the device
         cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
         cudaMemset(pub, 0xFF, A.size() * 8);
-        mf_flow_kernel<<<1, kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr);
+        cudaMemset(ticket, 0, 4);
+        mf_flow_kernel<<<1, kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr, ticket);
         cudaDeviceSynchronize();
         long long one[4]; cudaMemcpy(one, D.ubuf, sizeof(one), cudaMemcpyDeviceToHost);
         printf("tile (0,0) alone: %lld ns from the end of the update loop to the end (%s)\n", one[3] - one[2], cudaGetErrorString(cudaGetLastError()));
         cudaMemcpy(D.pan, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
         cudaMemset(pub, 0xFF, A.size() * 8);
-        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr);
+        cudaMemset(ticket, 0, 4);
+        mf_flow_kernel<<<(unsigned)tasks.size(), kTileThreads, kFlowSmem>>>(D, dt, pub, aptr, nullptr, ticket);
         cudaDeviceSynchronize();
     }
     std::vector<long long> st(tasks.size() * 4);
