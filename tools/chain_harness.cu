@@ -23,6 +23,7 @@ int main() {
     cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem);
     {
         uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernels take their tasks by ticket
+    uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernels take their tasks by ticket
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
         for (int rep = 0; rep < 3; rep++) {
             cudaEventRecord(a);
@@ -35,6 +36,7 @@ int main() {
     double* w; cudaMalloc(&w, ns * 8);
     double* pub; cudaMalloc(&pub, ns * 8);
     std::vector<double> rhs(ns, 1.0);
+    uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernels take their tasks by ticket
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     for (int rep = 0; rep < 4; rep++) {
         cudaMemcpy(w, rhs.data(), ns * 8, cudaMemcpyHostToDevice);
