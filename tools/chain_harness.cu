@@ -22,9 +22,7 @@ int main() {
     uint4* dt; cudaMalloc(&dt, tasks.size() * 16); cudaMemcpy(dt, tasks.data(), tasks.size() * 16, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(mf_chain_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainInvSmem);
     {
-        uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernels take their tasks by ticket
-    uint32_t* ticket; cudaMalloc(&ticket, 4);  // the kernels take their tasks by ticket
-    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
         for (int rep = 0; rep < 3; rep++) {
             cudaEventRecord(a);
             mf_chain_inv_kernel<<<B, TB, kChainInvSmem>>>(D, dt);
