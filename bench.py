@@ -287,8 +287,11 @@ def main():
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / e2e_s
     copy_ceiling = world * n * e2e_steps / copy_s
-    uses_sketch_kernel = topo.batch_kernel(n) == "sketch"
-    kernel_name = "fk_batch_lm_sketch_kernel (one thread per sketch)" if uses_sketch_kernel else "fk_batch_lm_kernel<%d,%d> (tile)" % (info["tile"], 1)
+    which = topo.batch_kernel(n)
+    uses_sketch_kernel = which != "tile"
+    kernel_name = {"sketch": "fk_batch_lm_sketch_kernel (one thread per sketch, one warp per 32 sketches)",
+                   "sketch_pair": "fk_batch_lm_sketch_pair_kernel (one thread per sketch, leader + helper warp per 32 sketches)",
+                   "tile": "fk_batch_lm_kernel<%d,%d> (tile)" % (info["tile"], 1)}[which]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -350,8 +353,8 @@ def main():
                                     "frac": alg_bytes / avg_s / 1e9 / peak, "peak_source": peak_src,
                                     "note": "inputs + outputs once per sketch; not the limiter"},
                             "profiles": "ncu --set full summaries of this command: profiles/r02_*lm_sketch*",
-                            "note": "latency bound: one warp solves 32 sketches out of shared memory and only one or two such warps fit an SM "
-                                    "for this topology; see DESIGN.md section 4 for the stall breakdown"}
+                            "note": "latency bound: 32 sketches are solved out of shared memory by one warp (or a leader / helper pair of warps) and "
+                                    "only two such groups fit an SM for this topology; see DESIGN.md section 4 for the stall breakdown"}
         if not args.no_extras:
             try:
                 line["large_system"] = large_system(fk, wl, peak, fp64_peak)

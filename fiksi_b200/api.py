@@ -182,7 +182,7 @@ class Topology:
 
     def batch_kernel(self, n_sketches):
         """fk_topology_batch_kernel: 'sketch' or 'tile', the kernel a batched LM solve of this size launches."""
-        return "sketch" if lib().fk_topology_batch_kernel(self._h, int(n_sketches)) == 1 else "tile"
+        return {0: "tile", 1: "sketch", 2: "sketch_pair"}[lib().fk_topology_batch_kernel(self._h, int(n_sketches))]
 
     def plan(self, capacity, device=0):
         return BatchPlan(self, capacity, device)

@@ -697,10 +697,13 @@ int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint
 int fk_topology_batch_kernel(const fk_topology* topo, uint32_t n_sketches) {
     if (!topo) return fail(FK_ERR_INVALID, "null topology");
     const fk::Topology::SketchTables& k = topo->t.sk;
-    static const fk::SkProgram probe{};
+    fk::SkProgram probe{};
+    probe.entries = k.entries;
+    probe.tab_words = (uint32_t)k.tab.size();
     fk::DevProgram p{};
     p.sketch_prog = (k.ok && fk::sk_fits(k.entries, k.tab.size())) ? &probe : nullptr;
-    return fk::batch_lm_uses_sketch_kernel(p, n_sketches);
+    if (!fk::batch_lm_uses_sketch_kernel(p, n_sketches)) return 0;
+    return fk::sketch_kernel_is_pair(probe) ? 2 : 1;
 }
 
 void* fk_host_alloc(size_t bytes) {

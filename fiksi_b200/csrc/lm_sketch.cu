@@ -1066,6 +1066,11 @@ static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
     return solo_warps < 4 && pair_ctas >= solo_warps;
 }
 
+int sketch_kernel_is_pair(const SkProgram& prog) {
+    int ctas = 0;
+    return sk_use_pair(prog, &ctas) ? 1 : 0;
+}
+
 uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count) {
     int pair_ctas = 0;
     if (sk_use_pair(prog, &pair_ctas)) return 32u * (uint32_t)pair_ctas * (uint32_t)sm_count;

@@ -253,7 +253,8 @@ FK_API int fk_get_lm_kernel(void);
 FK_API int fk_topology_sketch_kernel_info(const fk_topology* topo, int* available, uint32_t* state_doubles, uint32_t* table_words);
 
 /* Which kernel a batched LM solve of n_sketches sketches of this topology launches under the current
- * fk_set_lm_kernel choice: 1 sketch-per-thread, 0 tile kernel (negative: error). */
+ * fk_set_lm_kernel choice: 0 tile kernel, 1 sketch-per-thread (one warp per 32 sketches), 2 sketch-per-thread in its
+ * warp-pair shape (negative: error). */
 FK_API int fk_topology_batch_kernel(const fk_topology* topo, uint32_t n_sketches);
 
 /* Topology cache of fk_lm_solve / fk_lm_solve_batch / fk_system_solve*: the symbolic analysis of a flattened
