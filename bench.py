@@ -377,6 +377,10 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["single_pass"] = {"error": str(e)}
             try:
+                line["heterogeneous_batch"] = heterogeneous_side(fk, wl)
+            except Exception as e:  # noqa: BLE001
+                line["heterogeneous_batch"] = {"error": str(e)}
+            try:
                 line["lbfgs"] = lbfgs_side(fk, wl, local_rank)
             except Exception as e:  # noqa: BLE001
                 line["lbfgs"] = {"error": str(e)}
@@ -594,6 +598,52 @@ def single_pass_side(fk, wl):
             "gpu_single_pass_sketches_per_s": n / sp_s, "gpu_decomposer_none_sketches_per_s": n / none_s,
             "cpu_port_single_pass_sketches_per_s_1core": ns / cpu_s, "traces_equal_on_sample": bool(same),
             "fraction_converged_single_pass": float(np.mean(rg["ssr"] < 1e-8))}
+
+
+def heterogeneous_side(fk, wl):
+    """Many DIFFERENT small systems in one fk_lm_solve_batch call (the reference solves a drawing component by component,
+    fiksi/src/assemble/mod.rs:81): trusses of 4..23 points with different fixed coordinates, `members` copies each.
+    Topologies come from the library's cache on the timed calls; all small groups go through one launch of
+    fk_hetero_lm_kernel (one warp per system).  Beside it the CPU restatement on one core, symbolic analysis per call as
+    in the reference."""
+    import numpy as np
+    import oracle
+    from fiksi_b200 import api
+    out = []
+    for n_topo, members in ((200, 5), (1000, 1)):
+        rng = np.random.default_rng(0)
+        probs, x0s, keep, oprobs = [], [], [], []
+        for t in range(n_topo):
+            n_points = 4 + t % 20
+            w = wl.truss(members, n_points=n_points, seed=0xF1C50002 + 1000 * t)
+            fixed = set(rng.choice(2 * n_points, size=t // 20 % 3, replace=False).tolist()) if t >= 20 else set()
+            free = np.array([q for q in range(2 * n_points) if q not in fixed], np.uint32)
+            v, p, s = w.prepare()
+            for j in range(members):
+                fp, k = fk.make_problem(v[j], w.kind, w.idx, p[j], free, w.rows)
+                probs.append(fp); keep.append(k); x0s.append(v[j][free])
+                oprobs.append((v[j], w.kind, w.idx, p[j], free, w.rows))
+        api.topology_cache_clear()
+        t0 = time.perf_counter()
+        xs, reps = fk.lm_solve_batch(probs, x0s)
+        cold = time.perf_counter() - t0
+        warm = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            xs, reps = fk.lm_solve_batch(probs, x0s)
+            warm = min(warm, time.perf_counter() - t0)
+        ns = min(len(probs), 300)
+        same = 0
+        t0 = time.perf_counter()
+        for k in range(ns):
+            op, okeep = oracle.make_problem(*oprobs[k])
+            xo, ro, _ = oracle.lm_solve(op, x0s[k])
+            same += int(ro["trace_hash"] == reps["trace_hash"][k] and ro["exit_reason"] == reps["exit_reason"][k])
+        cpu_s = time.perf_counter() - t0
+        out.append({"topologies": n_topo, "systems": len(probs), "gpu_systems_per_s_warm_cache": len(probs) / warm,
+                    "gpu_first_call_s_incl_symbolic_analysis": cold, "cpu_port_systems_per_s_1core": ns / cpu_s,
+                    "trace_and_exit_equal_to_oracle": same / ns, "oracle_sample": ns})
+    return out
 
 
 def lbfgs_side(fk, wl, device):

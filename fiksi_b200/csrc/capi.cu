@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/fiksi_b200.h"
@@ -211,6 +212,26 @@ struct fk_topology {
         }
         *out = p.get();
         return FK_OK;
+    }
+
+    // This topology with op tables for 32 lanes per system (single-system solves and heterogeneous batches): itself when
+    // its batch-oriented lane count is already 32, else a twin that shares the symbolic analysis and re-packs the tables.
+    fk_topology* lanes32() {
+        if (t.path != 0 || t.tile == 32) return this;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!twin_tried) {
+            twin_tried = true;
+            static const bool off = std::getenv("FK_NO_LATENCY_TWIN") != nullptr;
+            if (!off) {
+                std::unique_ptr<fk_topology> tw(new (std::nothrow) fk_topology());
+                if (tw) {
+                    tw->t = t;
+                    tw->t.tile = 32;
+                    if (tw->t.build_tables() == FK_OK) latency_twin = std::move(tw);
+                }
+            }
+        }
+        return latency_twin ? latency_twin.get() : this;
     }
 
     DevicePipeline* pipeline_for(int device) {
@@ -1032,22 +1053,7 @@ int fk_topology_lm_solve(fk_topology* topo, const double* vars, const double* pa
     // (4-16 by footprint) leaves lanes of that warp idle.  A twin of the topology with all 32 lanes, built on the
     // first single-system solve, serves these calls (same operations per entry, same results; tools/lat_probe.py:
     // 144 -> 89 us on the mixed-primitive sketch).
-    fk_topology* exec = topo;
-    if (t.path == 0 && t.tile < 32) {
-        std::lock_guard<std::mutex> lock(topo->mu);
-        if (!topo->twin_tried) {
-            topo->twin_tried = true;
-            static const bool off = std::getenv("FK_NO_LATENCY_TWIN") != nullptr;
-            if (!off) {
-                fk_problem p{};
-                p.n_vars = t.n_vars; p.n_expr = t.n_expr; p.kind = t.kind.data(); p.idx = t.idx.data();
-                p.n_free = t.n_free; p.free_vars = t.free_vars.data(); p.n_rows = t.n_rows; p.rows = t.rows.data();
-                std::unique_ptr<fk_topology> tw(new (std::nothrow) fk_topology());
-                if (tw && tw->t.build(p, 32) == FK_OK && tw->t.path == 0) topo->latency_twin = std::move(tw);
-            }
-        }
-        if (topo->latency_twin) exec = topo->latency_twin.get();
-    }
+    fk_topology* exec = topo->lanes32();
     int rc = run_device_range(exec, cur, 0, 1, v.data(), param ? param : zero.data(), out.data(), report, nullptr);
     if (rc == FK_OK && t.n_free) std::memcpy(free_values, out.data(), sizeof(double) * t.n_free);
     return rc;
@@ -1094,9 +1100,16 @@ struct TopologyCache {
     struct Entry { uint64_t sig; std::shared_ptr<fk_topology> topo; };
     std::mutex mu;
     std::list<Entry> lru;  // front = most recently used
+    std::unordered_multimap<uint64_t, std::list<Entry>::iterator> index;  // signature -> entry
+    void drop(std::list<Entry>::iterator it) {
+        auto range = index.equal_range(it->sig);
+        for (auto q = range.first; q != range.second; ++q)
+            if (q->second == it) { index.erase(q); break; }
+        lru.erase(it);
+    }
     size_t capacity = [] {
         const char* e = std::getenv("FK_TOPOLOGY_CACHE");
-        const int v = e ? std::atoi(e) : 64;
+        const int v = e ? std::atoi(e) : 1024;
         return (size_t)std::max(0, v);
     }();
     uint64_t hits = 0, misses = 0;
@@ -1132,9 +1145,10 @@ bool problem_arrays_ok(const fk_problem& p) {
 std::shared_ptr<fk_topology> cache_lookup(uint64_t sig, const fk_problem& p) {
     TopologyCache& c = topology_cache();
     std::lock_guard<std::mutex> lock(c.mu);
-    for (auto it = c.lru.begin(); it != c.lru.end(); ++it)
-        if (it->sig == sig && same_structure(it->topo->t, p)) {
-            c.lru.splice(c.lru.begin(), c.lru, it);
+    auto range = c.index.equal_range(sig);
+    for (auto q = range.first; q != range.second; ++q)
+        if (same_structure(q->second->topo->t, p)) {
+            c.lru.splice(c.lru.begin(), c.lru, q->second);  // (list iterators stay valid)
             c.hits++;
             return c.lru.front().topo;
         }
@@ -1146,12 +1160,15 @@ void cache_insert(uint64_t sig, const std::shared_ptr<fk_topology>& topo) {
     std::lock_guard<std::mutex> lock(c.mu);
     if (c.capacity == 0) return;
     c.lru.push_front({sig, topo});
-    while (c.lru.size() > c.capacity) c.lru.pop_back();
+    c.index.emplace(sig, c.lru.begin());
+    while (c.lru.size() > c.capacity) c.drop(std::prev(c.lru.end()));
     // large single systems keep hundreds of megabytes of factor storage on the device: at most four of them stay
-    size_t large = 0;
-    for (auto it = c.lru.begin(); it != c.lru.end();) {
-        if (it->topo->t.path == 2 && ++large > 4) it = c.lru.erase(it);
-        else ++it;
+    if (topo->t.path == 2) {
+        size_t large = 0;
+        for (auto it = c.lru.begin(); it != c.lru.end();) {
+            auto cur = it++;
+            if (cur->topo->t.path == 2 && ++large > 4) c.drop(cur);
+        }
     }
 }
 
@@ -1161,11 +1178,12 @@ void fk_topology_cache_configure(uint32_t capacity) {
     TopologyCache& c = topology_cache();
     std::lock_guard<std::mutex> lock(c.mu);
     c.capacity = capacity;
-    while (c.lru.size() > c.capacity) c.lru.pop_back();
+    while (c.lru.size() > c.capacity) c.drop(std::prev(c.lru.end()));
 }
 void fk_topology_cache_clear(void) {
     TopologyCache& c = topology_cache();
     std::lock_guard<std::mutex> lock(c.mu);
+    c.index.clear();
     c.lru.clear();
 }
 void fk_topology_cache_stats(uint64_t* hits, uint64_t* misses, uint32_t* entries) {
@@ -1174,6 +1192,101 @@ void fk_topology_cache_stats(uint64_t* hits, uint64_t* misses, uint32_t* entries
     if (hits) *hits = c.hits;
     if (misses) *misses = c.misses;
     if (entries) *entries = (uint32_t)c.lru.size();
+}
+
+// Staging of the heterogeneous-batch kernel, one per device: pinned host block + device block (grow-only), one stream.
+struct HeteroPool {
+    std::mutex mu;
+    int device = -1;
+    unsigned char *h = nullptr, *d = nullptr;
+    size_t cap = 0;
+    cudaStream_t stream = nullptr;
+};
+static HeteroPool* hetero_pool_for(int device) {
+    static std::mutex m;
+    static std::map<int, HeteroPool*> pools;  // never destroyed (CUDA may be gone at static-destruction time)
+    std::lock_guard<std::mutex> lock(m);
+    HeteroPool*& p = pools[device];
+    if (!p) {
+        p = new HeteroPool();
+        p->device = device;
+    }
+    return p;
+}
+
+// Solves jobs (group index, member) of small path-0 groups with ONE launch of fk_hetero_lm_kernel on `device`.
+struct HeteroItem { uint32_t group, problem; };
+static int hetero_solve(int device, const std::vector<fk_topology*>& topos32, const std::vector<HeteroItem>& items,
+                        const fk_problem* const* problems, double* const* free_values, fk_report* reports) {
+    HeteroPool* pool = hetero_pool_for(device);
+    std::lock_guard<std::mutex> lock(pool->mu);
+    CU(cudaSetDevice(device));
+    const size_t ng = topos32.size(), nj = items.size();
+    std::vector<fk::DevProgram> progs(ng);
+    uint32_t max_state = 1;
+    for (size_t g = 0; g < ng; g++) {
+        const fk::DevProgram* v = nullptr;
+        int rc = topos32[g]->program_for(device, &v);
+        if (rc != FK_OK) return rc;
+        progs[g] = *v;
+        progs[g].sketch_prog = nullptr;
+        max_state = std::max(max_state, fk::lm_smem_doubles(v->n, v->m, v->jnnz, v->lnnz));
+    }
+    // layout of the staging block: [programs][jobs][inputs: vars row + param row per job] | [outputs][reports]
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    std::vector<fk::HeteroJob> jobs(nj);
+    size_t in_doubles = 0, out_doubles = 0;
+    for (size_t k = 0; k < nj; k++) {
+        const fk::Topology& t = topos32[items[k].group]->t;
+        jobs[k].prog = items[k].group; jobs[k].pad = 0;
+        jobs[k].vars_off = in_doubles; in_doubles += t.n_vars;
+        jobs[k].param_off = in_doubles; in_doubles += t.n_expr;
+        jobs[k].out_off = out_doubles; out_doubles += t.n_free;
+    }
+    const size_t o_progs = 0, o_jobs = align(o_progs + ng * sizeof(fk::DevProgram)), o_in = align(o_jobs + nj * sizeof(fk::HeteroJob));
+    const size_t o_out = align(o_in + in_doubles * sizeof(double)), o_rep = align(o_out + out_doubles * sizeof(double));
+    const size_t total = align(o_rep + nj * sizeof(fk_report));
+    if (pool->cap < total) {
+        if (pool->h) cudaFreeHost(pool->h);
+        if (pool->d) cudaFree(pool->d);
+        pool->h = pool->d = nullptr; pool->cap = 0;
+        const size_t cap = std::max<size_t>(total + total / 2, 1 << 20);
+        CU(cudaMallocHost((void**)&pool->h, cap));
+        cudaError_t e = cudaMalloc((void**)&pool->d, cap);
+        if (e != cudaSuccess) { cudaFreeHost(pool->h); pool->h = nullptr; return cuda_fail(e, "cudaMalloc"); }
+        pool->cap = cap;
+    }
+    if (!pool->stream) CU(cudaStreamCreateWithFlags(&pool->stream, cudaStreamNonBlocking));
+    std::memcpy(pool->h + o_progs, progs.data(), ng * sizeof(fk::DevProgram));
+    std::memcpy(pool->h + o_jobs, jobs.data(), nj * sizeof(fk::HeteroJob));
+    double* in = reinterpret_cast<double*>(pool->h + o_in);
+    for (size_t k = 0; k < nj; k++) {
+        const fk::Topology& t = topos32[items[k].group]->t;
+        const fk_problem* p = problems[items[k].problem];
+        double* v = in + jobs[k].vars_off;
+        if (t.n_vars) std::memcpy(v, p->vars, sizeof(double) * t.n_vars);
+        for (uint32_t f = 0; f < t.n_free; f++) v[t.free_vars[f]] = free_values[items[k].problem][f];
+        double* q = in + jobs[k].param_off;
+        if (t.n_expr) {
+            if (p->param) std::memcpy(q, p->param, sizeof(double) * t.n_expr);
+            else std::fill(q, q + t.n_expr, 0.0);
+        }
+    }
+    CU(cudaMemcpyAsync(pool->d, pool->h, o_out, cudaMemcpyHostToDevice, pool->stream));
+    const int e = fk::launch_hetero_lm(reinterpret_cast<const fk::DevProgram*>(pool->d + o_progs), reinterpret_cast<const fk::HeteroJob*>(pool->d + o_jobs),
+                                       (uint32_t)nj, max_state, reinterpret_cast<const double*>(pool->d + o_in), reinterpret_cast<double*>(pool->d + o_out),
+                                       reinterpret_cast<fk_report*>(pool->d + o_rep), pool->stream);
+    if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_hetero_lm_kernel");
+    CU(cudaMemcpyAsync(pool->h + o_out, pool->d + o_out, total - o_out, cudaMemcpyDeviceToHost, pool->stream));
+    CU(cudaStreamSynchronize(pool->stream));
+    const double* out = reinterpret_cast<const double*>(pool->h + o_out);
+    const fk_report* reps = reinterpret_cast<const fk_report*>(pool->h + o_rep);
+    for (size_t k = 0; k < nj; k++) {
+        const fk::Topology& t = topos32[items[k].group]->t;
+        if (t.n_free) std::memcpy(free_values[items[k].problem], out + jobs[k].out_off, sizeof(double) * t.n_free);
+        if (reports) reports[items[k].problem] = reps[k];
+    }
+    return FK_OK;
 }
 
 int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* const* free_values, fk_report* reports,
@@ -1195,6 +1308,7 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
         std::vector<fk_report> reps;
         SmallRequest small;
         int device = 0;
+        bool done = false;  // solved by the heterogeneous launch
     };
     std::vector<Group> groups;
     std::multimap<uint64_t, size_t> by_sig;
@@ -1265,7 +1379,32 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
     int first_rc = FK_OK;
     std::string first_err;
     auto note = [&](int rc, const std::string& e) { if (rc != FK_OK && first_rc == FK_OK) { first_rc = rc; first_err = e; } };
+    // Several small groups: ONE launch of the heterogeneous kernel for all of them (one warp per system) instead of one
+    // launch, two copies and a synchronisation per topology.  Groups large enough to fill the device on their own keep
+    // the uniform batch kernels.  (FK_NO_HETERO=1: A/B knob.)
+    {
+        static const bool no_hetero = std::getenv("FK_NO_HETERO") != nullptr;
+        std::vector<size_t> small;
+        for (size_t g = 0; g < groups.size(); g++) {
+            const fk::Topology& t = groups[g].topo->t;
+            if (t.path == 0 && groups[g].members.size() < 2048 && fk::lm_smem_doubles(t.n_free, t.n_rows, t.jac_nnz, (uint32_t)t.l_rowidx.size()) * 8 <= 48 * 1024)
+                small.push_back(g);
+        }
+        if (!no_hetero && small.size() >= 2) {
+            std::vector<fk_topology*> topos32;
+            std::vector<HeteroItem> items;
+            for (size_t q = 0; q < small.size(); q++) {
+                Group& gr = groups[small[q]];
+                topos32.push_back(gr.topo->lanes32());
+                for (uint32_t i : gr.members) items.push_back({(uint32_t)q, i});
+                gr.done = true;
+            }
+            const int rc = hetero_solve(cur, topos32, items, problems, free_values, reports);
+            if (rc != FK_OK) note(rc, g_error);
+        }
+    }
     for (Group& gr : groups) {
+        if (gr.done) continue;
         const fk::Topology& t = gr.topo->t;
         const size_t cnt = gr.members.size();
         if (t.path == 2) continue;  // large systems below
@@ -1287,6 +1426,7 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
         }
     }
     for (Group& gr : groups) {
+        if (gr.done) continue;
         const fk::Topology& t = gr.topo->t;
         const size_t cnt = gr.members.size();
         if (t.path == 2) {  // large systems: one after the other through the global sparse path

@@ -197,23 +197,11 @@ __device__ __forceinline__ uint64_t trace_push(uint64_t h, uint32_t code) { retu
 // The whole LM solve of one sketch by one tile.  The reference's nested loops (outer <= 100,
 // unbounded damping loop) are flattened into one loop over damping iterations with the outer
 // bookkeeping done at accept time, so that sketches sharing a warp (TILE < 32) stay in step.
+// The LM solve of ONE sketch by one tile: `x` = the tile's shared-memory block, vars / params / out / rep = the sketch's rows.
 template <int TILE, int KIND>
-__global__ void __launch_bounds__(TILE > 128 ? TILE : 128)
-fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doubles,
-                   const double* __restrict__ vars_all, const double* __restrict__ params_all,
-                   double* __restrict__ free_out, fk_report* __restrict__ reports) {
-    extern __shared__ double smem[];
-    const int tiles_per_cta = blockDim.x / TILE;
-    const int tile_id = threadIdx.x / TILE;
-    const int lane = threadIdx.x % TILE;
-    const uint32_t sketch = blockIdx.x * tiles_per_cta + tile_id;
-    if (sketch >= n_sketches) return;
-    const unsigned msk = TileOps<TILE>::mask();
+__device__ __forceinline__ void lm_tile_solve(const DevProgram& P, int lane, unsigned msk, double* x, const double* __restrict__ vars,
+                                              const double* __restrict__ params, double* __restrict__ out, fk_report* __restrict__ rep_out) {
     const uint32_t n = P.n, m = P.m;
-
-    // per-sketch shared arrays; the stride is odd so that tiles of one warp touching the same
-    // element index land in different banks
-    double* x = smem + (size_t)tile_id * stride_doubles;
     double* xs = x + n;
     double* g = xs + n;
     double* J = g + n;          // Jacobian values at the accepted point (CSC order)
@@ -221,9 +209,6 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
     double* w = L + (P.lnnz > P.jnnz ? P.lnnz : P.jnnz);  // right-hand side / solve vector, addressed
     double* rs = w;                                        // as L[wbase + i] by the factor steps; the
                                                            // trial residuals live here outside the solve
-
-    const double* vars = vars_all + (size_t)sketch * P.n_vars;
-    const double* params = params_all + (size_t)sketch * P.n_expr;
 
     for (uint32_t i = lane; i < n; i += TILE) x[i] = __ldg(vars + __ldg(P.free_vars + i));
     if (TILE > 1) TileOps<TILE>::sync(msk);
@@ -313,7 +298,6 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
     }
 
     if (TILE > 1) TileOps<TILE>::sync(msk);
-    double* out = free_out + (size_t)sketch * n;
     for (uint32_t i = lane; i < n; i += TILE) out[i] = x[i];
     if (lane == 0) {
         fk_report rep;
@@ -324,8 +308,57 @@ fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doub
         rep.ssr = ssr;
         rep.lambda = lambda;
         rep.trace_hash = trace;
-        reports[sketch] = rep;
+        *rep_out = rep;
     }
+}
+
+// Uniform batch: every sketch shares the topology P (kernel parameter: constant bank).
+template <int TILE, int KIND>
+__global__ void __launch_bounds__(TILE > 128 ? TILE : 128)
+fk_batch_lm_kernel(const DevProgram P, uint32_t n_sketches, uint32_t stride_doubles,
+                   const double* __restrict__ vars_all, const double* __restrict__ params_all,
+                   double* __restrict__ free_out, fk_report* __restrict__ reports) {
+    extern __shared__ double smem[];
+    const int tiles_per_cta = blockDim.x / TILE;
+    const int tile_id = threadIdx.x / TILE;
+    const int lane = threadIdx.x % TILE;
+    const uint32_t sketch = blockIdx.x * tiles_per_cta + tile_id;
+    if (sketch >= n_sketches) return;
+    // per-sketch shared arrays; the stride is odd so that tiles of one warp touching the same
+    // element index land in different banks
+    lm_tile_solve<TILE, KIND>(P, lane, TileOps<TILE>::mask(), smem + (size_t)tile_id * stride_doubles, vars_all + (size_t)sketch * P.n_vars,
+                              params_all + (size_t)sketch * P.n_expr, free_out + (size_t)sketch * P.n, reports + sketch);
+}
+
+// Heterogeneous batch: every system has its own topology.  One warp per system; the warp reads its job (program index and
+// the offsets of its rows in the call's input / output buffers) and then runs the same LM solve with the program's tables
+// (32-lane tables, in device memory).  One launch for any mix of small systems: the reference's unit of work is "each
+// connected component" (fiksi/src/assemble/mod.rs:81), and a drawing is many different small components.
+__global__ void __launch_bounds__(128)
+fk_hetero_lm_kernel(const DevProgram* __restrict__ progs, const HeteroJob* __restrict__ jobs, uint32_t n_jobs, uint32_t stride_doubles,
+                    const double* __restrict__ in, double* __restrict__ out, fk_report* __restrict__ reports) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t job = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (job >= n_jobs) return;
+    const HeteroJob j = jobs[job];
+    lm_tile_solve<32, -1>(progs[j.prog], lane, 0xFFFFFFFFu, smem + (size_t)warp * stride_doubles, in + j.vars_off, in + j.param_off,
+                          out + j.out_off, reports + job);
+}
+
+int launch_hetero_lm(const DevProgram* d_progs, const HeteroJob* d_jobs, uint32_t n_jobs, uint32_t max_state_doubles, const double* d_in,
+                     double* d_out, fk_report* d_reports, void* stream) {
+    if (n_jobs == 0) return 0;
+    const uint32_t stride = max_state_doubles | 1u;
+    const size_t per_warp = (size_t)stride * sizeof(double);
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > 100 * 1024) warps >>= 1;
+    const size_t smem = per_warp * warps;
+    if (smem > 220 * 1024) return (int)cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(fk_hetero_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fk_hetero_lm_kernel<<<(n_jobs + warps - 1) / warps, 32 * warps, smem, (cudaStream_t)stream>>>(d_progs, d_jobs, n_jobs, stride, d_in, d_out, d_reports);
+    return (int)cudaGetLastError();
 }
 
 // K1 / K2 on their own: one thread per (sketch, row), used for the assembly-bandwidth metric and

@@ -45,6 +45,16 @@ __host__ __device__ inline uint32_t lm_smem_doubles(uint32_t n, uint32_t m, uint
 // (10n) + residuals (m) + Jacobian values (jnnz) + rho, alpha (10).
 __host__ __device__ inline uint32_t lbfgs_smem_doubles(uint32_t n, uint32_t m, uint32_t jnnz) { return 14u * n + m + jnnz + 10u; }
 
+// One system of a heterogeneous batch (fk_hetero_lm_kernel): its program and the offsets (in doubles) of its variable row,
+// parameter row and output row in the call's device buffers.
+struct HeteroJob {
+    uint32_t prog, pad;
+    uint64_t vars_off, param_off, out_off;
+};
+// d_progs: DevProgram views built for 32 lanes; max_state_doubles: largest lm_smem_doubles() over them.
+int launch_hetero_lm(const DevProgram* d_progs, const HeteroJob* d_jobs, uint32_t n_jobs, uint32_t max_state_doubles, const double* d_in,
+                     double* d_out, fk_report* d_reports, void* stream);
+
 // Launchers (defined in lm_kernels.cu).  `stream` is a cudaStream_t.
 int launch_batch_lm(const DevProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
                     double* free_out, fk_report* reports, void* stream);

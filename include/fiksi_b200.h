@@ -259,7 +259,7 @@ FK_API int fk_topology_batch_kernel(const fk_topology* topo, uint32_t n_sketches
 
 /* Topology cache of fk_lm_solve / fk_lm_solve_batch / fk_system_solve*: the symbolic analysis of a flattened
  * problem (the reference repeats it on every LM call, fiksi/src/solve/lm.rs:98-104) is kept in a process-wide
- * LRU keyed by the problem's structure, so that re-solving a sketch costs no analysis.  Default capacity 64
+ * LRU keyed by the problem's structure, so that re-solving a sketch costs no analysis.  Default capacity 1024
  * topologies (environment FK_TOPOLOGY_CACHE; 0 disables).  Cached topologies keep their device tables and
  * staging buffers; _clear releases them. */
 FK_API void fk_topology_cache_configure(uint32_t capacity);

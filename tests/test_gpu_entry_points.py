@@ -59,7 +59,7 @@ def test_cache_can_be_disabled_and_bounded():
             fk.lm_solve(fp, v[0][w.free_vars])
         assert api.topology_cache_stats()[2] == 2
     finally:
-        api.topology_cache_configure(64)
+        api.topology_cache_configure(1024)
 
 
 def test_heterogeneous_batch_matches_the_oracle_problem_by_problem(oracle):
