@@ -87,3 +87,64 @@ def test_rows_naming_a_variable_twice_stay_on_the_tile_kernel():
     idx = np.array([[0, 2, 0, 0], [0, 0, 0, 0]], np.uint32)
     topo = fk.Topology.from_arrays(4, kind, idx, np.arange(4), np.arange(2))
     assert not topo.sketch_kernel_info()["available"]
+
+
+def _random_topology(rng):
+    """A random small system over all 11 expression kinds, some variables fixed (as tests/test_symbolic_parity.py builds them)."""
+    n_pts = int(rng.integers(3, 10))
+    n_len = int(rng.integers(1, 3))
+    n_vars = 2 * n_pts + n_len
+    kinds, idxs = [], []
+    for _ in range(int(rng.integers(2, 14))):
+        k = int(rng.integers(0, 11))
+        pts = (2 * rng.choice(n_pts, size=4, replace=n_pts < 4)).tolist()
+        if k == 0:
+            a, b = rng.choice(n_vars, size=2, replace=False)
+            ii = [int(a), int(b), 0, 0]
+        elif k == 5:
+            ii = pts[:2] + [2 * n_pts + int(rng.integers(0, n_len)), 0]
+        elif k == 10:
+            ii = pts[:3] + [2 * n_pts + int(rng.integers(0, n_len))]
+        else:
+            ii = pts
+        kinds.append(k)
+        idxs.append(ii)
+    free = np.sort(rng.choice(n_vars, size=int(rng.integers(max(1, n_vars // 2), n_vars + 1)), replace=False))
+    return n_vars, np.array(kinds, np.uint8), np.array(idxs, np.uint32), free.astype(np.uint32), np.arange(len(kinds), dtype=np.uint32)
+
+
+def test_random_mixed_kind_topologies_all_three_kernels_agree_bit_for_bit(oracle):
+    """Forty random systems over all expression kinds with fixed variables, 96 perturbed copies each: tile kernel,
+    sketch kernel and its warp-pair shape must agree in every report field and coordinate (NaNs included), and a
+    sample must agree with the oracle."""
+    rng = np.random.default_rng(77)
+    checked = against_oracle = 0
+    for trial in range(40):
+        n_vars, kind, idx, free, rows = _random_topology(rng)
+        topo = fk.Topology.from_arrays(n_vars, kind, idx, free, rows)
+        if topo.info["path"] != 0 or not topo.sketch_kernel_info()["available"]:
+            continue
+        n = 96
+        v = rng.normal(size=(1, n_vars)) * 3.0 + rng.normal(size=(n, n_vars)) * 0.05
+        v[:, -2:] = np.abs(v[:, -2:]) + 0.5  # lengths / radii positive
+        p = np.abs(rng.normal(size=(1, len(kind)))) + 0.3 + np.zeros((n, 1))
+        xt, rt = _solve(topo, v, p, "tile")
+        xs, rs = _solve(topo, v, p, "sketch_solo")
+        xp, rp = _solve(topo, v, p, "sketch_pair")
+        for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash"):
+            assert np.array_equal(rs[key], rt[key]), (trial, key)
+            assert np.array_equal(rp[key], rt[key]), (trial, key)
+        assert np.array_equal(rs["lambda"], rt["lambda"], equal_nan=True) and np.array_equal(rs["ssr"], rt["ssr"], equal_nan=True)
+        assert np.array_equal(xs, xt, equal_nan=True) and np.array_equal(xp, xt, equal_nan=True), trial
+        checked += 1
+        if trial % 4 == 0:
+            op, keep = oracle.make_problem(v[0], kind, idx, p[0], free, rows)
+            xo, ro, _ = oracle.lm_solve_batch_uniform(op, v[:16], p[:16], threads=4)
+            same = (rs["trace_hash"][:16] == ro["trace_hash"]) & (rs["exit_reason"][:16] == ro["exit_reason"])
+            assert same.mean() >= 0.8, (trial, same.mean())
+            ok = same & np.isfinite(xo).all(axis=1) & (ro["exit_reason"] == 0)
+            if ok.any():
+                err = np.max(np.abs(xs[:16][ok] - xo[ok]), axis=1) / np.maximum(np.max(np.abs(xo[ok]), axis=1), 1e-300)
+                assert err.max() <= 1e-6, (trial, err.max())  # (rank-deficient random systems: the converged point is not unique to 1e-9)
+            against_oracle += 1
+    assert checked >= 25 and against_oracle >= 5
