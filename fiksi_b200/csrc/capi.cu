@@ -765,7 +765,7 @@ static int launch_optimizer(const fk::DevProgram& prog, const DeviceProgram& ful
 
 // Small request (one sketch, a handful): the caller's (pageable) arrays go through ONE pinned staging block -- one
 // copy in, the kernel, one copy out, one synchronisation -- instead of four pageable copies on the chunk pipeline.
-// Split in two halves so that a heterogeneous batch can have the requests of all its topologies in flight at once.
+// (Enqueue and finish are separate so that a caller can overlap host work with the request.)
 struct SmallRequest {
     DevicePipeline* pl = nullptr;
     std::unique_lock<std::mutex> lock;  // the pipeline's staging block is ours until finish()
@@ -1306,7 +1306,6 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
         // staging of the group's uniform batch
         std::vector<double> vars, param, out;
         std::vector<fk_report> reps;
-        SmallRequest small;
         int device = 0;
         bool done = false;  // solved by the heterogeneous launch
     };
@@ -1371,9 +1370,8 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
     }
     int cur = 0;
     if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
-    // ---- solve: small groups of all topologies are in flight together, one stream per (topology, device) ------
-    // With several devices and at least as many groups, whole groups go to devices round robin; otherwise every
-    // large group is sharded by sketch over the devices (fk_batch_solve).
+    // ---- solve.  With several devices and at least as many groups, whole groups go to devices round robin; otherwise
+    // every large group is sharded by sketch over the devices (fk_batch_solve).
     const bool groups_to_devices = n_gpus > 1 && groups.size() >= (size_t)n_gpus;
     size_t rr = 0;
     int first_rc = FK_OK;
@@ -1395,12 +1393,30 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
             std::vector<HeteroItem> items;
             for (size_t q = 0; q < small.size(); q++) {
                 Group& gr = groups[small[q]];
-                topos32.push_back(gr.topo->lanes32());
-                for (uint32_t i : gr.members) items.push_back({(uint32_t)q, i});
+                fk_topology* t32 = gr.topo->lanes32();
+                if (t32->t.tile != 32) continue;  // no 32-lane tables (FK_NO_LATENCY_TWIN): the group keeps the uniform kernel
+                for (uint32_t i : gr.members) items.push_back({(uint32_t)topos32.size(), i});
+                topos32.push_back(t32);
                 gr.done = true;
             }
-            const int rc = hetero_solve(cur, topos32, items, problems, free_values, reports);
-            if (rc != FK_OK) note(rc, g_error);
+            if (!items.empty() && n_gpus > 1 && items.size() >= 64u * (size_t)n_gpus) {
+                // several devices: contiguous shares of the systems, one host thread and one launch per device
+                std::vector<int> rcs(n_gpus, FK_OK);
+                std::vector<std::string> errs(n_gpus);
+                std::vector<std::thread> pool;
+                for (int g = 0; g < n_gpus; g++)
+                    pool.emplace_back([&, g] {
+                        const size_t lo = items.size() * g / n_gpus, hi = items.size() * (g + 1) / n_gpus;
+                        std::vector<HeteroItem> part(items.begin() + lo, items.begin() + hi);
+                        rcs[g] = hetero_solve(g, topos32, part, problems, free_values, reports);
+                        if (rcs[g] != FK_OK) errs[g] = g_error;
+                    });
+                for (auto& th : pool) th.join();
+                for (int g = 0; g < n_gpus; g++) note(rcs[g], errs[g]);
+            } else if (!items.empty()) {
+                const int rc = hetero_solve(cur, topos32, items, problems, free_values, reports);
+                if (rc != FK_OK) note(rc, g_error);
+            }
         }
     }
     for (Group& gr : groups) {
@@ -1420,10 +1436,6 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
             }
         }
         gr.device = groups_to_devices ? (int)(rr++ % (size_t)n_gpus) : cur;
-        if (small_fits(t, (uint32_t)cnt)) {
-            std::string e;
-            note(small_enqueue(gr.topo.get(), gr.device, 0, (uint32_t)cnt, gr.vars.data(), gr.param.data(), 0, gr.small, &e), e);
-        }
     }
     for (Group& gr : groups) {
         if (gr.done) continue;
@@ -1438,11 +1450,7 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
         }
         int rc = FK_OK;
         std::string e;
-        if (gr.small.pl) {
-            rc = small_finish(t, 0, gr.small, gr.out.data(), gr.reps.data(), &e);
-        } else if (small_fits(t, (uint32_t)cnt)) {
-            continue;  // its enqueue failed: already noted
-        } else if (groups_to_devices || n_gpus == 1) {
+        if (groups_to_devices || n_gpus == 1 || small_fits(t, (uint32_t)cnt)) {
             rc = run_device_range(gr.topo.get(), gr.device, 0, (uint32_t)cnt, gr.vars.data(), gr.param.data(), gr.out.data(), gr.reps.data(), &e, 0);
         } else {
             rc = fk_batch_solve(gr.topo.get(), (uint32_t)cnt, gr.vars.data(), gr.param.data(), gr.out.data(), gr.reps.data(), n_gpus);

@@ -88,3 +88,21 @@ def test_single_pass_and_system_solve_on_two_devices():
     xa, sa, ra = topo.batch_system_solve(w.raw_vars, w.raw_param, device=0)
     xb, sb, rb = topo.batch_system_solve(w.raw_vars, w.raw_param, device=1)
     assert np.array_equal(xa, xb) and np.array_equal(sa, sb) and np.array_equal(ra["trace_hash"], rb["trace_hash"])
+
+
+def test_heterogeneous_batch_split_over_two_devices():
+    """Enough different small systems for both devices: each device gets a contiguous share and one launch of the
+    heterogeneous kernel; the answers are those of a single-device call."""
+    _need_two()
+    probs, x0s, keeps = [], [], []
+    for n_points in range(4, 20):
+        w = wl.truss(10, n_points=n_points)
+        v, p, s = w.prepare()
+        for j in range(10):
+            fp, keep = fk.make_problem(v[j], w.kind, w.idx, p[j], w.free_vars, w.rows)
+            probs.append(fp); keeps.append(keep); x0s.append(v[j][w.free_vars])
+    xa, ra = fk.lm_solve_batch(probs, x0s, n_gpus=1)
+    xb, rb = fk.lm_solve_batch(probs, x0s, n_gpus=2)
+    for a, b in zip(xa, xb):
+        assert np.array_equal(a, b)
+    assert np.array_equal(ra["trace_hash"], rb["trace_hash"])
