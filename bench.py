@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 
 N_PER_GPU = 65536
 METRIC = "lm_solved_sketches_per_sec"
+WORKLOAD = ("configs[1]: batch of 65,536 perturbed 20-point rigid distance trusses per GPU "
+            "(40 free vars, 37 PPD rows, 148 J nnz)")
 UNIT = "sketches/s"
 
 
@@ -106,7 +108,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: 20-point rigid distance truss batch (40 vars, 37 rows per sketch)",
+        "config": {"workload": WORKLOAD,
                    "sketches_per_gpu": n_sample, "sketches_per_step": n_sample,
                    "note": "the reference's CPU algorithm (oracle port; no Rust toolchain here) on all host threads, whole 65,536-sketch steps"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
@@ -297,8 +299,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch of 65,536 perturbed 20-point rigid distance trusses per GPU "
-                               "(40 free vars, 37 PPD rows, 148 J nnz)",
+        "config": {"workload": WORKLOAD,
                    "sketches_per_gpu": n, "sketches_per_step": n, "kernel": kernel_name,
                    "state_doubles_per_sketch": topo.sketch_kernel_info()["state_doubles"] if uses_sketch_kernel else info["smem_bytes"] // 8,
                    "l2": "flushed between timed steps (512 MB memset)", "parallelism": f"sketch-sharded x{world}, no data-path collective",
