@@ -179,9 +179,11 @@ struct PrepareTables {
     uint8_t* d_kind = nullptr;
     uint32_t* d_perturb = nullptr;
     double* d_draws = nullptr;
+    uint32_t* d_free_draw = nullptr;  // sketch kernel's raw mode: draw index per free column / per fixed variable the rows read
+    uint32_t* d_fix_draw = nullptr;
     ~PrepareTables() {
         if (device >= 0) cudaSetDevice(device);
-        cudaFree(d_kind); cudaFree(d_perturb); cudaFree(d_draws);
+        cudaFree(d_kind); cudaFree(d_perturb); cudaFree(d_draws); cudaFree(d_free_draw); cudaFree(d_fix_draw);
     }
 };
 
@@ -919,6 +921,17 @@ static int prepare_tables_for(fk_topology* topo, int device, const fk_prepare_op
     if (t.n_expr) CU(cudaMemcpy(q->d_kind, t.kind.data(), t.n_expr, cudaMemcpyHostToDevice));
     if (!list.empty()) CU(cudaMemcpy(q->d_perturb, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(q->d_draws, draws.data(), sizeof(double) * draws.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<uint32_t> where(t.n_vars, 0xFFFFFFFFu), free_draw(std::max<uint32_t>(t.n_free, 1), 0xFFFFFFFFu), fix_draw(std::max<uint32_t>(t.sk.nfix, 1), 0xFFFFFFFFu);
+        for (size_t j = 0; j < list.size(); j++) where[list[j]] = (uint32_t)j;
+        for (uint32_t c = 0; c < t.n_free; c++) free_draw[c] = where[t.free_vars[c]];
+        if (t.sk.ok)
+            for (uint32_t i = 0; i < t.sk.nfix; i++) fix_draw[i] = where[t.sk.tab[t.sk.off_fix + i]];
+        CU(cudaMalloc(&q->d_free_draw, sizeof(uint32_t) * free_draw.size()));
+        CU(cudaMalloc(&q->d_fix_draw, sizeof(uint32_t) * fix_draw.size()));
+        CU(cudaMemcpy(q->d_free_draw, free_draw.data(), sizeof(uint32_t) * free_draw.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(q->d_fix_draw, fix_draw.data(), sizeof(uint32_t) * fix_draw.size(), cudaMemcpyHostToDevice));
+    }
     p = std::move(q);
     *out = p.get();
     return FK_OK;
@@ -959,11 +972,13 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         if (!p->d_raw_param) CU(cudaMalloc(&p->d_raw_param, sizeof(double) * std::max<size_t>(1, (size_t)p->capacity * t.n_expr)));
         if (!p->d_scales) CU(cudaMalloc(&p->d_scales, sizeof(double) * p->capacity));
     }
+    static const bool no_fuse = std::getenv("FK_NO_FUSED_PREPARE") != nullptr;  // A/B knob
     uint32_t s = 0;
     for (uint32_t at = 0; at < n && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
         const uint32_t cnt = std::min(chunk, n - at);
         fk_batch_plan* p = pl->plans[s];
         cudaStream_t st = pl->streams[s];
+        const bool fused = !no_fuse && fk::batch_lm_uses_sketch_kernel(*p->prog, cnt) && fk::sk_raw_fits(*p->prog->sketch_prog, shared);
         CU(cudaStreamSynchronize(st));  // the plan's buffers are reused only after its previous chunk has drained
         p->n = cnt;
         if (t.n_vars) CU(cudaMemcpyAsync(p->d_raw_vars, raw_vars + (size_t)at * t.n_vars, sizeof(double) * (size_t)cnt * t.n_vars, cudaMemcpyHostToDevice, st));
@@ -971,12 +986,22 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
             if (shared) CU(cudaMemcpyAsync(p->d_raw_param, raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, st));
             else CU(cudaMemcpyAsync(p->d_raw_param, raw_param + (size_t)at * t.n_expr, sizeof(double) * (size_t)cnt * t.n_expr, cudaMemcpyHostToDevice, st));
         }
-        int e = fk::launch_batch_prepare(cnt, t.n_vars, t.n_expr, pt->d_kind, shared, (uint32_t)pt->perturb_vars.size(), pt->d_perturb, pt->d_draws,
+        int e;
+        if (fused) {  // the sketch-per-thread kernel scales, perturbs and writes back itself (SkRaw)
+            fk::SkRaw raw{};
+            raw.raw_vars = p->d_raw_vars; raw.raw_param = p->d_raw_param; raw.shared_param = shared ? 1u : 0u;
+            raw.kinds = pt->d_kind; raw.free_draw = pt->d_free_draw; raw.fix_draw = pt->d_fix_draw; raw.draws = pt->d_draws;
+            raw.scales = p->d_scales;
+            e = fk::launch_batch_lm_sketch(*p->prog->sketch_prog, cnt, nullptr, nullptr, p->d_out, p->d_rep, st, &raw);
+            p->launches += 1;
+        } else {
+            e = fk::launch_batch_prepare(cnt, t.n_vars, t.n_expr, pt->d_kind, shared, (uint32_t)pt->perturb_vars.size(), pt->d_perturb, pt->d_draws,
                                          p->d_raw_vars, p->d_raw_param, p->d_vars, p->d_params, p->d_scales, st);
-        if (e == 0) e = fk::launch_batch_lm(*p->prog, cnt, p->d_vars, p->d_params, p->d_out, p->d_rep, st);
-        if (e == 0) e = fk::launch_batch_unscale(cnt, t.n_free, p->d_scales, p->d_out, st);
+            if (e == 0) e = fk::launch_batch_lm(*p->prog, cnt, p->d_vars, p->d_params, p->d_out, p->d_rep, st);
+            if (e == 0) e = fk::launch_batch_unscale(cnt, t.n_free, p->d_scales, p->d_out, st);
+            p->launches += 3;
+        }
         if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_system_solve kernels");
-        p->launches += 3;
         if (t.n_free) CU(cudaMemcpyAsync(free_out + (size_t)at * t.n_free, p->d_out, sizeof(double) * (size_t)cnt * t.n_free, cudaMemcpyDeviceToHost, st));
         if (scales_out) CU(cudaMemcpyAsync(scales_out + at, p->d_scales, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
         if (reports) CU(cudaMemcpyAsync(reports + at, p->d_rep, sizeof(fk_report) * (size_t)cnt, cudaMemcpyDeviceToHost, st));

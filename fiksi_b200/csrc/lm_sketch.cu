@@ -256,10 +256,76 @@ __device__ __forceinline__ double sk_back_column(const uint32_t* body, const cha
 
 __device__ __forceinline__ uint64_t sk_trace_push(uint64_t h, uint32_t code) { return h * 3ull + code + 1ull; }
 
+// Stages one sketch's inputs in the interleaved layout; returns the sketch's scale (1 in plain mode).
+// Plain mode: the caller's (already scaled and perturbed) rows go straight in with 8-byte asynchronous copies: all of a
+// sketch's loads are in flight at once and the thread waits once (with one warp or two per SM nothing else would hide the
+// DRAM latency of a load-then-store loop).  Raw mode (SkRaw): the whole variable row (and the parameter row unless shared)
+// is staged in the g and H regions first, then scale, scaling and perturbation run exactly as fk_batch_prepare_kernel does.
+__device__ __forceinline__ double sk_stage_inputs(const SkProgram& P, const SkRaw& R, const uint32_t* tab, char* base, char* xp, uint32_t sk,
+                                                  const double* __restrict__ vars_all, const double* __restrict__ params_all) {
+    const uint32_t n = P.n;
+    if (R.raw_vars == nullptr) {
+        const double* vars = vars_all + (size_t)sk * P.n_vars;
+        const double* params = params_all + (size_t)sk * P.n_expr;
+        for (uint32_t i = 0; i < n; i++) cp_async8(xp + (i << 8), vars + tab[P.off_free + i]);
+        for (uint32_t i = 0; i < P.nfix; i++) cp_async8(base + ((P.fx + i) << 8), vars + tab[P.off_fix + i]);
+        for (uint32_t i = 0; i < P.npar; i++) cp_async8(base + ((P.pr + i) << 8), params + tab[P.off_par + i]);
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        return 1.0;
+    }
+    char* S = base + (P.w << 8);  // scratch: g and H regions, n + nnz(L) entries (sk_raw_fits)
+    const double* rv = R.raw_vars + (size_t)sk * P.n_vars;
+    const double* rp = R.raw_param + (R.shared_param ? 0 : (size_t)sk * P.n_expr);
+    for (uint32_t i = 0; i < P.n_vars; i++) cp_async8(S + (i << 8), rv + i);
+    if (!R.shared_param)
+        for (uint32_t e = 0; e < P.n_expr; e++) cp_async8(S + ((P.n_vars + e) << 8), rp + e);
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    // assemble/mod.rs:32-44 via utils.rs:12-19: all variables left to right, then the distance parameters in expression order
+    double sum = 0.0;
+    uint32_t cnt = P.n_vars;
+    {
+        uint32_t i = 0;
+        for (; i + 8 <= P.n_vars; i += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = ldp(S, (i + u) << 8);
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum = sum + v[u] * v[u];
+        }
+        for (; i < P.n_vars; i++) {
+            const double v = ldp(S, i << 8);
+            sum = sum + v * v;
+        }
+    }
+    for (uint32_t e = 0; e < P.n_expr; e++) {
+        const uint32_t kd = __ldg(R.kinds + e);
+        if (kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE) {
+            const double q = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
+            sum = sum + q * q;
+            cnt++;
+        }
+    }
+    const double scale = sqrt(sum / (double)cnt);
+    const double recip = 1.0 / scale;
+    auto perturbed = [&](double col, uint32_t j) {  // assemble/mod.rs:113-124
+        return j == kNone ? col : col + (col * (1.0 / 8196.0) * __ldg(R.draws + 2 * j) + (1.0 / 65568.0) * __ldg(R.draws + 2 * j + 1));
+    };
+    for (uint32_t c = 0; c < n; c++) stp(xp, c << 8, perturbed(ldp(S, tab[P.off_free + c] << 8) * recip, __ldg(R.free_draw + c)));
+    for (uint32_t i = 0; i < P.nfix; i++)
+        stp(base, (P.fx + i) << 8, perturbed(ldp(S, tab[P.off_fix + i] << 8) * recip, __ldg(R.fix_draw + i)));
+    for (uint32_t i = 0; i < P.npar; i++) {
+        const uint32_t e = tab[P.off_par + i];
+        const uint32_t kd = __ldg(R.kinds + e);
+        const double q = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
+        stp(base, (P.pr + i) << 8, (kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE) ? recip * q : q);
+    }
+    return scale;
+}
+
 constexpr int kSkMaxWarps = 4;
 
 __global__ void __launch_bounds__(32 * kSkMaxWarps)
-fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
+fk_batch_lm_sketch_kernel(const SkProgram P, const SkRaw R, uint32_t n_sketches, const double* __restrict__ vars_all,
                           const double* __restrict__ params_all, double* __restrict__ free_out, fk_report* __restrict__ reports) {
     extern __shared__ __align__(16) char sk_smem[];
     // the tables, once per CTA
@@ -274,8 +340,6 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
     const uint32_t sk = valid ? sketch : n_sketches - 1;  // idle lanes shadow the last sketch and store nothing
     char* const base = sk_smem + (size_t)P.tab_words * 4 + (size_t)warp * P.entries * 256u + lane * 8u;
     const uint32_t n = P.n;
-    const double* vars = vars_all + (size_t)sk * P.n_vars;
-    const double* params = params_all + (size_t)sk * P.n_expr;
 
     // accepted / trial point: the two roles swap per lane on accept (a register exchange instead of a copy)
     char* xp = base + (P.xa << 8);
@@ -285,13 +349,7 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
     const char* const fx = base + (P.fx << 8);
     const char* const pr = base + (P.pr << 8);
 
-    // The caller's rows ([sketch][variable]) go straight into the interleaved layout with 8-byte asynchronous
-    // copies: all of a sketch's loads are in flight at once and the thread waits once (with one warp or two per
-    // SM nothing else would hide the DRAM latency of a load-then-store loop).
-    for (uint32_t i = 0; i < n; i++) cp_async8(xp + (i << 8), vars + tab[P.off_free + i]);
-    for (uint32_t i = 0; i < P.nfix; i++) cp_async8(base + ((P.fx + i) << 8), vars + tab[P.off_fix + i]);
-    for (uint32_t i = 0; i < P.npar; i++) cp_async8(base + ((P.pr + i) << 8), params + tab[P.off_par + i]);
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    const double scale = sk_stage_inputs(P, R, tab, base, xp, sk, vars_all, params_all);
 
     double ssr = 0.0, lambda = 0.5, dn = 0.0;  // lm.rs:108
     uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
@@ -501,7 +559,12 @@ fk_batch_lm_sketch_kernel(const SkProgram P, uint32_t n_sketches, const double* 
 
     if (!valid) return;
     double* out = free_out + (size_t)sketch * n;
-    for (uint32_t i = 0; i < n; i++) out[i] = ldp(xp, i << 8);
+    if (R.raw_vars == nullptr) {
+        for (uint32_t i = 0; i < n; i++) out[i] = ldp(xp, i << 8);
+    } else {  // system.variables[var] = system_scale * x[k] (assemble/mod.rs:161-166)
+        for (uint32_t i = 0; i < n; i++) out[i] = scale * ldp(xp, i << 8);
+        if (R.scales) R.scales[sketch] = scale;
+    }
     fk_report rep;
     rep.exit_reason = exit_reason;
     rep.outer_iters = outer_iters;
@@ -712,7 +775,7 @@ __device__ __forceinline__ void sk_column_dispatch_half(uint32_t C, const uint32
 }
 
 __global__ void __launch_bounds__(64)
-fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
+fk_batch_lm_sketch_pair_kernel(const SkProgram P, const SkRaw R, uint32_t n_sketches, const double* __restrict__ vars_all,
                                const double* __restrict__ params_all, double* __restrict__ free_out, fk_report* __restrict__ reports) {
     extern __shared__ __align__(16) char sk_smem[];
     __shared__ int ctrl;  // leader -> helper after an evaluation: 0 iterate, 1 evaluate the accepted point again, 2 done
@@ -732,6 +795,7 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
 
     if (role == 1) {
         // ---- helper ---------------------------------------------------------------------------------------
+        if (R.raw_vars != nullptr) __syncthreads();  // raw mode: the leader stages the inputs in the g and H regions first
         for (;;) {
             uint32_t i = 0;
             for (; i + 8 <= n; i += 8)
@@ -800,16 +864,12 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
     }
 
     // ---- leader ---------------------------------------------------------------------------------------------
-    const double* vars = vars_all + (size_t)sk * P.n_vars;
-    const double* params = params_all + (size_t)sk * P.n_expr;
     char* xp = base + (P.xa << 8);
     char* xsp = base + (P.xb << 8);
     const char* const fx = base + (P.fx << 8);
     const char* const pr = base + (P.pr << 8);
-    for (uint32_t i = 0; i < n; i++) cp_async8(xp + (i << 8), vars + tab[P.off_free + i]);
-    for (uint32_t i = 0; i < P.nfix; i++) cp_async8(base + ((P.fx + i) << 8), vars + tab[P.off_fix + i]);
-    for (uint32_t i = 0; i < P.npar; i++) cp_async8(base + ((P.pr + i) << 8), params + tab[P.off_par + i]);
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    const double scale = sk_stage_inputs(P, R, tab, base, xp, sk, vars_all, params_all);
+    if (R.raw_vars != nullptr) __syncthreads();  // the helper may clear g and H now
 
     double ssr = 0.0, lambda = 0.5, dn = 0.0;  // lm.rs:108
     uint32_t exit_reason = FK_EXIT_MAX_OUTER, outer_iters = 0, factorizations = 0, accepted = 0;
@@ -1004,7 +1064,12 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, uint32_t n_sketches, const dou
     }
     if (!valid) return;
     double* out = free_out + (size_t)sketch * n;
-    for (uint32_t i = 0; i < n; i++) out[i] = ldp(xp, i << 8);
+    if (R.raw_vars == nullptr) {
+        for (uint32_t i = 0; i < n; i++) out[i] = ldp(xp, i << 8);
+    } else {  // system.variables[var] = system_scale * x[k] (assemble/mod.rs:161-166)
+        for (uint32_t i = 0; i < n; i++) out[i] = scale * ldp(xp, i << 8);
+        if (R.scales) R.scales[sketch] = scale;
+    }
     fk_report rep;
     rep.exit_reason = exit_reason;
     rep.outer_iters = outer_iters;
@@ -1080,9 +1145,14 @@ uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count) {
 }
 
 int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const double* vars, const double* params, double* free_out,
-                           fk_report* reports, void* stream) {
+                           fk_report* reports, void* stream, const SkRaw* raw_opt) {
     if (n_sketches == 0) return 0;
     if (!sk_fits(prog.entries, prog.tab_words)) return (int)cudaErrorInvalidConfiguration;
+    SkRaw raw{};
+    if (raw_opt) {
+        if (!sk_raw_fits(prog, raw_opt->shared_param != 0)) return (int)cudaErrorInvalidConfiguration;
+        raw = *raw_opt;
+    }
     int pair_ctas = 0;
     if (sk_use_pair(prog, &pair_ctas)) {
         const size_t smem = (size_t)prog.tab_words * 4 + ((size_t)prog.entries + kPairExtra) * 256;
@@ -1090,7 +1160,7 @@ int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const dou
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(fk_batch_lm_sketch_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        fk_batch_lm_sketch_pair_kernel<<<(n_sketches + 31) / 32, 64, smem, (cudaStream_t)stream>>>(prog, n_sketches, vars, params, free_out, reports);
+        fk_batch_lm_sketch_pair_kernel<<<(n_sketches + 31) / 32, 64, smem, (cudaStream_t)stream>>>(prog, raw, n_sketches, vars, params, free_out, reports);
         return (int)cudaGetLastError();
     }
     int best_w, ctas;
@@ -1102,7 +1172,7 @@ int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const dou
     if (e != cudaSuccess) return (int)e;
     const uint32_t per_cta = 32u * (uint32_t)best_w;
     const uint32_t grid = (n_sketches + per_cta - 1) / per_cta;
-    fk_batch_lm_sketch_kernel<<<grid, per_cta, smem, (cudaStream_t)stream>>>(prog, n_sketches, vars, params, free_out, reports);
+    fk_batch_lm_sketch_kernel<<<grid, per_cta, smem, (cudaStream_t)stream>>>(prog, raw, n_sketches, vars, params, free_out, reports);
     return (int)cudaGetLastError();
 }
 

@@ -33,6 +33,25 @@ struct SkProgram {
     const uint32_t* tab;  // DEVICE memory, 16-byte aligned; copied into shared memory by every CTA
 };
 
+// Raw mode (fk_batch_system_solve): the kernel takes UNSCALED variables and parameters and does assemble::solve's
+// pre- and post-processing itself (fiksi/src/assemble/mod.rs:32-44,58-79,113-124,161-166): RMS scale of the sketch
+// (sequential sums in the reference's order), variables * (1 / scale), distances * (1 / scale), the seeded perturbation
+// of the listed variables, and scale * x on the way out.  All pointers are device memory; raw_vars == nullptr: plain mode.
+struct SkRaw {
+    const double* raw_vars;     // [n][n_vars]
+    const double* raw_param;    // [n][n_expr], or one row when shared_param
+    uint32_t shared_param, pad;
+    const uint8_t* kinds;       // [n_expr]
+    const uint32_t* free_draw;  // [n]: position of free column c in the perturbation list, 0xFFFFFFFF if it draws nothing
+    const uint32_t* fix_draw;   // [nfix]: the same for the fixed variables the rows read
+    const double* draws;        // [2 x perturbed variables] (fiksi/src/rand.rs:24-39)
+    double* scales;             // [n] out, may be null
+};
+// Raw mode stages a sketch's variables (and its parameters unless shared) in the g and H regions before the first evaluation.
+inline bool sk_raw_fits(const SkProgram& p, bool shared_param) {
+    return (uint64_t)p.n_vars + (shared_param ? 0u : p.n_expr) <= (uint64_t)p.n + p.lnnz;
+}
+
 // Limits: one warp (32 sketches x `entries` doubles) plus the tables must fit an SM's shared memory.
 constexpr uint32_t kSkMaxEntries = 840;
 constexpr uint32_t kSkMaxTabWords = 16384;
@@ -41,7 +60,7 @@ inline bool sk_fits(uint32_t entries, size_t tab_words) {
 }
 
 int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const double* vars, const double* params,
-                           double* free_out, fk_report* reports, void* stream);
+                           double* free_out, fk_report* reports, void* stream, const SkRaw* raw = nullptr);
 // Sketches one full wave of the kernel holds on a device with sm_count SMs (callers that cut a batch into chunks
 // make the chunks whole waves: with one or two CTAs per SM a partial wave leaves SMs idle for a whole solve).
 uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count);
