@@ -726,7 +726,7 @@ int fk_topology_batch_kernel(const fk_topology* topo, uint32_t n_sketches) {
     fk::DevProgram p{};
     p.sketch_prog = (k.ok && fk::sk_fits(k.entries, k.tab.size())) ? &probe : nullptr;
     if (!fk::batch_lm_uses_sketch_kernel(p, n_sketches)) return 0;
-    return fk::sketch_kernel_is_pair(probe) ? 2 : 1;
+    return fk::sketch_kernel_is_pair(probe, n_sketches) ? 2 : 1;
 }
 
 void* fk_host_alloc(size_t bytes) {
@@ -1403,14 +1403,14 @@ int fk_lm_solve_batch(uint32_t n, const fk_problem* const* problems, double* con
     std::string first_err;
     auto note = [&](int rc, const std::string& e) { if (rc != FK_OK && first_rc == FK_OK) { first_rc = rc; first_err = e; } };
     // Several small groups: ONE launch of the heterogeneous kernel for all of them (one warp per system) instead of one
-    // launch, two copies and a synchronisation per topology.  Groups large enough to fill the device on their own keep
-    // the uniform batch kernels.  (FK_NO_HETERO=1: A/B knob.)
+    // launch, two copies and a synchronisation per topology.  Groups of 64 systems and more keep the uniform batch kernels
+    // (from there the sketch-per-thread kernel is the faster one).  (FK_NO_HETERO=1: A/B knob.)
     {
         static const bool no_hetero = std::getenv("FK_NO_HETERO") != nullptr;
         std::vector<size_t> small;
         for (size_t g = 0; g < groups.size(); g++) {
             const fk::Topology& t = groups[g].topo->t;
-            if (t.path == 0 && groups[g].members.size() < 2048 && fk::lm_smem_doubles(t.n_free, t.n_rows, t.jac_nnz, (uint32_t)t.l_rowidx.size()) * 8 <= 48 * 1024)
+            if (t.path == 0 && groups[g].members.size() < 64 && fk::lm_smem_doubles(t.n_free, t.n_rows, t.jac_nnz, (uint32_t)t.l_rowidx.size()) * 8 <= 48 * 1024)
                 small.push_back(g);
         }
         if (!no_hetero && small.size() >= 2) {

@@ -1052,7 +1052,10 @@ int batch_lm_uses_sketch_kernel(const DevProgram& prog, uint32_t n_sketches) {
     if (forced >= 0) return forced >= 1 ? 1 : 0;
     static const uint32_t min_batch = [] {
         const char* e = std::getenv("FK_LM_SKETCH_MIN");
-        return (uint32_t)(e ? std::max(1, std::atoi(e)) : 4096);
+        // measured (tools/lm_ab_small.py): the sketch kernel is ahead of the tile kernel from 256 sketches up on every topology
+        // tried, also in latency per batch (20-point truss, 256 sketches: 143 vs 165 us); below a warp's worth of sketches the
+        // tile kernel's lanes-per-sketch parallelism wins
+        return (uint32_t)(e ? std::max(1, std::atoi(e)) : 64);
     }();
     return n_sketches >= min_batch ? 1 : 0;
 }

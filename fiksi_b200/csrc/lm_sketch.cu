@@ -1109,7 +1109,7 @@ static void sk_shape(const SkProgram& prog, int* warps_per_cta, int* ctas_per_sm
 
 // The warp-pair variant is used when the solo shape leaves schedulers idle (fewer than four warps per SM) and the
 // pair shape keeps as many sketches in flight.  FK_SK_PAIR=0|1 forces the choice (A/B knob).
-static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
+static bool sk_use_pair(const SkProgram& prog, uint32_t n_sketches, int* ctas_per_sm) {
     const size_t per_cta = (size_t)prog.tab_words * 4 + ((size_t)prog.entries + kPairExtra) * 256;
     if (per_cta > 227 * 1024) return false;
     const int pair_ctas = (int)std::min<size_t>(8, (228 * 1024) / (per_cta + 1024));
@@ -1122,6 +1122,9 @@ static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
     const int forced = choice == 2 ? 0 : (choice == 3 ? 1 : env_forced);
     if (forced == 0) return false;
     if (forced == 1) return true;
+    // a batch that does not fill the device anyway: every group of 32 sketches gets its two warps for free, and the pair is
+    // the faster shape per group (tools/lm_ab_small.py: 256-3,072 sketches, pair 5-15 % ahead of solo on every topology tried)
+    if ((uint64_t)(n_sketches + 31) / 32 <= (uint64_t)pair_ctas * 148u) return true;
     int wpc, ctas;
     sk_shape(prog, &wpc, &ctas);
     const int solo_warps = wpc * ctas;
@@ -1131,14 +1134,14 @@ static bool sk_use_pair(const SkProgram& prog, int* ctas_per_sm) {
     return solo_warps < 4 && pair_ctas >= solo_warps;
 }
 
-int sketch_kernel_is_pair(const SkProgram& prog) {
+int sketch_kernel_is_pair(const SkProgram& prog, uint32_t n_sketches) {
     int ctas = 0;
-    return sk_use_pair(prog, &ctas) ? 1 : 0;
+    return sk_use_pair(prog, n_sketches, &ctas) ? 1 : 0;
 }
 
 uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count) {
     int pair_ctas = 0;
-    if (sk_use_pair(prog, &pair_ctas)) return 32u * (uint32_t)pair_ctas * (uint32_t)sm_count;
+    if (sk_use_pair(prog, 0xFFFFFFFFu, &pair_ctas)) return 32u * (uint32_t)pair_ctas * (uint32_t)sm_count;
     int wpc, ctas;
     sk_shape(prog, &wpc, &ctas);
     return 32u * (uint32_t)wpc * (uint32_t)ctas * (uint32_t)sm_count;
@@ -1154,7 +1157,7 @@ int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const dou
         raw = *raw_opt;
     }
     int pair_ctas = 0;
-    if (sk_use_pair(prog, &pair_ctas)) {
+    if (sk_use_pair(prog, n_sketches, &pair_ctas)) {
         const size_t smem = (size_t)prog.tab_words * 4 + ((size_t)prog.entries + kPairExtra) * 256;
         cudaError_t e = cudaFuncSetAttribute(fk_batch_lm_sketch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

@@ -64,7 +64,7 @@ int launch_batch_lm_sketch(const SkProgram& prog, uint32_t n_sketches, const dou
 // Sketches one full wave of the kernel holds on a device with sm_count SMs (callers that cut a batch into chunks
 // make the chunks whole waves: with one or two CTAs per SM a partial wave leaves SMs idle for a whole solve).
 uint32_t sketch_kernel_wave(const SkProgram& prog, int sm_count);
-// 1: the warp-pair shape (two warps share 32 sketches) is the one launched for this program, 0: one warp per 32 sketches.
-int sketch_kernel_is_pair(const SkProgram& prog);
+// 1: the warp-pair shape (two warps share 32 sketches) is the one launched for a batch of this size, 0: one warp per 32 sketches.
+int sketch_kernel_is_pair(const SkProgram& prog, uint32_t n_sketches);
 
 }  // namespace fk
