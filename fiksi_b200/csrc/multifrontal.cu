@@ -29,15 +29,14 @@ __device__ __forceinline__ void flag_pivot(int* status, double d) {
     else if (!(d > 0.0) || d == INFINITY) atomicMax(status, 1);
 }
 
-// 1/d: hardware seed + two Newton steps (relative error ~1e-16, no slow path, no branches).
+// 1/d: hardware seed (about 20 bits) + one third-order step r (1 + e + e^2), e = 1 - d r: relative error ~e^3 < 1e-17
+// before rounding, three dependent FMAs (two Newton steps are four), no slow path, no branches.
 __device__ __forceinline__ double fast_rcp(double d) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-d, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // ---- small subtrees: one warp per subtree, supernodes in ascending (= topological) order ---------------
@@ -354,12 +353,12 @@ __device__ __forceinline__ void micro_ldl(const double* Cs, uint32_t ld, uint32_
     for (int k = 0; k < MB; k++) {
         piv[k] = ll[k][k];
         inv[k] = fast_rcp(piv[k]);
+        // a_ab -= (a_ak a_bk) / d_k: the products do not wait for the reciprocal, so the chain from one pivot to the
+        // next is reciprocal + one FMA
 #pragma unroll
-        for (int a = k + 1; a < MB; a++) {
-            const double la = ll[a][k] * inv[k];
+        for (int a = k + 1; a < MB; a++)
 #pragma unroll
-            for (int b = k + 1; b <= a; b++) ll[a][b] = fma(-la, ll[b][k], ll[a][b]);  // ll[b][k] still unscaled
-        }
+            for (int b = k + 1; b <= a; b++) ll[a][b] = fma(-(ll[a][k] * ll[b][k]), inv[k], ll[a][b]);
 #pragma unroll
         for (int a = k + 1; a < MB; a++) ll[a][k] *= inv[k];
     }
@@ -380,73 +379,163 @@ constexpr int kTsLd = TB + 1;
 #else
 #define FK_DSTAMP(k) do { } while (0)
 #endif
+// Named CTA barriers of the diagonal-tile factorisation (barrier 0 is __syncthreads).
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+constexpr int kYfLd = TB + 2;          // row stride of the unscaled-multiplier tile: even, so an 8-column strip of a row is 16-byte aligned
+constexpr uint32_t kDiagBar = 224;     // threads on the named barriers: the pivot warp + six helper warps
+constexpr size_t kDiagSmem = (TB * kTsLd + TB * kYfLd) * sizeof(double);
+
+// The pivot chain of the tile is a sequence of dependent steps (per column: reciprocal, scale, one FMA into the next
+// pivot), so the tile is NOT spread over the CTA: ONE warp walks the chain, lane l owning rows l and l + 32, with no CTA
+// barrier on its path.  Per micro-panel of 8 columns it (1) brings the panel's columns of its rows up to date with the
+// previous micro-panel ("look-ahead": 16 independent FMA chains per lane), (2) factorises the 8x8 block redundantly in
+// registers, (3) solves its two rows against it and leaves the scaled multipliers in Cs, the unscaled ones (the pivot
+// itself on the diagonal) in Ys.  Six helper warps apply every finished micro-panel to the columns BEYOND the next micro-panel
+// in the background (thread = row x column quarter); the pivot warp only meets them two micro-panels later.  The
+// eighth warp copies every finished micro-panel to global memory (panel storage and, when PUB, the polled copy).
+// Every entry receives its updates in ascending micro-panel order whoever applies them, so the result does not depend
+// on timing.  Hand-over by named barriers (producer bar.arrive, consumer bar.sync; the ids alternate with the parity
+// of the micro-panel): 1, 2 "micro-panel p is in shared memory" (all 256 threads), 3, 4 "the helpers have applied
+// micro-panel p" (helpers -> pivot warp, 224 threads).  The upper triangle of Cs / Ys is never read.
 template <bool PUB>
 __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_t nc, double* T, double* Tp, uint32_t f, int* status) {
-    const uint32_t tid = threadIdx.x, i = tid & 63, q = tid >> 6;
-    for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
-        const uint32_t kw = min((uint32_t)MB, nc - k0);
-        __syncthreads();
-        FK_DSTAMP(0);
-        double ll[MB][MB], inv[MB], piv[MB], y[MB];
-        micro_ldl(Cs, kTsLd, k0, kw, ll, inv, piv);
-        FK_DSTAMP(1);
-        if (tid == 0) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t np = (nc + MB - 1) / MB;
+    __syncthreads();  // the tile is complete in Cs
+    if (tid < 32) {
+        const uint32_t lane = tid;
+        double lprev[2][MB];  // scaled multipliers of the own rows in the previous micro-panel
 #pragma unroll
-            for (int k = 0; k < MB; k++)
-                if ((uint32_t)k < kw) flag_pivot(status, piv[k]);
-        }
-        // own row against the block: y_c = p_c - sum_{c' < c} y_c' L88[c][c']  (unscaled multipliers; for a
-        // row inside the micro-panel y_c is its pivot at c == i - k0 and unused beyond)
-        const bool active = i >= k0 && i < nc;
-        // (column-oriented: once y[cp] is final, all later entries take its term -- the same sum order per entry as the
-        // row-oriented loop, but the FMAs of one step are independent; a dependent DFMA costs ~45 cycles here)
+        for (int h = 0; h < 2; h++)
 #pragma unroll
-        for (int c = 0; c < MB; c++) y[c] = (active && (uint32_t)c < kw && k0 + c <= i) ? Cs[i * kTsLd + k0 + c] : 0.0;
+            for (int c = 0; c < MB; c++) lprev[h][c] = 0.0;
+        for (uint32_t p = 0; p < np; p++) {
+            const uint32_t k0 = p * MB, kw = min((uint32_t)MB, nc - k0);
+            FK_DSTAMP(0);
+            if (p >= 2) bar_sync(3 + (p & 1), kDiagBar);  // the helpers have applied micro-panel p - 2 (it reaches these columns)
+            // (no predicates below: the upper triangle of Cs / Ys, rows that are already finished and columns beyond nc hold
+            // values nobody reads, so the warp loads, updates and stores all 2 x 8 entries of its rows)
+            double v[2][MB];
 #pragma unroll
-        for (int cp = 0; cp + 1 < MB; cp++)
+            for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int c = cp + 1; c < MB; c++) y[c] = fma(-y[cp], ll[c][cp], y[c]);
-        FK_DSTAMP(5);
-        if (active) {  // the four threads of a row hold the same y: each stores two of the eight columns
+                for (int c = 0; c < MB; c++) v[h][c] = Cs[(lane + 32u * h) * kTsLd + k0 + c];
+            if (p >= 1) {
 #pragma unroll
-            for (int c = 0; c < MB; c++) {
-                if ((uint32_t)(c & 3) == q && (uint32_t)c < kw && k0 + c <= i) {
-                    Ys[i * (MB + 1) + c] = y[c];
-                    const double out = (k0 + c == i) ? y[c] : y[c] * inv[c];
-                    T[(size_t)(k0 + c) * f + i] = out;
-                    if (PUB) st_relaxed(Tp + (size_t)(k0 + c) * f + i, out);
+                for (int c = 0; c < MB; c++) {
+                    // unscaled multipliers of row k0 + c in the previous micro-panel (broadcast, 16-byte aligned)
+                    const double2* yj = reinterpret_cast<const double2*>(Ys + (k0 + c) * kYfLd + (k0 - MB));
+                    double yv[MB];
+#pragma unroll
+                    for (int cp = 0; cp < MB; cp += 2) {
+                        const double2 t2 = yj[cp >> 1];
+                        yv[cp] = t2.x;
+                        yv[cp + 1] = t2.y;
+                    }
+#pragma unroll
+                    for (int cp = 0; cp < MB; cp++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) v[h][c] = fma(-lprev[h][cp], yv[cp], v[h][c]);
+                }
+                // back to shared memory for the redundant factorisation of the 8x8 block (rows k0..k0+7 matter)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int c = 0; c < MB; c++) Cs[(lane + 32u * h) * kTsLd + k0 + c] = v[h][c];
+                __syncwarp();
+            }
+            FK_DSTAMP(1);
+            double ll[MB][MB], inv[MB], piv[MB];
+            micro_ldl(Cs, kTsLd, k0, kw, ll, inv, piv);
+            FK_DSTAMP(2);
+            {   // columns beyond kw are the identity, so every piv[k] can be looked at
+                bool isnan_ = false, bad = false;
+#pragma unroll
+                for (int k = 0; k < MB; k++) {
+                    isnan_ = isnan_ || piv[k] != piv[k];
+                    bad = bad || !(piv[k] > 0.0) || piv[k] == INFINITY;
+                }
+                if (lane == 0 && (isnan_ || bad)) atomicMax(status, isnan_ ? 2 : 1);
+            }
+            // own rows against the block: y_c = v_c - sum_{c' < c} y_c' L88[c][c'] (column-oriented: the FMAs of one step are
+            // independent); for a row inside the block y_c is its pivot at c == r - k0 and unused beyond
+#pragma unroll
+            for (int cp = 0; cp + 1 < MB; cp++)
+#pragma unroll
+                for (int c = cp + 1; c < MB; c++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) v[h][c] = fma(-v[h][cp], ll[c][cp], v[h][c]);
+            __syncwarp();  // every lane has read the 8x8 block
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t r = lane + 32u * h;
+#pragma unroll
+                for (int c = 0; c < MB; c++) {
+                    lprev[h][c] = v[h][c] * inv[c];
+                    Ys[r * kYfLd + k0 + c] = v[h][c];       // unscaled; the pivot itself on the diagonal
+                    Cs[r * kTsLd + k0 + c] = lprev[h][c];   // scaled multipliers
                 }
             }
+            bar_arrive(1 + (p & 1), kDiagThreads);
+            FK_DSTAMP(3);
         }
-        FK_DSTAMP(2);
-        __syncthreads();
-        FK_DSTAMP(3);
-        // rank-8 update of the rows below the micro-panel: C[i][j] -= sum_c l_ic * y_jc
-        if (i >= k0 + MB && i < nc) {
-            double l[MB];
+    } else if (tid < kDiagBar) {
+        const uint32_t hid = tid - 32, i = 2 * MB + hid % (TB - 2 * MB), q = hid / (TB - 2 * MB);  // row 16..63, column quarter
+        double* row = Cs + i * kTsLd;
+        for (uint32_t p = 0; p < np; p++) {
+            const uint32_t k0 = p * MB;
+            bar_sync(1 + (p & 1), kDiagThreads);
+            if (p + 2 >= np) continue;
+            if (i >= k0 + 2 * MB && i < nc) {
+                double l[MB];
 #pragma unroll
-            for (int c = 0; c < MB; c++) l[c] = y[c] * inv[c];
-            double* row = Cs + i * kTsLd;
+                for (int c = 0; c < MB; c++) l[c] = row[k0 + c];
 #pragma unroll 4
-            for (uint32_t j = k0 + MB + q; j <= i; j += 4) {
-                const double* yj = Ys + j * (MB + 1);
-                double v0 = row[j], v1 = 0.0;  // two partial sums: half the dependent-FMA chain
+                for (uint32_t j = k0 + 2 * MB + q; j <= i; j += 4) {
+                    const double* yj = Ys + j * kYfLd + k0;
+                    double v0 = row[j], v1 = 0.0;  // two partial sums: half the dependent-FMA chain
 #pragma unroll
-                for (int c = 0; c < MB; c += 2) {
-                    v0 = fma(-l[c], yj[c], v0);
-                    v1 = fma(-l[c + 1], yj[c + 1], v1);
+                    for (int c = 0; c < MB; c += 2) {
+                        v0 = fma(-l[c], yj[c], v0);
+                        v1 = fma(-l[c + 1], yj[c + 1], v1);
+                    }
+                    row[j] = v0 + v1;
                 }
-                row[j] = v0 + v1;
+            }
+            bar_arrive(3 + (p & 1), kDiagBar);
+        }
+    } else {
+        // copy-out warp: the finished micro-panel (rows k0.., 8 columns) from Cs to the panel storage
+        const uint32_t lane = tid - kDiagBar;
+        for (uint32_t p = 0; p < np; p++) {
+            const uint32_t k0 = p * MB, kw = min((uint32_t)MB, nc - k0);
+            bar_sync(1 + (p & 1), kDiagThreads);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t r = lane + 32u * h;
+                if (r >= k0 && r < nc) {
+                    const uint32_t cm = min(r - k0, kw - 1);
+                    double* tp = T + (size_t)k0 * f + r;
+#pragma unroll
+                    for (int c = 0; c < MB; c++) {
+                        if ((uint32_t)c <= cm) {
+                            const double out = (uint32_t)c == r - k0 ? Ys[r * kYfLd + k0 + c] : Cs[r * kTsLd + k0 + c];  // D on the diagonal
+                            tp[(size_t)c * f] = out;
+                            if (PUB) st_relaxed(Tp + (size_t)(k0 + c) * f + r, out);
+                        }
+                    }
+                }
             }
         }
-        FK_DSTAMP(4);
     }
 }
 
 __global__ void __launch_bounds__(kDiagThreads)
 mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
-    __shared__ double Cs[TB * kTsLd];
-    __shared__ double Ys[TB * (MB + 1)];  // unscaled multipliers of the current micro-panel
+    extern __shared__ __align__(16) double smd_diag[];
+    double* Cs = smd_diag;               // [TB][kTsLd] the tile (lower part)
+    double* Ys = Cs + TB * kTsLd;        // [TB][kYfLd] unscaled multipliers
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, col0 = t.z, nc = t.w >> 16;
     const uint32_t f = __ldg(D.f + s);
@@ -593,7 +682,7 @@ mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
 #define FK_FSTAMP(k) do { } while (0)
 #endif
 constexpr size_t kFlowSmem = (TB * kYsLd + TB * kTsLd + TB) * sizeof(double);
-static_assert(kFlowSmem >= sizeof(TileBuf), "the staging buffers alias the solve tiles");
+static_assert(kFlowSmem >= sizeof(TileBuf) && kFlowSmem >= kDiagSmem, "the staging buffers and the diagonal-tile arrays alias the solve tiles");
 
 __global__ void __launch_bounds__(kTileThreads)
 mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pub, const uint32_t* __restrict__ asm_ptr,
@@ -1786,6 +1875,7 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
     }
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
     MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
+    MF_CU(cudaFuncSetAttribute(mf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
     const size_t big_solve_smem = (32 * 33 + 2 * (size_t)max_front) * sizeof(double);
@@ -1846,7 +1936,7 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
             timed(l.kind, [&] {
                 switch (l.kind) {
                     case 0: mf_asm_kernel<<<l.count, 256, 0, st>>>(dev_, tk); break;
-                    case 1: mf_diag_kernel<<<l.count, kDiagThreads, 0, st>>>(dev_, tk); break;
+                    case 1: mf_diag_kernel<<<l.count, kDiagThreads, kDiagSmem, st>>>(dev_, tk); break;
                     case 2: mf_col_kernel<<<l.count, kColThreads, kColSmem, st>>>(dev_, tk); break;
                     default: mf_rupd_kernel<<<l.count, kTileThreads, 0, st>>>(dev_, tk); break;
                 }

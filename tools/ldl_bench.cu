@@ -69,8 +69,9 @@ __global__ void store_bench(double* T, double* Tp, long long* cyc, uint32_t f, i
 }
 template <bool PUB>
 __global__ void __launch_bounds__(256) tile_bench(double* T, double* Tp, int* status, long long* cyc, uint32_t f) {
-    __shared__ double Cs[TB * kTsLd];
-    __shared__ double Ys[TB * (MB + 1)];
+    extern __shared__ __align__(16) double smt[];
+    double* Cs = smt;
+    double* Ys = smt + TB * kTsLd;
     for (uint32_t e = threadIdx.x; e < TB * kTsLd; e += blockDim.x) {
         const uint32_t i = e / kTsLd, j = e % kTsLd;
         Cs[e] = i == j ? 500.0 + i : 1.0 / (1 + (i > j ? i - j : j - i));
@@ -90,19 +91,25 @@ int main() {
     {
         const uint32_t f = 832;
         double *T, *Tp; int* st; cudaMalloc(&T, (size_t)f * 64 * 8); cudaMalloc(&Tp, (size_t)f * 64 * 8); cudaMalloc(&st, 4096); cudaMemset(st, 0, 4096);
+        cudaFuncSetAttribute(tile_bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
+        cudaFuncSetAttribute(tile_bench<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem);
         for (int pub = 0; pub < 2; pub++) {
             for (int rep = 0; rep < 3; rep++) {
-                if (pub) tile_bench<true><<<1, 256>>>(T, Tp, st, c, f);
-                else tile_bench<false><<<1, 256>>>(T, Tp, st, c, f);
+                if (pub) tile_bench<true><<<1, 256, kDiagSmem>>>(T, Tp, st, c, f);
+                else tile_bench<false><<<1, 256, kDiagSmem>>>(T, Tp, st, c, f);
             }
             cudaDeviceSynchronize();
             long long h[2]; cudaMemcpy(h, c, 16, cudaMemcpyDeviceToHost);
             printf("diag_tile_factor<%s> 64x64: %lld cycles, %lld ns by %%globaltimer -> SM clock %.0f MHz (%s)\n", pub ? "publishing" : "panel only", h[0], h[1], 1e3 * h[0] / h[1], cudaGetErrorString(cudaGetLastError()));
         }
-        for (int rep = 0; rep < 4000; rep++) tile_bench<true><<<1, 256>>>(T, Tp, st, c, f);  // ~60 ms of back-to-back launches
+#ifdef FK_CHAIN_PROFILE
+        { long long hs[64]; cudaMemcpy(hs, st, sizeof(hs), cudaMemcpyDeviceToHost);
+          for (int p = 0; p < 3; p++) { printf("micro-panel %d:", p); for (int k = 1; k <= 4; k++) printf("  stamp %d +%lld", k, hs[8 + p * 8 + k] - hs[8 + p * 8 + k - 1]); if (p) printf("  (since previous panel's stamp 0: %lld)", hs[8 + p * 8] - hs[8 + (p - 1) * 8]); printf("\n"); } }
+#endif
+        for (int rep = 0; rep < 400; rep++) tile_bench<true><<<1, 256, kDiagSmem>>>(T, Tp, st, c, f);  // ~60 ms of back-to-back launches
         cudaDeviceSynchronize();
         { long long h[2]; cudaMemcpy(h, c, 16, cudaMemcpyDeviceToHost);
-          printf("after 4000 back-to-back launches: %lld cycles, %lld ns -> SM clock %.0f MHz\n", h[0], h[1], 1e3 * h[0] / h[1]); }
+          printf("after 400 back-to-back launches: %lld cycles, %lld ns -> SM clock %.0f MHz\n", h[0], h[1], 1e3 * h[0] / h[1]); }
     }
     {
         const uint32_t f = 832;
