@@ -386,63 +386,48 @@ constexpr int kYfLd = TB + 2;          // row stride of the unscaled-multiplier 
 constexpr uint32_t kDiagBar = 224;     // threads on the named barriers: the pivot warp + six helper warps
 constexpr size_t kDiagSmem = (TB * kTsLd + TB * kYfLd) * sizeof(double);
 
-// The pivot chain of the tile is a sequence of dependent steps (per column: reciprocal, scale, one FMA into the next
-// pivot), so the tile is NOT spread over the CTA: ONE warp walks the chain, lane l owning rows l and l + 32, with no CTA
-// barrier on its path.  Per micro-panel of 8 columns it (1) brings the panel's columns of its rows up to date with the
-// previous micro-panel ("look-ahead": 16 independent FMA chains per lane), (2) factorises the 8x8 block redundantly in
-// registers, (3) solves its two rows against it and leaves the scaled multipliers in Cs, the unscaled ones (the pivot
-// itself on the diagonal) in Ys.  Six helper warps apply every finished micro-panel to the columns BEYOND the next micro-panel
-// in the background (thread = row x column quarter); the pivot warp only meets them two micro-panels later.  The
-// eighth warp copies every finished micro-panel to global memory (panel storage and, when PUB, the polled copy).
-// Every entry receives its updates in ascending micro-panel order whoever applies them, so the result does not depend
-// on timing.  Hand-over by named barriers (producer bar.arrive, consumer bar.sync; the ids alternate with the parity
-// of the micro-panel): 1, 2 "micro-panel p is in shared memory" (all 256 threads), 3, 4 "the helpers have applied
+// The pivot chain of the tile is a sequence of dependent steps (per column: reciprocal, one FMA into the next pivot), so
+// the tile is NOT spread over the CTA: ONE warp (warp 0) walks the chain, lane l owning rows l and l + 32, with no CTA
+// barrier on its path.  Per micro-panel p of 8 columns it (1) applies micro-panel p - 1 to the 8x8 diagonal block only
+// (36 entries, one or two per lane), (2) factorises the block redundantly in registers, (3) meets the helpers, solves
+// its two rows against the block and leaves the scaled multipliers in Cs, the unscaled ones (the pivot itself on the
+// diagonal) in Ys.  Six helper warps apply every finished micro-panel to everything below the next diagonal block
+// (thread = row x column quarter, columns in ascending order, so the next micro-panel's columns come first) while the
+// pivot warp is busy with (1) and (2) of the next micro-panel.  Warp 4 -- it shares the scheduler with the pivot warp --
+// only copies finished micro-panels to global memory (panel storage and, when PUB, the polled copy).  Every entry
+// receives its updates in ascending micro-panel order whoever applies them, so the result does not depend on timing.
+// Hand-over by named barriers (producer bar.arrive, consumer bar.sync; the ids alternate with the parity of the
+// micro-panel): 1, 2 "micro-panel p is in shared memory" (all 256 threads), 3, 4 "the helpers have applied
 // micro-panel p" (helpers -> pivot warp, 224 threads).  The upper triangle of Cs / Ys is never read.
 template <bool PUB>
 __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_t nc, double* T, double* Tp, uint32_t f, int* status) {
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t np = (nc + MB - 1) / MB;
     __syncthreads();  // the tile is complete in Cs
-    if (tid < 32) {
-        const uint32_t lane = tid;
-        double lprev[2][MB];  // scaled multipliers of the own rows in the previous micro-panel
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-#pragma unroll
-            for (int c = 0; c < MB; c++) lprev[h][c] = 0.0;
+    if (warp == 0) {
         for (uint32_t p = 0; p < np; p++) {
             const uint32_t k0 = p * MB, kw = min((uint32_t)MB, nc - k0);
             FK_DSTAMP(0);
-            if (p >= 2) bar_sync(3 + (p & 1), kDiagBar);  // the helpers have applied micro-panel p - 2 (it reaches these columns)
-            // (no predicates below: the upper triangle of Cs / Ys, rows that are already finished and columns beyond nc hold
-            // values nobody reads, so the warp loads, updates and stores all 2 x 8 entries of its rows)
-            double v[2][MB];
-#pragma unroll
-            for (int h = 0; h < 2; h++)
-#pragma unroll
-                for (int c = 0; c < MB; c++) v[h][c] = Cs[(lane + 32u * h) * kTsLd + k0 + c];
             if (p >= 1) {
+                // micro-panel p - 1 -> the diagonal block: lane (a, q) takes the entries (a, q) and (a, q + 4) of the block
+                // (computed for the whole 8x8 square: the upper triangle is never read)
+                const uint32_t a = lane >> 2, q = lane & 3;
+                const double* lr = Cs + (k0 + a) * kTsLd + (k0 - MB);
+                const double2* y0 = reinterpret_cast<const double2*>(Ys + (k0 + q) * kYfLd + (k0 - MB));
+                const double2* y1 = reinterpret_cast<const double2*>(Ys + (k0 + q + 4) * kYfLd + (k0 - MB));
+                double* c0 = Cs + (k0 + a) * kTsLd + k0 + q;
+                double s00 = c0[0], s01 = 0.0, s10 = c0[4], s11 = 0.0;  // two partial sums per entry
 #pragma unroll
-                for (int c = 0; c < MB; c++) {
-                    // unscaled multipliers of row k0 + c in the previous micro-panel (broadcast, 16-byte aligned)
-                    const double2* yj = reinterpret_cast<const double2*>(Ys + (k0 + c) * kYfLd + (k0 - MB));
-                    double yv[MB];
-#pragma unroll
-                    for (int cp = 0; cp < MB; cp += 2) {
-                        const double2 t2 = yj[cp >> 1];
-                        yv[cp] = t2.x;
-                        yv[cp + 1] = t2.y;
-                    }
-#pragma unroll
-                    for (int cp = 0; cp < MB; cp++)
-#pragma unroll
-                        for (int h = 0; h < 2; h++) v[h][c] = fma(-lprev[h][cp], yv[cp], v[h][c]);
+                for (int cp = 0; cp < MB; cp += 2) {
+                    const double la = lr[cp], lb = lr[cp + 1];
+                    const double2 ya = y0[cp >> 1], yb = y1[cp >> 1];
+                    s00 = fma(-la, ya.x, s00);
+                    s01 = fma(-lb, ya.y, s01);
+                    s10 = fma(-la, yb.x, s10);
+                    s11 = fma(-lb, yb.y, s11);
                 }
-                // back to shared memory for the redundant factorisation of the 8x8 block (rows k0..k0+7 matter)
-#pragma unroll
-                for (int h = 0; h < 2; h++)
-#pragma unroll
-                    for (int c = 0; c < MB; c++) Cs[(lane + 32u * h) * kTsLd + k0 + c] = v[h][c];
+                c0[0] = s00 + s01;
+                c0[4] = s10 + s11;
                 __syncwarp();
             }
             FK_DSTAMP(1);
@@ -458,6 +443,14 @@ __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_
                 }
                 if (lane == 0 && (isnan_ || bad)) atomicMax(status, isnan_ ? 2 : 1);
             }
+            if (p >= 1) bar_sync(3 + ((p - 1) & 1), kDiagBar);  // the helpers have applied micro-panel p - 1
+            // (no predicates below: the upper triangle of Cs / Ys, rows that are already finished and columns beyond nc hold
+            // values nobody reads, so the warp loads, solves and stores all 2 x 8 entries of its rows)
+            double v[2][MB];
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int c = 0; c < MB; c++) v[h][c] = Cs[(lane + 32u * h) * kTsLd + k0 + c];
             // own rows against the block: y_c = v_c - sum_{c' < c} y_c' L88[c][c'] (column-oriented: the FMAs of one step are
             // independent); for a row inside the block y_c is its pivot at c == r - k0 and unused beyond
 #pragma unroll
@@ -466,48 +459,62 @@ __device__ __forceinline__ void diag_tile_factor(double* Cs, double* Ys, uint32_
                 for (int c = cp + 1; c < MB; c++)
 #pragma unroll
                     for (int h = 0; h < 2; h++) v[h][c] = fma(-v[h][cp], ll[c][cp], v[h][c]);
-            __syncwarp();  // every lane has read the 8x8 block
+            __syncwarp();  // every lane has read its rows (the block's rows among them)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t r = lane + 32u * h;
 #pragma unroll
                 for (int c = 0; c < MB; c++) {
-                    lprev[h][c] = v[h][c] * inv[c];
-                    Ys[r * kYfLd + k0 + c] = v[h][c];       // unscaled; the pivot itself on the diagonal
-                    Cs[r * kTsLd + k0 + c] = lprev[h][c];   // scaled multipliers
+                    Ys[r * kYfLd + k0 + c] = v[h][c];            // unscaled; the pivot itself on the diagonal
+                    Cs[r * kTsLd + k0 + c] = v[h][c] * inv[c];   // scaled multipliers
                 }
             }
+            __syncwarp();  // (the next diagonal-block update reads what the other lanes have just stored)
             bar_arrive(1 + (p & 1), kDiagThreads);
             FK_DSTAMP(3);
         }
-    } else if (tid < kDiagBar) {
-        const uint32_t hid = tid - 32, i = 2 * MB + hid % (TB - 2 * MB), q = hid / (TB - 2 * MB);  // row 16..63, column quarter
+    } else if (warp != 4) {
+        const uint32_t hid = (warp < 4 ? warp - 1 : warp - 2) * 32 + lane;                     // 0..191
+        const uint32_t i = 2 * MB + hid % (TB - 2 * MB), q = hid / (TB - 2 * MB);               // row 16..63, column quarter
         double* row = Cs + i * kTsLd;
         for (uint32_t p = 0; p < np; p++) {
             const uint32_t k0 = p * MB;
             bar_sync(1 + (p & 1), kDiagThreads);
-            if (p + 2 >= np) continue;
+            if (p + 1 >= np) continue;
             if (i >= k0 + 2 * MB && i < nc) {
                 double l[MB];
 #pragma unroll
                 for (int c = 0; c < MB; c++) l[c] = row[k0 + c];
-#pragma unroll 4
-                for (uint32_t j = k0 + 2 * MB + q; j <= i; j += 4) {
-                    const double* yj = Ys + j * kYfLd + k0;
-                    double v0 = row[j], v1 = 0.0;  // two partial sums: half the dependent-FMA chain
+                // four columns per step, all loads before the first store (the compiler cannot tell that the store to row[j]
+                // leaves the next column's operands alone and would otherwise run the columns one after the other)
+                for (uint32_t j0 = k0 + MB + q; j0 <= i; j0 += 16) {
+                    double v0[4], v1[4];
+                    double2 y2[4][MB / 2];
 #pragma unroll
-                    for (int c = 0; c < MB; c += 2) {
-                        v0 = fma(-l[c], yj[c], v0);
-                        v1 = fma(-l[c + 1], yj[c + 1], v1);
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t j = min(j0 + 4u * u, (uint32_t)TB - 1);  // (clamped: columns beyond i are computed, not stored)
+                        const double2* yj = reinterpret_cast<const double2*>(Ys + j * kYfLd + k0);
+                        v0[u] = row[j];
+                        v1[u] = 0.0;  // two partial sums: half the dependent-FMA chain
+#pragma unroll
+                        for (int c = 0; c < MB / 2; c++) y2[u][c] = yj[c];
                     }
-                    row[j] = v0 + v1;
+#pragma unroll
+                    for (int c = 0; c < MB; c += 2)
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            v0[u] = fma(-l[c], y2[u][c >> 1].x, v0[u]);
+                            v1[u] = fma(-l[c + 1], y2[u][c >> 1].y, v1[u]);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j0 + 4u * u <= i) row[j0 + 4u * u] = v0[u] + v1[u];
                 }
             }
             bar_arrive(3 + (p & 1), kDiagBar);
         }
     } else {
-        // copy-out warp: the finished micro-panel (rows k0.., 8 columns) from Cs to the panel storage
-        const uint32_t lane = tid - kDiagBar;
+        // copy-out warp: the finished micro-panel (rows k0.., 8 columns) from shared memory to the panel storage
         for (uint32_t p = 0; p < np; p++) {
             const uint32_t k0 = p * MB, kw = min((uint32_t)MB, nc - k0);
             bar_sync(1 + (p & 1), kDiagThreads);
@@ -556,8 +563,7 @@ constexpr int kColThreads = 256;
 constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (row, quarter) hit distinct banks
 // Blocked forward substitution of the rows in Cs ([TB][kYsLd], zero padded) against the unit-lower tile in Ls
 // ([TB][kTsLd], strictly lower part, zero padded): on return Cs holds Y = C L_kk^-T (unscaled).
-__device__ __forceinline__ void col_tile_step(double* row, const double* Ls, uint32_t k0, uint32_t nc, uint32_t q) {
-    double y[MB];
+__device__ __forceinline__ void col_tile_step(double* row, const double* Ls, uint32_t k0, uint32_t nc, uint32_t q, double (&y)[MB]) {
 #pragma unroll
     for (int c = 0; c < MB; c++) y[c] = row[k0 + c];
 #pragma unroll
@@ -569,16 +575,28 @@ __device__ __forceinline__ void col_tile_step(double* row, const double* Ls, uin
 #pragma unroll
         for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
     }
-#pragma unroll 4
-    for (uint32_t cp = k0 + MB + q; cp < nc; cp += 4) {
-        const double* Lr = Ls + cp * kTsLd + k0;
-        double v0 = row[cp], v1 = 0.0;
+    // four columns per step, all loads before the first store (see the helper loop of diag_tile_factor)
+    for (uint32_t cp0 = k0 + MB + q; cp0 < nc; cp0 += 16) {
+        double v0[4], v1[4], lv[4][MB];
 #pragma unroll
-        for (int c = 0; c < MB; c += 2) {
-            v0 = fma(-y[c], Lr[c], v0);
-            v1 = fma(-y[c + 1], Lr[c + 1], v1);
+        for (int u = 0; u < 4; u++) {
+            const uint32_t cp = min(cp0 + 4u * u, (uint32_t)TB - 1);  // (clamped: columns beyond nc are computed, not stored)
+            const double* Lr = Ls + cp * kTsLd + k0;
+            v0[u] = row[cp];
+            v1[u] = 0.0;
+#pragma unroll
+            for (int c = 0; c < MB; c++) lv[u][c] = Lr[c];
         }
-        row[cp] = v0 + v1;
+#pragma unroll
+        for (int c = 0; c < MB; c += 2)
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                v0[u] = fma(-y[c], lv[u][c], v0[u]);
+                v1[u] = fma(-y[c + 1], lv[u][c + 1], v1[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (cp0 + 4u * u < nc) row[cp0 + 4u * u] = v0[u] + v1[u];
     }
     __syncwarp();
 }
@@ -587,7 +605,10 @@ __device__ __forceinline__ void col_tile_solve(double* Cs, const double* Ls, uin
     const uint32_t tid = threadIdx.x;
     const uint32_t i = tid >> 2, q = tid & 3;
     double* row = Cs + i * kYsLd;
-    for (uint32_t k0 = 0; k0 < nc; k0 += MB) col_tile_step(row, Ls, k0, nc, q);
+    for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
+        double y[MB];
+        col_tile_step(row, Ls, k0, nc, q, y);
+    }
 }
 
 __global__ void __launch_bounds__(kColThreads)
@@ -677,7 +698,7 @@ mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // column by column, so a CTA only ever waits for CTAs with a smaller block index: the schedule cannot
 // deadlock however many CTAs are resident.  One launch per level instead of 1 + 3 per pivot block.
 #ifdef FK_CHAIN_PROFILE
-#define FK_FSTAMP(k) do { if (threadIdx.x == 0) ((long long*)D.ubuf)[blockIdx.x * 4 + (k)] = global_ns(); } while (0)
+#define FK_FSTAMP(k) do { if (threadIdx.x == 0) ((long long*)D.ubuf)[bid * 4 + (k)] = global_ns(); } while (0)
 #else
 #define FK_FSTAMP(k) do { } while (0)
 #endif
@@ -787,43 +808,50 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
             if (ri < nrA && c4 + j < nc) Cs[ri * kYsLd + c4 + j] = acc[i][j];
         }
     for (uint32_t e = tid; e < TB * kTsLd; e += kTileThreads) Ls[e] = 0.0;
-    {   // follow the diagonal tile micro-panel by micro-panel: its 8-column strip (rows >= k0: strictly lower
-        // part + D) is polled as the owner of the diagonal tile publishes it, then this tile's rows take the step
+    {   // follow the diagonal tile micro-panel by micro-panel: its 8-column strip (rows >= k0: strictly lower part + D) is
+        // polled as the owner of the diagonal tile publishes it (the loads of strip k0 + 8 are issued before strip k0 is
+        // processed and verified afterwards, so the L2 round trip overlaps the substitution), this tile's rows take the
+        // step, and the strip's columns of THIS tile -- final from here on -- are stored and published at once: the tiles
+        // to the right consume them chunk by chunk while the rest of the substitution is still running
         const double* Lkk = Pp + (size_t)tcol0 * f + tcol0;
         const uint32_t ii = tid & 63, cA = tid >> 6;  // entries (ii, k0 + cA) and (ii, k0 + cA + 4)
-        double* row = Cs + (tid >> 2) * kYsLd;
-        for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
-            double v[2];
-            bool missing;
-            SpinGuard guard(D.status);
-            do {
-                missing = false;
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const uint32_t j = k0 + cA + 4u * u;
-                    v[u] = (ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
-                    missing = missing || is_unpublished(v[u]);
-                }
-            } while (missing && !guard.expired());
-            __syncthreads();  // (the zero fill / the previous step's readers are done)
+        const uint32_t r = tid >> 2, q = tid & 3;
+        double* row = Cs + r * kYsLd;
+        double* Tp = Pp + (size_t)tcol0 * f + row0;
+        double v[2];
+        auto issue = [&](uint32_t k0) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const uint32_t j = k0 + cA + 4u * u;
-                if (j < ii) Ls[ii * kTsLd + j] = v[u];
-                else if (j == ii && ii < nc) invd[ii] = fast_rcp(v[u]);
+                v[u] = (ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
+            }
+        };
+        issue(0);
+        __syncthreads();  // the zero fill of Ls is complete
+        for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
+            SpinGuard guard(D.status);
+            while ((is_unpublished(v[0]) || is_unpublished(v[1])) && !guard.expired()) issue(k0);
+            {   // every strip has its own columns of Ls and entries of invd: nothing a reader of an earlier strip still needs
+                const uint32_t j0 = k0 + cA, j1 = k0 + cA + 4;
+                if (j0 < ii) Ls[ii * kTsLd + j0] = v[0];
+                else if (j0 == ii && ii < nc) invd[ii] = fast_rcp(v[0]);
+                if (j1 < ii) Ls[ii * kTsLd + j1] = v[1];
+                else if (j1 == ii && ii < nc) invd[ii] = fast_rcp(v[1]);
             }
             __syncthreads();
-            col_tile_step(row, Ls, k0, nc, tid & 3);
-        }
-    }
-    __syncthreads();
-    double* Tp = Pp + (size_t)tcol0 * f + row0;
-    for (uint32_t e = tid; e < nc * TB; e += kTileThreads) {
-        const uint32_t ii = e & 63, j = e >> 6;
-        if (ii < nrA) {
-            const double v = Cs[ii * kYsLd + j] * invd[j];
-            T[(size_t)j * f + ii] = v;
-            st_relaxed(Tp + (size_t)j * f + ii, v);
+            if (k0 + MB < nc) issue(k0 + MB);  // (after the barrier: a barrier waits for the loads issued before it)
+            double y[MB];
+            col_tile_step(row, Ls, k0, nc, q, y);
+            if (r < nrA) {  // the four threads of a row hold the same y: each stores two of the eight columns
+#pragma unroll
+                for (int c = 0; c < MB; c++) {
+                    if ((uint32_t)(c & 3) == q && k0 + c < nc) {
+                        const double out = y[c] * invd[k0 + c];
+                        T[(size_t)(k0 + c) * f + r] = out;
+                        st_relaxed(Tp + (size_t)(k0 + c) * f + r, out);
+                    }
+                }
+            }
         }
     }
     FK_FSTAMP(3);
