@@ -1,4 +1,4 @@
-// Device-side residual + gradient evaluators for the 11 expression kinds of Fiksi
+// Device-side residual + gradient evaluators for the 11 expression kinds of Fiksi and the two pose rows of ClusteredSystem
 // (fiksi/src/constraints/expressions.rs:291-874; formulas tabulated in SURVEY.md App. B).
 //
 // Arithmetic contract: FP64, no fused multiply-add (Rust never contracts a*b+c; this translation
@@ -141,14 +141,35 @@ __device__ __forceinline__ double eval_expression(int kind, const double (&v)[8]
                 g[6] = -1.0;
             }
         } break;
+        case 11: case 12: {  // ClusteredSystem's coincidence rows, assemble/mod.rs:538-585 with Pose2D (expressions.rs:1122-1158)
+            // slots: rotation, tx, ty, updated coordinate, u, v (the point before the step; fixed, its gradient is unused)
+            double s, c;
+            sincos(v[0], &s, &c);
+            const double u = v[4], w = v[5];
+            const double uc = u * c, us = u * s, vc = w * c, vs = w * s;
+            if (kind == 11) {
+                r = (v[1] + uc - vs) - v[3];
+                g[0] = (-us - vc) * 1.0 + (uc - vs) * 0.0;
+                g[1] = 1.0;
+                g[2] = 0.0;
+            } else {
+                r = (v[2] + us + vc) - v[3];
+                g[0] = (-us - vc) * 0.0 + (uc - vs) * 1.0;
+                g[1] = 0.0;
+                g[2] = 1.0;
+            }
+            g[3] = -1.0;
+            g[4] = 0.0;
+            g[5] = 0.0;
+        } break;
         default: break;
     }
     return r;
 }
 
 __device__ __forceinline__ int arity_of(int kind) {
-    // 2 4 6 6 6 5 8 8 8 8 7 packed as nibbles
-    return (int)((0x78888566642ull >> (4 * kind)) & 0xF);
+    // 2 4 6 6 6 5 8 8 8 8 7 6 6 packed as nibbles
+    return (int)((0x6678888566642ull >> (4 * kind)) & 0xF);
 }
 
 }  // namespace dev

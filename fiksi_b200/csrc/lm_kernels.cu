@@ -426,7 +426,7 @@ struct alignas(16) EvalRow {
 template <int KIND, bool WITH_JACOBIAN, bool SPECIAL>
 __device__ __forceinline__ void eval_tiled_row(const EvalRow& T, uint32_t sk, uint32_t roff, const double* sv,
                                                const double* sp, double* sr, double* sj) {
-    constexpr int A = (int)((0x78888566642ull >> (4 * KIND)) & 0xF);
+    constexpr int A = (int)((0x6678888566642ull >> (4 * KIND)) & 0xF);
     double v[8], g[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) v[s] = s < A ? sv[T.voff[s] + sk] : 0.0;
@@ -552,7 +552,7 @@ fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double
         break;
             switch (T.kind) {
                 FK_ROW(0) FK_ROW(1) FK_ROW(2) FK_ROW(3) FK_ROW(4) FK_ROW(5)
-                FK_ROW(6) FK_ROW(7) FK_ROW(8) FK_ROW(9) FK_ROW(10)
+                FK_ROW(6) FK_ROW(7) FK_ROW(8) FK_ROW(9) FK_ROW(10) FK_ROW(11) FK_ROW(12)
                 default: break;
             }
 #undef FK_ROW

@@ -394,7 +394,7 @@ fk_batch_lm_sketch_kernel(const SkProgram P, const SkRaw R, uint32_t n_sketches,
     case 0x100 | K: sk_eval_row<K, true>(cur, h, xe, fx, pr, w, f, s); break;
                 switch (h.x & 0x1FFu) {  // (pairs of rows only for the kinds whose two-row body fits the register file)
                     FK_SK_ROW2(0) FK_SK_ROW2(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
-                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
+                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10) FK_SK_ROW(11) FK_SK_ROW(12)
                     default: break;
                 }
 #undef FK_SK_ROW
@@ -835,7 +835,7 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, const SkRaw R, uint32_t n_sket
     case 0x100 | K: sk_row_consume<K, true>(cur, st0, w, f); break;
                 switch (h & 0x1FFu) {
                     FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
-                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
+                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10) FK_SK_ROW(11) FK_SK_ROW(12)
                     default: break;
                 }
 #undef FK_SK_ROW
@@ -898,7 +898,7 @@ fk_batch_lm_sketch_pair_kernel(const SkProgram P, const SkRaw R, uint32_t n_sket
     case 0x100 | K: sk_row_produce<K, true>(cur, h, xe, fx, pr, st0, s); break;
                 switch (h.x & 0x1FFu) {
                     FK_SK_ROW(0) FK_SK_ROW(1) FK_SK_ROW(2) FK_SK_ROW(3) FK_SK_ROW(4) FK_SK_ROW(5)
-                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10)
+                    FK_SK_ROW(6) FK_SK_ROW(7) FK_SK_ROW(8) FK_SK_ROW(9) FK_SK_ROW(10) FK_SK_ROW(11) FK_SK_ROW(12)
                     default: break;
                 }
 #undef FK_SK_ROW

@@ -14,13 +14,15 @@ namespace fk {
 
 int expand_slots(uint8_t kind, const uint32_t idx[4], uint32_t out[8]) {
     // Layout per kind: which stored index each slot comes from and whether it is the +1 (y) half.
-    // 'p' = point (two slots), 'v' = single variable.  expressions.rs:48-182.
-    static const char* shape[FK_NUM_KINDS] = {"vv", "pp", "ppp", "ppp", "ppp", "ppv", "pppp", "pppp", "pppp", "pppp", "pppv"};
+    // 'p' = point (two slots), 'v' = single variable, 't' = pose (three slots).  expressions.rs:48-182; the pose rows
+    // of ClusteredSystem (assemble/mod.rs:538-585): pose, updated coordinate, point before the step.
+    static const char* shape[FK_NUM_KINDS] = {"vv", "pp", "ppp", "ppp", "ppp", "ppv", "pppp", "pppp", "pppp", "pppp", "pppv", "tvp", "tvp"};
     if (kind >= FK_NUM_KINDS) return -1;
     int n = 0;
     for (int k = 0; shape[kind][k]; k++) {
         out[n++] = idx[k];
-        if (shape[kind][k] == 'p') out[n++] = idx[k] + 1;
+        if (shape[kind][k] != 'v') out[n++] = idx[k] + 1;
+        if (shape[kind][k] == 't') out[n++] = idx[k] + 2;
     }
     return n;
 }
@@ -104,7 +106,7 @@ int Topology::build(const fk_problem& p, uint32_t lanes) {
     slot_pos.assign((size_t)m * 8, -1); slot_dup.assign((size_t)m * 8, 0);
     std::vector<uint32_t> col_count(n + 1, 0);
     eval_bytes = 0;
-    static const int stored_idx[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
+    static const int stored_idx[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 3, 3};
     for (uint32_t r = 0; r < m; r++) {
         uint32_t e = rows[r];
         uint8_t kd = kind[e];
@@ -576,7 +578,7 @@ void Topology::build_sketch_tables() {
     // fixed variables and parameters some row reads
     std::vector<int32_t> fix_slot(n_vars, -1), par_slot(n_expr, -1);
     std::vector<uint32_t> fix_list, par_list;
-    static const bool has_param[FK_NUM_KINDS] = {false, true, true, false, true, false, false, true, false, false, false};
+    static const bool has_param[FK_NUM_KINDS] = {false, true, true, false, true, false, false, true, false, false, false, false, false};
     for (uint32_t r = 0; r < m; r++) {
         const int a = kind_arity(row_kind[r]);
         for (int s = 0; s < a; s++)

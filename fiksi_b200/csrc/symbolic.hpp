@@ -22,7 +22,7 @@ namespace fk {
 
 // Number of variable slots per expression kind (fiksi/src/constraints/expressions.rs:48-182).
 inline int kind_arity(uint8_t kind) {
-    static const int a[FK_NUM_KINDS] = {2, 4, 6, 6, 6, 5, 8, 8, 8, 8, 7};
+    static const int a[FK_NUM_KINDS] = {2, 4, 6, 6, 6, 5, 8, 8, 8, 8, 7, 6, 6};
     return kind < FK_NUM_KINDS ? a[kind] : -1;
 }
 // Expands the stored base indices into variable slots.  Returns arity or -1.

@@ -9,10 +9,12 @@
 #include <map>
 #include <memory>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/fiksi_b200.h"
+#include "recursive_assembly.hpp"
 #include "single_pass.hpp"
 #include "symbolic.hpp"
 
@@ -28,6 +30,8 @@ struct Constr {
     uint8_t tag;         // ConstraintTag order (constraints/mod.rs:893-905)
     uint32_t first_expr; // index of its first expression
     uint8_t n_expr;      // valency: 2 for PointPointCoincidence, else 1 (constraints/mod.rs:992-1034)
+    uint8_t n_inc;       // incident primitive elements (graph.rs:112-117), in the order the reference lists them
+    uint32_t inc[4];
 };
 
 // Knuth/Lewis LCG of fiksi/src/rand.rs:24-39.
@@ -219,7 +223,9 @@ uint32_t fk_system_add_constraint(fk_system* s, int tag, const uint32_t* el, uin
         } break;
     }
     s->connect(id, inc, n_inc);
-    s->constrs.push_back({(uint8_t)tag, first, n_expr});
+    Constr rec{(uint8_t)tag, first, n_expr, (uint8_t)n_inc, {0, 0, 0, 0}};
+    for (int k = 0; k < n_inc; k++) rec.inc[k] = inc[k];
+    s->constrs.push_back(rec);
     s->eval_topo.reset();
     return id;
 }
@@ -313,7 +319,7 @@ int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32_t cap,
             L->free_local.push_back(local[g]);
             L->x.push_back(vt[g]);
         }
-        static const int stored[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
+        static const int stored[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 3, 3};
         for (uint32_t e : exprs) {
             L->rows.push_back((uint32_t)L->kind.size());
             L->kind.push_back(s->kind[e]);
@@ -397,7 +403,7 @@ void build_local(const fk_system* s, const std::vector<double>& vt, const std::v
         L.free_local.push_back(local[g]);
         L.x.push_back(vt[g]);
     }
-    static const int stored[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
+    static const int stored[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 3, 3};
     for (uint32_t e : exprs) {
         L.rows.push_back((uint32_t)L.kind.size());
         L.kind.push_back(s->kind[e]);
@@ -441,6 +447,207 @@ int fk_system_single_pass_plan(const fk_system* s, uint32_t* sizes3, uint32_t* f
     return FK_OK;
 }
 
+
+// ---- Decomposer::RecursiveAssembly -------------------------------------------------------
+namespace {
+
+// graph.rs:98-117 as the planner wants it: dof = variables an element adds (lib.rs:372-403), valency = expressions
+// of the constraint (constraints/mod.rs:331-334 and the like).
+fk::RaGraph constraint_graph(const fk_system* s) {
+    fk::RaGraph g;
+    for (const Elem& e : s->elems) g.add_vertex(e.tag == kLength ? 1 : (e.tag == kPoint ? 2 : 0));
+    for (const Constr& c : s->constrs) g.add_edge(c.n_expr, c.inc, c.n_inc);
+    return g;
+}
+
+std::vector<fk::RaStep> component_plan(const fk_system* s, const fk_system::Comp& c) {
+    fk::RecursiveAssemblyPlanner planner(constraint_graph(s));
+    return planner.plan(std::vector<uint32_t>(c.elements.begin(), c.elements.end()),
+                        std::vector<uint32_t>(c.constraints.begin(), c.constraints.end()));
+}
+
+const std::vector<uint32_t>* find_list(const fk::RaLists& m, uint32_t key) {
+    auto it = m.find(key);
+    return it == m.end() ? nullptr : &it->second;
+}
+
+// One step of the plan as a flattened problem (ClusteredSystem, assemble/mod.rs:282-590): free variables = the poses
+// of the clusters the step moves (three each, starting at 0) followed by the variables of the step's elements; rows =
+// two FK_POSE_POINT rows per (cluster, frontier point), then the step's expressions with their variables renumbered.
+// The points' positions before the step enter as fixed variables behind the free ones.
+struct ClusteredProblem {
+    std::vector<uint32_t> elements;                                        // step_plus_frontier_elements
+    std::vector<std::pair<uint32_t, std::vector<uint32_t>>> clusters;      // cluster key -> frontier points, in first-seen order
+    std::map<uint32_t, uint32_t> slot;                                     // system variable -> free variable of the step
+    std::vector<double> vars, param, x;
+    std::vector<uint8_t> kind;
+    std::vector<uint32_t> idx, free_vars, rows;
+    fk_problem prob{};
+    std::string error;
+
+    bool build(const fk_system* s, const fk::RaStep& step, const std::vector<double>& vt, const std::vector<double>& pt) {
+        auto has = [](const std::vector<uint32_t>& v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+        elements = step.elements;
+        // clusters reachable through shared frontier points (:355-398)
+        std::vector<uint32_t> reach;
+        auto add_clusters_of = [&](uint32_t el) -> size_t {
+            const std::vector<uint32_t>* l = find_list(step.on_frontiers, el);
+            if (!l) return 0;
+            for (uint32_t c : *l)
+                if (!has(reach, c)) reach.push_back(c);
+            return l->size();
+        };
+        for (uint32_t el : step.elements)
+            if (s->elems[el].tag == kPoint) add_clusters_of(el);
+        for (size_t i = 0; i < reach.size(); i++) {
+            const std::vector<uint32_t>* fr = find_list(step.frontier_elements, reach[i]);
+            if (!fr) { error = "recursive assembly: cluster without a frontier list"; return false; }
+            for (uint32_t el : *fr) {
+                if (s->elems[el].tag != kPoint) continue;
+                const size_t n_frontiers = add_clusters_of(el);
+                if (!has(elements, el) && n_frontiers > 1) elements.push_back(el);
+            }
+        }
+        // pose rows: one pair per (cluster, point on its frontier) (:401-429)
+        for (uint32_t el : elements) {
+            const std::vector<uint32_t>* l = find_list(step.on_frontiers, el);
+            if (!l || s->elems[el].tag != kPoint) continue;
+            for (uint32_t c : *l) {
+                auto it = std::find_if(clusters.begin(), clusters.end(), [&](const std::pair<uint32_t, std::vector<uint32_t>>& p) { return p.first == c; });
+                if (it == clusters.end()) {
+                    clusters.emplace_back(c, std::vector<uint32_t>());
+                    it = clusters.end() - 1;
+                }
+                it->second.push_back(el);
+            }
+        }
+        // free variables (:432-477)
+        vars.assign(clusters.size() * 3, 0.0);
+        for (uint32_t el : elements) {
+            const Elem& e = s->elems[el];
+            const int n = e.tag == kLength ? 1 : (e.tag == kPoint ? 2 : 0);
+            for (int k = 0; k < n; k++) {
+                slot[e.a + k] = (uint32_t)vars.size();
+                vars.push_back(vt[e.a + k]);
+            }
+        }
+        const uint32_t n_free = (uint32_t)vars.size();
+        x = vars;
+        for (uint32_t k = 0; k < n_free; k++) free_vars.push_back(k);
+        // rows
+        for (size_t ci = 0; ci < clusters.size(); ci++)
+            for (uint32_t point : clusters[ci].second) {
+                const uint32_t pv = s->elems[point].a;
+                const uint32_t at = (uint32_t)vars.size();
+                vars.push_back(vt[pv]);      // the point before the step: constant of the two rows
+                vars.push_back(vt[pv + 1]);
+                for (int y = 0; y < 2; y++) {
+                    rows.push_back((uint32_t)kind.size());
+                    kind.push_back(y ? FK_POSE_POINT_Y : FK_POSE_POINT_X);
+                    param.push_back(0.0);
+                    idx.push_back((uint32_t)(3 * ci)); idx.push_back(slot.at(pv) + (uint32_t)y); idx.push_back(at); idx.push_back(0);
+                }
+            }
+        static const int stored[FK_NUM_KINDS] = {2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 3, 3};
+        for (uint32_t c : step.constraints)
+            for (uint8_t k = 0; k < s->constrs[c].n_expr; k++) {
+                const uint32_t e = s->constrs[c].first_expr + k;
+                rows.push_back((uint32_t)kind.size());
+                kind.push_back(s->kind[e]);
+                param.push_back(pt[e]);
+                for (int q = 0; q < 4; q++) {
+                    uint32_t v = 0;
+                    if (q < stored[s->kind[e]]) {
+                        auto it = slot.find(s->idx[4 * (size_t)e + q]);
+                        if (it == slot.end()) { error = "recursive assembly: an expression reads a variable outside its step"; return false; }
+                        v = it->second;
+                    }
+                    idx.push_back(v);
+                }
+            }
+        prob.n_vars = (uint32_t)vars.size(); prob.vars = vars.data();
+        prob.n_expr = (uint32_t)kind.size(); prob.kind = kind.data(); prob.idx = idx.data(); prob.param = param.data();
+        prob.n_free = n_free; prob.free_vars = free_vars.data();
+        prob.n_rows = (uint32_t)rows.size(); prob.rows = rows.data();
+        return true;
+    }
+};
+
+// == System::solve(SolvingOptions { optimizer: LevenbergMarquardt, decomposer: RecursiveAssembly, perturb })
+// (assemble/mod.rs:212-277): every step of every component's plan is one LM solve on the GPU; afterwards the points a
+// moved cluster owns (and the step did not solve for) follow the cluster's pose on the host.  As in the reference,
+// `fix` has no effect on this decomposer (ClusteredSystem takes every variable of the step's elements).
+int solve_recursive_assembly(fk_system* s, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved) {
+    if (n_solved) *n_solved = 0;
+    const size_t nv = s->vars.size();
+    double sum = 0.0;
+    size_t cnt = 0;
+    for (double v : s->vars) { sum += v * v; cnt++; }
+    for (size_t e = 0; e < s->kind.size(); e++)
+        if (s->kind[e] == FK_POINT_POINT_DISTANCE || s->kind[e] == FK_POINT_LINE_DISTANCE) { sum += s->param[e] * s->param[e]; cnt++; }
+    const double scale = std::sqrt(sum / (double)cnt);
+    const double recip = 1.0 / scale;
+    std::vector<double> vt(nv);
+    for (size_t i = 0; i < nv; i++) vt[i] = s->vars[i] * recip;
+    std::vector<double> pt(s->param);
+    for (size_t e = 0; e < pt.size(); e++)
+        if (s->kind[e] == FK_POINT_POINT_DISTANCE || s->kind[e] == FK_POINT_LINE_DISTANCE) pt[e] = recip * s->param[e];
+    Lcg rng{42};
+    uint32_t solved = 0;
+    for (const fk_system::Comp& c : s->comps) {
+        if (c.elements.empty()) continue;
+        if (perturb) {
+            for (uint32_t fv : component_free_variables(s, c)) {
+                const double r1 = rng.next();
+                const double r2 = rng.next();
+                vt[fv] += vt[fv] * (1.0 / 8196.0) * r1 + (1.0 / 65568.0) * r2;
+            }
+        }
+        std::vector<fk::RaStep> steps;
+        try {
+            steps = component_plan(s, c);
+        } catch (const std::out_of_range&) {  // the reference panics here: unwrap on a missing cluster entry (recursive_assembly.rs:352-373)
+            s->error = "recursive assembly: the decomposition reaches a cluster without bookkeeping (the reference panics on this system)";
+            return FK_ERR_INVALID;
+        }
+        for (const fk::RaStep& step : steps) {
+            ClusteredProblem P;
+            if (!P.build(s, step, vt, pt)) {
+                s->error = P.error;
+                return FK_ERR_INVALID;
+            }
+            fk_report rep{};
+            const int rc = fk_lm_solve(&P.prob, P.x.data(), &rep);
+            if (rc != FK_OK) return rc;
+            for (const auto& kv : P.slot) {  // :226-233
+                vt[kv.first] = P.x[kv.second];
+                s->vars[kv.first] = scale * P.x[kv.second];
+            }
+            for (size_t ci = 0; ci < P.clusters.size(); ci++) {  // :235-273
+                const std::vector<uint32_t>* owned = find_list(step.owned_elements, P.clusters[ci].first);
+                if (!owned) continue;
+                const double rot = P.x[3 * ci], tx = P.x[3 * ci + 1], ty = P.x[3 * ci + 2];
+                const double sn = std::sin(rot), cs = std::cos(rot);  // Pose2D::transform_point, expressions.rs:1122-1136
+                for (uint32_t el : *owned) {
+                    if (std::find(P.elements.begin(), P.elements.end(), el) != P.elements.end() || s->elems[el].tag != kPoint) continue;
+                    const uint32_t pv = s->elems[el].a;
+                    const double u = vt[pv], w = vt[pv + 1];
+                    const double uc = u * cs, us = u * sn, vc = w * cs, vs = w * sn;
+                    const double nx = tx + uc - vs, ny = ty + us + vc;
+                    vt[pv] = nx; vt[pv + 1] = ny;
+                    s->vars[pv] = scale * nx; s->vars[pv + 1] = scale * ny;
+                }
+            }
+            if (reports && solved < cap) reports[solved] = rep;
+            solved++;
+        }
+    }
+    if (n_solved) *n_solved = solved;
+    return FK_OK;
+}
+
+}  // namespace
+
 // == System::solve(SolvingOptions { optimizer: LevenbergMarquardt, decomposer, perturb }).
 // decomposer 0: None (== fk_system_solve); 1: SinglePass (assemble/mod.rs:169-210): the strongly
 // connected expression sets of every component are solved one after the other on the GPU, each seeing
@@ -448,6 +655,7 @@ int fk_system_single_pass_plan(const fk_system* s, uint32_t* sizes3, uint32_t* f
 int fk_system_solve_opts(fk_system* s, int decomposer, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved) {
     if (!s) return FK_ERR_INVALID;
     if (decomposer == 0) return fk_system_solve(s, perturb, reports, cap, n_solved);
+    if (decomposer == 2) return solve_recursive_assembly(s, perturb, reports, cap, n_solved);
     if (decomposer != 1) return FK_ERR_INVALID;
     if (n_solved) *n_solved = 0;
     const size_t nv = s->vars.size();
@@ -493,6 +701,45 @@ int fk_system_solve_opts(fk_system* s, int decomposer, int perturb, fk_report* r
         }
     }
     if (n_solved) *n_solved = solved;
+    return FK_OK;
+}
+
+// The recombination plan of all components as one stream of 32-bit words (host only, no device): per step
+// n_constraints, constraints..., n_elements, elements..., n_free, free elements..., then on_frontiers, owned_elements,
+// frontier_elements, each as n_keys and per key (ascending)  key, n, values....  Returns FK_OK; *n_words receives the
+// stream's length (at most `cap` words are written), *n_steps the number of steps.
+int fk_system_recursive_assembly_plan(const fk_system* s, uint32_t* out, uint32_t cap, uint32_t* n_words, uint32_t* n_steps) {
+    if (!s) return FK_ERR_INVALID;
+    std::vector<uint32_t> w;
+    auto list = [&](const std::vector<uint32_t>& v) {
+        w.push_back((uint32_t)v.size());
+        w.insert(w.end(), v.begin(), v.end());
+    };
+    auto lists = [&](const fk::RaLists& m) {
+        w.push_back((uint32_t)m.size());
+        for (const auto& kv : m) {
+            w.push_back(kv.first);
+            list(kv.second);
+        }
+    };
+    uint32_t steps = 0;
+    for (const fk_system::Comp& c : s->comps) {
+        if (c.elements.empty()) continue;
+        std::vector<fk::RaStep> plan;
+        try {
+            plan = component_plan(s, c);
+        } catch (const std::out_of_range&) {  // (the reference panics on this system, see solve_recursive_assembly)
+            return FK_ERR_INVALID;
+        }
+        for (const fk::RaStep& st : plan) {
+            list(st.constraints); list(st.elements); list(st.free_elements);
+            lists(st.on_frontiers); lists(st.owned_elements); lists(st.frontier_elements);
+            steps++;
+        }
+    }
+    if (n_words) *n_words = (uint32_t)w.size();
+    if (n_steps) *n_steps = steps;
+    for (size_t k = 0; k < w.size() && k < cap && out; k++) out[k] = w[k];
     return FK_OK;
 }
 

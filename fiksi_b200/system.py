@@ -81,6 +81,22 @@ class System:
         check(lib().fk_system_solve_opts(self._h, 1, int(perturb), reps.ctypes.data_as(C.POINTER(FkReport)), cap, C.byref(n)))
         self._reports = reps[:n.value]
 
+    def solve_recursive_assembly(self, perturb=True):
+        """System::solve with Decomposer::RecursiveAssembly (assemble/mod.rs:212-277) on the GPU."""
+        cap = max(1, self.recursive_assembly_plan()[0])
+        reps = np.zeros(cap, dtype=REPORT_DTYPE)
+        n = C.c_uint32(0)
+        check(lib().fk_system_solve_opts(self._h, 2, int(perturb), reps.ctypes.data_as(C.POINTER(FkReport)), cap, C.byref(n)))
+        self._reports = reps[:n.value]
+
+    def recursive_assembly_plan(self):
+        """(number of steps, serialised plan words) of fk_system_recursive_assembly_plan (host only)."""
+        nw, ns = C.c_uint32(0), C.c_uint32(0)
+        check(lib().fk_system_recursive_assembly_plan(self._h, None, 0, C.byref(nw), C.byref(ns)))
+        out = np.zeros(max(nw.value, 1), dtype=np.uint32)
+        check(lib().fk_system_recursive_assembly_plan(self._h, ptr(out, C.c_uint32), nw.value, C.byref(nw), C.byref(ns)))
+        return int(ns.value), out[:nw.value].tolist()
+
     def single_pass_plan(self):
         """[(free variables, expressions), ...] of fk_system_single_pass_plan (host only)."""
         sizes = np.zeros(3, dtype=np.uint32)

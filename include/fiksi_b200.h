@@ -48,7 +48,14 @@ typedef enum fk_kind {
     FK_LINE_LINE_PARALLELISM = 8,           /* same idx                        slots 8 */
     FK_LINE_LINE_PERPENDICULARITY = 9,      /* same idx                        slots 8 */
     FK_LINE_CIRCLE_TANGENCY = 10,           /* idx: l1, l2, center, radius_var slots 7 */
-    FK_NUM_KINDS = 11
+    /* The two coincidence rows `ClusteredSystem` adds per (cluster, frontier point) for Decomposer::RecursiveAssembly
+     * (fiksi/src/assemble/mod.rs:538-585, Pose2D: constraints/expressions.rs:1094-1159); not members of the
+     * reference's `enum Expression`.  idx: pose (rotation, tx, ty: three consecutive variables), the updated
+     * coordinate (one variable), the point before the step (u, v: two consecutive variables, fixed).
+     * residual x: tx + u cos - v sin - updated;  y: ty + u sin + v cos - updated. */
+    FK_POSE_POINT_X = 11,                   /* idx: pose, updated_x, point             slots 6 */
+    FK_POSE_POINT_Y = 12,                   /* idx: pose, updated_y, point             slots 6 */
+    FK_NUM_KINDS = 13
 } fk_kind;
 
 /*
@@ -361,8 +368,17 @@ FK_API int fk_system_solve(fk_system* s, int perturb, fk_report* reports, uint32
 /* == System::solve(SolvingOptions { optimizer: LevenbergMarquardt, decomposer, perturb }), lib.rs:205-237.
  * decomposer 0: Decomposer::None (== fk_system_solve); 1: Decomposer::SinglePass (assemble/mod.rs:169-210;
  * maximum matching + strongly connected expression sets of analyze/graph/equations.rs on the host, every
- * set solved by the GPU LM in sequence).  reports: one per solved sub-problem, up to `cap`. */
+ * set solved by the GPU LM in sequence); 2: Decomposer::RecursiveAssembly (assemble/mod.rs:212-277: the
+ * recombination plan of analyze/graph/recursive_assembly.rs on the host -- hash-set iteration orders, which the
+ * reference leaves to its hasher's seed, taken in ascending id order --, every step a `ClusteredSystem`
+ * (assemble/mod.rs:282-590: cluster poses + the step's elements, FK_POSE_POINT_X/Y rows) solved by the GPU LM,
+ * owned points moved with their cluster's pose afterwards).  reports: one per solved sub-problem, up to `cap`. */
 FK_API int fk_system_solve_opts(fk_system* s, int decomposer, int perturb, fk_report* reports, uint32_t cap, uint32_t* n_solved);
+/* Host-only probe of the RecursiveAssembly plan (no device needed) as a stream of 32-bit words: per step
+ * n_constraints, constraints..., n_elements, elements..., n_free, free elements..., then the maps on_frontiers,
+ * owned_elements, frontier_elements (recursive_assembly.rs:75-114) as n_keys and per key (ascending) key, n,
+ * values....  *n_words = length of the stream (at most `cap` words are written), *n_steps = steps. */
+FK_API int fk_system_recursive_assembly_plan(const fk_system* s, uint32_t* out, uint32_t cap, uint32_t* n_words, uint32_t* n_steps);
 /* Host-only probe of the SinglePass plan (no device needed): call with NULL arrays for
  * sizes3 = {steps, total free variables, total expressions}; then free_ptr[steps+1], free_vars (ascending
  * per step), expr_ptr[steps+1], exprs (row order per step). */

@@ -80,7 +80,7 @@ def lib() -> C.CDLL:
                      "orc_line_circle_tangency", "orc_num_variables", "orc_num_expressions",
                      "orc_num_constraints", "orc_num_reports", "orc_num_components",
                      "orc_component_sizes", "orc_prepared_count", "orc_element_variable", "orc_system_analyze",
-                     "orc_single_pass_problem"):
+                     "orc_single_pass_problem", "orc_recursive_assembly_plan"):
             getattr(L, name).restype = C.c_uint32
         _lib = L
     return _lib
@@ -439,6 +439,22 @@ class System:
         ep = np.zeros(n + 1, np.uint32); ex = np.zeros(max(ne, 1), np.uint32)
         self._c("orc_single_pass_plan", _p(sizes, C.c_uint32), _p(fp, C.c_uint32), _p(fv, C.c_uint32), _p(ep, C.c_uint32), _p(ex, C.c_uint32))
         return [(fv[fp[k]:fp[k + 1]].tolist(), ex[ep[k]:ep[k + 1]].tolist()) for k in range(n)]
+
+    def solve_recursive_assembly(self, perturb=True):
+        """System::solve with Decomposer::RecursiveAssembly (assemble/mod.rs:212-277), LM optimizer; hash-set iteration
+        orders replaced by ascending ids (see fiksi_ref.hpp)."""
+        if self._c("orc_solve_recursive_assembly", int(perturb)):
+            raise RuntimeError("the reference panics on this system (unwrap on a missing cluster entry)")
+
+    def recursive_assembly_plan(self):
+        """(number of steps, serialised plan words) of the recombination plan (format: oracle_capi.cpp)."""
+        steps = C.c_uint32(0)
+        n = self._c("orc_recursive_assembly_plan", None, C.c_uint32(0), C.byref(steps))
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._c("orc_recursive_assembly_plan", _p(out, C.c_uint32), C.c_uint32(n), C.byref(steps))
+        if steps.value == 0xFFFFFFFF:
+            raise RuntimeError("the reference panics on this system (unwrap on a missing cluster entry)")
+        return int(steps.value), out[:n].tolist()
 
     def analyze(self):
         """System::analyze (lib.rs:454-458): ids of the constraints flagged as over-constraining."""

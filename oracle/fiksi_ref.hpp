@@ -19,6 +19,7 @@
 // overflows to +inf (every later step is NaN; lm.rs:115-191).  The oracle stops there and reports
 // exit_reason 4 ("reference would hang").
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -26,6 +27,7 @@
 #include <deque>
 #include <map>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -356,7 +358,8 @@ struct LmReport {
 inline uint64_t trace_push(uint64_t h, uint32_t code) { return h * 3u + code + 1u; }
 
 // fiksi/src/solve/lm.rs:21-197
-inline void levenberg_marquardt(const Subsystem& problem, double* variables, LmReport& rep,
+template <class Problem>  // solve/mod.rs:29-49 (trait Problem): Subsystem, ClusteredSystem
+inline void levenberg_marquardt(const Problem& problem, double* variables, LmReport& rep,
                                 bool keep_artifacts = false) {
     size_t nrows = problem.num_residuals(), ncols = problem.num_variables();
     std::vector<double> xs(variables, variables + ncols);
@@ -456,9 +459,14 @@ struct Graph {
     size_t n_elements = 0, n_constraints = 0;
     std::vector<uint32_t> element_cc;  // 0 == None, otherwise 1-based component index
     std::vector<ConnectedComponent> components;
+    // graph.rs:98-117: Element { dof, incident_constraints }, Constraint { valency, incident_elements }
+    std::vector<int16_t> dof, valency;
+    std::vector<std::vector<uint32_t>> incident_constraints, incident_elements;
 
-    uint32_t add_element() {
+    uint32_t add_element(int16_t element_dof = 0) {
         element_cc.push_back(0);
+        dof.push_back(element_dof);
+        incident_constraints.emplace_back();
         return (uint32_t)n_elements++;
     }
     // graph.rs:178-225
@@ -497,9 +505,12 @@ struct Graph {
         components[target - 1] = std::move(tc);
     }
     // graph.rs:235-254
-    uint32_t add_constraint(const uint32_t* elements, int n) {
+    uint32_t add_constraint(const uint32_t* elements, int n, int16_t constraint_valency = 1) {
         uint32_t id = (uint32_t)n_constraints++;
         merge_connected_components(id, elements, n);
+        for (int k = 0; k < n; k++) incident_constraints[elements[k]].push_back(id);  // :227-233
+        valency.push_back(constraint_valency);
+        incident_elements.emplace_back(elements, elements + n);
         return id;
     }
 };
@@ -515,6 +526,240 @@ struct EncodedConstraint {
 };
 // constraints/mod.rs:907-924,948-990: only PointPointCoincidence has valency 2.
 inline uint8_t valency_of(uint8_t constraint_tag) { return constraint_tag == 0 ? 2 : 1; }
+
+
+// ---- Decomposer::RecursiveAssembly: the recombination plan (analyze/graph/recursive_assembly.rs) ------
+// The reference keeps its vertex / edge / subgraph / frontier sets in `hashbrown` HashSets and iterates
+// them (recursive_assembly.rs:219,228,267,399,441,586,606); that order depends on the hasher's
+// per-process seed and is unspecified, so the plan of the reference is not a function of its input.  The
+// restatement iterates every such set in ASCENDING id order (std::set): one of the orders the reference
+// can take.  PARITY UNPINNED beyond that choice: the reference's only test of this decomposer is the
+// residual threshold of tests/triangles.rs:8-37 (tests/test_oracle_recursive.py checks it here).
+struct RecombinationStep {  // recursive_assembly.rs:75-114
+    std::vector<uint32_t> constraints, elements, free_elements;
+    std::map<uint32_t, std::vector<uint32_t>> on_frontiers;       // element -> cluster keys
+    std::map<uint32_t, std::vector<uint32_t>> owned_elements;     // cluster key -> elements
+    std::map<uint32_t, std::vector<uint32_t>> frontier_elements;  // cluster key -> elements
+};
+
+// recursive_assembly.rs:499-645 (dense_bfs::<D>): the first subgraph of the breadth-first enumeration with
+// `dof > -(D + 1)` that is not blocked.  (With non-negative element dofs the test holds for every subgraph the
+// search reaches, so this returns the first unblocked connected subgraph of at least two vertices: the
+// reference's behaviour, restated as it is.)
+template <int D>
+inline bool dense_bfs(const Graph& graph, const std::vector<std::set<uint32_t>>& blocked_subgraphs,
+                      const std::set<uint32_t>& available_edges, const std::set<uint32_t>& vertices, std::set<uint32_t>& out) {
+    const int k = -(D + 1);
+    auto all_in = [&](uint32_t edge, const std::set<uint32_t>& sub) {
+        for (uint32_t u : graph.incident_elements[edge])
+            if (!sub.count(u)) return false;
+        return true;
+    };
+    auto additional_valency = [&](const std::set<uint32_t>& next_subgraph, uint32_t new_vertex) {  // :510-532
+        int add = 0;
+        for (uint32_t edge : graph.incident_constraints[new_vertex])
+            if (available_edges.count(edge) && all_in(edge, next_subgraph)) add += graph.valency[edge];
+        return add;
+    };
+    auto extend_adjacent_vertices = [&](std::set<uint32_t>& adjacent, uint32_t from_vertex, const std::set<uint32_t>& sub) {  // :536-557
+        for (uint32_t edge : graph.incident_constraints[from_vertex]) {
+            if (!available_edges.count(edge)) continue;
+            for (uint32_t e : graph.incident_elements[edge])
+                if (vertices.count(e) && !sub.count(e)) adjacent.insert(e);
+        }
+    };
+    struct SubgraphState {  // :559-574
+        std::set<uint32_t> subgraph;
+        int dof;
+        std::set<uint32_t> adjacent_vertices;
+    };
+    std::deque<SubgraphState> queue;
+    for (uint32_t vertex : vertices) {  // :578-599
+        SubgraphState st;
+        st.subgraph.insert(vertex);
+        extend_adjacent_vertices(st.adjacent_vertices, vertex, st.subgraph);
+        st.dof = graph.dof[vertex];
+        queue.push_back(std::move(st));
+    }
+    while (!queue.empty()) {  // :601-641
+        SubgraphState cur = std::move(queue.front());
+        queue.pop_front();
+        for (uint32_t vertex : cur.adjacent_vertices) {
+            std::set<uint32_t> next_subgraph = cur.subgraph;
+            next_subgraph.insert(vertex);
+            const int valency = additional_valency(next_subgraph, vertex);
+            const int next_dof = cur.dof + graph.dof[vertex] - valency;
+            bool blocked = false;
+            for (const std::set<uint32_t>& b : blocked_subgraphs) blocked = blocked || b == next_subgraph;
+            if (!blocked && next_dof > k) {
+                out = std::move(next_subgraph);
+                return true;
+            }
+            SubgraphState nx;
+            nx.adjacent_vertices = cur.adjacent_vertices;
+            nx.adjacent_vertices.erase(vertex);
+            extend_adjacent_vertices(nx.adjacent_vertices, vertex, next_subgraph);
+            nx.subgraph = std::move(next_subgraph);
+            nx.dof = next_dof;
+            queue.push_back(std::move(nx));
+        }
+    }
+    return false;
+}
+
+// recursive_assembly.rs:165-483 (decompose::<D>), the Modified Frontier Algorithm as the reference runs it.
+template <int D>
+inline std::vector<RecombinationStep> decompose(Graph graph, const std::set<uint32_t>& vertices_in, const std::set<uint32_t>& edges_in) {
+    const uint32_t num_real_constraints = (uint32_t)graph.n_constraints, num_real_elements = (uint32_t)graph.n_elements;
+    std::set<uint32_t> vertices = vertices_in, available_edges = edges_in, constraints_handled, vertices_handled;
+    std::map<uint32_t, std::vector<uint32_t>> on_frontiers, owned_elements, frontier_elements;
+    std::map<uint32_t, uint32_t> owning_cluster;
+    std::vector<std::set<uint32_t>> blocked_clusters;
+    std::vector<RecombinationStep> plan;
+    std::vector<uint32_t> step_constraints, step_fixes_elements;
+    for (uint32_t step = 0;; step++) {
+        const uint32_t cluster_key = step;
+        std::set<uint32_t> subgraph;
+        if (!dense_bfs<D>(graph, blocked_clusters, available_edges, vertices, subgraph)) {  // :209-251
+            RecombinationStep rs;
+            for (uint32_t edge : available_edges)
+                if (edge < num_real_constraints && !constraints_handled.count(edge)) rs.constraints.push_back(edge);
+            for (uint32_t vertex : vertices)
+                if (vertex < num_real_elements && !vertices_handled.count(vertex)) rs.free_elements.push_back(vertex);
+            if (!rs.constraints.empty()) {
+                for (uint32_t vertex : vertices)
+                    if (vertex < num_real_elements) rs.elements.push_back(vertex);
+                rs.on_frontiers = on_frontiers;
+                rs.owned_elements = owned_elements;
+                rs.frontier_elements = frontier_elements;
+                plan.push_back(std::move(rs));
+            }
+            break;
+        }
+        std::vector<uint32_t> core, real_elements;  // :263-310
+        std::set<uint32_t> frontier;
+        for (uint32_t vertex : subgraph) {
+            if (vertex < num_real_elements) real_elements.push_back(vertex);
+            if (vertex < num_real_elements && !vertices_handled.count(vertex)) {
+                step_fixes_elements.push_back(vertex);
+                vertices_handled.insert(vertex);
+                owning_cluster[vertex] = cluster_key;
+            }
+            bool frontier_vertex = false;
+            for (uint32_t edge_id : graph.incident_constraints[vertex]) {
+                if (!available_edges.count(edge_id)) continue;
+                bool inside = true;
+                for (uint32_t e : graph.incident_elements[edge_id]) inside = inside && subgraph.count(e);
+                if (inside) {
+                    if (edge_id < num_real_constraints && !constraints_handled.count(edge_id)) {
+                        step_constraints.push_back(edge_id);
+                        constraints_handled.insert(edge_id);
+                    }
+                } else {
+                    frontier_vertex = true;
+                }
+            }
+            if (!frontier_vertex) core.push_back(vertex);
+            else frontier.insert(vertex);
+        }
+        if (!step_constraints.empty()) {  // :312-322
+            RecombinationStep rs;
+            rs.constraints = std::move(step_constraints);
+            step_constraints.clear();
+            rs.elements = real_elements;
+            rs.free_elements = step_fixes_elements;
+            rs.on_frontiers = on_frontiers;
+            rs.owned_elements = owned_elements;
+            rs.frontier_elements = frontier_elements;
+            plan.push_back(std::move(rs));
+        }
+        if (!core.empty() || !step_fixes_elements.empty()) {  // :324-337
+            owned_elements[cluster_key] = std::move(step_fixes_elements);
+            step_fixes_elements.clear();
+        }
+        auto in_core = [&](uint32_t e) { return std::find(core.begin(), core.end(), e) != core.end(); };
+        for (uint32_t vertex : core) {  // :340-387
+            if (vertex < num_real_elements) {
+                for (uint32_t edge_id : graph.incident_constraints[vertex]) {
+                    bool inside = true;
+                    for (uint32_t e : graph.incident_elements[edge_id]) inside = inside && in_core(e);
+                    if (inside) available_edges.erase(edge_id);
+                }
+            }
+            const uint32_t old_cluster_key = owning_cluster.at(vertex);  // (`insert(..).unwrap()`: the vertex has an owner)
+            owning_cluster[vertex] = cluster_key;
+            if (old_cluster_key != cluster_key) {
+                std::vector<uint32_t> old_owned = std::move(owned_elements.at(old_cluster_key));
+                owned_elements.erase(old_cluster_key);
+                for (uint32_t v : old_owned) owning_cluster[v] = cluster_key;
+                std::vector<uint32_t>& mine = owned_elements.at(cluster_key);
+                mine.insert(mine.end(), old_owned.begin(), old_owned.end());
+                std::vector<uint32_t> old_frontier = std::move(frontier_elements.at(old_cluster_key));
+                frontier_elements.erase(old_cluster_key);
+                for (uint32_t element : old_frontier) {
+                    auto it = on_frontiers.find(element);
+                    if (it == on_frontiers.end()) continue;
+                    std::vector<uint32_t>& of = it->second;
+                    const size_t idx = (size_t)(std::find(of.begin(), of.end(), old_cluster_key) - of.begin());
+                    if (idx == of.size()) throw std::out_of_range("position(..).unwrap() on None, recursive_assembly.rs:377-381");
+                    of[idx] = of.back();  // swap_remove
+                    of.pop_back();
+                }
+            }
+            on_frontiers.erase(vertex);
+        }
+        for (uint32_t vertex : frontier) {  // :388-397
+            on_frontiers[vertex].push_back(cluster_key);
+            if (vertex < num_real_elements) frontier_elements[cluster_key].push_back(vertex);
+        }
+        if (subgraph.size() - frontier.size() <= 1) {  // :409-419
+            blocked_clusters.push_back(subgraph);
+            continue;
+        }
+        for (uint32_t vertex : core) vertices.erase(vertex);  // :423-428
+        const uint32_t core_vertex = graph.add_element(0);
+        owning_cluster[core_vertex] = cluster_key;
+        vertices.insert(core_vertex);
+        int total_frontier_vertex_dof = 0, total_incoming_edge_valency = 0;
+        for (uint32_t vertex : frontier) {  // :432-472
+            total_frontier_vertex_dof += graph.dof[vertex];
+            int binary_edge_cluster_valency = 0;
+            const std::vector<uint32_t> incident = graph.incident_constraints[vertex];  // (add_constraint below appends to it)
+            for (uint32_t edge_id : incident) {
+                if (!available_edges.count(edge_id)) continue;
+                bool inside = true;
+                for (uint32_t e : graph.incident_elements[edge_id]) inside = inside && subgraph.count(e);
+                if (!inside) continue;
+                // graph.rs:58-93 merge_elements: every element that is not on the frontier becomes `core_vertex` (once)
+                std::vector<uint32_t> merged;
+                bool did = false;
+                for (uint32_t e : graph.incident_elements[edge_id]) {
+                    if (!frontier.count(e)) {
+                        if (!did) merged.push_back(core_vertex);
+                        did = true;
+                    } else {
+                        merged.push_back(e);
+                    }
+                }
+                if (merged.size() == 2) {
+                    binary_edge_cluster_valency += graph.valency[edge_id];
+                    available_edges.erase(edge_id);
+                } else {
+                    graph.incident_elements[edge_id] = merged;
+                }
+            }
+            if (binary_edge_cluster_valency > 0) {
+                const uint32_t inc[2] = {vertex, core_vertex};
+                const uint32_t cluster_edge = graph.add_constraint(inc, 2, (int16_t)binary_edge_cluster_valency);
+                available_edges.insert(cluster_edge);
+                total_incoming_edge_valency += binary_edge_cluster_valency;
+            }
+        }
+        if (total_incoming_edge_valency > 0) graph.dof[core_vertex] = (int16_t)(total_frontier_vertex_dof - total_incoming_edge_valency - D);  // :474-479
+        else vertices.erase(core_vertex);
+    }
+    return plan;
+}
 
 struct SolvingOptions {
     bool perturb = true;  // lib.rs:232-236
@@ -985,7 +1230,7 @@ struct System {
             variables.push_back(vars[k]);
             variable_to_primitive.push_back(id);
         }
-        graph.add_element();
+        graph.add_element((int16_t)n);  // lib.rs:372-403: dof = number of variables the element adds
         elements.push_back(mk(variables_idx, a, b));
         return id;
     }
@@ -1041,7 +1286,7 @@ struct System {
     uint32_t point_point_coincidence(uint32_t p1, uint32_t p2) {
         uint32_t i1 = elements[p1].a, i2 = elements[p2].a;
         uint32_t inc[2] = {p1, p2};
-        graph.add_constraint(inc, 2);
+        graph.add_constraint(inc, 2, 2);  // constraints/mod.rs:331-334: valency 2
         Expression e[2];
         e[0].kind = VariableVariableEquality; e[0].idx[0] = i1; e[0].idx[1] = i2;
         e[1].kind = VariableVariableEquality; e[1].idx[0] = i1 + 1; e[1].idx[1] = i2 + 1;
@@ -1260,6 +1505,208 @@ struct System {
         return dependent;
     }
 };
+
+
+// ---- Decomposer::RecursiveAssembly: the per-step problem and the driver (assemble/mod.rs:212-725) ------
+// constraints/expressions.rs:1094-1159
+struct Pose2D {
+    double rotation, tx, ty;
+    void transform_point(double u, double v, double& x, double& y) const {  // :1122-1136
+        const double s = std::sin(rotation), c = std::cos(rotation);  // f64::sin_cos
+        const double uc = u * c, us = u * s, vc = v * c, vs = v * s;
+        x = tx + uc - vs;
+        y = ty + us + vc;
+    }
+    void gradient_chain_rule_point(double u, double v, double g0, double g1, double out[3]) const {  // :1139-1158
+        const double s = std::sin(rotation), c = std::cos(rotation);
+        const double uc = u * c, us = u * s, vc = v * c, vs = v * s;
+        out[0] = (-us - vc) * g0 + (uc - vs) * g1;
+        out[1] = g0;
+        out[2] = g1;
+    }
+};
+
+// assemble/mod.rs:282-590: cluster poses (3 variables each, initially 0) followed by the variables of the step's elements;
+// rows: two coincidence rows per (cluster, frontier point), then the step's expressions.
+struct ClusteredSystem {
+    const System* system = nullptr;
+    uint32_t num_variables_ = 0, num_pose_expressions = 0;
+    std::vector<uint32_t> step_plus_frontier_elements, expressions;
+    std::vector<std::pair<uint32_t, std::vector<uint32_t>>> clusters;  // IndexMap<ClusterKey, Vec<ElementId>>: insertion order
+    std::map<uint32_t, uint32_t> variable_mapping_pose_and_element;
+
+    static const std::vector<uint32_t>* lookup(const std::map<uint32_t, std::vector<uint32_t>>& m, uint32_t key) {
+        auto it = m.find(key);
+        return it == m.end() ? nullptr : &it->second;
+    }
+    // :322-478
+    void build(const System& sys, const RecombinationStep& step, std::vector<double>& pose_and_element_variables) {
+        system = &sys;
+        num_variables_ = 0; num_pose_expressions = 0;
+        step_plus_frontier_elements.clear(); expressions.clear(); clusters.clear(); variable_mapping_pose_and_element.clear();
+        pose_and_element_variables.clear();
+        for (uint32_t c : step.constraints)
+            for (int off = 0; off < valency_of(sys.constraints[c].tag); off++) expressions.push_back(sys.constraints[c].expressions_idx + (uint32_t)off);
+        step_plus_frontier_elements = step.elements;
+        auto contains = [](const std::vector<uint32_t>& v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+        std::vector<uint32_t> reachable_clusters;  // :355-398
+        for (uint32_t el : step.elements) {
+            if (sys.elements[el].tag != EPoint) continue;
+            if (const std::vector<uint32_t>* cl = lookup(step.on_frontiers, el))
+                for (uint32_t c : *cl)
+                    if (!contains(reachable_clusters, c)) reachable_clusters.push_back(c);
+        }
+        for (size_t i = 0; i < reachable_clusters.size(); i++) {
+            const uint32_t cluster = reachable_clusters[i];
+            for (uint32_t el : step.frontier_elements.at(cluster)) {
+                if (sys.elements[el].tag != EPoint) continue;
+                const std::vector<uint32_t>* cl = lookup(step.on_frontiers, el);
+                if (cl)
+                    for (uint32_t c : *cl)
+                        if (!contains(reachable_clusters, c)) reachable_clusters.push_back(c);
+                const size_t num_frontiers = cl ? cl->size() : 0;
+                if (!contains(step_plus_frontier_elements, el) && num_frontiers > 1) step_plus_frontier_elements.push_back(el);
+            }
+        }
+        for (uint32_t el : step_plus_frontier_elements) {  // :401-429
+            const std::vector<uint32_t>* cl = lookup(step.on_frontiers, el);
+            if (!cl || sys.elements[el].tag != EPoint) continue;
+            for (uint32_t cluster : *cl) {
+                num_pose_expressions += 2;
+                auto it = std::find_if(clusters.begin(), clusters.end(), [&](const std::pair<uint32_t, std::vector<uint32_t>>& c) { return c.first == cluster; });
+                if (it == clusters.end()) {
+                    clusters.emplace_back(cluster, std::vector<uint32_t>());
+                    it = clusters.end() - 1;
+                }
+                it->second.push_back(el);
+            }
+        }
+        pose_and_element_variables.assign(clusters.size() * 3, 0.);  // :432
+        for (uint32_t el : step_plus_frontier_elements) {  // :437-475
+            const EncodedElement& e = sys.elements[el];
+            if (e.tag == ELength) {
+                variable_mapping_pose_and_element[e.a] = (uint32_t)pose_and_element_variables.size();
+                pose_and_element_variables.push_back(sys.variables_transformed[e.a]);
+            } else if (e.tag == EPoint) {
+                variable_mapping_pose_and_element[e.a] = (uint32_t)pose_and_element_variables.size();
+                variable_mapping_pose_and_element[e.a + 1] = (uint32_t)pose_and_element_variables.size() + 1;
+                pose_and_element_variables.push_back(sys.variables_transformed[e.a]);
+                pose_and_element_variables.push_back(sys.variables_transformed[e.a + 1]);
+            }
+        }
+        num_variables_ = (uint32_t)pose_and_element_variables.size();
+    }
+    uint32_t num_variables() const { return num_variables_; }                                          // :620-623
+    uint32_t num_residuals() const { return (uint32_t)expressions.size() + num_pose_expressions; }     // :625-628
+
+    // :630-685
+    void calculate_residuals(const double* x, double* residuals) const {
+        for (uint32_t r = 0; r < num_residuals(); r++) residuals[r] = 0.;
+        uint32_t vi[8];
+        double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8];
+        const size_t offset = num_pose_expressions;
+        for (size_t k = 0; k < expressions.size(); k++) {
+            const Expression& e = system->expressions_transformed[expressions[k]];
+            const int a = variable_indices(e, vi);
+            for (int q = 0; q < a; q++) vals[q] = x[variable_mapping_pose_and_element.at(vi[q])];
+            residuals[offset + k] = compute_residual_and_gradient(e, vals, grad);
+        }
+        size_t r = 0;
+        for (size_t ci = 0; ci < clusters.size(); ci++) {
+            const Pose2D pose{x[3 * ci], x[3 * ci + 1], x[3 * ci + 2]};
+            for (uint32_t point : clusters[ci].second) {
+                const uint32_t idx = system->elements[point].a;
+                double tx_, ty_;
+                pose.transform_point(system->variables_transformed[idx], system->variables_transformed[idx + 1], tx_, ty_);
+                const uint32_t updated_idx = variable_mapping_pose_and_element.at(idx);
+                residuals[r] = tx_ - x[updated_idx];
+                residuals[r + 1] = ty_ - x[updated_idx + 1];
+                r += 2;
+            }
+        }
+    }
+    // :486-588 through PushTriplet for TripletMat (:598-602)
+    void calculate_residuals_and_sparse_jacobian(const double* x, double* residuals, solvi::TripletMat& jac) const {
+        uint32_t vi[8];
+        double vals[8] = {0, 0, 0, 0, 0, 0, 0, 0}, grad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const size_t offset = num_pose_expressions;
+        for (size_t k = 0; k < expressions.size(); k++) {
+            const Expression& e = system->expressions_transformed[expressions[k]];
+            const int a = variable_indices(e, vi);
+            for (int q = 0; q < a; q++) vals[q] = x[variable_mapping_pose_and_element.at(vi[q])];
+            residuals[offset + k] = compute_residual_and_gradient(e, vals, grad);
+            for (int q = 0; q < a; q++) jac.push_triplet(offset + k, variable_mapping_pose_and_element.at(vi[q]), grad[q]);
+        }
+        size_t r = 0;
+        for (size_t ci = 0; ci < clusters.size(); ci++) {
+            const size_t pose_start_idx = 3 * ci;
+            const Pose2D pose{x[pose_start_idx], x[pose_start_idx + 1], x[pose_start_idx + 2]};
+            for (uint32_t point : clusters[ci].second) {
+                const uint32_t idx = system->elements[point].a;
+                const double u = system->variables_transformed[idx], v = system->variables_transformed[idx + 1];
+                double tx_, ty_;
+                pose.transform_point(u, v, tx_, ty_);
+                const uint32_t updated_idx = variable_mapping_pose_and_element.at(idx);
+                residuals[r] = tx_ - x[updated_idx];
+                residuals[r + 1] = ty_ - x[updated_idx + 1];
+                double gx[3], gy[3];
+                pose.gradient_chain_rule_point(u, v, 1., 0., gx);
+                pose.gradient_chain_rule_point(u, v, 0., 1., gy);
+                for (int q = 0; q < 3; q++) jac.push_triplet(r, pose_start_idx + q, gx[q]);
+                for (int q = 0; q < 3; q++) jac.push_triplet(r + 1, pose_start_idx + q, gy[q]);
+                jac.push_triplet(r, updated_idx, -1.);
+                jac.push_triplet(r + 1, updated_idx + 1, -1.);
+                r += 2;
+            }
+        }
+    }
+};
+
+// assemble/mod.rs:212-277.  `plan_out` (optional) receives the steps of every component in order.
+inline void solve_recursive_assembly(System& sys, const SolvingOptions& opts, std::vector<RecombinationStep>* plan_out = nullptr,
+                                     bool dry_run = false) {
+    sys.last_reports.clear();
+    // (for_each_component hands over the component's rows and free variables; the decomposition starts again from its
+    // element and constraint sets, so the loop of assemble/mod.rs:81-125 is walked here with the same generator)
+    size_t comp_at = 0;
+    sys.for_each_component(opts, [&](const System::ComponentProblem&, double system_scale) {
+        while (sys.graph.components[comp_at].elements.empty()) comp_at++;
+        const ConnectedComponent& cc = sys.graph.components[comp_at++];
+        const std::vector<RecombinationStep> steps = decompose<3>(sys.graph, cc.elements, cc.constraints);
+        ClusteredSystem clustered;
+        std::vector<double> x;
+        for (const RecombinationStep& step : steps) {
+            if (plan_out) plan_out->push_back(step);
+            if (dry_run) continue;
+            clustered.build(sys, step, x);
+            LmReport rep;
+            levenberg_marquardt(clustered, x.data(), rep, false);
+            for (const auto& kv : clustered.variable_mapping_pose_and_element) {  // :226-233
+                sys.variables_transformed[kv.first] = x[kv.second];
+                sys.variables[kv.first] = system_scale * x[kv.second];
+            }
+            for (size_t ci = 0; ci < clustered.clusters.size(); ci++) {  // :235-273
+                const Pose2D pose{x[3 * ci], x[3 * ci + 1], x[3 * ci + 2]};
+                const std::vector<uint32_t>* owned = ClusteredSystem::lookup(step.owned_elements, clustered.clusters[ci].first);
+                if (!owned) continue;
+                for (uint32_t el : *owned) {
+                    if (std::find(clustered.step_plus_frontier_elements.begin(), clustered.step_plus_frontier_elements.end(), el) !=
+                        clustered.step_plus_frontier_elements.end())
+                        continue;
+                    if (sys.elements[el].tag != EPoint) continue;
+                    const uint32_t idx = sys.elements[el].a;
+                    double nx, ny;
+                    pose.transform_point(sys.variables_transformed[idx], sys.variables_transformed[idx + 1], nx, ny);
+                    sys.variables_transformed[idx] = nx;
+                    sys.variables_transformed[idx + 1] = ny;
+                    sys.variables[idx] = system_scale * nx;
+                    sys.variables[idx + 1] = system_scale * ny;
+                }
+            }
+            sys.last_reports.push_back(std::move(rep));
+        }
+    });
+}
 
 }  // namespace fiksi
 }  // namespace orc

@@ -3,6 +3,7 @@
 // extern "C" surface over the CPU restatement (colamd_ref.hpp, solvi_ref.hpp, fiksi_ref.hpp) so
 // that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs can
 // drive it through ctypes.  Nothing under fiksi_b200/ links or loads this library.
+#include <stdexcept>
 #include <chrono>
 #include <cstring>
 #include <thread>
@@ -480,6 +481,53 @@ ORC_API void orc_single_pass_plan(void* s, uint32_t* sizes3, uint32_t* free_ptr,
         for (uint32_t e : plan[k].expressions) exprs[ae++] = e;
     }
     free_ptr[plan.size()] = af; expr_ptr[plan.size()] = ae;
+}
+// Decomposer::RecursiveAssembly (assemble/mod.rs:212-277)
+// Returns 0, or 1 where the reference would panic (an `unwrap()` on a missing map entry in
+// recursive_assembly.rs:352-373 or assemble/mod.rs:374; the restatement uses map::at there).
+ORC_API int orc_solve_recursive_assembly(void* s, int perturb) {
+    fiksi::SolvingOptions o;
+    o.perturb = perturb != 0;
+    try {
+        fiksi::solve_recursive_assembly(*SYS, o);
+    } catch (const std::out_of_range&) {
+        return 1;
+    }
+    return 0;
+}
+// The recombination plan of all components as one stream of 32-bit words (the same serialisation as
+// fk_system_recursive_assembly_plan): per step  n_constraints, constraints..., n_elements, elements..., n_free,
+// free elements..., then the three maps (on_frontiers, owned_elements, frontier_elements), each as n_keys and per key
+// (ascending)  key, n, values....  Returns the number of words; writes at most `cap`.
+ORC_API uint32_t orc_recursive_assembly_plan(void* s, uint32_t* out, uint32_t cap, uint32_t* n_steps) {
+    std::vector<fiksi::RecombinationStep> plan;
+    fiksi::System copy = *SYS;  // the dry run still scales / perturbs: keep the caller's system untouched
+    fiksi::SolvingOptions o;
+    try {
+        fiksi::solve_recursive_assembly(copy, o, &plan, true);
+    } catch (const std::out_of_range&) {  // the reference would panic (see orc_solve_recursive_assembly)
+        if (n_steps) *n_steps = 0xFFFFFFFFu;
+        return 0;
+    }
+    std::vector<uint32_t> w;
+    auto list = [&](const std::vector<uint32_t>& v) {
+        w.push_back((uint32_t)v.size());
+        w.insert(w.end(), v.begin(), v.end());
+    };
+    auto map = [&](const std::map<uint32_t, std::vector<uint32_t>>& m) {
+        w.push_back((uint32_t)m.size());
+        for (const auto& kv : m) {
+            w.push_back(kv.first);
+            list(kv.second);
+        }
+    };
+    for (const fiksi::RecombinationStep& st : plan) {
+        list(st.constraints); list(st.elements); list(st.free_elements);
+        map(st.on_frontiers); map(st.owned_elements); map(st.frontier_elements);
+    }
+    if (n_steps) *n_steps = (uint32_t)plan.size();
+    for (size_t k = 0; k < w.size() && k < cap && out; k++) out[k] = w[k];
+    return (uint32_t)w.size();
 }
 ORC_API uint32_t orc_num_reports(void* s) { return (uint32_t)SYS->last_reports.size(); }
 ORC_API void orc_get_report(void* s, uint32_t i, fk_report* out, char* trace, uint32_t cap) {
