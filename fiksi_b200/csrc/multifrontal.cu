@@ -561,53 +561,81 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // (redundantly x4), then the four share the rank-8 update of the rest of the row; __syncwarp only.
 constexpr int kColThreads = 256;
 constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (row, quarter) hit distinct banks
-// Blocked forward substitution of the rows in Cs ([TB][kYsLd], zero padded) against the unit-lower tile in Ls
-// ([TB][kTsLd], strictly lower part, zero padded): on return Cs holds Y = C L_kk^-T (unscaled).
-__device__ __forceinline__ void col_tile_step(double* row, const double* Ls, uint32_t k0, uint32_t nc, uint32_t q, double (&y)[MB]) {
+constexpr int kLtLd = TB + 2;  // row stride of the TRANSPOSED unit-lower tile: even (16-byte aligned 8-column strips), and the four
+                               // rows k, k+1, k+2, k+3 the quarters of a row read together start 4 banks apart
+// Blocked forward substitution of the rows in Cs ([TB][kYsLd], zero padded) against the unit-lower tile, held transposed in
+// Lt ([TB][kLtLd]: Lt[k][j] = L[j][k] for j > k, zero elsewhere): on return Cs holds Y = C L_kk^-T (unscaled).
+// One strip of 8 columns at a time, LEFT-looking: y[r][k0+c] = C[r][k0+c] - sum_{k < k0+c} y[r][k] L[k0+c][k], in two steps
+// separated by a CTA barrier (the caller's):
+//  (1) col_strip_partial, all 256 threads: warp w takes the rows 32 (w & 1) + lane and the columns k = (w >> 1) mod 4 of the
+//      sum over k < k0: per k one value of the lane's row (a conflict-free load) and one 64-byte strip of Lt that the whole
+//      warp reads from the SAME address (four broadcast loads) feed eight FMAs; the eight partial sums go to Ps;
+//  (2) col_strip_finish, threads 0..63 = rows: the four partial sums are added in a fixed order, the eight columns of the
+//      strip are solved in registers, y goes back to Cs.
+// What this replaces read the strip of Lt from four addresses per warp (a 16-byte load from four addresses costs four
+// passes of the shared-memory pipe, not one) and, before that, nine values per FMA pair of every LATER column in every
+// strip (right-looking): the tile took 1.9 us per strip behind a diagonal tile that publishes a strip every microsecond.
+constexpr int kPsLd = MB + 1;  // row stride of the partial sums: 32 rows -> 32 different banks
+constexpr size_t kPsDoubles = 4 * (size_t)TB * kPsLd;
+
+__device__ __forceinline__ void col_strip_partial(const double* Cs, const double* Lt, double* Ps, uint32_t k0) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = 32u * (warp & 1u) + lane, ks = warp >> 1;
+    const double* row = Cs + r * kYsLd;
+    double s[MB];
 #pragma unroll
-    for (int c = 0; c < MB; c++) y[c] = row[k0 + c];
+    for (int c = 0; c < MB; c++) s[c] = 0.0;
+#pragma unroll 2
+    for (uint32_t k = ks; k < k0; k += 4) {
+        const double yk = row[k];
+        const double2* l2 = reinterpret_cast<const double2*>(Lt + k * kLtLd + k0);
 #pragma unroll
-    for (int cp = 0; cp + 1 < MB; cp++)  // column-oriented substitution: independent FMAs per step, same sum order per entry
-#pragma unroll
-        for (int c = cp + 1; c < MB; c++) y[c] = fma(-y[cp], Ls[(k0 + c) * kTsLd + k0 + cp], y[c]);
-    __syncwarp();  // all four threads of the row have read the block before it is overwritten
-    if (q == 0) {
-#pragma unroll
-        for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
-    }
-    // four columns per step, all loads before the first store (see the helper loop of diag_tile_factor)
-    for (uint32_t cp0 = k0 + MB + q; cp0 < nc; cp0 += 16) {
-        double v0[4], v1[4], lv[4][MB];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t cp = min(cp0 + 4u * u, (uint32_t)TB - 1);  // (clamped: columns beyond nc are computed, not stored)
-            const double* Lr = Ls + cp * kTsLd + k0;
-            v0[u] = row[cp];
-            v1[u] = 0.0;
-#pragma unroll
-            for (int c = 0; c < MB; c++) lv[u][c] = Lr[c];
+        for (int c = 0; c < MB; c += 2) {
+            const double2 t = l2[c >> 1];
+            s[c] = fma(yk, t.x, s[c]);
+            s[c + 1] = fma(yk, t.y, s[c + 1]);
         }
-#pragma unroll
-        for (int c = 0; c < MB; c += 2)
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                v0[u] = fma(-y[c], lv[u][c], v0[u]);
-                v1[u] = fma(-y[c + 1], lv[u][c + 1], v1[u]);
-            }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (cp0 + 4u * u < nc) row[cp0 + 4u * u] = v0[u] + v1[u];
     }
-    __syncwarp();
+    double* ps = Ps + (ks * TB + r) * kPsLd;
+#pragma unroll
+    for (int c = 0; c < MB; c++) ps[c] = s[c];
 }
 
-__device__ __forceinline__ void col_tile_solve(double* Cs, const double* Ls, uint32_t nc) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t i = tid >> 2, q = tid & 3;
-    double* row = Cs + i * kYsLd;
+// threads 0..63 only (r = threadIdx.x); y: the row's eight values of the strip (unscaled)
+__device__ __forceinline__ void col_strip_finish(double* Cs, const double* Lt, const double* Ps, uint32_t k0, uint32_t r, double (&y)[MB]) {
+    double* row = Cs + r * kYsLd;
+#pragma unroll
+    for (int c = 0; c < MB; c++) {
+        const double a = Ps[(0 * TB + r) * kPsLd + c] + Ps[(1 * TB + r) * kPsLd + c];
+        const double b = Ps[(2 * TB + r) * kPsLd + c] + Ps[(3 * TB + r) * kPsLd + c];
+        y[c] = row[k0 + c] - (a + b);
+    }
+#pragma unroll
+    for (int cp = 0; cp + 1 < MB; cp++) {  // column-oriented substitution inside the strip: independent FMAs per step
+        const double2* l2 = reinterpret_cast<const double2*>(Lt + (k0 + cp) * kLtLd + k0);
+        double l[MB];
+#pragma unroll
+        for (int c = (cp + 1) & ~1; c < MB; c += 2) {
+            const double2 t = l2[c >> 1];
+            l[c] = t.x;
+            l[c + 1] = t.y;
+        }
+#pragma unroll
+        for (int c = cp + 1; c < MB; c++) y[c] = fma(-y[cp], l[c], y[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < MB; c++) row[k0 + c] = y[c];
+}
+
+__device__ __forceinline__ void col_tile_solve(double* Cs, const double* Lt, double* Ps, uint32_t nc) {
     for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
-        double y[MB];
-        col_tile_step(row, Ls, k0, nc, q, y);
+        col_strip_partial(Cs, Lt, Ps, k0);
+        __syncthreads();
+        if (threadIdx.x < TB) {
+            double y[MB];
+            col_strip_finish(Cs, Lt, Ps, k0, threadIdx.x, y);
+        }
+        __syncthreads();
     }
 }
 
@@ -615,7 +643,8 @@ __global__ void __launch_bounds__(kColThreads)
 mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
     extern __shared__ __align__(16) double smd_col[];
     double* Cs = smd_col;            // [TB][kYsLd] rows of the tile (Y, unscaled)
-    double* Ls = Cs + TB * kYsLd;    // [TB][kTsLd] L_kk (unit lower), D on the diagonal
+    double* Ls = Cs + TB * kYsLd;    // [TB][kLtLd] L_kk (unit lower) transposed
+    double* Ps = Ls + TB * kLtLd;    // [4][TB][kPsLd] partial sums of a strip
     __shared__ double invd[TB];
     const uint4 t = __ldg(tasks + blockIdx.x);
     const uint32_t s = t.x, row0 = t.y, col0 = t.z, nr = t.w & 0xFFFFu, nc = t.w >> 16;
@@ -628,11 +657,11 @@ mf_col_kernel(MfDev D, const uint4* __restrict__ tasks) {
     for (uint32_t e = tid; e < ncp * TB; e += kColThreads) {
         const uint32_t ii = e & 63, j = e >> 6;
         Cs[ii * kYsLd + j] = (ii < nr && j < nc) ? C[(size_t)j * f + ii] : 0.0;
-        Ls[ii * kTsLd + j] = (ii < nc && j < ii) ? Lkk[(size_t)j * f + ii] : 0.0;  // strictly lower part, zero padded
+        Ls[j * kLtLd + ii] = (ii < nc && j < ii) ? Lkk[(size_t)j * f + ii] : 0.0;  // strictly lower part, transposed, zero padded
     }
     if (tid < nc) invd[tid] = fast_rcp(Lkk[(size_t)tid * f + tid]);
     __syncthreads();
-    col_tile_solve(Cs, Ls, nc);
+    col_tile_solve(Cs, Ls, Ps, nc);
     __syncthreads();
     for (uint32_t e = tid; e < nc * TB; e += kColThreads) {
         const uint32_t ii = e & 63, j = e >> 6;
@@ -699,10 +728,13 @@ mf_rupd_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // deadlock however many CTAs are resident.  One launch per level instead of 1 + 3 per pivot block.
 #ifdef FK_CHAIN_PROFILE
 #define FK_FSTAMP(k) do { if (threadIdx.x == 0) ((long long*)D.ubuf)[bid * 4 + (k)] = global_ns(); } while (0)
+// harness only: per-strip stamps of the panel tile with ticket 1 (slots behind 1024 tiles)
+#define FK_PSTAMP(strip, k) do { if (threadIdx.x == 0 && bid == 1) ((long long*)D.ubuf)[4096 + (strip) * 4 + (k)] = global_ns(); } while (0)
 #else
 #define FK_FSTAMP(k) do { } while (0)
+#define FK_PSTAMP(strip, k) do { } while (0)
 #endif
-constexpr size_t kFlowSmem = (TB * kYsLd + TB * kTsLd + TB) * sizeof(double);
+constexpr size_t kFlowSmem = (TB * kYsLd + TB * kLtLd + TB + kPsDoubles) * sizeof(double);
 static_assert(kFlowSmem >= sizeof(TileBuf) && kFlowSmem >= kDiagSmem, "the staging buffers and the diagonal-tile arrays alias the solve tiles");
 
 __global__ void __launch_bounds__(kTileThreads)
@@ -796,8 +828,9 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
         return;
     }
     double* Cs = smf;                 // [TB][kYsLd]
-    double* Ls = Cs + TB * kYsLd;     // [TB][kTsLd]
-    double* invd = Ls + TB * kTsLd;   // [TB]
+    double* Ls = Cs + TB * kYsLd;     // [TB][kLtLd] the diagonal tile's unit-lower factor, transposed
+    double* invd = Ls + TB * kLtLd;   // [TB]
+    double* Ps = invd + TB;           // [4][TB][kPsLd] partial sums of a strip
     for (uint32_t e = tid; e < TB * kYsLd; e += kTileThreads) Cs[e] = 0.0;
     __syncthreads();
 #pragma unroll
@@ -807,7 +840,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
             const uint32_t ri = tile_row(tx, i);
             if (ri < nrA && c4 + j < nc) Cs[ri * kYsLd + c4 + j] = acc[i][j];
         }
-    for (uint32_t e = tid; e < TB * kTsLd; e += kTileThreads) Ls[e] = 0.0;
+    for (uint32_t e = tid; e < TB * kLtLd; e += kTileThreads) Ls[e] = 0.0;
     {   // follow the diagonal tile micro-panel by micro-panel: its 8-column strip (rows >= k0: strictly lower part + D) is
         // polled as the owner of the diagonal tile publishes it (the loads of strip k0 + 8 are issued before strip k0 is
         // processed and verified afterwards, so the L2 round trip overlaps the substitution), this tile's rows take the
@@ -815,40 +848,46 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
         // to the right consume them chunk by chunk while the rest of the substitution is still running
         const double* Lkk = Pp + (size_t)tcol0 * f + tcol0;
         const uint32_t ii = tid & 63, cA = tid >> 6;  // entries (ii, k0 + cA) and (ii, k0 + cA + 4)
-        const uint32_t r = tid >> 2, q = tid & 3;
-        double* row = Cs + r * kYsLd;
         double* Tp = Pp + (size_t)tcol0 * f + row0;
         double v[2];
         auto issue = [&](uint32_t k0) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const uint32_t j = k0 + cA + 4u * u;
-                v[u] = (ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
+                v[u] = (k0 < nc && ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
             }
         };
         issue(0);
-        __syncthreads();  // the zero fill of Ls is complete
-        for (uint32_t k0 = 0; k0 < nc; k0 += MB) {
+        for (uint32_t k0 = 0, st = 0; k0 < nc; k0 += MB, st++) {
+            (void)st;
             SpinGuard guard(D.status);
+            FK_PSTAMP(st, 0);
             while ((is_unpublished(v[0]) || is_unpublished(v[1])) && !guard.expired()) issue(k0);
+            FK_PSTAMP(st, 1);
             {   // every strip has its own columns of Ls and entries of invd: nothing a reader of an earlier strip still needs
                 const uint32_t j0 = k0 + cA, j1 = k0 + cA + 4;
-                if (j0 < ii) Ls[ii * kTsLd + j0] = v[0];
+                if (j0 < ii) Ls[j0 * kLtLd + ii] = v[0];
                 else if (j0 == ii && ii < nc) invd[ii] = fast_rcp(v[0]);
-                if (j1 < ii) Ls[ii * kTsLd + j1] = v[1];
+                if (j1 < ii) Ls[j1 * kLtLd + ii] = v[1];
                 else if (j1 == ii && ii < nc) invd[ii] = fast_rcp(v[1]);
             }
+            __syncthreads();  // the strip of Ls (and, the first time, the zero fill; later, the previous strip's y) is in place
+            issue(k0 + MB);   // (after the barrier: a barrier waits for the loads issued before it)
+            FK_PSTAMP(st, 2);
+            col_strip_partial(Cs, Ls, Ps, k0);
             __syncthreads();
-            if (k0 + MB < nc) issue(k0 + MB);  // (after the barrier: a barrier waits for the loads issued before it)
-            double y[MB];
-            col_tile_step(row, Ls, k0, nc, q, y);
-            if (r < nrA) {  // the four threads of a row hold the same y: each stores two of the eight columns
+            if (tid < TB) {
+                double y[MB];
+                col_strip_finish(Cs, Ls, Ps, k0, tid, y);
+                FK_PSTAMP(st, 3);
+                if (tid < nrA) {  // this tile's columns of the strip are final: stored and published at once
 #pragma unroll
-                for (int c = 0; c < MB; c++) {
-                    if ((uint32_t)(c & 3) == q && k0 + c < nc) {
-                        const double out = y[c] * invd[k0 + c];
-                        T[(size_t)(k0 + c) * f + r] = out;
-                        st_relaxed(Tp + (size_t)(k0 + c) * f + r, out);
+                    for (int c = 0; c < MB; c++) {
+                        if (k0 + c < nc) {
+                            const double out = y[c] * invd[k0 + c];
+                            T[(size_t)(k0 + c) * f + tid] = out;
+                            st_relaxed(Tp + (size_t)(k0 + c) * f + tid, out);
+                        }
                     }
                 }
             }
@@ -1458,7 +1497,7 @@ cudaError_t alloc_vec(T** out, size_t count, std::vector<void*>& owned) {
     return e;
 }
 
-constexpr size_t kColSmem = (TB * kYsLd + TB * kTsLd) * sizeof(double);
+constexpr size_t kColSmem = (TB * kYsLd + TB * kLtLd + kPsDoubles) * sizeof(double);
 constexpr size_t kSmallFactorSmem = (size_t)kWarpsPerCta * kSmallFront * kSmallLd * sizeof(double);
 constexpr size_t kSmallSolveSmem = (size_t)kWarpsPerCta * (32 * 33 + kSmallFront) * sizeof(double);
 

@@ -15,7 +15,7 @@ int main() {
     uint32_t* d32; cudaMalloc(&d32, 64); uint64_t* d64; cudaMalloc(&d64, 64);
     cudaMemcpy(d32, h32, 16, cudaMemcpyHostToDevice); cudaMemcpy(d64, &h_off, 8, cudaMemcpyHostToDevice); cudaMemcpy(d64 + 1, &h_off, 8, cudaMemcpyHostToDevice);
     D.S = 1; D.c0 = d32; D.ns = d32 + 1; D.f = d32 + 2; D.winv_blk = d32 + 3; D.pan_off = d64; D.upd_off = d64 + 1;
-    cudaMalloc(&D.pan, A.size() * 8); cudaMalloc(&D.ubuf, 4096 * 8); cudaMalloc(&D.upd, 64); cudaMalloc(&D.status, 4096); cudaMemset(D.status, 0, 4096);
+    cudaMalloc(&D.pan, A.size() * 8); cudaMalloc(&D.ubuf, 8192 * 8); cudaMalloc(&D.upd, 64); cudaMalloc(&D.status, 4096); cudaMemset(D.status, 0, 4096);
     std::vector<uint4> tasks;
     for (uint32_t bj = 0; bj < B; bj++) for (uint32_t bi = bj; bi < B; bi++) tasks.push_back({0, bi * 64, bj * 64, 63u | (63u << 8)});
     uint4* dt; cudaMalloc(&dt, tasks.size() * 16); cudaMemcpy(dt, tasks.data(), tasks.size() * 16, cudaMemcpyHostToDevice);
@@ -58,6 +58,10 @@ int main() {
             if (bi <= bj + 1)
                 printf("tile (%2u,%2u) %s: start %7lld  earlier-blocks-done %7lld  last-block-done %7lld  finished %7lld (ns)\n", bi, bj, bi == bj ? "diag " : "panel",
                        st[at * 4] - t0, st[at * 4 + 1] - t0, st[at * 4 + 2] - t0, st[at * 4 + 3] - t0);
+    {   // per-strip stamps of panel tile (1,0): strip entered, strip's values present, substitution starts, substitution done
+        long long ps[32]; cudaMemcpy(ps, (long long*)D.ubuf + 4096, sizeof(ps), cudaMemcpyDeviceToHost);
+        for (int m = 0; m < 8; m++) printf("panel (1,0) strip %d: enter %7lld  values present %7lld  substitution %7lld .. %7lld (ns)\n", m, ps[m*4] - t0, ps[m*4+1] - t0, ps[m*4+2] - t0, ps[m*4+3] - t0);
+    }
     {
         long long ds[24]; cudaMemcpy(ds, dst, sizeof(ds), cudaMemcpyDeviceToHost);
         for (int m = 0; m < 3; m++) printf("diag tile (0,0) micro-panel %d: 8x8 LDL %lld, own row %lld + stores %lld, barrier %lld, rank-8 update %lld cycles; next starts +%lld\n", m, ds[m*8+1]-ds[m*8], ds[m*8+5]-ds[m*8+1], ds[m*8+2]-ds[m*8+5], ds[m*8+3]-ds[m*8+2], ds[m*8+4]-ds[m*8+3], m < 2 ? ds[(m+1)*8]-ds[m*8+4] : 0);
