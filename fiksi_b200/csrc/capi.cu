@@ -138,10 +138,12 @@ int upload_program(const fk::Topology& t, int device, DeviceProgram& out) {
 struct fk_batch_plan;
 // Per-device staging pipeline of fk_batch_solve: kStreams plans + streams, reused across calls.
 struct DevicePipeline {
-// (six chunks in flight: a chunk's kernel lasts one LM solve however small the chunk is, so with three the copies of
-// small chunks could not keep the device busy; bench truss end to end 56.2 -> 57.7 M sketches/s with 16 chunks)
+// (eight chunks in flight: a chunk's kernel lasts one LM solve however small the chunk is, so with three the copies of
+// small chunks could not keep the device busy; bench truss end to end 56.2 -> 59.0 M sketches/s with 16 chunks.  Swept on
+// B200 with tools/e2e_sweep.py: 4 / 6 / 8 / 16 / 32 streams x 8..32 chunks all end between 1.10 and 1.19 ms per call of
+// 65,536 trusses against 0.905 ms for the kernel alone)
 #ifndef FK_PIPELINE_STREAMS
-#define FK_PIPELINE_STREAMS 6
+#define FK_PIPELINE_STREAMS 8
 #endif
     static constexpr uint32_t kStreams = FK_PIPELINE_STREAMS;
     std::mutex mu;
@@ -983,8 +985,13 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         if (!p->d_scales) CU(cudaMalloc(&p->d_scales, sizeof(double) * p->capacity));
     }
     static const bool no_fuse = std::getenv("FK_NO_FUSED_PREPARE") != nullptr;  // A/B knob
+    static const uint32_t use_streams = [] {
+        const char* e = std::getenv("FK_E2E_STREAMS");  // tuning knob: chunks in flight (at most kStreams)
+        const int v = e ? std::atoi(e) : 0;
+        return (uint32_t)(v >= 1 && v <= (int)DevicePipeline::kStreams ? v : (int)DevicePipeline::kStreams);
+    }();
     uint32_t s = 0;
-    for (uint32_t at = 0; at < n && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
+    for (uint32_t at = 0; at < n && rc == FK_OK; at += chunk, s = (s + 1) % use_streams) {
         const uint32_t cnt = std::min(chunk, n - at);
         fk_batch_plan* p = pl->plans[s];
         cudaStream_t st = pl->streams[s];
