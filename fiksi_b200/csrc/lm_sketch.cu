@@ -36,7 +36,7 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 }
 
 __host__ __device__ constexpr int sk_arity(int kind) {
-    return kind == 0 ? 2 : kind == 1 ? 4 : kind <= 4 ? 6 : kind == 5 ? 5 : kind <= 9 ? 8 : 7;
+    return kind == 0 ? 2 : kind == 1 ? 4 : kind <= 4 ? 6 : kind == 5 ? 5 : kind <= 9 ? 8 : kind == 10 ? 7 : 6;  // 11, 12: the pose rows
 }
 __host__ __device__ constexpr bool sk_has_param(int kind) { return kind == 1 || kind == 2 || kind == 4 || kind == 7; }
 

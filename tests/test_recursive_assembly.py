@@ -137,3 +137,77 @@ def test_panicking_system_is_an_error_not_a_crash():
     s = sc.ALL["connected_triangles"](fsys.System)["s"]
     with pytest.raises(Exception):
         s.solve_recursive_assembly()
+
+
+def _pose_batch(n, seed=7):
+    """n copies of one ClusteredSystem-shaped problem: a cluster pose (variables 0..2) moves point A (constants 7, 8:
+    its position before the step) onto the free point (3, 4), which keeps distance 1 from a second free point (5, 6)."""
+    rng = np.random.default_rng(seed)
+    kind = np.array([11, 12, 1], np.uint8)
+    idx = np.array([[0, 3, 7, 0], [0, 4, 7, 0], [3, 5, 0, 0]], np.uint32)
+    v = np.zeros((n, 9))
+    v[:, 7:9] = rng.normal(size=(n, 2))
+    v[:, 3:5] = v[:, 7:9] + 0.05 * rng.normal(size=(n, 2))
+    v[:, 5:7] = v[:, 3:5] + rng.normal(size=(n, 2))
+    p = np.zeros((n, 3))
+    p[:, 2] = 1.0
+    return kind, idx, v, p
+
+
+@pytest.mark.gpu
+def test_pose_rows_evaluate_as_pose2d():
+    """FK_POSE_POINT_X/Y through the evaluation kernel against constraints/expressions.rs:1122-1158 in numpy
+    (CUDA and glibc sin/cos may differ in the last place: 4 ulp of the operands' magnitude)."""
+    import fiksi_b200 as fk
+    kind, idx, v, p = _pose_batch(257)
+    v[:, 0] = np.linspace(-3.0, 3.0, len(v))      # rotations
+    v[:, 1:3] = 0.3 * v[:, 7:9]                   # translations
+    topo = fk.Topology.from_arrays(9, kind, idx, np.arange(7), np.arange(3))
+    n = len(v)
+    plan = topo.plan(n)
+    plan.upload(v, p)
+    r = np.zeros((n, 3)); J = np.zeros((n, topo.info["jac_nnz"]))
+    plan.eval(0); plan.eval_download(r, J)
+    import torch
+    torch.cuda.synchronize()
+    s, c = np.sin(v[:, 0]), np.cos(v[:, 0])
+    u, w = v[:, 7], v[:, 8]
+    rx = (v[:, 1] + u * c - w * s) - v[:, 3]
+    ry = (v[:, 2] + u * s + w * c) - v[:, 4]
+    tol = 4 * np.finfo(float).eps * (1 + np.abs(v).max())
+    assert np.max(np.abs(r[:, 0] - rx)) <= tol and np.max(np.abs(r[:, 1] - ry)) <= tol
+    # the Jacobian values are in the CSC order of the augmented matrix without its damping entry (the last of every column)
+    sym = topo.symbolic()
+    colptr, rowidx = np.asarray(sym["aug_colptr"]), np.asarray(sym["aug_rowidx"])
+    dense = np.zeros((n, 3, 7))
+    pattern = set()
+    for col in range(7):
+        for q in range(colptr[col], colptr[col + 1] - 1):
+            dense[:, rowidx[q], col] = J[:, q - col]
+            pattern.add((int(rowidx[q]), col))
+    # the explicit zeros the reference pushes (row x / ty, row y / tx: assemble/mod.rs:571-576) are part of the pattern
+    assert pattern == {(0, 0), (0, 1), (0, 2), (0, 3), (1, 0), (1, 1), (1, 2), (1, 4), (2, 3), (2, 4), (2, 5), (2, 6)}
+    assert np.max(np.abs(dense[:, 0, 0] - (-u * s - w * c))) <= tol and np.max(np.abs(dense[:, 1, 0] - (u * c - w * s))) <= tol
+    assert np.all(dense[:, 0, 1] == 1.0) and np.all(dense[:, 0, 2] == 0.0) and np.all(dense[:, 1, 1] == 0.0) and np.all(dense[:, 1, 2] == 1.0)
+    assert np.all(dense[:, 0, 3] == -1.0) and np.all(dense[:, 1, 4] == -1.0)
+
+
+@pytest.mark.gpu
+def test_pose_rows_in_the_batched_kernels():
+    """The three batched LM kernels on a batch of ClusteredSystem-shaped problems: identical reports and coordinates, and
+    the solved poses carry A onto the free point."""
+    import fiksi_b200 as fk
+    from fiksi_b200 import api
+    kind, idx, v, p = _pose_batch(2048 + 3)
+    topo = fk.Topology.from_arrays(9, kind, idx, np.arange(7), np.arange(3))
+    out = {}
+    for kernel in ("tile", "sketch_solo", "sketch_pair"):
+        with api.lm_kernel(kernel):
+            out[kernel] = topo.batch_solve(v, p)
+    xt, rt = out["tile"]
+    for kernel in ("sketch_solo", "sketch_pair"):
+        x, r = out[kernel]
+        for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash"):
+            assert np.array_equal(r[key], rt[key]), (kernel, key)
+        assert np.max(np.abs(x - xt)) <= 1e-9 * np.max(np.abs(xt))
+    assert np.mean(rt["ssr"] < 1e-8) >= 0.99

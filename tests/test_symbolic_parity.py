@@ -108,7 +108,7 @@ def test_random_problems(oracle):
 
 def test_invalid_problems_are_rejected():
     with pytest.raises(fk.FiksiError):
-        fk.Topology.from_arrays(4, [11], [[0, 2, 0, 0]], [0, 1], [0])      # unknown kind
+        fk.Topology.from_arrays(4, [13], [[0, 2, 0, 0]], [0, 1], [0])      # unknown kind (11 and 12 are the pose rows of ClusteredSystem)
     with pytest.raises(fk.FiksiError):
         fk.Topology.from_arrays(4, [1], [[0, 4, 0, 0]], [0, 1], [0])       # variable out of range
     with pytest.raises(fk.FiksiError):
