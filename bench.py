@@ -353,7 +353,7 @@ def main():
                             "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / avg_s / 1e9, "peak_gbs": peak,
                                     "frac": alg_bytes / avg_s / 1e9 / peak, "peak_source": peak_src,
                                     "note": "inputs + outputs once per sketch; not the limiter"},
-                            "profiles": "ncu --set full summaries of this command: profiles/r02_*lm_sketch*",
+                            "profiles": "ncu --set full summaries of this kernel on this workload: profiles/r02b_lm_sketch_pair_kernel_truss_ncu_full_summary.csv (latest), profiles/r02_*lm_sketch*; launch list of this command: profiles/r02b_launches_bench_truss.csv",
                             "note": "latency bound: 32 sketches are solved out of shared memory by one warp (or a leader / helper pair of warps) and "
                                     "only two such groups fit an SM for this topology; see DESIGN.md section 4 for the stall breakdown"}
         if not args.no_extras:
@@ -714,7 +714,8 @@ def assembly_bandwidth(fk, wl, torch, device, peak):
     alg = topo.info["eval_bytes"] * n
     i = topo.info
     dram = 8 * n * (i["n_vars"] + i["n_expr"] + i["n_rows"] + i["jac_nnz"])  # every input and output byte once
-    out = {"kernel": "fk_batch_eval_tiled_kernel<64,true>", "workload": "config 4 topology, 1,000,000 sketches",
+    out = {"kernel": "fk_batch_eval_tiled_kernel<S,true,256,prefetch> (S = 64 for this topology: the inputs of a CTA's next tile arrive by cp.async "
+                     "while the current one is evaluated)", "workload": "config 4 topology, 1,000,000 sketches",
            "bound": "hbm", "algorithmic_bytes": alg, "ms": ms, "achieved_algorithmic_gbs": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
     out["frac_algorithmic"] = out["achieved_algorithmic_gbs"] / peak
     # SURVEY 8d's algorithmic bytes count every per-row gather (17 + 4k + 20a B/row); the tile-staged kernel
@@ -723,7 +724,7 @@ def assembly_bandwidth(fk, wl, torch, device, peak):
     out["min_dram_bytes"] = dram
     out["achieved"] = dram / (ms * 1e-3) / 1e9   # REAL bytes (every input and output byte once): the HBM fraction to quote
     out["frac"] = out["achieved"] / peak
-    out["traffic"] = None  # one ncu --set full capture of this kernel: profiles/r01_k1_tiled_S64_ncu_full_summary.csv (152 MB read + 366 MB written)
+    out["traffic"] = None  # ncu --set full captures of this kernel: profiles/r02b_k1_prefetch_ncu_full_summary.csv, profiles/r01_k1_tiled_S64_ncu_full_summary.csv (152 MB read + 366 MB written)
     plan.close()
     # LM solve of the same 1,000,000 mixed-primitive sketches (config 4), device-resident
     try:

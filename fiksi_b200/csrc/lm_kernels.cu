@@ -448,7 +448,16 @@ __device__ __forceinline__ void eval_tiled_row(const EvalRow& T, uint32_t sk, ui
     }
 }
 
-template <int S, bool WITH_JACOBIAN, int kEvalThreads>
+// 8-byte asynchronous copy global -> shared (no register staging: the copy is in flight while the thread computes)
+__device__ __forceinline__ void eval_cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// PREFETCH: the inputs of a CTA's NEXT tile are copied into a second input buffer with cp.async while the current tile is
+// evaluated and stored (ncu on the version without it: 27 % of the warp samples sit on the stores of the load phase waiting
+// for their global loads, 9 % at the barriers between the phases).
+template <int S, bool WITH_JACOBIAN, int kEvalThreads, bool PREFETCH = false>
 __global__ void __launch_bounds__(kEvalThreads, 1024 / kEvalThreads)
 fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double* __restrict__ vars_all,
                            const double* __restrict__ params_all, double* __restrict__ out_r, double* __restrict__ out_j) {
@@ -456,11 +465,13 @@ fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double
     double* smem = smem_eval;
     constexpr uint32_t LD = S + 1;
     const uint32_t nv = P.n_vars, ne = P.n_expr, m = P.m, jn = P.jnnz;
+    const size_t in_doubles = (size_t)(nv + ne) * LD;
     double* sv = smem;                 // [nv][LD]
-    double* sp = sv + (size_t)nv * LD;  // [ne][LD]
-    double* sr = sp + (size_t)ne * LD;  // [m][LD]
+    double* sp = sv + (size_t)nv * LD;  // [ne][LD]   (PREFETCH: a second [nv + ne][LD] input buffer follows)
+    double* sr = smem + (PREFETCH ? 2 : 1) * in_doubles;  // [m][LD]
     double* sj = sr + (size_t)m * LD;   // [jn][LD]
-    EvalRow* tab = reinterpret_cast<EvalRow*>(sj + (WITH_JACOBIAN ? (size_t)jn * LD : 0) + ((nv + ne + m + (WITH_JACOBIAN ? jn : 0)) & 1u));
+    EvalRow* tab = reinterpret_cast<EvalRow*>(sj + (WITH_JACOBIAN ? (size_t)jn * LD : 0) +
+                                              (((PREFETCH ? 2 : 1) * (nv + ne) + m + (WITH_JACOBIAN ? jn : 0)) & 1u));
     const uint32_t tid = threadIdx.x;
     const uint32_t n_tiles = (n_sketches + S - 1) / S;
 
@@ -532,11 +543,40 @@ fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double
         }
     };
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto transpose_in_async = [&](const double* __restrict__ src, double* dst, uint32_t width, uint32_t total) {
+        if (width == 0) return;
+        const uint32_t M = width == 1 ? 0u : 0xFFFFFFFFu / width + 1u;
+        for (uint32_t i = tid; i < total; i += kEvalThreads) {
+            const uint32_t q = width == 1 ? i : __umulhi(i, M);
+            eval_cp_async8(dst + (i - q * width) * LD + q, src + i);
+        }
+    };
+    auto prefetch = [&](uint32_t tile, uint32_t buf) {
         const uint32_t first = tile * S;
         const uint32_t count = min((uint32_t)S, n_sketches - first);
-        transpose_in(vars_all + (size_t)first * nv, sv, nv, count * nv);
-        transpose_in(params_all + (size_t)first * ne, sp, ne, count * ne);
+        transpose_in_async(vars_all + (size_t)first * nv, smem + buf * in_doubles, nv, count * nv);
+        transpose_in_async(params_all + (size_t)first * ne, smem + buf * in_doubles + (size_t)nv * LD, ne, count * ne);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (PREFETCH && blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        const uint32_t first = tile * S;
+        const uint32_t count = min((uint32_t)S, n_sketches - first);
+        if (PREFETCH) {
+            const uint32_t b = it & 1u;
+            if (tile + gridDim.x < n_tiles) {  // the other buffer's readers finished before the barrier that ended the last tile
+                prefetch(tile + gridDim.x, b ^ 1u);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            sv = smem + b * in_doubles;
+            sp = sv + (size_t)nv * LD;
+        } else {
+            transpose_in(vars_all + (size_t)first * nv, sv, nv, count * nv);
+            transpose_in(params_all + (size_t)first * ne, sp, ne, count * ne);
+        }
         __syncthreads();
         for (uint32_t item = tid; item < m * S; item += kEvalThreads) {
             const uint32_t row = item / S, sk = item % S;  // S is a power of two >= 32: row is warp-uniform
@@ -1216,42 +1256,64 @@ int launch_batch_eval(const DevProgram& prog, uint32_t n_sketches, const double*
         auto bytes_for = [&](int S) { return (per_sketch_rows * (size_t)(S + 1) + 1) * sizeof(double) + (size_t)prog.m * sizeof(EvalRow); };
         // 256-thread CTAs, largest tile that keeps three of them (24 warps) on an SM: measured on B200 (tools/bench_assembly.py,
         // residual + Jacobian, M sketches of the config-4 topology / 262,144 trusses): 128 threads S=64 0.185 / 0.216 ms,
-        // 256 threads S=128 0.173 ms, S=32 (truss: the largest that fits) 0.163 ms.  The kernel is bound by instruction
-        // issue (IEEE divide / sqrt / atan2 sequences, ~3,200 thread instructions per config-4 sketch), not by bytes in flight.
+        // 256 threads S=128 0.173 ms, S=32 (truss: the largest that fits) 0.163 ms; with the input prefetch S=64 0.161 ms
+        // (S=128 0.165) and truss S=32 0.139 ms.  What remains is instruction issue (IEEE divide / sqrt / atan2 sequences and
+        // index arithmetic: ~3,000 thread instructions per config-4 sketch, a quarter of them IMAD), not bytes in flight.
+        // Input prefetch (second input buffer, cp.async): default on; FK_EVAL_PF=0 keeps the load phase in front of every tile.
+        static const bool want_pf = [] {
+            const char* e = std::getenv("FK_EVAL_PF");
+            return !(e && std::atoi(e) == 0);
+        }();
+        auto bytes_pf = [&](int S) { return bytes_for(S) + ((size_t)prog.n_vars + prog.n_expr) * (size_t)(S + 1) * sizeof(double); };
         int S = 0;
-        for (int cand : {32, 64, 128})
-            if (bytes_for(cand) <= 76 * 1024) S = cand;
+        bool pf = false;
+        if (want_pf) {  // largest tile that keeps four CTAs on an SM, else three
+            for (int cand : {32, 64, 128})
+                if (bytes_pf(cand) <= 55 * 1024) S = cand;
+            if (S == 0)
+                for (int cand : {32, 64, 128})
+                    if (bytes_pf(cand) <= 74 * 1024) S = cand;
+            if (S == 0)
+                for (int cand : {32, 64, 128})
+                    if (bytes_pf(cand) <= 110 * 1024) S = cand;  // two CTAs: still ahead (truss, S = 32: 0.139 ms against 0.163)
+            pf = S != 0;
+        }
+        if (S == 0)
+            for (int cand : {32, 64, 128})
+                if (bytes_for(cand) <= 76 * 1024) S = cand;
         if (S == 0)
             for (int cand : {128, 64, 32})
                 if (bytes_for(cand) <= 110 * 1024) { S = cand; break; }
         if (const char* e = std::getenv("FK_EVAL_S")) {
             const int f = std::atoi(e);
-            if ((f == 32 || f == 64 || f == 128) && bytes_for(f) <= 200 * 1024) S = f;
+            if ((f == 32 || f == 64 || f == 128) && (want_pf ? bytes_pf(f) : bytes_for(f)) <= 200 * 1024) { S = f; pf = want_pf; }
         }
         {   // exactness bound of the multiply-high division in the transposes
             const uint64_t wmax = std::max<uint64_t>(std::max(prog.n_vars, prog.n_expr), std::max(prog.m, prog.jnnz));
             if (S != 0 && wmax * wmax * (uint64_t)S >= (1ull << 32)) S = 0;
         }
         if (S != 0) {
-            const size_t smem = bytes_for(S);
             static const int threads = [] {  // CTA size of the tile-staged kernel (A/B knob)
                 const char* e = std::getenv("FK_EVAL_THREADS");
                 return (e && std::atoi(e) == 128) ? 128 : 256;
             }();
+            if (threads != 256) pf = false;  // (the prefetching variant exists for 256-thread CTAs)
+            const size_t smem = pf ? bytes_pf(S) : bytes_for(S);
             const int ctas_per_sm = (int)std::min<size_t>(16, (226 * 1024) / (smem + 1024));
             const uint32_t tiles = (n_sketches + S - 1) / S;
             const uint32_t grid = std::min<uint32_t>(tiles, 148u * (uint32_t)ctas_per_sm);
             cudaError_t e = cudaSuccess;
-#define FK_EVAL_TILED_T(SV, JV, TH)                                                                                        \
+#define FK_EVAL_TILED_T(SV, JV, TH, PF)                                                                                    \
     do {                                                                                                               \
-        e = cudaFuncSetAttribute(fk_batch_eval_tiled_kernel<SV, JV, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        e = cudaFuncSetAttribute(fk_batch_eval_tiled_kernel<SV, JV, TH, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e == cudaSuccess)                                                                                          \
-            fk_batch_eval_tiled_kernel<SV, JV, TH><<<grid, TH, smem, s>>>(prog, n_sketches, vars, params, out_r, out_j); \
+            fk_batch_eval_tiled_kernel<SV, JV, TH, PF><<<grid, TH, smem, s>>>(prog, n_sketches, vars, params, out_r, out_j); \
     } while (0)
-#define FK_EVAL_TILED(SV, JV)                          \
-    do {                                               \
-        if (threads == 256) FK_EVAL_TILED_T(SV, JV, 256); \
-        else FK_EVAL_TILED_T(SV, JV, 128);             \
+#define FK_EVAL_TILED(SV, JV)                                   \
+    do {                                                        \
+        if (pf) FK_EVAL_TILED_T(SV, JV, 256, true);             \
+        else if (threads == 256) FK_EVAL_TILED_T(SV, JV, 256, false); \
+        else FK_EVAL_TILED_T(SV, JV, 128, false);               \
     } while (0)
             if (S == 128) { if (mode == 0) FK_EVAL_TILED(128, true); else FK_EVAL_TILED(128, false); }
             else if (S == 64) { if (mode == 0) FK_EVAL_TILED(64, true); else FK_EVAL_TILED(64, false); }
