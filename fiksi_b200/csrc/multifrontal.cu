@@ -560,7 +560,8 @@ mf_diag_kernel(MfDev D, const uint4* __restrict__ tasks) {
 // one warp (lanes 4r..4r+3): per micro-panel every thread solves its row's 8 entries in registers
 // (redundantly x4), then the four share the rank-8 update of the rest of the row; __syncwarp only.
 constexpr int kColThreads = 256;
-constexpr int kYsLd = TB + 4;  // row stride of the substitution tile: lanes (row, quarter) hit distinct banks
+constexpr int kYsLd = TB + 1;  // row stride of the substitution tile: odd, so lanes = rows hit distinct banks (with TB + 4, the stride
+                               // of the four-threads-per-row mapping this tile used to have, a column access by 32 rows was an 8-way conflict)
 constexpr int kLtLd = TB + 2;  // row stride of the TRANSPOSED unit-lower tile: even (16-byte aligned 8-column strips), and the four
                                // rows k, k+1, k+2, k+3 the quarters of a row read together start 4 banks apart
 // Blocked forward substitution of the rows in Cs ([TB][kYsLd], zero padded) against the unit-lower tile, held transposed in
@@ -857,6 +858,20 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
                 v[u] = (k0 < nc && ii < nc && j < nc && j <= ii) ? ld_relaxed(Lkk + (size_t)j * f + ii) : 0.0;
             }
         };
+        // A strip's columns of THIS tile are final once its y is in Cs: stored and published by all threads (two values each,
+        // lanes = consecutive rows), so the tiles to the right consume them chunk by chunk while the substitution goes on.
+        auto publish = [&](uint32_t k0) {
+            const uint32_t r = tid & 63u;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t c = k0 + 2u * (tid >> 6) + (uint32_t)u;
+                if (r < nrA && c < nc) {
+                    const double out = Cs[r * kYsLd + c] * invd[c];
+                    T[(size_t)c * f + r] = out;
+                    st_relaxed(Tp + (size_t)c * f + r, out);
+                }
+            }
+        };
         issue(0);
         for (uint32_t k0 = 0, st = 0; k0 < nc; k0 += MB, st++) {
             (void)st;
@@ -873,6 +888,7 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
             }
             __syncthreads();  // the strip of Ls (and, the first time, the zero fill; later, the previous strip's y) is in place
             issue(k0 + MB);   // (after the barrier: a barrier waits for the loads issued before it)
+            if (k0) publish(k0 - MB);  // the previous strip's columns of this tile, by all 256 threads (its y is behind the barrier)
             FK_PSTAMP(st, 2);
             col_strip_partial(Cs, Ls, Ps, k0);
             __syncthreads();
@@ -880,18 +896,10 @@ mf_flow_kernel(MfDev D, const uint4* __restrict__ tasks, double* __restrict__ pu
                 double y[MB];
                 col_strip_finish(Cs, Ls, Ps, k0, tid, y);
                 FK_PSTAMP(st, 3);
-                if (tid < nrA) {  // this tile's columns of the strip are final: stored and published at once
-#pragma unroll
-                    for (int c = 0; c < MB; c++) {
-                        if (k0 + c < nc) {
-                            const double out = y[c] * invd[k0 + c];
-                            T[(size_t)(k0 + c) * f + tid] = out;
-                            st_relaxed(Tp + (size_t)(k0 + c) * f + tid, out);
-                        }
-                    }
-                }
             }
         }
+        __syncthreads();
+        publish(((nc - 1) / MB) * MB);
     }
     FK_FSTAMP(3);
 }
