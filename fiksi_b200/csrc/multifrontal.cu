@@ -92,6 +92,111 @@ mf_small_factor_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint
     }
 }
 
+// ---- mid-size fronts: one CTA per supernode, the whole front in shared memory -----------------------------
+// The first levels above the small subtrees hold thousands of supernodes with fronts of 33..72 rows and 5..14 pivot
+// columns (400x250 lattice: 3,277 / 1,630 supernodes with fronts <= 48 / 72).  The tile kernels spend five
+// launches and a 64x64-tile machinery per level on them (0.39 ms for 0.13 GFLOP); here one CTA assembles the front
+// (children in ascending order, distinct targets within a child: no atomics, fixed summation order), eliminates its
+// pivot columns right-looking (rows across warps, columns across lanes, one barrier per column: scaling column k
+// touches nothing the update with column k + 1 reads) and writes the panel and the update matrix back.
+constexpr int kMidFront = 72;  // (fronts up to 128 rows were tried: above ~72 rows the 64x64-tile kernels are faster, 245 us against 176 us on the third level of the lattice)
+constexpr int kMidThreads = 256;
+constexpr int kMidChildren = 64;  // children's descriptors staged per batch
+__global__ void __launch_bounds__(kMidThreads)
+mf_mid_factor_kernel(MfDev D, const uint32_t* __restrict__ list, uint32_t ld) {
+    extern __shared__ __align__(16) double Fm[];  // F[i][j], j <= i, row stride ld (odd)
+    const uint32_t s = __ldg(list + blockIdx.x);
+    const uint32_t f = __ldg(D.f + s), ns = __ldg(D.ns + s), r = f - ns;
+    double* P = D.pan + __ldg(D.pan_off + s);
+    double* U = D.upd + __ldg(D.upd_off + s);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t NW = kMidThreads / 32;
+    for (uint32_t j = warp; j < f; j += NW) {
+        if (j < ns) {
+            const double* col = P + (size_t)j * f;
+            for (uint32_t i = j + lane; i < f; i += 32) Fm[i * ld + j] = col[i];
+        } else {
+            for (uint32_t i = j + lane; i < f; i += 32) Fm[i * ld + j] = 0.0;
+        }
+    }
+    // children's descriptors first (one round trip for all of them instead of three dependent ones per child)
+    __shared__ uint32_t ch_rc[kMidChildren], ch_rel[kMidChildren];
+    __shared__ uint64_t ch_upd[kMidChildren];
+    const uint32_t cq0 = __ldg(D.child_ptr + s), nch = __ldg(D.child_ptr + s + 1) - cq0;
+    for (uint32_t base = 0; base < nch; base += kMidChildren) {
+        const uint32_t nb = min((uint32_t)kMidChildren, nch - base);
+        __syncthreads();  // (the front is loaded / the previous batch's descriptors are no longer read)
+        if (tid < nb) {
+            const uint32_t c = __ldg(D.child + cq0 + base + tid);
+            ch_rc[tid] = __ldg(D.f + c) - __ldg(D.ns + c);
+            ch_rel[tid] = __ldg(D.rel_off + c);
+            ch_upd[tid] = __ldg(D.upd_off + c);
+        }
+        __syncthreads();
+        for (uint32_t q = 0; q < nb; q++) {
+            const uint32_t rc = ch_rc[q];
+            const double* Uc = D.upd + ch_upd[q];
+            const uint32_t* relc = D.rel + ch_rel[q];
+            for (uint32_t b = warp; b < rc; b += NW) {
+                const uint32_t tb = __ldg(relc + b);
+                const double* src = Uc + (size_t)b * rc;
+                uint32_t a = b + lane;
+                for (; a + 32 < rc; a += 64) {  // two independent gather / add chains in flight
+                    const uint32_t t0 = __ldg(relc + a), t1 = __ldg(relc + a + 32);
+                    const double v0 = src[a], v1 = src[a + 32];
+                    const double f0 = Fm[t0 * ld + tb], f1 = Fm[t1 * ld + tb];
+                    Fm[t0 * ld + tb] = f0 + v0;
+                    Fm[t1 * ld + tb] = f1 + v1;
+                }
+                for (; a < rc; a += 32) Fm[__ldg(relc + a) * ld + tb] += src[a];
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t k = 0; k < ns; k++) {
+        const double d = Fm[k * ld + k];
+        if (tid == 0) flag_pivot(D.status, d);
+        const double inv = fast_rcp(d);
+        // four rows per warp and step: the column entry F[j][k] is read once for the four, and the four chains are independent
+        for (uint32_t i0 = k + 1 + 4 * warp; i0 < f; i0 += 4 * NW) {
+            double li[4];
+            double* rowp[4];
+            uint32_t last[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = min(i0 + (uint32_t)u, f - 1);
+                rowp[u] = Fm + i * ld;
+                li[u] = rowp[u][k] * inv;
+                last[u] = i0 + (uint32_t)u < f ? i : 0u;  // (0: the clamped duplicate of the last row updates nothing)
+            }
+            const uint32_t jmax = min(i0 + 3u, f - 1);
+            for (uint32_t j = k + 1 + lane; j <= jmax; j += 32) {
+                const double fjk = Fm[j * ld + k];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = rowp[u][j];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = fma(-li[u], fjk, v[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (j <= last[u]) rowp[u][j] = v[u];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = k + 1 + tid; i < f; i += kMidThreads) Fm[i * ld + k] *= inv;
+    }
+    __syncthreads();
+    for (uint32_t j = warp; j < f; j += NW) {
+        if (j < ns) {
+            double* col = P + (size_t)j * f;
+            for (uint32_t i = j + lane; i < f; i += 32) col[i] = Fm[i * ld + j];
+        } else {
+            double* col = U + (size_t)(j - ns) * r - ns;
+            for (uint32_t i = j + lane; i < f; i += 32) col[i] = Fm[i * ld + j];
+        }
+    }
+}
+
 // ---- big path -----------------------------------------------------------------------------------------
 // Assembly of one block of front columns [lo, hi) of supernode s: zero the block's part of U_s,
 // then add the children's update matrices in ascending child order.  Blocks of one front have
@@ -1875,6 +1980,25 @@ cudaError_t Multifrontal::build_symbolic(const Topology& t, std::string* err) {
             for (uint32_t r0 = 0; r0 < ns[s]; r0 += TB) push_chain(s, r0, std::min<uint32_t>(TB, ns[s] - r0));
         inv_count_ = (uint32_t)(chain_tasks_.size() / 4) - inv_first_;
     }
+    {   // mid-size levels (see mf_mid_factor_kernel)
+        static const bool no_mid = std::getenv("FK_NO_MID") != nullptr;  // debug / A-B knob
+        mid_.assign(nlevels, MidLevel());
+        mid_list_.clear();
+        for (uint32_t l = 0; l < nlevels && !no_mid; l++) {
+            const std::vector<uint32_t>& L = by_level[l];
+            uint32_t fmax = 0;
+            for (uint32_t s : L) fmax = std::max(fmax, f[s]);
+            if (L.empty() || fmax > (uint32_t)kMidFront) continue;
+            chain_[l].flow_count = 0;  // (a mid-size level is never a dataflow level: the same kernel with FK_NO_FLOW and without)
+            mid_[l].first = (uint32_t)mid_list_.size();
+            mid_[l].count = (uint32_t)L.size();
+            mid_[l].ld = fmax | 1u;
+            // heavier fronts first: the last wave of the launch is the light one
+            std::vector<uint32_t> order(L);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (uint64_t)f[a] * f[a] * ns[a] > (uint64_t)f[b] * f[b] * ns[b]; });
+            mid_list_.insert(mid_list_.end(), order.begin(), order.end());
+        }
+    }
     n_chain_flags_ = winv_blocks;
     lap("chain task lists");
     factor_launches_ = factor_seq_.size() + (nsub ? 1 : 0);
@@ -1949,6 +2073,8 @@ cudaError_t Multifrontal::init(const Topology& t, cudaStream_t stream, std::stri
         }
     }
     MF_CU(cudaFuncSetAttribute(mf_small_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallFactorSmem));
+    MF_CU(upload_vec(mid_list_, &d_mid_list_, owned_));
+    MF_CU(cudaFuncSetAttribute(mf_mid_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(kMidFront | 1) * (kMidFront | 1) * sizeof(double))));
     MF_CU(cudaFuncSetAttribute(mf_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmem));
     MF_CU(cudaFuncSetAttribute(mf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
     MF_CU(cudaFuncSetAttribute(mf_small_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSolveSmem));
@@ -2002,6 +2128,16 @@ cudaError_t Multifrontal::enqueue_factor(cudaStream_t st) {
     const uint32_t nlv = (uint32_t)level_seq_ptr_.size() - 1;
     for (uint32_t lv = 0; lv < nlv; lv++) {
         const bool flow = d_pan_pub_ && chain_[lv].flow_count;
+        const bool mid = !flow && lv < mid_.size() && mid_[lv].count;
+        if (mid) {  // the level's assembly / diag / panel / update launches are replaced by one launch: a CTA per front
+            seq_no++;
+            cur_count = mid_[lv].count;
+            const uint32_t ld = mid_[lv].ld;
+            timed(1, [&] {
+                mf_mid_factor_kernel<<<mid_[lv].count, kMidThreads, (size_t)ld * ld * sizeof(double), st>>>(dev_, d_mid_list_ + mid_[lv].first, ld);
+            });
+            continue;
+        }
         for (uint32_t qi = level_seq_ptr_[lv]; qi < level_seq_ptr_[lv + 1]; qi++) {
             const Launch& l = factor_seq_[qi];
             if (flow) continue;  // the level's assembly / diag / panel / update launches are replaced below

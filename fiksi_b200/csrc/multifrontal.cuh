@@ -122,6 +122,11 @@ private:
     double* d_pan_pub_ = nullptr;
     uint32_t* d_tickets_ = nullptr;  // task tickets of the polling launches (see take_ticket)
     uint32_t n_tickets_ = 0;
+    // levels whose fronts are all small (<= 72 rows): one launch of mf_mid_factor_kernel per level, a CTA per front
+    struct MidLevel { uint32_t first = 0, count = 0, ld = 0; };
+    std::vector<MidLevel> mid_;
+    std::vector<uint32_t> mid_list_;
+    const uint32_t* d_mid_list_ = nullptr;
     std::vector<uint32_t> flow_asm_ptr_, flow_asm_;  // per dataflow tile: extend-add ranges of its children (uint4 entries)
     const uint32_t* d_flow_asm_ptr_ = nullptr;
     const uint4* d_flow_asm_ = nullptr;
