@@ -990,6 +990,14 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         const int v = e ? std::atoi(e) : 0;
         return (uint32_t)(v >= 1 && v <= (int)DevicePipeline::kStreams ? v : (int)DevicePipeline::kStreams);
     }();
+    // FK_E2E_TRACE=1 (debug): CUDA-event timeline of the chunks of one call to stderr (upload done / kernel done / download done)
+    static const bool trace = std::getenv("FK_E2E_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t_start = nullptr;
+    if (trace) {
+        cudaEventCreate(&t_start);
+        cudaEventRecord(t_start, pl->streams[0]);
+    }
     uint32_t s = 0;
     for (uint32_t at = 0; at < n && rc == FK_OK; at += chunk, s = (s + 1) % use_streams) {
         const uint32_t cnt = std::min(chunk, n - at);
@@ -1003,6 +1011,7 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
             if (shared) CU(cudaMemcpyAsync(p->d_raw_param, raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, st));
             else CU(cudaMemcpyAsync(p->d_raw_param, raw_param + (size_t)at * t.n_expr, sizeof(double) * (size_t)cnt * t.n_expr, cudaMemcpyHostToDevice, st));
         }
+        if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); tev.push_back(ev); }
         int e;
         if (fused) {  // the sketch-per-thread kernel scales, perturbs and writes back itself (SkRaw)
             fk::SkRaw raw{};
@@ -1019,12 +1028,25 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
             p->launches += 3;
         }
         if (e != 0) return cuda_fail((cudaError_t)e, "launch fk_batch_system_solve kernels");
+        if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); tev.push_back(ev); }
         if (t.n_free) CU(cudaMemcpyAsync(free_out + (size_t)at * t.n_free, p->d_out, sizeof(double) * (size_t)cnt * t.n_free, cudaMemcpyDeviceToHost, st));
         if (scales_out) CU(cudaMemcpyAsync(scales_out + at, p->d_scales, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
         if (reports) CU(cudaMemcpyAsync(reports + at, p->d_rep, sizeof(fk_report) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); tev.push_back(ev); }
     }
     for (uint32_t k = 0; k < kStreams; k++)
         if (pl->streams[k]) CU(cudaStreamSynchronize(pl->streams[k]));
+    if (trace) {
+        for (size_t c = 0; c + 2 < tev.size() + 0 && c < tev.size(); c += 3) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, t_start, tev[c]);
+            cudaEventElapsedTime(&b, t_start, tev[c + 1]);
+            cudaEventElapsedTime(&d, t_start, tev[c + 2]);
+            fprintf(stderr, "[e2e trace] chunk %2zu: upload done %7.1f us, kernel done %7.1f us, download done %7.1f us\n", c / 3, a * 1e3f, b * 1e3f, d * 1e3f);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+        cudaEventDestroy(t_start);
+    }
     return rc;
 }
 

@@ -600,7 +600,8 @@ fk_batch_eval_tiled_kernel(const DevProgram P, uint32_t n_sketches, const double
         __syncthreads();
         transpose_out(sr, out_r + (size_t)first * m, m, count * m);
         if (WITH_JACOBIAN) transpose_out(sj, out_j + (size_t)first * jn, jn, count * jn);
-        __syncthreads();
+        // (no barrier here: the next tile's evaluation only starts behind the barrier that follows its inputs, which every
+        // thread reaches after these stores; the inputs read by this tile's evaluation were released by the barrier above)
     }
 }
 
