@@ -125,7 +125,7 @@ print(int(rep["exit_reason"]), int(rep["factorizations"]), int(rep["trace_hash"]
 
 def test_dataflow_and_chained_schedules_match_the_launch_per_step_schedule(tmp_path):
     """The levels near the root are factorised by the tile dataflow kernel and solved by the chained multi-CTA
-    kernels (csrc/multifrontal.cu).  Against the launch-per-step schedule (FK_NO_FLOW / FK_NO_CHAIN; the knobs are
+    kernels, small fronts by one CTA each (csrc/multifrontal.cu).  Against the launch-per-step schedule (FK_NO_FLOW / FK_NO_CHAIN / FK_NO_MID; the knobs are
     read once per process, hence the subprocesses): the dataflow factorisation keeps every summation order, so the
     LM solve is bit-identical; the chained solves use the inverse of the 64x64 pivot triangles, so the coordinates
     agree to rounding."""
@@ -133,7 +133,7 @@ def test_dataflow_and_chained_schedules_match_the_launch_per_step_schedule(tmp_p
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for name, env in (("default", {}), ("no_flow", {"FK_NO_FLOW": "1"}), ("no_chain", {"FK_NO_CHAIN": "1"})):
+    for name, env in (("default", {}), ("no_flow", {"FK_NO_FLOW": "1"}), ("no_chain", {"FK_NO_CHAIN": "1"}), ("no_mid", {"FK_NO_MID": "1"})):
         path = str(tmp_path / (name + ".npy"))
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, "-c", _SCHEDULE_SCRIPT % root, path], env=e, capture_output=True, text=True, timeout=600)
@@ -143,6 +143,10 @@ def test_dataflow_and_chained_schedules_match_the_launch_per_step_schedule(tmp_p
     assert outs["no_flow"][0] == outs["default"][0] and np.array_equal(outs["no_flow"][1], outs["default"][1])
     assert outs["no_chain"][0].split()[:3] == outs["default"][0].split()[:3]
     assert _rel(outs["no_chain"][1], outs["default"][1]) <= 1e-11
+    # fronts of at most 72 rows through the 64x64-tile kernels instead of the one-CTA-per-front kernel: other summation
+    # orders, same decisions, coordinates to rounding
+    assert outs["no_mid"][0].split()[:3] == outs["default"][0].split()[:3]
+    assert _rel(outs["no_mid"][1], outs["default"][1]) <= 1e-11
 
 
 @pytest.mark.parametrize("seed,n_pts,extra", [(1, 150, 40), (2, 400, 150), (3, 700, 0)])
