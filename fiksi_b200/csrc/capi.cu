@@ -823,12 +823,22 @@ static int small_enqueue(fk_topology* topo, int device, uint32_t lo, uint32_t hi
     }
     std::memcpy(pl->small_h, vars + (size_t)lo * t.n_vars, in_v);
     if (in_p) std::memcpy(pl->small_h + in_v, param + (size_t)lo * t.n_expr, in_p);
-    if ((e = cudaMemcpyAsync(pl->small_d, pl->small_h, in_v + in_p, cudaMemcpyHostToDevice, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
-    const int le = launch_optimizer(*prog, *full, optimizer, total, (const double*)pl->small_d, (const double*)(pl->small_d + in_v),
-                                    (double*)(pl->small_d + rq.in_al), (fk_report*)(pl->small_d + rq.in_al + rq.out_x), pl->small_stream);
+    // A few kilobytes: the kernel reads its inputs from, and writes its results to, the pinned block itself (pinned host
+    // memory is mapped into the device's address space under unified addressing; the kernel touches every input and output
+    // once) -- two DMA set-ups less on a path that is all latency.  FK_NO_ZERO_COPY=1 keeps the two copies (A/B knob).
+    static const bool no_zero_copy = std::getenv("FK_NO_ZERO_COPY") != nullptr;
+    static const bool can_map = [] {
+        int dev = 0, ok = 0;
+        return cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&ok, cudaDevAttrCanUseHostPointerForRegisteredMem, dev) == cudaSuccess && ok != 0;
+    }();
+    const bool zero_copy = !no_zero_copy && can_map && rq.in_al + rq.out_x + rq.out_r <= 8 * 1024;
+    unsigned char* base = zero_copy ? pl->small_h : pl->small_d;
+    if (!zero_copy && (e = cudaMemcpyAsync(pl->small_d, pl->small_h, in_v + in_p, cudaMemcpyHostToDevice, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+    const int le = launch_optimizer(*prog, *full, optimizer, total, (const double*)base, (const double*)(base + in_v),
+                                    (double*)(base + rq.in_al), (fk_report*)(base + rq.in_al + rq.out_x), pl->small_stream);
     if (le == (int)cudaErrorInvalidConfiguration && optimizer == 1) { fail(FK_ERR_TOO_LARGE, "the L-BFGS state of one sketch does not fit the tile path"); return give_up(FK_ERR_TOO_LARGE); }
     if (le != 0) return bad((cudaError_t)le, "launch batched solve kernel");
-    if ((e = cudaMemcpyAsync(pl->small_h + rq.in_al, pl->small_d + rq.in_al, rq.out_x + rq.out_r, cudaMemcpyDeviceToHost, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
+    if (!zero_copy && (e = cudaMemcpyAsync(pl->small_h + rq.in_al, pl->small_d + rq.in_al, rq.out_x + rq.out_r, cudaMemcpyDeviceToHost, pl->small_stream)) != cudaSuccess) return bad(e, "cudaMemcpyAsync");
     return FK_OK;
 }
 static int small_finish(const fk::Topology& t, uint32_t lo, SmallRequest& rq, double* free_out, fk_report* reports, std::string* err) {
