@@ -71,12 +71,23 @@ mf_small_factor_kernel(MfDev D, const uint32_t* __restrict__ sub_ptr, const uint
         for (uint32_t k = 0; k < ns; k++) {
             const double d = F[k * kSmallLd + k];
             if (lane == 0) flag_pivot(D.status, d);
-            const double inv = 1.0 / d;
+            const double inv = fast_rcp(d);
             double li = 0.0;
             if (i > k && i < f) {
                 li = F[i * kSmallLd + k] * inv;
-                for (uint32_t j = k + 1; j <= i; j++)
-                    F[i * kSmallLd + j] = fma(-li, F[j * kSmallLd + k], F[i * kSmallLd + j]);
+                double* row = F + i * kSmallLd;
+                uint32_t j = k + 1;
+                for (; j + 3 <= i; j += 4) {  // four entries per step, loads before stores (independent chains in flight)
+                    double c[4], v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        c[u] = F[(j + u) * kSmallLd + k];
+                        v[u] = row[j + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) row[j + u] = fma(-li, c[u], v[u]);
+                }
+                for (; j <= i; j++) row[j] = fma(-li, F[j * kSmallLd + k], row[j]);
             }
             __syncwarp();
             if (i > k && i < f) F[i * kSmallLd + k] = li;
