@@ -211,3 +211,81 @@ def test_pose_rows_in_the_batched_kernels():
             assert np.array_equal(r[key], rt[key]), (kernel, key)
         assert np.max(np.abs(x - xt)) <= 1e-9 * np.max(np.abs(xt))
     assert np.mean(rt["ssr"] < 1e-8) >= 0.99
+
+
+def _random_system(S, rng):
+    """A random small system of points, lengths, lines and circles with distance / coincidence / angle / incidence /
+    tangency constraints (at most 8 primitives: the reference's search is exponential)."""
+    s = S()
+    n_pts = int(rng.integers(3, 8))
+    pts = [s.add_point(float(x), float(y)) for x, y in rng.uniform(-2.0, 2.0, size=(n_pts, 2))]
+    lines, circles = [], []
+    for _ in range(int(rng.integers(0, 3))):
+        a, b = rng.choice(n_pts, size=2, replace=False)
+        lines.append(s.add_line(pts[a], pts[b]))
+    if rng.random() < 0.5:
+        circles.append(s.add_circle(pts[int(rng.integers(n_pts))], s.add_length(float(rng.uniform(0.5, 1.5)))))
+    for _ in range(int(rng.integers(2, 2 * n_pts))):
+        k = int(rng.integers(0, 6))
+        a, b, c = (int(x) for x in rng.choice(n_pts, size=3, replace=False))
+        if k <= 1:
+            s.point_point_distance(pts[a], pts[b], float(rng.uniform(0.5, 2.0)))
+        elif k == 2:
+            s.point_point_point_angle(pts[a], pts[b], pts[c], float(rng.uniform(-2.0, 2.0)))
+        elif k == 3:
+            s.point_point_coincidence(pts[a], pts[b])
+        elif k == 4 and lines:
+            s.point_line_incidence(pts[a], lines[int(rng.integers(len(lines)))])
+        elif k == 5 and circles:
+            s.point_circle_incidence(pts[a], circles[0])
+        else:
+            s.point_point_distance(pts[a], pts[c], float(rng.uniform(0.5, 2.0)))
+    return s
+
+
+def test_plan_matches_oracle_on_random_systems(oracle):
+    """60 random small systems: the product's planner and the oracle's restatement either both report the reference's
+    panic or return the same plan, word for word."""
+    plans = panics = 0
+    for seed in range(60):
+        po = _plan(lambda _: _random_system(oracle.System, np.random.default_rng(seed)), None)
+        pp = _plan(lambda _: _random_system(fsys.System, np.random.default_rng(seed)), None)
+        assert pp == po, seed
+        if po == "panic":
+            panics += 1
+        else:
+            plans += 1
+            assert po[0] >= 1
+    assert plans >= 20
+
+
+@pytest.mark.gpu
+def test_recursive_assembly_solves_random_systems_like_the_oracle(oracle):
+    """The 60 random systems of the plan test through fk_system_solve_opts(decomposer = 2).  Every step that the oracle
+    solves (final sum of squares below the LM threshold) must match in trace, exit and coordinates; a system with
+    contradicting random constraints ends "stalled" after dozens of steps with lambda down to 1e-17, where the normal
+    equations of the product and the QR of the reference round differently: there the exits and the final sums
+    of squares must agree, the traces may not."""
+    exact = loose = 0
+    for seed in range(60):
+        if _plan(lambda _: _random_system(oracle.System, np.random.default_rng(seed)), None) == "panic":
+            continue
+        so = _random_system(oracle.System, np.random.default_rng(seed))
+        sp = _random_system(fsys.System, np.random.default_rng(seed))
+        so.solve_recursive_assembly()
+        sp.solve_recursive_assembly()
+        ro, rp = so.reports(), sp.reports()
+        assert len(ro) == len(rp), seed
+        consistent = all(a["ssr"] < 1e-8 for a in ro)
+        same = all(a["exit_reason"] == b["exit_reason"] and a["trace_hash"] == b["trace_hash"] for a, b in zip(ro, rp))
+        vo, vp = np.asarray(so.variables), np.asarray(sp.variables)
+        if same:
+            assert np.max(np.abs(vo - vp)) <= 1e-9 * max(np.max(np.abs(vo)), 1e-300), seed
+            exact += 1
+        else:
+            assert not consistent, seed
+            for a, b in zip(ro, rp):
+                assert a["exit_reason"] == b["exit_reason"], (seed, a, b)
+                assert abs(a["ssr"] - b["ssr"]) <= 1e-5 * max(a["ssr"], 1.0), (seed, a, b)  # (later steps start from slightly different points)
+            loose += 1
+    assert exact >= 40 and loose <= 4
