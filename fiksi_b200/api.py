@@ -147,6 +147,12 @@ class Topology:
         check(lib().fk_batch_solve_device(self._h, device, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr),
                                           C.c_void_p(out_ptr), C.c_void_p(rep_ptr)))
 
+    def batch_solve_lbfgs_into(self, device, n, vars_ptr, param_ptr, out_ptr, rep_ptr):
+        """fk_batch_solve_lbfgs on caller-owned (ideally pinned) host buffers given as addresses."""
+        check(lib().fk_batch_solve_lbfgs(self._h, device, n, C.cast(C.c_void_p(vars_ptr), C.POINTER(C.c_double)),
+                                         C.cast(C.c_void_p(param_ptr), C.POINTER(C.c_double)), C.cast(C.c_void_p(out_ptr), C.POINTER(C.c_double)),
+                                         C.cast(C.c_void_p(rep_ptr), C.POINTER(FkReport))))
+
     def lm_solve(self, vars_, param, free_values):
         """fk_topology_lm_solve: one system, symbolic analysis reused."""
         vars_ = np.ascontiguousarray(vars_, dtype=np.float64)
