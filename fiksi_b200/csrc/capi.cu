@@ -156,6 +156,7 @@ struct DevicePipeline {
     unsigned char* small_h = nullptr;
     unsigned char* small_d = nullptr;
     cudaStream_t small_stream = nullptr;
+    cudaEvent_t shared_param_ev = nullptr;  // fk_batch_system_solve with one parameter row for all sketches: its upload, once per call
     void release();
     ~DevicePipeline() { release(); }
 };
@@ -303,6 +304,8 @@ void DevicePipeline::release() {
     if (small_stream) cudaStreamDestroy(small_stream);
     small_h = small_d = nullptr;
     small_stream = nullptr;
+    if (shared_param_ev) cudaEventDestroy(shared_param_ev);
+    shared_param_ev = nullptr;
 }
 
 extern "C" {
@@ -1008,6 +1011,20 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         cudaEventCreate(&t_start);
         cudaEventRecord(t_start, pl->streams[0]);
     }
+    // One parameter row for all sketches: uploaded once per call, every stream waits for it (a 300-byte copy per chunk kept the
+    // H2D engine ~10 us per chunk, which the first chunks of a call -- the ones the device is waiting for -- paid in full).
+    const double* d_shared_param = nullptr;
+    if (shared && t.n_expr) {
+        if (!pl->shared_param_ev) CU(cudaEventCreateWithFlags(&pl->shared_param_ev, cudaEventDisableTiming));
+        d_shared_param = pl->plans[0]->d_raw_param;
+        CU(cudaMemcpyAsync(pl->plans[0]->d_raw_param, raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, pl->streams[0]));
+        CU(cudaEventRecord(pl->shared_param_ev, pl->streams[0]));
+        for (uint32_t k = 1; k < use_streams; k++) CU(cudaStreamWaitEvent(pl->streams[k], pl->shared_param_ev, 0));
+    }
+    // (Chunks that taper at both ends of a call -- a quarter and a half of the regular size first, halving down to 1,024 sketches at the
+    // end -- bring the first kernel forward from 65 to 24 us and change nothing: 1,108 against 1,092 us per call.  The last kernel ends
+    // ~1,070 us after the call started either way; the chunked kernels together take ~1,040 us where one launch over the resident
+    // batch takes 905.)
     uint32_t s = 0;
     for (uint32_t at = 0; at < n && rc == FK_OK; at += chunk, s = (s + 1) % use_streams) {
         const uint32_t cnt = std::min(chunk, n - at);
@@ -1017,22 +1034,21 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         CU(cudaStreamSynchronize(st));  // the plan's buffers are reused only after its previous chunk has drained
         p->n = cnt;
         if (t.n_vars) CU(cudaMemcpyAsync(p->d_raw_vars, raw_vars + (size_t)at * t.n_vars, sizeof(double) * (size_t)cnt * t.n_vars, cudaMemcpyHostToDevice, st));
-        if (t.n_expr) {
-            if (shared) CU(cudaMemcpyAsync(p->d_raw_param, raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, st));
-            else CU(cudaMemcpyAsync(p->d_raw_param, raw_param + (size_t)at * t.n_expr, sizeof(double) * (size_t)cnt * t.n_expr, cudaMemcpyHostToDevice, st));
-        }
+        if (t.n_expr && !shared)
+            CU(cudaMemcpyAsync(p->d_raw_param, raw_param + (size_t)at * t.n_expr, sizeof(double) * (size_t)cnt * t.n_expr, cudaMemcpyHostToDevice, st));
+        const double* d_param = shared ? d_shared_param : p->d_raw_param;
         if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); tev.push_back(ev); }
         int e;
         if (fused) {  // the sketch-per-thread kernel scales, perturbs and writes back itself (SkRaw)
             fk::SkRaw raw{};
-            raw.raw_vars = p->d_raw_vars; raw.raw_param = p->d_raw_param; raw.shared_param = shared ? 1u : 0u;
+            raw.raw_vars = p->d_raw_vars; raw.raw_param = d_param; raw.shared_param = shared ? 1u : 0u;
             raw.kinds = pt->d_kind; raw.free_draw = pt->d_free_draw; raw.fix_draw = pt->d_fix_draw; raw.draws = pt->d_draws;
             raw.scales = p->d_scales;
             e = fk::launch_batch_lm_sketch(*p->prog->sketch_prog, cnt, nullptr, nullptr, p->d_out, p->d_rep, st, &raw);
             p->launches += 1;
         } else {
             e = fk::launch_batch_prepare(cnt, t.n_vars, t.n_expr, pt->d_kind, shared, (uint32_t)pt->perturb_vars.size(), pt->d_perturb, pt->d_draws,
-                                         p->d_raw_vars, p->d_raw_param, p->d_vars, p->d_params, p->d_scales, st);
+                                         p->d_raw_vars, d_param, p->d_vars, p->d_params, p->d_scales, st);
             if (e == 0) e = fk::launch_batch_lm(*p->prog, cnt, p->d_vars, p->d_params, p->d_out, p->d_rep, st);
             if (e == 0) e = fk::launch_batch_unscale(cnt, t.n_free, p->d_scales, p->d_out, st);
             p->launches += 3;

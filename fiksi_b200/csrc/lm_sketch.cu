@@ -297,12 +297,35 @@ __device__ __forceinline__ double sk_stage_inputs(const SkProgram& P, const SkRa
             sum = sum + v * v;
         }
     }
-    for (uint32_t e = 0; e < P.n_expr; e++) {
-        const uint32_t kd = __ldg(R.kinds + e);
-        if (kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE) {
-            const double q = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
-            sum = sum + q * q;
-            cnt++;
+    // (The loops below work on four or eight items at a time with every load in front of the arithmetic: one warp per 32 sketches
+    // does this while nothing else runs in its CTA, and item-by-item each iteration was a chain of two or three dependent L1 / shared
+    // loads in front of its FP64 operations -- 21k cycles per CTA: one launch over 65,536 raw trusses took 980 us against 905 us on
+    // prepared inputs; 948 us now, fk_batch_system_solve 1,092 -> 1,067 us per call.  Operations and their order per sketch are unchanged.)
+    auto is_distance = [](uint32_t kd) { return kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE; };
+    {
+        uint32_t e = 0;
+        for (; e + 8 <= P.n_expr; e += 8) {
+            uint32_t kd[8];
+            double q[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                kd[u] = __ldg(R.kinds + e + u);
+                q[u] = R.shared_param ? __ldg(rp + e + u) : ldp(S, (P.n_vars + e + u) << 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (is_distance(kd[u])) {
+                    sum = sum + q[u] * q[u];
+                    cnt++;
+                }
+        }
+        for (; e < P.n_expr; e++) {
+            const uint32_t kd = __ldg(R.kinds + e);
+            if (is_distance(kd)) {
+                const double q = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
+                sum = sum + q * q;
+                cnt++;
+            }
         }
     }
     const double scale = sqrt(sum / (double)cnt);
@@ -310,14 +333,54 @@ __device__ __forceinline__ double sk_stage_inputs(const SkProgram& P, const SkRa
     auto perturbed = [&](double col, uint32_t j) {  // assemble/mod.rs:113-124
         return j == kNone ? col : col + (col * (1.0 / 8196.0) * __ldg(R.draws + 2 * j) + (1.0 / 65568.0) * __ldg(R.draws + 2 * j + 1));
     };
-    for (uint32_t c = 0; c < n; c++) stp(xp, c << 8, perturbed(ldp(S, tab[P.off_free + c] << 8) * recip, __ldg(R.free_draw + c)));
-    for (uint32_t i = 0; i < P.nfix; i++)
-        stp(base, (P.fx + i) << 8, perturbed(ldp(S, tab[P.off_fix + i] << 8) * recip, __ldg(R.fix_draw + i)));
-    for (uint32_t i = 0; i < P.npar; i++) {
-        const uint32_t e = tab[P.off_par + i];
-        const uint32_t kd = __ldg(R.kinds + e);
-        const double q = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
-        stp(base, (P.pr + i) << 8, (kd == FK_POINT_POINT_DISTANCE || kd == FK_POINT_LINE_DISTANCE) ? recip * q : q);
+    // count variables listed at tab[off_tab ..], their draw positions in draw_idx, into entries entry0.. of the region dst
+    auto stage_vars = [&](uint32_t count, uint32_t off_tab, const uint32_t* __restrict__ draw_idx, char* dst, uint32_t entry0) {
+        uint32_t c = 0;
+        for (; c + 4 <= count; c += 4) {
+            uint32_t j[4];
+            double col[4], d0[4], d1[4], out[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                j[u] = __ldg(draw_idx + c + u);
+                col[u] = ldp(S, tab[off_tab + c + u] << 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {  // (no draw: any valid element, unused)
+                d0[u] = __ldg(R.draws + (j[u] == kNone ? 0u : 2u * j[u]));
+                d1[u] = __ldg(R.draws + (j[u] == kNone ? 0u : 2u * j[u] + 1u));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double v = col[u] * recip;
+                out[u] = j[u] == kNone ? v : v + (v * (1.0 / 8196.0) * d0[u] + (1.0 / 65568.0) * d1[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) stp(dst, (entry0 + c + u) << 8, out[u]);
+        }
+        for (; c < count; c++) stp(dst, (entry0 + c) << 8, perturbed(ldp(S, tab[off_tab + c] << 8) * recip, __ldg(draw_idx + c)));
+    };
+    stage_vars(n, P.off_free, R.free_draw, xp, 0u);
+    stage_vars(P.nfix, P.off_fix, R.fix_draw, base, P.fx);
+    {
+        uint32_t i = 0;
+        for (; i + 4 <= P.npar; i += 4) {
+            uint32_t kd[4];
+            double q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t e = tab[P.off_par + i + u];
+                kd[u] = __ldg(R.kinds + e);
+                q[u] = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) stp(base, (P.pr + i + u) << 8, is_distance(kd[u]) ? recip * q[u] : q[u]);
+        }
+        for (; i < P.npar; i++) {
+            const uint32_t e = tab[P.off_par + i];
+            const uint32_t kd = __ldg(R.kinds + e);
+            const double q = R.shared_param ? __ldg(rp + e) : ldp(S, (P.n_vars + e) << 8);
+            stp(base, (P.pr + i) << 8, is_distance(kd) ? recip * q : q);
+        }
     }
     return scale;
 }
