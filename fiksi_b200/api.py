@@ -142,6 +142,20 @@ class Topology:
         check(lib().fk_batch_system_solve(self._h, device, n, C.c_void_p(raw_vars_ptr), C.c_void_p(raw_param_ptr), C.byref(o),
                                           C.c_void_p(out_ptr), None, C.c_void_p(rep_ptr)))
 
+    def batch_system_solve_begin(self, device, n, raw_vars_ptr, raw_param_ptr, out_ptr, rep_ptr, shared_param=False, perturb=True):
+        """fk_batch_system_solve_begin on caller-owned pinned host buffers: returns a token once the batch is enqueued;
+        batch_system_solve_wait(token) returns when its results are in the buffers.  Up to two batches in flight."""
+        o = FkPrepareOpts()
+        o.flags = (1 if shared_param else 0) | (2 if perturb else 0)
+        o.seed = 42
+        token = C.c_uint64(0)
+        check(lib().fk_batch_system_solve_begin(self._h, device, n, C.c_void_p(raw_vars_ptr), C.c_void_p(raw_param_ptr), C.byref(o),
+                                                C.c_void_p(out_ptr), None, C.c_void_p(rep_ptr), C.byref(token)))
+        return token.value
+
+    def batch_system_solve_wait(self, token, device=0):
+        check(lib().fk_batch_system_solve_wait(self._h, device, C.c_uint64(token)))
+
     def batch_solve_into(self, device, n, vars_ptr, param_ptr, out_ptr, rep_ptr):
         """fk_batch_solve_device on caller-owned (ideally pinned) host buffers given as addresses."""
         check(lib().fk_batch_solve_device(self._h, device, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr),

@@ -157,6 +157,12 @@ struct DevicePipeline {
     unsigned char* small_d = nullptr;
     cudaStream_t small_stream = nullptr;
     cudaEvent_t shared_param_ev = nullptr;  // fk_batch_system_solve with one parameter row for all sketches: its upload, once per call
+    // fk_batch_system_solve_begin / _wait: up to two calls in flight.  A call's token picks (by parity) the events recorded behind its
+    // last chunk on every stream and its copy of the shared parameter row.
+    uint64_t next_token = 1;
+    cudaEvent_t done_ev[2][kStreams] = {};
+    double* d_shared_param[2] = {nullptr, nullptr};
+    uint32_t shared_param_cap = 0;
     void release();
     ~DevicePipeline() { release(); }
 };
@@ -306,6 +312,15 @@ void DevicePipeline::release() {
     small_stream = nullptr;
     if (shared_param_ev) cudaEventDestroy(shared_param_ev);
     shared_param_ev = nullptr;
+    for (int a = 0; a < 2; a++) {
+        for (uint32_t k = 0; k < kStreams; k++) {
+            if (done_ev[a][k]) cudaEventDestroy(done_ev[a][k]);
+            done_ev[a][k] = nullptr;
+        }
+        if (d_shared_param[a]) cudaFree(d_shared_param[a]);
+        d_shared_param[a] = nullptr;
+    }
+    shared_param_cap = 0;
 }
 
 extern "C" {
@@ -957,10 +972,14 @@ static int prepare_tables_for(fk_topology* topo, int device, const fk_prepare_op
     return FK_OK;
 }
 
-int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, const double* raw_vars, const double* raw_param,
-                          const fk_prepare_opts* opts, double* free_out, double* scales_out, fk_report* reports) {
+// token == nullptr: the call returns when the results are in the caller's buffers.  Otherwise it returns once every chunk is
+// enqueued (the host still waits, chunk by chunk, for a free plan: at most kStreams chunks are in flight) and *token names the
+// call for fk_batch_system_solve_wait.
+static int system_solve_enqueue(const fk_topology* topo_c, int device, uint32_t n, const double* raw_vars, const double* raw_param,
+                                const fk_prepare_opts* opts, double* free_out, double* scales_out, fk_report* reports, uint64_t* token) {
     fk_topology* topo = const_cast<fk_topology*>(topo_c);
     if (!topo || !opts) return fail(FK_ERR_INVALID, "null argument");
+    if (token) *token = 0;
     if (n == 0) return FK_OK;
     const fk::Topology& t = topo->t;
     if (!raw_vars || !free_out || (!raw_param && t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
@@ -1013,11 +1032,21 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
     }
     // One parameter row for all sketches: uploaded once per call, every stream waits for it (a 300-byte copy per chunk kept the
     // H2D engine ~10 us per chunk, which the first chunks of a call -- the ones the device is waiting for -- paid in full).
+    const uint64_t my_token = pl->next_token++;
+    const int slot = (int)(my_token & 1u);
     const double* d_shared_param = nullptr;
     if (shared && t.n_expr) {
         if (!pl->shared_param_ev) CU(cudaEventCreateWithFlags(&pl->shared_param_ev, cudaEventDisableTiming));
-        d_shared_param = pl->plans[0]->d_raw_param;
-        CU(cudaMemcpyAsync(pl->plans[0]->d_raw_param, raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, pl->streams[0]));
+        if (pl->shared_param_cap < t.n_expr) {  // (two rows: the kernels of the previous call may still read theirs)
+            for (int a = 0; a < 2; a++) {
+                if (pl->d_shared_param[a]) CU(cudaFree(pl->d_shared_param[a]));
+                pl->d_shared_param[a] = nullptr;
+                CU(cudaMalloc(&pl->d_shared_param[a], sizeof(double) * t.n_expr));
+            }
+            pl->shared_param_cap = t.n_expr;
+        }
+        d_shared_param = pl->d_shared_param[slot];
+        CU(cudaMemcpyAsync(pl->d_shared_param[slot], raw_param, sizeof(double) * t.n_expr, cudaMemcpyHostToDevice, pl->streams[0]));
         CU(cudaEventRecord(pl->shared_param_ev, pl->streams[0]));
         for (uint32_t k = 1; k < use_streams; k++) CU(cudaStreamWaitEvent(pl->streams[k], pl->shared_param_ev, 0));
     }
@@ -1060,8 +1089,18 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         if (reports) CU(cudaMemcpyAsync(reports + at, p->d_rep, sizeof(fk_report) * (size_t)cnt, cudaMemcpyDeviceToHost, st));
         if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st); tev.push_back(ev); }
     }
+    if (token && !trace) {
+        for (uint32_t k = 0; k < kStreams; k++) {
+            if (!pl->streams[k]) continue;
+            if (!pl->done_ev[slot][k]) CU(cudaEventCreateWithFlags(&pl->done_ev[slot][k], cudaEventDisableTiming));
+            CU(cudaEventRecord(pl->done_ev[slot][k], pl->streams[k]));
+        }
+        *token = my_token;
+        return rc;
+    }
     for (uint32_t k = 0; k < kStreams; k++)
         if (pl->streams[k]) CU(cudaStreamSynchronize(pl->streams[k]));
+    if (token) *token = my_token;  // (tracing: the call has completed; waiting for it is a no-op)
     if (trace) {
         for (size_t c = 0; c + 2 < tev.size() + 0 && c < tev.size(); c += 3) {
             float a = 0, b = 0, d = 0;
@@ -1074,6 +1113,37 @@ int fk_batch_system_solve(const fk_topology* topo_c, int device, uint32_t n, con
         cudaEventDestroy(t_start);
     }
     return rc;
+}
+
+int fk_batch_system_solve(const fk_topology* topo, int device, uint32_t n, const double* raw_vars, const double* raw_param,
+                          const fk_prepare_opts* opts, double* free_out, double* scales_out, fk_report* reports) {
+    return system_solve_enqueue(topo, device, n, raw_vars, raw_param, opts, free_out, scales_out, reports, nullptr);
+}
+
+int fk_batch_system_solve_begin(const fk_topology* topo, int device, uint32_t n, const double* raw_vars, const double* raw_param,
+                                const fk_prepare_opts* opts, double* free_out, double* scales_out, fk_report* reports, uint64_t* token) {
+    if (!token) return fail(FK_ERR_INVALID, "null token");
+    return system_solve_enqueue(topo, device, n, raw_vars, raw_param, opts, free_out, scales_out, reports, token);
+}
+
+int fk_batch_system_solve_wait(const fk_topology* topo_c, int device, uint64_t token) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo) return fail(FK_ERR_INVALID, "null topology");
+    if (token == 0) return FK_OK;  // (an empty call)
+    const int ndev = usable_devices();
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    DevicePipeline* pl = topo->pipeline_for(device);
+    cudaEvent_t ev[DevicePipeline::kStreams];
+    {
+        std::lock_guard<std::mutex> lock(pl->mu);
+        if (token >= pl->next_token) return fail(FK_ERR_INVALID, "unknown token");
+        // (a token older than the last two calls: its slot now holds a later call's events, recorded behind this call's work on
+        // the same streams, so waiting for those covers it)
+        for (uint32_t k = 0; k < DevicePipeline::kStreams; k++) ev[k] = pl->done_ev[token & 1u][k];
+    }
+    for (uint32_t k = 0; k < DevicePipeline::kStreams; k++)
+        if (ev[k]) CU(cudaEventSynchronize(ev[k]));
+    return FK_OK;
 }
 
 int fk_batch_solve_device(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param,

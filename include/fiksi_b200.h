@@ -223,6 +223,16 @@ typedef struct {
 FK_API int fk_batch_system_solve(const fk_topology* topo, int device, uint32_t n, const double* raw_vars,
                                  const double* raw_param, const fk_prepare_opts* opts, double* free_out,
                                  double* scales_out, fk_report* reports);
+/* The same call in two halves, so that a caller streaming batch after batch keeps the device busy across calls (the first chunk's
+ * upload of the next batch and the last chunk's download of this one overlap the kernels of the other): _begin returns when every
+ * chunk of the batch is enqueued (it waits, chunk by chunk, for a free slot of the pipeline) and hands out a token; _wait returns
+ * when that batch's results are in its host buffers (kernel / copy errors surface there).  Up to two batches may be in flight per
+ * (topology, device): begin(A), begin(B), wait(A), begin(C), wait(B), ...  Buffers of a batch in flight must not be reused
+ * (inputs may be shared between batches, outputs not); pinned host memory is what makes the copies asynchronous. */
+FK_API int fk_batch_system_solve_begin(const fk_topology* topo, int device, uint32_t n, const double* raw_vars,
+                                       const double* raw_param, const fk_prepare_opts* opts, double* free_out,
+                                       double* scales_out, fk_report* reports, uint64_t* token);
+FK_API int fk_batch_system_solve_wait(const fk_topology* topo, int device, uint64_t token);
 
 /* Device-resident batch plan (one device; used by bench.py and by fk_batch_solve internally). */
 typedef struct fk_batch_plan fk_batch_plan;

@@ -172,6 +172,41 @@ def test_batch_system_solve_does_the_pre_and_post_processing_on_the_device(oracl
     assert np.array_equal(x0, w.write_back(w.raw_vars, x0_ref, s0)[:, w.free_vars])
 
 
+def test_batch_system_solve_in_two_halves_keeps_two_batches_in_flight():
+    """fk_batch_system_solve_begin / _wait: batches A, B, C, D streamed two deep (different inputs, different parameter
+    rows, own output buffers) return exactly what the one-call form returns for each of them."""
+    import torch
+    n = 20000
+    topo = None
+    batches = []
+    for k in range(4):
+        w = wl.truss(n, first=k * n)
+        if topo is None:
+            topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+        raw = np.ascontiguousarray(w.raw_vars * (1.0 + 0.25 * k))  # (another scale per batch: other values, same topology)
+        par = np.ascontiguousarray(w.raw_param[0] * (1.0 + 0.25 * k))
+        x_ref, sc_ref, rep_ref = topo.batch_system_solve(raw, par, perturb=True, shared_param=True)
+        nf = topo.info["n_free"]
+        bufs = (torch.from_numpy(raw).pin_memory(), torch.from_numpy(par).pin_memory(),
+                torch.zeros((n, nf), dtype=torch.float64).pin_memory(), torch.zeros((n, 5), dtype=torch.float64).pin_memory())
+        batches.append((bufs, x_ref, rep_ref))
+    tokens = []
+    for k, (bufs, _, _) in enumerate(batches):
+        tokens.append(topo.batch_system_solve_begin(0, n, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(),
+                                                    shared_param=True))
+        if k >= 1:
+            topo.batch_system_solve_wait(tokens[k - 1])
+    topo.batch_system_solve_wait(tokens[-1])
+    topo.batch_system_solve_wait(tokens[0])  # waiting again (or for an old token) is harmless
+    for bufs, x_ref, rep_ref in batches:
+        rep = bufs[3].numpy().view(fk.REPORT_DTYPE).reshape(n)
+        assert np.array_equal(bufs[2].numpy(), x_ref)
+        for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash", "lambda", "ssr"):
+            assert np.array_equal(rep[key], rep_ref[key]), key
+    with pytest.raises(fk.FiksiError):
+        topo.batch_system_solve_wait(tokens[-1] + 1000)
+
+
 def test_batch_system_solve_with_fixed_variables_and_a_custom_perturbation_list():
     name, w = [f for f in wl.stress_families(n_each=700) if f[0] == "two_components_a"][0]
     v, p, scale = w.prepare()
