@@ -161,6 +161,16 @@ class Topology:
         check(lib().fk_batch_solve_device(self._h, device, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr),
                                           C.c_void_p(out_ptr), C.c_void_p(rep_ptr)))
 
+    def batch_solve_begin(self, device, n, vars_ptr, param_ptr, out_ptr, rep_ptr):
+        """fk_batch_solve_device_begin on caller-owned pinned host buffers: token; batch_solve_wait(token) completes it."""
+        token = C.c_uint64(0)
+        check(lib().fk_batch_solve_device_begin(self._h, device, n, C.c_void_p(vars_ptr), C.c_void_p(param_ptr),
+                                                C.c_void_p(out_ptr), C.c_void_p(rep_ptr), C.byref(token)))
+        return token.value
+
+    def batch_solve_wait(self, token, device=0):
+        check(lib().fk_batch_solve_device_wait(self._h, device, C.c_uint64(token)))
+
     def batch_solve_lbfgs_into(self, device, n, vars_ptr, param_ptr, out_ptr, rep_ptr):
         """fk_batch_solve_lbfgs on caller-owned (ideally pinned) host buffers given as addresses."""
         check(lib().fk_batch_solve_lbfgs(self._h, device, n, C.cast(C.c_void_p(vars_ptr), C.POINTER(C.c_double)),

@@ -539,7 +539,7 @@ int fk_batch_solve_single_pass(const fk_topology* topo_c, uint32_t n, double* va
 
 // ---- L-BFGS on a uniform batch -------------------------------------------------------------------
 static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars, const double* param,
-                            double* free_out, fk_report* reports, std::string* err, int optimizer = 0);
+                            double* free_out, fk_report* reports, std::string* err, int optimizer = 0, uint64_t* token = nullptr);
 
 int fk_batch_solve_lbfgs(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param, double* free_out,
                          fk_report* reports) {
@@ -876,10 +876,12 @@ static int small_finish(const fk::Topology& t, uint32_t lo, SmallRequest& rq, do
     return rc;
 }
 
+// token != nullptr: return once every chunk is enqueued; *token names the call for fk_batch_solve_device_wait (0: already complete).
 static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t hi, const double* vars, const double* param,
-                            double* free_out, fk_report* reports, std::string* err, int optimizer) {
+                            double* free_out, fk_report* reports, std::string* err, int optimizer, uint64_t* token) {
     const fk::Topology& t = topo->t;
     const uint32_t total = hi - lo;
+    if (token) *token = 0;
     if (total == 0) return FK_OK;
     if (small_fits(t, total)) {
         SmallRequest rq;
@@ -911,18 +913,59 @@ static int run_device_range(fk_topology* topo, int device, uint32_t lo, uint32_t
     } else {
         if (pl->chunk < total) chunk = std::min(chunk, pl->chunk);  // (plans sized by an earlier, smaller request)
     }
+    // FK_E2E_TRACE=1 (debug): CUDA-event timeline of the chunks of one call to stderr (upload done / kernel done / download done)
+    static const bool trace = std::getenv("FK_E2E_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    cudaEvent_t t_start = nullptr;
+    auto stamp = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tev.push_back(ev);
+    };
+    if (trace) {
+        cudaEventCreate(&t_start);
+        cudaEventRecord(t_start, pl->streams[0]);
+    }
     uint32_t s = 0;
     for (uint32_t at = lo; at < hi && rc == FK_OK; at += chunk, s = (s + 1) % kStreams) {
         uint32_t cnt = std::min(chunk, hi - at);
         // a plan's buffers are reused only after its previous chunk has fully drained
         if (cudaStreamSynchronize(pl->streams[s]) != cudaSuccess) { rc = fail(FK_ERR_CUDA, "stream sync failed"); break; }
         rc = fk_batch_plan_upload(pl->plans[s], cnt, vars + (size_t)at * t.n_vars, param ? param + (size_t)at * t.n_expr : nullptr, pl->streams[s]);
+        stamp(pl->streams[s]);
         if (rc == FK_OK) rc = optimizer == 1 ? fk_batch_plan_run_lbfgs(pl->plans[s], pl->streams[s]) : fk_batch_plan_run(pl->plans[s], pl->streams[s]);
+        stamp(pl->streams[s]);
         if (rc == FK_OK) rc = fk_batch_plan_download(pl->plans[s], free_out + (size_t)at * t.n_free, reports ? reports + at : nullptr, pl->streams[s]);
+        stamp(pl->streams[s]);
+    }
+    if (token && !trace && rc == FK_OK) {
+        const uint64_t my_token = pl->next_token++;
+        const int slot = (int)(my_token & 1u);
+        for (uint32_t k = 0; k < kStreams; k++) {
+            if (!pl->streams[k]) continue;
+            if (!pl->done_ev[slot][k] && cudaEventCreateWithFlags(&pl->done_ev[slot][k], cudaEventDisableTiming) != cudaSuccess)
+                return fail(FK_ERR_CUDA, "cudaEventCreate failed");
+            if (cudaEventRecord(pl->done_ev[slot][k], pl->streams[k]) != cudaSuccess) return fail(FK_ERR_CUDA, "cudaEventRecord failed");
+        }
+        *token = my_token;
+        return FK_OK;
     }
     for (uint32_t k = 0; k < kStreams; k++)
         if (pl->streams[k] && cudaStreamSynchronize(pl->streams[k]) != cudaSuccess && rc == FK_OK)
             rc = cuda_fail(cudaGetLastError(), "batch kernel / copy failed");
+    if (trace) {
+        for (size_t c = 0; c + 2 < tev.size(); c += 3) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, t_start, tev[c]);
+            cudaEventElapsedTime(&b, t_start, tev[c + 1]);
+            cudaEventElapsedTime(&d, t_start, tev[c + 2]);
+            fprintf(stderr, "[e2e trace] chunk %2zu: upload done %7.1f us, kernel done %7.1f us, download done %7.1f us\n", c / 3, a * 1e3f, b * 1e3f, d * 1e3f);
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+        cudaEventDestroy(t_start);
+    }
     if (rc != FK_OK && err) *err = g_error;
     return rc;
 }
@@ -1157,6 +1200,21 @@ int fk_batch_solve_device(const fk_topology* topo_c, int device, uint32_t n, con
     if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
     return run_device_range(topo, device, 0, n, vars, param, free_out, reports, nullptr);
 }
+
+int fk_batch_solve_device_begin(const fk_topology* topo_c, int device, uint32_t n, const double* vars, const double* param,
+                                double* free_out, fk_report* reports, uint64_t* token) {
+    fk_topology* topo = const_cast<fk_topology*>(topo_c);
+    if (!topo || !token) return fail(FK_ERR_INVALID, "null topology / token");
+    *token = 0;
+    if (n == 0) return FK_OK;
+    if (!vars || !free_out || (!param && topo->t.n_expr)) return fail(FK_ERR_INVALID, "null buffer");
+    int ndev = usable_devices();
+    if (ndev == 0) return fail(FK_ERR_NO_DEVICE, "no CUDA device visible; fiksi_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(FK_ERR_INVALID, "device index out of range");
+    return run_device_range(topo, device, 0, n, vars, param, free_out, reports, nullptr, 0, token);
+}
+
+int fk_batch_solve_device_wait(const fk_topology* topo, int device, uint64_t token) { return fk_batch_system_solve_wait(topo, device, token); }
 
 int fk_batch_solve(const fk_topology* topo_c, uint32_t n, const double* vars, const double* param, double* free_out,
                    fk_report* reports, int n_gpus) {

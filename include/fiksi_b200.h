@@ -202,6 +202,11 @@ FK_API int fk_batch_solve(const fk_topology* topo, uint32_t n, const double* var
 /* Same on one explicit device (one process per GPU launches, e.g. under torchrun). */
 FK_API int fk_batch_solve_device(const fk_topology* topo, int device, uint32_t n, const double* vars,
                                  const double* param, double* free_out, fk_report* reports);
+/* The same call in two halves (see fk_batch_system_solve_begin / _wait: same token rules, the two kinds of call share the pipeline of a
+ * (topology, device) and may be mixed). */
+FK_API int fk_batch_solve_device_begin(const fk_topology* topo, int device, uint32_t n, const double* vars, const double* param,
+                                       double* free_out, fk_report* reports, uint64_t* token);
+FK_API int fk_batch_solve_device_wait(const fk_topology* topo, int device, uint64_t token);
 
 /* System::solve for a batch of single-component sketches that share one topology, pre- and post-processing
  * included (fiksi/src/assemble/mod.rs:32-44,58-79,113-124,161-166): per sketch the RMS scale over all variables

@@ -207,6 +207,34 @@ def test_batch_system_solve_in_two_halves_keeps_two_batches_in_flight():
         topo.batch_system_solve_wait(tokens[-1] + 1000)
 
 
+def test_batch_solve_device_in_two_halves():
+    """fk_batch_solve_device_begin / _wait on three different batches of the mixed CAD topology, two in flight."""
+    import torch
+    n = 30001
+    batches = []
+    topo = None
+    for k in range(3):
+        w = wl.cad_mix(n, first=k * n)
+        v, p, scale = w.prepare()
+        if topo is None:
+            topo = fk.Topology.from_arrays(w.n_vars, w.kind, w.idx, w.free_vars, w.rows)
+        x_ref, rep_ref = topo.batch_solve(v, p)
+        bufs = (torch.from_numpy(v).pin_memory(), torch.from_numpy(p).pin_memory(),
+                torch.zeros((n, topo.info["n_free"]), dtype=torch.float64).pin_memory(), torch.zeros((n, 5), dtype=torch.float64).pin_memory())
+        batches.append((bufs, x_ref, rep_ref))
+    tokens = []
+    for k, (bufs, _, _) in enumerate(batches):
+        tokens.append(topo.batch_solve_begin(0, n, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr()))
+        if k >= 1:
+            topo.batch_solve_wait(tokens[k - 1])
+    topo.batch_solve_wait(tokens[-1])
+    for bufs, x_ref, rep_ref in batches:
+        rep = bufs[3].numpy().view(fk.REPORT_DTYPE).reshape(n)
+        assert np.array_equal(bufs[2].numpy(), x_ref)
+        for key in ("exit_reason", "outer_iters", "factorizations", "accepted", "trace_hash", "lambda", "ssr"):
+            assert np.array_equal(rep[key], rep_ref[key]), key
+
+
 def test_batch_system_solve_with_fixed_variables_and_a_custom_perturbation_list():
     name, w = [f for f in wl.stress_families(n_each=700) if f[0] == "two_components_a"][0]
     v, p, scale = w.prepare()
