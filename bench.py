@@ -387,7 +387,7 @@ def main():
                             "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / avg_s / 1e9, "peak_gbs": peak,
                                     "frac": alg_bytes / avg_s / 1e9 / peak, "peak_source": peak_src,
                                     "note": "inputs + outputs once per sketch; not the limiter"},
-                            "profiles": "ncu --set full summaries of this kernel on this workload: profiles/r02b_lm_sketch_pair_kernel_truss_ncu_full_summary.csv (latest), profiles/r02_*lm_sketch*; launch list of this command: profiles/r02b_launches_bench_truss.csv",
+                            "profiles": "ncu --set full summaries of this kernel on this workload: profiles/r02b_lm_sketch_pair_kernel_truss_ncu_full_summary.csv (the kernel is unchanged since), its raw mode (the end-to-end calls): profiles/r02c_lm_sketch_pair_kernel_raw_mode_ncu_full_summary.csv; launch list of this command (--no-extras): profiles/r02c_launches_bench_truss.csv",
                             "note": "latency bound: 32 sketches are solved out of shared memory by one warp (or a leader / helper pair of warps) and "
                                     "only two such groups fit an SM for this topology; see DESIGN.md section 4 for the stall breakdown"}
         if not args.no_extras:
