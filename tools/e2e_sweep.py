@@ -16,8 +16,21 @@ hout = torch.empty((n, info["n_free"]), dtype=torch.float64).pin_memory()
 hrep = torch.empty((n, 5), dtype=torch.float64).pin_memory()
 def step():
     topo.batch_system_solve_into(0, n, hraw.data_ptr(), hrawp.data_ptr(), hout.data_ptr(), hrep.data_ptr(), shared_param=True)
+stream = os.environ.get("FK_SWEEP_STREAM") == "1"  # steps streamed two deep through the two halves of the call
+hout2, hrep2 = torch.empty_like(hout).pin_memory(), torch.empty_like(hrep).pin_memory()
+outs = ((hout, hrep), (hout2, hrep2))
+def begin(i):
+    return topo.batch_system_solve_begin(0, n, hraw.data_ptr(), hrawp.data_ptr(), outs[i & 1][0].data_ptr(), outs[i & 1][1].data_ptr(), shared_param=True)
 for _ in range(3): step()
 t0 = time.perf_counter()
-for _ in range(steps): step()
+if stream:
+    prev = begin(0)
+    for i in range(1, steps):
+        cur = begin(i)
+        topo.batch_system_solve_wait(prev)
+        prev = cur
+    topo.batch_system_solve_wait(prev)
+else:
+    for _ in range(steps): step()
 dt = time.perf_counter() - t0
-print(f"FK_E2E_CHUNKS={os.environ.get('FK_E2E_CHUNKS', '8 (default)')}: {n * steps / dt / 1e6:.2f} M sketches/s end to end, {dt / steps * 1e6:.0f} us per call")
+print(("streamed " if stream else "") + f"FK_E2E_CHUNKS={os.environ.get('FK_E2E_CHUNKS', '8 (default)')}: {n * steps / dt / 1e6:.2f} M sketches/s end to end, {dt / steps * 1e6:.0f} us per call")
